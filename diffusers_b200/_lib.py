@@ -1,0 +1,117 @@
+"""ctypes binding of libb200diff.so (the C-ABI declared in include/b200_diffusion.h).
+
+There is no fallback: if the shared library is missing or fails to initialise, every op raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libb200diff.so")
+
+DTYPE_BF16, DTYPE_FP16 = 0, 1
+ACT_NONE, ACT_SILU, ACT_GELU_ERF, ACT_GELU_TANH = 0, 1, 2, 3
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class ConvGemmArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p * 2), ("c", C.c_int32 * 2), ("ldx", C.c_int32 * 2),
+        ("batch", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("ksize", C.c_int32), ("stride", C.c_int32),
+        ("w", C.c_void_p), ("N", C.c_int32),
+        ("bias", C.c_void_p), ("act", C.c_int32), ("geglu", C.c_int32),
+        ("gate", C.c_void_p), ("rowvec", C.c_void_p), ("ld_gate", C.c_int32), ("ld_rowvec", C.c_int32),
+        ("rows_per_group", C.c_int32),
+        ("residual", C.c_void_p), ("ldr", C.c_int32),
+        ("y", C.c_void_p), ("ldy", C.c_int32),
+        ("dtype", C.c_int32), ("tile_n", C.c_int32),
+    ]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("sq", C.c_int32), ("sk", C.c_int32), ("head_dim", C.c_int32),
+        ("q_row_stride", C.c_int64), ("q_batch_stride", C.c_int64),
+        ("k_row_stride", C.c_int64), ("k_batch_stride", C.c_int64),
+        ("v_row_stride", C.c_int64), ("v_batch_stride", C.c_int64),
+        ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
+        ("scale", C.c_float), ("dtype", C.c_int32),
+    ]
+
+
+class GroupNormArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p * 2), ("c", C.c_int32 * 2), ("ldx", C.c_int32 * 2),
+        ("batch", C.c_int32), ("hw", C.c_int32), ("groups", C.c_int32), ("eps", C.c_float),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("act", C.c_int32),
+        ("y", C.c_void_p), ("ldy", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("dtype", C.c_int32),
+    ]
+
+
+class LayerNormArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("ldx", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32), ("eps", C.c_float),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("scale", C.c_void_p), ("shift", C.c_void_p), ("ld_mod", C.c_int32), ("rows_per_group", C.c_int32),
+        ("y", C.c_void_p), ("ldy", C.c_int32), ("dtype", C.c_int32),
+    ]
+
+
+class SmallLinearArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("ldx", C.c_int32), ("M", C.c_int32), ("K", C.c_int32),
+        ("w", C.c_void_p), ("N", C.c_int32), ("bias", C.c_void_p),
+        ("act_in", C.c_int32), ("act_out", C.c_int32),
+        ("addend", C.c_void_p), ("ld_add", C.c_int32),
+        ("y", C.c_void_p), ("ldy", C.c_int32), ("dtype", C.c_int32),
+    ]
+
+
+_lib = None
+_inited_devices = set()
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(
+                f"{LIB_PATH} not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU / PyTorch fallback for the sm_100a kernels)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.b200_last_error.restype = C.c_char_p
+        _lib.b200_conv_gemm_packed_k.restype = C.c_int64
+        _lib.b200_conv_gemm_packed_k.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        _lib.b200_conv_gemm_pick_tile_n.restype = C.c_int32
+        _lib.b200_conv_gemm_pick_tile_n.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().b200_last_error()
+        raise B200Error(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def init(device_index):
+    """b200_init once per device; raises if the device is not a B200 or the driver lacks TMA support."""
+    if device_index not in _inited_devices:
+        check(lib().b200_init(C.c_int(device_index)), "b200_init")
+        _inited_devices.add(device_index)
+
+
+def exported_symbols():
+    """Symbols the header promises (used by the CPU-side ABI test)."""
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "b200_diffusion.h")
+    import re
+    names = []
+    with open(hdr) as f:
+        for m in re.finditer(r"^\s*(?:const\s+char\*|int(?:32_t|64_t)?)\s+(b200_\w+)\s*\(", f.read(), re.M):
+            names.append(m.group(1))
+    return names

@@ -1,0 +1,536 @@
+// b200_conv_gemm: implicit-GEMM convolution / linear layer on tcgen05 tensor cores.
+//
+//   persistent CTAs (one per SM), 8 warps:
+//     warp 0      TMA producer   : per 64-wide K chunk, one 4-D box of NHWC pixels (the im2col
+//                                  row block, staged 128B-swizzled in shared memory; halo pixels
+//                                  are zero-filled by TMA out-of-bounds handling) + one 2-D box of
+//                                  packed weights
+//     warp 1      MMA issuer     : tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM,
+//                                  double-buffered across tiles
+//     warp 2      TMEM allocator
+//     warps 4..7  epilogue       : tcgen05.ld -> bias/act/gate/rowvec/residual (or GEGLU) -> 16 B stores
+//
+// A-operand tile = 128 output pixels arranged as a bw x bh rectangle (bw*bh = 128) so that one
+// TMA box per filter tap fetches exactly the shifted input pixels.  nn.Linear is the 1x1, H = 1
+// case (bw = 128, bh = 1).
+#include <string.h>
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace b200 {
+
+struct ConvGemmParams {
+  CUtensorMap a_map[8];  // [src][parity]; stride-1 convs only use parity 0
+  CUtensorMap w_map;
+  int batch, Ho, Wo;
+  int bw, bh, bw_shift;
+  int tiles_w, tiles_h, m_tiles, n_tiles, total_tiles;
+  int N;  // rows of w
+  int num_taps, nsrc;
+  int chunks[2];
+  int k_chunks;  // num_taps * (chunks[0] + chunks[1])
+  int8_t tap_map[9], tap_dh[9], tap_dw[9];
+  const void* bias;
+  const void* gate;
+  const void* rowvec;
+  const void* residual;
+  void* y;
+  int ld_gate, ld_rowvec, ldr, ldy, rows_per_group, act;
+  int vec_ok;  // y / residual / gate / rowvec / bias allow 16-byte accesses
+};
+
+template <int BN>
+struct ConvGemmCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TileCoord {
+  int img, h0, w0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int t, int BN) {
+  TileCoord c;
+  int n_blk = t / p.m_tiles;
+  int m = t - n_blk * p.m_tiles;
+  int per_img = p.tiles_w * p.tiles_h;
+  c.img = m / per_img;
+  int r = m - c.img * per_img;
+  int th = r / p.tiles_w;
+  int tw = r - th * p.tiles_w;
+  c.h0 = th * p.bh;
+  c.w0 = tw * p.bw;
+  c.n0 = n_blk * BN;
+  return c;
+}
+
+template <int BN, bool GEGLU, bool FP16>
+__global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using Cfg = ConvGemmCfg<BN>;
+  using H = Half16<FP16>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nsrc; ++s) prefetch_tensormap(&p.a_map[s * 4]);
+    prefetch_tensormap(&p.w_map);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        TileCoord tc = decode_tile(p, t, BN);
+        int kc = 0;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int mp = p.tap_map[tap];
+          const int cw = tc.w0 + p.tap_dw[tap];
+          const int ch = tc.h0 + p.tap_dh[tap];
+          for (int s = 0; s < p.nsrc; ++s) {
+            const CUtensorMap* am = &p.a_map[s * 4 + mp];
+            for (int cc = 0; cc < p.chunks[s]; ++cc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              tma_load_4d(sa, am, &full_bar[stage], cc * 64, cw, ch, tc.img);
+              tma_load_2d(sa + Cfg::A_BYTES, &p.w_map, &full_bar[stage], kc * 64, tc.n0);
+              ++kc;
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN, FP16, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t a_desc = make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(a_addr + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // +32 B per UMMA_K=16 step inside the 128 B swizzle atom -> +2 in the (addr>>4) field
+            umma_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int rh = row >> p.bw_shift;
+    const int rw = row & (p.bw - 1);
+    const typename H::T* bias = static_cast<const typename H::T*>(p.bias);
+    const typename H::T* gate = static_cast<const typename H::T*>(p.gate);
+    const typename H::T* rowvec = static_cast<const typename H::T*>(p.rowvec);
+    const typename H::T* residual = static_cast<const typename H::T*>(p.residual);
+    typename H::T* y = static_cast<typename H::T*>(p.y);
+    const int n_limit = GEGLU ? (p.N >> 1) : p.N;  // number of y columns
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      TileCoord tc = decode_tile(p, t, BN);
+      const int oh = tc.h0 + rh, ow = tc.w0 + rw;
+      const bool valid = (oh < p.Ho) && (ow < p.Wo);
+      const long long pix = (static_cast<long long>(tc.img) * p.Ho + oh) * p.Wo + ow;
+      const long long grp = (valid && (gate != nullptr || rowvec != nullptr)) ? (pix / p.rows_per_group) : 0;
+      const typename H::T* gate_row = gate ? gate + grp * p.ld_gate : nullptr;
+      const typename H::T* rv_row = rowvec ? rowvec + grp * p.ld_rowvec : nullptr;
+      const typename H::T* res_row = residual ? residual + pix * p.ldr : nullptr;
+      typename H::T* y_row = y + pix * p.ldy;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+
+      constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
+      const int ycol0 = GEGLU ? (tc.n0 >> 1) : tc.n0;
+#pragma unroll 1
+      for (int c = 0; c < OUT_COLS / 32; ++c) {
+        if (ycol0 + c * 32 >= n_limit) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(t_row + c * 32, v);
+        uint32_t g[32];
+        if (GEGLU) tmem_ld32(t_row + BN / 2 + c * 32, g);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          const int yc = ycol0 + c * 32 + j8 * 8;  // y column of f[0]
+          if (yc >= n_limit) break;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
+          const bool full8 = (yc + 8 <= n_limit) && p.vec_ok;
+          if (GEGLU) {
+            // packed rows: [n0, n0+BN/2) value, [n0+BN/2, n0+BN) gate
+            const int bcol = tc.n0 + c * 32 + j8 * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a = f[j], gg = __uint_as_float(g[j8 * 8 + j]);
+              if (bias) {
+                a += H::to_float(bias[bcol + j]);
+                gg += H::to_float(bias[bcol + BN / 2 + j]);
+              }
+              f[j] = a * gelu_erf_f(gg);
+            }
+          } else {
+            if (full8) {
+              if (bias) {
+                uint4 b = *reinterpret_cast<const uint4*>(bias + yc);
+                float2 t0 = H::unpack(b.x), t1 = H::unpack(b.y), t2 = H::unpack(b.z), t3 = H::unpack(b.w);
+                f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
+                f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
+              }
+              if (p.act != ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
+              }
+              if (gate_row) {
+                uint4 b = *reinterpret_cast<const uint4*>(gate_row + yc);
+                float2 t0 = H::unpack(b.x), t1 = H::unpack(b.y), t2 = H::unpack(b.z), t3 = H::unpack(b.w);
+                f[0] *= t0.x; f[1] *= t0.y; f[2] *= t1.x; f[3] *= t1.y;
+                f[4] *= t2.x; f[5] *= t2.y; f[6] *= t3.x; f[7] *= t3.y;
+              }
+              if (rv_row) {
+                uint4 b = *reinterpret_cast<const uint4*>(rv_row + yc);
+                float2 t0 = H::unpack(b.x), t1 = H::unpack(b.y), t2 = H::unpack(b.z), t3 = H::unpack(b.w);
+                f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
+                f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
+              }
+              if (res_row && valid) {
+                uint4 b = *reinterpret_cast<const uint4*>(res_row + yc);
+                float2 t0 = H::unpack(b.x), t1 = H::unpack(b.y), t2 = H::unpack(b.z), t3 = H::unpack(b.w);
+                f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
+                f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int n = yc + j;
+                if (n < n_limit) {
+                  float x = f[j];
+                  if (bias) x += H::to_float(bias[n]);
+                  x = apply_act(x, p.act);
+                  if (gate_row) x *= H::to_float(gate_row[n]);
+                  if (rv_row) x += H::to_float(rv_row[n]);
+                  if (res_row && valid) x += H::to_float(res_row[n]);
+                  f[j] = x;
+                }
+              }
+            }
+          }
+          if (valid) {
+            if (full8) {
+              uint4 o;
+              o.x = H::pack(f[0], f[1]);
+              o.y = H::pack(f[2], f[3]);
+              o.z = H::pack(f[4], f[5]);
+              o.w = H::pack(f[6], f[7]);
+              *reinterpret_cast<uint4*>(y_row + yc) = o;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (yc + j < n_limit) y_row[yc + j] = H::from_float(f[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef void (*ConvGemmKernel)(const ConvGemmParams);
+
+template <int BN, bool GEGLU, bool FP16>
+static int set_smem_attr() {
+  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, GEGLU, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ConvGemmCfg<BN>::SMEM_BYTES);
+  if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "conv_gemm smem attr BN=%d: %s", BN, cudaGetErrorString(e));
+  return 0;
+}
+
+int init_conv_gemm() {
+  int r = 0;
+#define B200_SET(BN)                                   \
+  if ((r = set_smem_attr<BN, false, false>())) return r; \
+  if ((r = set_smem_attr<BN, false, true>())) return r;
+  B200_SET(32) B200_SET(64) B200_SET(128) B200_SET(256)
+#undef B200_SET
+#define B200_SETG(BN)                                 \
+  if ((r = set_smem_attr<BN, true, false>())) return r; \
+  if ((r = set_smem_attr<BN, true, true>())) return r;
+  B200_SETG(64) B200_SETG(128) B200_SETG(256)
+#undef B200_SETG
+  return 0;
+}
+
+template <bool GEGLU, bool FP16>
+static int launch_bn(int bn, const ConvGemmParams& prm, int grid, cudaStream_t st) {
+  switch (bn) {
+    case 256:
+      conv_gemm_kernel<256, GEGLU, FP16><<<grid, 256, ConvGemmCfg<256>::SMEM_BYTES, st>>>(prm);
+      break;
+    case 128:
+      conv_gemm_kernel<128, GEGLU, FP16><<<grid, 256, ConvGemmCfg<128>::SMEM_BYTES, st>>>(prm);
+      break;
+    case 64:
+      conv_gemm_kernel<64, GEGLU, FP16><<<grid, 256, ConvGemmCfg<64>::SMEM_BYTES, st>>>(prm);
+      break;
+    case 32:
+      if (GEGLU) return set_error(B200_ERR_UNSUPPORTED, "geglu needs tile_n >= 64");
+      conv_gemm_kernel<32, false, FP16><<<grid, 256, ConvGemmCfg<32>::SMEM_BYTES, st>>>(prm);
+      break;
+    default:
+      return set_error(B200_ERR_INVALID, "conv_gemm: unsupported tile_n %d", bn);
+  }
+  return check_launch("conv_gemm_kernel");
+}
+
+static int pick_tile_n(long long M, int N, int geglu) {
+  if (geglu) {
+    // the packer interleaves value/gate rows per tile, so BN must divide N
+    for (int bn : {256, 128, 64})
+      if (N % bn == 0) return bn;
+    return 0;
+  }
+  const long long m_tiles = (M + 127) / 128;
+  const int sms = num_sms();
+  int best = 32;
+  double best_cost = 1e30;
+  for (int bn : {256, 128, 64, 32}) {
+    long long tiles = m_tiles * ((N + bn - 1) / bn);
+    long long waves = (tiles + sms - 1) / sms;
+    // per-k16 step: MMA issue ~ BN/2 cycles, operand smem reads (128+BN)*32 B at 128 B/cycle; + fixed overhead
+    double step = bn / 2.0 > (128 + bn) / 4.0 ? bn / 2.0 : (128 + bn) / 4.0;
+    double cost = static_cast<double>(waves) * (step + 12);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int64_t b200_conv_gemm_packed_k(int32_t ksize, int32_t c0, int32_t c1) {
+  return static_cast<int64_t>(ksize) * ksize * (b200::rup(c0, 64) + (c1 > 0 ? b200::rup(c1, 64) : 0));
+}
+
+int32_t b200_conv_gemm_pick_tile_n(int64_t M, int32_t N, int32_t geglu) { return b200::pick_tile_n(M, N, geglu); }
+
+int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(a != nullptr, "conv_gemm: null args");
+  B200_CHECK_ARG(a->x[0] && a->w && a->y, "conv_gemm: null x/w/y");
+  B200_CHECK_ARG(a->ksize == 1 || a->ksize == 3, "conv_gemm: ksize %d (need 1 or 3)", a->ksize);
+  B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_gemm: stride %d (need 1 or 2)", a->stride);
+  B200_CHECK_ARG(a->batch > 0 && a->H > 0 && a->W > 0 && a->N > 0, "conv_gemm: bad shape");
+  B200_CHECK_ARG(a->dtype == B200_DTYPE_BF16 || a->dtype == B200_DTYPE_FP16, "conv_gemm: dtype %d", a->dtype);
+  const int nsrc = (a->x[1] != nullptr && a->c[1] > 0) ? 2 : 1;
+  for (int s = 0; s < nsrc; ++s) {
+    B200_CHECK_ARG(a->c[s] > 0 && a->c[s] % 8 == 0, "conv_gemm: c[%d]=%d must be a positive multiple of 8", s, a->c[s]);
+    B200_CHECK_ARG(a->ldx[s] >= a->c[s] && a->ldx[s] % 8 == 0, "conv_gemm: ldx[%d]=%d invalid", s, a->ldx[s]);
+    B200_CHECK_ARG(aligned16(a->x[s]), "conv_gemm: x[%d] not 16-byte aligned", s);
+  }
+  B200_CHECK_ARG(aligned16(a->w), "conv_gemm: w not 16-byte aligned");
+  if (a->stride == 2) B200_CHECK_ARG(a->H % 2 == 0 && a->W % 2 == 0, "conv_gemm: stride 2 needs even H, W");
+  if (a->geglu) B200_CHECK_ARG(a->N % 64 == 0, "conv_gemm: geglu needs N %% 64 == 0 (N=%d)", a->N);
+  if (a->gate || a->rowvec) B200_CHECK_ARG(a->rows_per_group > 0, "conv_gemm: rows_per_group must be > 0");
+
+  const int Ho = (a->stride == 1) ? a->H : a->H / 2;
+  const int Wo = (a->stride == 1) ? a->W : a->W / 2;
+  const long long M = static_cast<long long>(a->batch) * Ho * Wo;
+
+  int bn = a->tile_n ? a->tile_n : pick_tile_n(M, a->N, a->geglu);
+  B200_CHECK_ARG(bn == 32 || bn == 64 || bn == 128 || bn == 256, "conv_gemm: no valid tile_n (N=%d geglu=%d)", a->N,
+                 a->geglu);
+  if (a->geglu) B200_CHECK_ARG(a->N % bn == 0, "conv_gemm: geglu N=%d not a multiple of tile_n=%d", a->N, bn);
+
+  ConvGemmParams prm;
+  memset(&prm, 0, sizeof(prm));
+
+  // ---- output-pixel rectangle (bw x bh = 128) minimising the tile count
+  int best_bw = 128;
+  long long best_tiles = -1;
+  for (int bw = 128; bw >= 1; bw >>= 1) {
+    int bh = 128 / bw;
+    long long tiles = static_cast<long long>(cdiv(Wo, bw)) * cdiv(Ho, bh);
+    if (best_tiles < 0 || tiles < best_tiles) {
+      best_tiles = tiles;
+      best_bw = bw;
+    }
+  }
+  prm.bw = best_bw;
+  prm.bh = 128 / best_bw;
+  prm.bw_shift = 0;
+  while ((1 << prm.bw_shift) < prm.bw) ++prm.bw_shift;
+  prm.batch = a->batch;
+  prm.Ho = Ho;
+  prm.Wo = Wo;
+  prm.tiles_w = cdiv(Wo, prm.bw);
+  prm.tiles_h = cdiv(Ho, prm.bh);
+  prm.m_tiles = prm.tiles_w * prm.tiles_h * a->batch;
+  prm.n_tiles = cdiv(a->N, bn);
+  prm.total_tiles = prm.m_tiles * prm.n_tiles;
+  prm.N = a->N;
+  prm.nsrc = nsrc;
+  prm.num_taps = a->ksize * a->ksize;
+  prm.chunks[0] = cdiv(a->c[0], 64);
+  prm.chunks[1] = nsrc == 2 ? cdiv(a->c[1], 64) : 0;
+  prm.k_chunks = prm.num_taps * (prm.chunks[0] + prm.chunks[1]);
+
+  // ---- filter taps: which (parity) tensor map and which box shift each tap uses
+  int tap = 0;
+  for (int r = 0; r < a->ksize; ++r) {
+    for (int s = 0; s < a->ksize; ++s, ++tap) {
+      if (a->ksize == 1) {
+        prm.tap_map[tap] = 0;
+        prm.tap_dh[tap] = 0;
+        prm.tap_dw[tap] = 0;
+      } else if (a->stride == 1) {
+        prm.tap_map[tap] = 0;
+        prm.tap_dh[tap] = static_cast<int8_t>(r - 1);
+        prm.tap_dw[tap] = static_cast<int8_t>(s - 1);
+      } else {
+        // input row 2*ho + r - 1:  r=0 -> odd rows of ho-1, r=1 -> even rows of ho, r=2 -> odd rows of ho
+        const int ph = (r == 1) ? 0 : 1, pw = (s == 1) ? 0 : 1;
+        prm.tap_map[tap] = static_cast<int8_t>(ph * 2 + pw);
+        prm.tap_dh[tap] = static_cast<int8_t>(r == 0 ? -1 : 0);
+        prm.tap_dw[tap] = static_cast<int8_t>(s == 0 ? -1 : 0);
+      }
+    }
+  }
+
+  // ---- tensor maps
+  const uint32_t abox[4] = {64u, static_cast<uint32_t>(prm.bw), static_cast<uint32_t>(prm.bh), 1u};
+  for (int s = 0; s < nsrc; ++s) {
+    const uint64_t ld = static_cast<uint64_t>(a->ldx[s]);
+    if (a->stride == 1) {
+      const uint64_t dims[4] = {static_cast<uint64_t>(a->c[s]), static_cast<uint64_t>(a->W), static_cast<uint64_t>(a->H),
+                                static_cast<uint64_t>(a->batch)};
+      const uint64_t str[3] = {ld * 2, ld * 2 * a->W, ld * 2 * a->W * a->H};
+      int r = make_tensor_map_16b(&prm.a_map[s * 4], a->x[s], 4, dims, str, abox, "conv_gemm A");
+      if (r) return r;
+    } else {
+      const int npar = (a->ksize == 1) ? 1 : 4;
+      for (int par = 0; par < npar; ++par) {
+        const int ph = par >> 1, pw = par & 1;
+        const uint8_t* base = static_cast<const uint8_t*>(a->x[s]) + (static_cast<uint64_t>(ph) * a->W + pw) * ld * 2;
+        const uint64_t dims[4] = {static_cast<uint64_t>(a->c[s]), static_cast<uint64_t>(a->W / 2),
+                                  static_cast<uint64_t>(a->H / 2), static_cast<uint64_t>(a->batch)};
+        const uint64_t str[3] = {ld * 4, ld * 4 * a->W, ld * 2 * a->W * a->H};
+        int r = make_tensor_map_16b(&prm.a_map[s * 4 + par], base, 4, dims, str, abox, "conv_gemm A (stride 2)");
+        if (r) return r;
+      }
+    }
+  }
+  {
+    const uint64_t Kp = static_cast<uint64_t>(b200_conv_gemm_packed_k(a->ksize, a->c[0], nsrc == 2 ? a->c[1] : 0));
+    const uint64_t dims[2] = {Kp, static_cast<uint64_t>(a->N)};
+    const uint64_t str[1] = {Kp * 2};
+    const uint32_t box[2] = {64u, static_cast<uint32_t>(bn)};
+    int r = make_tensor_map_16b(&prm.w_map, a->w, 2, dims, str, box, "conv_gemm W");
+    if (r) return r;
+  }
+
+  prm.bias = a->bias;
+  prm.gate = a->gate;
+  prm.rowvec = a->rowvec;
+  prm.residual = a->residual;
+  prm.y = a->y;
+  prm.ld_gate = a->ld_gate;
+  prm.ld_rowvec = a->ld_rowvec;
+  prm.ldr = a->ldr;
+  prm.ldy = a->ldy;
+  prm.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  prm.act = a->act;
+  bool vec = aligned16(a->y) && (a->ldy % 8 == 0);
+  if (a->bias) vec = vec && aligned16(a->bias);
+  if (a->gate) vec = vec && aligned16(a->gate) && (a->ld_gate % 8 == 0);
+  if (a->rowvec) vec = vec && aligned16(a->rowvec) && (a->ld_rowvec % 8 == 0);
+  if (a->residual) vec = vec && aligned16(a->residual) && (a->ldr % 8 == 0);
+  prm.vec_ok = vec ? 1 : 0;
+
+  const int grid = prm.total_tiles < num_sms() ? prm.total_tiles : num_sms();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool fp16 = a->dtype == B200_DTYPE_FP16;
+  if (a->geglu) return fp16 ? launch_bn<true, true>(bn, prm, grid, st) : launch_bn<true, false>(bn, prm, grid, st);
+  return fp16 ? launch_bn<false, true>(bn, prm, grid, st) : launch_bn<false, false>(bn, prm, grid, st);
+}
+
+}  // extern "C"

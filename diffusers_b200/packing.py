@@ -1,0 +1,55 @@
+"""Weight re-layout for libb200diff.so (done once at load time, plain torch on any device).
+
+conv_gemm weights are K-major [N, Kp] with k = ((tap * nsrc + src) * rup64(C_src)) + channel, zero padded so
+that every 64-wide K chunk the kernel fetches belongs to exactly one (tap, source) pair
+(include/b200_diffusion.h, b200_conv_gemm).
+"""
+import torch
+
+
+def rup(v, m):
+    return (v + m - 1) // m * m
+
+
+def packed_k(ksize, c0, c1=0):
+    return ksize * ksize * (rup(c0, 64) + (rup(c1, 64) if c1 > 0 else 0))
+
+
+def pack_conv_weight(w, split=None):
+    """nn.Conv2d weight [O, I, kh, kw] -> [O, Kp].  `split` = (c0, c1) when the conv input is the channel
+    concatenation of two tensors (torch.cat([h, skip], dim=1), reference unet_2d_blocks.py:2444)."""
+    O, I, kh, kw = w.shape
+    assert kh == kw and kh in (1, 3)
+    srcs = [I] if split is None else list(split)
+    assert sum(srcs) == I
+    out = w.new_zeros(O, kh * kw, sum(rup(c, 64) for c in srcs))
+    wt = w.permute(0, 2, 3, 1).reshape(O, kh * kw, I)  # [O, tap, I]
+    src_off, dst_off = 0, 0
+    for c in srcs:
+        out[:, :, dst_off:dst_off + c] = wt[:, :, src_off:src_off + c]
+        src_off += c
+        dst_off += rup(c, 64)
+    return out.reshape(O, -1).contiguous()
+
+
+def pack_linear_weight(w, split=None):
+    """nn.Linear weight [N, K] -> [N, Kp] (1x1 'conv' over a row image)."""
+    return pack_conv_weight(w[:, :, None, None], split)
+
+
+def pack_geglu(w, b, tile_n):
+    """GEGLU proj weight [2*inner, K] / bias [2*inner] (value rows first, gate rows second,
+    reference activations.py:113-123 `hidden_states, gate = chunk(2)`) -> per-tile interleave
+    [tile_n/2 value rows | tile_n/2 gate rows] so one CTA tile holds matching value/gate columns."""
+    two_inner = w.shape[0]
+    inner = two_inner // 2
+    half = tile_n // 2
+    assert inner % half == 0, (inner, tile_n)
+    wv, wg = w[:inner], w[inner:]
+    nt = inner // half
+    wp = torch.stack([wv.reshape(nt, half, -1), wg.reshape(nt, half, -1)], dim=1).reshape(two_inner, -1)
+    bp = None
+    if b is not None:
+        bv, bg = b[:inner], b[inner:]
+        bp = torch.stack([bv.reshape(nt, half), bg.reshape(nt, half)], dim=1).reshape(two_inner).contiguous()
+    return pack_linear_weight(wp), bp

@@ -1,0 +1,157 @@
+"""GPU diagnostic for b200_conv_gemm: runs each case in a fresh subprocess (a trapped kernel poisons the
+CUDA context) and prints an error summary + mismatch structure.  Usage: python tools/diag_gemm.py [case ...]"""
+import json
+import os
+import subprocess
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+CASES = {
+    # name: dict(kind, ...)
+    "lin_1tile": dict(kind="linear", M=128, N=64, K=64),
+    "lin_k256": dict(kind="linear", M=256, N=128, K=256),
+    "lin_bn256": dict(kind="linear", M=512, N=512, K=512, tile_n=256),
+    "lin_bn32": dict(kind="linear", M=256, N=32, K=128, tile_n=32),
+    "lin_sdxl": dict(kind="linear", M=2048, N=1280, K=1280, bias=True, residual=True),
+    "lin_ragged": dict(kind="linear", M=200, N=72, K=96, bias=True),
+    "lin_n4": dict(kind="linear", M=300, N=4, K=320, bias=True),
+    "lin_act_gate": dict(kind="linear", M=1024, N=256, K=512, bias=True, act=3, gate=True, rowvec=True, residual=True, groups=2),
+    "lin_2src": dict(kind="linear", M=512, N=256, K=192, K2=320, bias=True),
+    "lin_geglu": dict(kind="linear", M=512, N=1024, K=256, bias=True, geglu=True),
+    "lin_geglu64": dict(kind="linear", M=130, N=192, K=64, bias=True, geglu=True),
+    "lin_fp16": dict(kind="linear", M=512, N=256, K=512, bias=True, fp16=True),
+    "lin_ff": dict(kind="linear", M=2048, N=10240, K=1280, bias=True, geglu=True),
+    "conv_small": dict(kind="conv", B=2, H=16, W=16, C=64, N=64, bias=True),
+    "conv_32": dict(kind="conv", B=2, H=32, W=32, C=128, N=192, bias=True, rowvec=True, residual=True),
+    "conv_128": dict(kind="conv", B=2, H=128, W=128, C=320, N=320, bias=True),
+    "conv_odd": dict(kind="conv", B=1, H=24, W=40, C=32, N=48, bias=True),
+    "conv_2src": dict(kind="conv", B=2, H=32, W=32, C=128, C2=64, N=128, bias=True),
+    "conv_s2": dict(kind="conv", B=2, H=32, W=32, C=64, N=128, bias=True, stride=2),
+    "conv_s2_big": dict(kind="conv", B=2, H=128, W=128, C=320, N=320, bias=True, stride=2),
+    "conv_c8": dict(kind="conv", B=2, H=32, W=32, C=8, N=64, bias=True),
+    "conv_1x1": dict(kind="conv", B=2, H=32, W=32, C=192, N=64, bias=True, ksize=1),
+}
+
+
+def run_case(name):
+    import torch
+    import torch.nn.functional as F
+    from diffusers_b200 import ops, packing
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = CASES[name]
+    dt = torch.float16 if cfg.get("fp16") else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    dev = "cuda"
+
+    def rnd(*shape, scale=1.0):
+        return (torch.randn(*shape, generator=g, device=dev) * scale).to(dt)
+
+    act = cfg.get("act", 0)
+    geglu = cfg.get("geglu", False)
+    tile_n = cfg.get("tile_n", 0)
+    if cfg["kind"] == "linear":
+        M, N, K = cfg["M"], cfg["N"], cfg["K"]
+        K2 = cfg.get("K2", 0)
+        x = rnd(M, K)
+        x2 = rnd(M, K2) if K2 else None
+        w = rnd(N, K + K2, scale=(K + K2) ** -0.5)
+        b = rnd(N) if cfg.get("bias") else None
+        groups = cfg.get("groups", 1)
+        n_out = N // 2 if geglu else N
+        gate = rnd(groups, n_out) if cfg.get("gate") else None
+        rowvec = rnd(groups, n_out) if cfg.get("rowvec") else None
+        res = rnd(M, n_out) if cfg.get("residual") else None
+        xx = torch.cat([x, x2], 1) if x2 is not None else x
+        ref = xx.float() @ w.float().t()
+        if b is not None:
+            ref = ref + b.float()
+        if geglu:
+            hv, gt = ref.chunk(2, dim=-1)
+            ref = hv * F.gelu(gt)
+        if act == 3:
+            ref = F.gelu(ref, approximate="tanh")
+        elif act == 2:
+            ref = F.gelu(ref)
+        elif act == 1:
+            ref = F.silu(ref)
+        rpg = M // groups
+        if gate is not None:
+            ref = ref * gate.float().repeat_interleave(rpg, 0)
+        if rowvec is not None:
+            ref = ref + rowvec.float().repeat_interleave(rpg, 0)
+        if res is not None:
+            ref = ref + res.float()
+        if geglu:
+            tn = tile_n or ops.pick_tile_n(M, N, True)
+            wp, bp = packing.pack_geglu(w, b, tn)
+            tile_n = tn
+        else:
+            wp, bp = packing.pack_linear_weight(w, (K, K2) if K2 else None), b
+        out = ops.linear(x, wp, N, bias=bp, act=act, geglu=geglu, gate=gate, rowvec=rowvec, rows_per_group=rpg,
+                         residual=res, x2=x2, tile_n=tile_n)
+    else:
+        B, H, W, Cc, N = cfg["B"], cfg["H"], cfg["W"], cfg["C"], cfg["N"]
+        C2 = cfg.get("C2", 0)
+        ks = cfg.get("ksize", 3)
+        stride = cfg.get("stride", 1)
+        x = rnd(B, H, W, Cc)
+        x2 = rnd(B, H, W, C2) if C2 else None
+        w = rnd(N, Cc + C2, ks, ks, scale=((Cc + C2) * ks * ks) ** -0.5)
+        b = rnd(N) if cfg.get("bias") else None
+        xx = torch.cat([x, x2], -1) if x2 is not None else x
+        ref = F.conv2d(xx.float().permute(0, 3, 1, 2), w.float(), b.float() if b is not None else None,
+                       stride=stride, padding=ks // 2).permute(0, 2, 3, 1).contiguous()
+        Ho, Wo = ref.shape[1], ref.shape[2]
+        rowvec = rnd(B, N) if cfg.get("rowvec") else None
+        res = rnd(B * Ho * Wo, N) if cfg.get("residual") else None
+        if rowvec is not None:
+            ref = ref + rowvec.float()[:, None, None, :]
+        ref = ref.reshape(B * Ho * Wo, N)
+        if res is not None:
+            ref = ref + res.float()
+        wp = packing.pack_conv_weight(w, (Cc, C2) if C2 else None)
+        out = ops.conv_gemm(x.reshape(-1, Cc), wp, N, batch=B, H=H, W=W, ksize=ks, stride=stride,
+                            x2=x2.reshape(-1, C2) if x2 is not None else None, bias=b, rowvec=rowvec,
+                            rows_per_group=Ho * Wo, residual=res, tile_n=tile_n)
+    torch.cuda.synchronize()
+    o = out.float()
+    err = (o - ref).abs()
+    tol = 1.5e-2 * ref.abs() + 2e-2 if dt == torch.bfloat16 else 3e-3 * ref.abs() + 4e-3
+    bad = err > tol
+    res = dict(case=name, shape=list(o.shape), max_abs=float(err.max()), ref_absmax=float(ref.abs().max()),
+               n_bad=int(bad.sum()), frac_bad=float(bad.float().mean()), nan=int(torch.isnan(o).sum()))
+    if res["n_bad"]:
+        rows_bad = bad.any(1).nonzero().flatten()
+        cols_bad = bad.any(0).nonzero().flatten()
+        res["bad_rows_head"] = rows_bad[:24].tolist()
+        res["bad_cols_head"] = cols_bad[:24].tolist()
+        res["n_bad_rows"] = int(rows_bad.numel())
+        res["n_bad_cols"] = int(cols_bad.numel())
+        i = bad.nonzero()[0].tolist()
+        res["first_bad"] = dict(idx=i, got=float(o[i[0], i[1]]), ref=float(ref[i[0], i[1]]))
+        # is the output a permutation / scaled version? correlation of whole tensor
+        res["corr"] = float(torch.corrcoef(torch.stack([o.flatten(), ref.flatten()]))[0, 1])
+    print("RESULT " + json.dumps(res))
+    return res["n_bad"] == 0 and res["nan"] == 0
+
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--one":
+        ok = run_case(sys.argv[2])
+        sys.exit(0 if ok else 1)
+    names = sys.argv[1:] or list(CASES)
+    summary = {}
+    for n in names:
+        try:
+            p = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=180)
+            out = p.stdout + p.stderr
+            line = [l for l in out.splitlines() if l.startswith("RESULT ")]
+            status = "PASS" if p.returncode == 0 else "FAIL"
+            print(f"[{status}] {n}: {line[-1][7:] if line else out[-1500:]}", flush=True)
+            summary[n] = status
+        except subprocess.TimeoutExpired:
+            print(f"[TIMEOUT] {n}", flush=True)
+            summary[n] = "TIMEOUT"
+    print("SUMMARY", json.dumps(summary))
