@@ -39,7 +39,7 @@ class AttentionArgs(C.Structure):
         ("k_row_stride", C.c_int64), ("k_batch_stride", C.c_int64),
         ("v_row_stride", C.c_int64), ("v_batch_stride", C.c_int64),
         ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
-        ("scale", C.c_float), ("dtype", C.c_int32),
+        ("scale", C.c_float), ("dtype", C.c_int32), ("nq_override", C.c_int32),
     ]
 
 
@@ -90,6 +90,19 @@ def lib():
         _lib.b200_conv_gemm_packed_k.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         _lib.b200_conv_gemm_pick_tile_n.restype = C.c_int32
         _lib.b200_conv_gemm_pick_tile_n.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+        _lib.b200_group_norm_workspace_bytes.restype = C.c_int64
+        _lib.b200_group_norm_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        I32, I64, F32, VP = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+        _lib.b200_nchw_to_nhwc.argtypes = [VP, VP, I32, I32, I32, I32, I32, VP]
+        _lib.b200_nhwc_to_nchw.argtypes = [VP, I32, VP, I32, I32, I32, I32, VP]
+        _lib.b200_upsample_nearest2x.argtypes = [VP, I32, VP, I32, I32, I32, I32, I32, I32, VP]
+        _lib.b200_timestep_embedding.argtypes = [VP, I32, VP, I32, I32, I32, F32, F32, F32, I32, VP]
+        _lib.b200_euler_step.argtypes = [VP, VP, VP, I64, F32, F32, I32, VP]
+        _lib.b200_scale.argtypes = [VP, VP, I64, F32, I32, VP]
+        _lib.b200_cfg_euler_step.argtypes = [VP, I32, VP, VP, I32, I32, I32, I32, F32, I32, F32, F32, I32, VP]
+        _lib.b200_flow_match_step.argtypes = [VP, VP, VP, I64, F32, F32, I32, VP]
+        for fn in ("b200_conv_gemm", "b200_attention", "b200_group_norm", "b200_layer_norm", "b200_small_linear"):
+            getattr(_lib, fn).argtypes = [VP, VP]
     return _lib
 
 

@@ -1,1 +1,444 @@
+// HBM-bound normalisation kernels (coalesced 16-byte accesses, warp-shuffle / shared reductions):
+//   b200_group_norm : GroupNorm(+SiLU) over NHWC, optionally over the channel concat of two tensors
+//   b200_layer_norm : LayerNorm over token rows, optional affine and AdaLN modulation
+#include <string.h>
+
+#include "common.cuh"
 #include "host_common.h"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm
+// ------------------------------------------------------------------------------------------------
+struct GroupNormParams {
+  const void* x[2];
+  int c[2], ldx[2];
+  int C, V, V0;  // total channels, 8-wide vectors per pixel (total / in source 0)
+  int batch, hw, groups, cg;
+  float eps;
+  const void* gamma;
+  const void* beta;
+  int act;
+  void* y;
+  int ldy;
+  int chunks, ppc;   // stats: chunks per image, pixels per chunk
+  int P;             // stats: pixels processed in parallel per CTA
+  float* partial;    // [batch][chunks][groups][3]  (count, mean, M2)
+  float* stats;      // [batch][groups][2]          (mean, rstd)
+  unsigned int* counter;  // [batch], zero between launches
+  int apply_ppb;     // apply: pixels per CTA
+};
+
+__device__ __forceinline__ void chan_combine(float& na, float& ma, float& M2a, float nb, float mb, float M2b) {
+  if (nb == 0.f) return;
+  float n = na + nb;
+  float d = mb - ma;
+  ma += d * (nb / n);
+  M2a += M2b + d * d * (na * nb / n);
+  na = n;
+}
+
+// grid (chunks, batch); block V*P threads.  Thread (pl, cv) owns 8 fixed channels and walks pixels
+// chunk_start + pl, + P, ...  Sums are taken relative to the first value seen (shifted data) so the
+// fp32 variance does not cancel; partials are merged with Chan's formula in a fixed order
+// (deterministic).  The last CTA of an image to finish folds the chunk partials into mean/rstd.
+template <bool FP16>
+__global__ void group_norm_stats_kernel(const GroupNormParams p) {
+  using H = Half16<FP16>;
+  extern __shared__ float2 s_mm[];  // [P][C] (mean, M2) per (pixel lane, channel)
+  __shared__ float s_cnt[64];       // per pixel lane count (P <= 64)
+  __shared__ unsigned int s_last;
+
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int t = threadIdx.x;
+  const int pl = t / p.V, cv = t - pl * p.V;
+  const int pix0 = chunk * p.ppc;
+  const int pix1 = min(p.hw, pix0 + p.ppc);
+
+  const int src = cv < p.V0 ? 0 : 1;
+  const int coff = (src == 0 ? cv : cv - p.V0) * 8;
+  const typename H::T* xb = static_cast<const typename H::T*>(p.x[src]) +
+                            (static_cast<size_t>(n) * p.hw) * p.ldx[src] + coff;
+  const int ld = p.ldx[src];
+
+  float sh[8], s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[j] = s[j] = ss[j] = 0.f;
+  float cnt = 0.f;
+  if (pl < p.P) {
+    for (int pix = pix0 + pl; pix < pix1; pix += p.P) {
+      uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pix) * ld);
+      float2 a = H::unpack(u.x), b = H::unpack(u.y), c = H::unpack(u.z), d = H::unpack(u.w);
+      float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+      if (cnt == 0.f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sh[j] = v[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float e = v[j] - sh[j];
+        s[j] += e;
+        ss[j] += e * e;
+      }
+      cnt += 1.f;
+    }
+    const int cbase = cv * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float mean = 0.f, M2 = 0.f;
+      if (cnt > 0.f) {
+        float m = s[j] / cnt;
+        mean = sh[j] + m;
+        M2 = fmaxf(ss[j] - s[j] * m, 0.f);
+      }
+      s_mm[pl * p.C + cbase + j] = make_float2(mean, M2);
+    }
+    if (cv == 0) s_cnt[pl] = cnt;
+  }
+  __syncthreads();
+  float* part = p.partial + (static_cast<size_t>(n) * p.chunks + chunk) * p.groups * 3;
+  if (t < p.groups) {
+    float na = 0.f, ma = 0.f, M2a = 0.f;
+    for (int pl2 = 0; pl2 < p.P; ++pl2) {
+      const float nb = s_cnt[pl2];
+      for (int c = t * p.cg; c < (t + 1) * p.cg; ++c) {
+        float2 mm = s_mm[pl2 * p.C + c];
+        chan_combine(na, ma, M2a, nb, mm.x, mm.y);
+      }
+    }
+    part[t * 3 + 0] = na;
+    part[t * 3 + 1] = ma;
+    part[t * 3 + 2] = M2a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    unsigned int ticket = atomicAdd(&p.counter[n], 1u);
+    s_last = (ticket == static_cast<unsigned int>(p.chunks - 1)) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (t < p.groups) {
+      float na = 0.f, ma = 0.f, M2a = 0.f;
+      const float* pp = p.partial + static_cast<size_t>(n) * p.chunks * p.groups * 3 + t * 3;
+      for (int ch = 0; ch < p.chunks; ++ch) {
+        const volatile float* q = pp + static_cast<size_t>(ch) * p.groups * 3;
+        chan_combine(na, ma, M2a, q[0], q[1], q[2]);
+      }
+      float var = M2a / na;
+      p.stats[(static_cast<size_t>(n) * p.groups + t) * 2 + 0] = ma;
+      p.stats[(static_cast<size_t>(n) * p.groups + t) * 2 + 1] = rsqrtf(var + p.eps);
+    }
+    if (t == 0) p.counter[n] = 0u;
+  }
+}
+
+// grid (ceil(hw / ppb), batch); 256 threads.  y = act(x * sc[c] + bi[c]) with sc = rstd*gamma,
+// bi = beta - mean*rstd*gamma staged in shared memory.
+template <bool FP16>
+__global__ void __launch_bounds__(256) group_norm_apply_kernel(const GroupNormParams p) {
+  using H = Half16<FP16>;
+  extern __shared__ float s_scbi[];  // [2][C]
+  float* s_sc = s_scbi;
+  float* s_bi = s_scbi + p.C;
+  const int n = blockIdx.y;
+  const typename H::T* gamma = static_cast<const typename H::T*>(p.gamma);
+  const typename H::T* beta = static_cast<const typename H::T*>(p.beta);
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const int g = c / p.cg;
+    const float mean = p.stats[(static_cast<size_t>(n) * p.groups + g) * 2 + 0];
+    const float rstd = p.stats[(static_cast<size_t>(n) * p.groups + g) * 2 + 1];
+    const float ga = gamma ? H::to_float(gamma[c]) : 1.f;
+    const float be = beta ? H::to_float(beta[c]) : 0.f;
+    s_sc[c] = rstd * ga;
+    s_bi[c] = be - mean * rstd * ga;
+  }
+  __syncthreads();
+  const int pix0 = blockIdx.x * p.apply_ppb;
+  const int npix = min(p.apply_ppb, p.hw - pix0);
+  const typename H::T* x0 = static_cast<const typename H::T*>(p.x[0]) + (static_cast<size_t>(n) * p.hw + pix0) * p.ldx[0];
+  const typename H::T* x1 =
+      p.x[1] ? static_cast<const typename H::T*>(p.x[1]) + (static_cast<size_t>(n) * p.hw + pix0) * p.ldx[1] : nullptr;
+  typename H::T* y = static_cast<typename H::T*>(p.y) + (static_cast<size_t>(n) * p.hw + pix0) * p.ldy;
+  const int total = npix * p.V;
+  const bool do_silu = p.act == ACT_SILU;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int pix = i / p.V;
+    const int cv = i - pix * p.V;
+    const typename H::T* src =
+        cv < p.V0 ? x0 + static_cast<size_t>(pix) * p.ldx[0] + cv * 8 : x1 + static_cast<size_t>(pix) * p.ldx[1] + (cv - p.V0) * 8;
+    uint4 u = *reinterpret_cast<const uint4*>(src);
+    float2 a = H::unpack(u.x), b = H::unpack(u.y), c = H::unpack(u.z), d = H::unpack(u.w);
+    float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+    const int cb = cv * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float o = fmaf(v[j], s_sc[cb + j], s_bi[cb + j]);
+      v[j] = do_silu ? silu_f(o) : o;
+    }
+    uint4 o;
+    o.x = H::pack(v[0], v[1]);
+    o.y = H::pack(v[2], v[3]);
+    o.z = H::pack(v[4], v[5]);
+    o.w = H::pack(v[6], v[7]);
+    *reinterpret_cast<uint4*>(y + static_cast<size_t>(pix) * p.ldy + cb) = o;
+  }
+}
+
+static void gn_plan(int batch, int hw, int C, int* chunks, int* ppc) {
+  // aim for >= ~2 waves of stats CTAs over the batch without making chunks tiny
+  int target = (2 * num_sms() + batch - 1) / batch;
+  int ch = hw / 128;  // >= 128 pixels per chunk
+  if (ch < 1) ch = 1;
+  if (ch > target) ch = target;
+  if (ch > 256) ch = 256;
+  if (ch < 1) ch = 1;
+  *ppc = (hw + ch - 1) / ch;
+  *chunks = (hw + *ppc - 1) / *ppc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row held in registers as packed 16-bit (<= 16 x 8 values per lane)
+// ------------------------------------------------------------------------------------------------
+struct LayerNormParams {
+  const void* x;
+  int ldx, rows, cols;
+  float eps;
+  const void* gamma;
+  const void* beta;
+  const void* scale;
+  const void* shift;
+  int ld_mod, rows_per_group;
+  void* y;
+  int ldy;
+};
+
+template <bool FP16, int NV>
+__global__ void __launch_bounds__(256) layer_norm_kernel(const LayerNormParams p) {
+  using H = Half16<FP16>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= p.rows) return;
+  const int nvec = p.cols >> 3;
+  const typename H::T* x = static_cast<const typename H::T*>(p.x) + static_cast<size_t>(row) * p.ldx;
+  uint4 r[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      r[i] = *reinterpret_cast<const uint4*>(x + v * 8);
+      float2 a = H::unpack(r[i].x), b = H::unpack(r[i].y), c = H::unpack(r[i].z), d = H::unpack(r[i].w);
+      sum += (a.x + a.y) + (b.x + b.y) + (c.x + c.y) + (d.x + d.y);
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(p.cols);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float2 a = H::unpack(r[i].x), b = H::unpack(r[i].y), c = H::unpack(r[i].z), d = H::unpack(r[i].w);
+      float e;
+      e = a.x - mean; sq += e * e; e = a.y - mean; sq += e * e;
+      e = b.x - mean; sq += e * e; e = b.y - mean; sq += e * e;
+      e = c.x - mean; sq += e * e; e = c.y - mean; sq += e * e;
+      e = d.x - mean; sq += e * e; e = d.y - mean; sq += e * e;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(p.cols) + p.eps);
+  const typename H::T* gamma = static_cast<const typename H::T*>(p.gamma);
+  const typename H::T* beta = static_cast<const typename H::T*>(p.beta);
+  const int grp = (p.scale || p.shift) ? row / p.rows_per_group : 0;
+  const typename H::T* scale = p.scale ? static_cast<const typename H::T*>(p.scale) + static_cast<size_t>(grp) * p.ld_mod : nullptr;
+  const typename H::T* shift = p.shift ? static_cast<const typename H::T*>(p.shift) + static_cast<size_t>(grp) * p.ld_mod : nullptr;
+  typename H::T* y = static_cast<typename H::T*>(p.y) + static_cast<size_t>(row) * p.ldy;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float2 a = H::unpack(r[i].x), b = H::unpack(r[i].y), c = H::unpack(r[i].z), d = H::unpack(r[i].w);
+      float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd;
+      if (gamma) {
+        uint4 g = *reinterpret_cast<const uint4*>(gamma + v * 8);
+        float2 g0 = H::unpack(g.x), g1 = H::unpack(g.y), g2 = H::unpack(g.z), g3 = H::unpack(g.w);
+        f[0] *= g0.x; f[1] *= g0.y; f[2] *= g1.x; f[3] *= g1.y; f[4] *= g2.x; f[5] *= g2.y; f[6] *= g3.x; f[7] *= g3.y;
+      }
+      if (beta) {
+        uint4 g = *reinterpret_cast<const uint4*>(beta + v * 8);
+        float2 g0 = H::unpack(g.x), g1 = H::unpack(g.y), g2 = H::unpack(g.z), g3 = H::unpack(g.w);
+        f[0] += g0.x; f[1] += g0.y; f[2] += g1.x; f[3] += g1.y; f[4] += g2.x; f[5] += g2.y; f[6] += g3.x; f[7] += g3.y;
+      }
+      if (scale) {
+        uint4 g = *reinterpret_cast<const uint4*>(scale + v * 8);
+        float2 g0 = H::unpack(g.x), g1 = H::unpack(g.y), g2 = H::unpack(g.z), g3 = H::unpack(g.w);
+        f[0] *= 1.f + g0.x; f[1] *= 1.f + g0.y; f[2] *= 1.f + g1.x; f[3] *= 1.f + g1.y;
+        f[4] *= 1.f + g2.x; f[5] *= 1.f + g2.y; f[6] *= 1.f + g3.x; f[7] *= 1.f + g3.y;
+      }
+      if (shift) {
+        uint4 g = *reinterpret_cast<const uint4*>(shift + v * 8);
+        float2 g0 = H::unpack(g.x), g1 = H::unpack(g.y), g2 = H::unpack(g.z), g3 = H::unpack(g.w);
+        f[0] += g0.x; f[1] += g0.y; f[2] += g1.x; f[3] += g1.y; f[4] += g2.x; f[5] += g2.y; f[6] += g3.x; f[7] += g3.y;
+      }
+      uint4 o;
+      o.x = H::pack(f[0], f[1]);
+      o.y = H::pack(f[2], f[3]);
+      o.z = H::pack(f[4], f[5]);
+      o.w = H::pack(f[6], f[7]);
+      *reinterpret_cast<uint4*>(y + v * 8) = o;
+    }
+  }
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int64_t b200_group_norm_workspace_bytes(int32_t batch, int32_t hw, int32_t groups) {
+  int chunks, ppc;
+  b200::gn_plan(batch, hw, 0, &chunks, &ppc);
+  // partial [batch][chunks][groups][3] + stats [batch][groups][2] + counters [batch]; chunks <= 256
+  int64_t floats = static_cast<int64_t>(batch) * 256 * groups * 3 + static_cast<int64_t>(batch) * groups * 2 + batch;
+  (void)chunks;
+  return floats * 4 + 256;
+}
+
+int b200_group_norm(const b200_group_norm_args* a, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(a && a->x[0] && a->y && a->workspace, "group_norm: null pointer");
+  const int nsrc = (a->x[1] && a->c[1] > 0) ? 2 : 1;
+  const int C = a->c[0] + (nsrc == 2 ? a->c[1] : 0);
+  B200_CHECK_ARG(a->groups > 0 && a->groups <= 256 && C % a->groups == 0, "group_norm: C=%d groups=%d", C, a->groups);
+  for (int s = 0; s < nsrc; ++s) {
+    B200_CHECK_ARG(a->c[s] % 8 == 0 && a->ldx[s] % 8 == 0 && a->ldx[s] >= a->c[s] && aligned16(a->x[s]),
+                   "group_norm: source %d needs channels/stride multiple of 8 and 16-byte alignment", s);
+  }
+  B200_CHECK_ARG(a->ldy % 8 == 0 && a->ldy >= C && aligned16(a->y), "group_norm: y stride/alignment");
+  B200_CHECK_ARG(a->act == B200_ACT_NONE || a->act == B200_ACT_SILU, "group_norm: act must be NONE or SILU");
+  B200_CHECK_ARG(a->workspace_bytes >= b200_group_norm_workspace_bytes(a->batch, a->hw, a->groups),
+                 "group_norm: workspace too small");
+  B200_CHECK_ARG(a->batch > 0 && a->hw > 0, "group_norm: bad shape");
+
+  GroupNormParams p;
+  memset(&p, 0, sizeof(p));
+  p.x[0] = a->x[0];
+  p.x[1] = nsrc == 2 ? a->x[1] : nullptr;
+  p.c[0] = a->c[0];
+  p.c[1] = nsrc == 2 ? a->c[1] : 0;
+  p.ldx[0] = a->ldx[0];
+  p.ldx[1] = nsrc == 2 ? a->ldx[1] : 0;
+  p.C = C;
+  p.V = C / 8;
+  p.V0 = a->c[0] / 8;
+  p.batch = a->batch;
+  p.hw = a->hw;
+  p.groups = a->groups;
+  p.cg = C / a->groups;
+  p.eps = a->eps;
+  p.gamma = a->gamma;
+  p.beta = a->beta;
+  p.act = a->act;
+  p.y = a->y;
+  p.ldy = a->ldy;
+  gn_plan(a->batch, a->hw, C, &p.chunks, &p.ppc);
+  B200_CHECK_ARG(p.V <= 1024, "group_norm: C=%d too large", C);
+  p.P = 256 / p.V;
+  if (p.P < 1) p.P = 1;
+  if (p.P > 64) p.P = 64;
+  if (p.P > p.ppc) p.P = p.ppc;
+  float* ws = static_cast<float*>(a->workspace);
+  p.partial = ws;
+  p.stats = ws + static_cast<size_t>(a->batch) * 256 * a->groups * 3;
+  p.counter = reinterpret_cast<unsigned int*>(p.stats + static_cast<size_t>(a->batch) * a->groups * 2);
+  p.apply_ppb = 64;
+  {
+    int64_t vec = static_cast<int64_t>(p.V) * 64;
+    // ~16 vectors per thread
+    while (vec < 4096 && p.apply_ppb < 1024) {
+      p.apply_ppb *= 2;
+      vec *= 2;
+    }
+  }
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool fp16 = a->dtype == B200_DTYPE_FP16;
+  {
+    int threads = p.V * p.P;
+    threads = (threads + 31) / 32 * 32;
+    if (threads < 32 * ((a->groups + 31) / 32)) threads = 32 * ((a->groups + 31) / 32);
+    size_t smem = static_cast<size_t>(p.P) * C * sizeof(float2);
+    dim3 grid(p.chunks, a->batch);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(fp16 ? group_norm_stats_kernel<true> : group_norm_stats_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "group_norm smem attr: %s", cudaGetErrorString(e));
+    }
+    if (fp16)
+      group_norm_stats_kernel<true><<<grid, threads, smem, st>>>(p);
+    else
+      group_norm_stats_kernel<false><<<grid, threads, smem, st>>>(p);
+    int r = check_launch("group_norm_stats_kernel");
+    if (r) return r;
+  }
+  {
+    dim3 grid((a->hw + p.apply_ppb - 1) / p.apply_ppb, a->batch);
+    size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
+    if (fp16)
+      group_norm_apply_kernel<true><<<grid, 256, smem, st>>>(p);
+    else
+      group_norm_apply_kernel<false><<<grid, 256, smem, st>>>(p);
+    return check_launch("group_norm_apply_kernel");
+  }
+}
+
+int b200_layer_norm(const b200_layer_norm_args* a, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(a && a->x && a->y, "layer_norm: null pointer");
+  B200_CHECK_ARG(a->cols > 0 && a->cols % 8 == 0 && a->cols <= 4096, "layer_norm: cols=%d (need multiple of 8, <= 4096)",
+                 a->cols);
+  B200_CHECK_ARG(a->ldx % 8 == 0 && a->ldy % 8 == 0 && aligned16(a->x) && aligned16(a->y), "layer_norm: alignment");
+  if (a->scale || a->shift)
+    B200_CHECK_ARG(a->rows_per_group > 0 && a->ld_mod % 8 == 0, "layer_norm: modulation needs rows_per_group, ld_mod %% 8");
+  if (a->rows <= 0) return 0;
+  LayerNormParams p;
+  p.x = a->x;
+  p.ldx = a->ldx;
+  p.rows = a->rows;
+  p.cols = a->cols;
+  p.eps = a->eps;
+  p.gamma = a->gamma;
+  p.beta = a->beta;
+  p.scale = a->scale;
+  p.shift = a->shift;
+  p.ld_mod = a->ld_mod;
+  p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  p.y = a->y;
+  p.ldy = a->ldy;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool fp16 = a->dtype == B200_DTYPE_FP16;
+  const int warps = 8;
+  const int grid = (a->rows + warps - 1) / warps;
+  const int nvec = a->cols / 8;
+#define B200_LN(NV)                                              \
+  if (fp16)                                                      \
+    layer_norm_kernel<true, NV><<<grid, warps * 32, 0, st>>>(p); \
+  else                                                           \
+    layer_norm_kernel<false, NV><<<grid, warps * 32, 0, st>>>(p);
+  if (nvec <= 32 * 3) {
+    B200_LN(3)
+  } else if (nvec <= 32 * 5) {
+    B200_LN(5)
+  } else if (nvec <= 32 * 12) {
+    B200_LN(12)
+  } else {
+    B200_LN(16)
+  }
+#undef B200_LN
+  return check_launch("layer_norm_kernel");
+}
+
+}  // extern "C"

@@ -91,3 +91,216 @@ def linear(x, w, N, *, bias=None, act=ACT_NONE, geglu=False, gate=None, rowvec=N
 
 def pick_tile_n(M, N, geglu=False):
     return int(_lib.lib().b200_conv_gemm_pick_tile_n(M, N, 1 if geglu else 0))
+
+
+def attention(q, k, v, *, heads, head_dim, scale=None, out=None, nq=0):
+    """softmax(q k^T * scale) v.  q [B, Sq, heads*head_dim-wide rows], k/v [B, Sk, ...]: 3-D views whose last
+    dim starts at this tensor's first head (row stride / batch stride taken from the view, so slices of a fused
+    QKV buffer work).  Returns [B, Sq, heads*head_dim]."""
+    _need_cuda(q, "q")
+    B, Sq = q.shape[0], q.shape[1]
+    Sk = k.shape[1]
+    if out is None:
+        out = torch.empty((B, Sq, heads * head_dim), dtype=q.dtype, device=q.device)
+    a = _lib.AttentionArgs()
+    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.batch, a.heads, a.sq, a.sk, a.head_dim = B, heads, Sq, Sk, head_dim
+    a.q_row_stride, a.q_batch_stride = q.stride(1), q.stride(0)
+    a.k_row_stride, a.k_batch_stride = k.stride(1), k.stride(0)
+    a.v_row_stride, a.v_batch_stride = v.stride(1), v.stride(0)
+    a.o_row_stride, a.o_batch_stride = out.stride(1), out.stride(0)
+    a.scale = float(scale) if scale is not None else 0.0
+    a.dtype = _dtype_code(q)
+    a.nq_override = nq
+    _lib.check(_lib.lib().b200_attention(C.byref(a), _stream()), "b200_attention")
+    _count()
+    return out
+
+
+_GN_WS = {}
+
+
+def _gn_workspace(device, batch, hw, groups):
+    need = int(_lib.lib().b200_group_norm_workspace_bytes(batch, hw, groups))
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _GN_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)  # zero-initialised once (counters)
+        _GN_WS[key] = ws
+    return ws
+
+
+def group_norm(x, *, batch, hw, groups, eps, gamma=None, beta=None, silu=False, x2=None, out=None):
+    """GroupNorm(+SiLU) over NHWC rows x [batch*hw, C0] (and x2 [batch*hw, C1] concatenated along channels)."""
+    _need_cuda(x, "x")
+    c0 = x.shape[-1]
+    c1 = x2.shape[-1] if x2 is not None else 0
+    if out is None:
+        out = torch.empty((batch * hw, c0 + c1), dtype=x.dtype, device=x.device)
+    ws = _gn_workspace(x.device, batch, hw, groups)
+    a = _lib.GroupNormArgs()
+    a.x[0], a.x[1] = x.data_ptr(), _ptr(x2)
+    a.c[0], a.c[1] = c0, c1
+    a.ldx[0], a.ldx[1] = x.stride(-2), (x2.stride(-2) if x2 is not None else 0)
+    a.batch, a.hw, a.groups, a.eps = batch, hw, groups, eps
+    a.gamma, a.beta = _ptr(gamma), _ptr(beta)
+    a.act = ACT_SILU if silu else ACT_NONE
+    a.y, a.ldy = out.data_ptr(), out.stride(-2)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    a.dtype = _dtype_code(x)
+    _lib.check(_lib.lib().b200_group_norm(C.byref(a), _stream()), "b200_group_norm")
+    _count(2)
+    return out
+
+
+def layer_norm(x, *, eps, gamma=None, beta=None, scale=None, shift=None, rows_per_group=0, out=None):
+    """LayerNorm over rows of x [rows, C]; optional AdaLN modulation y*(1+scale[g])+shift[g]."""
+    _need_cuda(x, "x")
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((rows, cols), dtype=x.dtype, device=x.device)
+    a = _lib.LayerNormArgs()
+    a.x, a.ldx, a.rows, a.cols, a.eps = x.data_ptr(), x.stride(0), rows, cols, eps
+    a.gamma, a.beta = _ptr(gamma), _ptr(beta)
+    a.scale, a.shift = _ptr(scale), _ptr(shift)
+    mod = scale if scale is not None else shift
+    a.ld_mod = mod.stride(-2) if mod is not None else 0
+    a.rows_per_group = rows_per_group
+    a.y, a.ldy = out.data_ptr(), out.stride(0)
+    a.dtype = _dtype_code(x)
+    _lib.check(_lib.lib().b200_layer_norm(C.byref(a), _stream()), "b200_layer_norm")
+    _count()
+    return out
+
+
+def small_linear(x, w, *, bias=None, act_in=ACT_NONE, act_out=ACT_NONE, addend=None, out=None):
+    """Linear for M <= 8 rows (weight-bandwidth bound): act_out(act_in(x) @ w.T + bias) (+ addend)."""
+    _need_cuda(x, "x")
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    for m0 in range(0, M, 8):
+        mm = min(8, M - m0)
+        a = _lib.SmallLinearArgs()
+        xs = x[m0:m0 + mm]
+        a.x, a.ldx, a.M, a.K = xs.data_ptr(), x.stride(0), mm, K
+        a.w, a.N, a.bias = w.data_ptr(), N, _ptr(bias)
+        a.act_in, a.act_out = act_in, act_out
+        if addend is not None:
+            a.addend, a.ld_add = addend[m0:m0 + mm].data_ptr(), addend.stride(0)
+        a.y, a.ldy = out[m0:m0 + mm].data_ptr(), out.stride(0)
+        a.dtype = _dtype_code(x)
+        _lib.check(_lib.lib().b200_small_linear(C.byref(a), _stream()), "b200_small_linear")
+        _count()
+    return out
+
+
+def nchw_to_nhwc(x, c_pad=None, out=None):
+    """[B, C, H, W] -> [B*H*W, c_pad] (zero-padded channels)."""
+    _need_cuda(x, "x")
+    B, Cc, H, W = x.shape
+    ld = c_pad or Cc
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty((B * H * W, ld), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().b200_nchw_to_nhwc(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), B, Cc, H * W, ld,
+                                            _dtype_code(x), _stream()), "b200_nchw_to_nhwc")
+    _count()
+    return out
+
+
+def nhwc_to_nchw(x, *, batch, C_out, H, W, out=None):
+    """[B*H*W, ld] (first C_out channels) -> [B, C_out, H, W]."""
+    _need_cuda(x, "x")
+    if out is None:
+        out = torch.empty((batch, C_out, H, W), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().b200_nhwc_to_nchw(C.c_void_p(x.data_ptr()), x.stride(-2), C.c_void_p(out.data_ptr()), batch,
+                                            C_out, H * W, _dtype_code(x), _stream()), "b200_nhwc_to_nchw")
+    _count()
+    return out
+
+
+def upsample_nearest2x(x, *, batch, H, W, out=None):
+    _need_cuda(x, "x")
+    Cc = x.shape[-1]
+    if out is None:
+        out = torch.empty((batch * 4 * H * W, Cc), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().b200_upsample_nearest2x(C.c_void_p(x.data_ptr()), x.stride(-2), C.c_void_p(out.data_ptr()),
+                                                  out.stride(-2), batch, H, W, Cc, _dtype_code(x), _stream()),
+               "b200_upsample_nearest2x")
+    _count()
+    return out
+
+
+def timestep_embedding(t, dim, *, dtype, flip_sin_to_cos, downscale_freq_shift, scale=1.0, max_period=10000.0,
+                       out=None):
+    """t fp32 [n] (device) -> [n, dim] in `dtype`."""
+    _need_cuda(t, "t")
+    assert t.dtype == torch.float32 and t.dim() == 1
+    n = t.shape[0]
+    if out is None:
+        out = torch.empty((n, dim), dtype=dtype, device=t.device)
+    _lib.check(_lib.lib().b200_timestep_embedding(C.c_void_p(t.data_ptr()), n, C.c_void_p(out.data_ptr()),
+                                                  out.stride(0), dim, 1 if flip_sin_to_cos else 0,
+                                                  C.c_float(downscale_freq_shift), C.c_float(scale),
+                                                  C.c_float(max_period), _dtype_code(out), _stream()),
+               "b200_timestep_embedding")
+    _count()
+    return out
+
+
+def euler_step(model_output, sample, sigma, sigma_next, out=None):
+    _need_cuda(sample, "sample")
+    model_output = model_output.contiguous()
+    sample = sample.contiguous()
+    if sample.dtype != model_output.dtype:
+        sample = sample.to(model_output.dtype)
+    if out is None:
+        out = torch.empty_like(model_output)
+    _lib.check(_lib.lib().b200_euler_step(C.c_void_p(model_output.data_ptr()), C.c_void_p(sample.data_ptr()),
+                                          C.c_void_p(out.data_ptr()), C.c_int64(sample.numel()), C.c_float(sigma),
+                                          C.c_float(sigma_next), _dtype_code(model_output), _stream()),
+               "b200_euler_step")
+    _count()
+    return out
+
+
+def scale_div(x, divisor, out=None):
+    _need_cuda(x, "x")
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.lib().b200_scale(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), C.c_int64(x.numel()),
+                                     C.c_float(divisor), _dtype_code(x), _stream()), "b200_scale")
+    _count()
+    return out
+
+
+def cfg_euler_step(eps_nhwc, latents_nchw, next_in_nhwc, *, guidance_scale, do_cfg, sigma, sigma_next):
+    """In place on `latents_nchw` [B, C, H, W]; writes the next UNet input into next_in_nhwc [(2)B*HW, ld]."""
+    _need_cuda(latents_nchw, "latents")
+    B, Cc, H, W = latents_nchw.shape
+    _lib.check(_lib.lib().b200_cfg_euler_step(C.c_void_p(eps_nhwc.data_ptr()), eps_nhwc.stride(-2),
+                                              C.c_void_p(latents_nchw.data_ptr()),
+                                              C.c_void_p(next_in_nhwc.data_ptr()), next_in_nhwc.stride(-2), B, Cc,
+                                              H * W, C.c_float(guidance_scale), 1 if do_cfg else 0, C.c_float(sigma),
+                                              C.c_float(sigma_next), _dtype_code(latents_nchw), _stream()),
+               "b200_cfg_euler_step")
+    _count()
+
+
+def flow_match_step(model_output, sample, sigma, sigma_next, out=None):
+    _need_cuda(sample, "sample")
+    model_output = model_output.contiguous()
+    sample = sample.contiguous()
+    if sample.dtype != model_output.dtype:
+        sample = sample.to(model_output.dtype)
+    if out is None:
+        out = torch.empty_like(model_output)
+    _lib.check(_lib.lib().b200_flow_match_step(C.c_void_p(model_output.data_ptr()), C.c_void_p(sample.data_ptr()),
+                                               C.c_void_p(out.data_ptr()), C.c_int64(sample.numel()), C.c_float(sigma),
+                                               C.c_float(sigma_next), _dtype_code(model_output), _stream()),
+               "b200_flow_match_step")
+    _count()
+    return out

@@ -102,6 +102,141 @@ int64_t b200_conv_gemm_packed_k(int32_t ksize, int32_t c0, int32_t c1);
 /* BN the auto heuristic picks (the GEGLU packer must interleave with the same BN). */
 int32_t b200_conv_gemm_pick_tile_n(int64_t M, int32_t N, int32_t geglu);
 
+/* -------------------------------------------------------------------------------------------
+ * b200_group_norm — nn.GroupNorm (+ fused SiLU) over NHWC, optionally over the channel concat of
+ * two tensors (the skip-connection torch.cat is never materialised).  Two launches: statistics
+ * (shifted sums + Chan merge, deterministic) and normalise/affine/activation.
+ * Replaces  models/resnet.py:326-327,349-362 (norm1/norm2 + nonlinearity),
+ *           transformers/transformer_2d.py:466 (Transformer2DModel.norm, eps 1e-6),
+ *           unets/unet_2d_condition.py:1227-1229 (conv_norm_out + conv_act),
+ *           autoencoders/vae.py:303-305, models/attention_processor.py:2740 (VAE attention group_norm).
+ * workspace: b200_group_norm_workspace_bytes() bytes, ZERO-INITIALISED once by the caller (the
+ * kernels leave its counters zeroed); fp32 statistics.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x[2];   /* NHWC sources [batch, hw, c[i]] concatenated along channels            */
+  int32_t c[2];       /* multiples of 8                                                         */
+  int32_t ldx[2];
+  int32_t batch, hw, groups;
+  float eps;
+  const void* gamma;  /* [C] or NULL                                                            */
+  const void* beta;   /* [C] or NULL                                                            */
+  int32_t act;        /* B200_ACT_NONE | B200_ACT_SILU                                          */
+  void* y;            /* [batch, hw, ldy]                                                       */
+  int32_t ldy;
+  void* workspace;
+  int64_t workspace_bytes;
+  int32_t dtype;
+} b200_group_norm_args;
+
+int b200_group_norm(const b200_group_norm_args* args, void* stream);
+int64_t b200_group_norm_workspace_bytes(int32_t batch, int32_t hw, int32_t groups);
+
+/* -------------------------------------------------------------------------------------------
+ * b200_layer_norm — nn.LayerNorm over token rows (one warp per row, two-pass statistics in
+ * registers), optional affine, optional AdaLN modulation  y = LN(x) * (1 + scale[g]) + shift[g]
+ * with g = row / rows_per_group.
+ * Replaces  models/attention.py:986,1030,1056 (BasicTransformerBlock norm1/2/3),
+ *           models/normalization.py:167-170,199-202,348-351 (AdaLayerNormZero/-Single/-Continuous).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;
+  int32_t ldx, rows, cols; /* cols: multiple of 8, <= 4096 */
+  float eps;
+  const void* gamma;  /* [cols] or NULL */
+  const void* beta;   /* [cols] or NULL */
+  const void* scale;  /* [groups, ld_mod] or NULL */
+  const void* shift;  /* [groups, ld_mod] or NULL */
+  int32_t ld_mod, rows_per_group;
+  void* y;
+  int32_t ldy;
+  int32_t dtype;
+} b200_layer_norm_args;
+
+int b200_layer_norm(const b200_layer_norm_args* args, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * b200_small_linear — nn.Linear for M <= 8 rows (time / text-time / AdaLN-modulation MLPs):
+ *   y[m, n] = act_out(sum_k act_in(x[m, k]) * w[n, k] + bias[n]) (+ addend[m, n])
+ * One warp per output column, weights streamed once with 16-byte loads (weight-bandwidth bound).
+ * w is the plain nn.Linear weight [N, K] (K multiple of 8).
+ * Replaces  models/embeddings.py:1262 (TimestepEmbedding), unets/unet_2d_condition.py:917-922
+ *           (add_embedding), models/resnet.py:343-347 (time_emb_proj(nonlinearity(temb))),
+ *           models/normalization.py:167,199,348 (AdaLN linear(silu(emb))).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;
+  int32_t ldx, M, K;
+  const void* w;
+  int32_t N;
+  const void* bias;
+  int32_t act_in, act_out;
+  const void* addend; /* [M, ld_add] or NULL; added after rounding y to 16 bit (emb + aug_emb) */
+  int32_t ld_add;
+  void* y;
+  int32_t ldy;
+  int32_t dtype;
+} b200_small_linear_args;
+
+int b200_small_linear(const b200_small_linear_args* args, void* stream);
+
+/* Boundary layout changes (model inputs/outputs are NCHW in the reference API) and nearest-2x
+ * upsample (models/upsampling.py:175 F.interpolate(scale_factor=2.0, mode="nearest")). */
+int b200_nchw_to_nhwc(const void* src, void* dst, int32_t batch, int32_t C, int32_t HW, int32_t ld_dst, int32_t dtype,
+                      void* stream);
+int b200_nhwc_to_nchw(const void* src, int32_t ld_src, void* dst, int32_t batch, int32_t C, int32_t HW, int32_t dtype,
+                      void* stream);
+int b200_upsample_nearest2x(const void* x, int32_t ldx, void* y, int32_t ldy, int32_t batch, int32_t H, int32_t W,
+                            int32_t C, int32_t dtype, void* stream);
+
+/* get_timestep_embedding (models/embeddings.py:27): t fp32 [n] -> out [n, dim] 16-bit. */
+int b200_timestep_embedding(const float* t, int32_t n, void* out, int32_t ld_out, int32_t dim, int32_t flip_sin_to_cos,
+                            float downscale_freq_shift, float scale, float max_period, int32_t dtype, void* stream);
+
+/* Scheduler steps; sigma values are the scheduler's fp32 table entries passed by value.
+ *   b200_euler_step       EulerDiscreteScheduler.step, epsilon prediction, s_churn = 0
+ *                         (schedulers/scheduling_euler_discrete.py:751-789)
+ *   b200_scale            EulerDiscreteScheduler.scale_model_input (:345): y = x / divisor
+ *   b200_cfg_euler_step   pipeline_stable_diffusion_xl.py:1202-1203,1224-1225,1233 in one launch:
+ *                         CFG combine, Euler update of the NCHW latents (in place), and the next
+ *                         step's scaled, CFG-duplicated NHWC model input
+ *   b200_flow_match_step  FlowMatchEulerDiscreteScheduler.step (scheduling_flow_match_euler_discrete.py:484-517) */
+int b200_euler_step(const void* model_output, const void* sample, void* prev_sample, int64_t n, float sigma,
+                    float sigma_next, int32_t dtype, void* stream);
+int b200_scale(const void* x, void* y, int64_t n, float divisor, int32_t dtype, void* stream);
+int b200_cfg_euler_step(const void* eps_nhwc, int32_t ld_eps, void* latents_nchw, void* next_in_nhwc, int32_t ld_in,
+                        int32_t batch, int32_t C, int32_t HW, float guidance_scale, int32_t do_cfg, float sigma,
+                        float sigma_next, int32_t dtype, void* stream);
+int b200_flow_match_step(const void* model_output, const void* sample, void* prev_sample, int64_t n, float sigma,
+                         float sigma_next, int32_t dtype, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * b200_attention — softmax(Q K^T * scale) V, no mask, no dropout (the only form the path uses),
+ * as one FlashAttention-style tcgen05/TMEM kernel fed by TMA.  q/k/v/o are [batch, seq, heads,
+ * head_dim] views given by row (token) and batch strides in elements; head h starts at column
+ * h*head_dim, so fused-QKV GEMM outputs are consumed in place.
+ * Replaces  F.scaled_dot_product_attention  models/attention_processor.py:2767 (AttnProcessor2_0,
+ *           self S_k = S_q and cross S_k = 77) and models/attention_dispatch.py:3678-3717
+ *           (_native_attention, the NATIVE backend FluxAttnProcessor dispatches to).
+ * head_dim 64 (SDXL) or 128 (Flux).  scale <= 0 selects 1/sqrt(head_dim).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  int32_t batch, heads, sq, sk, head_dim;
+  int64_t q_row_stride, q_batch_stride;
+  int64_t k_row_stride, k_batch_stride;
+  int64_t v_row_stride, v_batch_stride;
+  int64_t o_row_stride, o_batch_stride;
+  float scale;
+  int32_t dtype;
+  int32_t nq_override; /* 0 = auto; 1 | 2 = query tiles (of 128 rows) per CTA */
+} b200_attention_args;
+
+int b200_attention(const b200_attention_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

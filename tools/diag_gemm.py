@@ -141,6 +141,21 @@ if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--one":
         ok = run_case(sys.argv[2])
         sys.exit(0 if ok else 1)
+    if len(sys.argv) >= 2 and sys.argv[1] == "--inproc":
+        # one process for everything (fast); a CUDA error poisons the context, so stop at the first one
+        import traceback
+        summary = {}
+        for n in (sys.argv[2:] or list(CASES)):
+            try:
+                summary[n] = "PASS" if run_case(n) else "FAIL"
+            except Exception as e:  # noqa: BLE001
+                traceback.print_exc()
+                summary[n] = "ERROR " + str(e)[:200]
+                if "CUDA" in str(e) or "cuda" in str(e) or "launch" in str(e):
+                    break
+            print(f"[{summary[n][:5]}] {n}", flush=True)
+        print("SUMMARY", json.dumps(summary))
+        sys.exit(0)
     names = sys.argv[1:] or list(CASES)
     summary = {}
     for n in names:

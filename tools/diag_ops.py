@@ -1,0 +1,251 @@
+"""GPU diagnostic for the non-GEMM kernels (attention, norms, elementwise, scheduler steps).
+Each case runs in a fresh subprocess.  Usage: python tools/diag_ops.py [case ...]"""
+import json
+import math
+import os
+import subprocess
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+CASES = {
+    "attn_d64_1blk": dict(kind="attn", B=1, H=1, Sq=128, Sk=128, D=64),
+    "attn_d64_2blk": dict(kind="attn", B=1, H=2, Sq=128, Sk=256, D=64),
+    "attn_d64_nq2": dict(kind="attn", B=1, H=2, Sq=256, Sk=384, D=64, nq=2),
+    "attn_d64_sdxl": dict(kind="attn", B=2, H=20, Sq=1024, Sk=1024, D=64),
+    "attn_d64_4096": dict(kind="attn", B=2, H=10, Sq=4096, Sk=4096, D=64),
+    "attn_d64_cross": dict(kind="attn", B=2, H=20, Sq=1024, Sk=77, D=64, cross=True),
+    "attn_d64_ragged": dict(kind="attn", B=2, H=3, Sq=200, Sk=333, D=64),
+    "attn_d128_1blk": dict(kind="attn", B=1, H=1, Sq=128, Sk=128, D=128),
+    "attn_d128_flux": dict(kind="attn", B=1, H=24, Sq=4608, Sk=4608, D=128),
+    "attn_d128_nq1": dict(kind="attn", B=1, H=4, Sq=640, Sk=640, D=128, nq=1),
+    "attn_d64_fp16": dict(kind="attn", B=1, H=4, Sq=512, Sk=512, D=64, fp16=True),
+    "attn_bigvals": dict(kind="attn", B=1, H=2, Sq=256, Sk=1024, D=64, qscale=6.0),
+    "gn_small": dict(kind="gn", B=2, HW=64, C=64, G=32, silu=True),
+    "gn_320": dict(kind="gn", B=2, HW=16384, C=320, G=32, silu=True),
+    "gn_1280": dict(kind="gn", B=2, HW=1024, C=1280, G=32, silu=False, eps=1e-6),
+    "gn_cat": dict(kind="gn", B=2, HW=4096, C=640, C2=320, G=32, silu=True),
+    "gn_cat2560": dict(kind="gn", B=2, HW=1024, C=1280, C2=1280, G=32, silu=True),
+    "gn_offset": dict(kind="gn", B=1, HW=4096, C=128, G=32, silu=True, offset=50.0),
+    "gn_fp16": dict(kind="gn", B=2, HW=1000, C=96, G=32, silu=True, fp16=True),
+    "ln_1280": dict(kind="ln", rows=2048, C=1280, affine=True),
+    "ln_640": dict(kind="ln", rows=8192, C=640, affine=True),
+    "ln_3072_mod": dict(kind="ln", rows=4608, C=3072, affine=False, mod=True, eps=1e-6),
+    "ln_64": dict(kind="ln", rows=77, C=64, affine=True),
+    "small_linear": dict(kind="sl"),
+    "elementwise": dict(kind="ew"),
+    "steps": dict(kind="steps"),
+}
+
+
+def report(name, out, ref, tol_rel, tol_abs, extra=None):
+    import torch
+    o = out.float()
+    err = (o - ref).abs()
+    bad = err > (tol_rel * ref.abs() + tol_abs)
+    res = dict(case=name, shape=list(o.shape), max_abs=float(err.max()), ref_absmax=float(ref.abs().max()),
+               n_bad=int(bad.sum()), frac_bad=float(bad.float().mean()), nan=int(torch.isnan(o).sum()))
+    if res["n_bad"]:
+        flat = bad.reshape(bad.shape[0], -1) if bad.dim() > 1 else bad.reshape(1, -1)
+        res["n_bad_rows"] = int(flat.any(1).sum())
+        res["bad_rows_head"] = flat.any(1).nonzero().flatten()[:16].tolist()
+        i = bad.nonzero()[0].tolist()
+        res["first_bad"] = dict(idx=i, got=float(o[tuple(i)]), ref=float(ref[tuple(i)]))
+        res["corr"] = float(torch.corrcoef(torch.stack([o.flatten(), ref.flatten()]))[0, 1])
+    if extra:
+        res.update(extra)
+    print("RESULT " + json.dumps(res))
+    return res["n_bad"] == 0 and res["nan"] == 0
+
+
+def run_case(name):
+    import torch
+    import torch.nn.functional as F
+    from diffusers_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = CASES[name]
+    dt = torch.float16 if cfg.get("fp16") else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(4321)
+
+    def rnd(*shape, scale=1.0):
+        return (torch.randn(*shape, generator=g, device="cuda") * scale).to(dt)
+
+    kind = cfg["kind"]
+    if kind == "attn":
+        B, H, Sq, Sk, D = cfg["B"], cfg["H"], cfg["Sq"], cfg["Sk"], cfg["D"]
+        qs = cfg.get("qscale", 1.0)
+        if cfg.get("cross"):
+            q = rnd(B, Sq, H * D, scale=qs)
+            kv = rnd(B, Sk, 2 * H * D)
+            k, v = kv[:, :, :H * D], kv[:, :, H * D:]
+        else:
+            qkv = rnd(B, Sq, 3 * H * D)
+            q, k, v = qkv[:, :, :H * D] * qs, qkv[:, :, H * D:2 * H * D], qkv[:, :, 2 * H * D:]
+            q = q.to(dt)
+            if Sk != Sq:
+                kv = rnd(B, Sk, 2 * H * D)
+                k, v = kv[:, :, :H * D], kv[:, :, H * D:]
+        out = ops.attention(q, k, v, heads=H, head_dim=D, nq=cfg.get("nq", 0))
+        torch.cuda.synchronize()
+        qf = q.float().reshape(B, Sq, H, D).transpose(1, 2)
+        kf = k.float().reshape(B, Sk, H, D).transpose(1, 2)
+        vf = v.float().reshape(B, Sk, H, D).transpose(1, 2)
+        ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, Sq, H * D)
+        return report(name, out, ref, 2e-2, 6e-3 if dt == torch.bfloat16 else 1.5e-3)
+    if kind == "gn":
+        B, HW, Cc, G = cfg["B"], cfg["HW"], cfg["C"], cfg["G"]
+        C2 = cfg.get("C2", 0)
+        eps = cfg.get("eps", 1e-5)
+        off = cfg.get("offset", 0.0)
+        x = (torch.randn(B * HW, Cc, generator=g, device="cuda") * 1.5 + off).to(dt)
+        x2 = rnd(B * HW, C2) if C2 else None
+        gamma, beta = rnd(Cc + C2) + 1, rnd(Cc + C2)
+        out = ops.group_norm(x, batch=B, hw=HW, groups=G, eps=eps, gamma=gamma, beta=beta, silu=cfg["silu"], x2=x2)
+        out2 = ops.group_norm(x, batch=B, hw=HW, groups=G, eps=eps, gamma=gamma, beta=beta, silu=cfg["silu"], x2=x2)
+        torch.cuda.synchronize()
+        xx = torch.cat([x, x2], 1) if x2 is not None else x
+        xr = xx.float().reshape(B, HW, Cc + C2).permute(0, 2, 1)
+        ref = F.group_norm(xr, G, gamma.float(), beta.float(), eps)
+        if cfg["silu"]:
+            ref = F.silu(ref)
+        ref = ref.permute(0, 2, 1).reshape(B * HW, Cc + C2)
+        return report(name, out, ref, 1e-2, 1e-2 if dt == torch.bfloat16 else 2e-3,
+                      extra=dict(deterministic=bool(torch.equal(out, out2))))
+    if kind == "ln":
+        rows, Cc = cfg["rows"], cfg["C"]
+        eps = cfg.get("eps", 1e-5)
+        x = rnd(rows, Cc, scale=2.0)
+        gamma = rnd(Cc) + 1 if cfg.get("affine") else None
+        beta = rnd(Cc) if cfg.get("affine") else None
+        scale = shift = None
+        rpg = 0
+        if cfg.get("mod"):
+            ngrp = 2
+            rpg = rows // ngrp
+            mod = rnd(ngrp, 2 * Cc)
+            shift, scale = mod[:, :Cc], mod[:, Cc:]
+        out = ops.layer_norm(x, eps=eps, gamma=gamma, beta=beta, scale=scale, shift=shift, rows_per_group=rpg)
+        torch.cuda.synchronize()
+        ref = F.layer_norm(x.float(), (Cc,), gamma.float() if gamma is not None else None,
+                           beta.float() if beta is not None else None, eps)
+        if scale is not None:
+            ref = ref * (1 + scale.float().repeat_interleave(rpg, 0)) + shift.float().repeat_interleave(rpg, 0)
+        return report(name, out, ref, 1e-2, 1e-2)
+    if kind == "sl":
+        ok = True
+        for (M, K, N, ai, ao, add) in [(2, 320, 1280, 0, 1, False), (2, 1280, 1280, 0, 0, True), (2, 1280, 640, 1, 0, False),
+                                       (8, 2816, 1280, 0, 1, False), (1, 3072, 18432, 1, 0, False), (11, 256, 64, 0, 3, False)]:
+            x, w, b = rnd(M, K), rnd(N, K, scale=K ** -0.5), rnd(N)
+            addend = rnd(M, N) if add else None
+            out = ops.small_linear(x, w, bias=b, act_in=ai, act_out=ao, addend=addend)
+            torch.cuda.synchronize()
+            xi = F.silu(x.float()).to(dt).float() if ai == 1 else x.float()
+            ref = xi @ w.float().t() + b.float()
+            ref = F.silu(ref) if ao == 1 else (F.gelu(ref, approximate="tanh") if ao == 3 else ref)
+            if add:
+                ref = ref + addend.float()
+            ok &= report(f"{name}_{M}x{K}x{N}", out, ref, 1e-2, 1e-2)
+        return ok
+    if kind == "ew":
+        ok = True
+        x = rnd(2, 4, 16, 24)
+        o = ops.nchw_to_nhwc(x, c_pad=8)
+        ref = F.pad(x.permute(0, 2, 3, 1).reshape(-1, 4), (0, 4)).float()
+        ok &= report("nchw_to_nhwc", o, ref, 0, 0)
+        y = rnd(2 * 16 * 24, 8)
+        o = ops.nhwc_to_nchw(y, batch=2, C_out=4, H=16, W=24)
+        ref = y[:, :4].reshape(2, 16, 24, 4).permute(0, 3, 1, 2).float()
+        ok &= report("nhwc_to_nchw", o, ref, 0, 0)
+        z = rnd(2 * 8 * 12, 64)
+        o = ops.upsample_nearest2x(z, batch=2, H=8, W=12)
+        ref = F.interpolate(z.reshape(2, 8, 12, 64).permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest")
+        ref = ref.permute(0, 2, 3, 1).reshape(-1, 64)
+        ok &= report("upsample", o, ref, 0, 0)
+        t = torch.tensor([981.0, 1.0, 500.5, 0.0371], device="cuda")
+        for dim, flip, shift in [(320, True, 0.0), (256, True, 0.0), (256, True, 1.0), (32, False, 1.0)]:
+            o = ops.timestep_embedding(t, dim, dtype=dt, flip_sin_to_cos=flip, downscale_freq_shift=shift)
+            half = dim // 2
+            ex = -math.log(10000) * torch.arange(half, dtype=torch.float32, device="cuda") / (half - shift)
+            e = t[:, None] * torch.exp(ex)[None]
+            e = torch.cat([torch.sin(e), torch.cos(e)], -1)
+            if flip:
+                e = torch.cat([e[:, half:], e[:, :half]], -1)
+            ok &= report(f"temb_{dim}", o, e.to(dt).float(), 0, 8e-3)
+        return ok
+    if kind == "steps":
+        ok = True
+        eps = rnd(2, 4, 32, 32)
+        x = rnd(1, 4, 32, 32, scale=10.0)
+        sigma, sigma_next = 14.6146, 11.2333
+        s32 = torch.tensor(sigma, dtype=torch.float32)
+        sn32 = torch.tensor(sigma_next, dtype=torch.float32)
+
+        def ref_euler(e, xx):
+            smp = xx.to(torch.float32)
+            pred = smp - (s32.item() * e.float()).to(dt).float()
+            der = (smp - pred) / s32.item()
+            return (smp + der * (sn32 - s32).item()).to(dt)
+        o = ops.euler_step(eps[:1], x, float(s32), float(sn32))
+        ok &= report("euler_step", o, ref_euler(eps[:1], x).float(), 0, 0)
+        # fused cfg step
+        gs = 7.5
+        eps_nhwc = F.pad(eps.permute(0, 2, 3, 1).reshape(-1, 4), (0, 4)).contiguous()
+        lat = x.clone()
+        nxt = torch.empty(2 * 32 * 32, 8, dtype=dt, device="cuda")
+        ops.cfg_euler_step(eps_nhwc, lat, nxt, guidance_scale=gs, do_cfg=True, sigma=float(s32), sigma_next=float(sn32))
+        e_u, e_c = eps[:1], eps[1:]
+        guided = e_u + gs * (e_c - e_u)
+        ref_lat = ref_euler(guided, x)
+        ok &= report("cfg_step_latents", lat, ref_lat.float(), 0, 0)
+        div = float((sn32 ** 2 + 1) ** 0.5)
+        ref_in = (torch.cat([ref_lat] * 2) / div)
+        ref_in = F.pad(ref_in.permute(0, 2, 3, 1).reshape(-1, 4), (0, 4)).float()
+        ok &= report("cfg_step_next_in", nxt, ref_in, 0, 0)
+        o = ops.scale_div(x, div)
+        ok &= report("scale", o, (x / div).float(), 0, 0)
+        v = rnd(1, 4096, 64)
+        xs = rnd(1, 4096, 64)
+        sg, sgn = torch.tensor(0.9, dtype=torch.float32), torch.tensor(0.85, dtype=torch.float32)
+        o = ops.flow_match_step(v, xs, float(sg), float(sgn))
+        dtt = (sgn - sg).to("cuda")
+        ref = (xs.to(torch.float32) + dtt * v).to(dt)
+        ok &= report("flow_match_step", o, ref.float(), 0, 0)
+        return ok
+    raise KeyError(name)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--one":
+        sys.exit(0 if run_case(sys.argv[2]) else 1)
+    if len(sys.argv) >= 2 and sys.argv[1] == "--inproc":
+        # one process for everything (fast); a CUDA error poisons the context, so stop at the first one
+        import traceback
+        summary = {}
+        for n in (sys.argv[2:] or list(CASES)):
+            try:
+                summary[n] = "PASS" if run_case(n) else "FAIL"
+            except Exception as e:  # noqa: BLE001
+                traceback.print_exc()
+                summary[n] = "ERROR " + str(e)[:200]
+                if "CUDA" in str(e) or "cuda" in str(e) or "launch" in str(e):
+                    break
+            print(f"[{summary[n][:5]}] {n}", flush=True)
+        print("SUMMARY", json.dumps(summary))
+        sys.exit(0)
+    names = sys.argv[1:] or list(CASES)
+    summary = {}
+    for n in names:
+        try:
+            p = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=240)
+            out = p.stdout + p.stderr
+            lines = [l for l in out.splitlines() if l.startswith("RESULT ")]
+            status = "PASS" if p.returncode == 0 else "FAIL"
+            print(f"[{status}] {n}: " + (" | ".join(l[7:] for l in lines) if lines else out[-1500:]), flush=True)
+            if status == "FAIL" and lines:
+                print("   stderr tail:", out[-600:].replace("\n", " / "), flush=True)
+            summary[n] = status
+        except subprocess.TimeoutExpired:
+            print(f"[TIMEOUT] {n}", flush=True)
+            summary[n] = "TIMEOUT"
+    print("SUMMARY", json.dumps(summary))
