@@ -1,0 +1,190 @@
+"""Drop-in AutoencoderKL (decode side) on libb200diff.so.
+
+`decode(z, return_dict=False) -> (image,)`, `.config` (block_out_channels, scaling_factor, shift_factor,
+force_upcast, latents_mean/std), `.dtype`, `.post_quant_conv` - what the SDXL / Flux pipelines touch
+(pipeline_stable_diffusion_xl.py:1262-1287, pipeline_flux.py:959-961).  Reference: models/autoencoders/
+autoencoder_kl.py:199-233, autoencoders/vae.py:180-310.  Encode / tiling / slicing are outside the text->image path.
+
+NHWC activations; GroupNorm+SiLU is one fused pass feeding the implicit-GEMM conv; the single head_dim-512
+attention of the mid block runs unfused (see ops.attention_unfused).
+"""
+import types
+
+import torch
+
+from . import ops, packing, specs
+from .config import FrozenConfig
+
+
+class DecoderOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+
+class AutoencoderKL(torch.nn.Module):
+    def __init__(self, config, state_dict, dtype=torch.bfloat16, device="cuda"):
+        super().__init__()
+        cfg = dict(specs.SDXL_VAE_CONFIG)
+        cfg.update(config)
+        self.config = FrozenConfig(cfg)
+        self._dtype = dtype
+        self._n = 0
+        spec = specs.vae_decoder_params(cfg)
+        for k, shp in spec.items():
+            if k not in state_dict:
+                raise ValueError(f"state_dict is missing {k}")
+            if tuple(state_dict[k].shape) != tuple(shp):
+                raise ValueError(f"{k}: expected shape {tuple(shp)}, got {tuple(state_dict[k].shape)}")
+        self._build(state_dict, torch.device(device))
+        self.use_slicing = False
+        self.use_tiling = False
+        # the SDXL pipeline only reads post_quant_conv.parameters() to pick a dtype when up-casting fp16 VAEs
+        self.post_quant_conv = types.SimpleNamespace(parameters=lambda: iter([self._buffers["w0"]]))
+
+    def _reg(self, t, device):
+        name = f"w{self._n}"
+        self._n += 1
+        self.register_buffer(name, t.to(device=device, dtype=self._dtype).contiguous(), persistent=False)
+        return name
+
+    def W(self, name):
+        return self._buffers[name]
+
+    def _build(self, sd, device):
+        cfg = self.config
+        R = lambda t: self._reg(t, device)  # noqa: E731
+        g = lambda k: sd[k].to(torch.float32)  # noqa: E731
+        lc = cfg["latent_channels"]
+        self.lat_pad = packing.rup(lc, 8)
+
+        def conv(p, pad_in=None, ks=None):
+            w = g(p + ".weight")
+            if pad_in is not None and w.shape[1] < pad_in:
+                w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, pad_in - w.shape[1]))
+            return dict(w=R(packing.pack_conv_weight(w)), b=R(g(p + ".bias")), n=w.shape[0], k=w.shape[-1])
+
+        def resnet(p):
+            r = dict(n1w=R(g(p + ".norm1.weight")), n1b=R(g(p + ".norm1.bias")), c1=conv(p + ".conv1"),
+                     n2w=R(g(p + ".norm2.weight")), n2b=R(g(p + ".norm2.bias")), c2=conv(p + ".conv2"))
+            if (p + ".conv_shortcut.weight") in sd:
+                r["sc"] = conv(p + ".conv_shortcut")
+            return r
+
+        self.pq = conv("post_quant_conv", pad_in=self.lat_pad) if "post_quant_conv.weight" in sd else None
+        d = "decoder"
+        self.conv_in = conv(d + ".conv_in", pad_in=self.lat_pad)
+        self.mid_res = [resnet(d + ".mid_block.resnets.0"), resnet(d + ".mid_block.resnets.1")]
+        self.mid_attn = None
+        a = d + ".mid_block.attentions.0"
+        if (a + ".to_q.weight") in sd:
+            C = sd[a + ".to_q.weight"].shape[0]
+            qkv_w = torch.cat([g(a + ".to_q.weight"), g(a + ".to_k.weight"), g(a + ".to_v.weight")], 0)
+            qkv_b = torch.cat([g(a + ".to_q.bias"), g(a + ".to_k.bias"), g(a + ".to_v.bias")], 0)
+            self.mid_attn = dict(C=C, gw=R(g(a + ".group_norm.weight")), gb=R(g(a + ".group_norm.bias")),
+                                 qkv=R(packing.pack_linear_weight(qkv_w)), qkvb=R(qkv_b),
+                                 ow=R(packing.pack_linear_weight(g(a + ".to_out.0.weight"))), ob=R(g(a + ".to_out.0.bias")))
+        self.up = []
+        i = 0
+        while f"{d}.up_blocks.{i}.resnets.0.norm1.weight" in sd:
+            p = f"{d}.up_blocks.{i}"
+            blk = dict(res=[], up=None)
+            j = 0
+            while f"{p}.resnets.{j}.norm1.weight" in sd:
+                blk["res"].append(resnet(f"{p}.resnets.{j}"))
+                j += 1
+            if f"{p}.upsamplers.0.conv.weight" in sd:
+                blk["up"] = conv(f"{p}.upsamplers.0.conv")
+            self.up.append(blk)
+            i += 1
+        self.norm_out = dict(w=R(g(d + ".conv_norm_out.weight")), b=R(g(d + ".conv_norm_out.bias")))
+        self.conv_out = conv(d + ".conv_out")
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def device(self):
+        return self._buffers["w0"].device
+
+    @classmethod
+    def random_init(cls, config=None, seed=0, dtype=torch.bfloat16, device="cuda"):
+        cfg = dict(specs.SDXL_VAE_CONFIG)
+        cfg.update(config or {})
+        sd = specs.random_state_dict(specs.vae_decoder_params(cfg), seed=seed, dtype=dtype)
+        return cls(cfg, sd, dtype=dtype, device=device)
+
+    # ------------------------------------------------------------------
+    def _conv(self, c, x, B, H, W, residual=None, out=None):
+        return ops.conv_gemm(x, self.W(c["w"]), c["n"], batch=B, H=H, W=W, ksize=c["k"], bias=self.W(c["b"]),
+                             residual=residual, out=out)
+
+    def _gn(self, x, w, b, B, hw, silu):
+        return ops.group_norm(x, batch=B, hw=hw, groups=self.config["norm_num_groups"], eps=1e-6, gamma=self.W(w),
+                              beta=self.W(b), silu=silu)
+
+    def _resnet(self, r, x, B, H, W):
+        n1 = self._gn(x, r["n1w"], r["n1b"], B, H * W, True)
+        h = self._conv(r["c1"], n1, B, H, W)
+        n2 = self._gn(h, r["n2w"], r["n2b"], B, H * W, True)
+        sc = self._conv(r["sc"], x, B, H, W) if "sc" in r else x
+        return self._conv(r["c2"], n2, B, H, W, residual=sc)
+
+    def _attention(self, a, x, B, H, W):
+        hw, C = H * W, a["C"]
+        n = self._gn(x, a["gw"], a["gb"], B, hw, False)
+        qkv = ops.linear(n, self.W(a["qkv"]), 3 * C, bias=self.W(a["qkvb"]))
+        if C in (64, 128):
+            q3 = qkv.view(B, hw, 3 * C)
+            o = ops.attention(q3[:, :, :C], q3[:, :, C:2 * C], q3[:, :, 2 * C:], heads=1, head_dim=C).view(B * hw, C)
+        else:
+            o = torch.empty((B * hw, C), dtype=x.dtype, device=x.device)
+            for b in range(B):
+                rows = qkv[b * hw:(b + 1) * hw]
+                o[b * hw:(b + 1) * hw] = ops.attention_unfused(rows[:, :C], rows[:, C:2 * C], rows[:, 2 * C:],
+                                                              scale=C ** -0.5)
+        return ops.linear(o, self.W(a["ow"]), C, bias=self.W(a["ob"]), residual=x)
+
+    def _decode_nhwc(self, z_nhwc, B, H, W):
+        x = z_nhwc
+        if self.pq is not None:
+            y = torch.zeros((B * H * W, self.lat_pad), dtype=self._dtype, device=x.device)
+            x = self._conv(self.pq, x, B, H, W, out=y)
+        x = self._conv(self.conv_in, x, B, H, W)
+        x = self._resnet(self.mid_res[0], x, B, H, W)
+        if self.mid_attn is not None:
+            x = self._attention(self.mid_attn, x, B, H, W)
+        x = self._resnet(self.mid_res[1], x, B, H, W)
+        for blk in self.up:
+            for r in blk["res"]:
+                x = self._resnet(r, x, B, H, W)
+            if blk["up"] is not None:
+                xu = ops.upsample_nearest2x(x, batch=B, H=H, W=W)
+                H, W = 2 * H, 2 * W
+                x = self._conv(blk["up"], xu, B, H, W)
+        n = self._gn(x, self.norm_out["w"], self.norm_out["b"], B, H * W, True)
+        y = self._conv(self.conv_out, n, B, H, W)
+        return y, H, W
+
+    @torch.no_grad()
+    def decode(self, z, return_dict=True, generator=None, max_batch=None):
+        if not z.is_cuda:
+            raise ops.B200Error("AutoencoderKL (B200) needs CUDA tensors: there is no CPU fallback")
+        z = z.to(self._dtype)
+        B, C, H, W = z.shape
+        # 1024^2 activations are 268 MB per 128-channel tensor per image: decode in sub-batches (HBM footprint)
+        mb = max_batch or max(1, min(B, (8 * 128 * 128) // (H * W) or 1))
+        outs = []
+        for b0 in range(0, B, mb):
+            zb = z[b0:b0 + mb]
+            nb = zb.shape[0]
+            x = ops.nchw_to_nhwc(zb, c_pad=self.lat_pad)
+            y, Ho, Wo = self._decode_nhwc(x, nb, H, W)
+            outs.append(ops.nhwc_to_nchw(y, batch=nb, C_out=self.config["out_channels"], H=Ho, W=Wo))
+        out = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        if not return_dict:
+            return (out,)
+        return DecoderOutput(out)
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("only decode() is on the accelerated path")

@@ -38,6 +38,7 @@ struct ConvGemmParams {
   void* y;
   int ld_gate, ld_rowvec, ldr, ldy, rows_per_group, act;
   int vec_ok;  // y / residual / gate / rowvec / bias allow 16-byte accesses
+  int out_fp32;  // y is float (used for attention scores of the unfused head_dim-512 path)
 };
 
 template <int BN>
@@ -278,7 +279,17 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
               }
             }
           }
-          if (valid) {
+          if (valid && p.out_fp32) {
+            float* yf = reinterpret_cast<float*>(p.y) + pix * p.ldy + yc;
+            if (full8) {
+              *reinterpret_cast<float4*>(yf) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(yf + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (yc + j < n_limit) yf[j] = f[j];
+            }
+          } else if (valid) {
             if (full8) {
               uint4 o;
               o.x = H::pack(f[0], f[1]);
@@ -525,6 +536,7 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   if (a->rowvec) vec = vec && aligned16(a->rowvec) && (a->ld_rowvec % 8 == 0);
   if (a->residual) vec = vec && aligned16(a->residual) && (a->ldr % 8 == 0);
   prm.vec_ok = vec ? 1 : 0;
+  prm.out_fp32 = a->out_fp32 ? 1 : 0;
 
   const int grid = prm.total_tiles < num_sms() ? prm.total_tiles : num_sms();
   cudaStream_t st = static_cast<cudaStream_t>(stream);

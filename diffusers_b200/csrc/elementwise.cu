@@ -229,7 +229,8 @@ __global__ void cfg_euler_step_kernel(const void* eps_, int ld_eps, void* latent
   if (do_cfg) nin[i + total] = o;
 }
 
-// prev = r16(float(x) + r16(dt * v))
+// prev = r16(float(x) + r16(r16(dt) * v)).  dt = sigmas[i+1] - sigmas[i] is a 0-dim DEVICE tensor in the
+// reference, so eager CUDA casts it to the 16-bit common dtype before the multiply.
 template <bool FP16>
 __global__ void flow_match_step_kernel(const void* v_, const void* sample_, void* prev_, long long n, float dt) {
   using H = Half16<FP16>;
@@ -238,7 +239,7 @@ __global__ void flow_match_step_kernel(const void* v_, const void* sample_, void
   typename H::T* prev = static_cast<typename H::T*>(prev_);
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float m = r16<FP16>(__fmul_rn(dt, H::to_float(v[i])));
+  const float m = r16<FP16>(__fmul_rn(r16<FP16>(dt), H::to_float(v[i])));
   prev[i] = H::from_float(__fadd_rn(H::to_float(sample[i]), m));
 }
 
@@ -251,6 +252,77 @@ __global__ void scale_kernel(const void* x_, void* y_, long long n, float div) {
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   y[i] = H::from_float(__fdiv_rn(H::to_float(x[i]), div));
+}
+
+// ------------------------------------------------------------------------------------------------
+// row softmax fp32 -> 16 bit (one CTA per row) and 16-bit transpose (32x32 tiles through smem)
+// ------------------------------------------------------------------------------------------------
+template <bool FP16>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, long long ld_s, void* p_,
+                                                           long long ld_p, int cols, float scale_log2) {
+  using H = Half16<FP16>;
+  __shared__ float red[8];
+  const float* row = s + static_cast<long long>(blockIdx.x) * ld_s;
+  typename H::T* prow = static_cast<typename H::T*>(p_) + static_cast<long long>(blockIdx.x) * ld_p;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+    if (c + 4 <= cols) {
+      float4 v = *reinterpret_cast<const float4*>(row + c);
+      mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    } else {
+      for (int j = c; j < cols; ++j) mx = fmaxf(mx, row[j]);
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  const float m2 = mx * scale_log2;
+  float sum = 0.f;
+  for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+    if (c + 4 <= cols) {
+      float4 v = *reinterpret_cast<const float4*>(row + c);
+      sum += exp2f(fmaf(v.x, scale_log2, -m2)) + exp2f(fmaf(v.y, scale_log2, -m2)) +
+             exp2f(fmaf(v.z, scale_log2, -m2)) + exp2f(fmaf(v.w, scale_log2, -m2));
+    } else {
+      for (int j = c; j < cols; ++j) sum += exp2f(fmaf(row[j], scale_log2, -m2));
+    }
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) sum += red[w];
+  const float inv = 1.0f / sum;
+  for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+    if (c + 4 <= cols) {
+      float4 v = *reinterpret_cast<const float4*>(row + c);
+      uint2 o;
+      o.x = H::pack(exp2f(fmaf(v.x, scale_log2, -m2)) * inv, exp2f(fmaf(v.y, scale_log2, -m2)) * inv);
+      o.y = H::pack(exp2f(fmaf(v.z, scale_log2, -m2)) * inv, exp2f(fmaf(v.w, scale_log2, -m2)) * inv);
+      *reinterpret_cast<uint2*>(prow + c) = o;
+    } else {
+      for (int j = c; j < cols; ++j) prow[j] = H::from_float(exp2f(fmaf(row[j], scale_log2, -m2)) * inv);
+    }
+  }
+}
+
+__global__ void transpose16_kernel(const uint16_t* __restrict__ src, long long ld_src, uint16_t* __restrict__ dst,
+                                   long long ld_dst, int rows, int cols) {
+  __shared__ uint16_t tile[32][34];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = src[static_cast<long long>(r) * ld_src + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[static_cast<long long>(c) * ld_dst + r] = tile[threadIdx.x][i];
+  }
 }
 
 static inline unsigned int blocks_for(long long n, int threads) {
@@ -395,6 +467,31 @@ int b200_scale(const void* x, void* y, int64_t n, float divisor, int32_t dtype, 
   else
     scale_kernel<false><<<blocks_for(n, 256), 256, 0, st>>>(x, y, n, divisor);
   return check_launch("scale_kernel");
+}
+
+int b200_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t ld_p, int32_t rows, int32_t cols, float scale,
+                      int32_t dtype, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(s && p && rows > 0 && cols > 0, "softmax_rows: bad args");
+  B200_CHECK_ARG(ld_s % 4 == 0 && ld_p % 4 == 0 && aligned16(s) && (reinterpret_cast<uintptr_t>(p) & 7u) == 0,
+                 "softmax_rows: strides must be multiples of 4 elements, s 16-byte / p 8-byte aligned");
+  const float sl2 = scale * 1.4426950408889634f;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200_DTYPE_FP16)
+    softmax_rows_kernel<true><<<rows, 256, 0, st>>>(s, ld_s, p, ld_p, cols, sl2);
+  else
+    softmax_rows_kernel<false><<<rows, 256, 0, st>>>(s, ld_s, p, ld_p, cols, sl2);
+  return check_launch("softmax_rows_kernel");
+}
+
+int b200_transpose_16(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols,
+                      void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(src && dst && rows > 0 && cols > 0, "transpose_16: bad args");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(src), ld_src, static_cast<uint16_t*>(dst), ld_dst, rows, cols);
+  return check_launch("transpose16_kernel");
 }
 
 }  // extern "C"

@@ -43,7 +43,7 @@ def _need_cuda(t, name):
 
 
 def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, act=ACT_NONE, geglu=False,
-              gate=None, rowvec=None, rows_per_group=0, residual=None, out=None, tile_n=0):
+              gate=None, rowvec=None, rows_per_group=0, residual=None, out=None, tile_n=0, out_fp32=False):
     """y = epilogue(conv/linear(x [, x2]))  -  see b200_conv_gemm in include/b200_diffusion.h.
 
     x, x2: NHWC activations given as 2-D [batch*H*W, C] (or any shape whose last dim is C, contiguous rows).
@@ -54,7 +54,7 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
     Ho, Wo = (H, W) if stride == 1 else (H // 2, W // 2)
     n_out = N // 2 if geglu else N
     if out is None:
-        out = torch.empty((batch * Ho * Wo, n_out), dtype=x.dtype, device=x.device)
+        out = torch.empty((batch * Ho * Wo, n_out), dtype=torch.float32 if out_fp32 else x.dtype, device=x.device)
     a = _lib.ConvGemmArgs()
     a.x[0] = x.data_ptr()
     a.x[1] = _ptr(x2)
@@ -75,18 +75,19 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
     a.y, a.ldy = out.data_ptr(), out.stride(-2)
     a.dtype = _dtype_code(x)
     a.tile_n = tile_n
+    a.out_fp32 = 1 if out_fp32 else 0
     _lib.check(_lib.lib().b200_conv_gemm(C.byref(a), _stream()), "b200_conv_gemm")
     _count()
     return out
 
 
 def linear(x, w, N, *, bias=None, act=ACT_NONE, geglu=False, gate=None, rowvec=None, rows_per_group=0,
-           residual=None, x2=None, out=None, tile_n=0):
+           residual=None, x2=None, out=None, tile_n=0, out_fp32=False):
     """nn.Linear on token rows: x [rows, K] (row stride arbitrary multiple of 8)."""
     rows = x.shape[0]
     return conv_gemm(x, w, N, batch=1, H=1, W=rows, ksize=1, stride=1, x2=x2, bias=bias, act=act, geglu=geglu,
                      gate=gate, rowvec=rowvec, rows_per_group=rows_per_group, residual=residual, out=out,
-                     tile_n=tile_n)
+                     tile_n=tile_n, out_fp32=out_fp32)
 
 
 def pick_tile_n(M, N, geglu=False):
@@ -304,3 +305,42 @@ def flow_match_step(model_output, sample, sigma, sigma_next, out=None):
                "b200_flow_match_step")
     _count()
     return out
+
+
+def softmax_rows(s, scale, dtype, out=None):
+    """softmax(s * scale) over the last dim: s fp32 [rows, cols] -> 16-bit [rows, cols]."""
+    _need_cuda(s, "s")
+    rows, cols = s.shape
+    if out is None:
+        out = torch.empty((rows, cols), dtype=dtype, device=s.device)
+    _lib.check(_lib.lib().b200_softmax_rows(C.c_void_p(s.data_ptr()), s.stride(0), C.c_void_p(out.data_ptr()),
+                                            out.stride(0), rows, cols, C.c_float(scale), _dtype_code(out), _stream()),
+               "b200_softmax_rows")
+    _count()
+    return out
+
+
+def transpose_16(x, out=None):
+    """[R, C] 16-bit -> [C, R]."""
+    _need_cuda(x, "x")
+    R_, C_ = x.shape
+    if out is None:
+        out = torch.empty((C_, R_), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().b200_transpose_16(C.c_void_p(x.data_ptr()), x.stride(0), C.c_void_p(out.data_ptr()),
+                                            out.stride(0), R_, C_, _stream()), "b200_transpose_16")
+    _count()
+    return out
+
+
+def attention_unfused(q, k, v, *, scale):
+    """Single-head attention for head dims the fused kernel does not cover (AutoencoderKL: 512).
+    q [Sq, D], k/v [Sk, D] (row strides arbitrary multiples of 8) -> [Sq, D]."""
+    Sq, D = q.shape
+    Sk = k.shape[0]
+    s = linear(q, k, Sk, out_fp32=True) if k.stride(0) == D and D % 64 == 0 else None
+    if s is None:
+        kc = k.contiguous()
+        s = linear(q, kc, Sk, out_fp32=True)
+    p = softmax_rows(s, scale, q.dtype)
+    vt = transpose_16(v)  # [D, Sk]: K-major "weights" for the P @ V GEMM
+    return linear(p, vt, D)

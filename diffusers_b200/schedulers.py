@@ -1,0 +1,248 @@
+"""Drop-in schedulers for the hot path: the host-side schedule construction repeats the reference's
+numpy/torch arithmetic op for op (so sigmas/timesteps are bit-identical), `step()` / `scale_model_input()` launch
+one fused sm_100a kernel each (ops.euler_step, ops.scale_div, ops.flow_match_step).
+
+Reference: schedulers/scheduling_euler_discrete.py:143 (EulerDiscreteScheduler: __init__ :203, set_timesteps :350,
+scale_model_input :326, step :685), schedulers/scheduling_flow_match_euler_discrete.py:48
+(FlowMatchEulerDiscreteScheduler: set_timesteps :283, step :423, time_shift :241).  Only the configuration space the
+SDXL / Flux pipelines use is accepted; anything else raises.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .config import FrozenConfig
+
+
+class SchedulerOutput:
+    def __init__(self, prev_sample, pred_original_sample=None):
+        self.prev_sample = prev_sample
+        self.pred_original_sample = pred_original_sample
+
+
+class EulerDiscreteScheduler:
+    order = 1
+    init_noise_sigma_is_tensor = True
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                 prediction_type="epsilon", interpolation_type="linear", timestep_spacing="linspace", steps_offset=0,
+                 final_sigmas_type="zero", **unsupported):
+        for k, v in unsupported.items():
+            if v not in (None, False, "discrete"):
+                raise NotImplementedError(f"EulerDiscreteScheduler option {k}={v!r} is outside the hot path")
+        if prediction_type != "epsilon":
+            raise NotImplementedError("only prediction_type='epsilon'")
+        if interpolation_type != "linear" or final_sigmas_type != "zero":
+            raise NotImplementedError("only linear interpolation with a final sigma of zero")
+        self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+                                   beta_schedule=beta_schedule, prediction_type=prediction_type,
+                                   interpolation_type=interpolation_type, timestep_spacing=timestep_spacing,
+                                   steps_offset=steps_offset, final_sigmas_type=final_sigmas_type, use_karras_sigmas=False,
+                                   timestep_type="discrete")
+        if beta_schedule == "linear":
+            self.betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        elif beta_schedule == "scaled_linear":
+            self.betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        else:
+            raise NotImplementedError(beta_schedule)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        sigmas = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).flip(0)
+        timesteps = np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=float)[::-1].copy()
+        self.timesteps = torch.from_numpy(timesteps).to(dtype=torch.float32)
+        self.sigmas = torch.cat([sigmas, torch.zeros(1)]).to("cpu")
+        self.num_inference_steps = None
+        self.is_scale_input_called = False
+        self._step_index = None
+        self._begin_index = None
+        self._timesteps_cpu = self.timesteps.clone()
+
+    @property
+    def init_noise_sigma(self):
+        max_sigma = self.sigmas.max()
+        if self.config.timestep_spacing in ("linspace", "trailing"):
+            return max_sigma
+        return (max_sigma ** 2 + 1) ** 0.5
+
+    @property
+    def step_index(self):
+        return self._step_index
+
+    @property
+    def begin_index(self):
+        return self._begin_index
+
+    def set_begin_index(self, begin_index=0):
+        self._begin_index = begin_index
+
+    def set_timesteps(self, num_inference_steps=None, device=None, timesteps=None, sigmas=None):
+        if timesteps is not None or sigmas is not None:
+            raise NotImplementedError("custom timesteps / sigmas")
+        c = self.config
+        self.num_inference_steps = num_inference_steps
+        if c.timestep_spacing == "linspace":
+            ts = np.linspace(0, c.num_train_timesteps - 1, num_inference_steps, dtype=np.float32)[::-1].copy()
+        elif c.timestep_spacing == "leading":
+            step_ratio = c.num_train_timesteps // num_inference_steps
+            ts = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.float32)
+            ts += c.steps_offset
+        elif c.timestep_spacing == "trailing":
+            step_ratio = c.num_train_timesteps / num_inference_steps
+            ts = (np.arange(c.num_train_timesteps, 0, -step_ratio)).round().copy().astype(np.float32)
+            ts -= 1
+        else:
+            raise ValueError(c.timestep_spacing)
+        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        sig = np.concatenate([sig, [0]]).astype(np.float32)
+        self.sigmas = torch.from_numpy(sig).to(dtype=torch.float32)  # stays on the host, like the reference (:481)
+        self._timesteps_cpu = torch.from_numpy(ts.astype(np.float32))
+        self.timesteps = self._timesteps_cpu.to(device=device)
+        self._step_index = None
+        self._begin_index = None
+
+    def _init_step_index(self, timestep):
+        if self._begin_index is None:
+            t = float(timestep)  # device->host sync, as in the reference when set_begin_index was not called
+            idx = (self._timesteps_cpu == t).nonzero()
+            pos = 1 if len(idx) > 1 else 0
+            self._step_index = int(idx[pos])
+        else:
+            self._step_index = self._begin_index
+
+    def scale_model_input(self, sample, timestep):
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        sigma = self.sigmas[self._step_index]
+        div = float((sigma ** 2 + 1) ** 0.5)
+        self.is_scale_input_called = True
+        return ops.scale_div(sample, div)
+
+    def step(self, model_output, timestep, sample, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0,
+             generator=None, return_dict=True):
+        if isinstance(timestep, (int, torch.IntTensor, torch.LongTensor)):
+            raise ValueError("Passing integer indices as timesteps to EulerDiscreteScheduler.step() is not supported.")
+        if s_churn != 0.0:
+            raise NotImplementedError("s_churn > 0 (stochastic sampling) is outside the hot path")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        sigma = float(self.sigmas[self._step_index])
+        sigma_next = float(self.sigmas[self._step_index + 1])
+        prev = ops.euler_step(model_output, sample, sigma, sigma_next)
+        self._step_index += 1
+        if not return_dict:
+            return (prev, None)
+        return SchedulerOutput(prev)
+
+    def __len__(self):
+        return self.config.num_train_timesteps
+
+
+class FlowMatchEulerDiscreteScheduler:
+    order = 1
+
+    def __init__(self, num_train_timesteps=1000, shift=1.0, use_dynamic_shifting=False, base_shift=0.5, max_shift=1.15,
+                 base_image_seq_len=256, max_image_seq_len=4096, time_shift_type="exponential", **unsupported):
+        for k, v in unsupported.items():
+            if v not in (None, False):
+                raise NotImplementedError(f"FlowMatchEulerDiscreteScheduler option {k}={v!r} is outside the hot path")
+        if time_shift_type != "exponential":
+            raise NotImplementedError("only exponential time shift")
+        self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, shift=shift,
+                                   use_dynamic_shifting=use_dynamic_shifting, base_shift=base_shift, max_shift=max_shift,
+                                   base_image_seq_len=base_image_seq_len, max_image_seq_len=max_image_seq_len,
+                                   time_shift_type=time_shift_type, invert_sigmas=False, shift_terminal=None,
+                                   stochastic_sampling=False)
+        timesteps = np.linspace(1, num_train_timesteps, num_train_timesteps, dtype=np.float32)[::-1].copy()
+        timesteps = torch.from_numpy(timesteps).to(dtype=torch.float32)
+        sigmas = timesteps / num_train_timesteps
+        if not use_dynamic_shifting:
+            sigmas = shift * sigmas / (1 + (shift - 1) * sigmas)
+        self.timesteps = sigmas * num_train_timesteps
+        self._shift = shift
+        self.sigmas = sigmas.to("cpu")
+        self.sigma_min = self.sigmas[-1].item()
+        self.sigma_max = self.sigmas[0].item()
+        self._sigmas_cpu = self.sigmas
+        self._timesteps_cpu = self.timesteps
+        self._step_index = None
+        self._begin_index = None
+        self.num_inference_steps = None
+
+    init_noise_sigma = 1.0
+
+    @property
+    def shift(self):
+        return self._shift
+
+    @property
+    def step_index(self):
+        return self._step_index
+
+    @property
+    def begin_index(self):
+        return self._begin_index
+
+    def set_begin_index(self, begin_index=0):
+        self._begin_index = begin_index
+
+    def _sigma_to_t(self, sigma):
+        return sigma * self.config.num_train_timesteps
+
+    def time_shift(self, mu, sigma, t):
+        return math.exp(mu) / (math.exp(mu) + (1 / t - 1) ** sigma)
+
+    def set_timesteps(self, num_inference_steps=None, device=None, sigmas=None, mu=None, timesteps=None):
+        if self.config.use_dynamic_shifting and mu is None:
+            raise ValueError("`mu` must be passed when `use_dynamic_shifting` is set to be `True`")
+        if timesteps is not None:
+            raise NotImplementedError("custom timesteps")
+        if num_inference_steps is None:
+            num_inference_steps = len(sigmas)
+        self.num_inference_steps = num_inference_steps
+        if sigmas is None:
+            ts = np.linspace(self._sigma_to_t(self.sigma_max), self._sigma_to_t(self.sigma_min), num_inference_steps)
+            sigmas = ts / self.config.num_train_timesteps
+        else:
+            sigmas = np.array(sigmas).astype(np.float32)
+        if self.config.use_dynamic_shifting:
+            sigmas = self.time_shift(mu, 1.0, sigmas)
+        else:
+            sigmas = self._shift * sigmas / (1 + (self._shift - 1) * sigmas)
+        sig = torch.from_numpy(sigmas).to(dtype=torch.float32)
+        self._timesteps_cpu = sig * self.config.num_train_timesteps
+        self._sigmas_cpu = torch.cat([sig, torch.zeros(1)])
+        self.timesteps = self._timesteps_cpu.to(device=device)
+        self.sigmas = self._sigmas_cpu.to(device=device)  # the reference keeps these on the device (:380)
+        self._step_index = None
+        self._begin_index = None
+
+    def _init_step_index(self, timestep):
+        if self._begin_index is None:
+            t = float(timestep)
+            idx = (self._timesteps_cpu == t).nonzero()
+            pos = 1 if len(idx) > 1 else 0
+            self._step_index = int(idx[pos])
+        else:
+            self._step_index = self._begin_index
+
+    def step(self, model_output, timestep, sample, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0,
+             generator=None, per_token_timesteps=None, return_dict=True):
+        if isinstance(timestep, (int, torch.IntTensor, torch.LongTensor)):
+            raise ValueError("Passing integer indices as timesteps to FlowMatchEulerDiscreteScheduler.step() is not supported.")
+        if per_token_timesteps is not None:
+            raise NotImplementedError("per_token_timesteps")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        sigma = float(self._sigmas_cpu[self._step_index])
+        sigma_next = float(self._sigmas_cpu[self._step_index + 1])
+        prev = ops.flow_match_step(model_output, sample, sigma, sigma_next)
+        self._step_index += 1
+        if not return_dict:
+            return (prev,)
+        return SchedulerOutput(prev)
+
+    def __len__(self):
+        return self.config.num_train_timesteps

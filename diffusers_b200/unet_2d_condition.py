@@ -1,0 +1,415 @@
+"""Drop-in UNet2DConditionModel (SDXL-style) running on libb200diff.so.
+
+Same constructor config, `forward(sample, timestep, encoder_hidden_states, ..., added_cond_kwargs,
+return_dict)` signature, `.config`, `.dtype`, `.device`, `.add_embedding.linear_1.in_features` as the reference
+(models/unets/unet_2d_condition.py:76,979; what StableDiffusionXLPipeline touches is listed in SURVEY.md §8b).
+Internals are not a port: activations are NHWC bf16/fp16 buffers, every op is a C-ABI call into the sm_100a
+kernels (ops.py), skip-connection concats and layout permutes never materialise, the 17 resnet time
+projections are one skinny GEMM, and the text K/V projections of all 70 cross-attention layers are one GEMM
+that is cached per prompt.  There is no PyTorch fallback.
+"""
+import types
+
+import torch
+
+from . import ops, packing, specs
+from .config import FrozenConfig
+from .ops import ACT_NONE, ACT_SILU
+
+
+def _t(v, n):
+    return tuple(v) if isinstance(v, (list, tuple)) else (v,) * n
+
+
+class UNet2DConditionOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+
+class UNet2DConditionModel(torch.nn.Module):
+    _supports_cuda_graph = True
+
+    def __init__(self, config, state_dict, dtype=torch.bfloat16, device="cuda"):
+        super().__init__()
+        cfg = dict(specs.SDXL_UNET_CONFIG)
+        cfg.update(config)
+        self.config = FrozenConfig(cfg)
+        self._dtype = dtype
+        self._n = 0
+        spec = specs.unet2d_condition_params(cfg)
+        missing = [k for k in spec if k not in state_dict]
+        if missing:
+            raise ValueError(f"state_dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
+        for k, shp in spec.items():
+            if tuple(state_dict[k].shape) != tuple(shp):
+                raise ValueError(f"{k}: expected shape {tuple(shp)}, got {tuple(state_dict[k].shape)}")
+        if cfg.get("act_fn", "silu") not in ("silu", "swish"):
+            raise NotImplementedError("only act_fn='silu'")
+        self._build(state_dict, torch.device(device))
+        # attribute the SDXL pipeline reads (pipeline_stable_diffusion_xl.py:737)
+        self.add_embedding = types.SimpleNamespace(
+            linear_1=types.SimpleNamespace(in_features=cfg.get("projection_class_embeddings_input_dim")))
+        self._kv_key = None
+        self._kv = None
+        self._graphs = {}
+        self.use_cuda_graph = False
+
+    # ------------------------------------------------------------------ weights
+    def _reg(self, t, device):
+        name = f"w{self._n}"
+        self._n += 1
+        self.register_buffer(name, t.to(device=device, dtype=self._dtype).contiguous(), persistent=False)
+        return name
+
+    def _build(self, sd, device):
+        cfg = self.config
+        dt = self._dtype
+        R = lambda t: self._reg(t, device)  # noqa: E731
+        g = lambda k: sd[k].to(torch.float32)  # noqa: E731  (packing in fp32, stored in model dtype)
+        boc = tuple(cfg["block_out_channels"])
+        n = len(boc)
+        heads = _t(cfg.get("num_attention_heads") or cfg["attention_head_dim"], n)
+        self.time_dim = boc[0]
+        self.temb_dim = boc[0] * 4
+        self.in_pad = packing.rup(cfg["in_channels"], 8)
+
+        def lin_small(p):
+            return dict(w=R(g(p + ".weight")), b=R(g(p + ".bias")))
+
+        self.time_embedding = [lin_small("time_embedding.linear_1"), lin_small("time_embedding.linear_2")]
+        self.add_emb = None
+        if cfg.get("addition_embed_type") == "text_time":
+            self.add_emb = [lin_small("add_embedding.linear_1"), lin_small("add_embedding.linear_2")]
+
+        w_in = g("conv_in.weight")
+        w_in = torch.nn.functional.pad(w_in, (0, 0, 0, 0, 0, self.in_pad - w_in.shape[1]))
+        self.conv_in = dict(w=R(packing.pack_conv_weight(w_in)), b=R(g("conv_in.bias")), n=boc[0])
+
+        temb_w, temb_b = [], []
+        self._temb_total = 0
+        kv_w = []
+        self._kv_total = 0
+
+        def resnet(p, split=None):
+            w1 = g(p + ".conv1.weight")
+            cout, cin = w1.shape[0], w1.shape[1]
+            r = dict(cin=cin, cout=cout, split=split,
+                     n1w=R(g(p + ".norm1.weight")), n1b=R(g(p + ".norm1.bias")),
+                     c1w=R(packing.pack_conv_weight(w1, split)), c1b=R(g(p + ".conv1.bias")),
+                     n2w=R(g(p + ".norm2.weight")), n2b=R(g(p + ".norm2.bias")),
+                     c2w=R(packing.pack_conv_weight(g(p + ".conv2.weight"))), c2b=R(g(p + ".conv2.bias")))
+            r["temb_off"] = self._temb_total
+            temb_w.append(g(p + ".time_emb_proj.weight"))
+            temb_b.append(g(p + ".time_emb_proj.bias"))
+            self._temb_total += cout
+            if (p + ".conv_shortcut.weight") in sd:
+                r["scw"] = R(packing.pack_conv_weight(g(p + ".conv_shortcut.weight"), split))
+                r["scb"] = R(g(p + ".conv_shortcut.bias"))
+            elif split is not None:
+                raise NotImplementedError("two-source resnet without conv_shortcut")
+            return r
+
+        def transformer(p, ch, n_layers, nheads):
+            t = dict(ch=ch, heads=nheads, nw=R(g(p + ".norm.weight")), nb=R(g(p + ".norm.bias")),
+                     piw=R(packing.pack_linear_weight(g(p + ".proj_in.weight").reshape(ch, ch))), pib=R(g(p + ".proj_in.bias")),
+                     pow=R(packing.pack_linear_weight(g(p + ".proj_out.weight").reshape(ch, ch))), pob=R(g(p + ".proj_out.bias")),
+                     blocks=[])
+            if ch % nheads or (ch // nheads) not in (64, 128):
+                raise NotImplementedError(f"attention head_dim {ch // nheads if nheads else '?'}: the tcgen05 kernel supports 64 and 128")
+            for k in range(n_layers):
+                b = f"{p}.transformer_blocks.{k}"
+                qkv = torch.cat([g(b + ".attn1.to_q.weight"), g(b + ".attn1.to_k.weight"), g(b + ".attn1.to_v.weight")], 0)
+                ff1 = g(b + ".ff.net.0.proj.weight")
+                tile = ops.pick_tile_n(1 << 20, ff1.shape[0], True)
+                ff1w, ff1b = packing.pack_geglu(ff1, g(b + ".ff.net.0.proj.bias"), tile)
+                blk = dict(
+                    l1w=R(g(b + ".norm1.weight")), l1b=R(g(b + ".norm1.bias")),
+                    qkv=R(packing.pack_linear_weight(qkv)),
+                    ow=R(packing.pack_linear_weight(g(b + ".attn1.to_out.0.weight"))), ob=R(g(b + ".attn1.to_out.0.bias")),
+                    l2w=R(g(b + ".norm2.weight")), l2b=R(g(b + ".norm2.bias")),
+                    q2=R(packing.pack_linear_weight(g(b + ".attn2.to_q.weight"))),
+                    o2w=R(packing.pack_linear_weight(g(b + ".attn2.to_out.0.weight"))), o2b=R(g(b + ".attn2.to_out.0.bias")),
+                    l3w=R(g(b + ".norm3.weight")), l3b=R(g(b + ".norm3.bias")),
+                    ff1w=R(ff1w), ff1b=R(ff1b), ff1n=ff1.shape[0], ff1tile=tile,
+                    ff2w=R(packing.pack_linear_weight(g(b + ".ff.net.2.weight"))), ff2b=R(g(b + ".ff.net.2.bias")),
+                    kv_off=self._kv_total)
+                kv_w.append(torch.cat([g(b + ".attn2.to_k.weight"), g(b + ".attn2.to_v.weight")], 0))
+                self._kv_total += 2 * ch
+                t["blocks"].append(blk)
+            return t
+
+        lpb = _t(cfg.get("layers_per_block", 2), n)
+        tlpb = _t(cfg.get("transformer_layers_per_block", 1), n)
+        self.down = []
+        out_ch = boc[0]
+        skip_ch = [boc[0]]
+        for i, bt in enumerate(cfg["down_block_types"]):
+            p = f"down_blocks.{i}"
+            blk = dict(res=[], attn=[], down=None)
+            for j in range(lpb[i]):
+                blk["res"].append(resnet(f"{p}.resnets.{j}"))
+                out_ch = boc[i]
+                if bt == "CrossAttnDownBlock2D":
+                    blk["attn"].append(transformer(f"{p}.attentions.{j}", out_ch, _t(tlpb[i], lpb[i])[j], heads[i]))
+                skip_ch.append(out_ch)
+            if i != n - 1:
+                blk["down"] = dict(w=R(packing.pack_conv_weight(g(f"{p}.downsamplers.0.conv.weight"))),
+                                   b=R(g(f"{p}.downsamplers.0.conv.bias")), n=out_ch)
+                skip_ch.append(out_ch)
+            self.down.append(blk)
+        self.mid = dict(res=[resnet("mid_block.resnets.0"), resnet("mid_block.resnets.1")],
+                        attn=[transformer("mid_block.attentions.0", boc[-1], _t(tlpb[-1], 1)[0], heads[-1])])
+        self.up = []
+        rboc, rlpb, rtl, rheads = boc[::-1], lpb[::-1], tlpb[::-1], heads[::-1]
+        cur = rboc[0]
+        for i, bt in enumerate(cfg["up_block_types"]):
+            p = f"up_blocks.{i}"
+            blk = dict(res=[], attn=[], up=None)
+            nl = rlpb[i] + 1
+            for j in range(nl):
+                sk = skip_ch.pop()
+                blk["res"].append(resnet(f"{p}.resnets.{j}", split=(cur, sk)))
+                cur = rboc[i]
+                if bt == "CrossAttnUpBlock2D":
+                    blk["attn"].append(transformer(f"{p}.attentions.{j}", cur, _t(rtl[i], nl)[j], rheads[i]))
+            if i != n - 1:
+                blk["up"] = dict(w=R(packing.pack_conv_weight(g(f"{p}.upsamplers.0.conv.weight"))),
+                                 b=R(g(f"{p}.upsamplers.0.conv.bias")), n=cur)
+            self.up.append(blk)
+        self.norm_out = dict(w=R(g("conv_norm_out.weight")), b=R(g("conv_norm_out.bias")))
+        self.conv_out = dict(w=R(packing.pack_conv_weight(g("conv_out.weight"))), b=R(g("conv_out.bias")),
+                             n=cfg["out_channels"])
+        self.temb_all = dict(w=R(torch.cat(temb_w, 0)), b=R(torch.cat(temb_b, 0)))
+        self.kv_all = dict(w=R(packing.pack_linear_weight(torch.cat(kv_w, 0)))) if kv_w else None
+        del dt
+
+    # ------------------------------------------------------------------ nn.Module-ish surface
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def device(self):
+        return self._buffers["w0"].device
+
+    def W(self, name):
+        return self._buffers[name]
+
+    @classmethod
+    def from_state_dict(cls, config, state_dict, dtype=torch.bfloat16, device="cuda"):
+        return cls(config, state_dict, dtype=dtype, device=device)
+
+    @classmethod
+    def random_init(cls, config=None, seed=0, dtype=torch.bfloat16, device="cuda"):
+        cfg = dict(specs.SDXL_UNET_CONFIG)
+        cfg.update(config or {})
+        sd = specs.random_state_dict(specs.unet2d_condition_params(cfg), seed=seed, dtype=dtype)
+        return cls(cfg, sd, dtype=dtype, device=device)
+
+    def _reset_stateful_cache(self):
+        self._kv_key = None
+        self._kv = None
+
+    # ------------------------------------------------------------------ blocks
+    def _resnet(self, r, x, x2, temb_all, B, H, W):
+        hw = H * W
+        G, eps = self.config["norm_num_groups"], self.config.get("norm_eps", 1e-5)
+        n1 = ops.group_norm(x, x2=x2, batch=B, hw=hw, groups=G, eps=eps, gamma=self.W(r["n1w"]), beta=self.W(r["n1b"]), silu=True)
+        tslice = temb_all[:, r["temb_off"]:r["temb_off"] + r["cout"]]
+        h = ops.conv_gemm(n1, self.W(r["c1w"]), r["cout"], batch=B, H=H, W=W, ksize=3, bias=self.W(r["c1b"]),
+                          rowvec=tslice, rows_per_group=hw)
+        n2 = ops.group_norm(h, batch=B, hw=hw, groups=G, eps=eps, gamma=self.W(r["n2w"]), beta=self.W(r["n2b"]), silu=True)
+        if "scw" in r:
+            sc = ops.conv_gemm(x, self.W(r["scw"]), r["cout"], batch=B, H=H, W=W, ksize=1, x2=x2, bias=self.W(r["scb"]))
+        else:
+            sc = x
+        return ops.conv_gemm(n2, self.W(r["c2w"]), r["cout"], batch=B, H=H, W=W, ksize=3, bias=self.W(r["c2b"]), residual=sc)
+
+    def _transformer(self, t, x, kv, B, H, W, S_txt):
+        hw = H * W
+        C, nh = t["ch"], t["heads"]
+        hd = C // nh
+        n = ops.group_norm(x, batch=B, hw=hw, groups=self.config["norm_num_groups"], eps=1e-6, gamma=self.W(t["nw"]),
+                           beta=self.W(t["nb"]), silu=False)
+        h = ops.linear(n, self.W(t["piw"]), C, bias=self.W(t["pib"]))
+        for blk in t["blocks"]:
+            n = ops.layer_norm(h, eps=1e-5, gamma=self.W(blk["l1w"]), beta=self.W(blk["l1b"]))
+            qkv = ops.linear(n, self.W(blk["qkv"]), 3 * C).view(B, hw, 3 * C)
+            o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads=nh, head_dim=hd)
+            h = ops.linear(o.view(B * hw, C), self.W(blk["ow"]), C, bias=self.W(blk["ob"]), residual=h)
+            n = ops.layer_norm(h, eps=1e-5, gamma=self.W(blk["l2w"]), beta=self.W(blk["l2b"]))
+            q = ops.linear(n, self.W(blk["q2"]), C).view(B, hw, C)
+            kvb = kv[:, :, blk["kv_off"]:blk["kv_off"] + 2 * C]
+            o = ops.attention(q, kvb[:, :, :C], kvb[:, :, C:], heads=nh, head_dim=hd)
+            h = ops.linear(o.view(B * hw, C), self.W(blk["o2w"]), C, bias=self.W(blk["o2b"]), residual=h)
+            n = ops.layer_norm(h, eps=1e-5, gamma=self.W(blk["l3w"]), beta=self.W(blk["l3b"]))
+            gg = ops.linear(n, self.W(blk["ff1w"]), blk["ff1n"], bias=self.W(blk["ff1b"]), geglu=True, tile_n=blk["ff1tile"])
+            h = ops.linear(gg, self.W(blk["ff2w"]), C, bias=self.W(blk["ff2b"]), residual=h)
+        return ops.linear(h, self.W(t["pow"]), C, bias=self.W(t["pob"]), residual=x)
+
+    def _text_kv(self, ehs):
+        """K/V projections of the text states for every cross-attention layer: one GEMM, cached per prompt
+        (they do not depend on the timestep; the reference recomputes them 140x per step)."""
+        if self.kv_all is None:
+            return None
+        key = (ehs.data_ptr(), ehs._version, tuple(ehs.shape), ehs.dtype)
+        if self._kv_key != key or self._kv is None:
+            B, S, D = ehs.shape
+            flat = ehs.to(self._dtype).contiguous().view(B * S, D)
+            kv = ops.linear(flat, self.W(self.kv_all["w"]), self._kv_total)
+            self._kv = kv.view(B, S, self._kv_total)
+            self._kv_key = key
+        return self._kv
+
+    # ------------------------------------------------------------------ forward
+    def _embeddings(self, B, timestep, added_cond_kwargs, device):
+        cfg = self.config
+        dt = self._dtype
+        if not torch.is_tensor(timestep):
+            t = torch.full((B,), float(timestep), dtype=torch.float32, device=device)
+        else:
+            t = timestep.to(device=device, dtype=torch.float32).reshape(-1).expand(B).contiguous()
+        t_emb = ops.timestep_embedding(t, self.time_dim, dtype=dt, flip_sin_to_cos=cfg.get("flip_sin_to_cos", True),
+                                       downscale_freq_shift=float(cfg.get("freq_shift", 0)))
+        te = self.time_embedding
+        e = ops.small_linear(t_emb, self.W(te[0]["w"]), bias=self.W(te[0]["b"]), act_out=ACT_SILU)
+        if self.add_emb is None:
+            return ops.small_linear(e, self.W(te[1]["w"]), bias=self.W(te[1]["b"]))
+        emb = ops.small_linear(e, self.W(te[1]["w"]), bias=self.W(te[1]["b"]))
+        if added_cond_kwargs is None or "text_embeds" not in added_cond_kwargs or "time_ids" not in added_cond_kwargs:
+            raise ValueError("addition_embed_type='text_time' requires added_cond_kwargs with `text_embeds` and `time_ids`")
+        text_embeds = added_cond_kwargs["text_embeds"]
+        time_ids = added_cond_kwargs["time_ids"].to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+        ad = cfg["addition_time_embed_dim"]
+        add_in = torch.empty((B, text_embeds.shape[-1] + ad * (time_ids.numel() // B)), dtype=dt, device=device)
+        add_in[:, :text_embeds.shape[-1]] = text_embeds
+        tid = ops.timestep_embedding(time_ids, ad, dtype=dt, flip_sin_to_cos=cfg.get("flip_sin_to_cos", True),
+                                     downscale_freq_shift=float(cfg.get("freq_shift", 0)))
+        add_in[:, text_embeds.shape[-1]:] = tid.view(B, -1)
+        ae = self.add_emb
+        a1 = ops.small_linear(add_in, self.W(ae[0]["w"]), bias=self.W(ae[0]["b"]), act_out=ACT_SILU)
+        # emb = emb + aug_emb  (aug rounded to 16 bit first, as in the reference)
+        return ops.small_linear(a1, self.W(ae[1]["w"]), bias=self.W(ae[1]["b"]), addend=emb)
+
+    def _forward_nhwc(self, x_in, B, H, W, timestep, kv, added_cond_kwargs):
+        """x_in: [B*H*W, in_pad] NHWC; kv: cached text K/V [B, S_txt, kv_total].  Returns the NHWC prediction
+        [B*H*W, out_channels]."""
+        dev = x_in.device
+        emb = self._embeddings(B, timestep, added_cond_kwargs, dev)
+        temb_all = ops.small_linear(emb, self.W(self.temb_all["w"]), bias=self.W(self.temb_all["b"]), act_in=ACT_SILU)
+        S_txt = kv.shape[1] if kv is not None else 0
+
+        x = ops.conv_gemm(x_in, self.W(self.conv_in["w"]), self.conv_in["n"], batch=B, H=H, W=W, ksize=3,
+                          bias=self.W(self.conv_in["b"]))
+        skips = [(x, H, W)]
+        for blk in self.down:
+            for j, r in enumerate(blk["res"]):
+                x = self._resnet(r, x, None, temb_all, B, H, W)
+                if blk["attn"]:
+                    x = self._transformer(blk["attn"][j], x, kv, B, H, W, S_txt)
+                skips.append((x, H, W))
+            if blk["down"] is not None:
+                d = blk["down"]
+                x = ops.conv_gemm(x, self.W(d["w"]), d["n"], batch=B, H=H, W=W, ksize=3, stride=2, bias=self.W(d["b"]))
+                H, W = H // 2, W // 2
+                skips.append((x, H, W))
+        x = self._resnet(self.mid["res"][0], x, None, temb_all, B, H, W)
+        x = self._transformer(self.mid["attn"][0], x, kv, B, H, W, S_txt)
+        x = self._resnet(self.mid["res"][1], x, None, temb_all, B, H, W)
+        for blk in self.up:
+            for j, r in enumerate(blk["res"]):
+                sk, sh, sw = skips.pop()
+                assert (sh, sw) == (H, W)
+                x = self._resnet(r, x, sk, temb_all, B, H, W)
+                if blk["attn"]:
+                    x = self._transformer(blk["attn"][j], x, kv, B, H, W, S_txt)
+            if blk["up"] is not None:
+                u = blk["up"]
+                xu = ops.upsample_nearest2x(x, batch=B, H=H, W=W)
+                H, W = 2 * H, 2 * W
+                x = ops.conv_gemm(xu, self.W(u["w"]), u["n"], batch=B, H=H, W=W, ksize=3, bias=self.W(u["b"]))
+        n = ops.group_norm(x, batch=B, hw=H * W, groups=self.config["norm_num_groups"], eps=self.config.get("norm_eps", 1e-5),
+                           gamma=self.W(self.norm_out["w"]), beta=self.W(self.norm_out["b"]), silu=True)
+        return ops.conv_gemm(n, self.W(self.conv_out["w"]), self.conv_out["n"], batch=B, H=H, W=W, ksize=3,
+                             bias=self.W(self.conv_out["b"]))
+
+    @torch.no_grad()
+    def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, timestep_cond=None, attention_mask=None,
+                cross_attention_kwargs=None, added_cond_kwargs=None, down_block_additional_residuals=None,
+                mid_block_additional_residual=None, down_intrablock_additional_residuals=None,
+                encoder_attention_mask=None, return_dict=True):
+        for name, v in (("class_labels", class_labels), ("timestep_cond", timestep_cond), ("attention_mask", attention_mask),
+                        ("down_block_additional_residuals", down_block_additional_residuals),
+                        ("mid_block_additional_residual", mid_block_additional_residual),
+                        ("down_intrablock_additional_residuals", down_intrablock_additional_residuals),
+                        ("encoder_attention_mask", encoder_attention_mask)):
+            if v is not None:
+                raise NotImplementedError(f"{name} is outside the accelerated hot path (SURVEY.md §8)")
+        if not sample.is_cuda:
+            raise ops.B200Error("UNet2DConditionModel (B200) needs CUDA tensors: there is no CPU fallback")
+        B, C, H, W = sample.shape
+        if H % (2 ** (len(self.config["block_out_channels"]) - 1)) or W % (2 ** (len(self.config["block_out_channels"]) - 1)):
+            raise ValueError("sample height/width must be divisible by the total downsampling factor")
+        sample = sample.to(self._dtype)
+        if self.use_cuda_graph:
+            out = self._forward_graph(sample, timestep, encoder_hidden_states, added_cond_kwargs)
+        else:
+            x_in = ops.nchw_to_nhwc(sample, c_pad=self.in_pad)
+            y = self._forward_nhwc(x_in, B, H, W, timestep, self._text_kv(encoder_hidden_states), added_cond_kwargs)
+            out = ops.nhwc_to_nchw(y, batch=B, C_out=self.config["out_channels"], H=H, W=W)
+        if not return_dict:
+            return (out,)
+        return UNet2DConditionOutput(out)
+
+    # ------------------------------------------------------------------ CUDA graph replay of a whole forward
+    def enable_cuda_graph(self, enabled=True):
+        self.use_cuda_graph = enabled
+        if not enabled:
+            self._graphs.clear()
+
+    def _forward_graph(self, sample, timestep, ehs, added):
+        B, C, H, W = sample.shape
+        key = (B, C, H, W, tuple(ehs.shape), tuple(added["text_embeds"].shape) if added else None,
+               tuple(added["time_ids"].shape) if added else None)
+        st = self._graphs.get(key)
+        dev = sample.device
+        if st is None:
+            st = dict(sample=torch.empty_like(sample), t=torch.empty((), dtype=torch.float32, device=dev),
+                      kv=torch.empty((ehs.shape[0], ehs.shape[1], self._kv_total), dtype=self._dtype, device=dev),
+                      kv_src=None,
+                      added=None if not added else dict(text_embeds=torch.empty_like(added["text_embeds"], dtype=self._dtype),
+                                                        time_ids=torch.empty_like(added["time_ids"])))
+            self._graphs[key] = st
+
+        def load():
+            st["sample"].copy_(sample)
+            st["t"].copy_(timestep if torch.is_tensor(timestep) else torch.tensor(float(timestep)))
+            kv = self._text_kv(ehs)  # eager, cached per prompt: stays outside the per-step graph
+            if st["kv_src"] is not kv:
+                st["kv"].copy_(kv)
+                st["kv_src"] = kv
+            if added:
+                st["added"]["text_embeds"].copy_(added["text_embeds"])
+                st["added"]["time_ids"].copy_(added["time_ids"])
+
+        def run():
+            x_in = ops.nchw_to_nhwc(st["sample"], c_pad=self.in_pad)
+            y = self._forward_nhwc(x_in, B, H, W, st["t"], st["kv"], st["added"])
+            return ops.nhwc_to_nchw(y, batch=B, C_out=self.config["out_channels"], H=H, W=W)
+
+        load()
+        if "graph" not in st:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                run()  # warm-up: workspaces, smem attributes, lazy module load
+            torch.cuda.current_stream().wait_stream(s)
+            gph = torch.cuda.CUDAGraph()
+            n0 = ops.launches()
+            with torch.cuda.graph(gph):
+                st["out"] = run()
+            st["graph"] = gph
+            st["launches"] = ops.launches() - n0
+        st["graph"].replay()
+        ops._count(st["launches"])
+        return st["out"].clone()

@@ -94,6 +94,7 @@ typedef struct {
   int32_t ldy;
   int32_t dtype;         /* B200_DTYPE_*                                                        */
   int32_t tile_n;        /* 0 = auto, else force BN in {32, 64, 128, 256}                       */
+  int32_t out_fp32;      /* 1: y is float32 [.., ldy] (attention scores of the head_dim-512 path) */
 } b200_conv_gemm_args;
 
 int b200_conv_gemm(const b200_conv_gemm_args* args, void* stream);
@@ -236,6 +237,17 @@ typedef struct {
 } b200_attention_args;
 
 int b200_attention(const b200_attention_args* args, void* stream);
+
+/* Unfused attention helpers for head_dim 512 (AutoencoderKL mid-block attention, one head:
+ * models/attention_processor.py:2725-2789 via unets/unet_2d_blocks.py:684-698).  TMEM cannot hold a
+ * 128 x 512 fp32 output tile next to the scores, so that single layer runs as
+ * b200_conv_gemm(out_fp32) -> b200_softmax_rows -> b200_conv_gemm against b200_transpose_16(V).
+ *   b200_softmax_rows : p[r, :] = softmax(s[r, :] * scale), s fp32 [rows, ld_s], p 16-bit [rows, ld_p]
+ *   b200_transpose_16 : dst[c, r] = src[r, c] for 16-bit elements */
+int b200_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t ld_p, int32_t rows, int32_t cols, float scale,
+                      int32_t dtype, void* stream);
+int b200_transpose_16(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols,
+                      void* stream);
 
 #ifdef __cplusplus
 }
