@@ -63,6 +63,16 @@ class LayerNormArgs(C.Structure):
     ]
 
 
+class QkNormRopeArgs(C.Structure):
+    _fields_ = [
+        ("qkv", C.c_void_p), ("ld", C.c_int64),
+        ("rows", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32), ("k_off", C.c_int32),
+        ("txt_rows", C.c_int32), ("seq", C.c_int32),
+        ("wq", C.c_void_p), ("wk", C.c_void_p), ("wq_txt", C.c_void_p), ("wk_txt", C.c_void_p),
+        ("cos_table", C.c_void_p), ("sin_table", C.c_void_p), ("eps", C.c_float), ("dtype", C.c_int32),
+    ]
+
+
 class SmallLinearArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("ldx", C.c_int32), ("M", C.c_int32), ("K", C.c_int32),
@@ -103,7 +113,8 @@ def lib():
         _lib.b200_flow_match_step.argtypes = [VP, VP, VP, I64, F32, F32, I32, VP]
         _lib.b200_softmax_rows.argtypes = [VP, I64, VP, I64, I32, I32, F32, I32, VP]
         _lib.b200_transpose_16.argtypes = [VP, I64, VP, I64, I32, I32, VP]
-        for fn in ("b200_conv_gemm", "b200_attention", "b200_group_norm", "b200_layer_norm", "b200_small_linear"):
+        for fn in ("b200_conv_gemm", "b200_attention", "b200_group_norm", "b200_layer_norm", "b200_small_linear",
+                   "b200_qk_norm_rope"):
             getattr(_lib, fn).argtypes = [VP, VP]
     return _lib
 

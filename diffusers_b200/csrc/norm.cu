@@ -294,6 +294,90 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const LayerNormParams p
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// per-head RMSNorm (weight) + rotary embedding on the q and k slices of a fused QKV buffer, in place.
+// One warp per (token row, head).  Rounding points follow the reference eager ops: rms_norm output is
+// rounded to 16 bit twice (normalised value, then * weight), rope is computed in fp32 and rounded once.
+// ------------------------------------------------------------------------------------------------
+struct QkNormRopeParams {
+  void* qkv;
+  long long ld;
+  int rows, heads, k_off;
+  int txt_rows;  // rows [0, txt_rows) of every sequence use the *_txt weights (joint attention: text first)
+  int seq;       // rows per sequence (rope position = row % seq)
+  const void* wq;
+  const void* wk;
+  const void* wq_txt;
+  const void* wk_txt;
+  const float* cos_t;  // [seq, HD] or nullptr
+  const float* sin_t;
+  float eps;
+};
+
+template <bool FP16, int HD>
+__global__ void __launch_bounds__(256) qk_norm_rope_kernel(const QkNormRopeParams p) {
+  using H = Half16<FP16>;
+  constexpr int EPL = HD / 32;  // elements per lane (2 or 4): rotation pairs stay inside a lane
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  if (item >= static_cast<long long>(p.rows) * p.heads) return;
+  const int head = static_cast<int>(item % p.heads);
+  const long long row = item / p.heads;
+  const int pos = static_cast<int>(row % p.seq);
+  const bool is_txt = pos < p.txt_rows;
+  typename H::T* base = static_cast<typename H::T*>(p.qkv) + row * p.ld + head * HD + lane * EPL;
+  float cs[EPL], sn[EPL];
+  if (p.cos_t) {
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      cs[j] = p.cos_t[static_cast<long long>(pos) * HD + lane * EPL + j];
+      sn[j] = p.sin_t[static_cast<long long>(pos) * HD + lane * EPL + j];
+    }
+  }
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    typename H::T* ptr = base + (which ? p.k_off : 0);
+    const typename H::T* w = static_cast<const typename H::T*>(which ? (is_txt ? p.wk_txt : p.wk) : (is_txt ? p.wq_txt : p.wq));
+    float x[EPL];
+    if (EPL == 4) {
+      uint2 u = *reinterpret_cast<const uint2*>(ptr);
+      float2 a = H::unpack(u.x), b = H::unpack(u.y);
+      x[0] = a.x; x[1] = a.y; x[EPL - 2] = b.x; x[EPL - 1] = b.y;
+    } else {
+      uint32_t u = *reinterpret_cast<const uint32_t*>(ptr);
+      float2 a = H::unpack(u);
+      x[0] = a.x; x[1] = a.y;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) ss += x[j] * x[j];
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / static_cast<float>(HD) + p.eps);
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      float v = H::to_float(H::from_float(x[j] * rstd));
+      if (w) v = H::to_float(H::from_float(v * H::to_float(w[lane * EPL + j])));
+      x[j] = v;
+    }
+    if (p.cos_t) {
+#pragma unroll
+      for (int j = 0; j < EPL; j += 2) {
+        const float re = x[j], im = x[j + 1];
+        x[j] = re * cs[j] + (-im) * sn[j];
+        x[j + 1] = im * cs[j + 1] + re * sn[j + 1];
+      }
+    }
+    if (EPL == 4) {
+      uint2 o;
+      o.x = H::pack(x[0], x[1]);
+      o.y = H::pack(x[EPL - 2], x[EPL - 1]);
+      *reinterpret_cast<uint2*>(ptr) = o;
+    } else {
+      *reinterpret_cast<uint32_t*>(ptr) = H::pack(x[0], x[1]);
+    }
+  }
+}
+
 }  // namespace b200
 
 extern "C" {
@@ -439,6 +523,35 @@ int b200_layer_norm(const b200_layer_norm_args* a, void* stream) {
   }
 #undef B200_LN
   return check_launch("layer_norm_kernel");
+}
+
+int b200_qk_norm_rope(const b200_qk_norm_rope_args* a, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(a && a->qkv, "qk_norm_rope: null pointer");
+  B200_CHECK_ARG(a->head_dim == 64 || a->head_dim == 128, "qk_norm_rope: head_dim %d (64 or 128)", a->head_dim);
+  B200_CHECK_ARG(a->rows > 0 && a->heads > 0 && a->seq > 0 && a->ld % 4 == 0 && a->k_off % 4 == 0,
+                 "qk_norm_rope: bad shape / stride");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(a->qkv) & 7u) == 0, "qk_norm_rope: qkv must be 8-byte aligned");
+  B200_CHECK_ARG((a->cos_table == nullptr) == (a->sin_table == nullptr), "qk_norm_rope: need both cos and sin or neither");
+  QkNormRopeParams p;
+  p.qkv = a->qkv; p.ld = a->ld; p.rows = a->rows; p.heads = a->heads; p.k_off = a->k_off;
+  p.txt_rows = a->txt_rows; p.seq = a->seq;
+  p.wq = a->wq; p.wk = a->wk;
+  p.wq_txt = a->wq_txt ? a->wq_txt : a->wq;
+  p.wk_txt = a->wk_txt ? a->wk_txt : a->wk;
+  p.cos_t = a->cos_table; p.sin_t = a->sin_table; p.eps = a->eps;
+  const long long items = static_cast<long long>(a->rows) * a->heads;
+  const unsigned int grid = static_cast<unsigned int>((items + 7) / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool fp16 = a->dtype == B200_DTYPE_FP16;
+  if (a->head_dim == 128) {
+    if (fp16) qk_norm_rope_kernel<true, 128><<<grid, 256, 0, st>>>(p);
+    else qk_norm_rope_kernel<false, 128><<<grid, 256, 0, st>>>(p);
+  } else {
+    if (fp16) qk_norm_rope_kernel<true, 64><<<grid, 256, 0, st>>>(p);
+    else qk_norm_rope_kernel<false, 64><<<grid, 256, 0, st>>>(p);
+  }
+  return check_launch("qk_norm_rope_kernel");
 }
 
 }  // extern "C"

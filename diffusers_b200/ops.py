@@ -344,3 +344,20 @@ def attention_unfused(q, k, v, *, scale):
     p = softmax_rows(s, scale, q.dtype)
     vt = transpose_16(v)  # [D, Sk]: K-major "weights" for the P @ V GEMM
     return linear(p, vt, D)
+
+
+def qk_norm_rope(qkv, *, heads, head_dim, k_off, seq, txt_rows=0, wq=None, wk=None, wq_txt=None, wk_txt=None,
+                 cos=None, sin=None, eps=1e-6):
+    """In place on qkv [rows, ld]: RMSNorm(q), RMSNorm(k) per head (+ weight), then rotary embedding."""
+    _need_cuda(qkv, "qkv")
+    a = _lib.QkNormRopeArgs()
+    a.qkv, a.ld = qkv.data_ptr(), qkv.stride(0)
+    a.rows, a.heads, a.head_dim, a.k_off = qkv.shape[0], heads, head_dim, k_off
+    a.txt_rows, a.seq = txt_rows, seq
+    a.wq, a.wk, a.wq_txt, a.wk_txt = _ptr(wq), _ptr(wk), _ptr(wq_txt), _ptr(wk_txt)
+    a.cos_table, a.sin_table = _ptr(cos), _ptr(sin)
+    a.eps = eps
+    a.dtype = _dtype_code(qkv)
+    _lib.check(_lib.lib().b200_qk_norm_rope(C.byref(a), _stream()), "b200_qk_norm_rope")
+    _count()
+    return qkv

@@ -1,0 +1,279 @@
+"""Drop-in FluxTransformer2DModel on libb200diff.so.
+
+Same `forward(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
+joint_attention_kwargs, return_dict)` signature, `.config`, `.dtype`, `cache_context()` as the reference
+(models/transformers/transformer_flux.py:529,671; what FluxPipeline touches: SURVEY.md §8b).
+
+B200-first structure (not a port):
+  * all 115 AdaLN modulation projections (Linear(SiLU(temb)), M = batch) are ONE weight-streaming launch per
+    forward; LayerNorm + (1+scale)*x+shift is one pass; gates and residual adds live in GEMM epilogues;
+  * q/k/v (+ added q/k/v) GEMMs write straight into one joint [text | image] QKV buffer; RMSNorm + RoPE run
+    in place on it; the tcgen05 attention kernel reads q/k/v as strided views (no cat, no permute);
+  * single blocks never build cat([attn, mlp]): proj_out is a two-source-K GEMM;
+  * context_embedder(text) and the RoPE tables are step-invariant and cached.
+"""
+import contextlib
+
+import torch
+
+from . import ops, packing, specs
+from .config import FrozenConfig
+from .ops import ACT_GELU_TANH, ACT_SILU
+
+
+class Transformer2DModelOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+
+class FluxTransformer2DModel(torch.nn.Module):
+    def __init__(self, config, state_dict, dtype=torch.bfloat16, device="cuda"):
+        super().__init__()
+        cfg = dict(specs.FLUX_DEV_CONFIG)
+        cfg.update(config)
+        if cfg.get("out_channels") is None:
+            cfg["out_channels"] = cfg["in_channels"]
+        self.config = FrozenConfig(cfg)
+        self._dtype = dtype
+        self._n = 0
+        spec = specs.flux_params(cfg)
+        for k, shp in spec.items():
+            if k not in state_dict:
+                raise ValueError(f"state_dict is missing {k}")
+            if tuple(state_dict[k].shape) != tuple(shp):
+                raise ValueError(f"{k}: expected shape {tuple(shp)}, got {tuple(state_dict[k].shape)}")
+        if cfg["attention_head_dim"] not in (64, 128):
+            raise NotImplementedError("attention_head_dim must be 64 or 128 for the tcgen05 attention kernel")
+        if sum(cfg["axes_dims_rope"]) != cfg["attention_head_dim"]:
+            raise ValueError("sum(axes_dims_rope) must equal attention_head_dim")
+        self._build(state_dict, torch.device(device))
+        self._ctx_key = None
+        self._ctx = None
+        self._rope_key = None
+        self._rope = None
+
+    def _reg(self, t, device):
+        name = f"w{self._n}"
+        self._n += 1
+        self.register_buffer(name, t.to(device=device, dtype=self._dtype).contiguous(), persistent=False)
+        return name
+
+    def W(self, name):
+        return self._buffers[name]
+
+    def _build(self, sd, device):
+        cfg = self.config
+        R = lambda t: self._reg(t, device)  # noqa: E731
+        g = lambda k: sd[k].to(torch.float32)  # noqa: E731
+        D = cfg["num_attention_heads"] * cfg["attention_head_dim"]
+        self.D = D
+
+        def small(p):
+            return dict(w=R(g(p + ".weight")), b=R(g(p + ".bias")))
+
+        def lin(p, split=None):
+            w = g(p + ".weight")
+            return dict(w=R(packing.pack_linear_weight(w, split)), b=R(g(p + ".bias")), n=w.shape[0])
+
+        def lin_cat(ps):
+            w = torch.cat([g(p + ".weight") for p in ps], 0)
+            b = torch.cat([g(p + ".bias") for p in ps], 0)
+            return dict(w=R(packing.pack_linear_weight(w)), b=R(b), n=w.shape[0])
+
+        te = "time_text_embed"
+        self.t_emb = [small(te + ".timestep_embedder.linear_1"), small(te + ".timestep_embedder.linear_2")]
+        self.g_emb = None
+        if cfg.get("guidance_embeds", False):
+            self.g_emb = [small(te + ".guidance_embedder.linear_1"), small(te + ".guidance_embedder.linear_2")]
+        self.p_emb = [small(te + ".text_embedder.linear_1"), small(te + ".text_embedder.linear_2")]
+        self.x_embedder = lin("x_embedder")
+        self.context_embedder = lin("context_embedder")
+
+        mod_w, mod_b = [], []
+        self._mod_total = 0
+
+        def mod(p):
+            off = self._mod_total
+            w = g(p + ".weight")
+            mod_w.append(w)
+            mod_b.append(g(p + ".bias"))
+            self._mod_total += w.shape[0]
+            return off
+
+        self.double = []
+        for i in range(cfg["num_layers"]):
+            p = f"transformer_blocks.{i}"
+            a = p + ".attn"
+            self.double.append(dict(
+                mod=mod(p + ".norm1.linear"), cmod=mod(p + ".norm1_context.linear"),
+                qkv=lin_cat([a + ".to_q", a + ".to_k", a + ".to_v"]),
+                aqkv=lin_cat([a + ".add_q_proj", a + ".add_k_proj", a + ".add_v_proj"]),
+                nq=R(g(a + ".norm_q.weight")), nk=R(g(a + ".norm_k.weight")),
+                naq=R(g(a + ".norm_added_q.weight")), nak=R(g(a + ".norm_added_k.weight")),
+                out=lin(a + ".to_out.0"), aout=lin(a + ".to_add_out"),
+                ff1=lin(p + ".ff.net.0.proj"), ff2=lin(p + ".ff.net.2"),
+                cff1=lin(p + ".ff_context.net.0.proj"), cff2=lin(p + ".ff_context.net.2")))
+        self.single = []
+        for i in range(cfg["num_single_layers"]):
+            p = f"single_transformer_blocks.{i}"
+            a = p + ".attn"
+            self.single.append(dict(
+                mod=mod(p + ".norm.linear"),
+                qkv=lin_cat([a + ".to_q", a + ".to_k", a + ".to_v"]),
+                nq=R(g(a + ".norm_q.weight")), nk=R(g(a + ".norm_k.weight")),
+                mlp=lin(p + ".proj_mlp"), out=lin(p + ".proj_out", split=(D, 4 * D))))
+        self.mod_out = mod("norm_out.linear")
+        self.proj_out = lin("proj_out")
+        self.mod_all = dict(w=R(torch.cat(mod_w, 0)), b=R(torch.cat(mod_b, 0)))
+
+    # ------------------------------------------------------------------ reference-facing surface
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def device(self):
+        return self._buffers["w0"].device
+
+    @contextlib.contextmanager
+    def cache_context(self, name):
+        """CacheMixin.cache_context (models/cache_utils.py:155): the pipeline wraps every call in it."""
+        yield
+
+    def _reset_stateful_cache(self):
+        self._ctx_key = self._ctx = self._rope_key = self._rope = None
+
+    @classmethod
+    def random_init(cls, config=None, seed=0, dtype=torch.bfloat16, device="cuda"):
+        cfg = dict(specs.FLUX_DEV_CONFIG)
+        cfg.update(config or {})
+        sd = specs.random_state_dict(specs.flux_params(cfg), seed=seed, dtype=dtype)
+        return cls(cfg, sd, dtype=dtype, device=device)
+
+    # ------------------------------------------------------------------ step-invariant pieces
+    def _rope_tables(self, txt_ids, img_ids):
+        key = (txt_ids.data_ptr(), img_ids.data_ptr(), tuple(txt_ids.shape), tuple(img_ids.shape), txt_ids._version,
+               img_ids._version)
+        if self._rope_key != key:
+            ids = torch.cat((txt_ids, img_ids), dim=0)
+            pos = ids.float()
+            cos_out, sin_out = [], []
+            for i, dim in enumerate(self.config["axes_dims_rope"]):
+                # FluxPosEmbed.forward / get_1d_rotary_pos_embed: fp64 frequencies, fp32 tables (host-side glue, once)
+                freqs = 1.0 / (10000 ** (torch.arange(0, dim, 2, dtype=torch.float64, device=pos.device) / dim))
+                freqs = torch.outer(pos[:, i], freqs)
+                cos_out.append(freqs.cos().repeat_interleave(2, dim=1, output_size=freqs.shape[1] * 2).float())
+                sin_out.append(freqs.sin().repeat_interleave(2, dim=1, output_size=freqs.shape[1] * 2).float())
+            self._rope = (torch.cat(cos_out, dim=-1).contiguous(), torch.cat(sin_out, dim=-1).contiguous())
+            self._rope_key = key
+        return self._rope
+
+    def _context(self, ehs):
+        key = (ehs.data_ptr(), ehs._version, tuple(ehs.shape), ehs.dtype)
+        if self._ctx_key != key:
+            B, T, Dj = ehs.shape
+            ce = self.context_embedder
+            self._ctx = ops.linear(ehs.to(self._dtype).contiguous().view(B * T, Dj), self.W(ce["w"]), ce["n"],
+                                   bias=self.W(ce["b"])).view(B, T, self.D)
+            self._ctx_key = key
+        return self._ctx
+
+    def _temb(self, timestep, guidance, pooled):
+        dt = self._dtype
+        B = pooled.shape[0]
+        dev = pooled.device
+        # timestep.to(hidden_states.dtype) * 1000 (transformer_flux.py:725): rounded to 16 bit like the reference
+        t = (timestep.to(device=dev).to(dt) * 1000).to(torch.float32).reshape(-1).expand(B).contiguous()
+        tp = ops.timestep_embedding(t, 256, dtype=dt, flip_sin_to_cos=True, downscale_freq_shift=0.0)
+        e = ops.small_linear(tp, self.W(self.t_emb[0]["w"]), bias=self.W(self.t_emb[0]["b"]), act_out=ACT_SILU)
+        emb = ops.small_linear(e, self.W(self.t_emb[1]["w"]), bias=self.W(self.t_emb[1]["b"]))
+        if self.g_emb is not None:
+            if guidance is None:
+                raise ValueError("guidance_embeds=True requires `guidance`")
+            gd = (guidance.to(device=dev).to(dt) * 1000).to(torch.float32).reshape(-1).expand(B).contiguous()
+            gp = ops.timestep_embedding(gd, 256, dtype=dt, flip_sin_to_cos=True, downscale_freq_shift=0.0)
+            e = ops.small_linear(gp, self.W(self.g_emb[0]["w"]), bias=self.W(self.g_emb[0]["b"]), act_out=ACT_SILU)
+            emb = ops.small_linear(e, self.W(self.g_emb[1]["w"]), bias=self.W(self.g_emb[1]["b"]), addend=emb)
+        e = ops.small_linear(pooled.to(dt), self.W(self.p_emb[0]["w"]), bias=self.W(self.p_emb[0]["b"]), act_out=ACT_SILU)
+        return ops.small_linear(e, self.W(self.p_emb[1]["w"]), bias=self.W(self.p_emb[1]["b"]), addend=emb)
+
+    # ------------------------------------------------------------------ one batch element
+    def _lin(self, l, x, **kw):
+        return ops.linear(x, self.W(l["w"]), l["n"], bias=self.W(l["b"]), **kw)
+
+    def _forward_one(self, x_in, ctx, mod, rope):
+        """x_in [S, in_ch], ctx [T, D], mod [1, mod_total] (all AdaLN projections of this sample)."""
+        cfg = self.config
+        D, nh, hd = self.D, cfg["num_attention_heads"], cfg["attention_head_dim"]
+        S, T = x_in.shape[0], ctx.shape[0]
+        L = S + T
+        cos, sin = rope
+        dev = x_in.device
+        hbuf = torch.empty((L, D), dtype=self._dtype, device=dev)  # joint residual stream [text | image]
+        c, x = hbuf[:T], hbuf[T:]
+        self._lin(self.x_embedder, x_in, out=x)
+        c.copy_(ctx)
+        J = torch.empty((L, 3 * D), dtype=self._dtype, device=dev)  # joint fused QKV
+        J3 = J.view(1, L, 3 * D)
+
+        def m(off, i):
+            return mod[:, off + i * D: off + (i + 1) * D]
+
+        def attend(blk, txt_rows):
+            ops.qk_norm_rope(J, heads=nh, head_dim=hd, k_off=D, seq=L, txt_rows=txt_rows, wq=self.W(blk["nq"]),
+                             wk=self.W(blk["nk"]), wq_txt=self.W(blk["naq"]) if "naq" in blk else None,
+                             wk_txt=self.W(blk["nak"]) if "nak" in blk else None, cos=cos, sin=sin, eps=1e-6)
+            return ops.attention(J3[:, :, :D], J3[:, :, D:2 * D], J3[:, :, 2 * D:], heads=nh, head_dim=hd).view(L, D)
+
+        for blk in self.double:
+            o, co = blk["mod"], blk["cmod"]
+            nx = ops.layer_norm(x, eps=1e-6, scale=m(o, 1), shift=m(o, 0), rows_per_group=S)
+            nc = ops.layer_norm(c, eps=1e-6, scale=m(co, 1), shift=m(co, 0), rows_per_group=T)
+            self._lin(blk["aqkv"], nc, out=J[:T])
+            self._lin(blk["qkv"], nx, out=J[T:])
+            a = attend(blk, T)
+            self._lin(blk["out"], a[T:], gate=m(o, 2), rows_per_group=S, residual=x, out=x)
+            self._lin(blk["aout"], a[:T], gate=m(co, 2), rows_per_group=T, residual=c, out=c)
+            nx = ops.layer_norm(x, eps=1e-6, scale=m(o, 4), shift=m(o, 3), rows_per_group=S)
+            h = self._lin(blk["ff1"], nx, act=ACT_GELU_TANH)
+            self._lin(blk["ff2"], h, gate=m(o, 5), rows_per_group=S, residual=x, out=x)
+            nc = ops.layer_norm(c, eps=1e-6, scale=m(co, 4), shift=m(co, 3), rows_per_group=T)
+            h = self._lin(blk["cff1"], nc, act=ACT_GELU_TANH)
+            self._lin(blk["cff2"], h, gate=m(co, 5), rows_per_group=T, residual=c, out=c)
+        for blk in self.single:
+            o = blk["mod"]
+            nh_ = ops.layer_norm(hbuf, eps=1e-6, scale=m(o, 1), shift=m(o, 0), rows_per_group=L)
+            self._lin(blk["qkv"], nh_, out=J)
+            mlp = self._lin(blk["mlp"], nh_, act=ACT_GELU_TANH)
+            a = attend(blk, 0)
+            self._lin(blk["out"], a, x2=mlp, gate=m(o, 2), rows_per_group=L, residual=hbuf, out=hbuf)
+        # AdaLayerNormContinuous: scale, shift = chunk(2)  (normalization.py:349)
+        nx = ops.layer_norm(x, eps=1e-6, scale=m(self.mod_out, 0), shift=m(self.mod_out, 1), rows_per_group=S)
+        return self._lin(self.proj_out, nx)
+
+    @torch.no_grad()
+    def forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None,
+                txt_ids=None, guidance=None, joint_attention_kwargs=None, controlnet_block_samples=None,
+                controlnet_single_block_samples=None, return_dict=True, controlnet_blocks_repeat=False):
+        if controlnet_block_samples is not None or controlnet_single_block_samples is not None:
+            raise NotImplementedError("controlnet residuals are outside the accelerated hot path")
+        if joint_attention_kwargs:
+            raise NotImplementedError("joint_attention_kwargs (IP-adapter / LoRA scale) are outside the hot path")
+        if not hidden_states.is_cuda:
+            raise ops.B200Error("FluxTransformer2DModel (B200) needs CUDA tensors: there is no CPU fallback")
+        if txt_ids.ndim == 3:
+            txt_ids = txt_ids[0]
+        if img_ids.ndim == 3:
+            img_ids = img_ids[0]
+        B, S, Cin = hidden_states.shape
+        hs = hidden_states.to(self._dtype).contiguous()
+        temb = self._temb(timestep, guidance, pooled_projections)
+        mod = ops.small_linear(temb, self.W(self.mod_all["w"]), bias=self.W(self.mod_all["b"]), act_in=ACT_SILU)
+        ctx = self._context(encoder_hidden_states)
+        rope = self._rope_tables(txt_ids, img_ids)
+        out = torch.empty((B, S, self.proj_out["n"]), dtype=self._dtype, device=hs.device)
+        for b in range(B):
+            out[b] = self._forward_one(hs[b], ctx[b], mod[b:b + 1], rope)
+        if not return_dict:
+            return (out,)
+        return Transformer2DModelOutput(out)

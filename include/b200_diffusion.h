@@ -249,6 +249,31 @@ int b200_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t ld_p, int32
 int b200_transpose_16(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int32_t rows, int32_t cols,
                       void* stream);
 
+/* -------------------------------------------------------------------------------------------
+ * b200_qk_norm_rope — per-head RMSNorm (with weight) of q and k followed by the rotary embedding, in
+ * place on a fused QKV buffer [rows, ld] (q at column 0, k at column k_off, head h at h*head_dim).
+ * Rows [0, txt_rows) of every `seq`-row sequence use the text-stream norm weights (joint attention puts
+ * the text tokens first).  cos/sin are the fp32 [seq, head_dim] tables of FluxPosEmbed (repeat-interleaved).
+ * Replaces  transformers/transformer_flux.py:102-119 (norm_q/norm_k/norm_added_q/norm_added_k =
+ *           torch.nn.RMSNorm(head_dim, eps 1e-6); apply_rotary_emb models/embeddings.py:1187-1231).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  void* qkv;
+  int64_t ld;
+  int32_t rows, heads, head_dim, k_off;
+  int32_t txt_rows, seq;
+  const void* wq;      /* [head_dim] 16-bit, or NULL (no weight) */
+  const void* wk;
+  const void* wq_txt;  /* NULL = same as wq */
+  const void* wk_txt;
+  const float* cos_table; /* [seq, head_dim] or NULL (no rope) */
+  const float* sin_table;
+  float eps;
+  int32_t dtype;
+} b200_qk_norm_rope_args;
+
+int b200_qk_norm_rope(const b200_qk_norm_rope_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
