@@ -1,0 +1,266 @@
+"""Sampling loops for the hot path when the reference package is not installed (the GPU box).
+
+`StableDiffusionXLPipeline` / `FluxPipeline` here take the same component objects and the same
+embedding-level call arguments as the reference pipelines (pipelines/stable_diffusion_xl/
+pipeline_stable_diffusion_xl.py:823-1308, pipelines/flux/pipeline_flux.py:600-970) and run the same sequence:
+prepare latents -> set timesteps -> [scale -> denoiser -> CFG -> scheduler.step] x N -> VAE decode -> postprocess.
+Text encoders / tokenizers are out of scope: prompts enter as embeddings, which is also how
+the north-star benchmark feeds them.
+
+`fused=True` (default) keeps the loop state on the device in the kernels' native layout: one CUDA-graph replay
+of the NHWC UNet forward plus ONE fused CFG + Euler + next-input kernel per step, no per-step layout changes.
+`fused=False` drives the drop-in `unet.forward` / `scheduler.step` API exactly like the reference loop.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def randn_tensor(shape, generator=None, device=None, dtype=None):
+    """utils/torch_utils.py:183-233: a CPU generator draws on the CPU and the tensor is moved afterwards, so seeds
+    reproduce across devices; a list of generators seeds every sample separately."""
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    rand_device = device
+    if generator is not None:
+        gen_type = generator[0].device.type if isinstance(generator, list) else generator.device.type
+        if gen_type != device.type and gen_type == "cpu":
+            rand_device = torch.device("cpu")
+        elif gen_type != device.type and gen_type == "cuda":
+            raise ValueError(f"Cannot generate a {device} tensor from a generator of type {gen_type}.")
+    if isinstance(generator, list) and len(generator) == 1:
+        generator = generator[0]
+    if isinstance(generator, list):
+        one = (1,) + tuple(shape[1:])
+        lat = [torch.randn(one, generator=generator[i], device=rand_device, dtype=dtype) for i in range(shape[0])]
+        return torch.cat(lat, dim=0).to(device)
+    return torch.randn(tuple(shape), generator=generator, device=rand_device, dtype=dtype).to(device)
+
+
+def postprocess_pt(image):
+    """VaeImageProcessor.postprocess(output_type='pt') (image_processor.py:738, denormalize :222)."""
+    return (image * 0.5 + 0.5).clamp(0, 1)
+
+
+class PipelineOutput:
+    def __init__(self, images):
+        self.images = images
+
+
+class StableDiffusionXLPipeline:
+    def __init__(self, vae, unet, scheduler):
+        self.vae, self.unet, self.scheduler = vae, unet, scheduler
+        self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
+        self.default_sample_size = unet.config.sample_size
+        self._graph = None
+
+    @property
+    def device(self):
+        return self.unet.device
+
+    def prepare_latents(self, batch_size, num_channels, height, width, dtype, device, generator, latents=None):
+        shape = (batch_size, num_channels, int(height) // self.vae_scale_factor, int(width) // self.vae_scale_factor)
+        if latents is None:
+            latents = randn_tensor(shape, generator=generator, device=device, dtype=dtype)
+        else:
+            latents = latents.to(device)
+        return latents * self.scheduler.init_noise_sigma  # 0-dim fp32 CPU tensor * 16-bit tensor -> 16-bit
+
+    # ------------------------------------------------------------------ per-shape graph of the NHWC UNet forward
+    def _get_graph(self, B2, H, W, kv, added):
+        unet = self.unet
+        key = (B2, H, W, tuple(kv.shape), tuple(added["text_embeds"].shape))
+        if self._graph is not None and self._graph["key"] == key:
+            return self._graph
+        dev, dt = unet.device, unet.dtype
+        st = dict(key=key,
+                  x_in=torch.zeros((B2 * H * W, unet.in_pad), dtype=dt, device=dev),
+                  t=torch.zeros((), dtype=torch.float32, device=dev),
+                  kv=torch.empty_like(kv),
+                  added=dict(text_embeds=torch.empty_like(added["text_embeds"]), time_ids=torch.empty_like(added["time_ids"])))
+
+        def run():
+            return unet._forward_nhwc(st["x_in"], B2, H, W, st["t"], st["kv"], st["added"])
+
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            run()  # warm-up outside capture (workspaces, smem attributes, module load)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        n0 = ops.launches()
+        with torch.cuda.graph(g):
+            st["eps"] = run()
+        st["graph"] = g
+        st["launches"] = ops.launches() - n0
+        self._graph = st
+        return st
+
+    @torch.no_grad()
+    def __call__(self, prompt_embeds, negative_prompt_embeds=None, pooled_prompt_embeds=None,
+                 negative_pooled_prompt_embeds=None, height=None, width=None, num_inference_steps=50,
+                 guidance_scale=5.0, generator=None, latents=None, output_type="pt", original_size=None,
+                 crops_coords_top_left=(0, 0), target_size=None, return_dict=True, fused=True):
+        unet, sched = self.unet, self.scheduler
+        device = unet.device
+        height = height or self.default_sample_size * self.vae_scale_factor
+        width = width or self.default_sample_size * self.vae_scale_factor
+        original_size = original_size or (height, width)
+        target_size = target_size or (height, width)
+        do_cfg = guidance_scale > 1 and unet.config.time_cond_proj_dim is None
+        if do_cfg and (negative_prompt_embeds is None or negative_pooled_prompt_embeds is None):
+            raise ValueError("classifier-free guidance needs negative_prompt_embeds and negative_pooled_prompt_embeds")
+        batch = prompt_embeds.shape[0]
+        dtype = prompt_embeds.dtype
+
+        sched.set_timesteps(num_inference_steps, device=device)
+        timesteps = sched.timesteps
+        lat = self.prepare_latents(batch, unet.config.in_channels, height, width, dtype, device, generator, latents)
+
+        add_text = pooled_prompt_embeds
+        add_time_ids = torch.tensor([list(original_size) + list(crops_coords_top_left) + list(target_size)], dtype=dtype)
+        passed = unet.config.addition_time_embed_dim * add_time_ids.shape[1] + int(pooled_prompt_embeds.shape[-1])
+        if unet.add_embedding.linear_1.in_features != passed:
+            raise ValueError(f"Model expects an added time embedding vector of length {unet.add_embedding.linear_1.in_features}, "
+                             f"but a vector of {passed} was created.")
+        neg_time_ids = add_time_ids
+        if do_cfg:
+            prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0)
+            add_text = torch.cat([negative_pooled_prompt_embeds, add_text], dim=0)
+            add_time_ids = torch.cat([neg_time_ids, add_time_ids], dim=0)
+        prompt_embeds = prompt_embeds.to(device)
+        add_text = add_text.to(device)
+        add_time_ids = add_time_ids.to(device).repeat(batch, 1)
+        added = dict(text_embeds=add_text, time_ids=add_time_ids)
+        sched.set_begin_index(0)
+
+        if fused:
+            lat = self._denoise_fused(lat, timesteps, prompt_embeds, added, guidance_scale, do_cfg)
+        else:
+            for t in timesteps:
+                inp = torch.cat([lat] * 2) if do_cfg else lat
+                inp = sched.scale_model_input(inp, t)
+                noise_pred = unet(inp, t, encoder_hidden_states=prompt_embeds, added_cond_kwargs=added, return_dict=False)[0]
+                if do_cfg:
+                    u, c = noise_pred.chunk(2)
+                    noise_pred = u + guidance_scale * (c - u)
+                lat = sched.step(noise_pred, t, lat, return_dict=False)[0]
+
+        if output_type == "latent":
+            image = lat
+        else:
+            lat = lat / self.vae.config.scaling_factor
+            image = self.vae.decode(lat, return_dict=False)[0]
+            image = postprocess_pt(image)
+        if not return_dict:
+            return (image,)
+        return PipelineOutput(image)
+
+    def _denoise_fused(self, lat, timesteps, prompt_embeds, added, guidance_scale, do_cfg):
+        unet, sched = self.unet, self.scheduler
+        B, C, H, W = lat.shape
+        B2 = 2 * B if do_cfg else B
+        lat = lat.to(unet.dtype).contiguous().clone()
+        kv = unet._text_kv(prompt_embeds)
+        st = self._get_graph(B2, H, W, kv, added)
+        st["kv"].copy_(kv)
+        st["added"]["text_embeds"].copy_(added["text_embeds"])
+        st["added"]["time_ids"].copy_(added["time_ids"])
+        sig = sched.sigmas  # host fp32 table
+        # first model input: scale_model_input(cat([latents]*2), t0) in NHWC
+        first = ops.scale_div(torch.cat([lat] * 2) if do_cfg else lat, float((sig[0] ** 2 + 1) ** 0.5))
+        ops.nchw_to_nhwc(first, c_pad=unet.in_pad, out=st["x_in"])
+        n = len(timesteps)
+        for i in range(n):
+            st["t"].copy_(timesteps[i], non_blocking=True)
+            st["graph"].replay()
+            ops._count(st["launches"])
+            ops.cfg_euler_step(st["eps"], lat, st["x_in"], guidance_scale=guidance_scale, do_cfg=do_cfg,
+                               sigma=float(sig[i]), sigma_next=float(sig[i + 1]))
+        sched._step_index = n
+        return lat
+
+
+def calculate_shift(image_seq_len, base_seq_len=256, max_seq_len=4096, base_shift=0.5, max_shift=1.15):
+    """pipelines/flux/pipeline_flux.py:73-84"""
+    m = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+    b = base_shift - m * base_seq_len
+    return image_seq_len * m + b
+
+
+class FluxPipeline:
+    def __init__(self, scheduler, vae, transformer):
+        self.scheduler, self.vae, self.transformer = scheduler, vae, transformer
+        self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
+        self.default_sample_size = 128
+
+    @staticmethod
+    def _prepare_latent_image_ids(height, width, device, dtype):
+        ids = torch.zeros(height, width, 3)
+        ids[..., 1] = ids[..., 1] + torch.arange(height)[:, None]
+        ids[..., 2] = ids[..., 2] + torch.arange(width)[None, :]
+        return ids.reshape(height * width, 3).to(device=device, dtype=dtype)
+
+    @staticmethod
+    def _pack_latents(latents, batch_size, num_channels_latents, height, width):
+        latents = latents.view(batch_size, num_channels_latents, height // 2, 2, width // 2, 2)
+        latents = latents.permute(0, 2, 4, 1, 3, 5)
+        return latents.reshape(batch_size, (height // 2) * (width // 2), num_channels_latents * 4)
+
+    @staticmethod
+    def _unpack_latents(latents, height, width, vae_scale_factor):
+        batch_size, num_patches, channels = latents.shape
+        height = 2 * (int(height) // (vae_scale_factor * 2))
+        width = 2 * (int(width) // (vae_scale_factor * 2))
+        latents = latents.view(batch_size, height // 2, width // 2, channels // 4, 2, 2)
+        latents = latents.permute(0, 3, 1, 4, 2, 5)
+        return latents.reshape(batch_size, channels // 4, height, width)
+
+    def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None):
+        height = 2 * (int(height) // (self.vae_scale_factor * 2))
+        width = 2 * (int(width) // (self.vae_scale_factor * 2))
+        ids = self._prepare_latent_image_ids(height // 2, width // 2, device, dtype)
+        if latents is not None:
+            return latents.to(device=device, dtype=dtype), ids
+        latents = randn_tensor((batch_size, num_channels_latents, height, width), generator=generator, device=device, dtype=dtype)
+        return self._pack_latents(latents, batch_size, num_channels_latents, height, width), ids
+
+    @torch.no_grad()
+    def __call__(self, prompt_embeds, pooled_prompt_embeds, height=None, width=None, num_inference_steps=28,
+                 guidance_scale=3.5, generator=None, latents=None, output_type="latent", return_dict=True):
+        tr, sched = self.transformer, self.scheduler
+        device = tr.device
+        height = height or self.default_sample_size * self.vae_scale_factor
+        width = width or self.default_sample_size * self.vae_scale_factor
+        batch = prompt_embeds.shape[0]
+        dtype = prompt_embeds.dtype
+        prompt_embeds = prompt_embeds.to(device)
+        pooled_prompt_embeds = pooled_prompt_embeds.to(device)
+        text_ids = torch.zeros(prompt_embeds.shape[1], 3).to(device=device, dtype=dtype)
+        lat, img_ids = self.prepare_latents(batch, tr.config.in_channels // 4, height, width, dtype, device, generator, latents)
+        sigmas = np.linspace(1.0, 1 / num_inference_steps, num_inference_steps)
+        c = sched.config
+        mu = calculate_shift(lat.shape[1], c.get("base_image_seq_len", 256), c.get("max_image_seq_len", 4096),
+                             c.get("base_shift", 0.5), c.get("max_shift", 1.15))
+        sched.set_timesteps(num_inference_steps, device=device, sigmas=sigmas, mu=mu)
+        timesteps = sched.timesteps
+        guidance = None
+        if tr.config.guidance_embeds:
+            guidance = torch.full([1], guidance_scale, device=device, dtype=torch.float32).expand(lat.shape[0])
+        sched.set_begin_index(0)
+        for t in timesteps:
+            timestep = t.expand(lat.shape[0]).to(lat.dtype)
+            with tr.cache_context("cond"):
+                noise_pred = tr(hidden_states=lat, timestep=timestep / 1000, guidance=guidance,
+                                pooled_projections=pooled_prompt_embeds, encoder_hidden_states=prompt_embeds,
+                                txt_ids=text_ids, img_ids=img_ids, joint_attention_kwargs=None, return_dict=False)[0]
+            lat = sched.step(noise_pred, t, lat, return_dict=False)[0]
+        if output_type == "latent":
+            image = lat
+        else:
+            lat = self._unpack_latents(lat, height, width, self.vae_scale_factor)
+            lat = (lat / self.vae.config.scaling_factor) + self.vae.config.shift_factor
+            image = postprocess_pt(self.vae.decode(lat, return_dict=False)[0])
+        if not return_dict:
+            return (image,)
+        return PipelineOutput(image)

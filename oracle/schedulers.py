@@ -1,0 +1,192 @@
+"""ORACLE (test infrastructure): CPU restatement of the three schedulers on the path, including their tensor
+math, op for op (so dtype promotion / rounding points are the reference's).
+
+Reference: schedulers/scheduling_euler_discrete.py (__init__ :203-276, set_timesteps :350-482, scale_model_input
+:326-348, step :685-797), schedulers/scheduling_flow_match_euler_discrete.py (__init__ :77-140, time_shift :241,
+set_timesteps :283-386, step :423-530), schedulers/scheduling_ddpm.py (__init__ :166-240, set_timesteps :274-346,
+_get_variance :348-400, step :461-570, previous_timestep :648-670).
+"""
+import math
+
+import numpy as np
+import torch
+
+
+class EulerDiscrete:
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                 timestep_spacing="linspace", steps_offset=0, prediction_type="epsilon"):
+        self.N = num_train_timesteps
+        self.spacing, self.offset, self.prediction_type = timestep_spacing, steps_offset, prediction_type
+        if beta_schedule == "linear":
+            betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        elif beta_schedule == "scaled_linear":
+            betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        else:
+            raise NotImplementedError(beta_schedule)
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).flip(0)
+        self.sigmas = torch.cat([sig, torch.zeros(1)])
+        self.timesteps = torch.from_numpy(np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=float)[::-1].copy()).to(torch.float32)
+        self.step_index = None
+
+    @property
+    def init_noise_sigma(self):
+        m = self.sigmas.max()
+        return m if self.spacing in ("linspace", "trailing") else (m ** 2 + 1) ** 0.5
+
+    def _sigma_to_t(self, sigma, log_sigmas):
+        """:484-516"""
+        log_sigma = np.log(np.maximum(sigma, 1e-10))
+        dists = log_sigma - log_sigmas[:, np.newaxis]
+        low_idx = np.cumsum((dists >= 0), axis=0).argmax(axis=0).clip(max=log_sigmas.shape[0] - 2)
+        high_idx = low_idx + 1
+        low, high = log_sigmas[low_idx], log_sigmas[high_idx]
+        w = np.clip((low - log_sigma) / (low - high), 0, 1)
+        t = (1 - w) * low_idx + w * high_idx
+        return t.reshape(sigma.shape)
+
+    def set_timesteps(self, n=None, sigmas=None):
+        if sigmas is not None:  # custom sigma schedule (:424-427)
+            log_sigmas = np.log(np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5))
+            sigmas = np.array(sigmas).astype(np.float32)
+            ts = np.array([self._sigma_to_t(sigma, log_sigmas) for sigma in sigmas[:-1]])
+            self.sigmas = torch.from_numpy(sigmas).to(dtype=torch.float32)
+            self.timesteps = torch.from_numpy(ts.astype(np.float32))
+            self.step_index = 0
+            return
+        if self.spacing == "linspace":
+            ts = np.linspace(0, self.N - 1, n, dtype=np.float32)[::-1].copy()
+        elif self.spacing == "leading":
+            ts = (np.arange(0, n) * (self.N // n)).round()[::-1].copy().astype(np.float32)
+            ts += self.offset
+        elif self.spacing == "trailing":
+            ts = (np.arange(self.N, 0, -self.N / n)).round().copy().astype(np.float32)
+            ts -= 1
+        else:
+            raise ValueError(self.spacing)
+        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0]]).astype(np.float32))
+        self.timesteps = torch.from_numpy(ts.astype(np.float32))
+        self.step_index = 0
+
+    def scale_model_input(self, sample):
+        sigma = self.sigmas[self.step_index]
+        return sample / ((sigma ** 2 + 1) ** 0.5)
+
+    def step(self, model_output, sample):
+        sample = sample.to(torch.float32)
+        sigma = self.sigmas[self.step_index]
+        if self.prediction_type == "epsilon":
+            pred = sample - sigma * model_output
+        elif self.prediction_type == "v_prediction":
+            pred = model_output * (-sigma / (sigma ** 2 + 1) ** 0.5) + (sample / (sigma ** 2 + 1))
+        else:
+            raise ValueError(self.prediction_type)
+        derivative = (sample - pred) / sigma
+        dt = self.sigmas[self.step_index + 1] - sigma
+        prev = (sample + derivative * dt).to(model_output.dtype)
+        self.step_index += 1
+        return prev
+
+
+class FlowMatchEuler:
+    def __init__(self, num_train_timesteps=1000, shift=1.0, use_dynamic_shifting=False):
+        self.N, self.shift, self.dynamic = num_train_timesteps, shift, use_dynamic_shifting
+        ts = torch.from_numpy(np.linspace(1, num_train_timesteps, num_train_timesteps, dtype=np.float32)[::-1].copy()).to(torch.float32)
+        sig = ts / num_train_timesteps
+        if not use_dynamic_shifting:
+            sig = shift * sig / (1 + (shift - 1) * sig)
+        self.sigmas = sig
+        self.timesteps = sig * num_train_timesteps
+        self.sigma_min, self.sigma_max = sig[-1].item(), sig[0].item()
+        self.step_index = None
+
+    def set_timesteps(self, n=None, sigmas=None, mu=None):
+        if sigmas is None:
+            ts = np.linspace(self.sigma_max * self.N, self.sigma_min * self.N, n)
+            sigmas = ts / self.N
+        else:
+            sigmas = np.array(sigmas).astype(np.float32)
+        if self.dynamic:
+            sigmas = math.exp(mu) / (math.exp(mu) + (1 / sigmas - 1) ** 1.0)
+        else:
+            sigmas = self.shift * sigmas / (1 + (self.shift - 1) * sigmas)
+        sig = torch.from_numpy(sigmas).to(dtype=torch.float32)
+        self.timesteps = sig * self.N
+        self.sigmas = torch.cat([sig, torch.zeros(1)])
+        self.step_index = 0
+
+    def step(self, model_output, sample):
+        sample = sample.to(torch.float32)
+        dt = self.sigmas[self.step_index + 1] - self.sigmas[self.step_index]
+        prev = (sample + dt * model_output).to(model_output.dtype)
+        self.step_index += 1
+        return prev
+
+
+class DDPM:
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                 variance_type="fixed_small", clip_sample=True, clip_sample_range=1.0, timestep_spacing="leading",
+                 steps_offset=0):
+        self.N = num_train_timesteps
+        if beta_schedule == "linear":
+            betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        elif beta_schedule == "scaled_linear":
+            betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        else:
+            raise NotImplementedError(beta_schedule)
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.one = torch.tensor(1.0)
+        self.variance_type, self.clip, self.clip_range = variance_type, clip_sample, clip_sample_range
+        self.spacing, self.offset = timestep_spacing, steps_offset
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy())
+        self.num_inference_steps = None
+
+    def set_timesteps(self, n):
+        self.num_inference_steps = n
+        if self.spacing == "linspace":
+            ts = np.linspace(0, self.N - 1, n).round()[::-1].copy().astype(np.int64)
+        elif self.spacing == "leading":
+            ts = (np.arange(0, n) * (self.N // n)).round()[::-1].copy().astype(np.int64)
+            ts += self.offset
+        elif self.spacing == "trailing":
+            ts = np.round(np.arange(self.N, 0, -self.N / n)).astype(np.int64)
+            ts -= 1
+        else:
+            raise ValueError(self.spacing)
+        self.timesteps = torch.from_numpy(ts)
+
+    def previous_timestep(self, t):
+        if self.num_inference_steps:
+            index = (self.timesteps == t).nonzero(as_tuple=True)[0][0]
+            return torch.tensor(-1) if index == self.timesteps.shape[0] - 1 else self.timesteps[index + 1]
+        return t - 1
+
+    def _get_variance(self, t):
+        prev_t = self.previous_timestep(t)
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+        cur_beta = 1 - a_t / a_prev
+        var = (1 - a_prev) / (1 - a_t) * cur_beta
+        return torch.clamp(var, min=1e-20)
+
+    def step(self, model_output, t, sample, generator=None):
+        prev_t = self.previous_timestep(t)
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+        b_t = 1 - a_t
+        b_prev = 1 - a_prev
+        cur_alpha = a_t / a_prev
+        cur_beta = 1 - cur_alpha
+        x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+        if self.clip:
+            x0 = x0.clamp(-self.clip_range, self.clip_range)
+        c0 = (a_prev ** 0.5 * cur_beta) / b_t
+        c1 = cur_alpha ** 0.5 * b_prev / b_t
+        prev = c0 * x0 + c1 * sample
+        variance = 0
+        if t > 0:
+            noise = torch.randn(model_output.shape, generator=generator, dtype=model_output.dtype)
+            variance = (self._get_variance(t) ** 0.5) * noise
+        return prev + variance

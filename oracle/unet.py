@@ -10,6 +10,7 @@ Reference: models/unets/unet_2d_condition.py:979-1240, unet_2d_blocks.py:1239-12
 import torch
 import torch.nn.functional as F
 
+from . import blocks as Bk
 from . import nn as O
 
 
@@ -58,44 +59,25 @@ def unet2d_condition_forward(sd, cfg, sample, timestep, encoder_hidden_states, a
     # ---- down blocks
     for i in range(n_down):
         p = f"down_blocks.{i}"
-        n_res = _count(sd, p + ".resnets.{}.norm1.weight")
-        has_attn = (p + ".attentions.0.norm.weight") in sd
-        for j in range(n_res):
-            x = O.resnet_block(sd, f"{p}.resnets.{j}", x, emb, groups, eps)
-            if has_attn:
-                n_layers = _count(sd, f"{p}.attentions.{j}.transformer_blocks." + "{}.norm1.weight")
-                x = O.transformer_2d(sd, f"{p}.attentions.{j}", x, encoder_hidden_states, heads[i], n_layers, groups, use_lin)
-            skips += (x,)
-        if (p + ".downsamplers.0.conv.weight") in sd:
-            x = O.downsample2d(sd, p + ".downsamplers.0", x)
-            skips += (x,)
-    # ---- mid block (UNetMidBlock2DCrossAttn :854)
+        if (p + ".attentions.0.norm.weight") in sd:
+            x, outs = Bk.cross_attn_down_block_2d(sd, p, x, emb, encoder_hidden_states, heads[i], groups, eps, use_lin)
+        else:
+            x, outs = Bk.down_block_2d(sd, p, x, emb, groups, eps)
+        skips += outs
+    # ---- mid block
     if "mid_block.resnets.0.norm1.weight" in sd:
-        x = O.resnet_block(sd, "mid_block.resnets.0", x, emb, groups, eps)
-        n_attn = _count(sd, "mid_block.attentions.{}.norm.weight")
-        for j in range(n_attn):
-            n_layers = _count(sd, f"mid_block.attentions.{j}.transformer_blocks." + "{}.norm1.weight")
-            x = O.transformer_2d(sd, f"mid_block.attentions.{j}", x, encoder_hidden_states, heads[-1], n_layers, groups, use_lin)
-            x = O.resnet_block(sd, f"mid_block.resnets.{j + 1}", x, emb, groups, eps)
+        x = Bk.unet_mid_block_2d_cross_attn(sd, "mid_block", x, emb, encoder_hidden_states, heads[-1], groups, eps, use_lin)
     # ---- up blocks
     n_up = _count(sd, "up_blocks.{}.resnets.0.norm1.weight")
     rev_heads = tuple(reversed(heads))
     for i in range(n_up):
         p = f"up_blocks.{i}"
         n_res = _count(sd, p + ".resnets.{}.norm1.weight")
-        has_attn = (p + ".attentions.0.norm.weight") in sd
-        res = skips[-n_res:]
-        skips = skips[:-n_res]
-        for j in range(n_res):
-            r = res[-1]
-            res = res[:-1]
-            x = torch.cat([x, r], dim=1)
-            x = O.resnet_block(sd, f"{p}.resnets.{j}", x, emb, groups, eps)
-            if has_attn:
-                n_layers = _count(sd, f"{p}.attentions.{j}.transformer_blocks." + "{}.norm1.weight")
-                x = O.transformer_2d(sd, f"{p}.attentions.{j}", x, encoder_hidden_states, rev_heads[i], n_layers, groups, use_lin)
-        if (p + ".upsamplers.0.conv.weight") in sd:
-            x = O.upsample2d(sd, p + ".upsamplers.0", x)
+        res, skips = skips[-n_res:], skips[:-n_res]
+        if (p + ".attentions.0.norm.weight") in sd:
+            x = Bk.cross_attn_up_block_2d(sd, p, x, res, emb, encoder_hidden_states, rev_heads[i], groups, eps, use_lin)
+        else:
+            x = Bk.up_block_2d(sd, p, x, res, emb, groups, eps)
     x = O.group_norm(sd, "conv_norm_out", x, groups, eps)
     x = F.silu(x)
     return O.conv2d(sd, "conv_out", x)
@@ -117,47 +99,27 @@ def unet2d_forward(sd, cfg, sample, timestep):
                                      downscale_freq_shift=cfg.get("freq_shift", 0)).to(sample.dtype)
     emb = O.timestep_embedding_mlp(sd, "time_embedding", t_emb)
 
-    def attn(prefix, h):
-        c = h.shape[1]
-        heads = c // head_dim if head_dim is not None else 1
-        return O.attention(sd, prefix, h, None, heads, norm_groups=groups, group_norm_eps=eps, residual_connection=True,
-                           rescale_output_factor=1.0)
-
     x = O.conv2d(sd, "conv_in", sample)
     skips = (x,)
     n_down = _count(sd, "down_blocks.{}.resnets.0.norm1.weight")
+    pad = cfg.get("downsample_padding", 1)
     for i in range(n_down):
         p = f"down_blocks.{i}"
-        n_res = _count(sd, p + ".resnets.{}.norm1.weight")
-        has_attn = (p + ".attentions.0.to_q.weight") in sd
-        for j in range(n_res):
-            x = O.resnet_block(sd, f"{p}.resnets.{j}", x, emb, groups, eps)
-            if has_attn:
-                x = attn(f"{p}.attentions.{j}", x)
-            skips += (x,)
-        if (p + ".downsamplers.0.conv.weight") in sd:
-            x = O.downsample2d(sd, p + ".downsamplers.0", x, padding=cfg.get("downsample_padding", 1))
-            skips += (x,)
-    x = O.resnet_block(sd, "mid_block.resnets.0", x, emb, groups, eps)
-    if "mid_block.attentions.0.to_q.weight" in sd:
-        x = attn("mid_block.attentions.0", x)
-    x = O.resnet_block(sd, "mid_block.resnets.1", x, emb, groups, eps)
+        if (p + ".attentions.0.to_q.weight") in sd:
+            x, outs = Bk.attn_down_block_2d(sd, p, x, emb, head_dim, groups, eps, pad)
+        else:
+            x, outs = Bk.down_block_2d(sd, p, x, emb, groups, eps, pad)
+        skips += outs
+    x = Bk.unet_mid_block_2d(sd, "mid_block", x, emb, head_dim, groups, eps)
     n_up = _count(sd, "up_blocks.{}.resnets.0.norm1.weight")
     for i in range(n_up):
         p = f"up_blocks.{i}"
         n_res = _count(sd, p + ".resnets.{}.norm1.weight")
-        has_attn = (p + ".attentions.0.to_q.weight") in sd
-        res = skips[-n_res:]
-        skips = skips[:-n_res]
-        for j in range(n_res):
-            r = res[-1]
-            res = res[:-1]
-            x = torch.cat([x, r], dim=1)
-            x = O.resnet_block(sd, f"{p}.resnets.{j}", x, emb, groups, eps)
-            if has_attn:
-                x = attn(f"{p}.attentions.{j}", x)
-        if (p + ".upsamplers.0.conv.weight") in sd:
-            x = O.upsample2d(sd, p + ".upsamplers.0", x)
+        res, skips = skips[-n_res:], skips[:-n_res]
+        if (p + ".attentions.0.to_q.weight") in sd:
+            x = Bk.attn_up_block_2d(sd, p, x, res, emb, head_dim, groups, eps)
+        else:
+            x = Bk.up_block_2d(sd, p, x, res, emb, groups, eps)
     x = O.group_norm(sd, "conv_norm_out", x, groups, eps)
     x = F.silu(x)
     return O.conv2d(sd, "conv_out", x)

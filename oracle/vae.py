@@ -7,6 +7,7 @@ the attention, residual connection), :2575-2660 (UpDecoderBlock2D).
 """
 import torch.nn.functional as F
 
+from . import blocks as Bk
 from . import nn as O
 
 
@@ -23,18 +24,9 @@ def vae_decode(sd, cfg, z):
     if "post_quant_conv.weight" in sd:
         z = O.conv2d(sd, "post_quant_conv", z, padding=0)
     x = O.conv2d(sd, "decoder.conv_in", z)
-    x = O.resnet_block(sd, "decoder.mid_block.resnets.0", x, None, groups, eps)
-    if "decoder.mid_block.attentions.0.to_q.weight" in sd:
-        x = O.attention(sd, "decoder.mid_block.attentions.0", x, None, heads=1, norm_groups=groups, group_norm_eps=eps,
-                        residual_connection=True, rescale_output_factor=1.0)
-    x = O.resnet_block(sd, "decoder.mid_block.resnets.1", x, None, groups, eps)
-    n_up = _count(sd, "decoder.up_blocks.{}.resnets.0.norm1.weight")
-    for i in range(n_up):
-        p = f"decoder.up_blocks.{i}"
-        for j in range(_count(sd, p + ".resnets.{}.norm1.weight")):
-            x = O.resnet_block(sd, f"{p}.resnets.{j}", x, None, groups, eps)
-        if (p + ".upsamplers.0.conv.weight") in sd:
-            x = O.upsample2d(sd, p + ".upsamplers.0", x)
+    x = Bk.unet_mid_block_2d(sd, "decoder.mid_block", x, None, None, groups, eps)
+    for i in range(_count(sd, "decoder.up_blocks.{}.resnets.0.norm1.weight")):
+        x = Bk.up_decoder_block_2d(sd, f"decoder.up_blocks.{i}", x, groups, eps)
     x = O.group_norm(sd, "decoder.conv_norm_out", x, groups, eps)
     x = F.silu(x)
     return O.conv2d(sd, "decoder.conv_out", x)

@@ -1,0 +1,126 @@
+"""CPU tests of the host-side logic: schedule construction (bit-identical to the reference tables), weight
+packing, parameter specs, latent/RNG contract helpers, config objects."""
+import numpy as np
+import pytest
+import torch
+
+from diffusers_b200 import packing, specs
+from diffusers_b200 import schedulers as S
+from diffusers_b200.config import FrozenConfig
+from diffusers_b200.pipelines import FluxPipeline, calculate_shift, randn_tensor
+
+
+def test_euler_tables_bit_identical_to_reference(golden):
+    fx = golden("schedulers")["euler_sdxl"]
+    for n, tab in fx["tables"].items():
+        s = S.EulerDiscreteScheduler(**fx["config"])
+        s.set_timesteps(n)
+        assert torch.equal(s.sigmas, tab["sigmas"]) and torch.equal(s.timesteps, tab["timesteps"])
+        assert float(s.init_noise_sigma) == tab["init_noise_sigma"]
+        assert s.order == 1 and s.config.num_train_timesteps == 1000
+
+
+def test_flow_match_tables_bit_identical_to_reference(golden):
+    fx = golden("schedulers")["flow_match_flux"]
+    for (n, seq), tab in fx["tables"].items():
+        s = S.FlowMatchEulerDiscreteScheduler(**fx["config"])
+        s.set_timesteps(n, sigmas=np.linspace(1.0, 1 / n, n), mu=calculate_shift(seq))
+        assert torch.equal(s.sigmas, tab["sigmas"]) and torch.equal(s.timesteps, tab["timesteps"])
+        assert abs(calculate_shift(seq) - tab["mu"]) < 1e-12
+    with pytest.raises(ValueError):
+        S.FlowMatchEulerDiscreteScheduler(**fx["config"]).set_timesteps(4)  # dynamic shifting needs mu
+
+
+def test_scheduler_rejects_unsupported_options():
+    with pytest.raises(NotImplementedError):
+        S.EulerDiscreteScheduler(use_karras_sigmas=True)
+    with pytest.raises(NotImplementedError):
+        S.EulerDiscreteScheduler(prediction_type="v_prediction")
+
+
+def test_pack_conv_weight_layout():
+    torch.manual_seed(0)
+    w = torch.randn(5, 12, 3, 3)
+    p = packing.pack_conv_weight(w)
+    assert p.shape == (5, 9 * 64)
+    for tap in range(9):
+        r, s = divmod(tap, 3)
+        assert torch.equal(p[:, tap * 64: tap * 64 + 12], w[:, :, r, s])
+        assert not p[:, tap * 64 + 12:(tap + 1) * 64].any()
+    p2 = packing.pack_conv_weight(w, split=(8, 4))
+    assert p2.shape == (5, 9 * 128)
+    assert torch.equal(p2[:, 128 * 4: 128 * 4 + 8], w[:, :8, 1, 1]) and torch.equal(p2[:, 128 * 4 + 64: 128 * 4 + 68], w[:, 8:, 1, 1])
+
+
+def test_pack_geglu_interleave():
+    w = torch.arange(16 * 4, dtype=torch.float32).reshape(16, 4)  # inner = 8
+    b = torch.arange(16, dtype=torch.float32)
+    wp, bp = packing.pack_geglu(w, b, tile_n=8)  # tiles of 4 value + 4 gate rows
+    assert torch.equal(bp, torch.tensor([0., 1, 2, 3, 8, 9, 10, 11, 4, 5, 6, 7, 12, 13, 14, 15]))
+    assert torch.equal(wp[:4, :4], w[:4]) and torch.equal(wp[4:8, :4], w[8:12]) and torch.equal(wp[8:12, :4], w[4:8])
+
+
+def test_specs_full_size_parameter_counts():
+    n = lambda spec: sum(int(np.prod(s)) for s in spec.values())  # noqa: E731
+    assert n(specs.unet2d_condition_params(specs.SDXL_UNET_CONFIG)) == 2_567_463_684
+    assert n(specs.flux_params(specs.FLUX_DEV_CONFIG)) == 11_901_408_320               # config 2
+    assert n(specs.vae_decoder_params(specs.SDXL_VAE_CONFIG)) == 49_490_199  # decoder 49.49 M + post_quant_conv
+
+
+def test_specs_match_reference_state_dicts():
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference not present on this box")
+    d = ref_shim.import_reference()
+    with torch.device("meta"):
+        pairs = [(d.UNet2DConditionModel(**specs.SDXL_UNET_CONFIG).state_dict(), specs.unet2d_condition_params(specs.SDXL_UNET_CONFIG)),
+                 (d.FluxTransformer2DModel(**specs.FLUX_DEV_CONFIG).state_dict(), specs.flux_params(specs.FLUX_DEV_CONFIG)),
+                 (d.UNet2DModel(**specs.DDPM_TINY_CONFIG).state_dict(), specs.unet2d_params(specs.DDPM_TINY_CONFIG))]
+        v = d.AutoencoderKL(**specs.SDXL_VAE_CONFIG).state_dict()
+        pairs.append(({k: t for k, t in v.items() if k.startswith(("decoder", "post_quant"))}, specs.vae_decoder_params(specs.SDXL_VAE_CONFIG)))
+    for ref, mine in pairs:
+        assert {k: tuple(t.shape) for k, t in ref.items()} == {k: tuple(s) for k, s in mine.items()}
+
+
+def test_randn_tensor_contract():
+    """CPU generator => CPU draw (device independent seeds); list of generators => per-sample seeding."""
+    a = randn_tensor((2, 4, 8, 8), generator=torch.Generator().manual_seed(0), device="cpu", dtype=torch.float32)
+    b = torch.randn((2, 4, 8, 8), generator=torch.Generator().manual_seed(0))
+    assert torch.equal(a, b)
+    c = randn_tensor((2, 3), generator=[torch.Generator().manual_seed(1), torch.Generator().manual_seed(2)], device="cpu", dtype=torch.float32)
+    assert torch.equal(c[0:1], torch.randn((1, 3), generator=torch.Generator().manual_seed(1)))
+    assert torch.equal(c[1:2], torch.randn((1, 3), generator=torch.Generator().manual_seed(2)))
+
+
+def test_flux_pack_unpack_roundtrip():
+    x = torch.randn(2, 16, 8, 12)
+    p = FluxPipeline._pack_latents(x, 2, 16, 8, 12)
+    assert p.shape == (2, 24, 64)
+    assert torch.equal(FluxPipeline._unpack_latents(p, 8 * 8, 12 * 8, 8), x)
+    ids = FluxPipeline._prepare_latent_image_ids(4, 6, "cpu", torch.float32)
+    assert ids.shape == (24, 3) and ids[7].tolist() == [0, 1, 1]
+
+
+def test_frozen_config():
+    c = FrozenConfig(a=1, b=None)
+    assert c.a == 1 and c["a"] == 1 and c.get("zz", 5) == 5 and c.b is None
+    with pytest.raises(TypeError):
+        c.a = 2
+    with pytest.raises(AttributeError):
+        c.missing
+
+
+def test_models_refuse_cpu_tensors():
+    from diffusers_b200 import ops
+    from diffusers_b200.unet_2d_condition import UNet2DConditionModel
+    cfg = dict(sample_size=16, block_out_channels=(64, 128), down_block_types=("DownBlock2D", "CrossAttnDownBlock2D"),
+               up_block_types=("CrossAttnUpBlock2D", "UpBlock2D"), cross_attention_dim=64, transformer_layers_per_block=(1, 1),
+               attention_head_dim=(1, 2), addition_time_embed_dim=8, projection_class_embeddings_input_dim=6 * 8 + 16, layers_per_block=1)
+    m = UNet2DConditionModel.random_init(cfg, device="cpu")
+    with pytest.raises(ops.B200Error):
+        m(torch.zeros(1, 4, 16, 16), torch.tensor(1.0), torch.zeros(1, 7, 64),
+          added_cond_kwargs=dict(text_embeds=torch.zeros(1, 16), time_ids=torch.zeros(1, 6)))
+    bad = dict(cfg)
+    bad["attention_head_dim"] = (2, 4)  # head_dim 32: not supported by the tcgen05 attention kernel
+    with pytest.raises(NotImplementedError):
+        UNet2DConditionModel.random_init(bad, device="cpu")
