@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): images/sec, SDXL 1024x1024, 50 Euler steps, CFG, bf16, batch 1 per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload sdxl|flux|vae]
+
+A "step" is one full pass of the hot path over one batch: one image = 50 x (CFG-batched UNet forward + fused
+CFG/Euler step) + VAE decode to a (1,3,1024,1024) tensor (output_type="pt").  Prints ONE JSON line (rank 0).
+  value : images/s, embeddings already resident in HBM when the timed region starts (seeded latent draw included)
+  e2e   : same metric through the public pipeline call with HOST (pinned) embeddings: H2D of the embeddings and
+          D2H of the finished image inside the timed region
+  roofline : the dominant kernel (conv_gemm_kernel: every Linear and Conv of the UNet) timed launch by launch with
+          CUDA events on the launching stream in a separate eager pass of one UNet forward; achieved = algorithmic
+          FLOPs of those launches / their summed duration, peak = measured sustained bf16 GEMM (MEASURED_PEAKS.json)
+  cpu_baseline : the oracle port (the reference's op sequence in torch on the host cores) on a bounded sample
+--impl reference times that CPU port as the reference arm.  Multi-GPU: one process per GPU (torchrun), each rank
+samples its own image (weak scaling), one all-gather of the decoded images per step, max-over-ranks device timing.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+UNET_FLOP_PER_SAMPLE = 6.7612e12      # BASELINE.md §3 (FlopCounterMode on the reference, meta device)
+UNET_GEMM_FLOP_PER_SAMPLE = (3325.3 + 1623.1 + 1028.9) * 1e9  # addmm + conv + mm: what conv_gemm_kernel executes
+VAE_FLOP_PER_IMAGE = 10.470e12
+FLUX_FLOP_PER_FORWARD = 74.385e12
+IMAGE_FLOP = 2 * 50 * UNET_FLOP_PER_SAMPLE + VAE_FLOP_PER_IMAGE  # 686.6 TFLOP
+SDXL_SCHED = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="leading", steps_offset=1)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), burst=d["bf16_tflops"], source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, burst=1590.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+
+
+def synthetic_embeds(batch, dtype, pin):
+    g = torch.Generator().manual_seed(1)
+    mk = lambda *s: torch.randn(*s, generator=g).to(dtype)  # noqa: E731
+    t = dict(prompt_embeds=mk(batch, 77, 2048), negative_prompt_embeds=mk(batch, 77, 2048), pooled_prompt_embeds=mk(batch, 1280),
+             negative_pooled_prompt_embeds=mk(batch, 1280))
+    if pin:
+        t = {k: v.pin_memory() for k, v in t.items()}
+    return t
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def cpu_reference(args, full=True):
+    """The oracle port (reference op sequence, torch CPU kernels, all host threads) on a bounded sample."""
+    from diffusers_b200 import specs
+    from oracle import unet as ounet
+    from oracle import vae as ovae
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dt = torch.bfloat16
+    t0 = time.time()
+    usd = specs.random_state_dict(specs.unet2d_condition_params(specs.SDXL_UNET_CONFIG), seed=0, dtype=dt)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 128, 128, generator=g).to(dt)
+    ehs = torch.randn(2, 77, 2048, generator=g).to(dt)
+    te = torch.randn(2, 1280, generator=g).to(dt)
+    tid = torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * 2).to(dt)
+    fwd = lambda: ounet.unet2d_condition_forward(usd, specs.SDXL_UNET_CONFIG, x, torch.tensor(981.0), ehs, dict(text_embeds=te, time_ids=tid))  # noqa: E731
+    with torch.no_grad():
+        n_w, n_t = (args.warmup, args.steps) if full else (1, 2)
+        for _ in range(max(1, min(n_w, 3))):
+            fwd()
+        ts = []
+        for _ in range(max(1, min(n_t, 6))):
+            a = time.perf_counter()
+            fwd()
+            ts.append(time.perf_counter() - a)
+        t_unet = sum(ts) / len(ts)
+        t_vae = None
+        if full:
+            vsd = specs.random_state_dict(specs.vae_decoder_params(specs.SDXL_VAE_CONFIG), seed=0, dtype=dt)
+            z = torch.randn(1, 4, 128, 128, generator=g).to(dt)
+            a = time.perf_counter()
+            ovae.vae_decode(vsd, specs.SDXL_VAE_CONFIG, z)
+            t_vae = time.perf_counter() - a
+    t_vae_eff = t_vae if t_vae is not None else 13.5 * 8 / cores
+    ips = 1.0 / (50 * t_unet + t_vae_eff)
+    sample = (f"{len(ts)} timed CFG-batched (B=2) SDXL UNet forwards at 1024^2 in bf16 ({t_unet:.2f} s each)"
+              + (f" + 1 VAE decode ({t_vae:.1f} s)" if t_vae is not None else " (VAE decode time extrapolated)")
+              + "; images/s = 1/(50*t_unet + t_vae)")
+    return dict(value=ips, unit="images/s", cores=cores, kind="port", sample=sample, t_unet_b2_s=t_unet, t_vae_s=t_vae,
+                setup_s=round(time.time() - t0, 1))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cb = cpu_reference(args, full=True)
+    line = dict(metric="images/sec @ SDXL 1024^2 50-step", value=cb["value"], unit="images/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1000.0 / cb["value"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="bf16", data="synthetic", impl="reference",
+                config=dict(workload="sdxl_unet_1024_50step_cfg_b1", note="reference op sequence on host cores (oracle port), bounded sample"),
+                cpu_baseline={k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                e2e=dict(value=cb["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def gemm_roofline(unet, B2, pk):
+    """Eager pass of one UNet forward with CUDA events around every conv_gemm launch."""
+    from diffusers_b200 import ops
+    dev, dt = unet.device, unet.dtype
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(B2, 4, 128, 128, generator=g, device=dev).to(dt)
+    ehs = torch.randn(B2, 77, 2048, generator=g, device=dev).to(dt)
+    added = dict(text_embeds=torch.randn(B2, 1280, generator=g, device=dev).to(dt),
+                 time_ids=torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * B2, device=dev).to(dt))
+    t = torch.tensor(981.0, device=dev)
+    was = unet.use_cuda_graph
+    unet.enable_cuda_graph(False)
+    for _ in range(2):
+        unet(x, t, ehs, added_cond_kwargs=added, return_dict=False)
+    torch.cuda.synchronize()
+    ops._PROFILE = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    unet(x, t, ehs, added_cond_kwargs=added, return_dict=False)
+    e1.record()
+    torch.cuda.synchronize()
+    prof, ops._PROFILE = ops._PROFILE, None
+    unet.use_cuda_graph = was
+    ms = [a.elapsed_time(b) for a, b, *_ in prof]
+    flops = sum(p[2] for p in prof)
+    total_ms = sum(ms)
+    ach = flops / (total_ms * 1e-3) / 1e12
+    return dict(bound="tensor", achieved=round(ach, 1), peak=pk["tflops"], unit="TFLOP/s", frac=round(ach / pk["tflops"], 4), traffic=None,
+                kernel="conv_gemm_kernel", launches_per_forward=len(prof), algorithmic_flop_per_forward=flops,
+                avg_launch_us=round(1000 * total_ms / len(prof), 2), kernel_ms_per_forward=round(total_ms, 3),
+                forward_ms_eager=round(e0.elapsed_time(e1), 3), share_of_forward=round(total_ms / e0.elapsed_time(e1), 3),
+                peak_source=pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)")
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from diffusers_b200 import ops, parallel, specs
+    from diffusers_b200.autoencoder_kl import AutoencoderKL
+    from diffusers_b200.pipelines import StableDiffusionXLPipeline
+    from diffusers_b200.schedulers import EulerDiscreteScheduler
+    from diffusers_b200.unet_2d_condition import UNet2DConditionModel
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dt = torch.bfloat16
+    pk = peaks()
+    unet = UNet2DConditionModel.random_init(seed=0, dtype=dt, device=dev)
+    vae = AutoencoderKL.random_init(seed=0, dtype=dt, device=dev)
+    pipe = StableDiffusionXLPipeline(vae, unet, EulerDiscreteScheduler(**SDXL_SCHED))
+    B = args.batch
+    host = synthetic_embeds(B, dt, pin=True)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    call = dict(height=1024, width=1024, num_inference_steps=args.denoise_steps, guidance_scale=args.guidance_scale, output_type="pt")
+
+    def one_image(emb, seed, to_host):
+        img = pipe(generator=torch.Generator(device=dev).manual_seed(seed), **emb, **call).images
+        if world > 1:
+            img = parallel.all_gather_batch(img, B * world) if B * world > 1 else img
+        if to_host:
+            out = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
+            out.copy_(img, non_blocking=True)
+            return out
+        return img
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(emb_fn, to_host):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ops.launches()
+        e0.record()
+        for i in range(args.steps):
+            one_image(emb_fn(), 1000 + i, to_host)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, ops.launches() - n0
+
+    for i in range(args.warmup):
+        one_image(resident, i, False)
+    with ClockSampler(local_rank) as cs:
+        ms, launches = timed(lambda: resident, False)
+    clocks = cs.summary()
+    # end to end: host-pinned embeddings in, image back on the host, through the public pipeline call
+    one_image({k: v.to(dev, non_blocking=True) for k, v in host.items()}, 0, True)
+    ms_e2e, _ = timed(lambda: {k: v.to(dev, non_blocking=True) for k, v in host.items()}, True)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = B * (world if world > 1 and B * world > 1 else 1) * 3 * 1024 * 1024 * 2
+
+    n_img = args.steps * B * world
+    value = n_img / (ms * 1e-3)
+    line = None
+    if rank == 0:
+        roof = gemm_roofline(unet, 2 * B, pk)
+        flops_per_img = 2 * args.denoise_steps * UNET_FLOP_PER_SAMPLE + VAE_FLOP_PER_IMAGE
+        cb = cpu_reference(args, full=False) if world == 1 and not args.no_cpu_baseline else None
+        line = dict(metric="images/sec @ SDXL 1024^2 50-step", value=round(value, 4), unit="images/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="bf16", data="synthetic (random-init weights, N(0,1) text embeddings, seeded latents)",
+                    config=dict(workload=f"sdxl_unet_1024_{args.denoise_steps}step_cfg{args.guidance_scale}_b{B}_per_gpu+vae_decode",
+                                global_batch=B * world, parallelism=f"dp{world}", cfg_batched=True,
+                                l2="per-step working set >> L2: 5.1 GB of weights stream from HBM every UNet forward",
+                                model="UNet2DConditionModel SDXL-base config (2.567 B params) + AutoencoderKL SDXL decoder"),
+                    e2e=dict(value=round(n_img / (ms_e2e * 1e-3), 4), unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                    gpu_launches=launches, clocks=clocks, roofline=roof,
+                    model_flops=dict(tflop_per_image=round(flops_per_img / 1e12, 1),
+                                     achieved_tflops_per_gpu=round(value / world * flops_per_img / 1e12, 1),
+                                     frac_of_peak=round(value / world * flops_per_img / 1e12 / pk["tflops"], 4)))
+        if cb is not None:
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="images per GPU per step")
+    ap.add_argument("--denoise-steps", type=int, default=50)
+    ap.add_argument("--guidance-scale", type=float, default=7.5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -9,6 +9,7 @@ from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_SILU, DTYPE_BF16, 
                    B200Error)
 
 _LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+_PROFILE = None  # bench.py: list collecting (start_event, end_event, algorithmic_flops, M, N, K) per conv_gemm launch
 
 
 def launches():
@@ -76,7 +77,15 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
     a.dtype = _dtype_code(x)
     a.tile_n = tile_n
     a.out_fp32 = 1 if out_fp32 else 0
-    _lib.check(_lib.lib().b200_conv_gemm(C.byref(a), _stream()), "b200_conv_gemm")
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(_lib.lib().b200_conv_gemm(C.byref(a), _stream()), "b200_conv_gemm")
+        e1.record()
+        M_, K_ = batch * Ho * Wo, ksize * ksize * (c0 + c1)
+        _PROFILE.append((e0, e1, 2.0 * M_ * N * K_, M_, N, K_))
+    else:
+        _lib.check(_lib.lib().b200_conv_gemm(C.byref(a), _stream()), "b200_conv_gemm")
     _count()
     return out
 

@@ -51,3 +51,41 @@ def test_conv_gemm_rejects_bad_arguments():
     w = torch.zeros(64, 9 * 64, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(ops.B200Error):  # stride 2 needs even H, W
         ops.conv_gemm(x.view(-1, 64), w, 64, batch=1, H=15, W=15, ksize=3, stride=2)
+
+
+def test_attention_processor_plugin_matches_reference_processor_math():
+    """B200AttnProcessor on a module shaped like the reference's `Attention` (to_q/to_k/to_v/to_out, heads) against
+    AttnProcessor2_0's op sequence (models/attention_processor.py:2705-2789) in fp32."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from diffusers_b200.attention_processor import B200AttnProcessor, b200_attention_backend
+
+    class FakeAttention(nn.Module):
+        def __init__(self, dim, cross, heads):
+            super().__init__()
+            self.heads = heads
+            self.to_q, self.to_k, self.to_v = nn.Linear(dim, dim, bias=False), nn.Linear(cross, dim, bias=False), nn.Linear(cross, dim, bias=False)
+            self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
+            self.residual_connection, self.rescale_output_factor = False, 1.0
+
+    torch.manual_seed(0)
+    attn = FakeAttention(640, 2048, 10).cuda().bfloat16()
+    x = torch.randn(2, 256, 640, device="cuda").bfloat16()
+    ctx = torch.randn(2, 77, 2048, device="cuda").bfloat16()
+    proc = B200AttnProcessor()
+    for enc in (None, ctx):
+        a = FakeAttention(640, 2048 if enc is not None else 640, 10).cuda().bfloat16() if enc is None else attn
+        out = proc(a, x, encoder_hidden_states=enc)
+        c = x if enc is None else enc
+        lin = lambda m, t: F.linear(t.float(), m.weight.float(), None if m.bias is None else m.bias.float())  # noqa: E731
+        q, k, v = lin(a.to_q, x), lin(a.to_k, c), lin(a.to_v, c)
+        sp = lambda t: t.view(2, -1, 10, 64).transpose(1, 2)  # noqa: E731
+        ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(2, 256, 640)
+        ref = lin(a.to_out[0], ref)
+        assert (out.float() - ref).abs().max() < 3e-2
+    q = torch.randn(1, 512, 4, 128, device="cuda").bfloat16()
+    o = b200_attention_backend(q, q, q)
+    ref = F.scaled_dot_product_attention(*(t.float().permute(0, 2, 1, 3) for t in (q, q, q))).permute(0, 2, 1, 3)
+    assert o.shape == q.shape and (o.float() - ref).abs().max() < 2e-2
+    with pytest.raises(NotImplementedError):
+        b200_attention_backend(q, q, q, is_causal=True)

@@ -25,27 +25,35 @@ def _sdxl(fx, fused):
     kw = dict(prompt_embeds=bf(fx["prompt_embeds"]), negative_prompt_embeds=bf(fx["negative_prompt_embeds"]),
               pooled_prompt_embeds=bf(fx["pooled"]), negative_pooled_prompt_embeds=bf(fx["negative_pooled"]),
               height=fx["height"], width=fx["width"], num_inference_steps=fx["steps"], guidance_scale=fx["guidance_scale"], fused=fused)
-    lat = pipe(generator=torch.Generator().manual_seed(fx["latent_seed"]), output_type="latent", **kw).images
-    img = pipe(generator=torch.Generator().manual_seed(fx["latent_seed"]), output_type="pt", **kw).images
+    # the recorded fp32 run drew its latents in fp32; a bf16 draw from the same seed is a different sequence, so
+    # the seeded fp32 draw is passed explicitly (prepare_latents scales user latents the same way, :722-726)
+    lat0 = _latents0(fx).bfloat16()
+    lat = pipe(latents=lat0, output_type="latent", **kw).images
+    img = pipe(latents=lat0, output_type="pt", **kw).images
     return lat, img
+
+
+def _latents0(fx):
+    return torch.randn((1, 4, fx["height"] // 8, fx["width"] // 8), generator=torch.Generator().manual_seed(fx["latent_seed"]))
 
 
 def _oracle_bf16_distance(fx):
     from oracle import pipelines as opipe
     from oracle import schedulers as osched
     usd, _ = state_dicts(specs.unet2d_condition_params(fx["unet_cfg"]), fx["unet_seed"])
-    lat0 = torch.randn((1, 4, fx["height"] // 8, fx["width"] // 8), generator=torch.Generator().manual_seed(fx["latent_seed"]), dtype=torch.bfloat16)
+    vsd, _ = state_dicts(specs.vae_decoder_params(fx["vae_cfg"]), fx["vae_seed"])
+    lat0 = _latents0(fx).bfloat16()
     tid = torch.tensor([[fx["height"], fx["width"], 0, 0, fx["height"], fx["width"]]], dtype=torch.bfloat16)
     bf = lambda t: t.bfloat16()  # noqa: E731
-    lat = opipe.sdxl_sample(usd, fx["unet_cfg"], osched.EulerDiscrete(**fx["scheduler"]), lat0, bf(fx["prompt_embeds"]),
-                            bf(fx["negative_prompt_embeds"]), bf(fx["pooled"]), bf(fx["negative_pooled"]), tid, fx["steps"],
-                            fx["guidance_scale"])
-    return (lat.float() - fx["latents"]).abs()
+    img, lat, _ = opipe.sdxl_sample(usd, fx["unet_cfg"], osched.EulerDiscrete(**fx["scheduler"]), lat0, bf(fx["prompt_embeds"]),
+                                    bf(fx["negative_prompt_embeds"]), bf(fx["pooled"]), bf(fx["negative_pooled"]), tid, fx["steps"],
+                                    fx["guidance_scale"], vsd, fx["vae_cfg"], return_all=True)
+    return (lat.float() - fx["latents"]).abs(), (img.float() - fx["image"]).abs()
 
 
 def test_sdxl_pipeline_fused_and_dropin_paths(golden):
     fx = golden("pipelines")["sdxl_tiny"]
-    ref_err = _oracle_bf16_distance(fx)
+    ref_err, ref_img_err = _oracle_bf16_distance(fx)
     lat_f, img_f = _sdxl(fx, fused=True)
     lat_d, img_d = _sdxl(fx, fused=False)
     for name, lat, img in (("fused", lat_f, img_f), ("drop-in", lat_d, img_d)):
@@ -54,7 +62,9 @@ def test_sdxl_pipeline_fused_and_dropin_paths(golden):
         assert float(e.mean()) <= 1.5 * float(ref_err.mean()) + 2e-3
         assert float(e.max()) <= 2.0 * float(ref_err.max()) + 2e-2
         assert tuple(img.shape) == tuple(fx["image"].shape)
-        assert (img.float().cpu() - fx["image"]).abs().mean() < 2e-2
+        ie = (img.float().cpu() - fx["image"]).abs()
+        print(f"sdxl {name}: image err mean {float(ie.mean()):.4g} | reference-bf16 {float(ref_img_err.mean()):.4g}")
+        assert float(ie.mean()) <= 1.5 * float(ref_img_err.mean()) + 2e-3
         assert float(img.min()) >= 0 and float(img.max()) <= 1
     # the fused CFG+Euler kernel and the drop-in unet.forward / scheduler.step loop are the same computation
     assert (lat_f.float() - lat_d.float()).abs().max() < 1e-1
