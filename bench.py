@@ -275,8 +275,79 @@ def run_b200(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
 
 
+def run_flux(args, rank, world, local_rank):
+    """Secondary headline: latents/sec, FluxTransformer2DModel (Flux.1-dev shape), 1024^2 (4096 image + 512 text
+    tokens), 28 FlowMatch steps, guidance 3.5, output_type='latent' (BASELINE.json configs[2])."""
+    from diffusers_b200 import ops, specs
+    from diffusers_b200.pipelines import FluxPipeline
+    from diffusers_b200.schedulers import FlowMatchEulerDiscreteScheduler
+    from diffusers_b200.transformer_flux import FluxTransformer2DModel
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dt = torch.bfloat16
+    pk = peaks()
+    t0 = time.time()
+    tr = FluxTransformer2DModel.random_init(seed=0, dtype=dt, device=dev)
+    init_s = time.time() - t0
+
+    class _V:
+        config = type("C", (), dict(block_out_channels=(128, 256, 512, 512)))()
+
+    sk = dict(shift=3.0, use_dynamic_shifting=True, base_shift=0.5, max_shift=1.15, base_image_seq_len=256, max_image_seq_len=4096)
+    pipe = FluxPipeline(FlowMatchEulerDiscreteScheduler(**sk), _V(), tr)
+    g = torch.Generator().manual_seed(1)
+    host = dict(prompt_embeds=torch.randn(1, 512, 4096, generator=g).to(dt).pin_memory(),
+                pooled_prompt_embeds=torch.randn(1, 768, generator=g).to(dt).pin_memory())
+    call = dict(height=1024, width=1024, num_inference_steps=args.denoise_steps if args.denoise_steps != 50 else 28,
+                guidance_scale=3.5, output_type="latent")
+    nsteps = call["num_inference_steps"]
+
+    def one(emb, seed, to_host):
+        lat = pipe(generator=torch.Generator(device=dev).manual_seed(seed), **emb, **call).images
+        if to_host:
+            out = torch.empty(lat.shape, dtype=lat.dtype, pin_memory=True)
+            out.copy_(lat, non_blocking=True)
+            return out
+        return lat
+
+    res = {k: v.to(dev) for k, v in host.items()}
+    for i in range(args.warmup):
+        one(res, i, False)
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as cs:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ops.launches()
+        e0.record()
+        for i in range(args.steps):
+            one(res, 100 + i, False)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launches() - n0
+    e0.record()
+    for i in range(args.steps):
+        one({k: v.to(dev, non_blocking=True) for k, v in host.items()}, 200 + i, True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1)
+    value = args.steps / (ms * 1e-3)
+    fl = nsteps * FLUX_FLOP_PER_FORWARD
+    line = dict(metric="latents/sec @ Flux.1-dev-shape 1024^2 28-step", value=round(value, 4), unit="latents/s", n_gpus=1,
+                steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 1), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="bf16", data="synthetic (random-init weights, N(0,1) embeddings)",
+                config=dict(workload=f"flux_dev_shape_1024_{nsteps}step_g3.5_b1", model="FluxTransformer2DModel 11.90 B params",
+                            l2="23.8 GB of weights stream from HBM every forward", init_s=round(init_s, 1)),
+                e2e=dict(value=round(args.steps / (ms2 * 1e-3), 4), unit="latents/s",
+                         h2d_bytes_per_step=sum(v.numel() * 2 for v in host.values()), d2h_bytes_per_step=4096 * 64 * 2),
+                gpu_launches=launches, clocks=cs.summary(),
+                model_flops=dict(tflop_per_latent=round(fl / 1e12, 1), achieved_tflops=round(value * fl / 1e12, 1),
+                                 frac_of_peak=round(value * fl / 1e12 / pk["tflops"], 4), peak=pk["tflops"]))
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="sdxl", choices=["sdxl", "flux"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
@@ -297,7 +368,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_b200(args, rank, world, local_rank)
+        if args.workload == "flux":
+            run_flux(args, rank, world, local_rank)
+        else:
+            run_b200(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -48,7 +48,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int HD, int NQ, bool FP16>
-__global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1) ? 2 : 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<HD, NQ>;
   using H = Half16<FP16>;
   constexpr int SLABS = Cfg::SLABS;
@@ -391,9 +391,11 @@ int b200_attention(const b200_attention_args* a, void* stream) {
   const float scale = a->scale > 0.f ? a->scale : 1.0f / sqrtf(static_cast<float>(HD));
   prm.scale_log2 = scale * 1.4426950408889634f;
 
-  // two query tiles per CTA unless that leaves SMs idle / the sequence is short
+  // head_dim 64: one 128-row query tile per CTA, two CTAs co-resident per SM (96 KB smem, 256 TMEM columns each) so
+  // one CTA's MMAs overlap the other's softmax and the tail wave is finer grained; head_dim 128: two query tiles
+  // ping-pong inside one CTA (the K/V stages of two CTAs would not fit)
   const long long ctas2 = static_cast<long long>(a->batch) * a->heads * ((a->sq + 255) / 256);
-  int nq = (a->sq > 128 && ctas2 >= num_sms()) ? 2 : 1;
+  int nq = (HD == 128 && a->sq > 128 && 2 * ctas2 >= num_sms()) ? 2 : 1;
   if (a->nq_override == 1 || a->nq_override == 2) nq = a->nq_override;
   prm.q_tiles = (a->sq + 128 * nq - 1) / (128 * nq);
   const long long grid_ll = static_cast<long long>(a->batch) * a->heads * prm.q_tiles;

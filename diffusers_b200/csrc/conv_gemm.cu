@@ -13,6 +13,7 @@
 // A-operand tile = 128 output pixels arranged as a bw x bh rectangle (bw*bh = 128) so that one
 // TMA box per filter tap fetches exactly the shifted input pixels.  nn.Linear is the 1x1, H = 1
 // case (bw = 128, bh = 1).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -22,10 +23,14 @@ namespace b200 {
 
 struct ConvGemmParams {
   CUtensorMap a_map[8];  // [src][parity]; stride-1 convs only use parity 0
-  CUtensorMap w_map;
+  CUtensorMap w_map;     // box {64, BN / cm}: every CTA of a cluster loads one slice and multicasts it
+  CUtensorMap y_map;     // output, box {32, bw, bh, 1}, SWIZZLE_64B (TMA-store epilogue)
   int batch, Ho, Wo;
   int bw, bh, bw_shift;
-  int tiles_w, tiles_h, m_tiles, n_tiles, total_tiles;
+  int tiles_w, tiles_h, m_tiles, n_tiles;
+  int cm;                // cluster size along M (1, 2 or 4)
+  int m_groups;          // ceil(m_tiles / cm)
+  int total_groups;      // n_tiles * m_groups
   int N;  // rows of w
   int num_taps, nsrc;
   int chunks[2];
@@ -37,8 +42,9 @@ struct ConvGemmParams {
   const void* residual;
   void* y;
   int ld_gate, ld_rowvec, ldr, ldy, rows_per_group, act;
-  int vec_ok;  // y / residual / gate / rowvec / bias allow 16-byte accesses
-  int out_fp32;  // y is float (used for attention scores of the unfused head_dim-512 path)
+  int vec_ok;    // y / residual / gate / rowvec / bias allow 16-byte accesses
+  int out_fp32;  // y is float (attention scores of the unfused head_dim-512 path)
+  int tma_store; // epilogue stages 32-column slabs in smem and writes them with TMA (needs vec_ok, 16-bit y)
 };
 
 template <int BN>
@@ -47,19 +53,26 @@ struct ConvGemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SLAB_BYTES = 128 * 32 * 2;  // one 32-column output slab (64 B rows)
+  static constexpr int NSLAB = 4;
+  static constexpr int STAGES = (BN >= 192) ? 4 : (BN >= 160 ? 5 : (BN >= 96 ? 6 : 8));
+  // accumulator buffers sit at power-of-two column offsets
+  static constexpr int ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NSLAB * SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 };
 
 struct TileCoord {
   int img, h0, w0, n0;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int t, int BN) {
+// group g -> (n block, m group); CTA `rank` of the cluster takes m tile m_group*cm + rank (may be a phantom tile
+// past the end: its loads are all out of bounds -> zeros, and it stores nothing)
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int g, int rank, int BN) {
   TileCoord c;
-  int n_blk = t / p.m_tiles;
-  int m = t - n_blk * p.m_tiles;
+  int n_blk = g / p.m_groups;
+  int m = (g - n_blk * p.m_groups) * p.cm + rank;
   int per_img = p.tiles_w * p.tiles_h;
   c.img = m / per_img;
   int r = m - c.img * per_img;
@@ -79,7 +92,8 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* slabs = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + Cfg::NSLAB * Cfg::SLAB_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -87,13 +101,19 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cm = p.cm;
+  const int rank = cm > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster = cm > 1 ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
+  const int n_clusters = cm > 1 ? static_cast<int>(num_clusters_x()) : static_cast<int>(gridDim.x);
+  const uint16_t cmask = static_cast<uint16_t>((1u << cm) - 1u);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nsrc; ++s) prefetch_tensormap(&p.a_map[s * 4]);
     prefetch_tensormap(&p.w_map);
+    if (p.tma_store) prefetch_tensormap(&p.y_map);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], cm);  // one MMA-completion arrive from every CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -107,6 +127,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (cm > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive / multicast write
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -115,8 +136,9 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        TileCoord tc = decode_tile(p, t, BN);
+      const int b_rows = BN / cm;  // rows of the weight tile this CTA fetches (and multicasts)
+      for (int g = cluster; g < p.total_groups; g += n_clusters) {
+        TileCoord tc = decode_tile(p, g, rank, BN);
         int kc = 0;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int mp = p.tap_map[tap];
@@ -125,11 +147,15 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
           for (int s = 0; s < p.nsrc; ++s) {
             const CUtensorMap* am = &p.a_map[s * 4 + mp];
             for (int cc = 0; cc < p.chunks[s]; ++cc) {
-              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_wait(&empty_bar[stage], phase ^ 1u);  // every CTA of the cluster has drained this stage
               mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
               tma_load_4d(sa, am, &full_bar[stage], cc * 64, cw, ch, tc.img);
-              tma_load_2d(sa + Cfg::A_BYTES, &p.w_map, &full_bar[stage], kc * 64, tc.n0);
+              uint8_t* sb = sa + Cfg::A_BYTES + rank * b_rows * 128;
+              if (cm > 1)
+                tma_load_2d_mcast(sb, &p.w_map, &full_bar[stage], kc * 64, tc.n0 + rank * b_rows, cmask);
+              else
+                tma_load_2d(sb, &p.w_map, &full_bar[stage], kc * 64, tc.n0);
               ++kc;
               if (++stage == STAGES) {
                 stage = 0;
@@ -147,12 +173,12 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      for (int g = cluster; g < p.total_groups; g += n_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -164,7 +190,10 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
             // +32 B per UMMA_K=16 step inside the 128 B swizzle atom -> +2 in the (addr>>4) field
             umma_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (cm > 1)
+            umma_commit_mcast(&empty_bar[stage], cmask);
+          else
+            umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -185,13 +214,18 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     const typename H::T* residual = static_cast<const typename H::T*>(p.residual);
     typename H::T* y = static_cast<typename H::T*>(p.y);
     const int n_limit = GEGLU ? (p.N >> 1) : p.N;  // number of y columns
+    const bool tma_store = p.tma_store != 0;
+    const bool issuer = (warp == 4 && lane == 0);  // issues and tracks the TMA stores
+    const int sw = (row >> 1) & 3;                  // SWIZZLE_64B: 16-byte unit index ^= bits [7,9) of the byte offset
+    uint32_t slab_count = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    for (int g = cluster; g < p.total_groups; g += n_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      TileCoord tc = decode_tile(p, t, BN);
+      TileCoord tc = decode_tile(p, g, rank, BN);
       const int oh = tc.h0 + rh, ow = tc.w0 + rw;
-      const bool valid = (oh < p.Ho) && (ow < p.Wo);
+      const bool real_tile = tc.img < p.batch;
+      const bool valid = real_tile && (oh < p.Ho) && (ow < p.Wo);
       const long long pix = (static_cast<long long>(tc.img) * p.Ho + oh) * p.Wo + ow;
       const long long grp = (valid && (gate != nullptr || rowvec != nullptr)) ? (pix / p.rows_per_group) : 0;
       const typename H::T* gate_row = gate ? gate + grp * p.ld_gate : nullptr;
@@ -199,42 +233,54 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
       const typename H::T* res_row = residual ? residual + pix * p.ldr : nullptr;
       typename H::T* y_row = y + pix * p.ldy;
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-
       constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
       const int ycol0 = GEGLU ? (tc.n0 >> 1) : tc.n0;
+      if (res_row && valid) {  // pull this row's residual lines towards L2 while the main loop runs
+#pragma unroll
+        for (int c = 0; c < OUT_COLS; c += 64)
+          if (ycol0 + c < n_limit) prefetch_l2(res_row + ycol0 + c);
+      }
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
+
 #pragma unroll 1
       for (int c = 0; c < OUT_COLS / 32; ++c) {
         if (ycol0 + c * 32 >= n_limit) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(t_row + c * 32, v);
-        uint32_t g[32];
-        if (GEGLU) tmem_ld32(t_row + BN / 2 + c * 32, g);
+        uint32_t gv[32];
+        if (GEGLU) tmem_ld32(t_row + BN / 2 + c * 32, gv);
+        uint8_t* slab = slabs + (slab_count % Cfg::NSLAB) * Cfg::SLAB_BYTES;
+        if (tma_store) {
+          // the store that used this slab NSLAB slabs ago must have finished reading it
+          if (issuer) bulk_wait_group_read<Cfg::NSLAB - 1>();
+          named_bar_sync(1, 128);
+        }
         tmem_wait_ld();
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
           const int yc = ycol0 + c * 32 + j8 * 8;  // y column of f[0]
-          if (yc >= n_limit) break;
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
+          const bool in_range = yc < n_limit;
           const bool full8 = (yc + 8 <= n_limit) && p.vec_ok;
-          if (GEGLU) {
-            // packed rows: [n0, n0+BN/2) value, [n0+BN/2, n0+BN) gate
-            const int bcol = tc.n0 + c * 32 + j8 * 8;
+          if (in_range) {
+            if (GEGLU) {
+              // packed rows: [n0, n0+BN/2) value, [n0+BN/2, n0+BN) gate
+              const int bcol = tc.n0 + c * 32 + j8 * 8;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float a = f[j], gg = __uint_as_float(g[j8 * 8 + j]);
-              if (bias) {
-                a += H::to_float(bias[bcol + j]);
-                gg += H::to_float(bias[bcol + BN / 2 + j]);
+              for (int j = 0; j < 8; ++j) {
+                float a = f[j], gg = __uint_as_float(gv[j8 * 8 + j]);
+                if (bias) {
+                  a += H::to_float(bias[bcol + j]);
+                  gg += H::to_float(bias[bcol + BN / 2 + j]);
+                }
+                f[j] = a * gelu_erf_f(gg);
               }
-              f[j] = a * gelu_erf_f(gg);
-            }
-          } else {
-            if (full8) {
+            } else if (full8) {
               if (bias) {
                 uint4 b = *reinterpret_cast<const uint4*>(bias + yc);
                 float2 t0 = H::unpack(b.x), t1 = H::unpack(b.y), t2 = H::unpack(b.z), t3 = H::unpack(b.w);
@@ -279,7 +325,15 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
               }
             }
           }
-          if (valid && p.out_fp32) {
+          if (tma_store) {
+            // columns past n_limit are clipped by the TMA store; whatever lands there in smem is never written
+            uint4 o;
+            o.x = H::pack(f[0], f[1]);
+            o.y = H::pack(f[2], f[3]);
+            o.z = H::pack(f[4], f[5]);
+            o.w = H::pack(f[6], f[7]);
+            *reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4)) = o;
+          } else if (valid && in_range && p.out_fp32) {
             float* yf = reinterpret_cast<float*>(p.y) + pix * p.ldy + yc;
             if (full8) {
               *reinterpret_cast<float4*>(yf) = make_float4(f[0], f[1], f[2], f[3]);
@@ -289,7 +343,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
               for (int j = 0; j < 8; ++j)
                 if (yc + j < n_limit) yf[j] = f[j];
             }
-          } else if (valid) {
+          } else if (valid && in_range) {
             if (full8) {
               uint4 o;
               o.x = H::pack(f[0], f[1]);
@@ -304,15 +358,26 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
             }
           }
         }
+        if (tma_store) {
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
+          named_bar_sync(1, 128);
+          if (issuer) {
+            if (real_tile) tma_store_4d(&p.y_map, slab, ycol0 + c * 32, tc.w0, tc.h0, tc.img);
+            bulk_commit_group();
+          }
+          ++slab_count;
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (tma_store && issuer) bulk_wait_group<0>();  // smem must outlive the in-flight stores
   }
 
   tc_fence_before();
   __syncthreads();
+  if (cm > 1) cluster_sync_all();  // nobody exits while a peer can still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -322,8 +387,6 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef void (*ConvGemmKernel)(const ConvGemmParams);
-
 template <int BN, bool GEGLU, bool FP16>
 static int set_smem_attr() {
   cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, GEGLU, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -337,7 +400,7 @@ int init_conv_gemm() {
 #define B200_SET(BN)                                   \
   if ((r = set_smem_attr<BN, false, false>())) return r; \
   if ((r = set_smem_attr<BN, false, true>())) return r;
-  B200_SET(32) B200_SET(64) B200_SET(128) B200_SET(256)
+  B200_SET(32) B200_SET(64) B200_SET(96) B200_SET(128) B200_SET(160) B200_SET(192) B200_SET(256)
 #undef B200_SET
 #define B200_SETG(BN)                                 \
   if ((r = set_smem_attr<BN, true, false>())) return r; \
@@ -347,51 +410,113 @@ int init_conv_gemm() {
   return 0;
 }
 
-template <bool GEGLU, bool FP16>
-static int launch_bn(int bn, const ConvGemmParams& prm, int grid, cudaStream_t st) {
-  switch (bn) {
-    case 256:
-      conv_gemm_kernel<256, GEGLU, FP16><<<grid, 256, ConvGemmCfg<256>::SMEM_BYTES, st>>>(prm);
-      break;
-    case 128:
-      conv_gemm_kernel<128, GEGLU, FP16><<<grid, 256, ConvGemmCfg<128>::SMEM_BYTES, st>>>(prm);
-      break;
-    case 64:
-      conv_gemm_kernel<64, GEGLU, FP16><<<grid, 256, ConvGemmCfg<64>::SMEM_BYTES, st>>>(prm);
-      break;
-    case 32:
-      if (GEGLU) return set_error(B200_ERR_UNSUPPORTED, "geglu needs tile_n >= 64");
-      conv_gemm_kernel<32, false, FP16><<<grid, 256, ConvGemmCfg<32>::SMEM_BYTES, st>>>(prm);
-      break;
-    default:
-      return set_error(B200_ERR_INVALID, "conv_gemm: unsupported tile_n %d", bn);
+template <int BN, bool GEGLU, bool FP16>
+static int launch_one(const ConvGemmParams& prm, int grid, int cm, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = ConvGemmCfg<BN>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cm;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cm > 1) {
+    // GPC boundaries can strand SMs for clusters: never launch more clusters than can be co-resident, the
+    // persistent tile loop strides by the number of clusters actually launched
+    static int max_active[5] = {0, 0, 0, 0, 0};
+    if (max_active[cm] == 0) {
+      int n = 0;
+      cudaLaunchConfig_t q = cfg;
+      q.gridDim = dim3(num_sms() / cm * cm);
+      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<BN, GEGLU, FP16>, &q) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = num_sms() / cm;
+      }
+      max_active[cm] = n;
+    }
+    if (grid > max_active[cm] * cm) cfg.gridDim = dim3(max_active[cm] * cm);
   }
-  return check_launch("conv_gemm_kernel");
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, GEGLU, FP16>, prm);
+  if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "conv_gemm launch (BN=%d cm=%d grid=%d): %s", BN, cm, grid, cudaGetErrorString(e));
+  return 0;
+}
+
+template <bool GEGLU, bool FP16>
+static int launch_bn(int bn, const ConvGemmParams& prm, int grid, int cm, cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch_one<256, GEGLU, FP16>(prm, grid, cm, st);
+    case 128: return launch_one<128, GEGLU, FP16>(prm, grid, cm, st);
+    case 64: return launch_one<64, GEGLU, FP16>(prm, grid, cm, st);
+    default: break;
+  }
+  if (GEGLU) return set_error(B200_ERR_UNSUPPORTED, "geglu needs tile_n in {64, 128, 256} (got %d)", bn);
+  switch (bn) {
+    case 192: return launch_one<192, false, FP16>(prm, grid, cm, st);
+    case 160: return launch_one<160, false, FP16>(prm, grid, cm, st);
+    case 96: return launch_one<96, false, FP16>(prm, grid, cm, st);
+    case 32: return launch_one<32, false, FP16>(prm, grid, cm, st);
+    default: return set_error(B200_ERR_INVALID, "conv_gemm: unsupported tile_n %d", bn);
+  }
+}
+
+// Cost model (SM cycles) used to pick the tile width BN and the cluster size cm (CTAs along M that share one
+// multicast weight tile).  Per 64-wide K chunk a CTA issues 4 MMAs of 128 x BN x 16 (2*BN cycles) and pulls
+// 16 KB of activations + BN*128/cm bytes of weights through its ~64 B/clk L2 port; one tile then costs
+// k_chunks * max(mma, l2) + epilogue + fixed, and the launch costs ceil(groups / clusters) such tiles.
+static double tile_cost(int bn, int cm, int k_chunks, bool geglu) {
+  const double mma = 2.0 * bn;
+  const double l2 = (16384.0 + bn * 128.0 / cm) / 64.0;
+  const double chunk = mma > l2 ? mma : l2;
+  const double epi = 300.0 + (geglu ? bn / 2 : bn) / 32.0 * 220.0;
+  return k_chunks * chunk + epi + 2500.0;
+}
+
+static void pick_config(long long m_tiles, int N, int k_chunks, int geglu, int force_bn, int* bn_out, int* cm_out) {
+  const int sms = num_sms();
+  static const int force_cm = getenv("B200_FORCE_CM") ? atoi(getenv("B200_FORCE_CM")) : 0;  // test knob
+  double best = 1e30;
+  int best_bn = 0, best_cm = 1;
+  static const int kBn[] = {256, 192, 160, 128, 96, 64, 32};
+  for (int bn : kBn) {
+    if (force_bn && bn != force_bn) continue;
+    if (geglu && !(bn == 256 || bn == 128 || bn == 64)) continue;
+    if (geglu && N % bn != 0) continue;
+    const long long n_tiles = (N + bn - 1) / bn;
+    for (int cm : {1, 2, 4}) {
+      if (force_cm && cm != force_cm) continue;
+      if ((bn / cm) % 8 != 0) continue;
+      if (cm > 1 && m_tiles < cm) continue;
+      const long long groups = n_tiles * ((m_tiles + cm - 1) / cm);
+      const long long clusters = cm == 4 ? (sms * 7 / 8) / cm : sms / cm;  // GPC boundaries strand some SMs for 4-CTA clusters
+      const long long waves = (groups + clusters - 1) / clusters;
+      const double cost = waves * tile_cost(bn, cm, k_chunks, geglu != 0);
+      if (cost < best * 0.999) {
+        best = cost;
+        best_bn = bn;
+        best_cm = cm;
+      }
+    }
+  }
+  *bn_out = best_bn;
+  *cm_out = best_cm;
 }
 
 static int pick_tile_n(long long M, int N, int geglu) {
   if (geglu) {
-    // the packer interleaves value/gate rows per tile, so BN must divide N
+    // the packer interleaves value/gate rows per tile, so BN must divide N; fixed per N so that weights packed
+    // once serve every M
     for (int bn : {256, 128, 64})
       if (N % bn == 0) return bn;
     return 0;
   }
-  const long long m_tiles = (M + 127) / 128;
-  const int sms = num_sms();
-  int best = 32;
-  double best_cost = 1e30;
-  for (int bn : {256, 128, 64, 32}) {
-    long long tiles = m_tiles * ((N + bn - 1) / bn);
-    long long waves = (tiles + sms - 1) / sms;
-    // per-k16 step: MMA issue ~ BN/2 cycles, operand smem reads (128+BN)*32 B at 128 B/cycle; + fixed overhead
-    double step = bn / 2.0 > (128 + bn) / 4.0 ? bn / 2.0 : (128 + bn) / 4.0;
-    double cost = static_cast<double>(waves) * (step + 12);
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = bn;
-    }
-  }
-  return best;
+  int bn, cm;
+  pick_config((M + 127) / 128, N, 20, 0, 0, &bn, &cm);
+  return bn;
 }
 
 }  // namespace b200
@@ -422,15 +547,12 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   if (a->stride == 2) B200_CHECK_ARG(a->H % 2 == 0 && a->W % 2 == 0, "conv_gemm: stride 2 needs even H, W");
   if (a->geglu) B200_CHECK_ARG(a->N % 64 == 0, "conv_gemm: geglu needs N %% 64 == 0 (N=%d)", a->N);
   if (a->gate || a->rowvec) B200_CHECK_ARG(a->rows_per_group > 0, "conv_gemm: rows_per_group must be > 0");
+  B200_CHECK_ARG(a->tile_n == 0 || a->tile_n == 32 || a->tile_n == 64 || a->tile_n == 96 || a->tile_n == 128 ||
+                     a->tile_n == 160 || a->tile_n == 192 || a->tile_n == 256,
+                 "conv_gemm: tile_n %d not in {32,64,96,128,160,192,256}", a->tile_n);
 
   const int Ho = (a->stride == 1) ? a->H : a->H / 2;
   const int Wo = (a->stride == 1) ? a->W : a->W / 2;
-  const long long M = static_cast<long long>(a->batch) * Ho * Wo;
-
-  int bn = a->tile_n ? a->tile_n : pick_tile_n(M, a->N, a->geglu);
-  B200_CHECK_ARG(bn == 32 || bn == 64 || bn == 128 || bn == 256, "conv_gemm: no valid tile_n (N=%d geglu=%d)", a->N,
-                 a->geglu);
-  if (a->geglu) B200_CHECK_ARG(a->N % bn == 0, "conv_gemm: geglu N=%d not a multiple of tile_n=%d", a->N, bn);
 
   ConvGemmParams prm;
   memset(&prm, 0, sizeof(prm));
@@ -456,14 +578,21 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   prm.tiles_w = cdiv(Wo, prm.bw);
   prm.tiles_h = cdiv(Ho, prm.bh);
   prm.m_tiles = prm.tiles_w * prm.tiles_h * a->batch;
-  prm.n_tiles = cdiv(a->N, bn);
-  prm.total_tiles = prm.m_tiles * prm.n_tiles;
   prm.N = a->N;
   prm.nsrc = nsrc;
   prm.num_taps = a->ksize * a->ksize;
   prm.chunks[0] = cdiv(a->c[0], 64);
   prm.chunks[1] = nsrc == 2 ? cdiv(a->c[1], 64) : 0;
   prm.k_chunks = prm.num_taps * (prm.chunks[0] + prm.chunks[1]);
+
+  int bn = 0, cm = 1;
+  pick_config(prm.m_tiles, a->N, prm.k_chunks, a->geglu, a->geglu && !a->tile_n ? pick_tile_n(0, a->N, 1) : a->tile_n, &bn, &cm);
+  B200_CHECK_ARG(bn != 0, "conv_gemm: no valid tile configuration (N=%d geglu=%d tile_n=%d)", a->N, a->geglu, a->tile_n);
+  if (a->geglu) B200_CHECK_ARG(a->N % bn == 0, "conv_gemm: geglu N=%d not a multiple of tile_n=%d", a->N, bn);
+  prm.cm = cm;
+  prm.n_tiles = cdiv(a->N, bn);
+  prm.m_groups = cdiv(prm.m_tiles, cm);
+  prm.total_groups = prm.n_tiles * prm.m_groups;
 
   // ---- filter taps: which (parity) tensor map and which box shift each tap uses
   int tap = 0;
@@ -514,7 +643,7 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
     const uint64_t Kp = static_cast<uint64_t>(b200_conv_gemm_packed_k(a->ksize, a->c[0], nsrc == 2 ? a->c[1] : 0));
     const uint64_t dims[2] = {Kp, static_cast<uint64_t>(a->N)};
     const uint64_t str[1] = {Kp * 2};
-    const uint32_t box[2] = {64u, static_cast<uint32_t>(bn)};
+    const uint32_t box[2] = {64u, static_cast<uint32_t>(bn / cm)};
     int r = make_tensor_map_16b(&prm.w_map, a->w, 2, dims, str, box, "conv_gemm W");
     if (r) return r;
   }
@@ -537,12 +666,25 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   if (a->residual) vec = vec && aligned16(a->residual) && (a->ldr % 8 == 0);
   prm.vec_ok = vec ? 1 : 0;
   prm.out_fp32 = a->out_fp32 ? 1 : 0;
+  const int n_out = a->geglu ? a->N / 2 : a->N;
+  prm.tma_store = (vec && !a->out_fp32 && n_out % 8 == 0) ? 1 : 0;
+  if (prm.tma_store) {
+    const uint64_t ldy = static_cast<uint64_t>(a->ldy);
+    const uint64_t dims[4] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                              static_cast<uint64_t>(a->batch)};
+    const uint64_t str[3] = {ldy * 2, ldy * 2 * Wo, ldy * 2 * Wo * Ho};
+    const uint32_t ybox[4] = {32u, static_cast<uint32_t>(prm.bw), static_cast<uint32_t>(prm.bh), 1u};
+    int r = make_tensor_map_16b(&prm.y_map, a->y, 4, dims, str, ybox, "conv_gemm Y", 64);
+    if (r) return r;
+  }
 
-  const int grid = prm.total_tiles < num_sms() ? prm.total_tiles : num_sms();
+  const int clusters_avail = num_sms() / cm;
+  const int n_clusters = prm.total_groups < clusters_avail ? prm.total_groups : clusters_avail;
+  const int grid = n_clusters * cm;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool fp16 = a->dtype == B200_DTYPE_FP16;
-  if (a->geglu) return fp16 ? launch_bn<true, true>(bn, prm, grid, st) : launch_bn<true, false>(bn, prm, grid, st);
-  return fp16 ? launch_bn<false, true>(bn, prm, grid, st) : launch_bn<false, false>(bn, prm, grid, st);
+  if (a->geglu) return fp16 ? launch_bn<true, true>(bn, prm, grid, cm, st) : launch_bn<true, false>(bn, prm, grid, cm, st);
+  return fp16 ? launch_bn<false, true>(bn, prm, grid, cm, st) : launch_bn<false, false>(bn, prm, grid, cm, st);
 }
 
 }  // extern "C"

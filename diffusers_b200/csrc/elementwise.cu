@@ -325,6 +325,28 @@ __global__ void transpose16_kernel(const uint16_t* __restrict__ src, long long l
   }
 }
 
+// DDPMScheduler.step (schedulers/scheduling_ddpm.py:513-565), epsilon prediction, fixed_small variance:
+//   x0 = (x - sqrt(1-abar_t) * eps) / sqrt(abar_t); clip; prev = c0*x0 + c1*x + sigma*noise
+// computed in fp32 from 16-bit tensors (the reference runs this path in the model dtype; config 0 is fp32 there).
+template <bool FP16>
+__global__ void ddpm_step_kernel(const void* eps_, const void* sample_, const void* noise_, void* prev_, long long n,
+                                 float sqrt_beta_prod, float sqrt_alpha_prod, float c0, float c1, float sigma, int clip,
+                                 float clip_range) {
+  using H = Half16<FP16>;
+  const typename H::T* eps = static_cast<const typename H::T*>(eps_);
+  const typename H::T* sample = static_cast<const typename H::T*>(sample_);
+  const typename H::T* noise = static_cast<const typename H::T*>(noise_);
+  typename H::T* prev = static_cast<typename H::T*>(prev_);
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = H::to_float(sample[i]);
+  float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(sqrt_beta_prod, H::to_float(eps[i]))), sqrt_alpha_prod);
+  if (clip) x0 = fminf(fmaxf(x0, -clip_range), clip_range);
+  float p = __fadd_rn(__fmul_rn(c0, x0), __fmul_rn(c1, x));
+  if (noise) p = __fadd_rn(p, __fmul_rn(sigma, H::to_float(noise[i])));
+  prev[i] = H::from_float(p);
+}
+
 static inline unsigned int blocks_for(long long n, int threads) {
   return static_cast<unsigned int>((n + threads - 1) / threads);
 }
@@ -492,6 +514,23 @@ int b200_transpose_16(const void* src, int64_t ld_src, void* dst, int64_t ld_dst
   transpose16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint16_t*>(src), ld_src, static_cast<uint16_t*>(dst), ld_dst, rows, cols);
   return check_launch("transpose16_kernel");
+}
+
+int b200_ddpm_step(const void* model_output, const void* sample, const void* noise, void* prev_sample, int64_t n,
+                   float sqrt_beta_prod_t, float sqrt_alpha_prod_t, float pred_original_coeff, float current_sample_coeff,
+                   float sigma, int32_t clip_sample, float clip_range, int32_t dtype, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(model_output && sample && prev_sample && n > 0 && sqrt_alpha_prod_t > 0.f, "ddpm_step: bad args");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200_DTYPE_FP16)
+    ddpm_step_kernel<true><<<blocks_for(n, 256), 256, 0, st>>>(model_output, sample, noise, prev_sample, n, sqrt_beta_prod_t,
+                                                              sqrt_alpha_prod_t, pred_original_coeff, current_sample_coeff,
+                                                              sigma, clip_sample, clip_range);
+  else
+    ddpm_step_kernel<false><<<blocks_for(n, 256), 256, 0, st>>>(model_output, sample, noise, prev_sample, n, sqrt_beta_prod_t,
+                                                               sqrt_alpha_prod_t, pred_original_coeff, current_sample_coeff,
+                                                               sigma, clip_sample, clip_range);
+  return check_launch("ddpm_step_kernel");
 }
 
 }  // extern "C"

@@ -23,7 +23,7 @@ EncodeTiledFn encode_tiled_fn();  // nullptr (and last_error set) if unavailable
 // 16-bit tensor map, SWIZZLE_128B, zero OOB fill.  dims/strides innermost-first; strides in BYTES for
 // dims 1..rank-1.  Returns 0 or an error code.
 int make_tensor_map_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                        const uint64_t* strides_bytes, const uint32_t* box, const char* what);
+                        const uint64_t* strides_bytes, const uint32_t* box, const char* what, int swizzle_bytes = 128);
 
 #define B200_CHECK_ARG(cond, ...) \
   do {                            \

@@ -40,7 +40,7 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 int make_tensor_map_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                        const uint64_t* strides_bytes, const uint32_t* box, const char* what) {
+                        const uint64_t* strides_bytes, const uint32_t* box, const char* what, int swizzle_bytes) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return B200_ERR_CUDA;
   cuuint64_t gdim[5];
@@ -54,7 +54,9 @@ int make_tensor_map_16b(CUtensorMap* out, const void* base, int rank, const uint
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
-                  gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                      : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return set_error(B200_ERR_INVALID,

@@ -67,21 +67,30 @@ __global__ void group_norm_stats_kernel(const GroupNormParams p) {
   for (int j = 0; j < 8; ++j) sh[j] = s[j] = ss[j] = 0.f;
   float cnt = 0.f;
   if (pl < p.P) {
-    for (int pix = pix0 + pl; pix < pix1; pix += p.P) {
-      uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pix) * ld);
-      float2 a = H::unpack(u.x), b = H::unpack(u.y), c = H::unpack(u.z), d = H::unpack(u.w);
-      float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
-      if (cnt == 0.f) {
+    const int step = p.P;
+    for (int pix = pix0 + pl; pix < pix1; pix += 4 * step) {
+      uint4 u[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sh[j] = v[j];
-      }
+      for (int k = 0; k < 4; ++k)  // 4 independent 16-byte loads in flight per thread
+        if (pix + k * step < pix1) u[k] = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pix + k * step) * ld);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float e = v[j] - sh[j];
-        s[j] += e;
-        ss[j] += e * e;
+      for (int k = 0; k < 4; ++k) {
+        if (pix + k * step < pix1) {
+          float2 a = H::unpack(u[k].x), b = H::unpack(u[k].y), c = H::unpack(u[k].z), d = H::unpack(u[k].w);
+          float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+          if (cnt == 0.f) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sh[j] = v[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float e = v[j] - sh[j];
+            s[j] += e;
+            ss[j] += e * e;
+          }
+          cnt += 1.f;
+        }
       }
-      cnt += 1.f;
     }
     const int cbase = cv * 8;
 #pragma unroll
@@ -120,12 +129,28 @@ __global__ void group_norm_stats_kernel(const GroupNormParams p) {
   __syncthreads();
   if (s_last) {
     __threadfence();
+    // stage this image's partials in shared memory with coalesced loads (reusing the per-lane buffer), then
+    // merge them in a fixed order
+    float* s_part = reinterpret_cast<float*>(s_mm);
+    const int total = p.chunks * p.groups * 3;
+    const volatile float* pp = p.partial + static_cast<size_t>(n) * p.chunks * p.groups * 3;
+    const int cap = p.P * p.C * 2;  // floats available in s_mm
+    if (total <= cap) {
+      for (int i = t; i < total; i += blockDim.x) s_part[i] = pp[i];
+    }
+    __syncthreads();
     if (t < p.groups) {
       float na = 0.f, ma = 0.f, M2a = 0.f;
-      const float* pp = p.partial + static_cast<size_t>(n) * p.chunks * p.groups * 3 + t * 3;
-      for (int ch = 0; ch < p.chunks; ++ch) {
-        const volatile float* q = pp + static_cast<size_t>(ch) * p.groups * 3;
-        chan_combine(na, ma, M2a, q[0], q[1], q[2]);
+      if (total <= cap) {
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          const float* q = s_part + (ch * p.groups + t) * 3;
+          chan_combine(na, ma, M2a, q[0], q[1], q[2]);
+        }
+      } else {
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          const volatile float* q = pp + (static_cast<size_t>(ch) * p.groups + t) * 3;
+          chan_combine(na, ma, M2a, q[0], q[1], q[2]);
+        }
       }
       float var = M2a / na;
       p.stats[(static_cast<size_t>(n) * p.groups + t) * 2 + 0] = ma;
@@ -164,39 +189,53 @@ __global__ void __launch_bounds__(256) group_norm_apply_kernel(const GroupNormPa
   typename H::T* y = static_cast<typename H::T*>(p.y) + (static_cast<size_t>(n) * p.hw + pix0) * p.ldy;
   const int total = npix * p.V;
   const bool do_silu = p.act == ACT_SILU;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+  auto src_of = [&](int i) -> const typename H::T* {
     const int pix = i / p.V;
     const int cv = i - pix * p.V;
-    const typename H::T* src =
-        cv < p.V0 ? x0 + static_cast<size_t>(pix) * p.ldx[0] + cv * 8 : x1 + static_cast<size_t>(pix) * p.ldx[1] + (cv - p.V0) * 8;
-    uint4 u = *reinterpret_cast<const uint4*>(src);
-    float2 a = H::unpack(u.x), b = H::unpack(u.y), c = H::unpack(u.z), d = H::unpack(u.w);
-    float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
-    const int cb = cv * 8;
+    return cv < p.V0 ? x0 + static_cast<size_t>(pix) * p.ldx[0] + cv * 8
+                     : x1 + static_cast<size_t>(pix) * p.ldx[1] + (cv - p.V0) * 8;
+  };
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+    uint4 u[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float o = fmaf(v[j], s_sc[cb + j], s_bi[cb + j]);
-      v[j] = do_silu ? silu_f(o) : o;
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * blockDim.x;
+      if (i < total) u[k] = *reinterpret_cast<const uint4*>(src_of(i));
     }
-    uint4 o;
-    o.x = H::pack(v[0], v[1]);
-    o.y = H::pack(v[2], v[3]);
-    o.z = H::pack(v[4], v[5]);
-    o.w = H::pack(v[6], v[7]);
-    *reinterpret_cast<uint4*>(y + static_cast<size_t>(pix) * p.ldy + cb) = o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * blockDim.x;
+      if (i < total) {
+        const int pix = i / p.V;
+        const int cb = (i - pix * p.V) * 8;
+        float2 a = H::unpack(u[k].x), b = H::unpack(u[k].y), c = H::unpack(u[k].z), d = H::unpack(u[k].w);
+        float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float o = fmaf(v[j], s_sc[cb + j], s_bi[cb + j]);
+          v[j] = do_silu ? silu_f(o) : o;
+        }
+        uint4 o;
+        o.x = H::pack(v[0], v[1]);
+        o.y = H::pack(v[2], v[3]);
+        o.z = H::pack(v[4], v[5]);
+        o.w = H::pack(v[6], v[7]);
+        *reinterpret_cast<uint4*>(y + static_cast<size_t>(pix) * p.ldy + cb) = o;
+      }
+    }
   }
 }
 
 static void gn_plan(int batch, int hw, int C, int* chunks, int* ppc) {
-  // aim for >= ~2 waves of stats CTAs over the batch without making chunks tiny
-  int target = (2 * num_sms() + batch - 1) / batch;
-  int ch = hw / 128;  // >= 128 pixels per chunk
-  if (ch < 1) ch = 1;
-  if (ch > target) ch = target;
-  if (ch > 256) ch = 256;
-  if (ch < 1) ch = 1;
-  *ppc = (hw + ch - 1) / ch;
-  *chunks = (hw + *ppc - 1) / *ppc;
+  // ~4 CTAs per SM over the whole batch, at least 8 pixels per chunk, at most 256 chunks per image (workspace)
+  long long total = static_cast<long long>(batch) * hw;
+  int pp = static_cast<int>((total + 4LL * num_sms() - 1) / (4LL * num_sms()));
+  if (pp < 8) pp = 8;
+  if (pp * 256 < hw) pp = (hw + 255) / 256;
+  if (pp > hw) pp = hw;
+  *ppc = pp;
+  *chunks = (hw + pp - 1) / pp;
+  (void)C;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -430,7 +469,7 @@ int b200_group_norm(const b200_group_norm_args* a, void* stream) {
   p.ldy = a->ldy;
   gn_plan(a->batch, a->hw, C, &p.chunks, &p.ppc);
   B200_CHECK_ARG(p.V <= 1024, "group_norm: C=%d too large", C);
-  p.P = 256 / p.V;
+  p.P = 512 / p.V;
   if (p.P < 1) p.P = 1;
   if (p.P > 64) p.P = 64;
   if (p.P > p.ppc) p.P = p.ppc;
@@ -438,14 +477,13 @@ int b200_group_norm(const b200_group_norm_args* a, void* stream) {
   p.partial = ws;
   p.stats = ws + static_cast<size_t>(a->batch) * 256 * a->groups * 3;
   p.counter = reinterpret_cast<unsigned int*>(p.stats + static_cast<size_t>(a->batch) * a->groups * 2);
-  p.apply_ppb = 64;
   {
-    int64_t vec = static_cast<int64_t>(p.V) * 64;
-    // ~16 vectors per thread
-    while (vec < 4096 && p.apply_ppb < 1024) {
-      p.apply_ppb *= 2;
-      vec *= 2;
-    }
+    // ~8 CTAs per SM for the apply pass, at least 8 pixels each so the per-CTA scale/bias prologue amortises
+    long long total = static_cast<long long>(a->batch) * a->hw;
+    long long ppb = (total + 8LL * num_sms() - 1) / (8LL * num_sms());
+    if (ppb < 8) ppb = 8;
+    if (ppb > 1024) ppb = 1024;
+    p.apply_ppb = static_cast<int>(ppb);
   }
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -370,3 +370,18 @@ def qk_norm_rope(qkv, *, heads, head_dim, k_off, seq, txt_rows=0, wq=None, wk=No
     _lib.check(_lib.lib().b200_qk_norm_rope(C.byref(a), _stream()), "b200_qk_norm_rope")
     _count()
     return qkv
+
+
+def ddpm_step(model_output, sample, noise, *, sqrt_beta_prod, sqrt_alpha_prod, c0, c1, sigma, clip, clip_range, out=None):
+    _need_cuda(sample, "sample")
+    model_output, sample = model_output.contiguous(), sample.contiguous()
+    if out is None:
+        out = torch.empty_like(model_output)
+    _lib.check(_lib.lib().b200_ddpm_step(C.c_void_p(model_output.data_ptr()), C.c_void_p(sample.data_ptr()),
+                                         C.c_void_p(_ptr(noise.contiguous()) if noise is not None else None),
+                                         C.c_void_p(out.data_ptr()), C.c_int64(sample.numel()), C.c_float(sqrt_beta_prod),
+                                         C.c_float(sqrt_alpha_prod), C.c_float(c0), C.c_float(c1), C.c_float(sigma),
+                                         1 if clip else 0, C.c_float(clip_range), _dtype_code(model_output), _stream()),
+               "b200_ddpm_step")
+    _count()
+    return out

@@ -264,3 +264,29 @@ class FluxPipeline:
         if not return_dict:
             return (image,)
         return PipelineOutput(image)
+
+
+class DDPMPipeline:
+    """pipelines/ddpm/pipeline_ddpm.py:55-139 (BASELINE.json config 0): ancestral sampling with a fresh noise draw from
+    the caller's generator every step."""
+
+    def __init__(self, unet, scheduler):
+        self.unet, self.scheduler = unet, scheduler
+
+    @torch.no_grad()
+    def __call__(self, batch_size=1, generator=None, num_inference_steps=1000, output_type="pt", return_dict=True):
+        u = self.unet
+        size = u.config.sample_size
+        shape = (batch_size, u.config.in_channels, size, size) if isinstance(size, int) else (batch_size, u.config.in_channels, *size)
+        # the reference draws the initial image in the model dtype (fp32 for config 0): same fp32 draw, then cast
+        image = randn_tensor(shape, generator=generator, device=u.device, dtype=torch.float32).to(u.dtype)
+        self.scheduler.set_timesteps(num_inference_steps)
+        for t in self.scheduler._timesteps_cpu:
+            eps = u(image, int(t)).sample
+            image = self.scheduler.step(eps, int(t), image, generator=generator).prev_sample
+        image = (image / 2 + 0.5).clamp(0, 1)
+        if output_type == "np":
+            image = image.float().cpu().permute(0, 2, 3, 1).numpy()
+        if not return_dict:
+            return (image,)
+        return PipelineOutput(image)

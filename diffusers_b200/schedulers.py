@@ -246,3 +246,99 @@ class FlowMatchEulerDiscreteScheduler:
 
     def __len__(self):
         return self.config.num_train_timesteps
+
+
+class DDPMScheduler:
+    """schedulers/scheduling_ddpm.py:137 (epsilon prediction, fixed_small variance, clip_sample): host tables are the
+    reference's torch ops, `step` is one fused kernel; the noise is drawn with the caller's generator exactly like
+    `randn_tensor` (utils/torch_utils.py:183) so the RNG stream is consumed identically."""
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                 variance_type="fixed_small", clip_sample=True, prediction_type="epsilon", clip_sample_range=1.0,
+                 timestep_spacing="leading", steps_offset=0, **unsupported):
+        for k, v in unsupported.items():
+            if v not in (None, False):
+                raise NotImplementedError(f"DDPMScheduler option {k}={v!r} is outside the hot path")
+        if prediction_type != "epsilon" or variance_type != "fixed_small":
+            raise NotImplementedError("only epsilon prediction with fixed_small variance")
+        self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+                                   beta_schedule=beta_schedule, variance_type=variance_type, clip_sample=clip_sample,
+                                   prediction_type=prediction_type, clip_sample_range=clip_sample_range,
+                                   timestep_spacing=timestep_spacing, steps_offset=steps_offset)
+        if beta_schedule == "linear":
+            self.betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        elif beta_schedule == "scaled_linear":
+            self.betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        else:
+            raise NotImplementedError(beta_schedule)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.one = torch.tensor(1.0)
+        self.custom_timesteps = False
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy())
+        self._timesteps_cpu = self.timesteps
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def set_timesteps(self, num_inference_steps=None, device=None, timesteps=None):
+        if timesteps is not None:
+            raise NotImplementedError("custom timesteps")
+        c = self.config
+        if num_inference_steps > c.num_train_timesteps:
+            raise ValueError("`num_inference_steps` cannot be larger than `num_train_timesteps`")
+        self.num_inference_steps = num_inference_steps
+        if c.timestep_spacing == "linspace":
+            ts = np.linspace(0, c.num_train_timesteps - 1, num_inference_steps).round()[::-1].copy().astype(np.int64)
+        elif c.timestep_spacing == "leading":
+            ts = (np.arange(0, num_inference_steps) * (c.num_train_timesteps // num_inference_steps)).round()[::-1].copy().astype(np.int64)
+            ts += c.steps_offset
+        elif c.timestep_spacing == "trailing":
+            ts = np.round(np.arange(c.num_train_timesteps, 0, -c.num_train_timesteps / num_inference_steps)).astype(np.int64)
+            ts -= 1
+        else:
+            raise ValueError(c.timestep_spacing)
+        self._timesteps_cpu = torch.from_numpy(ts)
+        self.timesteps = self._timesteps_cpu.to(device)
+
+    def previous_timestep(self, timestep):
+        if self.custom_timesteps or self.num_inference_steps:
+            index = (self._timesteps_cpu == timestep).nonzero(as_tuple=True)[0][0]
+            return -1 if index == self._timesteps_cpu.shape[0] - 1 else int(self._timesteps_cpu[index + 1])
+        return timestep - 1
+
+    def _get_variance(self, t):
+        prev_t = self.previous_timestep(t)
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+        cur_beta = 1 - a_t / a_prev
+        return torch.clamp((1 - a_prev) / (1 - a_t) * cur_beta, min=1e-20)
+
+    def step(self, model_output, timestep, sample, generator=None, return_dict=True):
+        t = int(timestep)
+        prev_t = self.previous_timestep(t)
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+        b_t, b_prev = 1 - a_t, 1 - a_prev
+        cur_alpha = a_t / a_prev
+        cur_beta = 1 - cur_alpha
+        c0 = (a_prev ** 0.5 * cur_beta) / b_t
+        c1 = cur_alpha ** 0.5 * b_prev / b_t
+        noise, sigma = None, 0.0
+        if t > 0:
+            from .pipelines import randn_tensor
+            # the draw happens in fp32 (config 0 is an fp32 model in the reference) and is rounded to the model dtype
+            noise = randn_tensor(model_output.shape, generator=generator, device=model_output.device, dtype=torch.float32).to(model_output.dtype)
+            sigma = float(self._get_variance(t) ** 0.5)
+        prev = ops.ddpm_step(model_output, sample.to(model_output.dtype), noise, sqrt_beta_prod=float(b_t ** 0.5),
+                             sqrt_alpha_prod=float(a_t ** 0.5), c0=float(c0), c1=float(c1), sigma=sigma,
+                             clip=self.config.clip_sample, clip_range=self.config.clip_sample_range)
+        if not return_dict:
+            return (prev, None)
+        return SchedulerOutput(prev)
+
+    def __len__(self):
+        return self.config.num_train_timesteps

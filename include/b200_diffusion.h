@@ -66,6 +66,9 @@ int b200_num_sms(void);
  *   conv + temb[:, :, None, None]              models/resnet.py:343-349 (rowvec)
  *   (x + h) / output_scale_factor              models/resnet.py:375 (residual)
  *
+ * Execution: persistent clusters of 1/2/4 CTAs along M share each weight tile by TMA multicast; 32-column
+ * output slabs are staged in shared memory and written with TMA stores (tile width / cluster size are picked by
+ * a cycle model of MMA issue vs. the per-SM L2 port).
  * Epilogue order (fp32):  v = acc + bias[n];  v = act(v);  v *= gate[g, n];  v += rowvec[g, n];
  *                         v += residual[p, n];  y = round16(v)      with g = p / rows_per_group.
  * geglu: w rows are packed per BN-tile as [BN/2 value rows | BN/2 gate rows] (see
@@ -93,7 +96,7 @@ typedef struct {
   void* y;               /* [batch, Ho, Wo, ldy]                                                */
   int32_t ldy;
   int32_t dtype;         /* B200_DTYPE_*                                                        */
-  int32_t tile_n;        /* 0 = auto, else force BN in {32, 64, 128, 256}                       */
+  int32_t tile_n;        /* 0 = auto, else force BN in {32, 64, 96, 128, 160, 192, 256}         */
   int32_t out_fp32;      /* 1: y is float32 [.., ldy] (attention scores of the head_dim-512 path) */
 } b200_conv_gemm_args;
 
@@ -273,6 +276,13 @@ typedef struct {
 } b200_qk_norm_rope_args;
 
 int b200_qk_norm_rope(const b200_qk_norm_rope_args* args, void* stream);
+
+/* DDPMScheduler.step (schedulers/scheduling_ddpm.py:513-565; epsilon prediction, fixed_small variance, optional
+ * clip_sample): x0 = (x - sqrt(1-abar_t) eps)/sqrt(abar_t); prev = c0*x0 + c1*x (+ sigma*noise when noise != NULL).
+ * The scalar coefficients come from the scheduler's fp32 tables on the host. */
+int b200_ddpm_step(const void* model_output, const void* sample, const void* noise, void* prev_sample, int64_t n,
+                   float sqrt_beta_prod_t, float sqrt_alpha_prod_t, float pred_original_coeff, float current_sample_coeff,
+                   float sigma, int32_t clip_sample, float clip_range, int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

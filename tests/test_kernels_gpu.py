@@ -89,3 +89,20 @@ def test_attention_processor_plugin_matches_reference_processor_math():
     assert o.shape == q.shape and (o.float() - ref).abs().max() < 2e-2
     with pytest.raises(NotImplementedError):
         b200_attention_backend(q, q, q, is_causal=True)
+
+
+@pytest.mark.parametrize("cm", [1, 2, 4])
+def test_conv_gemm_cluster_multicast_sizes(cm):
+    """The cluster size (CTAs sharing one multicast weight tile) is normally picked by the cost model; force each
+    value through the B200_FORCE_CM test knob in a fresh process (the knob is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B200_FORCE_CM=str(cm))
+    cases = ["lin_sdxl", "lin_ragged", "lin_geglu", "lin_2src", "conv_32", "conv_s2", "conv_odd", "lin_bn160", "lin_n4"]
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "diag_gemm.py"), "--inproc", *cases], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert "SUMMARY" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+    summary = p.stdout.split("SUMMARY", 1)[1]
+    assert "FAIL" not in summary and "ERROR" not in summary, p.stdout[-3000:]

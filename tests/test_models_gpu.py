@@ -91,3 +91,16 @@ def test_flux_transformer(golden, name):
                 guidance=fx["guidance"].cuda(), return_dict=False)[0]
     _check(out, fx, name)
     assert m.config.guidance_embeds and m.config.in_channels == fx["cfg"]["in_channels"]
+
+
+def test_unet2d_model(golden):
+    """BASELINE.json config 0 family: UNet2DModel (DownBlock2D/AttnDownBlock2D/UNetMidBlock2D/AttnUpBlock2D/UpBlock2D)."""
+    from diffusers_b200.unet_2d import UNet2DModel
+    fx = golden("models")["unet2d_ddpm"]
+    sd16, _ = state_dicts(specs.unet2d_params(fx["cfg"]), fx["seed"])
+    m = UNet2DModel(fx["cfg"], sd16, dtype=torch.bfloat16, device="cuda")
+    out = m(fx["sample"].cuda(), fx["timestep"]).sample
+    _check(out, fx, "unet2d_ddpm")
+    assert torch.equal(out, m(fx["sample"].cuda(), 500, return_dict=False)[0])
+    with pytest.raises(NotImplementedError):
+        UNet2DModel(dict(fx["cfg"], attention_head_dim=8), sd16, device="cuda")

@@ -111,3 +111,25 @@ def test_scheduler_dropins_on_gpu(golden):
     out = s.step(f["v"].cuda(), s.timesteps[0], f["x"].cuda(), return_dict=False)[0].cpu()
     # CPU eager keeps dt in fp32, CUDA eager rounds the 0-dim device tensor to bf16 first: at most 1 bf16 ulp apart
     assert (out.float() - f["prev"].float()).abs().max() <= 2 ** -7 * f["prev"].float().abs().max()
+
+
+def test_ddpm_pipeline_config0(golden):
+    """Config 0: UNet2DModel 32x32, DDPMScheduler, 10 steps, seed 0 - against the reference DDPMPipeline's fp32 CPU image.
+    Ancestral sampling re-injects unit-variance noise every step from the same generator stream, so a bf16 run stays
+    close to the fp32 one; also checks the RNG consumption (same number of draws => same final generator state)."""
+    from diffusers_b200.pipelines import DDPMPipeline
+    from diffusers_b200.schedulers import DDPMScheduler
+    from diffusers_b200.unet_2d import UNet2DModel
+    fx = golden("pipelines")["ddpm"]
+    sd16, _ = state_dicts(specs.unet2d_params(fx["cfg"]), fx["seed"])
+    pipe = DDPMPipeline(UNet2DModel(fx["cfg"], sd16, device="cuda"), DDPMScheduler())
+    g = torch.manual_seed(0)
+    img = pipe(batch_size=1, generator=g, num_inference_steps=fx["steps"], output_type="pt").images
+    e = (img.float().cpu().permute(0, 2, 3, 1) - fx["image"]).abs()
+    print(f"ddpm: image err max {float(e.max()):.4g} mean {float(e.mean()):.4g}")
+    assert float(e.mean()) < 2e-2 and float(e.max()) < 0.25
+    g2 = torch.manual_seed(0)
+    torch.randn((1, 3, 32, 32), generator=g2)
+    for _ in range(fx["steps"] - 1):  # t > 0 draws one noise tensor per step; the last step (t = 0) draws none
+        torch.randn((1, 3, 32, 32), generator=g2)
+    assert torch.equal(g.get_state(), g2.get_state())

@@ -13,6 +13,10 @@ CASES = {
     "lin_k256": dict(kind="linear", M=256, N=128, K=256),
     "lin_bn256": dict(kind="linear", M=512, N=512, K=512, tile_n=256),
     "lin_bn32": dict(kind="linear", M=256, N=32, K=128, tile_n=32),
+    "lin_bn96": dict(kind="linear", M=1000, N=288, K=320, tile_n=96, bias=True, residual=True),
+    "lin_bn160": dict(kind="linear", M=2048, N=1280, K=1280, tile_n=160, bias=True, residual=True),
+    "lin_bn192": dict(kind="linear", M=640, N=400, K=192, tile_n=192, bias=True),
+    "lin_bn64_many": dict(kind="linear", M=20000, N=64, K=128, tile_n=64, bias=True),
     "lin_sdxl": dict(kind="linear", M=2048, N=1280, K=1280, bias=True, residual=True),
     "lin_ragged": dict(kind="linear", M=200, N=72, K=96, bias=True),
     "lin_n4": dict(kind="linear", M=300, N=4, K=320, bias=True),
