@@ -47,6 +47,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x on the FMA/ALU pipes (Cody-Waite split + cubic on [-0.5, 0.5], max rel. error 1.0e-4 << bf16/fp16 rounding of
+// P): the MUFU unit (16 ex2/clk/SM) is the bottleneck of a head_dim-64 attention tile, so half of the exponentials are
+// computed here, in parallel with the other half on MUFU.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05583828f, 0.24263948f);
+  p = fmaf(p, f, 0.69313675f);
+  p = fmaf(p, f, 0.99992454f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 template <int HD, int NQ, bool FP16>
 __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1) ? 2 : 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<HD, NQ>;
@@ -272,7 +285,7 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * k]), sc, -m));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * k + 1]), sc, -m));
+          float p1 = ex2_poly(fmaf(__uint_as_float(v[2 * k + 1]), sc, -m));
           if (partial) {
             if (c * 32 + 2 * k >= kv_left) p0 = 0.f;
             if (c * 32 + 2 * k + 1 >= kv_left) p1 = 0.f;

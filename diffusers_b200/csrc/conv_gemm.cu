@@ -476,9 +476,10 @@ static double tile_cost(int bn, int cm, int k_chunks, bool geglu) {
   return k_chunks * chunk + epi + 2500.0;
 }
 
-static void pick_config(long long m_tiles, int N, int k_chunks, int geglu, int force_bn, int* bn_out, int* cm_out) {
+static void pick_config(long long m_tiles, int N, int k_chunks, int geglu, int force_bn, int force_cm_arg, int* bn_out, int* cm_out) {
   const int sms = num_sms();
-  static const int force_cm = getenv("B200_FORCE_CM") ? atoi(getenv("B200_FORCE_CM")) : 0;  // test knob
+  static const int env_cm = getenv("B200_FORCE_CM") ? atoi(getenv("B200_FORCE_CM")) : 0;  // test knob
+  const int force_cm = force_cm_arg ? force_cm_arg : env_cm;
   double best = 1e30;
   int best_bn = 0, best_cm = 1;
   static const int kBn[] = {256, 192, 160, 128, 96, 64, 32};
@@ -515,7 +516,7 @@ static int pick_tile_n(long long M, int N, int geglu) {
     return 0;
   }
   int bn, cm;
-  pick_config((M + 127) / 128, N, 20, 0, 0, &bn, &cm);
+  pick_config((M + 127) / 128, N, 20, 0, 0, 0, &bn, &cm);
   return bn;
 }
 
@@ -547,6 +548,7 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   if (a->stride == 2) B200_CHECK_ARG(a->H % 2 == 0 && a->W % 2 == 0, "conv_gemm: stride 2 needs even H, W");
   if (a->geglu) B200_CHECK_ARG(a->N % 64 == 0, "conv_gemm: geglu needs N %% 64 == 0 (N=%d)", a->N);
   if (a->gate || a->rowvec) B200_CHECK_ARG(a->rows_per_group > 0, "conv_gemm: rows_per_group must be > 0");
+  B200_CHECK_ARG(a->cluster_m == 0 || a->cluster_m == 1 || a->cluster_m == 2 || a->cluster_m == 4, "conv_gemm: cluster_m %d", a->cluster_m);
   B200_CHECK_ARG(a->tile_n == 0 || a->tile_n == 32 || a->tile_n == 64 || a->tile_n == 96 || a->tile_n == 128 ||
                      a->tile_n == 160 || a->tile_n == 192 || a->tile_n == 256,
                  "conv_gemm: tile_n %d not in {32,64,96,128,160,192,256}", a->tile_n);
@@ -586,7 +588,7 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   prm.k_chunks = prm.num_taps * (prm.chunks[0] + prm.chunks[1]);
 
   int bn = 0, cm = 1;
-  pick_config(prm.m_tiles, a->N, prm.k_chunks, a->geglu, a->geglu && !a->tile_n ? pick_tile_n(0, a->N, 1) : a->tile_n, &bn, &cm);
+  pick_config(prm.m_tiles, a->N, prm.k_chunks, a->geglu, a->geglu && !a->tile_n ? pick_tile_n(0, a->N, 1) : a->tile_n, a->cluster_m, &bn, &cm);
   B200_CHECK_ARG(bn != 0, "conv_gemm: no valid tile configuration (N=%d geglu=%d tile_n=%d)", a->N, a->geglu, a->tile_n);
   if (a->geglu) B200_CHECK_ARG(a->N % bn == 0, "conv_gemm: geglu N=%d not a multiple of tile_n=%d", a->N, bn);
   prm.cm = cm;

@@ -424,8 +424,8 @@ extern "C" {
 int64_t b200_group_norm_workspace_bytes(int32_t batch, int32_t hw, int32_t groups) {
   int chunks, ppc;
   b200::gn_plan(batch, hw, 0, &chunks, &ppc);
-  // partial [batch][chunks][groups][3] + stats [batch][groups][2] + counters [batch]; chunks <= 256
-  int64_t floats = static_cast<int64_t>(batch) * 256 * groups * 3 + static_cast<int64_t>(batch) * groups * 2 + batch;
+  // counters [1024] + stats [batch][groups][2] + partial [batch][chunks][groups][3]; chunks <= 256
+  int64_t floats = 1024 + static_cast<int64_t>(batch) * 256 * groups * 3 + static_cast<int64_t>(batch) * groups * 2;
   (void)chunks;
   return floats * 4 + 256;
 }
@@ -473,10 +473,13 @@ int b200_group_norm(const b200_group_norm_args* a, void* stream) {
   if (p.P < 1) p.P = 1;
   if (p.P > 64) p.P = 64;
   if (p.P > p.ppc) p.P = p.ppc;
+  // workspace layout: [1024 completion counters | stats | partials].  The counters live at a FIXED offset so that
+  // they stay zero between launches whatever batch / shape the previous call used.
+  B200_CHECK_ARG(a->batch <= 1024, "group_norm: batch %d > 1024", a->batch);
   float* ws = static_cast<float*>(a->workspace);
-  p.partial = ws;
-  p.stats = ws + static_cast<size_t>(a->batch) * 256 * a->groups * 3;
-  p.counter = reinterpret_cast<unsigned int*>(p.stats + static_cast<size_t>(a->batch) * a->groups * 2);
+  p.counter = reinterpret_cast<unsigned int*>(ws);
+  p.stats = ws + 1024;
+  p.partial = p.stats + static_cast<size_t>(a->batch) * a->groups * 2;
   {
     // ~8 CTAs per SM for the apply pass, at least 8 pixels each so the per-CTA scale/bias prologue amortises
     long long total = static_cast<long long>(a->batch) * a->hw;
