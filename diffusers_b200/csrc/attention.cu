@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
   uint64_t* o_full = p_full + 2;        // [NQ]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // work decomposition: blockIdx.x -> (q tile group, head, batch)
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int n_blocks = p.kv_blocks;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -358,8 +360,9 @@ int init_attention() {
 
 template <int HD, int NQ, bool FP16>
 static int attn_launch(const AttnParams& prm, int grid, cudaStream_t st) {
-  attention_kernel<HD, NQ, FP16><<<grid, AttnCfg<HD, NQ>::THREADS, AttnCfg<HD, NQ>::SMEM_BYTES, st>>>(prm);
-  return check_launch("attention_kernel");
+  cudaError_t e = launch_pdl(attention_kernel<HD, NQ, FP16>, dim3(grid), dim3(AttnCfg<HD, NQ>::THREADS), AttnCfg<HD, NQ>::SMEM_BYTES, st, prm);
+  if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention launch: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 }  // namespace b200

@@ -264,6 +264,12 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// Programmatic dependent launch: `pdl_trigger` lets the next kernel in the stream start its prologue as soon as this
+// grid's CTAs have all issued it (or exited); `pdl_wait` blocks until every prerequisite grid has completed and its
+// memory is visible.  Every kernel calls pdl_wait before its first global-memory access.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -45,6 +45,7 @@ struct ConvGemmParams {
   int vec_ok;    // y / residual / gate / rowvec / bias allow 16-byte accesses
   int out_fp32;  // y is float (attention scores of the unfused head_dim-512 path)
   int tma_store; // epilogue stages 32-column slabs in smem and writes them with TMA (needs vec_ok, 16-bit y)
+  long long* dbg; // optional [grid][8] clock64 timestamps (tuning aid)
 };
 
 template <int BN>
@@ -99,6 +100,8 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
+  const long long t_entry = clock64();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cm = p.cm;
@@ -130,6 +133,12 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   if (cm > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive / multicast write
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; no global access before this point
+  long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) {
+    dbg[0] = t_entry;
+    dbg[1] = clock64();
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -156,6 +165,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                 tma_load_2d_mcast(sb, &p.w_map, &full_bar[stage], kc * 64, tc.n0 + rank * b_rows, cmask);
               else
                 tma_load_2d(sb, &p.w_map, &full_bar[stage], kc * 64, tc.n0);
+              if (dbg && kc == 0 && g == cluster) dbg[2] = clock64();
               ++kc;
               if (++stage == STAGES) {
                 stage = 0;
@@ -182,6 +192,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (dbg && kc == 0 && it == 0) dbg[3] = clock64();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t a_desc = make_smem_desc_sw128(a_addr, 16, 1024);
           const uint64_t b_desc = make_smem_desc_sw128(a_addr + Cfg::A_BYTES, 16, 1024);
@@ -200,6 +211,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
           }
         }
         umma_commit(&tfull_bar[acc]);
+        if (dbg) dbg[4] = clock64();
       }
     }
   } else if (warp >= 4) {
@@ -235,17 +247,21 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 
       constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
       const int ycol0 = GEGLU ? (tc.n0 >> 1) : tc.n0;
-      if (res_row && valid) {  // pull this row's residual lines towards L2 while the main loop runs
+      // this row's residual values are fetched into registers now, while the main loop of the tile is still running
+      uint4 res[GEGLU ? 1 : OUT_COLS / 8];
+      const bool res_pre = !GEGLU && res_row != nullptr && valid && p.vec_ok;
+      if (res_pre) {
 #pragma unroll
-        for (int c = 0; c < OUT_COLS; c += 64)
-          if (ycol0 + c < n_limit) prefetch_l2(res_row + ycol0 + c);
+        for (int i = 0; i < OUT_COLS / 8; ++i)
+          res[i] = (ycol0 + i * 8 + 8 <= n_limit) ? *reinterpret_cast<const uint4*>(res_row + ycol0 + i * 8) : make_uint4(0, 0, 0, 0);
       }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (dbg && issuer) dbg[5] = clock64();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
 
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < OUT_COLS / 32; ++c) {
         if (ycol0 + c * 32 >= n_limit) break;  // warp-uniform
         uint32_t v[32];
@@ -303,8 +319,8 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                 f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
                 f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
               }
-              if (res_row && valid) {
-                uint4 b = *reinterpret_cast<const uint4*>(res_row + yc);
+              if (res_pre) {
+                const uint4 b = res[GEGLU ? 0 : c * 4 + j8];
                 float2 t0 = H::unpack(b.x), t1 = H::unpack(b.y), t2 = H::unpack(b.z), t3 = H::unpack(b.w);
                 f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
                 f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
@@ -372,7 +388,8 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
-    if (tma_store && issuer) bulk_wait_group<0>();  // smem must outlive the in-flight stores
+    if (dbg && issuer) dbg[6] = clock64();
+    if (tma_store && issuer) bulk_wait_group_read<0>();  // smem must outlive the stores' reads; kernel exit publishes the writes
   }
 
   tc_fence_before();
@@ -382,6 +399,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+  if (dbg && threadIdx.x == 0) dbg[7] = clock64();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -418,13 +436,15 @@ static int launch_one(const ConvGemmParams& prm, int grid, int cm, cudaStream_t 
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = ConvGemmCfg<BN>::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cm;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   if (cm > 1) {
     // GPC boundaries can strand SMs for clusters: never launch more clusters than can be co-resident, the
     // persistent tile loop strides by the number of clusters actually launched
@@ -668,6 +688,7 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   if (a->residual) vec = vec && aligned16(a->residual) && (a->ldr % 8 == 0);
   prm.vec_ok = vec ? 1 : 0;
   prm.out_fp32 = a->out_fp32 ? 1 : 0;
+  prm.dbg = static_cast<long long*>(a->debug_timestamps);
   const int n_out = a->geglu ? a->N / 2 : a->N;
   prm.tma_store = (vec && !a->out_fp32 && n_out % 8 == 0) ? 1 : 0;
   if (prm.tma_store) {

@@ -14,6 +14,8 @@ namespace b200 {
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int HW, int ld_dst,
                                     long long total) {
+  pdl_trigger();
+  pdl_wait();
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = static_cast<int>(i % ld_dst);
@@ -28,6 +30,8 @@ __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, T* __restrict__ d
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int ld_src, T* __restrict__ dst, int C, int HW,
                                     long long total) {
+  pdl_trigger();
+  pdl_wait();
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // index into dst (n, c, pix)
   if (i >= total) return;
   const int pix = static_cast<int>(i % HW);
@@ -42,6 +46,8 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int ld_src, T* __
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, int ldx8, uint4* __restrict__ y, int ldy8, int H, int W,
                                   int V, long long total) {
+  pdl_trigger();
+  pdl_wait();
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int v = static_cast<int>(i % V);
@@ -62,6 +68,8 @@ template <bool FP16>
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, void* out_, int ld_out, int dim,
                                           int flip_sin_to_cos, float downscale_freq_shift, float scale,
                                           float max_period) {
+  pdl_trigger();
+  pdl_wait();
   using H = Half16<FP16>;
   typename H::T* out = static_cast<typename H::T*>(out_);
   const int half = dim / 2;
@@ -104,6 +112,8 @@ struct SmallLinearParams {
 
 template <bool FP16>
 __global__ void __launch_bounds__(256) small_linear_kernel(const SmallLinearParams p) {
+  pdl_trigger();
+  pdl_wait();
   using H = Half16<FP16>;
   extern __shared__ float s_x[];  // [M][K] fp32 (rounded through the 16-bit type after act_in, like the reference)
   const typename H::T* x = static_cast<const typename H::T*>(p.x);
@@ -177,6 +187,8 @@ __device__ __forceinline__ float euler_update(float x, float eps, float sigma, f
 template <bool FP16>
 __global__ void euler_step_kernel(const void* eps_, const void* sample_, void* prev_, long long n, float sigma,
                                   float dt) {
+  pdl_trigger();
+  pdl_wait();
   using H = Half16<FP16>;
   const typename H::T* eps = static_cast<const typename H::T*>(eps_);
   const typename H::T* sample = static_cast<const typename H::T*>(sample_);
@@ -194,6 +206,8 @@ template <bool FP16>
 __global__ void cfg_euler_step_kernel(const void* eps_, int ld_eps, void* latents_, void* next_in_, int ld_in, int B,
                                       int C, int HW, float guidance, float sigma, float dt, float next_div,
                                       int do_cfg) {
+  pdl_trigger();
+  pdl_wait();
   using H = Half16<FP16>;
   const typename H::T* eps = static_cast<const typename H::T*>(eps_);
   typename H::T* lat = static_cast<typename H::T*>(latents_);
@@ -233,6 +247,8 @@ __global__ void cfg_euler_step_kernel(const void* eps_, int ld_eps, void* latent
 // reference, so eager CUDA casts it to the 16-bit common dtype before the multiply.
 template <bool FP16>
 __global__ void flow_match_step_kernel(const void* v_, const void* sample_, void* prev_, long long n, float dt) {
+  pdl_trigger();
+  pdl_wait();
   using H = Half16<FP16>;
   const typename H::T* v = static_cast<const typename H::T*>(v_);
   const typename H::T* sample = static_cast<const typename H::T*>(sample_);
@@ -246,6 +262,8 @@ __global__ void flow_match_step_kernel(const void* v_, const void* sample_, void
 // y = r16(x / div)  (EulerDiscreteScheduler.scale_model_input, scheduling_euler_discrete.py:345)
 template <bool FP16>
 __global__ void scale_kernel(const void* x_, void* y_, long long n, float div) {
+  pdl_trigger();
+  pdl_wait();
   using H = Half16<FP16>;
   const typename H::T* x = static_cast<const typename H::T*>(x_);
   typename H::T* y = static_cast<typename H::T*>(y_);
@@ -260,6 +278,8 @@ __global__ void scale_kernel(const void* x_, void* y_, long long n, float div) {
 template <bool FP16>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, long long ld_s, void* p_,
                                                            long long ld_p, int cols, float scale_log2) {
+  pdl_trigger();
+  pdl_wait();
   using H = Half16<FP16>;
   __shared__ float red[8];
   const float* row = s + static_cast<long long>(blockIdx.x) * ld_s;
@@ -312,6 +332,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 
 __global__ void transpose16_kernel(const uint16_t* __restrict__ src, long long ld_src, uint16_t* __restrict__ dst,
                                    long long ld_dst, int rows, int cols) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ uint16_t tile[32][34];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -332,6 +354,8 @@ template <bool FP16>
 __global__ void ddpm_step_kernel(const void* eps_, const void* sample_, const void* noise_, void* prev_, long long n,
                                  float sqrt_beta_prod, float sqrt_alpha_prod, float c0, float c1, float sigma, int clip,
                                  float clip_range) {
+  pdl_trigger();
+  pdl_wait();
   using H = Half16<FP16>;
   const typename H::T* eps = static_cast<const typename H::T*>(eps_);
   const typename H::T* sample = static_cast<const typename H::T*>(sample_);
@@ -361,7 +385,7 @@ int b200_nchw_to_nhwc(const void* src, void* dst, int32_t batch, int32_t C, int3
   B200_CHECK_ARG(src && dst && batch > 0 && C > 0 && HW > 0 && ld_dst >= C, "nchw_to_nhwc: bad args");
   (void)dtype;  // both 16-bit types move as raw 16-bit words; zero is all-bits-zero in both
   const long long total = static_cast<long long>(batch) * HW * ld_dst;
-  nchw_to_nhwc_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(nchw_to_nhwc_kernel<__nv_bfloat16>, dim3(blocks_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), C, HW, ld_dst, total);
   return check_launch("nchw_to_nhwc_kernel");
 }
@@ -372,7 +396,7 @@ int b200_nhwc_to_nchw(const void* src, int32_t ld_src, void* dst, int32_t batch,
   B200_CHECK_ARG(src && dst && batch > 0 && C > 0 && HW > 0 && ld_src >= C, "nhwc_to_nchw: bad args");
   (void)dtype;
   const long long total = static_cast<long long>(batch) * HW * C;
-  nhwc_to_nchw_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(nhwc_to_nchw_kernel<__nv_bfloat16>, dim3(blocks_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(src), ld_src, static_cast<__nv_bfloat16*>(dst), C, HW, total);
   return check_launch("nhwc_to_nchw_kernel");
 }
@@ -386,7 +410,7 @@ int b200_upsample_nearest2x(const void* x, int32_t ldx, void* y, int32_t ldy, in
   (void)dtype;
   const int V = C / 8;
   const long long total = static_cast<long long>(batch) * 4 * H * W * V;
-  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(upsample2x_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const uint4*>(x), ldx / 8, static_cast<uint4*>(y), ldy / 8, H, W, V, total);
   return check_launch("upsample2x_kernel");
 }
@@ -398,10 +422,10 @@ int b200_timestep_embedding(const float* t, int32_t n, void* out, int32_t ld_out
   const int total = n * (dim / 2);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200_DTYPE_FP16)
-    timestep_embedding_kernel<true><<<blocks_for(total, 128), 128, 0, st>>>(t, n, out, ld_out, dim, flip_sin_to_cos,
+    launch_pdl(timestep_embedding_kernel<true>, dim3(blocks_for(total, 128)), dim3(128), 0, st, t, n, out, ld_out, dim, flip_sin_to_cos,
                                                                            downscale_freq_shift, scale, max_period);
   else
-    timestep_embedding_kernel<false><<<blocks_for(total, 128), 128, 0, st>>>(t, n, out, ld_out, dim, flip_sin_to_cos,
+    launch_pdl(timestep_embedding_kernel<false>, dim3(blocks_for(total, 128)), dim3(128), 0, st, t, n, out, ld_out, dim, flip_sin_to_cos,
                                                                             downscale_freq_shift, scale, max_period);
   return check_launch("timestep_embedding_kernel");
 }
@@ -425,9 +449,9 @@ int b200_small_linear(const b200_small_linear_args* a, void* stream) {
   const int grid = (a->N + 7) / 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (fp16)
-    small_linear_kernel<true><<<grid, 256, smem, st>>>(p);
+    launch_pdl(small_linear_kernel<true>, dim3(grid), dim3(256), smem, st, p);
   else
-    small_linear_kernel<false><<<grid, 256, smem, st>>>(p);
+    launch_pdl(small_linear_kernel<false>, dim3(grid), dim3(256), smem, st, p);
   return check_launch("small_linear_kernel");
 }
 
@@ -438,9 +462,9 @@ int b200_euler_step(const void* model_output, const void* sample, void* prev_sam
   const float dt = sigma_next - sigma;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200_DTYPE_FP16)
-    euler_step_kernel<true><<<blocks_for(n, 256), 256, 0, st>>>(model_output, sample, prev_sample, n, sigma, dt);
+    launch_pdl(euler_step_kernel<true>, dim3(blocks_for(n, 256)), dim3(256), 0, st, model_output, sample, prev_sample, n, sigma, dt);
   else
-    euler_step_kernel<false><<<blocks_for(n, 256), 256, 0, st>>>(model_output, sample, prev_sample, n, sigma, dt);
+    launch_pdl(euler_step_kernel<false>, dim3(blocks_for(n, 256)), dim3(256), 0, st, model_output, sample, prev_sample, n, sigma, dt);
   return check_launch("euler_step_kernel");
 }
 
@@ -457,11 +481,11 @@ int b200_cfg_euler_step(const void* eps_nhwc, int32_t ld_eps, void* latents_nchw
   const long long total = static_cast<long long>(batch) * HW * ld_in;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200_DTYPE_FP16)
-    cfg_euler_step_kernel<true><<<blocks_for(total, 256), 256, 0, st>>>(eps_nhwc, ld_eps, latents_nchw, next_in_nhwc,
+    launch_pdl(cfg_euler_step_kernel<true>, dim3(blocks_for(total, 256)), dim3(256), 0, st, eps_nhwc, ld_eps, latents_nchw, next_in_nhwc,
                                                                         ld_in, batch, C, HW, guidance_scale, sigma, dt,
                                                                         next_div, do_cfg);
   else
-    cfg_euler_step_kernel<false><<<blocks_for(total, 256), 256, 0, st>>>(eps_nhwc, ld_eps, latents_nchw, next_in_nhwc,
+    launch_pdl(cfg_euler_step_kernel<false>, dim3(blocks_for(total, 256)), dim3(256), 0, st, eps_nhwc, ld_eps, latents_nchw, next_in_nhwc,
                                                                          ld_in, batch, C, HW, guidance_scale, sigma, dt,
                                                                          next_div, do_cfg);
   return check_launch("cfg_euler_step_kernel");
@@ -474,9 +498,9 @@ int b200_flow_match_step(const void* model_output, const void* sample, void* pre
   const float dt = sigma_next - sigma;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200_DTYPE_FP16)
-    flow_match_step_kernel<true><<<blocks_for(n, 256), 256, 0, st>>>(model_output, sample, prev_sample, n, dt);
+    launch_pdl(flow_match_step_kernel<true>, dim3(blocks_for(n, 256)), dim3(256), 0, st, model_output, sample, prev_sample, n, dt);
   else
-    flow_match_step_kernel<false><<<blocks_for(n, 256), 256, 0, st>>>(model_output, sample, prev_sample, n, dt);
+    launch_pdl(flow_match_step_kernel<false>, dim3(blocks_for(n, 256)), dim3(256), 0, st, model_output, sample, prev_sample, n, dt);
   return check_launch("flow_match_step_kernel");
 }
 
@@ -485,9 +509,9 @@ int b200_scale(const void* x, void* y, int64_t n, float divisor, int32_t dtype, 
   B200_CHECK_ARG(x && y && n > 0 && divisor != 0.f, "scale: bad args");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200_DTYPE_FP16)
-    scale_kernel<true><<<blocks_for(n, 256), 256, 0, st>>>(x, y, n, divisor);
+    launch_pdl(scale_kernel<true>, dim3(blocks_for(n, 256)), dim3(256), 0, st, x, y, n, divisor);
   else
-    scale_kernel<false><<<blocks_for(n, 256), 256, 0, st>>>(x, y, n, divisor);
+    launch_pdl(scale_kernel<false>, dim3(blocks_for(n, 256)), dim3(256), 0, st, x, y, n, divisor);
   return check_launch("scale_kernel");
 }
 
@@ -500,9 +524,9 @@ int b200_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t ld_p, int32
   const float sl2 = scale * 1.4426950408889634f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200_DTYPE_FP16)
-    softmax_rows_kernel<true><<<rows, 256, 0, st>>>(s, ld_s, p, ld_p, cols, sl2);
+    launch_pdl(softmax_rows_kernel<true>, dim3(rows), dim3(256), 0, st, s, ld_s, p, ld_p, cols, sl2);
   else
-    softmax_rows_kernel<false><<<rows, 256, 0, st>>>(s, ld_s, p, ld_p, cols, sl2);
+    launch_pdl(softmax_rows_kernel<false>, dim3(rows), dim3(256), 0, st, s, ld_s, p, ld_p, cols, sl2);
   return check_launch("softmax_rows_kernel");
 }
 
@@ -511,7 +535,7 @@ int b200_transpose_16(const void* src, int64_t ld_src, void* dst, int64_t ld_dst
   using namespace b200;
   B200_CHECK_ARG(src && dst && rows > 0 && cols > 0, "transpose_16: bad args");
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-  transpose16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(transpose16_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const uint16_t*>(src), ld_src, static_cast<uint16_t*>(dst), ld_dst, rows, cols);
   return check_launch("transpose16_kernel");
 }
@@ -523,11 +547,11 @@ int b200_ddpm_step(const void* model_output, const void* sample, const void* noi
   B200_CHECK_ARG(model_output && sample && prev_sample && n > 0 && sqrt_alpha_prod_t > 0.f, "ddpm_step: bad args");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200_DTYPE_FP16)
-    ddpm_step_kernel<true><<<blocks_for(n, 256), 256, 0, st>>>(model_output, sample, noise, prev_sample, n, sqrt_beta_prod_t,
+    launch_pdl(ddpm_step_kernel<true>, dim3(blocks_for(n, 256)), dim3(256), 0, st, model_output, sample, noise, prev_sample, n, sqrt_beta_prod_t,
                                                               sqrt_alpha_prod_t, pred_original_coeff, current_sample_coeff,
                                                               sigma, clip_sample, clip_range);
   else
-    ddpm_step_kernel<false><<<blocks_for(n, 256), 256, 0, st>>>(model_output, sample, noise, prev_sample, n, sqrt_beta_prod_t,
+    launch_pdl(ddpm_step_kernel<false>, dim3(blocks_for(n, 256)), dim3(256), 0, st, model_output, sample, noise, prev_sample, n, sqrt_beta_prod_t,
                                                                sqrt_alpha_prod_t, pred_original_coeff, current_sample_coeff,
                                                                sigma, clip_sample, clip_range);
   return check_launch("ddpm_step_kernel");

@@ -1,4 +1,5 @@
 // Library-level entry points: version, error string, device init, tensor-map encoding.
+#include <stdlib.h>
 #include <string.h>
 
 #include "host_common.h"
@@ -15,6 +16,11 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("B200_NO_PDL") && atoi(getenv("B200_NO_PDL")) != 0);
+  return on;
 }
 
 int num_sms() {

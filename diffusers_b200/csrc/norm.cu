@@ -45,6 +45,8 @@ __device__ __forceinline__ void chan_combine(float& na, float& ma, float& M2a, f
 // (deterministic).  The last CTA of an image to finish folds the chunk partials into mean/rstd.
 template <bool FP16>
 __global__ void group_norm_stats_kernel(const GroupNormParams p) {
+  pdl_trigger();
+  pdl_wait();
   using H = Half16<FP16>;
   extern __shared__ float2 s_mm[];  // [P][C] (mean, M2) per (pixel lane, channel)
   __shared__ float s_cnt[64];       // per pixel lane count (P <= 64)
@@ -164,6 +166,8 @@ __global__ void group_norm_stats_kernel(const GroupNormParams p) {
 // bi = beta - mean*rstd*gamma staged in shared memory.
 template <bool FP16>
 __global__ void __launch_bounds__(256) group_norm_apply_kernel(const GroupNormParams p) {
+  pdl_trigger();
+  pdl_wait();
   using H = Half16<FP16>;
   extern __shared__ float s_scbi[];  // [2][C]
   float* s_sc = s_scbi;
@@ -256,6 +260,8 @@ struct LayerNormParams {
 
 template <bool FP16, int NV>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const LayerNormParams p) {
+  pdl_trigger();
+  pdl_wait();
   using H = Half16<FP16>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -355,6 +361,8 @@ struct QkNormRopeParams {
 
 template <bool FP16, int HD>
 __global__ void __launch_bounds__(256) qk_norm_rope_kernel(const QkNormRopeParams p) {
+  pdl_trigger();
+  pdl_wait();
   using H = Half16<FP16>;
   constexpr int EPL = HD / 32;  // elements per lane (2 or 4): rotation pairs stay inside a lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -503,9 +511,9 @@ int b200_group_norm(const b200_group_norm_args* a, void* stream) {
       if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "group_norm smem attr: %s", cudaGetErrorString(e));
     }
     if (fp16)
-      group_norm_stats_kernel<true><<<grid, threads, smem, st>>>(p);
+      launch_pdl(group_norm_stats_kernel<true>, dim3(grid), dim3(threads), smem, st, p);
     else
-      group_norm_stats_kernel<false><<<grid, threads, smem, st>>>(p);
+      launch_pdl(group_norm_stats_kernel<false>, dim3(grid), dim3(threads), smem, st, p);
     int r = check_launch("group_norm_stats_kernel");
     if (r) return r;
   }
@@ -513,9 +521,9 @@ int b200_group_norm(const b200_group_norm_args* a, void* stream) {
     dim3 grid((a->hw + p.apply_ppb - 1) / p.apply_ppb, a->batch);
     size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
     if (fp16)
-      group_norm_apply_kernel<true><<<grid, 256, smem, st>>>(p);
+      launch_pdl(group_norm_apply_kernel<true>, dim3(grid), dim3(256), smem, st, p);
     else
-      group_norm_apply_kernel<false><<<grid, 256, smem, st>>>(p);
+      launch_pdl(group_norm_apply_kernel<false>, dim3(grid), dim3(256), smem, st, p);
     return check_launch("group_norm_apply_kernel");
   }
 }
@@ -550,9 +558,9 @@ int b200_layer_norm(const b200_layer_norm_args* a, void* stream) {
   const int nvec = a->cols / 8;
 #define B200_LN(NV)                                              \
   if (fp16)                                                      \
-    layer_norm_kernel<true, NV><<<grid, warps * 32, 0, st>>>(p); \
+    launch_pdl(layer_norm_kernel<true, NV>, dim3(grid), dim3(warps * 32), 0, st, p); \
   else                                                           \
-    layer_norm_kernel<false, NV><<<grid, warps * 32, 0, st>>>(p);
+    launch_pdl(layer_norm_kernel<false, NV>, dim3(grid), dim3(warps * 32), 0, st, p);
   if (nvec <= 32 * 3) {
     B200_LN(3)
   } else if (nvec <= 32 * 5) {
@@ -586,11 +594,11 @@ int b200_qk_norm_rope(const b200_qk_norm_rope_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool fp16 = a->dtype == B200_DTYPE_FP16;
   if (a->head_dim == 128) {
-    if (fp16) qk_norm_rope_kernel<true, 128><<<grid, 256, 0, st>>>(p);
-    else qk_norm_rope_kernel<false, 128><<<grid, 256, 0, st>>>(p);
+    if (fp16) launch_pdl(qk_norm_rope_kernel<true, 128>, dim3(grid), dim3(256), 0, st, p);
+    else launch_pdl(qk_norm_rope_kernel<false, 128>, dim3(grid), dim3(256), 0, st, p);
   } else {
-    if (fp16) qk_norm_rope_kernel<true, 64><<<grid, 256, 0, st>>>(p);
-    else qk_norm_rope_kernel<false, 64><<<grid, 256, 0, st>>>(p);
+    if (fp16) launch_pdl(qk_norm_rope_kernel<true, 64>, dim3(grid), dim3(256), 0, st, p);
+    else launch_pdl(qk_norm_rope_kernel<false, 64>, dim3(grid), dim3(256), 0, st, p);
   }
   return check_launch("qk_norm_rope_kernel");
 }

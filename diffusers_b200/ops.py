@@ -44,7 +44,7 @@ def _need_cuda(t, name):
 
 
 def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, act=ACT_NONE, geglu=False,
-              gate=None, rowvec=None, rows_per_group=0, residual=None, out=None, tile_n=0, out_fp32=False, cluster_m=0):
+              gate=None, rowvec=None, rows_per_group=0, residual=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None):
     """y = epilogue(conv/linear(x [, x2]))  -  see b200_conv_gemm in include/b200_diffusion.h.
 
     x, x2: NHWC activations given as 2-D [batch*H*W, C] (or any shape whose last dim is C, contiguous rows).
@@ -78,6 +78,7 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
     a.tile_n = tile_n
     a.out_fp32 = 1 if out_fp32 else 0
     a.cluster_m = cluster_m
+    a.debug_timestamps = _ptr(debug_timestamps)
     if _PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -92,12 +93,12 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
 
 
 def linear(x, w, N, *, bias=None, act=ACT_NONE, geglu=False, gate=None, rowvec=None, rows_per_group=0,
-           residual=None, x2=None, out=None, tile_n=0, out_fp32=False, cluster_m=0):
+           residual=None, x2=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None):
     """nn.Linear on token rows: x [rows, K] (row stride arbitrary multiple of 8)."""
     rows = x.shape[0]
     return conv_gemm(x, w, N, batch=1, H=1, W=rows, ksize=1, stride=1, x2=x2, bias=bias, act=act, geglu=geglu,
                      gate=gate, rowvec=rowvec, rows_per_group=rows_per_group, residual=residual, out=out,
-                     tile_n=tile_n, out_fp32=out_fp32, cluster_m=cluster_m)
+                     tile_n=tile_n, out_fp32=out_fp32, cluster_m=cluster_m, debug_timestamps=debug_timestamps)
 
 
 def pick_tile_n(M, N, geglu=False):

@@ -26,25 +26,32 @@ def main():
         b = torch.randn(N, generator=g, device="cuda").bfloat16()
         r = torch.randn(M, N, generator=g, device="cuda").bfloat16() if res else None
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-        flush = torch.empty(64 << 20, dtype=torch.int32, device="cuda")  # 256 MB > L2
         print(f"--- M={M} N={N} K={K} residual={res}  (auto tile_n={ops.pick_tile_n(M, N)})")
-        for bn, cm in itertools.product((256, 192, 160, 128, 96, 64), (1, 2, 4)):
+        cfgs = [(int(os.environ['BN']), int(os.environ.get('CM', 1)))] if 'BN' in os.environ else itertools.product((256, 192, 160, 128, 96, 64), (1, 2))
+        for bn, cm in cfgs:
             if (bn // cm) % 8:
                 continue
             try:
-                f = lambda: ops.linear(x, w, N, bias=b, residual=r, out=out, tile_n=bn, cluster_m=cm)  # noqa: E731
-                for _ in range(3):
-                    f()
+                ws = [w] + [w.clone() for _ in range(7)]  # rotate weight copies so the weights are not L2-resident
+                f = lambda i=0: ops.linear(x, ws[i % 8], N, bias=b, residual=r, out=out, tile_n=bn, cluster_m=cm)  # noqa: E731
+                for i in range(3):
+                    f(i)
+                torch.cuda.synchronize()
+                # GPU-bound timing: 24 launches captured in one CUDA graph (host launch cost would otherwise dominate)
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph):
+                    for i in range(24):
+                        f(i)
+                gph.replay()
                 torch.cuda.synchronize()
                 ts = []
-                for _ in range(10):
-                    flush.zero_()
+                for _ in range(5):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    f()
+                    gph.replay()
                     e1.record()
                     torch.cuda.synchronize()
-                    ts.append(e0.elapsed_time(e1) * 1e3)
+                    ts.append(e0.elapsed_time(e1) * 1e3 / 24)
                 ts.sort()
                 us = ts[len(ts) // 2]
                 print(f"   bn={bn:3d} cm={cm}  {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s  (min {ts[0]:.1f})", flush=True)

@@ -1,0 +1,37 @@
+"""Per-CTA clock64 timeline of one b200_conv_gemm launch (debug_timestamps): where do the cycles go?"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from diffusers_b200 import ops, packing
+
+M, N, K = [int(v) for v in (sys.argv[1:4] or (2048, 1280, 1280))]
+bn = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+g = torch.Generator(device="cuda").manual_seed(0)
+x = torch.randn(M, K, generator=g, device="cuda").bfloat16()
+w = packing.pack_linear_weight((torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).bfloat16())
+b = torch.randn(N, generator=g, device="cuda").bfloat16()
+r = torch.randn(M, N, generator=g, device="cuda").bfloat16()
+out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+dbg = torch.zeros(148, 8, dtype=torch.int64, device="cuda")
+for _ in range(3):
+    ops.linear(x, w, N, bias=b, residual=r, out=out, tile_n=bn, debug_timestamps=dbg)
+torch.cuda.synchronize()
+flush = torch.empty(64 << 20, dtype=torch.int32, device="cuda")
+for rep in range(2):
+    flush.zero_()
+    dbg.zero_()
+    ops.linear(x, w, N, bias=b, residual=r, out=out, tile_n=bn, debug_timestamps=dbg)
+    torch.cuda.synchronize()
+    d = dbg.cpu()
+    d = d[d[:, 7] > 0]
+    names = ["entry", "prologue done", "first TMA issued", "first data landed", "last MMA committed", "accumulator ready (epi)",
+             "epilogue stores issued", "exit"]
+    print(f"rep {rep}: {d.shape[0]} CTAs; medians of (t_i - t_entry) in cycles:")
+    for i in range(1, 8):
+        v = (d[:, i] - d[:, 0]).float()
+        v = v[d[:, i] > 0]
+        if len(v):
+            print(f"   {names[i]:28s} median {int(v.median()):7d}  min {int(v.min()):7d}  max {int(v.max()):7d}")
