@@ -21,6 +21,28 @@
 
 namespace b200 {
 
+// compact activations for the epilogue (code size is performance-critical there):
+//   SiLU      x * sigmoid(x)
+//   GELU-tanh 0.5 x (1 + tanh(u)) == x * sigmoid(2u),  u = sqrt(2/pi) (x + 0.044715 x^3)
+//   GELU-erf  0.5 x (1 + erf(x / sqrt 2)) with Abramowitz-Stegun 7.1.26 (|erf error| < 1.5e-7, far below 16-bit rounding)
+__device__ __forceinline__ float sigmoid_fast(float t) { return __fdividef(1.0f, 1.0f + __expf(-t)); }
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float act_fast(float x, int act) {
+  if (act == ACT_GELU_ERF) return gelu_erf_fast(x);
+  const float a = (act == ACT_SILU) ? 1.0f : 1.5957691216057308f;     // 2*sqrt(2/pi)
+  const float b = (act == ACT_SILU) ? 0.0f : 0.07135481627f;          // 2*sqrt(2/pi)*0.044715
+  return x * sigmoid_fast(x * fmaf(b, x * x, a));
+}
+
 struct ConvGemmParams {
   CUtensorMap a_map[8];  // [src][parity]; stride-1 convs only use parity 0
   CUtensorMap w_map;     // box {64, BN / cm}: every CTA of a cluster loads one slice and multicasts it
@@ -45,7 +67,7 @@ struct ConvGemmParams {
   int vec_ok;    // y / residual / gate / rowvec / bias allow 16-byte accesses
   int out_fp32;  // y is float (attention scores of the unfused head_dim-512 path)
   int tma_store; // epilogue stages 32-column slabs in smem and writes them with TMA (needs vec_ok, 16-bit y)
-  long long* dbg; // optional [grid][8] clock64 timestamps (tuning aid)
+  long long* dbg; // optional [grid][16] clock64 timestamps (tuning aid)
 };
 
 template <int BN>
@@ -83,6 +105,40 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int g,
   c.w0 = tw * p.bw;
   c.n0 = n_blk * BN;
   return c;
+}
+
+// Slow path of the epilogue for shapes the vector path cannot take (kept out of line: it must not bloat the hot loop).
+template <bool GEGLU, bool FP16>
+__device__ __noinline__ void epilogue_scalar(const uint32_t* v, const uint32_t* gv, const ConvGemmParams& p,
+                                             const typename Half16<FP16>::T* bias, const typename Half16<FP16>::T* gate_row,
+                                             const typename Half16<FP16>::T* rv_row, const typename Half16<FP16>::T* res_row,
+                                             typename Half16<FP16>::T* y_row, long long pix, int yc0, int wcol0, int bn,
+                                             int n_limit) {
+  using H = Half16<FP16>;
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    const int n = yc0 + j;
+    if (n >= n_limit) break;
+    float x = __uint_as_float(v[j]);
+    if (GEGLU) {
+      float gg = __uint_as_float(gv[j]);
+      if (bias) {
+        x += H::to_float(bias[wcol0 + j]);
+        gg += H::to_float(bias[wcol0 + bn / 2 + j]);
+      }
+      x *= gelu_erf_fast(gg);
+    } else {
+      if (bias) x += H::to_float(bias[n]);
+      if (p.act != ACT_NONE) x = act_fast(x, p.act);
+      if (gate_row) x *= H::to_float(gate_row[n]);
+      if (rv_row) x += H::to_float(rv_row[n]);
+      if (res_row) x += H::to_float(res_row[n]);
+    }
+    if (p.out_fp32)
+      reinterpret_cast<float*>(p.y)[pix * p.ldy + n] = x;
+    else
+      y_row[n] = H::from_float(x);
+  }
 }
 
 template <int BN, bool GEGLU, bool FP16>
@@ -134,7 +190,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();  // everything above overlapped the previous kernel's tail; no global access before this point
-  long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+  long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
   if (dbg && threadIdx.x == 0) {
     dbg[0] = t_entry;
     dbg[1] = clock64();
@@ -216,6 +272,9 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // Code size matters here: the loops over 32-column chunks stay rolled and the per-element math is branch-light,
+    // so the whole epilogue body stays resident in the instruction cache (a fully unrolled version with inlined
+    // tanhf/erff ran 4x slower than the main loop).
     const int q = warp - 4;
     const int row = q * 32 + lane;
     const int rh = row >> p.bw_shift;
@@ -229,6 +288,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     const bool tma_store = p.tma_store != 0;
     const bool issuer = (warp == 4 && lane == 0);  // issues and tracks the TMA stores
     const int sw = (row >> 1) & 3;                  // SWIZZLE_64B: 16-byte unit index ^= bits [7,9) of the byte offset
+    const int act = p.act;
     uint32_t slab_count = 0;
     int it = 0;
     for (int g = cluster; g < p.total_groups; g += n_clusters, ++it) {
@@ -242,18 +302,15 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
       const long long grp = (valid && (gate != nullptr || rowvec != nullptr)) ? (pix / p.rows_per_group) : 0;
       const typename H::T* gate_row = gate ? gate + grp * p.ld_gate : nullptr;
       const typename H::T* rv_row = rowvec ? rowvec + grp * p.ld_rowvec : nullptr;
-      const typename H::T* res_row = residual ? residual + pix * p.ldr : nullptr;
+      const typename H::T* res_row = (residual && valid) ? residual + pix * p.ldr : nullptr;
       typename H::T* y_row = y + pix * p.ldy;
 
       constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
       const int ycol0 = GEGLU ? (tc.n0 >> 1) : tc.n0;
-      // this row's residual values are fetched into registers now, while the main loop of the tile is still running
-      uint4 res[GEGLU ? 1 : OUT_COLS / 8];
-      const bool res_pre = !GEGLU && res_row != nullptr && valid && p.vec_ok;
-      if (res_pre) {
-#pragma unroll
-        for (int i = 0; i < OUT_COLS / 8; ++i)
-          res[i] = (ycol0 + i * 8 + 8 <= n_limit) ? *reinterpret_cast<const uint4*>(res_row + ycol0 + i * 8) : make_uint4(0, 0, 0, 0);
+      if (res_row) {  // pull this row's residual lines towards L2 while the main loop of the tile is still running
+#pragma unroll 1
+        for (int c = 0; c < OUT_COLS; c += 64)
+          if (ycol0 + c < n_limit) prefetch_l2(res_row + ycol0 + c);
       }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -261,13 +318,25 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
       if (dbg && issuer) dbg[5] = clock64();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
 
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < OUT_COLS / 32; ++c) {
-        if (ycol0 + c * 32 >= n_limit) break;  // warp-uniform
+        const int yc0 = ycol0 + c * 32;
+        if (yc0 >= n_limit) break;  // tile-uniform
         uint32_t v[32];
         tmem_ld32(t_row + c * 32, v);
         uint32_t gv[32];
         if (GEGLU) tmem_ld32(t_row + BN / 2 + c * 32, gv);
+        const bool chunk_vec = p.vec_ok && (yc0 + 32 <= n_limit);
+        // operands of this chunk are requested now and consumed after the TMEM load has landed
+        uint4 rs[4], bs[4];
+        const int bcol = GEGLU ? (tc.n0 + c * 32) : yc0;
+        if (chunk_vec) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            rs[j] = (!GEGLU && res_row) ? *reinterpret_cast<const uint4*>(res_row + yc0 + j * 8) : make_uint4(0, 0, 0, 0);
+            bs[j] = bias ? *reinterpret_cast<const uint4*>(bias + bcol + j * 8) : make_uint4(0, 0, 0, 0);
+          }
+        }
         uint8_t* slab = slabs + (slab_count % Cfg::NSLAB) * Cfg::SLAB_BYTES;
         if (tma_store) {
           // the store that used this slab NSLAB slabs ago must have finished reading it
@@ -275,37 +344,30 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
           named_bar_sync(1, 128);
         }
         tmem_wait_ld();
+        if (dbg && issuer && it == 0 && c < 2) dbg[8 + c * 4] = clock64();
+        if (chunk_vec) {
 #pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          const int yc = ycol0 + c * 32 + j8 * 8;  // y column of f[0]
-          float f[8];
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const int yc = yc0 + j8 * 8;
+            float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
-          const bool in_range = yc < n_limit;
-          const bool full8 = (yc + 8 <= n_limit) && p.vec_ok;
-          if (in_range) {
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
+            {
+              float2 t0 = H::unpack(bs[j8].x), t1 = H::unpack(bs[j8].y), t2 = H::unpack(bs[j8].z), t3 = H::unpack(bs[j8].w);
+              f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
+              f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
+            }
             if (GEGLU) {
               // packed rows: [n0, n0+BN/2) value, [n0+BN/2, n0+BN) gate
-              const int bcol = tc.n0 + c * 32 + j8 * 8;
+              uint4 bg = bias ? *reinterpret_cast<const uint4*>(bias + bcol + BN / 2 + j8 * 8) : make_uint4(0, 0, 0, 0);
+              float2 t0 = H::unpack(bg.x), t1 = H::unpack(bg.y), t2 = H::unpack(bg.z), t3 = H::unpack(bg.w);
+              const float gb[8] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float a = f[j], gg = __uint_as_float(gv[j8 * 8 + j]);
-                if (bias) {
-                  a += H::to_float(bias[bcol + j]);
-                  gg += H::to_float(bias[bcol + BN / 2 + j]);
-                }
-                f[j] = a * gelu_erf_f(gg);
-              }
-            } else if (full8) {
-              if (bias) {
-                uint4 b = *reinterpret_cast<const uint4*>(bias + yc);
-                float2 t0 = H::unpack(b.x), t1 = H::unpack(b.y), t2 = H::unpack(b.z), t3 = H::unpack(b.w);
-                f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
-                f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
-              }
-              if (p.act != ACT_NONE) {
+              for (int j = 0; j < 8; ++j) f[j] *= gelu_erf_fast(__uint_as_float(gv[j8 * 8 + j]) + gb[j]);
+            } else {
+              if (act != ACT_NONE) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
+                for (int j = 0; j < 8; ++j) f[j] = act_fast(f[j], act);
               }
               if (gate_row) {
                 uint4 b = *reinterpret_cast<const uint4*>(gate_row + yc);
@@ -319,67 +381,48 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                 f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
                 f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
               }
-              if (res_pre) {
-                const uint4 b = res[GEGLU ? 0 : c * 4 + j8];
-                float2 t0 = H::unpack(b.x), t1 = H::unpack(b.y), t2 = H::unpack(b.z), t3 = H::unpack(b.w);
+              {
+                float2 t0 = H::unpack(rs[j8].x), t1 = H::unpack(rs[j8].y), t2 = H::unpack(rs[j8].z), t3 = H::unpack(rs[j8].w);
                 f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
                 f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int n = yc + j;
-                if (n < n_limit) {
-                  float x = f[j];
-                  if (bias) x += H::to_float(bias[n]);
-                  x = apply_act(x, p.act);
-                  if (gate_row) x *= H::to_float(gate_row[n]);
-                  if (rv_row) x += H::to_float(rv_row[n]);
-                  if (res_row && valid) x += H::to_float(res_row[n]);
-                  f[j] = x;
-                }
+            }
+            if (p.out_fp32) {
+              if (valid) {
+                float* yf = reinterpret_cast<float*>(p.y) + pix * p.ldy + yc;
+                *reinterpret_cast<float4*>(yf) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(yf + 4) = make_float4(f[4], f[5], f[6], f[7]);
               }
-            }
-          }
-          if (tma_store) {
-            // columns past n_limit are clipped by the TMA store; whatever lands there in smem is never written
-            uint4 o;
-            o.x = H::pack(f[0], f[1]);
-            o.y = H::pack(f[2], f[3]);
-            o.z = H::pack(f[4], f[5]);
-            o.w = H::pack(f[6], f[7]);
-            *reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4)) = o;
-          } else if (valid && in_range && p.out_fp32) {
-            float* yf = reinterpret_cast<float*>(p.y) + pix * p.ldy + yc;
-            if (full8) {
-              *reinterpret_cast<float4*>(yf) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(yf + 4) = make_float4(f[4], f[5], f[6], f[7]);
             } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (yc + j < n_limit) yf[j] = f[j];
-            }
-          } else if (valid && in_range) {
-            if (full8) {
               uint4 o;
               o.x = H::pack(f[0], f[1]);
               o.y = H::pack(f[2], f[3]);
               o.z = H::pack(f[4], f[5]);
               o.w = H::pack(f[6], f[7]);
-              *reinterpret_cast<uint4*>(y_row + yc) = o;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (yc + j < n_limit) y_row[yc + j] = H::from_float(f[j]);
+              if (tma_store)
+                *reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4)) = o;
+              else if (valid)
+                *reinterpret_cast<uint4*>(y_row + yc) = o;
             }
           }
+        } else if (valid) {
+          // rare shapes (N not a multiple of 32 / unaligned buffers): scalar, element by element
+          uint32_t tv[32], tg[32];  // stack copies: only this cold branch touches local memory
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            tv[j] = v[j];
+            tg[j] = GEGLU ? gv[j] : 0u;
+          }
+          epilogue_scalar<GEGLU, FP16>(tv, tg, p, bias, gate_row, rv_row, res_row, y_row, pix, yc0, tc.n0 + c * 32, BN, n_limit);
         }
+        if (dbg && issuer && it == 0 && c < 2) dbg[9 + c * 4] = clock64();
         if (tma_store) {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
           named_bar_sync(1, 128);
           if (issuer) {
-            if (real_tile) tma_store_4d(&p.y_map, slab, ycol0 + c * 32, tc.w0, tc.h0, tc.img);
+            if (real_tile) tma_store_4d(&p.y_map, slab, yc0, tc.w0, tc.h0, tc.img);
             bulk_commit_group();
+            if (dbg && it == 0 && c < 2) dbg[11 + c * 4] = clock64();
           }
           ++slab_count;
         }
@@ -690,7 +733,8 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   prm.out_fp32 = a->out_fp32 ? 1 : 0;
   prm.dbg = static_cast<long long*>(a->debug_timestamps);
   const int n_out = a->geglu ? a->N / 2 : a->N;
-  prm.tma_store = (vec && !a->out_fp32 && n_out % 8 == 0) ? 1 : 0;
+  static const bool no_tma_store = getenv("B200_NO_TMA_STORE") && atoi(getenv("B200_NO_TMA_STORE")) != 0;  // tuning knob
+  prm.tma_store = (vec && !a->out_fp32 && n_out % 32 == 0 && !no_tma_store) ? 1 : 0;
   if (prm.tma_store) {
     const uint64_t ldy = static_cast<uint64_t>(a->ldy);
     const uint64_t dims[4] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),

@@ -15,7 +15,10 @@ w = packing.pack_linear_weight((torch.randn(N, K, generator=g, device="cuda") * 
 b = torch.randn(N, generator=g, device="cuda").bfloat16()
 r = torch.randn(M, N, generator=g, device="cuda").bfloat16()
 out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-dbg = torch.zeros(148, 8, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(148, 16, dtype=torch.int64, device="cuda")
+use_res = os.environ.get('NORES') is None
+if not use_res:
+    r = None
 for _ in range(3):
     ops.linear(x, w, N, bias=b, residual=r, out=out, tile_n=bn, debug_timestamps=dbg)
 torch.cuda.synchronize()
@@ -30,7 +33,9 @@ for rep in range(2):
     names = ["entry", "prologue done", "first TMA issued", "first data landed", "last MMA committed", "accumulator ready (epi)",
              "epilogue stores issued", "exit"]
     print(f"rep {rep}: {d.shape[0]} CTAs; medians of (t_i - t_entry) in cycles:")
-    for i in range(1, 8):
+    names = names + ["c0 tmem loaded", "c0 math+sts done", "c0 fence done", "c0 store issued", "c1 tmem loaded", "c1 math+sts done",
+                     "c1 fence done", "c1 store issued"]
+    for i in range(1, 16):
         v = (d[:, i] - d[:, 0]).float()
         v = v[d[:, i] > 0]
         if len(v):
