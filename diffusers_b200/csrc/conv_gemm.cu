@@ -189,7 +189,13 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   if (cm > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive / multicast write
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  pdl_wait();  // everything above overlapped the previous kernel's tail; no global access before this point
+  constexpr int PF = 8;  // weight chunks requested into L2 ahead of the shared-memory pipeline
+  if (warp == 0 && lane == 0 && cluster < p.total_groups) {
+    // weights do not depend on the previous kernel: start pulling the first tile's chunks from HBM into L2 now
+    const int n0 = (cluster / p.m_groups) * BN + rank * (BN / cm);
+    for (int kc = 0; kc < PF && kc < p.k_chunks; ++kc) tma_prefetch_l2_2d(&p.w_map, kc * 64, n0);
+  }
+  pdl_wait();  // everything above overlapped the previous kernel's tail; no activation access before this point
   long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
   if (dbg && threadIdx.x == 0) {
     dbg[0] = t_entry;
@@ -212,6 +218,15 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
           for (int s = 0; s < p.nsrc; ++s) {
             const CUtensorMap* am = &p.a_map[s * 4 + mp];
             for (int cc = 0; cc < p.chunks[s]; ++cc) {
+              {  // keep the weight stream PF chunks ahead in L2 (wraps into the next tile of this CTA)
+                int pk = kc + PF, pg = g;
+                if (pk >= p.k_chunks) {
+                  pk -= p.k_chunks;
+                  pg += n_clusters;
+                }
+                if (pg < p.total_groups && pk < p.k_chunks)
+                  tma_prefetch_l2_2d(&p.w_map, pk * 64, (pg / p.m_groups) * BN + rank * b_rows);
+              }
               mbar_wait(&empty_bar[stage], phase ^ 1u);  // every CTA of the cluster has drained this stage
               mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -313,6 +328,20 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
           if (ycol0 + c < n_limit) prefetch_l2(res_row + ycol0 + c);
       }
 
+      // bias / residual of a chunk are requested one chunk ahead (chunk 0: before the accumulator is even ready)
+      uint4 rs[4], bs[4];
+      auto request = [&](int c) {
+        const int yc0 = ycol0 + c * 32;
+        const bool ok = p.vec_ok && c < OUT_COLS / 32 && (yc0 + 32 <= n_limit);
+        const int bcol = GEGLU ? (tc.n0 + c * 32) : yc0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          rs[j] = (ok && !GEGLU && res_row) ? *reinterpret_cast<const uint4*>(res_row + yc0 + j * 8) : make_uint4(0, 0, 0, 0);
+          bs[j] = (ok && bias) ? *reinterpret_cast<const uint4*>(bias + bcol + j * 8) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      request(0);
+
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (dbg && issuer) dbg[5] = clock64();
@@ -327,16 +356,14 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
         uint32_t gv[32];
         if (GEGLU) tmem_ld32(t_row + BN / 2 + c * 32, gv);
         const bool chunk_vec = p.vec_ok && (yc0 + 32 <= n_limit);
-        // operands of this chunk are requested now and consumed after the TMEM load has landed
-        uint4 rs[4], bs[4];
         const int bcol = GEGLU ? (tc.n0 + c * 32) : yc0;
-        if (chunk_vec) {
+        uint4 rc[4], bc[4];  // this chunk's operands (requested during the previous chunk)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            rs[j] = (!GEGLU && res_row) ? *reinterpret_cast<const uint4*>(res_row + yc0 + j * 8) : make_uint4(0, 0, 0, 0);
-            bs[j] = bias ? *reinterpret_cast<const uint4*>(bias + bcol + j * 8) : make_uint4(0, 0, 0, 0);
-          }
+        for (int j = 0; j < 4; ++j) {
+          rc[j] = rs[j];
+          bc[j] = bs[j];
         }
+        request(c + 1);
         uint8_t* slab = slabs + (slab_count % Cfg::NSLAB) * Cfg::SLAB_BYTES;
         if (tma_store) {
           // the store that used this slab NSLAB slabs ago must have finished reading it
@@ -353,7 +380,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
             {
-              float2 t0 = H::unpack(bs[j8].x), t1 = H::unpack(bs[j8].y), t2 = H::unpack(bs[j8].z), t3 = H::unpack(bs[j8].w);
+              float2 t0 = H::unpack(bc[j8].x), t1 = H::unpack(bc[j8].y), t2 = H::unpack(bc[j8].z), t3 = H::unpack(bc[j8].w);
               f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
               f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
             }
@@ -382,7 +409,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                 f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
               }
               {
-                float2 t0 = H::unpack(rs[j8].x), t1 = H::unpack(rs[j8].y), t2 = H::unpack(rs[j8].z), t3 = H::unpack(rs[j8].w);
+                float2 t0 = H::unpack(rc[j8].x), t1 = H::unpack(rc[j8].y), t2 = H::unpack(rc[j8].z), t3 = H::unpack(rc[j8].w);
                 f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
                 f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
               }
@@ -551,8 +578,8 @@ static void pick_config(long long m_tiles, int N, int k_chunks, int geglu, int f
     if (geglu && !(bn == 256 || bn == 128 || bn == 64)) continue;
     if (geglu && N % bn != 0) continue;
     const long long n_tiles = (N + bn - 1) / bn;
-    for (int cm : {1, 2, 4}) {
-      if (force_cm && cm != force_cm) continue;
+    for (int cm : {1, 2}) {
+      if (force_cm ? cm != force_cm : cm != 1) continue;  // measured: multicast clusters bring nothing here (not L2-bound)
       if ((bn / cm) % 8 != 0) continue;
       if (cm > 1 && m_tiles < cm) continue;
       const long long groups = n_tiles * ((m_tiles + cm - 1) / cm);
@@ -611,7 +638,7 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   if (a->stride == 2) B200_CHECK_ARG(a->H % 2 == 0 && a->W % 2 == 0, "conv_gemm: stride 2 needs even H, W");
   if (a->geglu) B200_CHECK_ARG(a->N % 64 == 0, "conv_gemm: geglu needs N %% 64 == 0 (N=%d)", a->N);
   if (a->gate || a->rowvec) B200_CHECK_ARG(a->rows_per_group > 0, "conv_gemm: rows_per_group must be > 0");
-  B200_CHECK_ARG(a->cluster_m == 0 || a->cluster_m == 1 || a->cluster_m == 2 || a->cluster_m == 4, "conv_gemm: cluster_m %d", a->cluster_m);
+  B200_CHECK_ARG(a->cluster_m == 0 || a->cluster_m == 1 || a->cluster_m == 2, "conv_gemm: cluster_m %d (0, 1 or 2)", a->cluster_m);
   B200_CHECK_ARG(a->tile_n == 0 || a->tile_n == 32 || a->tile_n == 64 || a->tile_n == 96 || a->tile_n == 128 ||
                      a->tile_n == 160 || a->tile_n == 192 || a->tile_n == 256,
                  "conv_gemm: tile_n %d not in {32,64,96,128,160,192,256}", a->tile_n);

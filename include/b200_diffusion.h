@@ -66,7 +66,7 @@ int b200_num_sms(void);
  *   conv + temb[:, :, None, None]              models/resnet.py:343-349 (rowvec)
  *   (x + h) / output_scale_factor              models/resnet.py:375 (residual)
  *
- * Execution: persistent clusters of 1/2/4 CTAs along M share each weight tile by TMA multicast; 32-column
+ * Execution: persistent CTAs (optionally clusters of 2 along M sharing each weight tile by TMA multicast); 32-column
  * output slabs are staged in shared memory and written with TMA stores (tile width / cluster size are picked by
  * a cycle model of MMA issue vs. the per-SM L2 port).
  * Epilogue order (fp32):  v = acc + bias[n];  v = act(v);  v *= gate[g, n];  v += rowvec[g, n];
@@ -98,7 +98,7 @@ typedef struct {
   int32_t dtype;         /* B200_DTYPE_*                                                        */
   int32_t tile_n;        /* 0 = auto, else force BN in {32, 64, 96, 128, 160, 192, 256}         */
   int32_t out_fp32;      /* 1: y is float32 [.., ldy] (attention scores of the head_dim-512 path) */
-  int32_t cluster_m;     /* 0 = auto, else force the cluster size along M in {1, 2, 4} (tuning / tests) */
+  int32_t cluster_m;     /* 0 = auto, else force the cluster size along M in {1, 2} (tuning / tests) */
   void* debug_timestamps; /* NULL, or int64 [grid][8] device buffer receiving per-CTA clock64 marks (tuning) */
 } b200_conv_gemm_args;
 

@@ -91,7 +91,7 @@ def test_attention_processor_plugin_matches_reference_processor_math():
         b200_attention_backend(q, q, q, is_causal=True)
 
 
-@pytest.mark.parametrize("cm", [1, 2, 4])
+@pytest.mark.parametrize("cm", [1, 2])
 def test_conv_gemm_cluster_multicast_sizes(cm):
     """The cluster size (CTAs sharing one multicast weight tile) is normally picked by the cost model; force each
     value through the B200_FORCE_CM test knob in a fresh process (the knob is read once per process)."""
