@@ -189,13 +189,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   if (cm > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive / multicast write
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  constexpr int PF = 8;  // weight chunks requested into L2 ahead of the shared-memory pipeline
-  if (warp == 0 && lane == 0 && cluster < p.total_groups) {
-    // weights do not depend on the previous kernel: start pulling the first tile's chunks from HBM into L2 now
-    const int n0 = (cluster / p.m_groups) * BN + rank * (BN / cm);
-    for (int kc = 0; kc < PF && kc < p.k_chunks; ++kc) tma_prefetch_l2_2d(&p.w_map, kc * 64, n0);
-  }
-  pdl_wait();  // everything above overlapped the previous kernel's tail; no activation access before this point
+  pdl_wait();  // everything above overlapped the previous kernel's tail; no global access before this point
   long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
   if (dbg && threadIdx.x == 0) {
     dbg[0] = t_entry;
@@ -218,15 +212,6 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
           for (int s = 0; s < p.nsrc; ++s) {
             const CUtensorMap* am = &p.a_map[s * 4 + mp];
             for (int cc = 0; cc < p.chunks[s]; ++cc) {
-              {  // keep the weight stream PF chunks ahead in L2 (wraps into the next tile of this CTA)
-                int pk = kc + PF, pg = g;
-                if (pk >= p.k_chunks) {
-                  pk -= p.k_chunks;
-                  pg += n_clusters;
-                }
-                if (pg < p.total_groups && pk < p.k_chunks)
-                  tma_prefetch_l2_2d(&p.w_map, pk * 64, (pg / p.m_groups) * BN + rank * b_rows);
-              }
               mbar_wait(&empty_bar[stage], phase ^ 1u);  // every CTA of the cluster has drained this stage
               mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
