@@ -7,7 +7,7 @@
 //   warp 2        TMEM allocator
 //   warps 4..7    softmax warpgroup for tile 0 (thread = row: no shuffles), 8..11 for tile 1
 //
-//   TMEM columns: S_i (128 fp32) at i*128, P_i (bf16, 64 columns) aliases the front of S_i,
+//   TMEM columns: S_i (128 fp32) at i*128, P_i (16-bit, 64 columns) aliases the upper half of S_i,
 //   O_i (HD fp32) at NQ*128 + i*HD.  Online softmax with lazy rescaling: the running max only
 //   moves (and O is only rescaled) when it grew by more than 2^8, which keeps exp2 arguments
 //   bounded and is exact up to rounding.
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
       auto issue_pv = [&](int i, int vstage, bool accumulate) {
         // O_i[:, slab] += P_i V[:, slab] : K-dim = 128 kv rows, 16 per instruction (2 x 8-row groups = 2048 B)
         const uint32_t va = smem_u32(s_v + vstage * Cfg::TILE_BYTES);
-        const uint32_t p_t = tmem_base + i * 128;
+        const uint32_t p_t = tmem_base + i * 128 + 64;  // P lives in the upper half of the S row
         const uint32_t o_t = tmem_base + NQ * 128 + i * HD;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -237,21 +237,36 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
       const int kv_left = p.sk - j * 128;  // valid columns in this block
       const bool partial = kv_left < 128;
 
-      // ---- pass 1: block row max (scaled log2 domain)
+      // Columns 64..127 of the score row (H1) are read from TMEM once and stay in registers for both the max and the
+      // exp pass; columns 0..63 (H0) are read twice.  3 TMEM waits per block instead of 8.  P (16-bit, 64 columns)
+      // is written over the UPPER half of the S row: H1 is consumed from registers first, so nothing live is clobbered.
+      uint32_t a1[32], b1[32], t0[32];
+      tmem_ld32(s_t + 64, a1);
+      tmem_ld32(s_t + 96, b1);
+      tmem_ld32(s_t + 0, t0);
+      tmem_wait_ld();
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(s_t + c * 32, v);
-        tmem_wait_ld();
-        if (!partial) {
+      if (!partial) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
-        } else {
+        for (int k = 0; k < 32; ++k)
+          mx = fmaxf(mx, fmaxf(__uint_as_float(t0[k]), fmaxf(__uint_as_float(a1[k]), __uint_as_float(b1[k]))));
+      } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (c * 32 + k < kv_left) mx = fmaxf(mx, __uint_as_float(v[k]));
+        for (int k = 0; k < 32; ++k) {
+          if (k < kv_left) mx = fmaxf(mx, __uint_as_float(t0[k]));
+          if (64 + k < kv_left) mx = fmaxf(mx, __uint_as_float(a1[k]));
+          if (96 + k < kv_left) mx = fmaxf(mx, __uint_as_float(b1[k]));
         }
+      }
+      tmem_ld32(s_t + 32, t0);
+      tmem_wait_ld();
+      if (!partial) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(t0[k]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (32 + k < kv_left) mx = fmaxf(mx, __uint_as_float(t0[k]));
       }
       mx *= sc;  // sc > 0
       if (j == 0) {
@@ -266,36 +281,45 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
           }
 #pragma unroll 1
           for (int c = 0; c < HD / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(o_t + c * 32, v);
+            tmem_ld32(o_t + c * 32, t0);
             tmem_wait_ld();
 #pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) * alpha);
-            tmem_st32(o_t + c * 32, v);
+            for (int k = 0; k < 32; ++k) t0[k] = __float_as_uint(__uint_as_float(t0[k]) * alpha);
+            tmem_st32(o_t + c * 32, t0);
           }
           tmem_wait_st();
         }
       }
 
-      // ---- pass 2: P = exp2(S*sc - m) -> 16-bit into TMEM (front of the S region), row sum
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(s_t + c * 32, v);
-        tmem_wait_ld();
-        uint32_t pk[16];
+      // exp2(S*sc - m): three of four on MUFU, one on the FMA pipes (ex2_poly); pairs packed to 16 bit
+      auto exps32 = [&](const uint32_t (&src)[32], uint32_t* dst, int col0) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * k]), sc, -m));
-          float p1 = ex2_poly(fmaf(__uint_as_float(v[2 * k + 1]), sc, -m));
+          float p0 = ex2_approx(fmaf(__uint_as_float(src[2 * k]), sc, -m));
+          float p1 = (k & 1) ? ex2_poly(fmaf(__uint_as_float(src[2 * k + 1]), sc, -m))
+                             : ex2_approx(fmaf(__uint_as_float(src[2 * k + 1]), sc, -m));
           if (partial) {
-            if (c * 32 + 2 * k >= kv_left) p0 = 0.f;
-            if (c * 32 + 2 * k + 1 >= kv_left) p1 = 0.f;
+            if (col0 + 2 * k >= kv_left) p0 = 0.f;
+            if (col0 + 2 * k + 1 >= kv_left) p1 = 0.f;
           }
           l += p0 + p1;
-          pk[k] = H::pack(p0, p1);
+          dst[k] = H::pack(p0, p1);
         }
-        tmem_st16(s_t + c * 16, pk);
+      };
+      {
+        uint32_t pk[32];
+        exps32(a1, pk, 64);
+        exps32(b1, pk + 16, 96);
+        tmem_st32(s_t + 64 + 32, pk);  // P columns of kv 64..127
+      }
+      tmem_ld32(s_t + 0, a1);
+      tmem_ld32(s_t + 32, b1);
+      tmem_wait_ld();
+      {
+        uint32_t pk[32];
+        exps32(a1, pk, 0);
+        exps32(b1, pk + 16, 32);
+        tmem_st32(s_t + 64, pk);  // P columns of kv 0..63
       }
       tmem_wait_st();
       tc_fence_before();

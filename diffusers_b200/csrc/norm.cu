@@ -137,23 +137,29 @@ __global__ void group_norm_stats_kernel(const GroupNormParams p) {
     const int total = p.chunks * p.groups * 3;
     const volatile float* pp = p.partial + static_cast<size_t>(n) * p.chunks * p.groups * 3;
     const int cap = p.P * p.C * 2;  // floats available in s_mm
-    if (total <= cap) {
-      for (int i = t; i < total; i += blockDim.x) s_part[i] = pp[i];
-    }
-    __syncthreads();
-    if (t < p.groups) {
-      float na = 0.f, ma = 0.f, M2a = 0.f;
-      if (total <= cap) {
-        for (int ch = 0; ch < p.chunks; ++ch) {
-          const float* q = s_part + (ch * p.groups + t) * 3;
-          chan_combine(na, ma, M2a, q[0], q[1], q[2]);
-        }
-      } else {
-        for (int ch = 0; ch < p.chunks; ++ch) {
-          const volatile float* q = pp + (static_cast<size_t>(ch) * p.groups + t) * 3;
-          chan_combine(na, ma, M2a, q[0], q[1], q[2]);
+    const int per_round = max(1, cap / (p.groups * 3));  // chunks staged per round
+    float na = 0.f, ma = 0.f, M2a = 0.f;
+    for (int c0 = 0; c0 < p.chunks; c0 += per_round) {
+      const int nc = min(per_round, p.chunks - c0);
+      const int cnt_f = nc * p.groups * 3;
+      __syncthreads();
+      if (cnt_f <= cap) {
+        for (int i = t; i < cnt_f; i += blockDim.x) s_part[i] = pp[static_cast<size_t>(c0) * p.groups * 3 + i];  // coalesced
+      }
+      __syncthreads();
+      if (t < p.groups) {
+        for (int ch = 0; ch < nc; ++ch) {
+          if (cnt_f <= cap) {
+            const float* q = s_part + (ch * p.groups + t) * 3;
+            chan_combine(na, ma, M2a, q[0], q[1], q[2]);
+          } else {  // shared buffer smaller than one chunk row (tiny blocks): read global directly
+            const volatile float* q = pp + (static_cast<size_t>(c0 + ch) * p.groups + t) * 3;
+            chan_combine(na, ma, M2a, q[0], q[1], q[2]);
+          }
         }
       }
+    }
+    if (t < p.groups) {
       float var = M2a / na;
       p.stats[(static_cast<size_t>(n) * p.groups + t) * 2 + 0] = ma;
       p.stats[(static_cast<size_t>(n) * p.groups + t) * 2 + 1] = rsqrtf(var + p.eps);
@@ -231,9 +237,9 @@ __global__ void __launch_bounds__(256) group_norm_apply_kernel(const GroupNormPa
 }
 
 static void gn_plan(int batch, int hw, int C, int* chunks, int* ppc) {
-  // ~4 CTAs per SM over the whole batch, at least 8 pixels per chunk, at most 256 chunks per image (workspace)
+  // ~2 CTAs per SM over the whole batch, at least 8 pixels per chunk, at most 256 chunks per image (workspace)
   long long total = static_cast<long long>(batch) * hw;
-  int pp = static_cast<int>((total + 4LL * num_sms() - 1) / (4LL * num_sms()));
+  int pp = static_cast<int>((total + 2LL * num_sms() - 1) / (2LL * num_sms()));
   if (pp < 8) pp = 8;
   if (pp * 256 < hw) pp = (hw + 255) / 256;
   if (pp > hw) pp = hw;
