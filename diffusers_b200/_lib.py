@@ -28,7 +28,7 @@ class ConvGemmArgs(C.Structure):
         ("residual", C.c_void_p), ("ldr", C.c_int32),
         ("y", C.c_void_p), ("ldy", C.c_int32),
         ("dtype", C.c_int32), ("tile_n", C.c_int32), ("out_fp32", C.c_int32), ("cluster_m", C.c_int32),
-        ("debug_timestamps", C.c_void_p),
+        ("debug_timestamps", C.c_void_p), ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
     ]
 
 

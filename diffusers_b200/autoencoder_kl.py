@@ -145,6 +145,7 @@ class AutoencoderKL(torch.nn.Module):
                                                               scale=C ** -0.5)
         return ops.linear(o, self.W(a["ow"]), C, bias=self.W(a["ob"]), residual=x)
 
+    @ops.prefetching_forward
     def _decode_nhwc(self, z_nhwc, B, H, W):
         x = z_nhwc
         if self.pq is not None:

@@ -125,32 +125,36 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
   pdl_wait();
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp, one elected lane issues: see elect_one) =====================
+    if (elect_one()) {
       for (int i = 0; i < NQ; ++i) {
         mbar_expect_tx(&q_full[i], Cfg::TILE_BYTES);
         for (int s = 0; s < SLABS; ++s)
           tma_load_4d(s_q + i * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &p.q_map, &q_full[i], s * 64, q_row0 + i * 128,
                       head, b);
       }
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0;
-      for (int j = 0; j < n_blocks; ++j) {
-        mbar_wait(&k_empty[ks], kph ^ 1u);
+    }
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0;
+    for (int j = 0; j < n_blocks; ++j) {
+      mbar_wait(&k_empty[ks], kph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(&k_full[ks], Cfg::TILE_BYTES);
         for (int s = 0; s < SLABS; ++s)
           tma_load_4d(s_k + ks * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &p.k_map, &k_full[ks], s * 64, j * 128, head, b);
-        if (++ks == KS) { ks = 0; kph ^= 1u; }
-        mbar_wait(&v_empty[vs], vph ^ 1u);
+      }
+      if (++ks == KS) { ks = 0; kph ^= 1u; }
+      mbar_wait(&v_empty[vs], vph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(&v_full[vs], Cfg::TILE_BYTES);
         for (int s = 0; s < SLABS; ++s)
           tma_load_4d(s_v + vs * Cfg::TILE_BYTES + s * Cfg::SLAB_BYTES, &p.v_map, &v_full[vs], s * 64, j * 128, head, b);
-        if (++vs == VS) { vs = 0; vph ^= 1u; }
       }
+      if (++vs == VS) { vs = 0; vph ^= 1u; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc_qk = make_idesc(128, 128, FP16, false, false);
       constexpr uint32_t idesc_pv = make_idesc(128, 64, FP16, false, true);
       int ks = 0, vs = 0;
@@ -189,10 +193,12 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
       for (int i = 0; i < NQ; ++i) {
         mbar_wait(&q_full[i], 0);
         tc_fence_after();
-        issue_s(i, 0);
-        umma_commit(&s_full[i]);
+        if (elect_one()) {
+          issue_s(i, 0);
+          umma_commit(&s_full[i]);
+        }
       }
-      umma_commit(&k_empty[0]);
+      if (elect_one()) umma_commit(&k_empty[0]);
       ks = (KS > 1) ? 1 : 0;
       if (KS == 1) kph ^= 1u;
 
@@ -202,15 +208,19 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
         for (int i = 0; i < NQ; ++i) {
           mbar_wait(&p_full[i], j & 1);
           tc_fence_after();
-          issue_pv(i, vs, j > 0);
-          if (i == NQ - 1) umma_commit(&v_empty[vs]);
+          if (elect_one()) {
+            issue_pv(i, vs, j > 0);
+            if (i == NQ - 1) umma_commit(&v_empty[vs]);
+          }
           if (has_next) {
             if (i == 0) mbar_wait(&k_full[ks], kph);
             tc_fence_after();
-            issue_s(i, ks);
-            umma_commit(&s_full[i]);
-            if (i == NQ - 1) umma_commit(&k_empty[ks]);
-          } else {
+            if (elect_one()) {
+              issue_s(i, ks);
+              umma_commit(&s_full[i]);
+              if (i == NQ - 1) umma_commit(&k_empty[ks]);
+            }
+          } else if (elect_one()) {
             umma_commit(&o_full[i]);
           }
         }
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
     float m = 0.f, l = 0.f;
 
     for (int j = 0; j < n_blocks; ++j) {
-      mbar_wait(&s_full[i], j & 1);
+      mbar_wait_warp(&s_full[i], j & 1);
       tc_fence_after();
       const int kv_left = p.sk - j * 128;  // valid columns in this block
       const bool partial = kv_left < 128;
@@ -327,7 +337,7 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
     }
 
     // ---- epilogue: O / l -> global
-    mbar_wait(&o_full[i], 0);
+    mbar_wait_warp(&o_full[i], 0);
     tc_fence_after();
     const int qrow = q_row0 + i * 128 + row;
     const bool valid = qrow < p.sq;

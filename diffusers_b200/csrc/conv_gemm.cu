@@ -45,12 +45,13 @@ __device__ __forceinline__ float act_fast(float x, int act) {
 
 struct ConvGemmParams {
   CUtensorMap a_map[8];  // [src][parity]; stride-1 convs only use parity 0
-  CUtensorMap w_map;     // box {64, BN / cm}: every CTA of a cluster loads one slice and multicasts it
+  CUtensorMap w_map;     // box {64, BN / cm}: a CTA of a pair stages its half of the weight tile
   CUtensorMap y_map;     // output, box {32, bw, bh, 1}, SWIZZLE_64B (TMA-store epilogue)
+  CUtensorMap r_map;     // residual, same box: TMA-loaded into the output slab ahead of the epilogue (tma_res)
   int batch, Ho, Wo;
   int bw, bh, bw_shift;
   int tiles_w, tiles_h, m_tiles, n_tiles;
-  int cm;                // cluster size along M (1, 2 or 4)
+  int cm;                // 1, or 2 = CTA pair (cta_group::2 MMA over two consecutive m tiles)
   int m_groups;          // ceil(m_tiles / cm)
   int total_groups;      // n_tiles * m_groups
   int N;  // rows of w
@@ -67,23 +68,28 @@ struct ConvGemmParams {
   int vec_ok;    // y / residual / gate / rowvec / bias allow 16-byte accesses
   int out_fp32;  // y is float (attention scores of the unfused head_dim-512 path)
   int tma_store; // epilogue stages 32-column slabs in smem and writes them with TMA (needs vec_ok, 16-bit y)
+  int tma_res;   // residual tiles are staged by the loader warp (needs tma_store, 16-bit residual, no GEGLU)
+  const uint8_t* pf_ptr;  // next launch's weights: pulled into L2 while this launch runs (nullptr = none)
+  long long pf_bytes;
+  int dbg_mode;  // tuning: 1 = producer stops loading after the first pipeline round, 2 = MMA thread issues no MMAs
   long long* dbg; // optional [grid][16] clock64 timestamps (tuning aid)
 };
 
-template <int BN>
+template <int BN, bool PAIR>
 struct ConvGemmCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;  // a CTA of a pair holds half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SLAB_BYTES = 128 * 32 * 2;  // one 32-column output slab (64 B rows)
   static constexpr int NSLAB = 4;
-  static constexpr int STAGES = (BN >= 192) ? 4 : (BN >= 160 ? 5 : (BN >= 96 ? 6 : 8));
+  static constexpr int RAW_STAGES = (232448 - NSLAB * SLAB_BYTES - 1024 - 256) / STAGE_BYTES;
+  static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
   // accumulator buffers sit at power-of-two column offsets
   static constexpr int ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NSLAB * SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+  static_assert(SMEM_BYTES <= 232448 && STAGES >= 3, "shared memory budget");
 };
 
 struct TileCoord {
@@ -141,9 +147,9 @@ __device__ __noinline__ void epilogue_scalar(const uint32_t* v, const uint32_t* 
   }
 }
 
-template <int BN, bool GEGLU, bool FP16>
-__global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BN>;
+template <int BN, bool GEGLU, bool FP16, bool PAIR>
+__global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using Cfg = ConvGemmCfg<BN, PAIR>;
   using H = Half16<FP16>;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -154,7 +160,10 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* rfull_bar = tempty_bar + 2;          // residual slab landed (loader warp -> epilogue)
+  uint64_t* sfree_bar = rfull_bar + Cfg::NSLAB;  // the TMA store that read the slab has drained it (epilogue -> loader)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfree_bar + Cfg::NSLAB);
+  static_assert((2 * STAGES + 4 + 2 * Cfg::NSLAB) * 8 + 4 <= 256, "barrier area");
 
   const long long t_entry = clock64();
   pdl_trigger();
@@ -164,25 +173,34 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   const int rank = cm > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int cluster = cm > 1 ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
   const int n_clusters = cm > 1 ? static_cast<int>(num_clusters_x()) : static_cast<int>(gridDim.x);
-  const uint16_t cmask = static_cast<uint16_t>((1u << cm) - 1u);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nsrc; ++s) prefetch_tensormap(&p.a_map[s * 4]);
     prefetch_tensormap(&p.w_map);
     if (p.tma_store) prefetch_tensormap(&p.y_map);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], cm);  // one MMA-completion arrive from every CTA of the cluster
+      mbar_init(&full_bar[i], PAIR ? 2 : 1);  // pair: one expect_tx arrive from each CTA's producer (leader's copy is used)
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], PAIR ? 16 : 8);  // 8 epilogue warps; pair: the leader waits for those of both CTAs
     }
+    for (int i = 0; i < Cfg::NSLAB; ++i) {
+      mbar_init(&rfull_bar[i], 1);
+      mbar_init(&sfree_bar[i], 1);
+    }
+    if (p.tma_res) prefetch_tensormap(&p.r_map);
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2(tmem_ptr, Cfg::TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -196,46 +214,58 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     dbg[1] = clock64();
   }
 
+  const int dbg_mode = p.dbg_mode;
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int b_rows = BN / cm;  // rows of the weight tile this CTA fetches (and multicasts)
-      for (int g = cluster; g < p.total_groups; g += n_clusters) {
-        TileCoord tc = decode_tile(p, g, rank, BN);
-        int kc = 0;
-        for (int tap = 0; tap < p.num_taps; ++tap) {
-          const int mp = p.tap_map[tap];
-          const int cw = tc.w0 + p.tap_dw[tap];
-          const int ch = tc.h0 + p.tap_dh[tap];
-          for (int s = 0; s < p.nsrc; ++s) {
-            const CUtensorMap* am = &p.a_map[s * 4 + mp];
-            for (int cc = 0; cc < p.chunks[s]; ++cc) {
-              mbar_wait(&empty_bar[stage], phase ^ 1u);  // every CTA of the cluster has drained this stage
-              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-              tma_load_4d(sa, am, &full_bar[stage], cc * 64, cw, ch, tc.img);
-              uint8_t* sb = sa + Cfg::A_BYTES + rank * b_rows * 128;
-              if (cm > 1)
-                tma_load_2d_mcast(sb, &p.w_map, &full_bar[stage], kc * 64, tc.n0 + rank * b_rows, cmask);
-              else
-                tma_load_2d(sb, &p.w_map, &full_bar[stage], kc * 64, tc.n0);
-              if (dbg && kc == 0 && g == cluster) dbg[2] = clock64();
-              ++kc;
-              if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1u;
+    // ===================== TMA producer (whole warp, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int b_rows = BN / cm;  // rows of the weight tile this CTA fetches (pair: its half)
+    for (int g = cluster; g < p.total_groups; g += n_clusters) {
+      TileCoord tc = decode_tile(p, g, rank, BN);
+      int kc = 0;
+      for (int tap = 0; tap < p.num_taps; ++tap) {
+        const int mp = p.tap_map[tap];
+        const int cw = tc.w0 + p.tap_dw[tap];
+        const int ch = tc.h0 + p.tap_dh[tap];
+        for (int s = 0; s < p.nsrc; ++s) {
+          const CUtensorMap* am = &p.a_map[s * 4 + mp];
+          for (int cc = 0; cc < p.chunks[s]; ++cc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);  // the MMAs that read this stage (in both CTAs) have retired
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            const bool skip_loads = dbg_mode == 1 && (kc >= STAGES || g != cluster);  // tuning: MMA rate alone
+            if (elect_one()) {
+              if (skip_loads) {
+                if (PAIR) {
+                  mbar_arrive_cluster(leader_addr(&full_bar[stage]));
+                } else {
+                  mbar_arrive(&full_bar[stage]);
+                }
+              } else if (PAIR) {
+                // own 128 rows of A + own half of the weight tile; the bytes are credited to the LEADER's barrier
+                const uint32_t lf = leader_addr(&full_bar[stage]);
+                mbar_expect_tx_cluster(lf, Cfg::STAGE_BYTES);
+                tma_load_4d_2sm(sa, am, lf, cc * 64, cw, ch, tc.img);
+                tma_load_2d_2sm(sa + Cfg::A_BYTES, &p.w_map, lf, kc * 64, tc.n0 + rank * b_rows);
+              } else {
+                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                tma_load_4d(sa, am, &full_bar[stage], cc * 64, cw, ch, tc.img);
+                tma_load_2d(sa + Cfg::A_BYTES, &p.w_map, &full_bar[stage], kc * 64, tc.n0);
               }
+              if (dbg && kc == 0 && g == cluster) dbg[2] = clock64();
+            }
+            ++kc;
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, BN, FP16, false, false);
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    if (!PAIR || rank == 0) {
+      constexpr uint32_t idesc = make_idesc(PAIR ? 256 : 128, BN, FP16, false, false);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -248,34 +278,91 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (dbg && kc == 0 && it == 0) dbg[3] = clock64();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t a_desc = make_smem_desc_sw128(a_addr, 16, 1024);
           const uint64_t b_desc = make_smem_desc_sw128(a_addr + Cfg::A_BYTES, 16, 1024);
+          if (elect_one()) {
+            if (dbg && kc == 0 && it == 0) dbg[3] = clock64();
+            if (dbg_mode != 2) {  // (2 = tuning: TMA fill rate without operand reads)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // +32 B per UMMA_K=16 step inside the 128 B swizzle atom -> +2 in the (addr>>4) field
-            umma_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                // +32 B per UMMA_K=16 step inside the 128 B swizzle atom -> +2 in the (addr>>4) field
+                if (PAIR)
+                  umma_ss2(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                else
+                  umma_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+              }
+            }
+            if (PAIR)
+              umma_commit2_mcast(&empty_bar[stage], 3);  // frees the stage in both CTAs
+            else
+              umma_commit(&empty_bar[stage]);
           }
-          if (cm > 1)
-            umma_commit_mcast(&empty_bar[stage], cmask);
-          else
-            umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[acc]);
-        if (dbg) dbg[4] = clock64();
+        if (elect_one()) {
+          if (PAIR)
+            umma_commit2_mcast(&tfull_bar[acc], 3);  // both CTAs' epilogues read their own 128 accumulator rows
+          else
+            umma_commit(&tfull_bar[acc]);
+          if (dbg) dbg[4] = clock64();
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== L2 prefetch of the NEXT launch's weights =====================
+    // Weights (5 GB for SDXL) never survive in L2 from one forward to the next, so every launch would start with
+    // DRAM-latency-bound weight fetches; the previous launch pulls them into L2 in the background instead.
+    if (p.pf_ptr) {
+      constexpr long long PIECE = 4096;
+      const long long pieces = (p.pf_bytes + PIECE - 1) / PIECE;
+      for (long long i = static_cast<long long>(blockIdx.x) * 32 + lane; i < pieces; i += static_cast<long long>(gridDim.x) * 32) {
+        const long long off = i * PIECE;
+        const long long rem = p.pf_bytes - off;
+        l2_prefetch_bulk(p.pf_ptr + off, static_cast<uint32_t>(rem < PIECE ? (rem & ~15ll) : PIECE));
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== slab manager (whole warp, one elected lane issues) =====================
+    // Hands the 32-column output slabs to the epilogue in launch order.  With a residual operand the residual tile of
+    // the chunk is TMA-loaded into the very slab the chunk's output will be written to (same box, same swizzle), up
+    // to NSLAB chunks ahead and overlapping the main loop, so the epilogue never issues a global load for it.
+    if (p.tma_store) {
+      uint32_t k = 0;
+      constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
+      const int n_limit = GEGLU ? (p.N >> 1) : p.N;
+      const bool load_res = p.tma_res != 0;
+      for (int g = cluster; g < p.total_groups; g += n_clusters) {
+        TileCoord tc = decode_tile(p, g, rank, BN);
+        const int ycol0 = GEGLU ? (tc.n0 >> 1) : tc.n0;
+#pragma unroll 1
+        for (int c = 0; c < OUT_COLS / 32; ++c, ++k) {
+          const int yc0 = ycol0 + c * 32;
+          if (yc0 >= n_limit) break;
+          const uint32_t s = k % Cfg::NSLAB;
+          mbar_wait(&sfree_bar[s], ((k / Cfg::NSLAB) & 1u) ^ 1u);
+          if (elect_one()) {
+            if (load_res) {
+              mbar_expect_tx(&rfull_bar[s], Cfg::SLAB_BYTES);
+              tma_load_4d(slabs + s * Cfg::SLAB_BYTES, &p.r_map, &rfull_bar[s], yc0, tc.w0, tc.h0, tc.img);  // phantom tile: zeros
+            } else {
+              mbar_arrive(&rfull_bar[s]);
+            }
+          }
+        }
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    // Code size matters here: the loops over 32-column chunks stay rolled and the per-element math is branch-light,
-    // so the whole epilogue body stays resident in the instruction cache (a fully unrolled version with inlined
-    // tanhf/erff ran 4x slower than the main loop).
-    const int q = warp - 4;
+    // ===================== epilogue: 8 warps =====================
+    // A warp may only read the TMEM lane quarter (warp % 4); the two warps of a quarter take alternate 32-column
+    // chunks, so every SM sub-partition has two epilogue warps to interleave (one warp alone is issue-latency bound).
+    // Code size matters: the chunk loop stays rolled and the common case (bias and/or residual only) has its own
+    // lean body, so the hot path stays resident in the instruction cache.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const int rh = row >> p.bw_shift;
     const int rw = row & (p.bw - 1);
@@ -286,14 +373,18 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     typename H::T* y = static_cast<typename H::T*>(p.y);
     const int n_limit = GEGLU ? (p.N >> 1) : p.N;  // number of y columns
     const bool tma_store = p.tma_store != 0;
-    const bool issuer = (warp == 4 && lane == 0);  // issues and tracks the TMA stores
-    const int sw = (row >> 1) & 3;                  // SWIZZLE_64B: 16-byte unit index ^= bits [7,9) of the byte offset
+    const bool tma_res = !GEGLU && p.tma_res != 0;
+    const bool issuer = (q == 0 && lane == 0);  // one per half: issues and tracks that half's TMA stores
+    const uint32_t bar_id = 1 + half;
+    const int sw = (row >> 1) & 3;  // SWIZZLE_64B: 16-byte unit index ^= bits [7,9) of the byte offset
     const int act = p.act;
-    uint32_t slab_count = 0;
+    const bool lean = !GEGLU && tma_store && act == ACT_NONE && gate == nullptr && rowvec == nullptr;
+    uint32_t k = 0;           // running chunk count over all tiles of this CTA (slab k % NSLAB, half k & 1)
+    uint32_t prev_k = 0;      // issuer: chunk of this half's store still in flight
+    bool have_prev = false;
     int it = 0;
     for (int g = cluster; g < p.total_groups; g += n_clusters, ++it) {
       const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1u;
       TileCoord tc = decode_tile(p, g, rank, BN);
       const int oh = tc.h0 + rh, ow = tc.w0 + rw;
       const bool real_tile = tc.img < p.batch;
@@ -302,65 +393,77 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
       const long long grp = (valid && (gate != nullptr || rowvec != nullptr)) ? (pix / p.rows_per_group) : 0;
       const typename H::T* gate_row = gate ? gate + grp * p.ld_gate : nullptr;
       const typename H::T* rv_row = rowvec ? rowvec + grp * p.ld_rowvec : nullptr;
-      const typename H::T* res_row = (residual && valid) ? residual + pix * p.ldr : nullptr;
+      const typename H::T* res_row = (residual && valid && !tma_res) ? residual + pix * p.ldr : nullptr;
       typename H::T* y_row = y + pix * p.ldy;
 
       constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
       const int ycol0 = GEGLU ? (tc.n0 >> 1) : tc.n0;
-      if (res_row) {  // pull this row's residual lines towards L2 while the main loop of the tile is still running
-#pragma unroll 1
-        for (int c = 0; c < OUT_COLS; c += 64)
-          if (ycol0 + c < n_limit) prefetch_l2(res_row + ycol0 + c);
-      }
 
-      // bias / residual of a chunk are requested one chunk ahead (chunk 0: before the accumulator is even ready)
-      uint4 rs[4], bs[4];
-      auto request = [&](int c) {
-        const int yc0 = ycol0 + c * 32;
-        const bool ok = p.vec_ok && c < OUT_COLS / 32 && (yc0 + 32 <= n_limit);
-        const int bcol = GEGLU ? (tc.n0 + c * 32) : yc0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          rs[j] = (ok && !GEGLU && res_row) ? *reinterpret_cast<const uint4*>(res_row + yc0 + j * 8) : make_uint4(0, 0, 0, 0);
-          bs[j] = (ok && bias) ? *reinterpret_cast<const uint4*>(bias + bcol + j * 8) : make_uint4(0, 0, 0, 0);
-        }
-      };
-      request(0);
-
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait_warp(&tfull_bar[acc], (it >> 1) & 1u);
       tc_fence_after();
-      if (dbg && issuer) dbg[5] = clock64();
+      if (dbg && issuer && half == 0) dbg[5] = clock64();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
 
 #pragma unroll 1
-      for (int c = 0; c < OUT_COLS / 32; ++c) {
+      for (int c = 0; c < OUT_COLS / 32; ++c, ++k) {
         const int yc0 = ycol0 + c * 32;
         if (yc0 >= n_limit) break;  // tile-uniform
+        if ((k & 1u) != static_cast<uint32_t>(half)) continue;
+        const bool chunk_vec = p.vec_ok && (yc0 + 32 <= n_limit);
+        const int bcol = GEGLU ? (tc.n0 + c * 32) : yc0;
         uint32_t v[32];
         tmem_ld32(t_row + c * 32, v);
         uint32_t gv[32];
         if (GEGLU) tmem_ld32(t_row + BN / 2 + c * 32, gv);
-        const bool chunk_vec = p.vec_ok && (yc0 + 32 <= n_limit);
-        const int bcol = GEGLU ? (tc.n0 + c * 32) : yc0;
-        uint4 rc[4], bc[4];  // this chunk's operands (requested during the previous chunk)
+        uint4 bc[4];  // bias of this chunk (same for every row: L1 hits after the first warp)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          rc[j] = rs[j];
-          bc[j] = bs[j];
-        }
-        request(c + 1);
-        uint8_t* slab = slabs + (slab_count % Cfg::NSLAB) * Cfg::SLAB_BYTES;
+        for (int j = 0; j < 4; ++j)
+          bc[j] = (chunk_vec && bias) ? *reinterpret_cast<const uint4*>(bias + bcol + j * 8) : make_uint4(0, 0, 0, 0);
+        uint8_t* slab = slabs + (k % Cfg::NSLAB) * Cfg::SLAB_BYTES;
         if (tma_store) {
-          // the store that used this slab NSLAB slabs ago must have finished reading it
-          if (issuer) bulk_wait_group_read<Cfg::NSLAB - 1>();
-          named_bar_sync(1, 128);
+          if (q == 0 && have_prev) {
+            // this half's previous store has long been read out: hand its slab back to the slab manager
+            if (elect_one()) {
+              bulk_wait_group_read<0>();
+              mbar_arrive(&sfree_bar[prev_k % Cfg::NSLAB]);
+            }
+            have_prev = false;
+          }
+          mbar_wait_warp(&rfull_bar[k % Cfg::NSLAB], (k / Cfg::NSLAB) & 1u);  // slab is ours (and holds the residual if any)
         }
         tmem_wait_ld();
-        if (dbg && issuer && it == 0 && c < 2) dbg[8 + c * 4] = clock64();
-        if (chunk_vec) {
+        const bool stamp = dbg && issuer && it == 0 && c < 2;
+        if (stamp) dbg[8 + c * 4] = clock64();
+        if (lean) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            uint4* sp = reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4));
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
+            {
+              float2 t0 = H::unpack(bc[j8].x), t1 = H::unpack(bc[j8].y), t2 = H::unpack(bc[j8].z), t3 = H::unpack(bc[j8].w);
+              f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
+              f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
+            }
+            if (tma_res) {  // the residual sits where this thread is about to write its output
+              const uint4 r4 = *sp;
+              float2 t0 = H::unpack(r4.x), t1 = H::unpack(r4.y), t2 = H::unpack(r4.z), t3 = H::unpack(r4.w);
+              f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
+              f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
+            }
+            uint4 o;
+            o.x = H::pack(f[0], f[1]);
+            o.y = H::pack(f[2], f[3]);
+            o.z = H::pack(f[4], f[5]);
+            o.w = H::pack(f[6], f[7]);
+            *sp = o;
+          }
+        } else if (chunk_vec) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             const int yc = yc0 + j8 * 8;
+            uint4* sp = reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4));
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
@@ -393,8 +496,9 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
                 f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
                 f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
               }
-              {
-                float2 t0 = H::unpack(rc[j8].x), t1 = H::unpack(rc[j8].y), t2 = H::unpack(rc[j8].z), t3 = H::unpack(rc[j8].w);
+              if (tma_res || res_row) {
+                const uint4 r4 = tma_res ? *sp : *reinterpret_cast<const uint4*>(res_row + yc);
+                float2 t0 = H::unpack(r4.x), t1 = H::unpack(r4.y), t2 = H::unpack(r4.z), t3 = H::unpack(r4.w);
                 f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
                 f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
               }
@@ -412,7 +516,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
               o.z = H::pack(f[4], f[5]);
               o.w = H::pack(f[6], f[7]);
               if (tma_store)
-                *reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4)) = o;
+                *sp = o;
               else if (valid)
                 *reinterpret_cast<uint4*>(y_row + yc) = o;
             }
@@ -427,24 +531,38 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
           }
           epilogue_scalar<GEGLU, FP16>(tv, tg, p, bias, gate_row, rv_row, res_row, y_row, pix, yc0, tc.n0 + c * 32, BN, n_limit);
         }
-        if (dbg && issuer && it == 0 && c < 2) dbg[9 + c * 4] = clock64();
+        if (stamp) dbg[9 + c * 4] = clock64();
         if (tma_store) {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
-          named_bar_sync(1, 128);
-          if (issuer) {
-            if (real_tile) tma_store_4d(&p.y_map, slab, yc0, tc.w0, tc.h0, tc.img);
-            bulk_commit_group();
-            if (dbg && it == 0 && c < 2) dbg[11 + c * 4] = clock64();
+          named_bar_sync(bar_id, 128);
+          if (q == 0) {
+            if (elect_one()) {
+              if (real_tile) tma_store_4d(&p.y_map, slab, yc0, tc.w0, tc.h0, tc.img);
+              bulk_commit_group();
+              if (stamp) dbg[11 + c * 4] = clock64();
+            }
+            have_prev = true;
+            prev_k = k;
           }
-          ++slab_count;
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR)
+          mbar_arrive_cluster(leader_addr(&tempty_bar[acc]));
+        else
+          mbar_arrive(&tempty_bar[acc]);
+      }
+      if (q == 0 && have_prev) {  // tile done: free this half's last slab so the next tile's residual can stream in
+        if (elect_one()) {
+          bulk_wait_group_read<0>();
+          mbar_arrive(&sfree_bar[prev_k % Cfg::NSLAB]);
+        }
+        have_prev = false;
+      }
     }
-    if (dbg && issuer) dbg[6] = clock64();
-    if (tma_store && issuer) bulk_wait_group_read<0>();  // smem must outlive the stores' reads; kernel exit publishes the writes
+    if (dbg && issuer && half == 0) dbg[6] = clock64();
   }
 
   tc_fence_before();
@@ -452,7 +570,10 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   if (cm > 1) cluster_sync_all();  // nobody exits while a peer can still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR)
+      tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+    else
+      tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
   if (dbg && threadIdx.x == 0) dbg[7] = clock64();
 }
@@ -462,8 +583,13 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 // ------------------------------------------------------------------------------------------------
 template <int BN, bool GEGLU, bool FP16>
 static int set_smem_attr() {
-  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, GEGLU, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       ConvGemmCfg<BN>::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, GEGLU, FP16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ConvGemmCfg<BN, false>::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_gemm_kernel<BN, GEGLU, FP16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             ConvGemmCfg<BN, true>::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_gemm_kernel<BN, GEGLU, FP16, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "conv_gemm smem attr BN=%d: %s", BN, cudaGetErrorString(e));
   return 0;
 }
@@ -483,13 +609,14 @@ int init_conv_gemm() {
   return 0;
 }
 
-template <int BN, bool GEGLU, bool FP16>
-static int launch_one(const ConvGemmParams& prm, int grid, int cm, cudaStream_t st) {
+template <int BN, bool GEGLU, bool FP16, bool PAIR>
+static int launch_one(const ConvGemmParams& prm, int grid, cudaStream_t st) {
+  constexpr int cm = PAIR ? 2 : 1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = ConvGemmCfg<BN>::SMEM_BYTES;
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = ConvGemmCfg<BN, PAIR>::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -503,45 +630,46 @@ static int launch_one(const ConvGemmParams& prm, int grid, int cm, cudaStream_t 
   if (cm > 1) {
     // GPC boundaries can strand SMs for clusters: never launch more clusters than can be co-resident, the
     // persistent tile loop strides by the number of clusters actually launched
-    static int max_active[5] = {0, 0, 0, 0, 0};
-    if (max_active[cm] == 0) {
+    static int max_active = 0;
+    if (max_active == 0) {
       int n = 0;
       cudaLaunchConfig_t q = cfg;
       q.gridDim = dim3(num_sms() / cm * cm);
-      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<BN, GEGLU, FP16>, &q) != cudaSuccess || n <= 0) {
+      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<BN, GEGLU, FP16, PAIR>, &q) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         n = num_sms() / cm;
       }
-      max_active[cm] = n;
+      max_active = n;
     }
-    if (grid > max_active[cm] * cm) cfg.gridDim = dim3(max_active[cm] * cm);
+    if (grid > max_active * cm) cfg.gridDim = dim3(max_active * cm);
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, GEGLU, FP16>, prm);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, GEGLU, FP16, PAIR>, prm);
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "conv_gemm launch (BN=%d cm=%d grid=%d): %s", BN, cm, grid, cudaGetErrorString(e));
   return 0;
 }
 
-template <bool GEGLU, bool FP16>
-static int launch_bn(int bn, const ConvGemmParams& prm, int grid, int cm, cudaStream_t st) {
+template <bool GEGLU, bool FP16, bool PAIR>
+static int launch_bn(int bn, const ConvGemmParams& prm, int grid, cudaStream_t st) {
   switch (bn) {
-    case 256: return launch_one<256, GEGLU, FP16>(prm, grid, cm, st);
-    case 128: return launch_one<128, GEGLU, FP16>(prm, grid, cm, st);
-    case 64: return launch_one<64, GEGLU, FP16>(prm, grid, cm, st);
+    case 256: return launch_one<256, GEGLU, FP16, PAIR>(prm, grid, st);
+    case 128: return launch_one<128, GEGLU, FP16, PAIR>(prm, grid, st);
+    case 64: return launch_one<64, GEGLU, FP16, PAIR>(prm, grid, st);
     default: break;
   }
   if (GEGLU) return set_error(B200_ERR_UNSUPPORTED, "geglu needs tile_n in {64, 128, 256} (got %d)", bn);
   switch (bn) {
-    case 192: return launch_one<192, false, FP16>(prm, grid, cm, st);
-    case 160: return launch_one<160, false, FP16>(prm, grid, cm, st);
-    case 96: return launch_one<96, false, FP16>(prm, grid, cm, st);
-    case 32: return launch_one<32, false, FP16>(prm, grid, cm, st);
+    case 192: return launch_one<192, false, FP16, PAIR>(prm, grid, st);
+    case 160: return launch_one<160, false, FP16, PAIR>(prm, grid, st);
+    case 96: return launch_one<96, false, FP16, PAIR>(prm, grid, st);
+    case 32: return launch_one<32, false, FP16, PAIR>(prm, grid, st);
     default: return set_error(B200_ERR_INVALID, "conv_gemm: unsupported tile_n %d", bn);
   }
 }
 
-// Cost model (SM cycles) used to pick the tile width BN and the cluster size cm (CTAs along M that share one
-// multicast weight tile).  Per 64-wide K chunk a CTA issues 4 MMAs of 128 x BN x 16 (2*BN cycles) and pulls
-// 16 KB of activations + BN*128/cm bytes of weights through its ~64 B/clk L2 port; one tile then costs
+// Cost model (SM cycles) used to pick the tile width BN and cm (1 = one CTA per tile, 2 = a CTA pair driving one
+// 256 x BN cta_group::2 MMA, each CTA staging half of the weight tile).  Per 64-wide K chunk an SM executes
+// 128 x BN x 64 of MMA (2*BN cycles) and pulls 16 KB of activations + BN*128/cm bytes of weights through its
+// ~64 B/clk L2 port; one tile then costs
 // k_chunks * max(mma, l2) + epilogue + fixed, and the launch costs ceil(groups / clusters) such tiles.
 static double tile_cost(int bn, int cm, int k_chunks, bool geglu) {
   const double mma = 2.0 * bn;
@@ -563,12 +691,13 @@ static void pick_config(long long m_tiles, int N, int k_chunks, int geglu, int f
     if (geglu && !(bn == 256 || bn == 128 || bn == 64)) continue;
     if (geglu && N % bn != 0) continue;
     const long long n_tiles = (N + bn - 1) / bn;
+    static const bool no_pair = getenv("B200_NO_PAIR") && atoi(getenv("B200_NO_PAIR")) != 0;  // tuning knob
     for (int cm : {1, 2}) {
-      if (force_cm ? cm != force_cm : cm != 1) continue;  // measured: multicast clusters bring nothing here (not L2-bound)
+      if (force_cm ? cm != force_cm : (cm == 2 && no_pair)) continue;
       if ((bn / cm) % 8 != 0) continue;
       if (cm > 1 && m_tiles < cm) continue;
       const long long groups = n_tiles * ((m_tiles + cm - 1) / cm);
-      const long long clusters = cm == 4 ? (sms * 7 / 8) / cm : sms / cm;  // GPC boundaries strand some SMs for 4-CTA clusters
+      const long long clusters = sms / cm;
       const long long waves = (groups + clusters - 1) / clusters;
       const double cost = waves * tile_cost(bn, cm, k_chunks, geglu != 0);
       if (cost < best * 0.999) {
@@ -744,6 +873,8 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   prm.vec_ok = vec ? 1 : 0;
   prm.out_fp32 = a->out_fp32 ? 1 : 0;
   prm.dbg = static_cast<long long*>(a->debug_timestamps);
+  static const int dbg_mode = getenv("B200_GEMM_DEBUG_MODE") ? atoi(getenv("B200_GEMM_DEBUG_MODE")) : 0;  // wrong results!
+  prm.dbg_mode = dbg_mode;
   const int n_out = a->geglu ? a->N / 2 : a->N;
   static const bool no_tma_store = getenv("B200_NO_TMA_STORE") && atoi(getenv("B200_NO_TMA_STORE")) != 0;  // tuning knob
   prm.tma_store = (vec && !a->out_fp32 && n_out % 32 == 0 && !no_tma_store) ? 1 : 0;
@@ -757,13 +888,34 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
     if (r) return r;
   }
 
+  prm.tma_res = (prm.tma_store && a->residual && !a->geglu) ? 1 : 0;
+  if (prm.tma_res) {
+    const uint64_t ldr = static_cast<uint64_t>(a->ldr);
+    const uint64_t dims[4] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                              static_cast<uint64_t>(a->batch)};
+    const uint64_t str[3] = {ldr * 2, ldr * 2 * Wo, ldr * 2 * Wo * Ho};
+    const uint32_t rbox[4] = {32u, static_cast<uint32_t>(prm.bw), static_cast<uint32_t>(prm.bh), 1u};
+    int r = make_tensor_map_16b(&prm.r_map, a->residual, 4, dims, str, rbox, "conv_gemm residual", 64);
+    if (r) return r;
+  }
+  static const bool no_pf = getenv("B200_NO_WEIGHT_PREFETCH") && atoi(getenv("B200_NO_WEIGHT_PREFETCH")) != 0;  // tuning knob
+  if (a->prefetch && a->prefetch_bytes > 0 && !no_pf) {
+    B200_CHECK_ARG(aligned16(a->prefetch), "conv_gemm: prefetch pointer not 16-byte aligned");
+    prm.pf_ptr = static_cast<const uint8_t*>(a->prefetch);
+    prm.pf_bytes = a->prefetch_bytes;
+  }
+
   const int clusters_avail = num_sms() / cm;
   const int n_clusters = prm.total_groups < clusters_avail ? prm.total_groups : clusters_avail;
   const int grid = n_clusters * cm;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool fp16 = a->dtype == B200_DTYPE_FP16;
-  if (a->geglu) return fp16 ? launch_bn<true, true>(bn, prm, grid, cm, st) : launch_bn<true, false>(bn, prm, grid, cm, st);
-  return fp16 ? launch_bn<false, true>(bn, prm, grid, cm, st) : launch_bn<false, false>(bn, prm, grid, cm, st);
+  if (cm == 2) {
+    if (a->geglu) return fp16 ? launch_bn<true, true, true>(bn, prm, grid, st) : launch_bn<true, false, true>(bn, prm, grid, st);
+    return fp16 ? launch_bn<false, true, true>(bn, prm, grid, st) : launch_bn<false, false, true>(bn, prm, grid, st);
+  }
+  if (a->geglu) return fp16 ? launch_bn<true, true, false>(bn, prm, grid, st) : launch_bn<true, false, false>(bn, prm, grid, st);
+  return fp16 ? launch_bn<false, true, false>(bn, prm, grid, st) : launch_bn<false, false, false>(bn, prm, grid, st);
 }
 
 }  // extern "C"

@@ -40,15 +40,16 @@ __device__ __forceinline__ void chan_combine(float& na, float& ma, float& M2a, f
 }
 
 // grid (chunks, batch); block V*P threads.  Thread (pl, cv) owns 8 fixed channels and walks pixels
-// chunk_start + pl, + P, ...  Sums are taken relative to the first value seen (shifted data) so the
-// fp32 variance does not cancel; partials are merged with Chan's formula in a fixed order
-// (deterministic).  The last CTA of an image to finish folds the chunk partials into mean/rstd.
+// chunk_start + pl, + P, ...  All sums of a CTA are taken relative to one representative value per group (the group's
+// first channel at the chunk's first pixel), so the fp32 variance does not cancel and the in-CTA reduction is plain
+// additions in a fixed order (deterministic).  Chunk partials (count, mean, M2) are merged with Chan's formula by
+// the last CTA of the image to finish, 8 lanes per group.
 template <bool FP16>
 __global__ void group_norm_stats_kernel(const GroupNormParams p) {
   pdl_trigger();
   pdl_wait();
   using H = Half16<FP16>;
-  extern __shared__ float2 s_mm[];  // [P][C] (mean, M2) per (pixel lane, channel)
+  extern __shared__ float2 s_mm[];  // [P][C] (sum, sum of squares) of shifted values per (pixel lane, channel)
   __shared__ float s_cnt[64];       // per pixel lane count (P <= 64)
   __shared__ unsigned int s_last;
 
@@ -63,12 +64,21 @@ __global__ void group_norm_stats_kernel(const GroupNormParams p) {
   const typename H::T* xb = static_cast<const typename H::T*>(p.x[src]) +
                             (static_cast<size_t>(n) * p.hw) * p.ldx[src] + coff;
   const int ld = p.ldx[src];
+  auto rep_value = [&](int g) -> float {  // group g's first channel at the chunk's first pixel
+    const int c = g * p.cg;
+    const int s2 = c < p.c[0] ? 0 : 1;
+    const typename H::T* q = static_cast<const typename H::T*>(p.x[s2]) +
+                             (static_cast<size_t>(n) * p.hw + pix0) * p.ldx[s2] + (s2 ? c - p.c[0] : c);
+    return H::to_float(*q);
+  };
 
   float sh[8], s[8], ss[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) sh[j] = s[j] = ss[j] = 0.f;
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = sh[j] = 0.f;
   float cnt = 0.f;
   if (pl < p.P) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[j] = rep_value((cv * 8 + j) / p.cg);
     const int step = p.P;
     for (int pix = pix0 + pl; pix < pix1; pix += 4 * step) {
       uint4 u[4];
@@ -80,10 +90,6 @@ __global__ void group_norm_stats_kernel(const GroupNormParams p) {
         if (pix + k * step < pix1) {
           float2 a = H::unpack(u[k].x), b = H::unpack(u[k].y), c = H::unpack(u[k].z), d = H::unpack(u[k].w);
           float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
-          if (cnt == 0.f) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) sh[j] = v[j];
-          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float e = v[j] - sh[j];
@@ -96,31 +102,27 @@ __global__ void group_norm_stats_kernel(const GroupNormParams p) {
     }
     const int cbase = cv * 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float mean = 0.f, M2 = 0.f;
-      if (cnt > 0.f) {
-        float m = s[j] / cnt;
-        mean = sh[j] + m;
-        M2 = fmaxf(ss[j] - s[j] * m, 0.f);
-      }
-      s_mm[pl * p.C + cbase + j] = make_float2(mean, M2);
-    }
+    for (int j = 0; j < 8; ++j) s_mm[pl * p.C + cbase + j] = make_float2(s[j], ss[j]);
     if (cv == 0) s_cnt[pl] = cnt;
   }
   __syncthreads();
   float* part = p.partial + (static_cast<size_t>(n) * p.chunks + chunk) * p.groups * 3;
   if (t < p.groups) {
-    float na = 0.f, ma = 0.f, M2a = 0.f;
+    float S = 0.f, SS = 0.f, npix = 0.f;
     for (int pl2 = 0; pl2 < p.P; ++pl2) {
-      const float nb = s_cnt[pl2];
+      npix += s_cnt[pl2];
       for (int c = t * p.cg; c < (t + 1) * p.cg; ++c) {
-        float2 mm = s_mm[pl2 * p.C + c];
-        chan_combine(na, ma, M2a, nb, mm.x, mm.y);
+        const float2 v = s_mm[pl2 * p.C + c];
+        S += v.x;
+        SS += v.y;
       }
     }
-    part[t * 3 + 0] = na;
-    part[t * 3 + 1] = ma;
-    part[t * 3 + 2] = M2a;
+    const float cntg = npix * static_cast<float>(p.cg);
+    const float K = rep_value(t);
+    const float m = cntg > 0.f ? S / cntg : 0.f;
+    part[t * 3 + 0] = cntg;
+    part[t * 3 + 1] = K + m;
+    part[t * 3 + 2] = fmaxf(SS - S * m, 0.f);
   }
   __threadfence();
   __syncthreads();
@@ -131,38 +133,30 @@ __global__ void group_norm_stats_kernel(const GroupNormParams p) {
   __syncthreads();
   if (s_last) {
     __threadfence();
-    // stage this image's partials in shared memory with coalesced loads (reusing the per-lane buffer), then
-    // merge them in a fixed order
-    float* s_part = reinterpret_cast<float*>(s_mm);
-    const int total = p.chunks * p.groups * 3;
+    // merge the chunk partials of this image: 8 lanes per group take every 8th chunk (fixed order), then a fixed
+    // shuffle tree merges the lanes
     const volatile float* pp = p.partial + static_cast<size_t>(n) * p.chunks * p.groups * 3;
-    const int cap = p.P * p.C * 2;  // floats available in s_mm
-    const int per_round = max(1, cap / (p.groups * 3));  // chunks staged per round
-    float na = 0.f, ma = 0.f, M2a = 0.f;
-    for (int c0 = 0; c0 < p.chunks; c0 += per_round) {
-      const int nc = min(per_round, p.chunks - c0);
-      const int cnt_f = nc * p.groups * 3;
-      __syncthreads();
-      if (cnt_f <= cap) {
-        for (int i = t; i < cnt_f; i += blockDim.x) s_part[i] = pp[static_cast<size_t>(c0) * p.groups * 3 + i];  // coalesced
-      }
-      __syncthreads();
-      if (t < p.groups) {
-        for (int ch = 0; ch < nc; ++ch) {
-          if (cnt_f <= cap) {
-            const float* q = s_part + (ch * p.groups + t) * 3;
-            chan_combine(na, ma, M2a, q[0], q[1], q[2]);
-          } else {  // shared buffer smaller than one chunk row (tiny blocks): read global directly
-            const volatile float* q = pp + (static_cast<size_t>(c0 + ch) * p.groups + t) * 3;
-            chan_combine(na, ma, M2a, q[0], q[1], q[2]);
-          }
+    for (int g0 = 0; g0 < p.groups; g0 += blockDim.x / 8) {
+      const int g = g0 + t / 8, l8 = t & 7;
+      float na = 0.f, ma = 0.f, M2a = 0.f;
+      if (g < p.groups) {
+        for (int ch = l8; ch < p.chunks; ch += 8) {
+          const volatile float* q = pp + (static_cast<size_t>(ch) * p.groups + g) * 3;
+          chan_combine(na, ma, M2a, q[0], q[1], q[2]);
         }
       }
-    }
-    if (t < p.groups) {
-      float var = M2a / na;
-      p.stats[(static_cast<size_t>(n) * p.groups + t) * 2 + 0] = ma;
-      p.stats[(static_cast<size_t>(n) * p.groups + t) * 2 + 1] = rsqrtf(var + p.eps);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const float nb = __shfl_down_sync(0xffffffffu, na, o, 8);
+        const float mb = __shfl_down_sync(0xffffffffu, ma, o, 8);
+        const float Mb = __shfl_down_sync(0xffffffffu, M2a, o, 8);
+        if (l8 < o) chan_combine(na, ma, M2a, nb, mb, Mb);
+      }
+      if (g < p.groups && l8 == 0) {
+        const float var = M2a / na;
+        p.stats[(static_cast<size_t>(n) * p.groups + g) * 2 + 0] = ma;
+        p.stats[(static_cast<size_t>(n) * p.groups + g) * 2 + 1] = rsqrtf(var + p.eps);
+      }
     }
     if (t == 0) p.counter[n] = 0u;
   }

@@ -16,6 +16,80 @@ def launches():
     return _LAUNCHES
 
 
+class WeightPrefetchPlan:
+    """Launch-order trace of the packed weights one model forward feeds to b200_conv_gemm.
+
+    SDXL's 5 GB of weights never survive in the 126 MB L2 from one forward to the next, so a GEMM would open with
+    DRAM-latency-bound weight fetches.  Once a forward has been traced, every launch hands the kernel the weights of
+    the launch that FOLLOWS it (b200_conv_gemm_args.prefetch) and the kernel pulls them into L2 in the background.
+    A forward whose launch order differs from the trace simply re-records (the hint is never needed for
+    correctness)."""
+    MAX_BYTES = 48 << 20  # per launch; the head of a bigger weight is what its first tiles read
+
+    def __init__(self):
+        self.seq = []
+        self._rec = None
+        self._i = 0
+
+    def _begin(self):
+        self._rec = []
+        self._i = 0
+
+    def _step(self, w):
+        key = (w.data_ptr(), min(w.numel() * w.element_size(), self.MAX_BYTES))
+        self._rec.append(key)
+        i = self._i
+        self._i += 1
+        if i < len(self.seq) and self.seq[i] == key:
+            return self.seq[(i + 1) % len(self.seq)]
+        return None
+
+    def _end(self):
+        if self._rec != self.seq:
+            self.seq = self._rec
+        self._rec = None
+
+
+_PLAN = None
+
+
+class weight_prefetch:
+    """`with ops.weight_prefetch(plan):` around one model forward."""
+
+    def __init__(self, plan):
+        self.plan = plan
+
+    def __enter__(self):
+        global _PLAN
+        self._prev = _PLAN
+        _PLAN = self.plan
+        self.plan._begin()
+        return self.plan
+
+    def __exit__(self, *exc):
+        global _PLAN
+        self.plan._end()
+        _PLAN = self._prev
+        return False
+
+
+def prefetching_forward(fn):
+    """Decorator for a model's forward/decode: runs it under the model's own WeightPrefetchPlan."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        plan = self.__dict__.get("_weight_prefetch_plan")
+        if plan is None:
+            plan = self.__dict__["_weight_prefetch_plan"] = WeightPrefetchPlan()
+        if _PLAN is plan:  # re-entrant call (e.g. sub-batched decode)
+            return fn(self, *args, **kwargs)
+        with weight_prefetch(plan):
+            return fn(self, *args, **kwargs)
+
+    return wrapped
+
+
 def _count(n=1):
     global _LAUNCHES
     _LAUNCHES += n
@@ -79,6 +153,10 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
     a.out_fp32 = 1 if out_fp32 else 0
     a.cluster_m = cluster_m
     a.debug_timestamps = _ptr(debug_timestamps)
+    if _PLAN is not None:
+        nxt = _PLAN._step(w)
+        if nxt is not None:
+            a.prefetch, a.prefetch_bytes = nxt
     if _PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -252,6 +252,7 @@ class FluxTransformer2DModel(torch.nn.Module):
         return self._lin(self.proj_out, nx)
 
     @torch.no_grad()
+    @ops.prefetching_forward
     def forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None,
                 txt_ids=None, guidance=None, joint_attention_kwargs=None, controlnet_block_samples=None,
                 controlnet_single_block_samples=None, return_dict=True, controlnet_blocks_repeat=False):

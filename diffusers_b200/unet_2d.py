@@ -160,6 +160,7 @@ class UNet2DModel(torch.nn.Module):
         return ops.linear(o.view(B * hw, C), self.W(a["ow"]), C, bias=self.W(a["ob"]), residual=x)
 
     @torch.no_grad()
+    @ops.prefetching_forward
     def forward(self, sample, timestep, class_labels=None, return_dict=True):
         if class_labels is not None:
             raise NotImplementedError("class conditioning is outside the hot path")

@@ -291,6 +291,7 @@ class UNet2DConditionModel(torch.nn.Module):
         # emb = emb + aug_emb  (aug rounded to 16 bit first, as in the reference)
         return ops.small_linear(a1, self.W(ae[1]["w"]), bias=self.W(ae[1]["b"]), addend=emb)
 
+    @ops.prefetching_forward
     def _forward_nhwc(self, x_in, B, H, W, timestep, kv, added_cond_kwargs):
         """x_in: [B*H*W, in_pad] NHWC; kv: cached text K/V [B, S_txt, kv_total].  Returns the NHWC prediction
         [B*H*W, out_channels]."""

@@ -99,7 +99,9 @@ typedef struct {
   int32_t tile_n;        /* 0 = auto, else force BN in {32, 64, 96, 128, 160, 192, 256}         */
   int32_t out_fp32;      /* 1: y is float32 [.., ldy] (attention scores of the head_dim-512 path) */
   int32_t cluster_m;     /* 0 = auto, else force the cluster size along M in {1, 2} (tuning / tests) */
-  void* debug_timestamps; /* NULL, or int64 [grid][8] device buffer receiving per-CTA clock64 marks (tuning) */
+  void* debug_timestamps; /* NULL, or int64 [grid][16] device buffer receiving per-CTA clock64 marks (tuning) */
+  const void* prefetch;  /* NULL, or device memory (16-byte aligned) to pull into L2 while this launch runs:      */
+  int64_t prefetch_bytes; /* the packed weights of the NEXT launch, which would otherwise start DRAM-latency-bound */
 } b200_conv_gemm_args;
 
 int b200_conv_gemm(const b200_conv_gemm_args* args, void* stream);

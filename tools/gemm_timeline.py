@@ -23,18 +23,31 @@ for _ in range(3):
     ops.linear(x, w, N, bias=b, residual=r, out=out, tile_n=bn, debug_timestamps=dbg)
 torch.cuda.synchronize()
 flush = torch.empty(64 << 20, dtype=torch.int32, device="cuda")
+mode = os.environ.get("MODE", "cold")  # cold | hotact (activations in L2, weights cold) | pf (+ weights prefetched by the previous launch) | hot
+xs = torch.randn(256, 256, device="cuda").bfloat16()
+ws = packing.pack_linear_weight(torch.randn(256, 256, device="cuda").bfloat16())
+names = ["entry", "prologue done", "first TMA issued", "first data landed", "last MMA committed", "accumulator ready (epi)",
+         "epilogue stores issued", "exit", "c0 tmem loaded", "c0 math+sts done", "c0 fence done", "c0 store issued",
+         "c1 tmem loaded", "c1 math+sts done", "c1 fence done", "c1 store issued"]
 for rep in range(2):
-    flush.zero_()
+    if mode != "hot":
+        flush.zero_()
+    if mode in ("hotact", "pf"):
+        x.float().sum()
+        if r is not None:
+            r.float().sum()
+    if mode == "pf":
+        ops._PLAN = type("P", (), {"_step": lambda self, w_: (w.data_ptr(), w.numel() * 2)})()
+        ops.linear(xs, ws, 256)
+        ops._PLAN = None
     dbg.zero_()
     ops.linear(x, w, N, bias=b, residual=r, out=out, tile_n=bn, debug_timestamps=dbg)
     torch.cuda.synchronize()
     d = dbg.cpu()
     d = d[d[:, 7] > 0]
-    names = ["entry", "prologue done", "first TMA issued", "first data landed", "last MMA committed", "accumulator ready (epi)",
-             "epilogue stores issued", "exit"]
-    print(f"rep {rep}: {d.shape[0]} CTAs; medians of (t_i - t_entry) in cycles:")
-    names = names + ["c0 tmem loaded", "c0 math+sts done", "c0 fence done", "c0 store issued", "c1 tmem loaded", "c1 math+sts done",
-                     "c1 fence done", "c1 store issued"]
+    if rep == 0:
+        continue
+    print(f"mode {mode}: {d.shape[0]} CTAs; medians of (t_i - t_entry) in cycles:")
     for i in range(1, 16):
         v = (d[:, i] - d[:, 0]).float()
         v = v[d[:, i] > 0]
