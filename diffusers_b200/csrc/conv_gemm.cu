@@ -666,17 +666,22 @@ static int launch_bn(int bn, const ConvGemmParams& prm, int grid, cudaStream_t s
   }
 }
 
-// Cost model (SM cycles) used to pick the tile width BN and cm (1 = one CTA per tile, 2 = a CTA pair driving one
-// 256 x BN cta_group::2 MMA, each CTA staging half of the weight tile).  Per 64-wide K chunk an SM executes
-// 128 x BN x 64 of MMA (2*BN cycles) and pulls 16 KB of activations + BN*128/cm bytes of weights through its
-// ~64 B/clk L2 port; one tile then costs
-// k_chunks * max(mma, l2) + epilogue + fixed, and the launch costs ceil(groups / clusters) such tiles.
-static double tile_cost(int bn, int cm, int k_chunks, bool geglu) {
-  const double mma = 2.0 * bn;
-  const double l2 = (16384.0 + bn * 128.0 / cm) / 64.0;
-  const double chunk = mma > l2 ? mma : l2;
-  const double epi = 300.0 + (geglu ? bn / 2 : bn) / 32.0 * 220.0;
-  return k_chunks * chunk + epi + 2500.0;
+// Cost model (SM cycles, measured on B200 with tools/gemm_chunk_rate.py / gemm_timeline.py) used to pick the tile
+// width BN and cm (1 = one CTA per tile, 2 = a CTA pair driving one 256 x BN cta_group::2 MMA, each CTA staging half
+// of the weight tile).  Per 64-wide K chunk the tensor pipe needs ~2*BN cycles, but the TMA/mbarrier round of a stage
+// has a floor of ~400 (pair) / ~450-470 (single) cycles whatever the tile width; the 8-warp epilogue drains two
+// 32-column chunks per ~1450 cycles and overlaps the next tile's main loop when a CTA owns several tiles.
+static double chunk_cycles(int bn, int cm) {
+  if (cm == 2) return bn <= 192 ? 400.0 : 1.96 * bn;
+  if (bn <= 160) return 445.0 + 0.18 * bn;
+  return bn <= 192 ? 543.0 : 2.31 * bn;
+}
+static double launch_cost(int bn, int cm, int k_chunks, bool geglu, long long waves) {
+  const double main_loop = k_chunks * chunk_cycles(bn, cm) + 900.0;  // + pipeline fill / accumulator hand-over
+  const int n_chunks = (geglu ? bn / 2 : bn) / 32;
+  const double epi = 700.0 + 1450.0 * ((n_chunks + 1) / 2) * (geglu ? 1.6 : 1.0);
+  const double hidden = epi > main_loop ? epi - main_loop : 0.0;  // part of an epilogue the next main loop cannot cover
+  return 3000.0 + (cm == 2 ? 900.0 : 0.0) + waves * main_loop + (waves - 1) * hidden + epi;
 }
 
 static void pick_config(long long m_tiles, int N, int k_chunks, int geglu, int force_bn, int force_cm_arg, int* bn_out, int* cm_out) {
@@ -685,7 +690,7 @@ static void pick_config(long long m_tiles, int N, int k_chunks, int geglu, int f
   const int force_cm = force_cm_arg ? force_cm_arg : env_cm;
   double best = 1e30;
   int best_bn = 0, best_cm = 1;
-  static const int kBn[] = {256, 192, 160, 128, 96, 64, 32};
+  static const int kBn[] = {32, 64, 96, 128, 160, 192, 256};  // ascending: ties go to the narrower tile
   for (int bn : kBn) {
     if (force_bn && bn != force_bn) continue;
     if (geglu && !(bn == 256 || bn == 128 || bn == 64)) continue;
@@ -699,7 +704,7 @@ static void pick_config(long long m_tiles, int N, int k_chunks, int geglu, int f
       const long long groups = n_tiles * ((m_tiles + cm - 1) / cm);
       const long long clusters = sms / cm;
       const long long waves = (groups + clusters - 1) / clusters;
-      const double cost = waves * tile_cost(bn, cm, k_chunks, geglu != 0);
+      const double cost = launch_cost(bn, cm, k_chunks, geglu != 0, waves);
       if (cost < best * 0.999) {
         best = cost;
         best_bn = bn;

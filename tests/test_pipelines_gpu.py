@@ -110,8 +110,12 @@ def test_scheduler_dropins_on_gpu(golden):
     # checked bit-exactly against the CUDA-eager formula in test_kernels_gpu).
     prev = s.step(e["eps"].cuda(), s.timesteps[0], e["x"].cuda(), return_dict=False)[0].cpu().float()
     ref = e["prev"].float()
-    assert ((prev - ref).abs() <= 2.0 ** -6 * ref.abs() + 1e-6).all()
-    assert (prev != ref).float().mean() < 0.05
+    # error budget: 2 ulps of the larger of x / prev (the final add can cancel) + the ulp of pred_original = x - sigma * eps
+    # carried through derivative * dt
+    dt = float(s.sigmas[1] - s.sigmas[0])
+    tol = 2.0 ** -6 * torch.maximum(ref.abs(), e["x"].float().abs()) + 2.0 ** -7 * (e["eps"].float() * dt).abs() + 1e-6
+    assert ((prev - ref).abs() <= tol).all()
+    assert (prev != ref).float().mean() < 0.3  # ~23 % of the elements see a flipped rounding between the two eager semantics
     with pytest.raises(ValueError):
         s.step(e["eps"].cuda(), 3, e["x"].cuda())
     f = fx["flow_step_bf16"]
