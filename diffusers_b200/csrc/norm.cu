@@ -107,22 +107,34 @@ __global__ void group_norm_stats_kernel(const GroupNormParams p) {
   }
   __syncthreads();
   float* part = p.partial + (static_cast<size_t>(n) * p.chunks + chunk) * p.groups * 3;
-  if (t < p.groups) {
-    float S = 0.f, SS = 0.f, npix = 0.f;
-    for (int pl2 = 0; pl2 < p.P; ++pl2) {
-      npix += s_cnt[pl2];
-      for (int c = t * p.cg; c < (t + 1) * p.cg; ++c) {
+  // 8 lanes per group add strided subsets of the (pixel lane, channel) sums, then a fixed shuffle tree: deterministic
+  for (int g0 = 0; g0 < p.groups; g0 += blockDim.x / 8) {
+    const int g = g0 + t / 8, l8 = t & 7;
+    float S = 0.f, SS = 0.f;
+    if (g < p.groups) {
+      const int items = p.P * p.cg;
+      for (int i = l8; i < items; i += 8) {
+        const int pl2 = i / p.cg, c = g * p.cg + (i - pl2 * p.cg);
         const float2 v = s_mm[pl2 * p.C + c];
         S += v.x;
         SS += v.y;
       }
     }
-    const float cntg = npix * static_cast<float>(p.cg);
-    const float K = rep_value(t);
-    const float m = cntg > 0.f ? S / cntg : 0.f;
-    part[t * 3 + 0] = cntg;
-    part[t * 3 + 1] = K + m;
-    part[t * 3 + 2] = fmaxf(SS - S * m, 0.f);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      S += __shfl_down_sync(0xffffffffu, S, o, 8);
+      SS += __shfl_down_sync(0xffffffffu, SS, o, 8);
+    }
+    if (g < p.groups && l8 == 0) {
+      float npix = 0.f;
+      for (int pl2 = 0; pl2 < p.P; ++pl2) npix += s_cnt[pl2];
+      const float cntg = npix * static_cast<float>(p.cg);
+      const float K = rep_value(g);
+      const float m = cntg > 0.f ? S / cntg : 0.f;
+      part[g * 3 + 0] = cntg;
+      part[g * 3 + 1] = K + m;
+      part[g * 3 + 2] = fmaxf(SS - S * m, 0.f);
+    }
   }
   __threadfence();
   __syncthreads();
@@ -135,14 +147,30 @@ __global__ void group_norm_stats_kernel(const GroupNormParams p) {
     __threadfence();
     // merge the chunk partials of this image: 8 lanes per group take every 8th chunk (fixed order), then a fixed
     // shuffle tree merges the lanes
-    const volatile float* pp = p.partial + static_cast<size_t>(n) * p.chunks * p.groups * 3;
+    const float* pp = p.partial + static_cast<size_t>(n) * p.chunks * p.groups * 3;
     for (int g0 = 0; g0 < p.groups; g0 += blockDim.x / 8) {
       const int g = g0 + t / 8, l8 = t & 7;
       float na = 0.f, ma = 0.f, M2a = 0.f;
       if (g < p.groups) {
-        for (int ch = l8; ch < p.chunks; ch += 8) {
-          const volatile float* q = pp + (static_cast<size_t>(ch) * p.groups + g) * 3;
-          chan_combine(na, ma, M2a, q[0], q[1], q[2]);
+        // 8 chunks per batch: 24 independent L2 loads in flight (ld.global.cg: the partials were written by other
+        // SMs), then Chan merges in the same fixed chunk order as ever
+        for (int ch0 = l8; ch0 < p.chunks; ch0 += 64) {
+          float cb[8], mb[8], Mb[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int ch = ch0 + u * 8;
+            cb[u] = 0.f;
+            mb[u] = 0.f;
+            Mb[u] = 0.f;
+            if (ch < p.chunks) {
+              const float* q = pp + (static_cast<size_t>(ch) * p.groups + g) * 3;
+              cb[u] = __ldcg(q);
+              mb[u] = __ldcg(q + 1);
+              Mb[u] = __ldcg(q + 2);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) chan_combine(na, ma, M2a, cb[u], mb[u], Mb[u]);
         }
       }
 #pragma unroll
@@ -162,61 +190,54 @@ __global__ void group_norm_stats_kernel(const GroupNormParams p) {
   }
 }
 
-// grid (ceil(hw / ppb), batch); 256 threads.  y = act(x * sc[c] + bi[c]) with sc = rstd*gamma,
-// bi = beta - mean*rstd*gamma staged in shared memory.
+// grid (apply_chunks, batch); block V*P threads like the statistics pass: thread (pl, cv) owns 8 fixed channels, keeps
+// their scale = rstd*gamma and bias = beta - mean*rstd*gamma in registers and walks pixels pl, pl+P, ... of its chunk with
+// four 16-byte loads in flight.  y = act(x * scale + bias).
 template <bool FP16>
-__global__ void __launch_bounds__(256) group_norm_apply_kernel(const GroupNormParams p) {
+__global__ void __launch_bounds__(512) group_norm_apply_kernel(const GroupNormParams p) {
   pdl_trigger();
   pdl_wait();
   using H = Half16<FP16>;
-  extern __shared__ float s_scbi[];  // [2][C]
-  float* s_sc = s_scbi;
-  float* s_bi = s_scbi + p.C;
   const int n = blockIdx.y;
+  const int t = threadIdx.x;
+  const int pl = t / p.V, cv = t - pl * p.V;
+  if (pl >= p.P) return;
+  const int pix0 = blockIdx.x * p.apply_ppb;
+  const int pix1 = min(p.hw, pix0 + p.apply_ppb);
   const typename H::T* gamma = static_cast<const typename H::T*>(p.gamma);
   const typename H::T* beta = static_cast<const typename H::T*>(p.beta);
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+  float sc[8], bi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
     const int g = c / p.cg;
     const float mean = p.stats[(static_cast<size_t>(n) * p.groups + g) * 2 + 0];
     const float rstd = p.stats[(static_cast<size_t>(n) * p.groups + g) * 2 + 1];
     const float ga = gamma ? H::to_float(gamma[c]) : 1.f;
     const float be = beta ? H::to_float(beta[c]) : 0.f;
-    s_sc[c] = rstd * ga;
-    s_bi[c] = be - mean * rstd * ga;
+    sc[j] = rstd * ga;
+    bi[j] = be - mean * rstd * ga;
   }
-  __syncthreads();
-  const int pix0 = blockIdx.x * p.apply_ppb;
-  const int npix = min(p.apply_ppb, p.hw - pix0);
-  const typename H::T* x0 = static_cast<const typename H::T*>(p.x[0]) + (static_cast<size_t>(n) * p.hw + pix0) * p.ldx[0];
-  const typename H::T* x1 =
-      p.x[1] ? static_cast<const typename H::T*>(p.x[1]) + (static_cast<size_t>(n) * p.hw + pix0) * p.ldx[1] : nullptr;
-  typename H::T* y = static_cast<typename H::T*>(p.y) + (static_cast<size_t>(n) * p.hw + pix0) * p.ldy;
-  const int total = npix * p.V;
+  const int src = cv < p.V0 ? 0 : 1;
+  const int ld = p.ldx[src];
+  const typename H::T* xb = static_cast<const typename H::T*>(p.x[src]) + (static_cast<size_t>(n) * p.hw) * ld +
+                            (src == 0 ? cv : cv - p.V0) * 8;
+  typename H::T* yb = static_cast<typename H::T*>(p.y) + (static_cast<size_t>(n) * p.hw) * p.ldy + cv * 8;
   const bool do_silu = p.act == ACT_SILU;
-  auto src_of = [&](int i) -> const typename H::T* {
-    const int pix = i / p.V;
-    const int cv = i - pix * p.V;
-    return cv < p.V0 ? x0 + static_cast<size_t>(pix) * p.ldx[0] + cv * 8
-                     : x1 + static_cast<size_t>(pix) * p.ldx[1] + (cv - p.V0) * 8;
-  };
-  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+  const int step = p.P;
+  for (int pix = pix0 + pl; pix < pix1; pix += 4 * step) {
     uint4 u[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * blockDim.x;
-      if (i < total) u[k] = *reinterpret_cast<const uint4*>(src_of(i));
-    }
+    for (int k = 0; k < 4; ++k)
+      if (pix + k * step < pix1) u[k] = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pix + k * step) * ld);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * blockDim.x;
-      if (i < total) {
-        const int pix = i / p.V;
-        const int cb = (i - pix * p.V) * 8;
+      if (pix + k * step < pix1) {
         float2 a = H::unpack(u[k].x), b = H::unpack(u[k].y), c = H::unpack(u[k].z), d = H::unpack(u[k].w);
         float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float o = fmaf(v[j], s_sc[cb + j], s_bi[cb + j]);
+          const float o = fmaf(v[j], sc[j], bi[j]);
           v[j] = do_silu ? silu_f(o) : o;
         }
         uint4 o;
@@ -224,7 +245,7 @@ __global__ void __launch_bounds__(256) group_norm_apply_kernel(const GroupNormPa
         o.y = H::pack(v[2], v[3]);
         o.z = H::pack(v[4], v[5]);
         o.w = H::pack(v[6], v[7]);
-        *reinterpret_cast<uint4*>(y + static_cast<size_t>(pix) * p.ldy + cb) = o;
+        *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pix + k * step) * p.ldy) = o;
       }
     }
   }
@@ -476,7 +497,7 @@ int b200_group_norm(const b200_group_norm_args* a, void* stream) {
   p.y = a->y;
   p.ldy = a->ldy;
   gn_plan(a->batch, a->hw, C, &p.chunks, &p.ppc);
-  B200_CHECK_ARG(p.V <= 1024, "group_norm: C=%d too large", C);
+  B200_CHECK_ARG(p.V <= 512, "group_norm: C=%d too large (<= 4096)", C);
   p.P = 512 / p.V;
   if (p.P < 1) p.P = 1;
   if (p.P > 64) p.P = 64;
@@ -489,11 +510,12 @@ int b200_group_norm(const b200_group_norm_args* a, void* stream) {
   p.stats = ws + 1024;
   p.partial = p.stats + static_cast<size_t>(a->batch) * a->groups * 2;
   {
-    // ~8 CTAs per SM for the apply pass, at least 8 pixels each so the per-CTA scale/bias prologue amortises
+    // ~4 CTAs per SM for the apply pass, every pixel lane of a CTA gets at least 4 pixels (the per-thread scale/bias
+    // prologue amortises over them)
     long long total = static_cast<long long>(a->batch) * a->hw;
-    long long ppb = (total + 8LL * num_sms() - 1) / (8LL * num_sms());
-    if (ppb < 8) ppb = 8;
-    if (ppb > 1024) ppb = 1024;
+    long long ppb = (total + 4LL * num_sms() - 1) / (4LL * num_sms());
+    if (ppb < 4LL * p.P) ppb = 4LL * p.P;
+    if (ppb > a->hw) ppb = a->hw;
     p.apply_ppb = static_cast<int>(ppb);
   }
 
@@ -519,11 +541,11 @@ int b200_group_norm(const b200_group_norm_args* a, void* stream) {
   }
   {
     dim3 grid((a->hw + p.apply_ppb - 1) / p.apply_ppb, a->batch);
-    size_t smem = static_cast<size_t>(C) * 2 * sizeof(float);
+    int threads = (p.V * p.P + 31) / 32 * 32;
     if (fp16)
-      launch_pdl(group_norm_apply_kernel<true>, dim3(grid), dim3(256), smem, st, p);
+      launch_pdl(group_norm_apply_kernel<true>, dim3(grid), dim3(threads), 0, st, p);
     else
-      launch_pdl(group_norm_apply_kernel<false>, dim3(grid), dim3(256), smem, st, p);
+      launch_pdl(group_norm_apply_kernel<false>, dim3(grid), dim3(threads), 0, st, p);
     return check_launch("group_norm_apply_kernel");
   }
 }

@@ -1,4 +1,3 @@
-mkdir -p gpurun_out
-echo "=== sched test"; timeout 100 python -m pytest tests/test_pipelines_gpu.py -x -q -k scheduler 2>&1 | tail -2
-echo "=== breakdown"; timeout 300 python tools/pipeline_breakdown.py 2>&1 | tail -6
-echo "=== bench"; timeout 600 python bench.py > gpurun_out/bench_r1e.json 2> gpurun_out/bench_r1e.err; tail -c 3000 gpurun_out/bench_r1e.json; tail -3 gpurun_out/bench_r1e.err
+echo "=== gn/ln tests"; timeout 200 python -m pytest tests/test_kernels_gpu.py -x -q -k "gn or ln or group_norm" 2>&1 | tail -4
+echo "=== models"; timeout 300 python -m pytest tests/test_models_gpu.py -x -q 2>&1 | tail -3
+echo "=== full unet"; timeout 200 python tools/diag_models.py full_unet full_vae 2>&1 | tail -7
