@@ -14,6 +14,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_common.h"
 
@@ -302,13 +304,15 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
       }
 
       // exp2(S*sc - m): three of four on MUFU, one on the FMA pipes (ex2_poly); pairs packed to 16 bit
-      auto exps32 = [&](const uint32_t (&src)[32], uint32_t* dst, int col0) {
+      // (the ragged-tail masking is compiled out of the full-block path: as predicated compares/selects it cost two
+      // instructions per score in EVERY block, a third of the loop)
+      auto exps32 = [&](auto masked, const uint32_t (&src)[32], uint32_t* dst, int col0) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           float p0 = ex2_approx(fmaf(__uint_as_float(src[2 * k]), sc, -m));
           float p1 = (k & 1) ? ex2_poly(fmaf(__uint_as_float(src[2 * k + 1]), sc, -m))
                              : ex2_approx(fmaf(__uint_as_float(src[2 * k + 1]), sc, -m));
-          if (partial) {
+          if constexpr (decltype(masked)::value) {
             if (col0 + 2 * k >= kv_left) p0 = 0.f;
             if (col0 + 2 * k + 1 >= kv_left) p1 = 0.f;
           }
@@ -316,10 +320,17 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
           dst[k] = H::pack(p0, p1);
         }
       };
+      using Masked = std::integral_constant<bool, true>;
+      using Full = std::integral_constant<bool, false>;
       {
         uint32_t pk[32];
-        exps32(a1, pk, 64);
-        exps32(b1, pk + 16, 96);
+        if (partial) {
+          exps32(Masked{}, a1, pk, 64);
+          exps32(Masked{}, b1, pk + 16, 96);
+        } else {
+          exps32(Full{}, a1, pk, 64);
+          exps32(Full{}, b1, pk + 16, 96);
+        }
         tmem_st32(s_t + 64 + 32, pk);  // P columns of kv 64..127
       }
       tmem_ld32(s_t + 0, a1);
@@ -327,8 +338,13 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
       tmem_wait_ld();
       {
         uint32_t pk[32];
-        exps32(a1, pk, 0);
-        exps32(b1, pk + 16, 32);
+        if (partial) {
+          exps32(Masked{}, a1, pk, 0);
+          exps32(Masked{}, b1, pk + 16, 32);
+        } else {
+          exps32(Full{}, a1, pk, 0);
+          exps32(Full{}, b1, pk + 16, 32);
+        }
         tmem_st32(s_t + 64, pk);  // P columns of kv 0..63
       }
       tmem_wait_st();

@@ -1,3 +1,3 @@
-echo "=== gn/ln tests"; timeout 200 python -m pytest tests/test_kernels_gpu.py -x -q -k "gn or ln or group_norm" 2>&1 | tail -4
-echo "=== models"; timeout 300 python -m pytest tests/test_models_gpu.py -x -q 2>&1 | tail -3
-echo "=== full unet"; timeout 200 python tools/diag_models.py full_unet full_vae 2>&1 | tail -7
+echo "=== attn tests"; timeout 200 python -m pytest tests/test_kernels_gpu.py -x -q -k "attn or attention" 2>&1 | tail -3
+echo "=== attn bench"; timeout 120 python tools/bench_attention.py 2>&1 | tail -6
+echo "=== full unet"; timeout 200 python tools/diag_models.py full_unet 2>&1 | tail -4
