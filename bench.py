@@ -114,12 +114,23 @@ def cpu_reference(args, full=True):
     t0 = time.time()
 
     def probe(dt):
+        # the op mix of the block (3x3 conv, token GEMM, attention) at reduced size; a GEMM alone is misleading: hosts
+        # with a fast bf16 GEMM can still run bf16 convolutions / attention several times slower than fp32
+        import torch.nn.functional as F
+        xc, wc = torch.randn(2, 320, 32, 32).to(dt), torch.randn(320, 320, 3, 3).to(dt)
         a, b = torch.randn(2048, 1280).to(dt), torch.randn(1280, 1280).to(dt)
-        a @ b
-        t = time.perf_counter()
-        for _ in range(3):
+        q = torch.randn(2, 20, 1024, 64).to(dt)
+
+        def once():
+            F.conv2d(xc, wc, padding=1)
             a @ b
-        return (time.perf_counter() - t) / 3
+            F.scaled_dot_product_attention(q, q, q)
+
+        once()
+        t = time.perf_counter()
+        for _ in range(2):
+            once()
+        return (time.perf_counter() - t) / 2
 
     dt = torch.bfloat16 if probe(torch.bfloat16) < probe(torch.float32) else torch.float32
     spec = {k[len("mid_block."):]: v for k, v in specs.unet2d_condition_params(specs.SDXL_UNET_CONFIG).items() if k.startswith("mid_block.")}
@@ -191,7 +202,18 @@ def gemm_roofline(unet, B2, pk):
     flops = sum(p[2] for p in prof)
     total_ms = sum(ms)
     ach = flops / (total_ms * 1e-3) / 1e12
-    return dict(bound="tensor", achieved=round(ach, 1), peak=pk["tflops"], unit="TFLOP/s", frac=round(ach / pk["tflops"], 4), traffic=None,
+    # DRAM traffic of the kernel's most frequent launch (linear 2048x1280x1280 + bias + residual, 192 per forward) from the
+    # committed `ncu --set full` capture; its algorithmic bytes are x 5.24 MB + W 3.28 MB + residual 5.24 MB read (the
+    # 5.24 MB output stays in L2) = 13.77 MB, i.e. no re-reads reach HBM
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_conv_gemm_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            cap = json.load(f)["launches"][0]
+        traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+        traffic_note = f"bytes per launch of '{cap['launch']}' (ncu --set full capture, profiles/r1_ncu_full_hot_kernels.txt); algorithmic 13.77e6"
+    return dict(bound="tensor", achieved=round(ach, 1), peak=pk["tflops"], unit="TFLOP/s", frac=round(ach / pk["tflops"], 4), traffic=traffic,
+                traffic_note=traffic_note,
                 kernel="conv_gemm_kernel", launches_per_forward=len(prof), algorithmic_flop_per_forward=flops,
                 avg_launch_us=round(1000 * total_ms / len(prof), 2), kernel_ms_per_forward=round(total_ms, 3),
                 forward_ms_eager=round(e0.elapsed_time(e1), 3), share_of_forward=round(total_ms / e0.elapsed_time(e1), 3),
