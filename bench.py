@@ -220,6 +220,49 @@ def gemm_roofline(unet, B2, pk):
                 peak_source=pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)")
 
 
+def hbm_kernel_rooflines(dev, dt, pk):
+    """The HBM-bound kernels of the path at their dominant SDXL shapes: 16 launches inside one CUDA graph
+    over 8 rotating buffers (168 MB > L2, so the reads really come from HBM), algorithmic bytes = one read + one write of
+    the activation, against the measured copy bandwidth."""
+    from diffusers_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(0)
+    out = []
+
+    def timed(fn, n=16):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for i in range(n):
+                fn(i)
+        gr.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return 1000.0 * e0.elapsed_time(e1) / n
+
+    xs = [torch.randn(2 * 16384, 320, generator=g, device=dev).to(dt) for _ in range(8)]
+    ys = [torch.empty_like(x) for x in xs]
+    gam, bet = torch.randn(320, generator=g, device=dev).to(dt), torch.randn(320, generator=g, device=dev).to(dt)
+    us = timed(lambda i: ops.group_norm(xs[i % 8], batch=2, hw=16384, groups=32, eps=1e-5, gamma=gam, beta=bet, silu=True, out=ys[i % 8]))
+    nbytes = 2 * xs[0].numel() * 2
+    out.append(dict(kernel="group_norm_stats+apply (+SiLU)", shape="2x16384x320", algorithmic_bytes=nbytes, us=round(us, 2),
+                    achieved_gbs=round(nbytes / us / 1e3, 1), frac=round(nbytes / us / 1e3 / pk["hbm_gbs"], 4),
+                    note="two launches; the statistics pass re-reads the input (3 passes over 21 MB for 2 algorithmic)"))
+    xl = [torch.randn(2048, 1280, generator=g, device=dev).to(dt) for _ in range(32)]
+    yl = [torch.empty_like(x) for x in xl]
+    lg, lb = torch.randn(1280, generator=g, device=dev).to(dt), torch.randn(1280, generator=g, device=dev).to(dt)
+    us = timed(lambda i: ops.layer_norm(xl[i % 32], eps=1e-5, gamma=lg, beta=lb, out=yl[i % 32]), n=32)
+    nbytes = 2 * xl[0].numel() * 2
+    out.append(dict(kernel="layer_norm", shape="2048x1280", algorithmic_bytes=nbytes, us=round(us, 2), achieved_gbs=round(nbytes / us / 1e3, 1),
+                    frac=round(nbytes / us / 1e3 / pk["hbm_gbs"], 4), note="10 MB per launch: launch-latency bound"))
+    return out
+
+
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from diffusers_b200 import ops, parallel, specs
@@ -303,6 +346,10 @@ def run_b200(args, rank, world, local_rank):
                                      frac_of_peak=round(value / world * flops_per_img / 1e12 / pk["tflops"], 4)))
         if cb is not None:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        try:
+            line["hbm_kernels"] = hbm_kernel_rooflines(dev, dt, pk)
+        except Exception as e:  # noqa: BLE001  (a side measurement must never cost the headline line)
+            line["hbm_kernels"] = f"failed: {e}"
         print(json.dumps(line), flush=True)
 
 
@@ -376,9 +423,63 @@ def run_flux(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_vae(args, rank, world, local_rank):
+    """BASELINE.json configs[4]: AutoencoderKL.decode (SDXL decoder, 49.5 M params) of z (B,4,128,128) -> (B,3,1024,1024),
+    batch sweep 1 / 8 / 64 - the convolution-roofline view of the path (10.47 TFLOP per image)."""
+    from diffusers_b200 import ops
+    from diffusers_b200.autoencoder_kl import AutoencoderKL
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dt = torch.bfloat16
+    pk = peaks()
+    vae = AutoencoderKL.random_init(seed=0, dtype=dt, device=dev)
+    sweep, line = {}, None
+    with ClockSampler(local_rank) as cs:
+        for B in (1, 8, 64):
+            g = torch.Generator().manual_seed(B)
+            zh = torch.randn(B, 4, 128, 128, generator=g).to(dt).pin_memory()
+            z = zh.to(dev)
+            for _ in range(max(1, args.warmup if B < 64 else 1)):
+                vae.decode(z, return_dict=False)
+            torch.cuda.synchronize()
+            n = max(1, args.steps if B < 64 else min(args.steps, 2))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = ops.launches()
+            e0.record()
+            for _ in range(n):
+                img = vae.decode(z, return_dict=False)[0]
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            launches = (ops.launches() - n0) // n
+            host_out = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
+            e0.record()
+            for _ in range(n):
+                host_out.copy_(vae.decode(zh.to(dev, non_blocking=True), return_dict=False)[0], non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / n
+            sweep[B] = dict(images_per_s=round(B / (ms * 1e-3), 2), ms_per_batch=round(ms, 2), e2e_images_per_s=round(B / (ms2 * 1e-3), 2),
+                            tflops=round(B * VAE_FLOP_PER_IMAGE / (ms * 1e-3) / 1e12, 1), launches=launches)
+            del img, host_out, z
+    best = max(sweep, key=lambda b: sweep[b]["images_per_s"])
+    v = sweep[best]
+    line = dict(metric="images/sec @ AutoencoderKL.decode 1024^2 (SDXL VAE)", value=v["images_per_s"], unit="images/s", n_gpus=1, steps=args.steps,
+                warmup=args.warmup, ms_per_step=v["ms_per_batch"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                data="synthetic (random-init weights, N(0,1) latents)",
+                config=dict(workload=f"sdxl_vae_decode_1024_b{best}", sweep={str(k): s for k, s in sweep.items()},
+                            l2="activations of one image (268 MB per 128-channel 1024^2 tensor) >> L2"),
+                e2e=dict(value=v["e2e_images_per_s"], unit="images/s", h2d_bytes_per_step=best * 4 * 128 * 128 * 2,
+                         d2h_bytes_per_step=best * 3 * 1024 * 1024 * 2),
+                gpu_launches=v["launches"], clocks=cs.summary(),
+                model_flops=dict(tflop_per_image=round(VAE_FLOP_PER_IMAGE / 1e12, 2), achieved_tflops=v["tflops"],
+                                 frac_of_peak=round(v["tflops"] / pk["tflops"], 4), peak=pk["tflops"]))
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="sdxl", choices=["sdxl", "flux"])
+    ap.add_argument("--workload", default="sdxl", choices=["sdxl", "flux", "vae"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
@@ -401,6 +502,8 @@ def main():
     try:
         if args.workload == "flux":
             run_flux(args, rank, world, local_rank)
+        elif args.workload == "vae":
+            run_vae(args, rank, world, local_rank)
         else:
             run_b200(args, rank, world, local_rank)
     finally:

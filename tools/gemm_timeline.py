@@ -47,7 +47,9 @@ for rep in range(2):
     d = d[d[:, 7] > 0]
     if rep == 0:
         continue
-    print(f"mode {mode}: {d.shape[0]} CTAs; medians of (t_i - t_entry) in cycles:")
+    span = int(d[:, 7].max() - d[:, 0].min())
+    print(f"mode {mode}: {d.shape[0]} CTAs; first entry -> last exit {span} cycles (clock64 is per SM: indicative only); "
+          f"medians of (t_i - t_entry) in cycles:")
     for i in range(1, 16):
         v = (d[:, i] - d[:, 0]).float()
         v = v[d[:, i] > 0]
