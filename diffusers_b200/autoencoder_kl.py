@@ -13,6 +13,7 @@ import types
 import torch
 
 from . import ops, packing, specs
+from .checkpoint import FromPretrainedMixin
 from .config import FrozenConfig
 
 
@@ -21,7 +22,20 @@ class DecoderOutput:
         self.sample = sample
 
 
-class AutoencoderKL(torch.nn.Module):
+class AutoencoderKL(torch.nn.Module, FromPretrainedMixin):
+    _ref_class_names = ("AutoencoderKL",)
+
+    @classmethod
+    def _param_spec(cls, cfg):
+        full = dict(specs.SDXL_VAE_CONFIG)
+        full.update(cfg)
+        return specs.vae_decoder_params(full)  # the encoder half of the checkpoint is not on the path
+
+    @staticmethod
+    def _fix_keys(sd):
+        from .checkpoint import convert_deprecated_attention_keys
+        return convert_deprecated_attention_keys(sd)
+
     def __init__(self, config, state_dict, dtype=torch.bfloat16, device="cuda"):
         super().__init__()
         cfg = dict(specs.SDXL_VAE_CONFIG)

@@ -11,6 +11,8 @@ the north-star benchmark feeds them.
 of the NHWC UNet forward plus ONE fused CFG + Euler + next-input kernel per step, no per-step layout changes.
 `fused=False` drives the drop-in `unet.forward` / `scheduler.step` API exactly like the reference loop.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -48,6 +50,19 @@ class PipelineOutput:
 
 
 class StableDiffusionXLPipeline:
+    @classmethod
+    def from_pretrained(cls, path, torch_dtype=torch.bfloat16, device="cuda", variant=None):
+        """A reference `StableDiffusionXLPipeline.save_pretrained` directory -> this pipeline (unet/, vae/, scheduler/;
+        the text encoders / tokenizers are not on the path: call with prompt_embeds).  checkpoint.py, SURVEY.md 8f N1."""
+        from . import checkpoint
+        from .autoencoder_kl import AutoencoderKL
+        from .schedulers import EulerDiscreteScheduler
+        from .unet_2d_condition import UNet2DConditionModel
+        c = checkpoint.load_pipeline_components(path, "StableDiffusionXLPipeline",
+                                                dict(unet=UNet2DConditionModel, vae=AutoencoderKL, scheduler=EulerDiscreteScheduler),
+                                                torch_dtype=torch_dtype, device=device, variant=variant)
+        return cls(c["vae"], c["unet"], c["scheduler"])
+
     def __init__(self, vae, unet, scheduler):
         self.vae, self.unet, self.scheduler = vae, unet, scheduler
         self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
@@ -189,6 +204,21 @@ def calculate_shift(image_seq_len, base_seq_len=256, max_seq_len=4096, base_shif
 
 
 class FluxPipeline:
+    @classmethod
+    def from_pretrained(cls, path, torch_dtype=torch.bfloat16, device="cuda", variant=None):
+        """A reference `FluxPipeline.save_pretrained` directory -> this pipeline (transformer/, vae/ config for the latent
+        geometry, scheduler/); output_type='latent' only, prompt embeddings in."""
+        from . import checkpoint
+        from .config import FrozenConfig
+        from .schedulers import FlowMatchEulerDiscreteScheduler
+        from .transformer_flux import FluxTransformer2DModel
+        c = checkpoint.load_pipeline_components(path, "FluxPipeline",
+                                                dict(transformer=FluxTransformer2DModel, scheduler=FlowMatchEulerDiscreteScheduler),
+                                                torch_dtype=torch_dtype, device=device, variant=variant)
+        vae_cfg = checkpoint.public_config(checkpoint.load_config(os.path.join(path, "vae")))
+        vae = type("VaeGeometry", (), dict(config=FrozenConfig(vae_cfg)))()
+        return cls(c["scheduler"], vae, c["transformer"])
+
     def __init__(self, scheduler, vae, transformer):
         self.scheduler, self.vae, self.transformer = scheduler, vae, transformer
         self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
@@ -269,6 +299,15 @@ class FluxPipeline:
 class DDPMPipeline:
     """pipelines/ddpm/pipeline_ddpm.py:55-139 (BASELINE.json config 0): ancestral sampling with a fresh noise draw from
     the caller's generator every step."""
+
+    @classmethod
+    def from_pretrained(cls, path, torch_dtype=torch.bfloat16, device="cuda"):
+        from . import checkpoint
+        from .schedulers import DDPMScheduler
+        from .unet_2d import UNet2DModel
+        c = checkpoint.load_pipeline_components(path, "DDPMPipeline", dict(unet=UNet2DModel, scheduler=DDPMScheduler),
+                                                torch_dtype=torch_dtype, device=device)
+        return cls(c["unet"], c["scheduler"])
 
     def __init__(self, unet, scheduler):
         self.unet, self.scheduler = unet, scheduler

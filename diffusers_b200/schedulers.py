@@ -23,6 +23,17 @@ class SchedulerOutput:
 
 
 class EulerDiscreteScheduler:
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None):
+        """Constructor arguments from the reference's scheduler_config.json (schedulers/scheduling_utils.py:100)."""
+        from .checkpoint import scheduler_from_pretrained
+        return scheduler_from_pretrained(cls, path, subfolder)
+
+    @classmethod
+    def from_config(cls, config):
+        from .checkpoint import scheduler_kwargs
+        return cls(**scheduler_kwargs(cls, config))
+
     order = 1
     init_noise_sigma_is_tensor = True
 
@@ -94,7 +105,7 @@ class EulerDiscreteScheduler:
             ts -= 1
         else:
             raise ValueError(c.timestep_spacing)
-        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig)), sig)
         sig = np.concatenate([sig, [0]]).astype(np.float32)
         self.sigmas = torch.from_numpy(sig).to(dtype=torch.float32)  # stays on the host, like the reference (:481)
@@ -141,6 +152,17 @@ class EulerDiscreteScheduler:
 
 
 class FlowMatchEulerDiscreteScheduler:
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None):
+        """Constructor arguments from the reference's scheduler_config.json (schedulers/scheduling_utils.py:100)."""
+        from .checkpoint import scheduler_from_pretrained
+        return scheduler_from_pretrained(cls, path, subfolder)
+
+    @classmethod
+    def from_config(cls, config):
+        from .checkpoint import scheduler_kwargs
+        return cls(**scheduler_kwargs(cls, config))
+
     order = 1
 
     def __init__(self, num_train_timesteps=1000, shift=1.0, use_dynamic_shifting=False, base_shift=0.5, max_shift=1.15,
@@ -249,6 +271,17 @@ class FlowMatchEulerDiscreteScheduler:
 
 
 class DDPMScheduler:
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None):
+        """Constructor arguments from the reference's scheduler_config.json (schedulers/scheduling_utils.py:100)."""
+        from .checkpoint import scheduler_from_pretrained
+        return scheduler_from_pretrained(cls, path, subfolder)
+
+    @classmethod
+    def from_config(cls, config):
+        from .checkpoint import scheduler_kwargs
+        return cls(**scheduler_kwargs(cls, config))
+
     """schedulers/scheduling_ddpm.py:137 (epsilon prediction, fixed_small variance, clip_sample): host tables are the
     reference's torch ops, `step` is one fused kernel; the noise is drawn with the caller's generator exactly like
     `randn_tensor` (utils/torch_utils.py:183) so the RNG stream is consumed identically."""
@@ -258,8 +291,10 @@ class DDPMScheduler:
     def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
                  variance_type="fixed_small", clip_sample=True, prediction_type="epsilon", clip_sample_range=1.0,
                  timestep_spacing="leading", steps_offset=0, **unsupported):
+        # the reference serialises every constructor default; these two only act when `thresholding` is on
+        inert = dict(dynamic_thresholding_ratio=0.995, sample_max_value=1.0)
         for k, v in unsupported.items():
-            if v not in (None, False):
+            if v not in (None, False) and inert.get(k) != v:
                 raise NotImplementedError(f"DDPMScheduler option {k}={v!r} is outside the hot path")
         if prediction_type != "epsilon" or variance_type != "fixed_small":
             raise NotImplementedError("only epsilon prediction with fixed_small variance")

@@ -17,6 +17,7 @@ import contextlib
 import torch
 
 from . import ops, packing, specs
+from .checkpoint import FromPretrainedMixin
 from .config import FrozenConfig
 from .ops import ACT_GELU_TANH, ACT_SILU
 
@@ -26,7 +27,15 @@ class Transformer2DModelOutput:
         self.sample = sample
 
 
-class FluxTransformer2DModel(torch.nn.Module):
+class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
+    _ref_class_names = ("FluxTransformer2DModel",)
+
+    @classmethod
+    def _param_spec(cls, cfg):
+        full = dict(specs.FLUX_DEV_CONFIG)
+        full.update(cfg)
+        return specs.flux_params(full)
+
     def __init__(self, config, state_dict, dtype=torch.bfloat16, device="cuda"):
         super().__init__()
         cfg = dict(specs.FLUX_DEV_CONFIG)

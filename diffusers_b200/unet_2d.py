@@ -9,6 +9,7 @@ the residual in its epilogue.  attention_head_dim must be 64 or 128 (the fused k
 import torch
 
 from . import ops, packing, specs
+from .checkpoint import FromPretrainedMixin
 from .config import FrozenConfig
 from .ops import ACT_SILU
 
@@ -18,7 +19,15 @@ class UNet2DOutput:
         self.sample = sample
 
 
-class UNet2DModel(torch.nn.Module):
+class UNet2DModel(torch.nn.Module, FromPretrainedMixin):
+    _ref_class_names = ("UNet2DModel",)
+
+    @classmethod
+    def _param_spec(cls, cfg):
+        full = dict(specs.DDPM_TINY_CONFIG)
+        full.update(cfg)
+        return specs.unet2d_params(full)
+
     def __init__(self, config, state_dict, dtype=torch.bfloat16, device="cuda"):
         super().__init__()
         cfg = dict(specs.DDPM_TINY_CONFIG)

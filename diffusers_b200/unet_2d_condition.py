@@ -13,6 +13,7 @@ import types
 import torch
 
 from . import ops, packing, specs
+from .checkpoint import FromPretrainedMixin
 from .config import FrozenConfig
 from .ops import ACT_NONE, ACT_SILU
 
@@ -26,7 +27,15 @@ class UNet2DConditionOutput:
         self.sample = sample
 
 
-class UNet2DConditionModel(torch.nn.Module):
+class UNet2DConditionModel(torch.nn.Module, FromPretrainedMixin):
+    _ref_class_names = ("UNet2DConditionModel",)
+
+    @classmethod
+    def _param_spec(cls, cfg):
+        full = dict(specs.SDXL_UNET_CONFIG)
+        full.update(cfg)
+        return specs.unet2d_condition_params(full)
+
     _supports_cuda_graph = True
 
     def __init__(self, config, state_dict, dtype=torch.bfloat16, device="cuda"):

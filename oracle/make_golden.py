@@ -262,6 +262,62 @@ def gen_pipelines(d):
     torch.save(out, os.path.join(OUT, "pipelines.pt"))
 
 
+MICRO_UNET = dict(sample_size=16, block_out_channels=(64, 64), down_block_types=("DownBlock2D", "CrossAttnDownBlock2D"),
+                  up_block_types=("CrossAttnUpBlock2D", "UpBlock2D"), layers_per_block=1, cross_attention_dim=64,
+                  transformer_layers_per_block=1, attention_head_dim=(1, 1), addition_time_embed_dim=32,
+                  projection_class_embeddings_input_dim=256)
+MICRO_VAE = dict(block_out_channels=(32, 32), down_block_types=("DownEncoderBlock2D",) * 2, up_block_types=("UpDecoderBlock2D",) * 2,
+                 layers_per_block=1, sample_size=32)
+
+
+def gen_checkpoints(d):
+    """tests/golden/ckpt_sdxl_micro/: a pipeline directory written by the REFERENCE's own `save_pretrained` (bf16
+    safetensors + config.json + scheduler_config.json + model_index.json) plus the reference pipeline's fp32 output for it:
+    what `from_pretrained` of the shells must load."""
+    import shutil
+    ucfg = dict(specs.SDXL_UNET_CONFIG)
+    ucfg.update(MICRO_UNET)
+    vcfg = dict(specs.SDXL_VAE_CONFIG)
+    vcfg.update(MICRO_VAE)
+    torch.manual_seed(21)
+    unet = d.UNet2DConditionModel(**ucfg).eval()
+    vae = d.AutoencoderKL(**vcfg).eval()
+    with torch.no_grad():  # default init leaves the zero-initialised / tiny tensors uninteresting: redraw everything
+        g = torch.Generator().manual_seed(22)
+        for m in (unet, vae):
+            for n_, p_ in m.named_parameters():
+                if p_.dim() >= 2:
+                    p_.copy_(torch.randn(p_.shape, generator=g) * (1.0 / max(1, p_[0].numel())) ** 0.5)
+                elif n_.endswith("weight"):
+                    p_.copy_(1.0 + 0.1 * torch.randn(p_.shape, generator=g))
+                else:
+                    p_.copy_(0.1 * torch.randn(p_.shape, generator=g))
+    unet, vae = unet.to(torch.bfloat16), vae.to(torch.bfloat16)
+    skw = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="leading", steps_offset=1)
+    pipe = d.StableDiffusionXLPipeline(vae=vae, text_encoder=None, text_encoder_2=None, tokenizer=None, tokenizer_2=None,
+                                       unet=unet, scheduler=d.EulerDiscreteScheduler(**skw), add_watermarker=False)
+    root = os.path.join(OUT, "ckpt_sdxl_micro")
+    shutil.rmtree(root, ignore_errors=True)
+    pipe.save_pretrained(root, safe_serialization=True)
+    # the fp32 run of the very same (bf16-valued) weights is the ground truth; the bf16 eager run is the error yardstick
+    g = torch.Generator().manual_seed(12)
+    pe, npe = torch.randn(1, 77, 64, generator=g), torch.randn(1, 77, 64, generator=g)
+    pool, npool = torch.randn(1, 64, generator=g), torch.randn(1, 64, generator=g)
+    kw = dict(prompt_embeds=pe, negative_prompt_embeds=npe, pooled_prompt_embeds=pool, negative_pooled_prompt_embeds=npool,
+              height=32, width=32, num_inference_steps=3, guidance_scale=5.0)
+    pipe.set_progress_bar_config(disable=True)
+    lat0 = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(0))
+    img16 = pipe(latents=lat0.bfloat16(), output_type="pt", **{k: (v.bfloat16() if torch.is_tensor(v) else v) for k, v in kw.items()}).images
+    pipe32 = d.StableDiffusionXLPipeline(vae=vae.float(), text_encoder=None, text_encoder_2=None, tokenizer=None, tokenizer_2=None,
+                                         unet=unet.float(), scheduler=d.EulerDiscreteScheduler(**skw), add_watermarker=False)
+    pipe32.set_progress_bar_config(disable=True)
+    img32 = pipe32(latents=lat0.bfloat16().float(), output_type="pt", **kw).images
+    torch.save(dict(call={k: v for k, v in kw.items()}, latents=lat0.bfloat16(), image_fp32=img32, image_bf16=img16.float()),
+               os.path.join(root, "expected.pt"))
+    n = sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(root) for f in fs)
+    print("ckpt_sdxl_micro", n // 1024, "KiB;", "bf16-vs-fp32 max", float((img16.float() - img32).abs().max()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)

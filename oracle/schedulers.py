@@ -64,7 +64,7 @@ class EulerDiscrete:
             ts -= 1
         else:
             raise ValueError(self.spacing)
-        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig)), sig)
         self.sigmas = torch.from_numpy(np.concatenate([sig, [0]]).astype(np.float32))
         self.timesteps = torch.from_numpy(ts.astype(np.float32))

@@ -147,3 +147,25 @@ def test_ddpm_pipeline_config0(golden):
     for _ in range(fx["steps"] - 1):  # t > 0 draws one noise tensor per step; the last step (t = 0) draws none
         torch.randn((1, 3, 32, 32), generator=g2)
     assert torch.equal(g.get_state(), g2.get_state())
+
+
+def test_sdxl_pipeline_from_reference_checkpoint():
+    """tests/golden/ckpt_sdxl_micro: a directory written by the reference's StableDiffusionXLPipeline.save_pretrained (bf16
+    safetensors) together with the reference pipeline's fp32 and bf16-eager images for it (oracle/make_golden.py
+    checkpoints).  from_pretrained of the shells + one sampling run; the bound is the reference's own bf16 error."""
+    import os
+    from diffusers_b200.pipelines import StableDiffusionXLPipeline
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ckpt_sdxl_micro")
+    exp = torch.load(os.path.join(root, "expected.pt"), weights_only=False)
+    pipe = StableDiffusionXLPipeline.from_pretrained(root)
+    assert pipe.unet.device.type == "cuda" and pipe.unet.dtype == torch.bfloat16
+    call = {k: (v.bfloat16() if torch.is_tensor(v) else v) for k, v in exp["call"].items()}
+    ref_err = (exp["image_bf16"] - exp["image_fp32"]).abs()
+    for fused in (True, False):
+        img = pipe(latents=exp["latents"], output_type="pt", fused=fused, **call).images
+        e = (img.float().cpu() - exp["image_fp32"]).abs()
+        print(f"checkpoint pipeline fused={fused}: image err max {float(e.max()):.4g} mean {float(e.mean()):.4g} | "
+              f"reference bf16 eager max {float(ref_err.max()):.4g} mean {float(ref_err.mean()):.4g}")
+        assert tuple(img.shape) == tuple(exp["image_fp32"].shape)
+        assert float(e.mean()) <= 1.5 * float(ref_err.mean()) + 2e-3
+        assert float(e.max()) <= 2.0 * float(ref_err.max()) + 2e-2
