@@ -1,14 +1,18 @@
 // b200_conv_gemm: implicit-GEMM convolution / linear layer on tcgen05 tensor cores.
 //
-//   persistent CTAs (one per SM), 8 warps:
-//     warp 0      TMA producer   : per 64-wide K chunk, one 4-D box of NHWC pixels (the im2col
-//                                  row block, staged 128B-swizzled in shared memory; halo pixels
-//                                  are zero-filled by TMA out-of-bounds handling) + one 2-D box of
-//                                  packed weights
-//     warp 1      MMA issuer     : tcgen05.mma 128 x BN x 16, fp32 accumulators in TMEM,
-//                                  double-buffered across tiles
-//     warp 2      TMEM allocator
-//     warps 4..7  epilogue       : tcgen05.ld -> bias/act/gate/rowvec/residual (or GEGLU) -> 16 B stores
+//   persistent CTAs (one per SM), 12 warps; two CTAs of a cluster normally work as a PAIR on two consecutive m tiles
+//   (cta_group::2: one 256 x BN MMA issued by the leader, each CTA stages its own A rows and HALF of the weight tile):
+//     warp 0       TMA producer    : per 64-wide K chunk, one 4-D box of NHWC pixels (the im2col row block, staged
+//                                    128B-swizzled in shared memory; halo pixels are zero-filled by TMA out-of-bounds
+//                                    handling) + one 2-D box of packed weights
+//     warp 1       MMA issuer      : tcgen05.mma 128(256) x BN x 16, fp32 accumulators in TMEM, double-buffered
+//                                    across tiles
+//     warp 2       TMEM allocator, then L2 prefetch of the NEXT launch's weights
+//     warp 3       slab manager    : hands 32-column output slabs to the epilogue, TMA-loading the residual tile
+//                                    into them ahead of time
+//     warps 4..11  epilogue        : two warps per TMEM lane quarter on alternate 32-column chunks: tcgen05.ld ->
+//                                    bias/act/gate/rowvec/residual (or GEGLU) -> swizzled smem slab -> TMA store
+//   Warps 0, 1 and 3 run warp-convergent and predicate only the issue on elect.sync (see elect_one in common.cuh).
 //
 // A-operand tile = 128 output pixels arranged as a bw x bh rectangle (bw*bh = 128) so that one
 // TMA box per filter tap fetches exactly the shifted input pixels.  nn.Linear is the 1x1, H = 1
