@@ -262,6 +262,78 @@ def gen_pipelines(d):
     torch.save(out, os.path.join(OUT, "pipelines.pt"))
 
 
+# layer-level known answers of the reference (tests/models/test_layers_utils.py): (name, class, init kwargs, input
+# shape, extra inputs, expected 3x3 slice, test line).  Weights come from the reference's default init under manual_seed(0)
+# AFTER the sample draw, exactly like the reference test does it.
+LAYER_KATS = [
+    ("upsample_default", "Upsample2D", dict(channels=32, use_conv=False), (1, 32, 32, 32), None,
+     [-0.2173, -1.2079, -1.2079, 0.2952, 1.1254, 1.1254, 0.2952, 1.1254, 1.1254], 113),
+    ("upsample_with_conv", "Upsample2D", dict(channels=32, use_conv=True), (1, 32, 32, 32), None,
+     [0.7145, 1.3773, 0.3492, 0.8448, 1.0839, -0.3341, 0.5956, 0.1250, -0.4841], 140),
+    ("upsample_with_conv_out_dim", "Upsample2D", dict(channels=32, use_conv=True, out_channels=64), (1, 32, 32, 32), None,
+     [0.2703, 0.1656, -0.2538, -0.0553, -0.2984, 0.1044, 0.1155, 0.2579, 0.7755], 152),
+    ("downsample_with_conv", "Downsample2D", dict(channels=32, use_conv=True), (1, 32, 64, 64), None,
+     [0.9267, 0.5878, 0.3337, 1.2321, -0.1191, -0.3984, -0.7532, -0.0715, -0.3913], 192),
+    ("downsample_with_conv_pad1", "Downsample2D", dict(channels=32, use_conv=True, padding=1), (1, 32, 64, 64), None,
+     [0.9267, 0.5878, 0.3337, 1.2321, -0.1191, -0.3984, -0.7532, -0.0715, -0.3913], 207),
+    ("downsample_with_conv_out_dim", "Downsample2D", dict(channels=32, use_conv=True, out_channels=16), (1, 32, 64, 64), None,
+     [-0.6586, 0.5985, 0.0721, 0.1256, -0.1492, 0.4436, -0.2544, 0.5021, 1.1522], 219),
+    ("resnet_default", "ResnetBlock2D", dict(in_channels=32, temb_channels=128), (1, 32, 64, 64), "temb",
+     [-1.9010, -0.2974, -0.8245, -1.3533, 0.8742, -0.9645, -2.0584, 1.3387, -0.4746], 233),
+    ("resnet_use_in_shortcut", "ResnetBlock2D", dict(in_channels=32, temb_channels=128, use_in_shortcut=True), (1, 32, 64, 64), "temb",
+     [0.2226, -1.0791, -0.1629, 0.3659, -0.2889, -1.2376, 0.0582, 0.9206, 0.0044], 248),
+    ("transformer2d_default", "Transformer2DModel", dict(in_channels=32, num_attention_heads=1, attention_head_dim=32, dropout=0.0,
+                                                          cross_attention_dim=None), (1, 32, 64, 64), None,
+     [-1.9455, -0.0066, -1.3933, -1.5878, 0.5325, -0.6486, -1.8648, 0.7515, -0.9689], 325),
+    ("transformer2d_cross_attention_dim", "Transformer2DModel", dict(in_channels=64, num_attention_heads=2, attention_head_dim=32,
+                                                                      dropout=0.0, cross_attention_dim=64), (1, 64, 64, 64), "context",
+     [0.0143, -0.6909, -2.1547, -1.8893, 1.4097, 0.1359, -0.2521, -1.3359, 0.2598], 348),
+]
+
+
+def gen_layers(d):
+    import diffusers.models.downsampling as DS
+    import diffusers.models.resnet as RS
+    import diffusers.models.upsampling as US
+    from diffusers.models.transformers.transformer_2d import Transformer2DModel
+    mods = dict(Upsample2D=US.Upsample2D, Downsample2D=DS.Downsample2D, ResnetBlock2D=RS.ResnetBlock2D, Transformer2DModel=Transformer2DModel)
+    out = {}
+    for name, cls, init, shape, extra, expected, line in LAYER_KATS:
+        torch.manual_seed(0)
+        sample = torch.randn(*shape)
+        temb = torch.randn(1, 128) if extra == "temb" else None
+        m = mods[cls](**init).eval()
+        ctx = torch.randn(1, 4, 64) if extra == "context" else None  # drawn after the module's init, as in the reference test
+        with torch.no_grad():
+            if cls == "ResnetBlock2D":
+                o = m(sample, temb)
+            elif cls == "Transformer2DModel":
+                o = m(sample, ctx).sample if ctx is not None else m(sample).sample
+            else:
+                o = m(sample)
+        sl = o[0, -1, -3:, -3:].flatten()
+        assert torch.allclose(sl, torch.tensor(expected), atol=1e-3), (name, sl, expected)
+        out[name] = dict(cls=cls, init=init, shape=shape, extra=extra, context=ctx, state_dict={k: v.clone() for k, v in m.state_dict().items()},
+                         expected_slice=torch.tensor(expected), reference_line=line, output_shape=tuple(o.shape),
+                         output_abs_mean=float(o.abs().mean()))
+        print("layer", name, "ok")
+    # ---- tests/pipelines/ddpm/test_ddpm.py:28-66: dummy_uncond_unet (default init under manual_seed(0)) + DDPMScheduler(),
+    # 2 steps, generator seed 0 -> hard-coded 3x3 slice of the last channel
+    kcfg = dict(block_out_channels=(4, 8), layers_per_block=1, norm_num_groups=4, sample_size=8, in_channels=3, out_channels=3,
+                down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"))
+    torch.manual_seed(0)
+    u = d.UNet2DModel(**kcfg).eval()
+    dp = d.DDPMPipeline(unet=u, scheduler=d.DDPMScheduler())
+    dp.set_progress_bar_config(disable=True)
+    im = dp(generator=torch.Generator().manual_seed(0), num_inference_steps=2, output_type="np").images
+    expected = np.array([0.0, 0.9996672, 0.00329116, 1.0, 0.9995991, 1.0, 0.0060907, 0.00115037, 0.0])
+    assert np.abs(im[0, -3:, -3:, -1].flatten() - expected).max() < 1e-2
+    out["ddpm_pipeline_kat"] = dict(cfg={**kcfg, "attention_head_dim": u.config.attention_head_dim}, state_dict={k: v.clone() for k, v in u.state_dict().items()},
+                                    expected_slice=torch.from_numpy(expected), image=torch.from_numpy(im), reference_line=45)
+    print("ddpm pipeline kat ok")
+    torch.save(out, os.path.join(OUT, "layers.pt"))
+
+
 MICRO_UNET = dict(sample_size=16, block_out_channels=(64, 64), down_block_types=("DownBlock2D", "CrossAttnDownBlock2D"),
                   up_block_types=("CrossAttnUpBlock2D", "UpBlock2D"), layers_per_block=1, cross_attention_dim=64,
                   transformer_layers_per_block=1, attention_head_dim=(1, 1), addition_time_embed_dim=32,
@@ -322,7 +394,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     dmod = ref_shim.import_reference()
-    which = sys.argv[1:] or ["blocks", "schedulers", "models", "pipelines"]
+    which = sys.argv[1:] or ["blocks", "layers", "schedulers", "models", "pipelines", "checkpoints"]
     for w in which:
         globals()["gen_" + w](dmod)
     for f in sorted(os.listdir(OUT)):
