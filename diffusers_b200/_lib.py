@@ -88,6 +88,10 @@ _lib = None
 _inited_devices = set()
 
 
+def library_path():
+    return LIB_PATH
+
+
 def lib():
     global _lib
     if _lib is None:

@@ -62,3 +62,57 @@ def test_no_cpu_fallback():
 def test_init_fails_loudly_without_gpu():
     with pytest.raises(ops.B200Error):
         _lib.init(0)
+
+
+def test_plain_c_client(tmp_path):
+    """tests/c/abi_client.c: gcc + dlopen only (no torch, no CUDA headers) against the header and the built library;
+    also checks that the ctypes mirror of b200_conv_gemm_args has the C struct's size."""
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "abi_client")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-o", exe, os.path.join(here, "c", "abi_client.c"), "-ldl"], check=True)
+    p = subprocess.run([exe, _lib.library_path()], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "abi client ok" in p.stdout
+    size = int(p.stdout.strip().rsplit("=", 1)[1])
+    assert size == C.sizeof(_lib.ConvGemmArgs)
+
+
+def test_weight_prefetch_plan_records_and_replays():
+    """ops.WeightPrefetchPlan: first forward records the launch order, later forwards hand every launch the NEXT weight
+    (wrapping around to the first), a changed order re-records and never hands out a stale pointer."""
+    class W:  # stands in for a packed weight tensor
+        def __init__(self, ptr, n):
+            self.ptr, self.n = ptr, n
+
+        def data_ptr(self):
+            return self.ptr
+
+        def numel(self):
+            return self.n
+
+        def element_size(self):
+            return 2
+
+    ws = [W(0x1000 * (i + 1), 100 * (i + 1)) for i in range(4)]
+    plan = ops.WeightPrefetchPlan()
+    with ops.weight_prefetch(plan):
+        assert [plan._step(w) for w in ws] == [None] * 4  # nothing known yet
+    assert plan.seq == [(w.ptr, 2 * w.n) for w in ws]
+    with ops.weight_prefetch(plan):
+        nxt = [plan._step(w) for w in ws]
+    assert nxt == [(ws[1].ptr, 400), (ws[2].ptr, 600), (ws[3].ptr, 800), (ws[0].ptr, 200)]
+    with ops.weight_prefetch(plan):  # a different order: hints stop at the first mismatch, the new order is recorded
+        order = [ws[0], ws[2], ws[1]]
+        got = [plan._step(w) for w in order]
+    assert got[0] == (ws[1].ptr, 400) and got[1] is None and got[2] is None
+    assert plan.seq == [(w.ptr, 2 * w.n) for w in order]
+    big = W(0x9000, ops.WeightPrefetchPlan.MAX_BYTES)  # 2 bytes per element: twice the cap
+    with ops.weight_prefetch(ops.WeightPrefetchPlan()) as p2:
+        p2._step(big)
+    assert p2.seq == [(0x9000, ops.WeightPrefetchPlan.MAX_BYTES)]
+    assert ops._PLAN is None
