@@ -66,9 +66,10 @@ int b200_num_sms(void);
  *   conv + temb[:, :, None, None]              models/resnet.py:343-349 (rowvec)
  *   (x + h) / output_scale_factor              models/resnet.py:375 (residual)
  *
- * Execution: persistent CTAs (optionally clusters of 2 along M sharing each weight tile by TMA multicast); 32-column
- * output slabs are staged in shared memory and written with TMA stores (tile width / cluster size are picked by
- * a cycle model of MMA issue vs. the per-SM L2 port).
+ * Execution: persistent CTAs, normally pairs of CTAs (cta_group::2) over two consecutive 128-row tiles, each staging
+ * half of the weight tile; 32-column output slabs are staged in shared memory and written with TMA stores, a residual
+ * operand is TMA-loaded into the slab ahead of time (tile width / pairing are picked by a cost model fitted to
+ * measured K-chunk rates).
  * Epilogue order (fp32):  v = acc + bias[n];  v = act(v);  v *= gate[g, n];  v += rowvec[g, n];
  *                         v += residual[p, n];  y = round16(v)      with g = p / rows_per_group.
  * geglu: w rows are packed per BN-tile as [BN/2 value rows | BN/2 gate rows] (see
@@ -98,7 +99,7 @@ typedef struct {
   int32_t dtype;         /* B200_DTYPE_*                                                        */
   int32_t tile_n;        /* 0 = auto, else force BN in {32, 64, 96, 128, 160, 192, 256}         */
   int32_t out_fp32;      /* 1: y is float32 [.., ldy] (attention scores of the head_dim-512 path) */
-  int32_t cluster_m;     /* 0 = auto, else force the cluster size along M in {1, 2} (tuning / tests) */
+  int32_t cluster_m;     /* 0 = auto, 1 = one CTA per tile, 2 = CTA pairs (cta_group::2) (tuning / tests)   */
   void* debug_timestamps; /* NULL, or int64 [grid][16] device buffer receiving per-CTA clock64 marks (tuning) */
   const void* prefetch;  /* NULL, or device memory (16-byte aligned) to pull into L2 while this launch runs:      */
   int64_t prefetch_bytes; /* the packed weights of the NEXT launch, which would otherwise start DRAM-latency-bound */
