@@ -387,6 +387,11 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
   }
 }
 
+// attention_pipe.cu: the head_dim-64, one-query-tile variant with the score tile pipelined in 64-key halves
+int init_attention_pipe();
+bool attention_pipe_enabled();
+int launch_attention64_pipe(const b200_attention_args* a, cudaStream_t st);
+
 template <int HD, int NQ, bool FP16>
 static int attn_set_attr() {
   cudaError_t e = cudaFuncSetAttribute(attention_kernel<HD, NQ, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -405,6 +410,7 @@ int init_attention() {
   if ((r = attn_set_attr<128, 1, true>())) return r;
   if ((r = attn_set_attr<128, 2, false>())) return r;
   if ((r = attn_set_attr<128, 2, true>())) return r;
+  if ((r = init_attention_pipe())) return r;
   return 0;
 }
 
@@ -430,6 +436,8 @@ int b200_attention(const b200_attention_args* a, void* stream) {
                      a->v_batch_stride % 8 == 0 && a->o_batch_stride % 8 == 0,
                  "attention: strides must be multiples of 8 elements");
   const int HD = a->head_dim;
+  if (HD == 64 && a->nq_override != 2 && attention_pipe_enabled())
+    return launch_attention64_pipe(a, static_cast<cudaStream_t>(stream));
 
   AttnParams prm;
   memset(&prm, 0, sizeof(prm));
