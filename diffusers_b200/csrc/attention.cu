@@ -391,6 +391,10 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
 int init_attention_pipe();
 bool attention_pipe_enabled();
 int launch_attention64_pipe(const b200_attention_args* a, cudaStream_t st);
+// attention_split.cu: EXPERIMENTAL two-warps-per-row variant of the above (B200_ATTN_SPLIT=1, not validated on hardware)
+int init_attention_split();
+bool attention_split_enabled();
+int launch_attention64_split(const b200_attention_args* a, cudaStream_t st);
 
 template <int HD, int NQ, bool FP16>
 static int attn_set_attr() {
@@ -411,6 +415,7 @@ int init_attention() {
   if ((r = attn_set_attr<128, 2, false>())) return r;
   if ((r = attn_set_attr<128, 2, true>())) return r;
   if ((r = init_attention_pipe())) return r;
+  if ((r = init_attention_split())) return r;
   return 0;
 }
 
@@ -436,6 +441,8 @@ int b200_attention(const b200_attention_args* a, void* stream) {
                      a->v_batch_stride % 8 == 0 && a->o_batch_stride % 8 == 0,
                  "attention: strides must be multiples of 8 elements");
   const int HD = a->head_dim;
+  if (HD == 64 && a->nq_override != 2 && attention_split_enabled())
+    return launch_attention64_split(a, static_cast<cudaStream_t>(stream));
   if (HD == 64 && a->nq_override != 2 && attention_pipe_enabled())
     return launch_attention64_pipe(a, static_cast<cudaStream_t>(stream));
 
