@@ -1,4 +1,5 @@
-"""GPU diagnostic: product models (UNet / VAE) vs the oracle on small configs + full-size timing."""
+"""GPU diagnostic (test infrastructure - it imports the oracle, so it lives under tests/): product models (UNet / VAE)
+vs the oracle on small configs + full-size timing.  Usage: python tests/diag_models.py [tiny_unet tiny_vae full_unet full_vae]"""
 import json
 import os
 import sys
