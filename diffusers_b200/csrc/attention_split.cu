@@ -332,11 +332,15 @@ __global__ void __launch_bounds__(384, 2) attention64_split_kernel(const __grid_
   }
 }
 
+static bool g_split_ready = false;
+
+// Never fatal for b200_init: the experimental kernel must not be able to take the validated paths down with it.
 int init_attention_split() {
   cudaError_t e = cudaFuncSetAttribute(attention64_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSplitCfg::SMEM_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(attention64_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSplitCfg::SMEM_BYTES);
-  if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention (split) smem attr: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) cudaGetLastError();  // clear the sticky-less error state
+  g_split_ready = (e == cudaSuccess);
   return 0;
 }
 
@@ -347,6 +351,7 @@ bool attention_split_enabled() {
 
 // head_dim 64, one query tile per CTA; arguments already validated by b200_attention
 int launch_attention64_split(const b200_attention_args* a, cudaStream_t st) {
+  if (!g_split_ready) return set_error(B200_ERR_UNSUPPORTED, "attention (split): kernel attributes could not be set at init");
   AttnSplitParams prm;
   memset(&prm, 0, sizeof(prm));
   auto mk = [&](CUtensorMap* m, const void* base, int rows, long long row_stride, long long batch_stride, uint32_t box_rows,
