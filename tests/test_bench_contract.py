@@ -1,0 +1,68 @@
+"""bench.py's output contract, checked without a GPU: the reference arm's JSON line (with the CPU timing stubbed), the
+clock-sample reduction and the peak lookup."""
+import argparse
+import io
+import json
+import os
+import sys
+from contextlib import redirect_stdout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "e2e"}
+
+
+def _args(**kw):
+    d = dict(workload="sdxl", gpus=1, steps=3, warmup=3, impl="reference", batch=1, denoise_steps=50, guidance_scale=7.5,
+             no_cpu_baseline=False)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def test_reference_arm_line(monkeypatch):
+    stub = dict(value=3.2e-4, unit="images/s", cores=128, kind="port", sample="stub", t_unet_b2_s=60.0, setup_s=1.0)
+    monkeypatch.setattr(bench, "cpu_reference", lambda args, full=True: stub)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        bench.run_reference(_args(gpus=2), rank=1, world=2)  # only rank 0 reports
+    assert buf.getvalue() == ""
+    with redirect_stdout(buf):
+        bench.run_reference(_args(gpus=2), rank=0, world=2)
+    lines = [l for l in buf.getvalue().splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert REQUIRED <= d.keys()
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["metric"].startswith("images/sec") and d["unit"] == "images/s" and "workload" in d["config"]
+    assert d["cpu_baseline"] == {k: stub[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    assert d["e2e"] == dict(value=stub["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    assert d["gpu_launches"] == 0 and abs(d["ms_per_step"] - 1000.0 / stub["value"]) < 1e-6
+
+
+def test_clock_sampler_summary():
+    cs = bench.ClockSampler(0)
+    cs.rows = [["1965", "1965", "900.1", "Not Active", "Not Active", "Not Active", "Active"],
+               ["1575", "1965", "990.0", "Not Active", "Not Active", "Not Active", "Not Active"],
+               ["1800", "1965", "950.0", "Not Active", "Not Active", "Not Active", "Not Active"],
+               ["garbage"]]
+    s = cs.summary()
+    assert s["sm_mhz"] == 1800.0 and s["sm_max_mhz"] == 1965.0 and s["reasons"] == ["sw_power_cap"] and s["samples"] == 3
+    assert bench.ClockSampler(0).summary() == dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+
+
+def test_peaks_source(tmp_path, monkeypatch):
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    p = bench.peaks()
+    assert p["source"] == "fallback" and p["tflops"] > 1000 and p["hbm_gbs"] > 5000
+    with open(tmp_path / "MEASURED_PEAKS.json", "w") as f:
+        json.dump(dict(hbm_gbs=6500.0, bf16_tflops=1600.0, bf16_tflops_sustained=1400.0), f)
+    p = bench.peaks()
+    assert p == dict(hbm_gbs=6500.0, tflops=1400.0, burst=1600.0, source="measured")
+
+
+def test_flop_constants_match_baseline():
+    assert abs(bench.IMAGE_FLOP / 1e12 - 686.6) < 0.1  # 2 x 50 x 6.7612 + 10.470 TFLOP per image
+    assert abs(bench.MID_BLOCK_SHARE - 0.1179) < 1e-3
