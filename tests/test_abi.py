@@ -116,3 +116,24 @@ def test_weight_prefetch_plan_records_and_replays():
         p2._step(big)
     assert p2.seq == [(0x9000, ops.WeightPrefetchPlan.MAX_BYTES)]
     assert ops._PLAN is None
+
+
+HELPERS = {"b200_version", "b200_last_error", "b200_init", "b200_num_sms", "b200_conv_gemm_packed_k", "b200_conv_gemm_pick_tile_n",
+           "b200_group_norm_workspace_bytes"}
+
+
+def test_every_compute_entry_point_rejects_null_operands():
+    """All 17 compute entry points validate their arguments before the first CUDA call: with every pointer NULL and every
+    size 0 they must return a negative code and leave a message - on any box, GPU or not - never crash or launch."""
+    lib = _lib.lib()
+    compute = [n for n in _lib.exported_symbols() if n not in HELPERS]
+    assert len(compute) >= 17
+    for name in compute:
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None, f"{name}: no ctypes signature declared in _lib.py"
+        args = []
+        for t in fn.argtypes:
+            args.append(None if t is C.c_void_p else (t(0.0) if t is C.c_float else t(0)))
+        rc = fn(*args)
+        assert rc < 0, f"{name} accepted null operands (rc={rc})"
+        assert len(lib.b200_last_error()) > 0, name
