@@ -160,10 +160,13 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         return cls(cfg, sd, dtype=dtype, device=device)
 
     # ------------------------------------------------------------------ step-invariant pieces
-    def _rope_tables(self, txt_ids, img_ids):
-        key = (txt_ids.data_ptr(), img_ids.data_ptr(), tuple(txt_ids.shape), tuple(img_ids.shape), txt_ids._version,
-               img_ids._version)
-        if self._rope_key != key:
+    def _rope_tables(self, txt_ids, img_ids, owners=None):
+        # keyed on the tensor OBJECTS the caller passed (kept alive by the key) + version counters: an address-based key
+        # goes stale when the allocator hands a freed buffer to a new tensor.  `owners` = the caller's original arguments
+        # when txt_ids / img_ids are per-call views of them (deprecated 3-D ids)
+        ko = owners or (txt_ids, img_ids)
+        k = self._rope_key
+        if k is None or k[0] is not ko[0] or k[1] is not ko[1] or k[2] != (ko[0]._version, ko[1]._version):
             ids = torch.cat((txt_ids, img_ids), dim=0)
             pos = ids.float()
             cos_out, sin_out = [], []
@@ -174,17 +177,17 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
                 cos_out.append(freqs.cos().repeat_interleave(2, dim=1, output_size=freqs.shape[1] * 2).float())
                 sin_out.append(freqs.sin().repeat_interleave(2, dim=1, output_size=freqs.shape[1] * 2).float())
             self._rope = (torch.cat(cos_out, dim=-1).contiguous(), torch.cat(sin_out, dim=-1).contiguous())
-            self._rope_key = key
+            self._rope_key = (ko[0], ko[1], (ko[0]._version, ko[1]._version))
         return self._rope
 
     def _context(self, ehs):
-        key = (ehs.data_ptr(), ehs._version, tuple(ehs.shape), ehs.dtype)
-        if self._ctx_key != key:
+        k = self._ctx_key
+        if k is None or k[0] is not ehs or k[1] != ehs._version:
             B, T, Dj = ehs.shape
             ce = self.context_embedder
             self._ctx = ops.linear(ehs.to(self._dtype).contiguous().view(B * T, Dj), self.W(ce["w"]), ce["n"],
                                    bias=self.W(ce["b"])).view(B, T, self.D)
-            self._ctx_key = key
+            self._ctx_key = (ehs, ehs._version)
         return self._ctx
 
     def _temb(self, timestep, guidance, pooled):
@@ -271,6 +274,7 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
             raise NotImplementedError("joint_attention_kwargs (IP-adapter / LoRA scale) are outside the hot path")
         if not hidden_states.is_cuda:
             raise ops.B200Error("FluxTransformer2DModel (B200) needs CUDA tensors: there is no CPU fallback")
+        id_owners = (txt_ids, img_ids)
         if txt_ids.ndim == 3:
             txt_ids = txt_ids[0]
         if img_ids.ndim == 3:
@@ -280,7 +284,7 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         temb = self._temb(timestep, guidance, pooled_projections)
         mod = ops.small_linear(temb, self.W(self.mod_all["w"]), bias=self.W(self.mod_all["b"]), act_in=ACT_SILU)
         ctx = self._context(encoder_hidden_states)
-        rope = self._rope_tables(txt_ids, img_ids)
+        rope = self._rope_tables(txt_ids, img_ids, owners=id_owners)
         out = torch.empty((B, S, self.proj_out["n"]), dtype=self._dtype, device=hs.device)
         for b in range(B):
             out[b] = self._forward_one(hs[b], ctx[b], mod[b:b + 1], rope)

@@ -261,13 +261,15 @@ class UNet2DConditionModel(torch.nn.Module, FromPretrainedMixin):
         (they do not depend on the timestep; the reference recomputes them 140x per step)."""
         if self.kv_all is None:
             return None
-        key = (ehs.data_ptr(), ehs._version, tuple(ehs.shape), ehs.dtype)
-        if self._kv_key != key or self._kv is None:
+        # cached on the tensor OBJECT (kept alive here) and its version counter: an address-based key would hand a new
+        # prompt the previous prompt's K/V whenever the allocator reuses the freed buffer
+        src = self._kv_key
+        if src is None or src[0] is not ehs or src[1] != ehs._version or self._kv is None:
             B, S, D = ehs.shape
             flat = ehs.to(self._dtype).contiguous().view(B * S, D)
             kv = ops.linear(flat, self.W(self.kv_all["w"]), self._kv_total)
             self._kv = kv.view(B, S, self._kv_total)
-            self._kv_key = key
+            self._kv_key = (ehs, ehs._version)
         return self._kv
 
     # ------------------------------------------------------------------ forward

@@ -124,3 +124,52 @@ def test_models_refuse_cpu_tensors():
     bad["attention_head_dim"] = (2, 4)  # head_dim 32: not supported by the tcgen05 attention kernel
     with pytest.raises(NotImplementedError):
         UNet2DConditionModel.random_init(bad, device="cpu")
+
+
+def test_step_invariant_caches_follow_the_tensor_not_its_address(monkeypatch):
+    """The per-prompt caches (UNet text K/V, Flux context embedding and RoPE tables) must notice a new prompt even when
+    the allocator gives the new tensor the old one's address: they key on the tensor object + its version counter."""
+    from diffusers_b200 import ops
+    from diffusers_b200.transformer_flux import FluxTransformer2DModel
+    from diffusers_b200.unet_2d_condition import UNet2DConditionModel
+    calls = []
+
+    def fake_linear(x, w, N, **kw):
+        calls.append(x.data_ptr())
+        return torch.zeros(x.shape[0], N, dtype=x.dtype)
+
+    monkeypatch.setattr(ops, "linear", fake_linear)
+    ucfg = dict(specs.SDXL_UNET_CONFIG)
+    ucfg.update(sample_size=16, block_out_channels=(64, 64), down_block_types=("DownBlock2D", "CrossAttnDownBlock2D"),
+                up_block_types=("CrossAttnUpBlock2D", "UpBlock2D"), layers_per_block=1, cross_attention_dim=64,
+                transformer_layers_per_block=1, attention_head_dim=(1, 1), addition_time_embed_dim=32,
+                projection_class_embeddings_input_dim=256)
+    unet = UNet2DConditionModel(ucfg, specs.random_state_dict(specs.unet2d_condition_params(ucfg), seed=0), device="cpu")
+    a = torch.randn(2, 77, 64).bfloat16()
+    kv1 = unet._text_kv(a)
+    assert unet._text_kv(a) is kv1 and len(calls) == 1            # same prompt tensor, same step-invariant K/V
+    b = a.clone()                                                  # another prompt (wherever the allocator puts it)
+    assert unet._text_kv(b) is not kv1 and len(calls) == 2
+    b.add_(1.0)                                                    # edited in place: version counter moves
+    unet._text_kv(b)
+    assert len(calls) == 3
+    unet._reset_stateful_cache()
+    unet._text_kv(b)
+    assert len(calls) == 4
+
+    fcfg = dict(patch_size=1, in_channels=16, num_layers=1, num_single_layers=1, attention_head_dim=64, num_attention_heads=2,
+                joint_attention_dim=32, pooled_projection_dim=16, guidance_embeds=True, axes_dims_rope=(8, 28, 28))
+    flux = FluxTransformer2DModel(fcfg, specs.random_state_dict(specs.flux_params(fcfg), seed=0), device="cpu")
+    calls.clear()
+    e = torch.randn(1, 8, 32).bfloat16()
+    c1 = flux._context(e)
+    assert flux._context(e) is c1 and len(calls) == 1
+    assert flux._context(e.clone()) is not c1 and len(calls) == 2
+    txt, img = torch.zeros(8, 3), torch.arange(48, dtype=torch.float32).reshape(16, 3)
+    r1 = flux._rope_tables(txt, img)
+    assert flux._rope_tables(txt, img) is r1
+    r2 = flux._rope_tables(txt, img.clone())
+    assert r2 is not r1 and torch.equal(r1[0], r2[0])
+    img3 = img[None]
+    r3 = flux._rope_tables(img3[0][:8] * 0, img3[0], owners=(txt, img3))  # per-call views: keyed on the caller's tensors
+    assert flux._rope_tables(img3[0][:8] * 0, img3[0], owners=(txt, img3)) is r3
