@@ -41,6 +41,14 @@ class AutoencoderKL(torch.nn.Module, FromPretrainedMixin):
         cfg = dict(specs.SDXL_VAE_CONFIG)
         cfg.update(config)
         self.config = FrozenConfig(cfg)
+        # reference options (models/autoencoders/autoencoder_kl.py:75-100) this decoder does not implement must fail loudly
+        if cfg.get("act_fn", "silu") not in ("silu", "swish"):
+            raise NotImplementedError(f"AutoencoderKL act_fn={cfg['act_fn']!r} is outside the accelerated hot path")
+        for t in tuple(cfg["up_block_types"]):
+            if t != "UpDecoderBlock2D":
+                raise NotImplementedError(f"decoder block type {t} is outside the accelerated hot path")
+        if cfg.get("norm_num_groups") is None:
+            raise NotImplementedError("norm_num_groups=None is outside the hot path")
         self._dtype = dtype
         self._n = 0
         spec = specs.vae_decoder_params(cfg)

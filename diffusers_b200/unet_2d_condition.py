@@ -52,8 +52,7 @@ class UNet2DConditionModel(torch.nn.Module, FromPretrainedMixin):
         for k, shp in spec.items():
             if tuple(state_dict[k].shape) != tuple(shp):
                 raise ValueError(f"{k}: expected shape {tuple(shp)}, got {tuple(state_dict[k].shape)}")
-        if cfg.get("act_fn", "silu") not in ("silu", "swish"):
-            raise NotImplementedError("only act_fn='silu'")
+        self._validate_config(cfg)
         self._build(state_dict, torch.device(device))
         # attribute the SDXL pipeline reads (pipeline_stable_diffusion_xl.py:737)
         self.add_embedding = types.SimpleNamespace(
@@ -62,6 +61,38 @@ class UNet2DConditionModel(torch.nn.Module, FromPretrainedMixin):
         self._kv = None
         self._graphs = {}
         self.use_cuda_graph = False
+
+    # Constructor options of the reference (models/unets/unet_2d_condition.py:178-239) whose non-default values change the
+    # numerics and are NOT implemented here: a checkpoint that sets one must fail loudly, not be approximated.
+    _ONLY = dict(act_fn=("silu", "swish"), mid_block_type=("UNetMidBlock2DCrossAttn",), addition_embed_type=(None, "text_time"),
+                 time_embedding_type=("positional",), resnet_time_scale_shift=("default",), attention_type=("default",),
+                 class_embed_type=(None,), num_class_embeds=(None,), time_cond_proj_dim=(None,), timestep_post_act=(None,),
+                 time_embedding_act_fn=(None,), time_embedding_dim=(None,), encoder_hid_dim=(None,), encoder_hid_dim_type=(None,),
+                 cross_attention_norm=(None,), reverse_transformer_layers_per_block=(None,), mid_block_only_cross_attention=(None, False),
+                 only_cross_attention=(False,), dual_cross_attention=(False,), upcast_attention=(False, None),
+                 resnet_skip_time_act=(False,), class_embeddings_concat=(False,), center_input_sample=(False,),
+                 resnet_out_scale_factor=(1.0, 1), mid_block_scale_factor=(1.0, 1), conv_in_kernel=(3,), conv_out_kernel=(3,),
+                 downsample_padding=(1,))
+    _BLOCKS = ("DownBlock2D", "CrossAttnDownBlock2D", "UpBlock2D", "CrossAttnUpBlock2D")
+
+    @classmethod
+    def _validate_config(cls, cfg):
+        for k, allowed in cls._ONLY.items():
+            if k in cfg:
+                v = cfg[k]
+                v = tuple(v) if isinstance(v, list) else v
+                if isinstance(v, tuple) and len(set(v)) == 1:
+                    v = v[0]
+                if v not in allowed:
+                    raise NotImplementedError(f"UNet2DConditionModel option {k}={cfg[k]!r} is outside the accelerated hot path "
+                                              f"(supported: {allowed})")
+        for t in tuple(cfg["down_block_types"]) + tuple(cfg["up_block_types"]):
+            if t not in cls._BLOCKS:
+                raise NotImplementedError(f"block type {t} is outside the accelerated hot path ({cls._BLOCKS})")
+        if cfg.get("norm_num_groups") is None:
+            raise NotImplementedError("norm_num_groups=None (no GroupNorm) is outside the hot path")
+        if isinstance(cfg.get("cross_attention_dim"), (list, tuple)) and len(set(cfg["cross_attention_dim"])) > 1:
+            raise NotImplementedError("per-block cross_attention_dim is outside the hot path")
 
     # ------------------------------------------------------------------ weights
     def _reg(self, t, device):

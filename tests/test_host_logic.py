@@ -173,3 +173,24 @@ def test_step_invariant_caches_follow_the_tensor_not_its_address(monkeypatch):
     img3 = img[None]
     r3 = flux._rope_tables(img3[0][:8] * 0, img3[0], owners=(txt, img3))  # per-call views: keyed on the caller's tensors
     assert flux._rope_tables(img3[0][:8] * 0, img3[0], owners=(txt, img3)) is r3
+
+
+def test_unsupported_checkpoint_options_are_refused():
+    """Options of a reference config that change the numerics and are not implemented must raise, never be ignored
+    (they would otherwise slip in through from_pretrained)."""
+    from diffusers_b200.autoencoder_kl import AutoencoderKL
+    from diffusers_b200.unet_2d_condition import UNet2DConditionModel
+    base = dict(specs.SDXL_UNET_CONFIG)
+    UNet2DConditionModel._validate_config(base)
+    UNet2DConditionModel._validate_config({**base, "use_linear_projection": False, "upcast_attention": None, "only_cross_attention": [False, False, False]})
+    for bad in (dict(upcast_attention=True), dict(class_embed_type="timestep"), dict(num_class_embeds=10), dict(resnet_time_scale_shift="scale_shift"),
+                dict(down_block_types=("DownBlock2D", "AttnDownBlock2D", "CrossAttnDownBlock2D")), dict(mid_block_type="UNetMidBlock2DSimpleCrossAttn"),
+                dict(time_cond_proj_dim=256), dict(only_cross_attention=True), dict(addition_embed_type="text_image"), dict(act_fn="gelu"),
+                dict(attention_type="gated"), dict(conv_in_kernel=5), dict(norm_num_groups=None), dict(cross_attention_dim=(768, 1024, 2048))):
+        with pytest.raises(NotImplementedError):
+            UNet2DConditionModel._validate_config({**base, **bad})
+    vcfg = dict(specs.SDXL_VAE_CONFIG)
+    vcfg.update(block_out_channels=(32, 32), up_block_types=("UpDecoderBlock2D", "AttnUpDecoderBlock2D"), down_block_types=("DownEncoderBlock2D",) * 2,
+                layers_per_block=1)
+    with pytest.raises(NotImplementedError):
+        AutoencoderKL(vcfg, {}, device="cpu")
