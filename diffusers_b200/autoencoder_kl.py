@@ -121,6 +121,59 @@ class AutoencoderKL(torch.nn.Module, FromPretrainedMixin):
         self.norm_out = dict(w=R(g(d + ".conv_norm_out.weight")), b=R(g(d + ".conv_norm_out.bias")))
         self.conv_out = conv(d + ".conv_out")
 
+    def reference_state_dict(self):
+        """The decoder half (+ post_quant_conv) of the reference's `state_dict()`, rebuilt from the packed buffers: the exact
+        inverse of `_build`.  The encoder half is not on the path and is not kept."""
+        spec = specs.vae_decoder_params(dict(self.config))
+        W = lambda n: self._buffers[n].detach().cpu()  # noqa: E731
+        out = {}
+
+        def conv(p, c, cin, padded_from=None):
+            w = packing.unpack_conv_weight(W(c["w"]), padded_from or cin, c["k"])
+            out[p + ".weight"], out[p + ".bias"] = w[:, :cin].contiguous(), W(c["b"])
+
+        def resnet(p, r, cin):
+            cout = r["c1"]["n"]
+            out[p + ".norm1.weight"], out[p + ".norm1.bias"] = W(r["n1w"]), W(r["n1b"])
+            conv(p + ".conv1", r["c1"], cin)
+            out[p + ".norm2.weight"], out[p + ".norm2.bias"] = W(r["n2w"]), W(r["n2b"])
+            conv(p + ".conv2", r["c2"], cout)
+            if "sc" in r:
+                conv(p + ".conv_shortcut", r["sc"], cin)
+            return cout
+
+        lc = self.config["latent_channels"]
+        if self.pq is not None:
+            conv("post_quant_conv", self.pq, lc, padded_from=self.lat_pad)
+        d = "decoder"
+        conv(d + ".conv_in", self.conv_in, lc, padded_from=self.lat_pad)
+        ch = self.conv_in["n"]
+        ch = resnet(d + ".mid_block.resnets.0", self.mid_res[0], ch)
+        if self.mid_attn is not None:
+            a, m = d + ".mid_block.attentions.0", self.mid_attn
+            C = m["C"]
+            out[a + ".group_norm.weight"], out[a + ".group_norm.bias"] = W(m["gw"]), W(m["gb"])
+            qkv, qkvb = packing.unpack_linear_weight(W(m["qkv"]), C), W(m["qkvb"])
+            for i, nm in enumerate(("to_q", "to_k", "to_v")):
+                out[f"{a}.{nm}.weight"], out[f"{a}.{nm}.bias"] = qkv[i * C:(i + 1) * C].contiguous(), qkvb[i * C:(i + 1) * C].contiguous()
+            out[a + ".to_out.0.weight"], out[a + ".to_out.0.bias"] = packing.unpack_linear_weight(W(m["ow"]), C), W(m["ob"])
+        ch = resnet(d + ".mid_block.resnets.1", self.mid_res[1], ch)
+        for i, blk in enumerate(self.up):
+            for j, r in enumerate(blk["res"]):
+                ch = resnet(f"{d}.up_blocks.{i}.resnets.{j}", r, ch)
+            if blk["up"] is not None:
+                conv(f"{d}.up_blocks.{i}.upsamplers.0.conv", blk["up"], ch)
+        out[d + ".conv_norm_out.weight"], out[d + ".conv_norm_out.bias"] = W(self.norm_out["w"]), W(self.norm_out["b"])
+        conv(d + ".conv_out", self.conv_out, ch)
+        missing = [k for k in spec if k not in out]
+        if missing or len(out) != len(spec):
+            raise RuntimeError(f"reference_state_dict: {len(missing)} parameters not reconstructed, e.g. {missing[:3]}")
+        return {k: out[k].reshape(spec[k]).contiguous() for k in spec}
+
+    def save_pretrained(self, *args, **kwargs):
+        raise NotImplementedError("AutoencoderKL (B200) keeps only the decoder half of a checkpoint: it cannot write a complete "
+                                  "reference checkpoint (reference_state_dict() returns the decoder parameters)")
+
     @property
     def dtype(self):
         return self._dtype

@@ -141,6 +141,23 @@ class FromPretrainedMixin:
     def _param_spec_for(cls, cfg):
         return cls._param_spec(cfg)
 
+    def save_pretrained(self, save_directory, safe_serialization=True, variant=None):
+        """The reference's `ModelMixin.save_pretrained` layout (models/modeling_utils.py:680-790): config.json with
+        `_class_name` + one `diffusion_pytorch_model[.variant].safetensors` holding `reference_state_dict()`, so the
+        unmodified reference (or `from_pretrained` here) loads it back."""
+        if not safe_serialization:
+            raise NotImplementedError("only safetensors serialization")
+        if not hasattr(self, "reference_state_dict"):
+            raise NotImplementedError(f"{type(self).__name__} cannot rebuild the reference's parameters from its packed buffers")
+        from safetensors.torch import save_file
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = {"_class_name": self._ref_class_names[0], "_diffusers_version": "0.40.0.dev0"}
+        cfg.update({k: (list(v) if isinstance(v, tuple) else v) for k, v in dict(self.config).items()})
+        with open(os.path.join(save_directory, CONFIG_NAME), "w") as f:
+            json.dump(cfg, f, indent=2, sort_keys=True)
+        save_file(self.reference_state_dict(), os.path.join(save_directory, add_variant(SAFETENSORS_WEIGHTS_NAME, variant)),
+                  metadata={"format": "pt"})
+
 
 def scheduler_kwargs(cls, cfg):
     """Constructor arguments out of a reference scheduler config.  Options the class does not name reach its `**kwargs`

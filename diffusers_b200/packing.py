@@ -53,3 +53,43 @@ def pack_geglu(w, b, tile_n):
         bv, bg = b[:inner], b[inner:]
         bp = torch.stack([bv.reshape(nt, half), bg.reshape(nt, half)], dim=1).reshape(two_inner).contiguous()
     return pack_linear_weight(wp), bp
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# inverses (used by the shells' reference_state_dict(): packed buffers -> the reference's parameter tensors)
+# ----------------------------------------------------------------------------------------------------------------------
+def unpack_conv_weight(p, in_channels, ksize, split=None):
+    """[O, Kp] -> nn.Conv2d weight [O, I, k, k]; exact inverse of pack_conv_weight (the zero padding is dropped)."""
+    O = p.shape[0]
+    srcs = [in_channels] if split is None else list(split)
+    assert sum(srcs) == in_channels
+    taps = ksize * ksize
+    per_tap = sum(rup(c, 64) for c in srcs)
+    assert p.shape[1] == taps * per_tap, (tuple(p.shape), taps, per_tap)
+    pt = p.reshape(O, taps, per_tap)
+    parts, off = [], 0
+    for c in srcs:
+        parts.append(pt[:, :, off:off + c])
+        off += rup(c, 64)
+    w = torch.cat(parts, dim=2)  # [O, tap, I]
+    return w.reshape(O, ksize, ksize, in_channels).permute(0, 3, 1, 2).contiguous()
+
+
+def unpack_linear_weight(p, in_features, split=None):
+    """[N, Kp] -> nn.Linear weight [N, K]."""
+    return unpack_conv_weight(p, in_features, 1, split)[:, :, 0, 0].contiguous()
+
+
+def unpack_geglu(wp, bp, in_features, tile_n):
+    """Inverse of pack_geglu: per-tile [value rows | gate rows] -> [all value rows ; all gate rows]."""
+    w = unpack_linear_weight(wp, in_features)
+    two_inner = w.shape[0]
+    inner, half = two_inner // 2, tile_n // 2
+    nt = inner // half
+    wt = w.reshape(nt, 2, half, -1)
+    wo = torch.cat([wt[:, 0].reshape(inner, -1), wt[:, 1].reshape(inner, -1)], 0).contiguous()
+    bo = None
+    if bp is not None:
+        bt = bp.reshape(nt, 2, half)
+        bo = torch.cat([bt[:, 0].reshape(inner), bt[:, 1].reshape(inner)], 0).contiguous()
+    return wo, bo

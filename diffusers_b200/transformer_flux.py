@@ -135,6 +135,74 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         self.proj_out = lin("proj_out")
         self.mod_all = dict(w=R(torch.cat(mod_w, 0)), b=R(torch.cat(mod_b, 0)))
 
+    def reference_state_dict(self):
+        """The reference's `state_dict()` rebuilt from the packed buffers (exact inverse of `_build`)."""
+        cfg = self.config
+        spec = specs.flux_params(dict(cfg))
+        W = lambda n: self._buffers[n].detach().cpu()  # noqa: E731
+        out = {}
+        D = self.D
+        mod_w, mod_b = W(self.mod_all["w"]), W(self.mod_all["b"])
+
+        def small(p, d):
+            out[p + ".weight"], out[p + ".bias"] = W(d["w"]), W(d["b"])
+
+        def lin(p, d, split=None):
+            out[p + ".weight"] = packing.unpack_linear_weight(W(d["w"]), spec[p + ".weight"][1], split)
+            out[p + ".bias"] = W(d["b"])
+
+        def lin_cat(ps, d):
+            w, b = packing.unpack_linear_weight(W(d["w"]), spec[ps[0] + ".weight"][1]), W(d["b"])
+            o = 0
+            for q in ps:
+                n = spec[q + ".weight"][0]
+                out[q + ".weight"], out[q + ".bias"] = w[o:o + n].contiguous(), b[o:o + n].contiguous()
+                o += n
+
+        def mod(p, off):
+            n = spec[p + ".weight"][0]
+            out[p + ".weight"], out[p + ".bias"] = mod_w[off:off + n].contiguous(), mod_b[off:off + n].contiguous()
+
+        te = "time_text_embed"
+        small(te + ".timestep_embedder.linear_1", self.t_emb[0])
+        small(te + ".timestep_embedder.linear_2", self.t_emb[1])
+        if self.g_emb is not None:
+            small(te + ".guidance_embedder.linear_1", self.g_emb[0])
+            small(te + ".guidance_embedder.linear_2", self.g_emb[1])
+        small(te + ".text_embedder.linear_1", self.p_emb[0])
+        small(te + ".text_embedder.linear_2", self.p_emb[1])
+        lin("x_embedder", self.x_embedder)
+        lin("context_embedder", self.context_embedder)
+        for i, blk in enumerate(self.double):
+            p = f"transformer_blocks.{i}"
+            a = p + ".attn"
+            mod(p + ".norm1.linear", blk["mod"])
+            mod(p + ".norm1_context.linear", blk["cmod"])
+            lin_cat([a + ".to_q", a + ".to_k", a + ".to_v"], blk["qkv"])
+            lin_cat([a + ".add_q_proj", a + ".add_k_proj", a + ".add_v_proj"], blk["aqkv"])
+            out[a + ".norm_q.weight"], out[a + ".norm_k.weight"] = W(blk["nq"]), W(blk["nk"])
+            out[a + ".norm_added_q.weight"], out[a + ".norm_added_k.weight"] = W(blk["naq"]), W(blk["nak"])
+            lin(a + ".to_out.0", blk["out"])
+            lin(a + ".to_add_out", blk["aout"])
+            lin(p + ".ff.net.0.proj", blk["ff1"])
+            lin(p + ".ff.net.2", blk["ff2"])
+            lin(p + ".ff_context.net.0.proj", blk["cff1"])
+            lin(p + ".ff_context.net.2", blk["cff2"])
+        for i, blk in enumerate(self.single):
+            p = f"single_transformer_blocks.{i}"
+            a = p + ".attn"
+            mod(p + ".norm.linear", blk["mod"])
+            lin_cat([a + ".to_q", a + ".to_k", a + ".to_v"], blk["qkv"])
+            out[a + ".norm_q.weight"], out[a + ".norm_k.weight"] = W(blk["nq"]), W(blk["nk"])
+            lin(p + ".proj_mlp", blk["mlp"])
+            lin(p + ".proj_out", blk["out"], split=(D, 4 * D))
+        mod("norm_out.linear", self.mod_out)
+        lin("proj_out", self.proj_out)
+        missing = [k for k in spec if k not in out]
+        if missing or len(out) != len(spec):
+            raise RuntimeError(f"reference_state_dict: {len(missing)} parameters not reconstructed, e.g. {missing[:3]}")
+        return {k: out[k].reshape(spec[k]).contiguous() for k in spec}
+
     # ------------------------------------------------------------------ reference-facing surface
     @property
     def dtype(self):

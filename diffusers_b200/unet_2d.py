@@ -147,6 +147,72 @@ class UNet2DModel(torch.nn.Module, FromPretrainedMixin):
         self.conv_out = conv("conv_out")
         self.temb_all = dict(w=R(torch.cat(temb_w, 0)), b=R(torch.cat(temb_b, 0)))
 
+    def reference_state_dict(self):
+        """The reference's `state_dict()` rebuilt from the packed buffers (exact inverse of `_build`; the channel bookkeeping
+        mirrors it)."""
+        cfg = self.config
+        spec = specs.unet2d_params(dict(cfg))
+        W = lambda n: self._buffers[n].detach().cpu()  # noqa: E731
+        out = {}
+        boc = tuple(cfg["block_out_channels"])
+        temb_w, temb_b = W(self.temb_all["w"]), W(self.temb_all["b"])
+        out["time_embedding.linear_1.weight"], out["time_embedding.linear_1.bias"] = W(self.t1["w"]), W(self.t1["b"])
+        out["time_embedding.linear_2.weight"], out["time_embedding.linear_2.bias"] = W(self.t2["w"]), W(self.t2["b"])
+        out["conv_in.weight"] = packing.unpack_conv_weight(W(self.conv_in["w"]), self.in_pad, 3)[:, :cfg["in_channels"]].contiguous()
+        out["conv_in.bias"] = W(self.conv_in["b"])
+
+        def resnet(p, r, cin, split=None):
+            cout, o = r["cout"], r["temb_off"]
+            out[p + ".norm1.weight"], out[p + ".norm1.bias"] = W(r["n1w"]), W(r["n1b"])
+            out[p + ".conv1.weight"], out[p + ".conv1.bias"] = packing.unpack_conv_weight(W(r["c1w"]), cin, 3, split), W(r["c1b"])
+            out[p + ".time_emb_proj.weight"], out[p + ".time_emb_proj.bias"] = temb_w[o:o + cout].contiguous(), temb_b[o:o + cout].contiguous()
+            out[p + ".norm2.weight"], out[p + ".norm2.bias"] = W(r["n2w"]), W(r["n2b"])
+            out[p + ".conv2.weight"], out[p + ".conv2.bias"] = packing.unpack_conv_weight(W(r["c2w"]), cout, 3), W(r["c2b"])
+            if "scw" in r:
+                out[p + ".conv_shortcut.weight"] = packing.unpack_conv_weight(W(r["scw"]), cin, 1, split)
+                out[p + ".conv_shortcut.bias"] = W(r["scb"])
+            return cout
+
+        def attn(p, a):
+            C = a["C"]
+            out[p + ".group_norm.weight"], out[p + ".group_norm.bias"] = W(a["gw"]), W(a["gb"])
+            qkv, qkvb = packing.unpack_linear_weight(W(a["qkv"]), C), W(a["qkvb"])
+            for i, nm in enumerate(("to_q", "to_k", "to_v")):
+                out[f"{p}.{nm}.weight"], out[f"{p}.{nm}.bias"] = qkv[i * C:(i + 1) * C].contiguous(), qkvb[i * C:(i + 1) * C].contiguous()
+            out[p + ".to_out.0.weight"], out[p + ".to_out.0.bias"] = packing.unpack_linear_weight(W(a["ow"]), C), W(a["ob"])
+
+        def conv(p, c, cin):
+            out[p + ".weight"], out[p + ".bias"] = packing.unpack_conv_weight(W(c["w"]), cin, 3), W(c["b"])
+
+        skip_ch, cur = [boc[0]], boc[0]
+        for i, blk in enumerate(self.down):
+            for j, r in enumerate(blk["res"]):
+                cur = resnet(f"down_blocks.{i}.resnets.{j}", r, cur)
+                skip_ch.append(cur)
+            for j, a in enumerate(blk["attn"]):
+                attn(f"down_blocks.{i}.attentions.{j}", a)
+            if blk["down"] is not None:
+                conv(f"down_blocks.{i}.downsamplers.0.conv", blk["down"], cur)
+                skip_ch.append(cur)
+        cur = resnet("mid_block.resnets.0", self.mid["res"][0], cur)
+        if self.mid["attn"] is not None:
+            attn("mid_block.attentions.0", self.mid["attn"])
+        cur = resnet("mid_block.resnets.1", self.mid["res"][1], cur)
+        for i, blk in enumerate(self.up):
+            for j, r in enumerate(blk["res"]):
+                sk = skip_ch.pop()
+                cur = resnet(f"up_blocks.{i}.resnets.{j}", r, cur + sk, split=(cur, sk))
+            for j, a in enumerate(blk["attn"]):
+                attn(f"up_blocks.{i}.attentions.{j}", a)
+            if blk["up"] is not None:
+                conv(f"up_blocks.{i}.upsamplers.0.conv", blk["up"], cur)
+        out["conv_norm_out.weight"], out["conv_norm_out.bias"] = W(self.norm_out["w"]), W(self.norm_out["b"])
+        conv("conv_out", self.conv_out, boc[0])
+        missing = [k for k in spec if k not in out]
+        if missing or len(out) != len(spec):
+            raise RuntimeError(f"reference_state_dict: {len(missing)} parameters not reconstructed, e.g. {missing[:3]}")
+        return {k: out[k].reshape(spec[k]).contiguous() for k in spec}
+
     # ------------------------------------------------------------------
     def _gn(self, x, w, b, B, hw, silu, x2=None):
         return ops.group_norm(x, x2=x2, batch=B, hw=hw, groups=self.config["norm_num_groups"], eps=self.config.get("norm_eps", 1e-5),

@@ -223,6 +223,97 @@ class UNet2DConditionModel(torch.nn.Module, FromPretrainedMixin):
         self.kv_all = dict(w=R(packing.pack_linear_weight(torch.cat(kv_w, 0)))) if kv_w else None
         del dt
 
+    # ------------------------------------------------------------------ packed buffers -> reference parameters
+    def reference_state_dict(self):
+        """The reference's `state_dict()` (same names, shapes; values in the model dtype) rebuilt from the packed buffers:
+        the exact inverse of `_build`, so `save_pretrained` writes a checkpoint the unmodified reference loads."""
+        cfg = self.config
+        spec = specs.unet2d_condition_params(dict(cfg))
+        W = lambda n: self._buffers[n].detach().cpu()  # noqa: E731
+        out = {}
+        boc = tuple(cfg["block_out_channels"])
+        cross = cfg["cross_attention_dim"]
+        cross = cross[0] if isinstance(cross, (list, tuple)) else cross
+        temb_w, temb_b = W(self.temb_all["w"]), W(self.temb_all["b"])
+        kv = packing.unpack_linear_weight(W(self.kv_all["w"]), cross) if self.kv_all is not None else None
+
+        def lin_small(p, d):
+            out[p + ".weight"], out[p + ".bias"] = W(d["w"]), W(d["b"])
+
+        lin_small("time_embedding.linear_1", self.time_embedding[0])
+        lin_small("time_embedding.linear_2", self.time_embedding[1])
+        if self.add_emb is not None:
+            lin_small("add_embedding.linear_1", self.add_emb[0])
+            lin_small("add_embedding.linear_2", self.add_emb[1])
+        out["conv_in.weight"] = packing.unpack_conv_weight(W(self.conv_in["w"]), self.in_pad, 3)[:, :cfg["in_channels"]].contiguous()
+        out["conv_in.bias"] = W(self.conv_in["b"])
+
+        def resnet(p, r):
+            cin, cout, split = r["cin"], r["cout"], r["split"]
+            out[p + ".norm1.weight"], out[p + ".norm1.bias"] = W(r["n1w"]), W(r["n1b"])
+            out[p + ".conv1.weight"] = packing.unpack_conv_weight(W(r["c1w"]), cin, 3, split)
+            out[p + ".conv1.bias"] = W(r["c1b"])
+            o = r["temb_off"]
+            out[p + ".time_emb_proj.weight"], out[p + ".time_emb_proj.bias"] = temb_w[o:o + cout].contiguous(), temb_b[o:o + cout].contiguous()
+            out[p + ".norm2.weight"], out[p + ".norm2.bias"] = W(r["n2w"]), W(r["n2b"])
+            out[p + ".conv2.weight"] = packing.unpack_conv_weight(W(r["c2w"]), cout, 3)
+            out[p + ".conv2.bias"] = W(r["c2b"])
+            if "scw" in r:
+                out[p + ".conv_shortcut.weight"] = packing.unpack_conv_weight(W(r["scw"]), cin, 1, split)
+                out[p + ".conv_shortcut.bias"] = W(r["scb"])
+
+        def transformer(p, t):
+            ch = t["ch"]
+            out[p + ".norm.weight"], out[p + ".norm.bias"] = W(t["nw"]), W(t["nb"])
+            out[p + ".proj_in.weight"] = packing.unpack_linear_weight(W(t["piw"]), ch)   # reshaped to the spec below
+            out[p + ".proj_in.bias"] = W(t["pib"])
+            out[p + ".proj_out.weight"] = packing.unpack_linear_weight(W(t["pow"]), ch)
+            out[p + ".proj_out.bias"] = W(t["pob"])
+            for k, blk in enumerate(t["blocks"]):
+                b = f"{p}.transformer_blocks.{k}"
+                for nm, (w_, b_) in (("norm1", ("l1w", "l1b")), ("norm2", ("l2w", "l2b")), ("norm3", ("l3w", "l3b"))):
+                    out[f"{b}.{nm}.weight"], out[f"{b}.{nm}.bias"] = W(blk[w_]), W(blk[b_])
+                qkv = packing.unpack_linear_weight(W(blk["qkv"]), ch)
+                out[b + ".attn1.to_q.weight"], out[b + ".attn1.to_k.weight"], out[b + ".attn1.to_v.weight"] = (
+                    qkv[:ch].contiguous(), qkv[ch:2 * ch].contiguous(), qkv[2 * ch:].contiguous())
+                out[b + ".attn1.to_out.0.weight"], out[b + ".attn1.to_out.0.bias"] = packing.unpack_linear_weight(W(blk["ow"]), ch), W(blk["ob"])
+                out[b + ".attn2.to_q.weight"] = packing.unpack_linear_weight(W(blk["q2"]), ch)
+                o = blk["kv_off"]
+                out[b + ".attn2.to_k.weight"], out[b + ".attn2.to_v.weight"] = kv[o:o + ch].contiguous(), kv[o + ch:o + 2 * ch].contiguous()
+                out[b + ".attn2.to_out.0.weight"], out[b + ".attn2.to_out.0.bias"] = packing.unpack_linear_weight(W(blk["o2w"]), ch), W(blk["o2b"])
+                ffw, ffb = packing.unpack_geglu(W(blk["ff1w"]), W(blk["ff1b"]), ch, blk["ff1tile"])
+                out[b + ".ff.net.0.proj.weight"], out[b + ".ff.net.0.proj.bias"] = ffw, ffb
+                out[b + ".ff.net.2.weight"] = packing.unpack_linear_weight(W(blk["ff2w"]), blk["ff1n"] // 2)
+                out[b + ".ff.net.2.bias"] = W(blk["ff2b"])
+
+        def sampler(p, d, cin):
+            out[p + ".conv.weight"], out[p + ".conv.bias"] = packing.unpack_conv_weight(W(d["w"]), cin, 3), W(d["b"])
+
+        for i, blk in enumerate(self.down):
+            for j, r in enumerate(blk["res"]):
+                resnet(f"down_blocks.{i}.resnets.{j}", r)
+            for j, t in enumerate(blk["attn"]):
+                transformer(f"down_blocks.{i}.attentions.{j}", t)
+            if blk["down"] is not None:
+                sampler(f"down_blocks.{i}.downsamplers.0", blk["down"], blk["down"]["n"])
+        resnet("mid_block.resnets.0", self.mid["res"][0])
+        resnet("mid_block.resnets.1", self.mid["res"][1])
+        transformer("mid_block.attentions.0", self.mid["attn"][0])
+        for i, blk in enumerate(self.up):
+            for j, r in enumerate(blk["res"]):
+                resnet(f"up_blocks.{i}.resnets.{j}", r)
+            for j, t in enumerate(blk["attn"]):
+                transformer(f"up_blocks.{i}.attentions.{j}", t)
+            if blk["up"] is not None:
+                sampler(f"up_blocks.{i}.upsamplers.0", blk["up"], blk["up"]["n"])
+        out["conv_norm_out.weight"], out["conv_norm_out.bias"] = W(self.norm_out["w"]), W(self.norm_out["b"])
+        out["conv_out.weight"] = packing.unpack_conv_weight(W(self.conv_out["w"]), boc[0], 3)
+        out["conv_out.bias"] = W(self.conv_out["b"])
+        missing = [k for k in spec if k not in out]
+        if missing or len(out) != len(spec):
+            raise RuntimeError(f"reference_state_dict: {len(missing)} parameters not reconstructed, e.g. {missing[:3]}")
+        return {k: out[k].reshape(spec[k]).contiguous() for k in spec}  # spec order; 1x1-conv projections get their 4-D shape back
+
     # ------------------------------------------------------------------ nn.Module-ish surface
     @property
     def dtype(self):

@@ -183,3 +183,60 @@ def test_reference_save_pretrained_round_trip(tmp_path):
     p = DDPMPipeline.from_pretrained(str(tmp_path / "p"), device="cpu")
     _same_buffers(ours, p.unet)
     assert isinstance(p.scheduler, DDPMScheduler) and p.scheduler.config.num_train_timesteps == 1000
+
+
+@pytest.mark.parametrize("name,cls,defaults,micro,spec_fn", CASES, ids=[c[0] for c in CASES])
+def test_reference_state_dict_is_the_exact_inverse_of_packing(tmp_path, name, cls, defaults, micro, spec_fn):
+    """Every shell can rebuild the reference's parameters (names, shapes, values) from its packed buffers, bit for bit."""
+    cfg = dict(defaults)
+    cfg.update(micro)
+    spec = spec_fn(cfg)
+    sd = specs.random_state_dict(spec, seed=7, dtype=torch.bfloat16)
+    m = cls(cfg, sd, dtype=torch.bfloat16, device="cpu")
+    back = m.reference_state_dict()
+    assert list(back) == list(spec)
+    for k, v in sd.items():
+        assert back[k].dtype == torch.bfloat16 and tuple(back[k].shape) == tuple(spec[k]) and torch.equal(back[k], v), k
+    if name == "AutoencoderKL":
+        with pytest.raises(NotImplementedError):  # only the decoder half is held
+            m.save_pretrained(str(tmp_path / "vae"))
+        return
+    m.save_pretrained(str(tmp_path / "m"))
+    raw = checkpoint.load_config(str(tmp_path / "m"))
+    assert raw["_class_name"] == name
+    _same_buffers(m, cls.from_pretrained(str(tmp_path / "m"), device="cpu"))
+    m.save_pretrained(str(tmp_path / "v"), variant="fp16")
+    assert os.path.isfile(tmp_path / "v" / "diffusion_pytorch_model.fp16.safetensors")
+
+
+def test_unet_conv_projection_and_multi_layer_round_trip():
+    """SD-1.x style conv 1x1 proj_in / proj_out come back 4-D; several transformer layers / three levels keep their offsets."""
+    for upd in (dict(MICRO_UNET, use_linear_projection=False),
+                dict(sample_size=16, block_out_channels=(64, 128, 256), cross_attention_dim=128, transformer_layers_per_block=(1, 2, 3),
+                     attention_head_dim=(1, 2, 4), addition_time_embed_dim=32, projection_class_embeddings_input_dim=256)):
+        cfg = dict(specs.SDXL_UNET_CONFIG)
+        cfg.update(upd)
+        spec = specs.unet2d_condition_params(cfg)
+        sd = specs.random_state_dict(spec, seed=9, dtype=torch.bfloat16)
+        back = UNet2DConditionModel(cfg, sd, device="cpu").reference_state_dict()
+        assert all(torch.equal(back[k], sd[k]) for k in sd)
+        if not cfg["use_linear_projection"]:
+            assert back["mid_block.attentions.0.proj_in.weight"].dim() == 4
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference (build container only)")
+def test_unmodified_reference_loads_what_the_shells_save(tmp_path):
+    """shell.save_pretrained -> the reference's own from_pretrained: same parameters, no missing / unexpected keys."""
+    from oracle import ref_shim
+    d = ref_shim.import_reference()
+    for name, cls, defaults, micro, spec_fn in CASES:
+        if name == "AutoencoderKL":
+            continue
+        cfg = dict(defaults)
+        cfg.update(micro)
+        sd = specs.random_state_dict(spec_fn(cfg), seed=11, dtype=torch.bfloat16)
+        cls(cfg, sd, device="cpu").save_pretrained(str(tmp_path / name))
+        ref, info = getattr(d, name).from_pretrained(str(tmp_path / name), torch_dtype=torch.bfloat16, output_loading_info=True)
+        assert not info["missing_keys"] and not info["unexpected_keys"] and not info["mismatched_keys"], info
+        rsd = ref.state_dict()
+        assert all(torch.equal(rsd[k], sd[k]) for k in sd)
