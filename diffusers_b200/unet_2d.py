@@ -37,6 +37,17 @@ class UNet2DModel(torch.nn.Module, FromPretrainedMixin):
         self._n = 0
         if cfg.get("time_embedding_type", "positional") != "positional":
             raise NotImplementedError("only positional time embeddings")
+        # reference options (models/unets/unet_2d.py:95-125) whose non-default values are not implemented: refuse, never ignore
+        only = dict(act_fn=("silu", "swish"), mid_block_type=("UNetMidBlock2D",), downsample_type=("conv",), upsample_type=("conv",),
+                    resnet_time_scale_shift=("default",), center_input_sample=(False,), attn_norm_num_groups=(None,),
+                    class_embed_type=(None,), num_class_embeds=(None,), time_embedding_dim=(None,), downsample_padding=(1,),
+                    mid_block_scale_factor=(1, 1.0))
+        for k, allowed in only.items():
+            if k in cfg and cfg[k] not in allowed:
+                raise NotImplementedError(f"UNet2DModel option {k}={cfg[k]!r} is outside the accelerated hot path (supported: {allowed})")
+        for t in tuple(cfg["down_block_types"]) + tuple(cfg["up_block_types"]):
+            if t not in ("DownBlock2D", "AttnDownBlock2D", "UpBlock2D", "AttnUpBlock2D"):
+                raise NotImplementedError(f"block type {t} is outside the accelerated hot path")
         hd = cfg.get("attention_head_dim", 8)
         if any("Attn" in t for t in tuple(cfg["down_block_types"]) + tuple(cfg["up_block_types"])) or cfg.get("add_attention", True):
             if hd not in (64, 128):
