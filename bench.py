@@ -161,6 +161,11 @@ def cpu_reference(args, full=True):
     return dict(value=ips, unit="images/s", cores=cores, kind="port", sample=sample, t_unet_b2_s=t_unet, setup_s=round(time.time() - t0, 1))
 
 
+def sdxl_workload(args):
+    """config.workload of the headline benchmark: both arms (B200 and reference) report the same string."""
+    return f"sdxl_unet_1024_{args.denoise_steps}step_cfg{args.guidance_scale}_b{args.batch}_per_gpu+vae_decode"
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -168,7 +173,8 @@ def run_reference(args, rank, world):
     line = dict(metric="images/sec @ SDXL 1024^2 50-step", value=cb["value"], unit="images/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1000.0 / cb["value"], higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="bf16", data="synthetic", impl="reference",
-                config=dict(workload="sdxl_unet_1024_50step_cfg_b1", note="reference op sequence on host cores (oracle port), bounded sample"),
+                config=dict(workload=sdxl_workload(args), global_batch=args.batch, parallelism="host cores",
+                            note="reference op sequence on host cores (oracle port), bounded sample"),
                 cpu_baseline={k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 e2e=dict(value=cb["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -335,7 +341,7 @@ def run_b200(args, rank, world, local_rank):
         line = dict(metric="images/sec @ SDXL 1024^2 50-step", value=round(value, 4), unit="images/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16", data="synthetic (random-init weights, N(0,1) text embeddings, seeded latents)",
-                    config=dict(workload=f"sdxl_unet_1024_{args.denoise_steps}step_cfg{args.guidance_scale}_b{B}_per_gpu+vae_decode",
+                    config=dict(workload=sdxl_workload(args),
                                 global_batch=B * world, parallelism=f"dp{world}", cfg_batched=True,
                                 l2="per-step working set >> L2: 5.1 GB of weights stream from HBM every UNet forward",
                                 model="UNet2DConditionModel SDXL-base config (2.567 B params) + AutoencoderKL SDXL decoder"),

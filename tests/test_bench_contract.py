@@ -36,7 +36,8 @@ def test_reference_arm_line(monkeypatch):
     d = json.loads(lines[0])
     assert REQUIRED <= d.keys()
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["metric"].startswith("images/sec") and d["unit"] == "images/s" and "workload" in d["config"]
+    assert d["metric"].startswith("images/sec") and d["unit"] == "images/s"
+    assert d["config"]["workload"] == bench.sdxl_workload(_args()) == "sdxl_unet_1024_50step_cfg7.5_b1_per_gpu+vae_decode"
     assert d["cpu_baseline"] == {k: stub[k] for k in ("value", "unit", "cores", "kind", "sample")}
     assert d["e2e"] == dict(value=stub["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert d["gpu_launches"] == 0 and abs(d["ms_per_step"] - 1000.0 / stub["value"]) < 1e-6
