@@ -107,27 +107,3 @@ def test_conv_gemm_cluster_multicast_sizes(cm):
     summary = p.stdout.split("SUMMARY", 1)[1]
     assert "FAIL" not in summary and "ERROR" not in summary, p.stdout[-3000:]
 
-
-def _attention_cases_under(env_extra, timeout=300):
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cases = [c for c in diag_ops.CASES if c.startswith("attn_")]
-    p = subprocess.run([sys.executable, os.path.join(root, "tools", "diag_ops.py"), "--inproc", *cases], env=dict(os.environ, **env_extra),
-                       capture_output=True, text=True, timeout=timeout)
-    assert "SUMMARY" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
-    summary = p.stdout.split("SUMMARY", 1)[1]
-    assert "FAIL" not in summary and "ERROR" not in summary, p.stdout[-3000:]
-
-
-def test_attention_unpipelined_kernel_still_matches():
-    """head_dim 64 defaults to the pipelined kernel (attention_pipe.cu); the original kernel stays reachable with
-    B200_ATTN_PIPE=0 and must keep passing the same cases."""
-    _attention_cases_under(dict(B200_ATTN_PIPE="0"))
-
-
-@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_EXPERIMENTAL") != "1",
-                    reason="attention_split.cu is experimental and off by default; set B200_TEST_EXPERIMENTAL=1 to try it")
-def test_attention_split_variant_experimental():
-    _attention_cases_under(dict(B200_ATTN_SPLIT="1"), timeout=120)

@@ -1,9 +1,15 @@
-"""BASELINE.json's full sizes on the GPU (SDXL UNet 2.57 B parameters at 1024^2, CFG batch 2; SDXL VAE decode to 1024^2).
+"""(Named test_zz_* so that it runs after the parity suites.)  BASELINE.json's full sizes on the GPU (SDXL UNet 2.57 B parameters at 1024^2, CFG batch 2; SDXL VAE decode to 1024^2).
 No fp32 reference fits the time budget here, so these check size-independent properties of the path:
 determinism, equality of the CUDA-graph replay and the eager launch sequence, and sample independence (the reference has no
 cross-sample operation anywhere in the UNet / VAE: permuting the batch permutes the output)."""
+import os
+import sys
+
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tools import diag_ops  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -72,3 +78,26 @@ def test_sdxl_vae_decode_full_size_properties():
     assert float(d0.mean()) <= 5e-3 * amax + 1e-4
     del m
     torch.cuda.empty_cache()
+
+
+def _attention_cases_under(env_extra, timeout=300):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cases = [c for c in diag_ops.CASES if c.startswith("attn_")]
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "diag_ops.py"), "--inproc", *cases], env=dict(os.environ, **env_extra),
+                       capture_output=True, text=True, timeout=timeout)
+    assert "SUMMARY" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+    summary = p.stdout.split("SUMMARY", 1)[1]
+    assert "FAIL" not in summary and "ERROR" not in summary, p.stdout[-3000:]
+
+
+def test_attention_unpipelined_kernel_still_matches():
+    """head_dim 64 defaults to the pipelined kernel (attention_pipe.cu); the original kernel stays reachable with
+    B200_ATTN_PIPE=0 and must keep passing the same cases."""
+    _attention_cases_under(dict(B200_ATTN_PIPE="0"))
+
+
+@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_EXPERIMENTAL") != "1",
+                    reason="attention_split.cu is experimental and off by default; set B200_TEST_EXPERIMENTAL=1 to try it")
+def test_attention_split_variant_experimental():
+    _attention_cases_under(dict(B200_ATTN_SPLIT="1"), timeout=120)
