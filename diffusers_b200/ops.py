@@ -423,15 +423,26 @@ def transpose_16(x, out=None):
 
 def attention_unfused(q, k, v, *, scale):
     """Single-head attention for head dims the fused kernel does not cover (AutoencoderKL: 512).
-    q [Sq, D], k/v [Sk, D] (row strides arbitrary multiples of 8) -> [Sq, D]."""
+    q [Sq, D], k/v [Sk, D] (row strides arbitrary multiples of 8) -> [Sq, D].
+
+    Both GEMMs hand an activation to b200_conv_gemm as its "weight" operand, whose rows the kernel reads with a stride of
+    rup(K, 64) elements (the packed-weight layout): K = D for Q K^T and K = Sk for P V.  Operands whose K is not a multiple
+    of 64 (e.g. an 800x800 image: Sk = 10000) are therefore staged in zero-padded buffers of that stride."""
     Sq, D = q.shape
     Sk = k.shape[0]
-    s = linear(q, k, Sk, out_fp32=True) if k.stride(0) == D and D % 64 == 0 else None
-    if s is None:
-        kc = k.contiguous()
-        s = linear(q, kc, Sk, out_fp32=True)
+    if Sk % 8 or D % 8:
+        raise B200Error(f"attention_unfused: Sk={Sk} and D={D} must be multiples of 8 (16-byte rows for TMA)")
+    Dp, Skp = (D + 63) // 64 * 64, (Sk + 63) // 64 * 64
+    if k.stride(0) == Dp and k.stride(1) == 1:
+        kc = k
+    else:
+        kc = torch.zeros((Sk, Dp), dtype=k.dtype, device=k.device) if Dp != D else torch.empty((Sk, Dp), dtype=k.dtype, device=k.device)
+        kc[:, :D] = k
+    s = linear(q, kc, Sk, out_fp32=True)
     p = softmax_rows(s, scale, q.dtype)
-    vt = transpose_16(v)  # [D, Sk]: K-major "weights" for the P @ V GEMM
+    # [D, Sk] K-major "weights" for the P @ V GEMM, row stride rup(Sk, 64)
+    vt = torch.zeros((D, Skp), dtype=v.dtype, device=v.device) if Skp != Sk else torch.empty((D, Skp), dtype=v.dtype, device=v.device)
+    transpose_16(v, out=vt[:, :Sk])
     return linear(p, vt, D)
 
 

@@ -40,9 +40,21 @@ class EulerDiscreteScheduler:
     def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
                  prediction_type="epsilon", interpolation_type="linear", timestep_spacing="linspace", steps_offset=0,
                  final_sigmas_type="zero", **unsupported):
+        # Options of the reference constructor (schedulers/scheduling_euler_discrete.py:203-222) this path does not implement:
+        # a non-default value changes the sigma table, so it must fail loudly.  Keys that are NOT in the reference's signature
+        # (legacy entries of published configs: SDXL-base's scheduler_config.json carries `sample_max_value`, `skip_prk_steps`,
+        # `set_alpha_to_one`, `clip_sample`) are ignored with a warning, as the reference's own config loader does
+        # (configuration_utils.py extract_init_dict).
+        not_implemented = dict(trained_betas=(None,), use_karras_sigmas=(None, False), use_exponential_sigmas=(None, False),
+                               use_beta_sigmas=(None, False), sigma_min=(None,), sigma_max=(None,), timestep_type=("discrete",),
+                               rescale_betas_zero_snr=(None, False))
         for k, v in unsupported.items():
-            if v not in (None, False, "discrete"):
-                raise NotImplementedError(f"EulerDiscreteScheduler option {k}={v!r} is outside the hot path")
+            if k in not_implemented:
+                if v not in not_implemented[k]:
+                    raise NotImplementedError(f"EulerDiscreteScheduler option {k}={v!r} is outside the hot path")
+            else:
+                import warnings
+                warnings.warn(f"EulerDiscreteScheduler: config key {k!r} is not an argument of the reference scheduler and is ignored")
         if prediction_type != "epsilon":
             raise NotImplementedError("only prediction_type='epsilon'")
         if interpolation_type != "linear" or final_sigmas_type != "zero":
@@ -167,9 +179,16 @@ class FlowMatchEulerDiscreteScheduler:
 
     def __init__(self, num_train_timesteps=1000, shift=1.0, use_dynamic_shifting=False, base_shift=0.5, max_shift=1.15,
                  base_image_seq_len=256, max_image_seq_len=4096, time_shift_type="exponential", **unsupported):
+        # reference signature: schedulers/scheduling_flow_match_euler_discrete.py:96-113; other keys are ignored with a warning
+        not_implemented = ("invert_sigmas", "shift_terminal", "use_karras_sigmas", "use_exponential_sigmas", "use_beta_sigmas",
+                           "stochastic_sampling")
         for k, v in unsupported.items():
-            if v not in (None, False):
-                raise NotImplementedError(f"FlowMatchEulerDiscreteScheduler option {k}={v!r} is outside the hot path")
+            if k in not_implemented:
+                if v not in (None, False):
+                    raise NotImplementedError(f"FlowMatchEulerDiscreteScheduler option {k}={v!r} is outside the hot path")
+            else:
+                import warnings
+                warnings.warn(f"FlowMatchEulerDiscreteScheduler: config key {k!r} is not an argument of the reference scheduler and is ignored")
         if time_shift_type != "exponential":
             raise NotImplementedError("only exponential time shift")
         self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, shift=shift,

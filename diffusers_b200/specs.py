@@ -284,14 +284,19 @@ def flux_params(cfg):
 def random_state_dict(spec, seed=0, dtype=torch.bfloat16, device="cpu"):
     """Random weights with torch's default-init distributions (kaiming-uniform bound 1/sqrt(fan_in) for
     Linear/Conv weights and biases, ones/zeros for norms).  Values differ from a seeded reference module;
-    parity tests use fixtures exported from the reference instead."""
-    g = torch.Generator(device="cpu").manual_seed(seed)
+    parity tests use fixtures exported from the reference instead.
+
+    device="cpu" (default) draws from a CPU generator: the stream the committed fixtures (tests/golden) were recorded
+    with.  A CUDA device draws from that device's Philox generator instead (different values, same distributions): the
+    11.9 B parameters of the Flux.1-dev shape take seconds instead of minutes."""
+    device = torch.device(device)
+    g = torch.Generator(device=device if device.type == "cuda" else "cpu").manual_seed(seed)
     sd = {}
     for name, shape in spec.items():
         is_norm = (".norm" in name or name.startswith("norm") or "group_norm" in name or "conv_norm_out" in name) \
             and len(shape) == 1 and not name.endswith("linear.bias")
         if is_norm:
-            t = torch.ones(shape) if name.endswith("weight") else torch.zeros(shape)
+            t = torch.ones(shape, device=g.device) if name.endswith("weight") else torch.zeros(shape, device=g.device)
         else:
             if len(shape) > 1:
                 fan_in = math.prod(shape[1:])
@@ -299,6 +304,6 @@ def random_state_dict(spec, seed=0, dtype=torch.bfloat16, device="cpu"):
                 w = spec.get(name[:-4] + "weight")
                 fan_in = math.prod(w[1:]) if w is not None and len(w) > 1 else shape[0]
             bound = 1.0 / math.sqrt(fan_in)
-            t = (torch.rand(shape, generator=g) * 2 - 1) * bound
+            t = (torch.rand(shape, generator=g, device=g.device) * 2 - 1) * bound
         sd[name] = t.to(dtype=dtype, device=device)
     return sd

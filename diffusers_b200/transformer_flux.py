@@ -224,7 +224,8 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
     def random_init(cls, config=None, seed=0, dtype=torch.bfloat16, device="cuda"):
         cfg = dict(specs.FLUX_DEV_CONFIG)
         cfg.update(config or {})
-        sd = specs.random_state_dict(specs.flux_params(cfg), seed=seed, dtype=dtype)
+        # weights drawn on the target device (seconds for 11.9 B parameters on a GPU); device="cpu" keeps the CPU stream
+        sd = specs.random_state_dict(specs.flux_params(cfg), seed=seed, dtype=dtype, device=device if torch.device(device).type == "cuda" else "cpu")
         return cls(cfg, sd, dtype=dtype, device=device)
 
     # ------------------------------------------------------------------ step-invariant pieces

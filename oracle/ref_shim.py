@@ -1,31 +1,18 @@
-"""Import helper for the REAL reference (huggingface/diffusers at /root/reference) - build container only.
-
-Used exclusively by oracle/make_golden.py and by CPU tests that pin the oracle; nothing that runs on the GPU
-box may import this (the reference does not exist there).  The two huggingface_hub symbols are only used by
-DiffusionPipeline.download (pipelines/pipeline_utils.py:1669-1685) and are missing from the installed hub.
-"""
+"""Import helper for the REAL reference (huggingface/diffusers), used by oracle/make_golden.py and by tests that pin
+the oracle or drive the shells from the unmodified reference.  The work is done by baseline/ref_env.py (installed copy
+under baseline/_ref first, /root/reference/src in the build container otherwise)."""
 import os
 import sys
 
-REFERENCE_SRC = "/root/reference/src"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from baseline import ref_env  # noqa: E402
+
+REFERENCE_SRC = ref_env.SOURCE_TREE
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE_SRC, "diffusers"))
+    return ref_env.available()
 
 
 def import_reference():
-    if not available():
-        raise ImportError("reference not present (expected on the GPU box)")
-    import huggingface_hub
-    import huggingface_hub.errors
-    if not hasattr(huggingface_hub, "get_cached_repo_tree"):
-        huggingface_hub.get_cached_repo_tree = lambda *a, **k: []
-    if not hasattr(huggingface_hub.errors, "CachedRepoTreeNotFoundError"):
-        class CachedRepoTreeNotFoundError(Exception):
-            pass
-        huggingface_hub.errors.CachedRepoTreeNotFoundError = CachedRepoTreeNotFoundError
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
-    import diffusers
-    return diffusers
+    return ref_env.import_reference()

@@ -145,6 +145,30 @@ def test_scheduler_configs(tmp_path):
     assert fm.config.use_dynamic_shifting and fm.config.max_shift == 1.15
 
 
+def test_published_sdxl_scheduler_config_with_legacy_keys(tmp_path):
+    """The scheduler_config.json that ships with stabilityai/stable-diffusion-xl-base-1.0 (quoted here: the file is not in the
+    reference tree and there is no network) still carries keys of older scheduler classes.  The reference drops keys that are
+    not in the scheduler's signature with a warning (configuration_utils.py extract_init_dict); so must the shell, and the
+    resulting tables must equal the ones of the explicit SDXL construction."""
+    published = {"_class_name": "EulerDiscreteScheduler", "_diffusers_version": "0.19.0.dev0", "beta_end": 0.012, "beta_schedule": "scaled_linear",
+                 "beta_start": 0.00085, "clip_sample": False, "interpolation_type": "linear", "num_train_timesteps": 1000,
+                 "prediction_type": "epsilon", "sample_max_value": 1.0, "set_alpha_to_one": False, "skip_prk_steps": True, "steps_offset": 1,
+                 "timestep_spacing": "leading", "trained_betas": None, "use_karras_sigmas": False}
+    os.makedirs(tmp_path / "scheduler")
+    with open(tmp_path / "scheduler" / "scheduler_config.json", "w") as f:
+        json.dump(published, f)
+    with pytest.warns(UserWarning, match="skip_prk_steps"):
+        s = EulerDiscreteScheduler.from_pretrained(str(tmp_path), subfolder="scheduler")
+    ref = EulerDiscreteScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="leading", steps_offset=1)
+    s.set_timesteps(50)
+    ref.set_timesteps(50)
+    assert torch.equal(s.sigmas, ref.sigmas) and torch.equal(s.timesteps, ref.timesteps)
+    # reference-signature options this path does not implement still fail loudly
+    for bad in (dict(use_karras_sigmas=True), dict(rescale_betas_zero_snr=True), dict(timestep_type="continuous"), dict(sigma_min=0.1)):
+        with pytest.raises(NotImplementedError):
+            EulerDiscreteScheduler.from_config({**published, **bad})
+
+
 def test_reference_written_pipeline_directory():
     """tests/golden/ckpt_sdxl_micro was written by the reference's own StableDiffusionXLPipeline.save_pretrained
     (oracle/make_golden.py checkpoints)."""

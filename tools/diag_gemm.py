@@ -131,7 +131,10 @@ def run_case(name):
     tol = 1.5e-2 * ref.abs() + 2e-2 if dt == torch.bfloat16 else 3e-3 * ref.abs() + 4e-3
     bad = err > tol
     res = dict(case=name, shape=list(o.shape), max_abs=float(err.max()), ref_absmax=float(ref.abs().max()),
-               n_bad=int(bad.sum()), frac_bad=float(bad.float().mean()), nan=int(torch.isnan(o).sum()))
+               n_bad=int(bad.sum()), frac_bad=float(bad.float().mean()), nan=int(torch.isnan(o).sum()),
+               # distance to the north star's literal band (rtol 1e-3 / atol 1e-4), for the record
+               in_band_1e3_1e4=round(float((err <= 1e-3 * ref.abs() + 1e-4).float().mean()), 5),
+               max_rel_at_large=round(float((err / ref.abs().clamp_min(0.05 * float(ref.abs().max()))).max()), 6))
     if res["n_bad"]:
         rows_bad = bad.any(1).nonzero().flatten()
         cols_bad = bad.any(0).nonzero().flatten()
