@@ -1,19 +1,28 @@
 #!/usr/bin/env python
-"""Headline benchmark (BASELINE.json): images/sec, SDXL 1024x1024, 50 Euler steps, CFG, bf16, batch 1 per GPU.
+"""Headline benchmark (BASELINE.json): images/sec @ SDXL 1024^2 50-step & latents/sec @ Flux 1024^2 28-step, 1/2/4/8 B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload sdxl|flux|vae]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload all|sdxl|flux|vae]
 
-A "step" is one full pass of the hot path over one batch: one image = 50 x (CFG-batched UNet forward + fused
-CFG/Euler step) + VAE decode to a (1,3,1024,1024) tensor (output_type="pt").  Prints ONE JSON line (rank 0).
-  value : images/s, embeddings already resident in HBM when the timed region starts (seeded latent draw included)
-  e2e   : same metric through the public pipeline call with HOST (pinned) embeddings: H2D of the embeddings and
-          D2H of the finished image inside the timed region
-  roofline : the dominant kernel (conv_gemm_kernel: every Linear and Conv of the UNet) timed launch by launch with
-          CUDA events on the launching stream in a separate eager pass of one UNet forward; achieved = algorithmic
-          FLOPs of those launches / their summed duration, peak = measured sustained bf16 GEMM (MEASURED_PEAKS.json)
-  cpu_baseline : the oracle port (the reference's op sequence in torch on the host cores) on a bounded sample
---impl reference times that CPU port as the reference arm.  Multi-GPU: one process per GPU (torchrun), each rank
-samples its own image (weak scaling), one all-gather of the decoded images per step, max-over-ranks device timing.
+ONE JSON line (rank 0).  Top level = BASELINE config 1: SDXL UNet 1024^2 bf16, batch 1 per GPU (CFG -> 2 samples per
+forward), 50 Euler steps + VAE decode to a (1,3,1024,1024) tensor; a "step" is one whole image.
+  value    : images/s, embeddings already resident in HBM when the timed region starts (seeded latent draw included)
+  e2e      : the same through the public pipeline call with HOST (pinned) embeddings: H2D of the embeddings and D2H of the
+             finished image inside the timed region
+  roofline : the dominant kernel (conv_gemm_kernel: every Linear and Conv) timed launch by launch with CUDA events on the
+             launching stream in a separate eager forward; achieved = algorithmic FLOPs / summed duration; peak = measured
+             sustained bf16 GEMM (MEASURED_PEAKS.json).  `attention` = the same for the attention launches.
+  cpu_baseline : the reference's own CPU path on a bounded sample (see cpu_reference)
+  reference_cuda_eager : the UNMODIFIED reference UNet's CUDA-eager forward on the same B200 (cuBLASLt / cuDNN / SDPA): the
+             "existing sm_100 kernel" bar at model level (only when baseline/_ref is on the box)
+With --workload all (default) the line also carries
+  flux     : BASELINE config 2 - latents/s, FluxTransformer2DModel Flux.1-dev shape, 28 FlowMatch steps (value, e2e, roofline of
+             its GEMM and head_dim-128 attention launches, clocks)
+  vae      : BASELINE config 4 - AutoencoderKL.decode 128^2 latent -> 1024^2, batch sweep 1 / 8 / 64
+  config3  : (N > 1 only) BASELINE config 3 - SDXL batch 4 per GPU (global 32 at N = 8) through parallel.sdxl_data_parallel:
+             one seeded full-batch latent draw sliced per rank, one all-gather of the decoded images, D2H once on rank 0
+--impl reference times the UNMODIFIED reference (baseline/_ref) through its own StableDiffusionXLPipeline on the host cores.
+Multi-GPU: one process per GPU (torchrun), each rank samples its own image (weak scaling), one all-gather of the decoded
+images per step, max-over-ranks device timing.
 """
 import argparse
 import json
@@ -27,12 +36,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-UNET_FLOP_PER_SAMPLE = 6.7612e12      # BASELINE.md §3 (FlopCounterMode on the reference, meta device)
-UNET_GEMM_FLOP_PER_SAMPLE = (3325.3 + 1623.1 + 1028.9) * 1e9  # addmm + conv + mm: what conv_gemm_kernel executes
+UNET_FLOP_PER_SAMPLE = 6.7612e12      # BASELINE.md section 3 (FlopCounterMode on the reference, meta device)
 VAE_FLOP_PER_IMAGE = 10.470e12
 FLUX_FLOP_PER_FORWARD = 74.385e12
-IMAGE_FLOP = 2 * 50 * UNET_FLOP_PER_SAMPLE + VAE_FLOP_PER_IMAGE  # 686.6 TFLOP
 SDXL_SCHED = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="leading", steps_offset=1)
+FLUX_SCHED = dict(shift=3.0, use_dynamic_shifting=True, base_shift=0.5, max_shift=1.15, base_image_seq_len=256, max_image_seq_len=4096)
 
 
 def peaks():
@@ -98,67 +106,154 @@ def synthetic_embeds(batch, dtype, pin):
     return t
 
 
-# ----------------------------------------------------------------------------------------------- reference arm
-MID_BLOCK_SHARE = 797.3 / 6761.2  # per-block FLOPs of one SDXL UNet sample-forward (GF)
+# ----------------------------------------------------------------------------------------------- reference arm (host cores)
+def one_numa_node_physical_cores():
+    """One logical CPU per physical core of NUMA node 0 (all of this process's CPUs when sysfs is silent): oversubscribing
+    both NUMA nodes / hyperthreads made the round-1 CPU arm vary 10x between boxes."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return list(range(os.cpu_count() or 1))
+
+    def parse(s):
+        out = []
+        for part in s.strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                out += list(range(int(a), int(b) + 1))
+            elif part:
+                out.append(int(part))
+        return out
+
+    try:
+        with open("/sys/devices/system/node/node0/cpulist") as f:
+            node0 = [c for c in parse(f.read()) if c in allowed]
+    except OSError:
+        node0 = allowed
+    node0 = node0 or allowed
+    seen, cores = set(), []
+    for c in node0:
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                sib = tuple(parse(f.read()))
+        except OSError:
+            sib = (c,)
+        if sib not in seen:
+            seen.add(sib)
+            cores.append(c)
+    return cores or allowed
+
+
+def cpu_has_fast_bf16():
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = f.read()
+        return "amx_bf16" in flags or "avx512_bf16" in flags
+    except OSError:
+        return False
 
 
 def cpu_reference(args, full=True):
-    """The oracle port (the reference's op sequence on torch CPU kernels, all host threads) on a BOUNDED sample:
-    the SDXL UNet mid block (ResnetBlock2D + 10-layer Transformer2DModel + ResnetBlock2D at 32x32, CFG batch 2) =
-    11.79 % of a UNet forward's FLOPs; t_forward = t_mid / 0.1179.  dtype = whichever of bf16 / fp32 this host's
-    GEMM kernels run faster (bf16 is fast only with AMX / AVX512-BF16), stated in `sample`."""
+    """The reference's CPU implementation of the path on a BOUNDED sample, on the physical cores of one NUMA node.
+
+    With baseline/_ref on the box (kind "reference"): the UNMODIFIED `diffusers.StableDiffusionXLPipeline.__call__`
+    (pipeline_stable_diffusion_xl.py:823) around the reference's own UNet2DConditionModel (SDXL-base config, 2.567 B random
+    parameters) / EulerDiscreteScheduler / AutoencoderKL, batch 1 with CFG (two samples per UNet forward), n denoising steps
+    with output_type="latent", plus (full=True) one `vae.decode` of the 128^2 latent; images/s = 1 / (50 * t_step + t_vae).
+    Without it (kind "port"): the oracle's restatement of the same forward (oracle/unet.py) on the same inputs.
+    dtype: bf16 when the host has AMX-bf16 / AVX512-bf16 (the reference's own choice for this workload),
+    fp32 otherwise - stated in `sample` and in the returned dict."""
+    from baseline import ref_env
     from diffusers_b200 import specs
-    from oracle import blocks as Bk
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = one_numa_node_physical_cores()
+    prev_aff = None
+    try:
+        prev_aff = os.sched_getaffinity(0)
+        os.sched_setaffinity(0, cores)
+    except (AttributeError, OSError):
+        pass
+    prev_threads = torch.get_num_threads()
+    torch.set_num_threads(len(cores))
+    dt = torch.bfloat16 if cpu_has_fast_bf16() else torch.float32
+    dname = "bf16" if dt == torch.bfloat16 else "fp32"
     t0 = time.time()
-
-    def probe(dt):
-        # the op mix of the block (3x3 conv, token GEMM, attention) at reduced size; a GEMM alone is misleading: hosts
-        # with a fast bf16 GEMM can still run bf16 convolutions / attention several times slower than fp32
-        import torch.nn.functional as F
-        xc, wc = torch.randn(2, 320, 32, 32).to(dt), torch.randn(320, 320, 3, 3).to(dt)
-        a, b = torch.randn(2048, 1280).to(dt), torch.randn(1280, 1280).to(dt)
-        q = torch.randn(2, 20, 1024, 64).to(dt)
-
-        def once():
-            F.conv2d(xc, wc, padding=1)
-            a @ b
-            F.scaled_dot_product_attention(q, q, q)
-
-        once()
-        t = time.perf_counter()
-        for _ in range(2):
-            once()
-        return (time.perf_counter() - t) / 2
-
-    dt = torch.bfloat16 if probe(torch.bfloat16) < probe(torch.float32) else torch.float32
-    spec = {k[len("mid_block."):]: v for k, v in specs.unet2d_condition_params(specs.SDXL_UNET_CONFIG).items() if k.startswith("mid_block.")}
-    sd = {"mid_block." + k: v for k, v in specs.random_state_dict(spec, seed=0, dtype=dt).items()}
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(2, 1280, 32, 32, generator=g).to(dt)
-    emb = torch.randn(2, 1280, generator=g).to(dt)
-    ehs = torch.randn(2, 77, 2048, generator=g).to(dt)
-    fwd = lambda: Bk.unet_mid_block_2d_cross_attn(sd, "mid_block", x, emb, ehs, heads=20, groups=32, eps=1e-5, use_linear_projection=True)  # noqa: E731
+    cfg = dict(specs.SDXL_UNET_CONFIG)
+    sd = specs.random_state_dict(specs.unet2d_condition_params(cfg), seed=0, dtype=dt)
+    emb = synthetic_embeds(1, dt, pin=False)
+    n_steps = max(1, min(args.steps, 3)) if full else 2
+    n_warm = 1
+    times = []
     with torch.no_grad():
-        n_w, n_t = (max(1, min(args.warmup, 2)), max(1, min(args.steps, 5))) if full else (1, 2)
-        for _ in range(n_w):
+        if ref_env.available():
+            kind = "reference"
+            diffusers = ref_env.import_reference()
+            import inspect
+            allowed = set(inspect.signature(diffusers.UNet2DConditionModel.__init__).parameters)
+            with torch.device("meta"):
+                unet = diffusers.UNet2DConditionModel(**{k: v for k, v in cfg.items() if k in allowed})
+            unet.load_state_dict(sd, assign=True)
+            unet.eval()
+            vae = diffusers.AutoencoderKL(**{k: v for k, v in specs.SDXL_VAE_CONFIG.items() if k in inspect.signature(diffusers.AutoencoderKL.__init__).parameters})
+            vae = vae.to(dt).eval()
+            pipe = diffusers.StableDiffusionXLPipeline(vae=vae, text_encoder=None, text_encoder_2=None, tokenizer=None, tokenizer_2=None, unet=unet,
+                                                       scheduler=diffusers.EulerDiscreteScheduler(**SDXL_SCHED))
+            pipe.set_progress_bar_config(disable=True)
+
+            def steps(n, seed):
+                return pipe(**emb, height=1024, width=1024, num_inference_steps=n, guidance_scale=args.guidance_scale,
+                            generator=torch.Generator().manual_seed(seed), output_type="latent").images
+
+            steps(n_warm, 0)
+            for i in range(2):  # two independent timed runs: the spread is reported
+                a = time.perf_counter()
+                lat = steps(n_steps, 1 + i)
+                times.append((time.perf_counter() - a) / n_steps)
+                if sum(times) * n_steps > 60:
+                    break
+            t_vae = None
+            if full:
+                a = time.perf_counter()
+                vae.decode(lat / vae.config.scaling_factor, return_dict=False)
+                t_vae = time.perf_counter() - a
+        else:
+            kind = "port"
+            from oracle import unet as ounet
+            g = torch.Generator().manual_seed(0)
+            x = torch.randn(2, 4, 128, 128, generator=g).to(dt)
+            ehs = torch.cat([emb["negative_prompt_embeds"], emb["prompt_embeds"]])
+            added = dict(text_embeds=torch.cat([emb["negative_pooled_prompt_embeds"], emb["pooled_prompt_embeds"]]),
+                         time_ids=torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * 2).to(dt))
+            fwd = lambda: ounet.unet2d_condition_forward(sd, cfg, x, torch.tensor(981.0), ehs, added)  # noqa: E731
             fwd()
-        ts = []
-        for _ in range(n_t):
-            a = time.perf_counter()
-            fwd()
-            ts.append(time.perf_counter() - a)
-            if sum(ts) > 40:
-                break
-    t_mid = sum(ts) / len(ts)
-    t_unet = t_mid / MID_BLOCK_SHARE
-    t_vae = t_unet * VAE_FLOP_PER_IMAGE / (2 * UNET_FLOP_PER_SAMPLE)  # same FLOP rate assumed for the decode
-    ips = 1.0 / (50 * t_unet + t_vae)
-    sample = (f"{len(ts)} timed passes of the SDXL UNet mid block (B=2, 32x32, {str(dt).split('.')[-1]}; {t_mid:.2f} s each = "
-              f"{100 * MID_BLOCK_SHARE:.2f}% of a CFG-batched UNet forward by FLOPs -> {t_unet:.1f} s/forward); "
-              f"images/s = 1/(50*t_forward + t_vae), t_vae scaled by FLOPs")
-    return dict(value=ips, unit="images/s", cores=cores, kind="port", sample=sample, t_unet_b2_s=t_unet, setup_s=round(time.time() - t0, 1))
+            for i in range(2):
+                a = time.perf_counter()
+                for _ in range(n_steps):
+                    fwd()
+                times.append((time.perf_counter() - a) / n_steps)
+                if sum(times) * n_steps > 60:
+                    break
+            t_vae = None
+    t_step = sum(times) / len(times)
+    if t_vae is None:
+        t_vae = t_step * VAE_FLOP_PER_IMAGE / (2 * UNET_FLOP_PER_SAMPLE)  # same FLOP rate assumed for the decode
+        vae_note = "t_vae scaled from t_step by FLOPs"
+    else:
+        vae_note = f"t_vae measured once: {t_vae:.2f} s"
+    ips = 1.0 / (args.denoise_steps * t_step + t_vae)
+    spread = (max(times) - min(times)) / t_step if len(times) > 1 else 0.0
+    what = ("unmodified diffusers.StableDiffusionXLPipeline (reference UNet2DConditionModel SDXL-base config + EulerDiscreteScheduler)"
+            if kind == "reference" else "oracle port of UNet2DConditionModel.forward")
+    sample = (f"{what}, batch 1 with CFG (2 samples per forward), {dname}, {len(cores)} threads pinned to the physical cores of NUMA node 0: "
+              f"{len(times)} runs of {n_steps} denoising step(s) after {n_warm} warm-up = {', '.join(f'{t:.2f}' for t in times)} s per step "
+              f"(spread {100 * spread:.0f}%); {vae_note}; images/s = 1 / ({args.denoise_steps} * t_step + t_vae)")
+    try:
+        if prev_aff is not None:
+            os.sched_setaffinity(0, prev_aff)
+    except OSError:
+        pass
+    torch.set_num_threads(prev_threads)
+    return dict(value=ips, unit="images/s", cores=len(cores), kind=kind, sample=sample, dtype=dname, t_step_s=round(t_step, 3),
+                t_step_runs_s=[round(t, 3) for t in times], run_spread=round(spread, 3), setup_s=round(time.time() - t0, 1))
 
 
 def sdxl_workload(args):
@@ -172,58 +267,89 @@ def run_reference(args, rank, world):
     cb = cpu_reference(args, full=True)
     line = dict(metric="images/sec @ SDXL 1024^2 50-step", value=cb["value"], unit="images/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1000.0 / cb["value"], higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="bf16", data="synthetic", impl="reference",
-                config=dict(workload=sdxl_workload(args), global_batch=args.batch, parallelism="host cores",
-                            note="reference op sequence on host cores (oracle port), bounded sample"),
-                cpu_baseline={k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                dtype=cb["dtype"], data="synthetic (random-init weights, N(0,1) text embeddings, seeded latents)", impl="reference",
+                config=dict(workload=sdxl_workload(args), global_batch=args.batch, parallelism=f"host cores ({cb['cores']} threads, one NUMA node)",
+                            note="bounded sample of the workload (a few denoising steps + one decode), extrapolated to 50 steps: see cpu_baseline.sample"),
+                cpu_baseline={k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "dtype", "t_step_runs_s", "run_spread")},
                 e2e=dict(value=cb["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
 
 
-# ----------------------------------------------------------------------------------------------- B200 arm
-def gemm_roofline(unet, B2, pk):
-    """Eager pass of one UNet forward with CUDA events around every conv_gemm launch."""
+# ----------------------------------------------------------------------------------------------- B200 arm: rooflines
+def profiled(fn):
+    """Runs fn() once with CUDA events around every conv_gemm / attention launch; returns (launch list, total ms)."""
     from diffusers_b200 import ops
-    dev, dt = unet.device, unet.dtype
+    torch.cuda.synchronize()
+    ops._PROFILE = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        prof, ops._PROFILE = ops._PROFILE, None
+    return [(a.elapsed_time(b), fl, kern, shape) for a, b, fl, kern, shape in prof], e0.elapsed_time(e1)
+
+
+def kernel_roofline(prof, total_ms, kern, pk, extra=None):
+    rows = [p for p in prof if p[2] == kern]
+    if not rows:
+        return None
+    ms = sum(p[0] for p in rows)
+    flops = sum(p[1] for p in rows)
+    ach = flops / (ms * 1e-3) / 1e12
+    by_shape = {}
+    for t, fl, _, shape in rows:
+        d = by_shape.setdefault(shape, [0, 0.0, 0.0])
+        d[0] += 1
+        d[1] += t
+        d[2] += fl
+    top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:4]
+    out = dict(bound="tensor", achieved=round(ach, 1), peak=pk["tflops"], unit="TFLOP/s", frac=round(ach / pk["tflops"], 4), traffic=None,
+               kernel=kern, launches_per_forward=len(rows), algorithmic_flop_per_forward=flops, avg_launch_us=round(1000 * ms / len(rows), 2),
+               kernel_ms_per_forward=round(ms, 3), forward_ms_eager=round(total_ms, 3), share_of_forward=round(ms / total_ms, 3),
+               top_shapes=[dict(shape=list(s), launches=c, us_per_launch=round(1000 * t / c, 1), tflops=round(fl / t / 1e9, 1)) for s, (c, t, fl) in top],
+               peak_source=pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)")
+    if extra:
+        out.update(extra)
+    return out
+
+
+def conv_gemm_traffic():
+    """DRAM traffic of conv_gemm's most frequent launch (linear 2048x1280x1280 + bias + residual, 192 per forward) from the
+    committed `ncu --set full` capture; its algorithmic bytes are x 5.24 MB + W 3.28 MB + residual 5.24 MB read (the 5.24 MB
+    output stays in L2) = 13.77 MB."""
+    for name in ("r2_conv_gemm_traffic.json", "r1_conv_gemm_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            with open(tp) as f:
+                cap = json.load(f)["launches"][0]
+            return dict(traffic=cap["dram_bytes_read"] + cap["dram_bytes_write"],
+                        traffic_note=f"bytes per launch of '{cap['launch']}' (ncu --set full capture, profiles/{name}); algorithmic 13.77e6")
+    return dict(traffic=None)
+
+
+def sdxl_unet_inputs(B2, dev, dt):
     g = torch.Generator(device=dev).manual_seed(0)
     x = torch.randn(B2, 4, 128, 128, generator=g, device=dev).to(dt)
     ehs = torch.randn(B2, 77, 2048, generator=g, device=dev).to(dt)
     added = dict(text_embeds=torch.randn(B2, 1280, generator=g, device=dev).to(dt),
                  time_ids=torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * B2, device=dev).to(dt))
-    t = torch.tensor(981.0, device=dev)
+    return x, torch.tensor(981.0, device=dev), ehs, added
+
+
+def sdxl_rooflines(unet, B2, pk):
+    """Eager pass of one UNet forward with CUDA events around every conv_gemm / attention launch."""
+    x, t, ehs, added = sdxl_unet_inputs(B2, unet.device, unet.dtype)
     was = unet.use_cuda_graph
     unet.enable_cuda_graph(False)
+    fwd = lambda: unet(x, t, ehs, added_cond_kwargs=added, return_dict=False)  # noqa: E731
     for _ in range(2):
-        unet(x, t, ehs, added_cond_kwargs=added, return_dict=False)
-    torch.cuda.synchronize()
-    ops._PROFILE = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    unet(x, t, ehs, added_cond_kwargs=added, return_dict=False)
-    e1.record()
-    torch.cuda.synchronize()
-    prof, ops._PROFILE = ops._PROFILE, None
+        fwd()
+    prof, total = profiled(fwd)
     unet.use_cuda_graph = was
-    ms = [a.elapsed_time(b) for a, b, *_ in prof]
-    flops = sum(p[2] for p in prof)
-    total_ms = sum(ms)
-    ach = flops / (total_ms * 1e-3) / 1e12
-    # DRAM traffic of the kernel's most frequent launch (linear 2048x1280x1280 + bias + residual, 192 per forward) from the
-    # committed `ncu --set full` capture; its algorithmic bytes are x 5.24 MB + W 3.28 MB + residual 5.24 MB read (the
-    # 5.24 MB output stays in L2) = 13.77 MB, i.e. no re-reads reach HBM
-    traffic, traffic_note = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_conv_gemm_traffic.json")
-    if os.path.exists(tp):
-        with open(tp) as f:
-            cap = json.load(f)["launches"][0]
-        traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
-        traffic_note = f"bytes per launch of '{cap['launch']}' (ncu --set full capture, profiles/r1_ncu_full_hot_kernels.txt); algorithmic 13.77e6"
-    return dict(bound="tensor", achieved=round(ach, 1), peak=pk["tflops"], unit="TFLOP/s", frac=round(ach / pk["tflops"], 4), traffic=traffic,
-                traffic_note=traffic_note,
-                kernel="conv_gemm_kernel", launches_per_forward=len(prof), algorithmic_flop_per_forward=flops,
-                avg_launch_us=round(1000 * total_ms / len(prof), 2), kernel_ms_per_forward=round(total_ms, 3),
-                forward_ms_eager=round(e0.elapsed_time(e1), 3), share_of_forward=round(total_ms / e0.elapsed_time(e1), 3),
-                peak_source=pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)")
+    return kernel_roofline(prof, total, "conv_gemm", pk, conv_gemm_traffic()), kernel_roofline(prof, total, "attention", pk)
 
 
 def hbm_kernel_rooflines(dev, dt, pk):
@@ -256,9 +382,8 @@ def hbm_kernel_rooflines(dev, dt, pk):
     gam, bet = torch.randn(320, generator=g, device=dev).to(dt), torch.randn(320, generator=g, device=dev).to(dt)
     us = timed(lambda i: ops.group_norm(xs[i % 8], batch=2, hw=16384, groups=32, eps=1e-5, gamma=gam, beta=bet, silu=True, out=ys[i % 8]))
     nbytes = 2 * xs[0].numel() * 2
-    out.append(dict(kernel="group_norm_stats+apply (+SiLU)", shape="2x16384x320", algorithmic_bytes=nbytes, us=round(us, 2),
-                    achieved_gbs=round(nbytes / us / 1e3, 1), frac=round(nbytes / us / 1e3 / pk["hbm_gbs"], 4),
-                    note="two launches; the statistics pass re-reads the input (3 passes over 21 MB for 2 algorithmic)"))
+    out.append(dict(kernel="group_norm (+SiLU)", shape="2x16384x320", algorithmic_bytes=nbytes, us=round(us, 2),
+                    achieved_gbs=round(nbytes / us / 1e3, 1), frac=round(nbytes / us / 1e3 / pk["hbm_gbs"], 4)))
     xl = [torch.randn(2048, 1280, generator=g, device=dev).to(dt) for _ in range(32)]
     yl = [torch.empty_like(x) for x in xl]
     lg, lb = torch.randn(1280, generator=g, device=dev).to(dt), torch.randn(1280, generator=g, device=dev).to(dt)
@@ -269,18 +394,86 @@ def hbm_kernel_rooflines(dev, dt, pk):
     return out
 
 
-def run_b200(args, rank, world, local_rank):
-    import torch.distributed as dist
-    from diffusers_b200 import ops, parallel, specs
+def reference_cuda_eager(unet_cfg, dev, dt):
+    """The unmodified reference UNet2DConditionModel in CUDA eager on this GPU (same config, random weights): ms per CFG forward."""
+    from baseline import ref_env
+    from diffusers_b200 import specs
+    if not ref_env.available():
+        return None
+    import inspect
+    diffusers = ref_env.import_reference()
+    allowed = set(inspect.signature(diffusers.UNet2DConditionModel.__init__).parameters)
+    with torch.device("meta"):
+        m = diffusers.UNet2DConditionModel(**{k: v for k, v in unet_cfg.items() if k in allowed})
+    sd = specs.random_state_dict(specs.unet2d_condition_params(unet_cfg), seed=0, dtype=dt, device=dev)
+    m.load_state_dict(sd, assign=True)
+    m.eval()
+    x, t, ehs, added = sdxl_unet_inputs(2, dev, dt)
+    with torch.no_grad():
+        for _ in range(3):
+            m(x, t, ehs, added_cond_kwargs=added, return_dict=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            m(x, t, ehs, added_cond_kwargs=added, return_dict=False)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    del m, sd
+    torch.cuda.empty_cache()
+    return dict(unet_forward_ms=round(ms, 2), tflops=round(2 * UNET_FLOP_PER_SAMPLE / ms / 1e9, 1),
+                note="diffusers UNet2DConditionModel.forward, bf16 CUDA eager (cuBLASLt / cuDNN / SDPA), CFG batch 2, 5 timed forwards")
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm: workloads
+class Ctx:
+    def __init__(self, args, rank, world, local_rank):
+        self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.dt = torch.bfloat16
+        self.pk = peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, n, body):
+        """barrier + sync, n x body(i) between CUDA events, barrier + sync; max over ranks.  Returns (ms, launches)."""
+        from diffusers_b200 import ops
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ops.launches()
+        e0.record()
+        for i in range(n):
+            body(i)
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, ops.launches() - n0
+
+
+def to_host(t):
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    return out
+
+
+def sdxl_section(cx):
+    from diffusers_b200 import parallel, specs
     from diffusers_b200.autoencoder_kl import AutoencoderKL
     from diffusers_b200.pipelines import StableDiffusionXLPipeline
     from diffusers_b200.schedulers import EulerDiscreteScheduler
     from diffusers_b200.unet_2d_condition import UNet2DConditionModel
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dt = torch.bfloat16
-    pk = peaks()
+    args, dev, dt, world, pk = cx.args, cx.dev, cx.dt, cx.world, cx.pk
     unet = UNet2DConditionModel.random_init(seed=0, dtype=dt, device=dev)
     vae = AutoencoderKL.random_init(seed=0, dtype=dt, device=dev)
     pipe = StableDiffusionXLPipeline(vae, unet, EulerDiscreteScheduler(**SDXL_SCHED))
@@ -288,204 +481,224 @@ def run_b200(args, rank, world, local_rank):
     host = synthetic_embeds(B, dt, pin=True)
     resident = {k: v.to(dev) for k, v in host.items()}
     call = dict(height=1024, width=1024, num_inference_steps=args.denoise_steps, guidance_scale=args.guidance_scale, output_type="pt")
+    gather = world > 1 and B * world > 1
 
-    def one_image(emb, seed, to_host):
+    def one_image(emb, seed, host_out):
         img = pipe(generator=torch.Generator(device=dev).manual_seed(seed), **emb, **call).images
-        if world > 1:
-            img = parallel.all_gather_batch(img, B * world) if B * world > 1 else img
-        if to_host:
-            out = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
-            out.copy_(img, non_blocking=True)
-            return out
+        if gather:
+            img = parallel.all_gather_batch(img, B * world)
+        if host_out and (cx.rank == 0 or not gather):
+            return to_host(img)
         return img
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(emb_fn, to_host):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = ops.launches()
-        e0.record()
-        for i in range(args.steps):
-            one_image(emb_fn(), 1000 + i, to_host)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms, ops.launches() - n0
 
     for i in range(args.warmup):
         one_image(resident, i, False)
-    with ClockSampler(local_rank) as cs:
-        ms, launches = timed(lambda: resident, False)
+    with ClockSampler(cx.local_rank) as cs:
+        ms, launches = cx.timed(args.steps, lambda i: one_image(resident, 1000 + i, False))
     clocks = cs.summary()
-    # end to end: host-pinned embeddings in, image back on the host, through the public pipeline call
-    one_image({k: v.to(dev, non_blocking=True) for k, v in host.items()}, 0, True)
-    ms_e2e, _ = timed(lambda: {k: v.to(dev, non_blocking=True) for k, v in host.items()}, True)
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = B * (world if world > 1 and B * world > 1 else 1) * 3 * 1024 * 1024 * 2
-
+    h2d = lambda: {k: v.to(dev, non_blocking=True) for k, v in host.items()}  # noqa: E731
+    one_image(h2d(), 0, True)
+    ms_e2e, _ = cx.timed(args.steps, lambda i: one_image(h2d(), 2000 + i, True))
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    d2h_bytes = B * (world if gather else 1) * 3 * 1024 * 1024 * 2
     n_img = args.steps * B * world
     value = n_img / (ms * 1e-3)
-    line = None
-    if rank == 0:
-        roof = gemm_roofline(unet, 2 * B, pk)
-        flops_per_img = 2 * args.denoise_steps * UNET_FLOP_PER_SAMPLE + VAE_FLOP_PER_IMAGE
-        cb = cpu_reference(args, full=False) if world == 1 and not args.no_cpu_baseline else None
-        line = dict(metric="images/sec @ SDXL 1024^2 50-step", value=round(value, 4), unit="images/s", n_gpus=world, steps=args.steps,
-                    warmup=args.warmup, ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="bf16", data="synthetic (random-init weights, N(0,1) text embeddings, seeded latents)",
-                    config=dict(workload=sdxl_workload(args),
-                                global_batch=B * world, parallelism=f"dp{world}", cfg_batched=True,
-                                l2="per-step working set >> L2: 5.1 GB of weights stream from HBM every UNet forward",
-                                model="UNet2DConditionModel SDXL-base config (2.567 B params) + AutoencoderKL SDXL decoder"),
-                    e2e=dict(value=round(n_img / (ms_e2e * 1e-3), 4), unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-                    gpu_launches=launches, clocks=clocks, roofline=roof,
-                    model_flops=dict(tflop_per_image=round(flops_per_img / 1e12, 1),
-                                     achieved_tflops_per_gpu=round(value / world * flops_per_img / 1e12, 1),
-                                     frac_of_peak=round(value / world * flops_per_img / 1e12 / pk["tflops"], 4)))
-        if cb is not None:
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    flops_per_img = 2 * args.denoise_steps * UNET_FLOP_PER_SAMPLE + VAE_FLOP_PER_IMAGE
+    line = dict(metric="images/sec @ SDXL 1024^2 50-step", value=round(value, 4), unit="images/s", n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="bf16", data="synthetic (random-init weights, N(0,1) text embeddings, seeded latents)",
+                config=dict(workload=sdxl_workload(args), global_batch=B * world, parallelism=f"dp{world}", cfg_batched=True,
+                            l2="per-step working set >> L2: 5.1 GB of weights stream from HBM every UNet forward",
+                            model="UNet2DConditionModel SDXL-base config (2.567 B params) + AutoencoderKL SDXL decoder"),
+                e2e=dict(value=round(n_img / (ms_e2e * 1e-3), 4), unit="images/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
+                         note="pinned host embeddings in, decoded image(s) back to pinned host memory" + (" on rank 0 after the all-gather" if gather else "")),
+                gpu_launches=launches, clocks=clocks,
+                model_flops=dict(tflop_per_image=round(flops_per_img / 1e12, 1),
+                                 achieved_tflops_per_gpu=round(value / world * flops_per_img / 1e12, 1),
+                                 frac_of_peak=round(value / world * flops_per_img / 1e12 / pk["tflops"], 4)))
+    if cx.rank == 0:
+        roof, attn = sdxl_rooflines(unet, 2 * B, pk)
+        line["roofline"] = roof
+        line["attention"] = attn
         try:
             line["hbm_kernels"] = hbm_kernel_rooflines(dev, dt, pk)
         except Exception as e:  # noqa: BLE001  (a side measurement must never cost the headline line)
             line["hbm_kernels"] = f"failed: {e}"
-        print(json.dumps(line), flush=True)
+    # BASELINE config 3: batch 4 per GPU through the seeded-slice data-parallel entry point (global 32 at N = 8)
+    if world > 1 and not args.no_config3:
+        line["config3"] = config3_section(cx, pipe)
+    if cx.rank == 0 and world == 1 and not args.no_reference_cuda:
+        try:
+            line["reference_cuda_eager"] = reference_cuda_eager(dict(specs.SDXL_UNET_CONFIG), dev, dt)
+        except Exception as e:  # noqa: BLE001
+            line["reference_cuda_eager"] = f"failed: {type(e).__name__}: {str(e)[:160]}"
+    del pipe, unet, vae
+    torch.cuda.empty_cache()
+    return line
 
 
-def run_flux(args, rank, world, local_rank):
-    """Secondary headline: latents/sec, FluxTransformer2DModel (Flux.1-dev shape), 1024^2 (4096 image + 512 text
-    tokens), 28 FlowMatch steps, guidance 3.5, output_type='latent' (BASELINE.json configs[2])."""
-    from diffusers_b200 import ops, specs
+def config3_section(cx, pipe):
+    from diffusers_b200 import parallel
+    args, dev, dt, world = cx.args, cx.dev, cx.dt, cx.world
+    Bg = 4 * world
+    host = synthetic_embeds(Bg, dt, pin=True)  # every rank holds the full-batch embeddings; the entry point slices them
+    kw = dict(height=1024, width=1024, num_inference_steps=args.denoise_steps, guidance_scale=args.guidance_scale)
+
+    def batch(seed):
+        emb = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        imgs = parallel.sdxl_data_parallel(pipe, emb["prompt_embeds"], emb["negative_prompt_embeds"], emb["pooled_prompt_embeds"],
+                                           emb["negative_pooled_prompt_embeds"], seed=seed, **kw)
+        return to_host(imgs) if cx.rank == 0 else imgs
+
+    batch(0)
+    n = max(1, min(args.steps, 2))
+    with ClockSampler(cx.local_rank) as cs:
+        ms, launches = cx.timed(n, lambda i: batch(10 + i))
+    return dict(workload=f"sdxl_1024_{args.denoise_steps}step_cfg{args.guidance_scale}_global_batch{Bg}_b4_per_gpu(B_eff 8)",
+                value=round(n * Bg / (ms * 1e-3), 4), unit="images/s", ms_per_batch=round(ms / n, 1), batches_timed=n, e2e=True,
+                h2d_bytes_per_step=sum(v.numel() * v.element_size() for v in host.values()), d2h_bytes_per_step=Bg * 3 * 1024 * 1024 * 2,
+                collective="one all_gather_into_tensor of the decoded images per batch", gpu_launches=launches, clocks=cs.summary(),
+                note="one seeded full-batch latent draw sliced per rank (parallel.sdxl_data_parallel); host embeddings in, all images to rank 0's host")
+
+
+def flux_section(cx, standalone=False):
+    """BASELINE configs[2]: latents/sec, FluxTransformer2DModel (Flux.1-dev shape), 1024^2 (4096 image + 512 text tokens),
+    28 FlowMatch steps, guidance 3.5, output_type='latent'.  N > 1: one latent per GPU per step (replicas, weak scaling)."""
     from diffusers_b200.pipelines import FluxPipeline
     from diffusers_b200.schedulers import FlowMatchEulerDiscreteScheduler
     from diffusers_b200.transformer_flux import FluxTransformer2DModel
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dt = torch.bfloat16
-    pk = peaks()
+    args, dev, dt, world, pk = cx.args, cx.dev, cx.dt, cx.world, cx.pk
     t0 = time.time()
     tr = FluxTransformer2DModel.random_init(seed=0, dtype=dt, device=dev)
+    torch.cuda.synchronize()
     init_s = time.time() - t0
 
     class _V:
         config = type("C", (), dict(block_out_channels=(128, 256, 512, 512)))()
 
-    sk = dict(shift=3.0, use_dynamic_shifting=True, base_shift=0.5, max_shift=1.15, base_image_seq_len=256, max_image_seq_len=4096)
-    pipe = FluxPipeline(FlowMatchEulerDiscreteScheduler(**sk), _V(), tr)
+    pipe = FluxPipeline(FlowMatchEulerDiscreteScheduler(**FLUX_SCHED), _V(), tr)
     g = torch.Generator().manual_seed(1)
     host = dict(prompt_embeds=torch.randn(1, 512, 4096, generator=g).to(dt).pin_memory(),
                 pooled_prompt_embeds=torch.randn(1, 768, generator=g).to(dt).pin_memory())
-    call = dict(height=1024, width=1024, num_inference_steps=args.denoise_steps if args.denoise_steps != 50 else 28,
-                guidance_scale=3.5, output_type="latent")
-    nsteps = call["num_inference_steps"]
+    nsteps = 28 if args.denoise_steps == 50 else args.denoise_steps
+    call = dict(height=1024, width=1024, num_inference_steps=nsteps, guidance_scale=3.5, output_type="latent")
+    n = max(args.steps, 5) if not standalone else args.steps
 
-    def one(emb, seed, to_host):
+    def one(emb, seed, host_out):
         lat = pipe(generator=torch.Generator(device=dev).manual_seed(seed), **emb, **call).images
-        if to_host:
-            out = torch.empty(lat.shape, dtype=lat.dtype, pin_memory=True)
-            out.copy_(lat, non_blocking=True)
-            return out
-        return lat
+        return to_host(lat) if host_out else lat
 
     res = {k: v.to(dev) for k, v in host.items()}
-    for i in range(args.warmup):
+    for i in range(max(1, min(args.warmup, 2))):
         one(res, i, False)
-    torch.cuda.synchronize()
-    with ClockSampler(local_rank) as cs:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = ops.launches()
-        e0.record()
-        for i in range(args.steps):
-            one(res, 100 + i, False)
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    launches = ops.launches() - n0
-    e0.record()
-    for i in range(args.steps):
-        one({k: v.to(dev, non_blocking=True) for k, v in host.items()}, 200 + i, True)
-    e1.record()
-    torch.cuda.synchronize()
-    ms2 = e0.elapsed_time(e1)
-    value = args.steps / (ms * 1e-3)
+    with ClockSampler(cx.local_rank) as cs:
+        ms, launches = cx.timed(n, lambda i: one(res, 100 + i, False))
+    ms2, _ = cx.timed(n, lambda i: one({k: v.to(dev, non_blocking=True) for k, v in host.items()}, 200 + i, True))
+    value = n * world / (ms * 1e-3)
     fl = nsteps * FLUX_FLOP_PER_FORWARD
-    line = dict(metric="latents/sec @ Flux.1-dev-shape 1024^2 28-step", value=round(value, 4), unit="latents/s", n_gpus=1,
-                steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 1), higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype="bf16", data="synthetic (random-init weights, N(0,1) embeddings)",
-                config=dict(workload=f"flux_dev_shape_1024_{nsteps}step_g3.5_b1", model="FluxTransformer2DModel 11.90 B params",
-                            l2="23.8 GB of weights stream from HBM every forward", init_s=round(init_s, 1)),
-                e2e=dict(value=round(args.steps / (ms2 * 1e-3), 4), unit="latents/s",
-                         h2d_bytes_per_step=sum(v.numel() * 2 for v in host.values()), d2h_bytes_per_step=4096 * 64 * 2),
-                gpu_launches=launches, clocks=cs.summary(),
-                model_flops=dict(tflop_per_latent=round(fl / 1e12, 1), achieved_tflops=round(value * fl / 1e12, 1),
-                                 frac_of_peak=round(value * fl / 1e12 / pk["tflops"], 4), peak=pk["tflops"]))
-    print(json.dumps(line), flush=True)
+    sec = dict(metric="latents/sec @ Flux.1-dev-shape 1024^2 28-step", value=round(value, 4), unit="latents/s", n_gpus=world, steps=n,
+               warmup=max(1, min(args.warmup, 2)), ms_per_step=round(ms / n, 1), ms_per_forward=round(ms / n / nsteps, 2), higher_is_better=True,
+               scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic (random-init weights, N(0,1) embeddings)",
+               config=dict(workload=f"flux_dev_shape_1024_{nsteps}step_g3.5_b1_per_gpu", model="FluxTransformer2DModel 11.90 B params",
+                           l2="23.8 GB of weights stream from HBM every forward", init_s=round(init_s, 1), parallelism=f"dp{world} (replicas)"),
+               e2e=dict(value=round(n * world / (ms2 * 1e-3), 4), unit="latents/s", h2d_bytes_per_step=sum(v.numel() * 2 for v in host.values()),
+                        d2h_bytes_per_step=4096 * 64 * 2),
+               gpu_launches=launches, clocks=cs.summary(),
+               model_flops=dict(tflop_per_latent=round(fl / 1e12, 1), achieved_tflops_per_gpu=round(value / world * fl / 1e12, 1),
+                                frac_of_peak=round(value / world * fl / 1e12 / pk["tflops"], 4), peak=pk["tflops"]))
+    if cx.rank == 0:
+        # per-kernel rooflines from one eager forward with events around every GEMM / attention launch
+        try:
+            lat = torch.randn(1, 4096, 64, device=dev).to(dt)
+            ids = FluxPipeline._prepare_latent_image_ids(64, 64, dev, dt)
+            tid = torch.zeros(512, 3, device=dev, dtype=dt)
+            kw = dict(hidden_states=lat, timestep=torch.tensor([0.5], device=dev, dtype=dt), guidance=torch.tensor([3.5], device=dev),
+                      pooled_projections=res["pooled_prompt_embeds"], encoder_hidden_states=res["prompt_embeds"], txt_ids=tid, img_ids=ids, return_dict=False)
+            tr(**kw)
+            prof, total = profiled(lambda: tr(**kw))
+            sec["roofline"] = kernel_roofline(prof, total, "conv_gemm", pk)
+            sec["attention"] = kernel_roofline(prof, total, "attention", pk)
+        except Exception as e:  # noqa: BLE001
+            sec["roofline"] = f"failed: {type(e).__name__}: {str(e)[:160]}"
+    del pipe, tr
+    torch.cuda.empty_cache()
+    return sec
 
 
-def run_vae(args, rank, world, local_rank):
+def vae_section(cx):
     """BASELINE.json configs[4]: AutoencoderKL.decode (SDXL decoder, 49.5 M params) of z (B,4,128,128) -> (B,3,1024,1024),
     batch sweep 1 / 8 / 64 - the convolution-roofline view of the path (10.47 TFLOP per image)."""
-    from diffusers_b200 import ops
     from diffusers_b200.autoencoder_kl import AutoencoderKL
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dt = torch.bfloat16
-    pk = peaks()
+    args, dev, dt, pk = cx.args, cx.dev, cx.dt, cx.pk
     vae = AutoencoderKL.random_init(seed=0, dtype=dt, device=dev)
-    sweep, line = {}, None
-    with ClockSampler(local_rank) as cs:
+    sweep = {}
+    with ClockSampler(cx.local_rank) as cs:
         for B in (1, 8, 64):
             g = torch.Generator().manual_seed(B)
             zh = torch.randn(B, 4, 128, 128, generator=g).to(dt).pin_memory()
             z = zh.to(dev)
             for _ in range(max(1, args.warmup if B < 64 else 1)):
                 vae.decode(z, return_dict=False)
-            torch.cuda.synchronize()
             n = max(1, args.steps if B < 64 else min(args.steps, 2))
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n0 = ops.launches()
-            e0.record()
-            for _ in range(n):
-                img = vae.decode(z, return_dict=False)[0]
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / n
-            launches = (ops.launches() - n0) // n
-            host_out = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
-            e0.record()
-            for _ in range(n):
-                host_out.copy_(vae.decode(zh.to(dev, non_blocking=True), return_dict=False)[0], non_blocking=True)
-            e1.record()
-            torch.cuda.synchronize()
-            ms2 = e0.elapsed_time(e1) / n
-            sweep[B] = dict(images_per_s=round(B / (ms * 1e-3), 2), ms_per_batch=round(ms, 2), e2e_images_per_s=round(B / (ms2 * 1e-3), 2),
-                            tflops=round(B * VAE_FLOP_PER_IMAGE / (ms * 1e-3) / 1e12, 1), launches=launches)
-            del img, host_out, z
+            ms, launches = cx.timed(n, lambda i: vae.decode(z, return_dict=False))
+            ms2, _ = cx.timed(n, lambda i: to_host(vae.decode(zh.to(dev, non_blocking=True), return_dict=False)[0]))
+            sweep[B] = dict(images_per_s=round(B * n / (ms * 1e-3), 2), ms_per_batch=round(ms / n, 2), e2e_images_per_s=round(B * n / (ms2 * 1e-3), 2),
+                            tflops=round(B * n * VAE_FLOP_PER_IMAGE / (ms * 1e-3) / 1e12, 1), launches=launches // n)
+            del z
     best = max(sweep, key=lambda b: sweep[b]["images_per_s"])
     v = sweep[best]
-    line = dict(metric="images/sec @ AutoencoderKL.decode 1024^2 (SDXL VAE)", value=v["images_per_s"], unit="images/s", n_gpus=1, steps=args.steps,
-                warmup=args.warmup, ms_per_step=v["ms_per_batch"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
-                data="synthetic (random-init weights, N(0,1) latents)",
-                config=dict(workload=f"sdxl_vae_decode_1024_b{best}", sweep={str(k): s for k, s in sweep.items()},
-                            l2="activations of one image (268 MB per 128-channel 1024^2 tensor) >> L2"),
-                e2e=dict(value=v["e2e_images_per_s"], unit="images/s", h2d_bytes_per_step=best * 4 * 128 * 128 * 2,
-                         d2h_bytes_per_step=best * 3 * 1024 * 1024 * 2),
-                gpu_launches=v["launches"], clocks=cs.summary(),
-                model_flops=dict(tflop_per_image=round(VAE_FLOP_PER_IMAGE / 1e12, 2), achieved_tflops=v["tflops"],
-                                 frac_of_peak=round(v["tflops"] / pk["tflops"], 4), peak=pk["tflops"]))
-    print(json.dumps(line), flush=True)
+    sec = dict(metric="images/sec @ AutoencoderKL.decode 1024^2 (SDXL VAE)", value=v["images_per_s"], unit="images/s", n_gpus=1, steps=args.steps,
+               warmup=args.warmup, ms_per_step=v["ms_per_batch"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+               data="synthetic (random-init weights, N(0,1) latents)",
+               config=dict(workload=f"sdxl_vae_decode_1024_b{best}", sweep={str(k): s for k, s in sweep.items()},
+                           l2="activations of one image (268 MB per 128-channel 1024^2 tensor) >> L2"),
+               e2e=dict(value=v["e2e_images_per_s"], unit="images/s", h2d_bytes_per_step=best * 4 * 128 * 128 * 2,
+                        d2h_bytes_per_step=best * 3 * 1024 * 1024 * 2),
+               gpu_launches=v["launches"], clocks=cs.summary(),
+               model_flops=dict(tflop_per_image=round(VAE_FLOP_PER_IMAGE / 1e12, 2), achieved_tflops=v["tflops"],
+                                frac_of_peak=round(v["tflops"] / pk["tflops"], 4), peak=pk["tflops"]))
+    try:
+        z1 = torch.randn(1, 4, 128, 128, device=dev).to(dt)
+        prof, total = profiled(lambda: vae.decode(z1, return_dict=False))
+        sec["roofline"] = kernel_roofline(prof, total, "conv_gemm", pk)
+    except Exception as e:  # noqa: BLE001
+        sec["roofline"] = f"failed: {type(e).__name__}: {str(e)[:160]}"
+    del vae
+    torch.cuda.empty_cache()
+    return sec
+
+
+def run_b200(args, rank, world, local_rank):
+    cx = Ctx(args, rank, world, local_rank)
+    wl = args.workload
+    if wl == "flux":
+        line = flux_section(cx, standalone=True)
+    elif wl == "vae":
+        line = vae_section(cx) if rank == 0 else None
+    else:
+        line = sdxl_section(cx)
+        if wl == "all":
+            try:
+                line["flux"] = flux_section(cx)
+            except Exception as e:  # noqa: BLE001  (the headline line must survive a failure of a secondary section)
+                if world > 1:
+                    raise  # a one-sided failure would deadlock the other ranks' collectives: fail loudly instead
+                line["flux"] = f"failed: {type(e).__name__}: {str(e)[:200]}"
+            if world == 1:
+                try:
+                    line["vae"] = vae_section(cx)
+                except Exception as e:  # noqa: BLE001
+                    line["vae"] = f"failed: {type(e).__name__}: {str(e)[:200]}"
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference(args, full=False)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "dtype", "t_step_runs_s", "run_spread")}
+    if rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="sdxl", choices=["sdxl", "flux", "vae"])
+    ap.add_argument("--workload", default="all", choices=["all", "sdxl", "flux", "vae"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
@@ -494,6 +707,8 @@ def main():
     ap.add_argument("--denoise-steps", type=int, default=50)
     ap.add_argument("--guidance-scale", type=float, default=7.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config3", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -506,12 +721,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        if args.workload == "flux":
-            run_flux(args, rank, world, local_rank)
-        elif args.workload == "vae":
-            run_vae(args, rank, world, local_rank)
-        else:
-            run_b200(args, rank, world, local_rank)
+        run_b200(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -9,7 +9,7 @@ from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_SILU, DTYPE_BF16, 
                    B200Error)
 
 _LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
-_PROFILE = None  # bench.py: list collecting (start_event, end_event, algorithmic_flops, M, N, K) per conv_gemm launch
+_PROFILE = None  # bench.py: list collecting (start_event, end_event, algorithmic_flops, kernel, shape) per conv_gemm / attention launch
 
 
 def launches():
@@ -163,7 +163,7 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
         _lib.check(_lib.lib().b200_conv_gemm(C.byref(a), _stream()), "b200_conv_gemm")
         e1.record()
         M_, K_ = batch * Ho * Wo, ksize * ksize * (c0 + c1)
-        _PROFILE.append((e0, e1, 2.0 * M_ * N * K_, M_, N, K_))
+        _PROFILE.append((e0, e1, 2.0 * M_ * N * K_, "conv_gemm", (M_, N, K_)))
     else:
         _lib.check(_lib.lib().b200_conv_gemm(C.byref(a), _stream()), "b200_conv_gemm")
     _count()
@@ -202,7 +202,14 @@ def attention(q, k, v, *, heads, head_dim, scale=None, out=None, nq=0):
     a.scale = float(scale) if scale is not None else 0.0
     a.dtype = _dtype_code(q)
     a.nq_override = nq
-    _lib.check(_lib.lib().b200_attention(C.byref(a), _stream()), "b200_attention")
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(_lib.lib().b200_attention(C.byref(a), _stream()), "b200_attention")
+        e1.record()
+        _PROFILE.append((e0, e1, 4.0 * B * heads * Sq * Sk * head_dim, "attention", (B * heads, Sq, Sk, head_dim)))
+    else:
+        _lib.check(_lib.lib().b200_attention(C.byref(a), _stream()), "b200_attention")
     _count()
     return out
 

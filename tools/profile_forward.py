@@ -46,8 +46,10 @@ def main():
     torch.cuda.synchronize()
     prof, ops._PROFILE = ops._PROFILE, None
     agg = collections.OrderedDict()
-    for a, b, fl, M, N, K in prof:
-        k = (M, N, K)
+    for a, b, fl, kern, shape in prof:
+        if kern != "conv_gemm":
+            continue
+        k = shape
         d = agg.setdefault(k, [0, 0.0, 0.0])
         d[0] += 1
         d[1] += a.elapsed_time(b)
