@@ -391,10 +391,11 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
 int init_attention_pipe();
 bool attention_pipe_enabled();
 int launch_attention64_pipe(const b200_attention_args* a, cudaStream_t st);
-// attention_split.cu: EXPERIMENTAL two-warps-per-row variant of the above (B200_ATTN_SPLIT=1, not validated on hardware)
-int init_attention_split();
-bool attention_split_enabled();
-int launch_attention64_split(const b200_attention_args* a, cudaStream_t st);
+// attention64.cu: the head_dim-64 default (software-pipelined softmax, register reallocation, KV split with in-kernel combine)
+int init_attention64();
+bool attention64_enabled();
+int launch_attention64(const b200_attention_args* a, cudaStream_t st);
+long long attention64_workspace_bytes(long long tiles);
 
 template <int HD, int NQ, bool FP16>
 static int attn_set_attr() {
@@ -415,7 +416,7 @@ int init_attention() {
   if ((r = attn_set_attr<128, 2, false>())) return r;
   if ((r = attn_set_attr<128, 2, true>())) return r;
   if ((r = init_attention_pipe())) return r;
-  init_attention_split();  // experimental: never fatal
+  if ((r = init_attention64())) return r;
   return 0;
 }
 
@@ -441,8 +442,8 @@ int b200_attention(const b200_attention_args* a, void* stream) {
                      a->v_batch_stride % 8 == 0 && a->o_batch_stride % 8 == 0,
                  "attention: strides must be multiples of 8 elements");
   const int HD = a->head_dim;
-  if (HD == 64 && a->nq_override != 2 && attention_split_enabled())
-    return launch_attention64_split(a, static_cast<cudaStream_t>(stream));
+  if (HD == 64 && a->nq_override != 2 && attention64_enabled())
+    return launch_attention64(a, static_cast<cudaStream_t>(stream));
   if (HD == 64 && a->nq_override != 2 && attention_pipe_enabled())
     return launch_attention64_pipe(a, static_cast<cudaStream_t>(stream));
 
@@ -492,6 +493,12 @@ int b200_attention(const b200_attention_args* a, void* stream) {
     if (nq == 2) { B200_ATTN(128, 2); } else { B200_ATTN(128, 1); }
   }
 #undef B200_ATTN
+}
+
+int64_t b200_attention_workspace_bytes(int32_t batch, int32_t heads, int32_t sq, int32_t sk, int32_t head_dim) {
+  (void)sk;
+  if (head_dim != 64 || batch <= 0 || heads <= 0 || sq <= 0) return 0;
+  return b200::attention64_workspace_bytes(static_cast<long long>(batch) * heads * ((sq + 127) / 128));
 }
 
 }  // extern "C"

@@ -1,0 +1,605 @@
+// head_dim-64 attention (SDXL self / cross attention): the default for head_dim 64 with one query tile per CTA
+// (B200_ATTN_V2=0 falls back to the kernel in attention.cu).
+//
+// Structure (2 CTAs per SM, 256 threads each):
+//   warp 0  TMA producer (Q once, K / V rings in 64-key halves)
+//   warp 1  tcgen05.mma issuer:  S(h) = Q K_h^T  (SS, 128 x 64 x 64)   and   O += P(h) V_h  (TS: P from TMEM, V MN-major)
+//   warp 2  TMEM allocator (idle afterwards), warp 3 idle         -> warps 0-3 give their registers away (setmaxnreg.dec)
+//   warps 4-7  softmax warpgroup, thread = query row               -> 200 registers per thread (setmaxnreg.inc)
+//
+//   TMEM (256 columns): S0 [0,64)  S1 [64,128)  P0 [128,160)  P1 [160,192)  O [192,256)
+//   MMA warp:      S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ...          (S(h+2) refills the buffer softmax(h) released)
+//
+// What round 1's pipelined kernel left on the table (ncu: tensor pipe 20-23 % active, the softmax warps - two per SM
+// sub-partition - stalled on their own dependency chains: TMEM load -> serial row max -> exponentials -> TMEM store):
+//  * SOFTWARE-PIPELINED softmax: while the exponentials of half h occupy the MUFU / FMA pipes, the same thread already holds
+//    the scores of half h+1 in a second register set and reduces their row maximum on the ALU pipe.  The two halves are
+//    independent instruction streams in one basic block, so the scheduler interleaves them and no pipe waits for a TMEM round
+//    trip.  128 score registers + 16 packed P need the register reallocation above.
+//  * cheaper arithmetic: 3-input max (FMNMX3), packed fp32x2 FMA / ADD for the scale-and-shift, the row sum and the
+//    exponential polynomial, 4 independent partial sums instead of one serial chain; 3 of every 8 exponentials are evaluated
+//    as a degree-3 polynomial on the FMA pipe (MUFU does 16 ex2 / clk / SM: with all 64 of a row's exponentials on it the
+//    unit alone would take longer than both GEMMs of the tile).
+//  * KV SPLIT with an in-kernel combine: 2 x 148 CTA slots make 320 tiles (1024 tokens, 20 heads, CFG batch 2) two waves of
+//    which the second is 8 % full.  Each tile's keys can be split over 2 or 4 CTAs; a CTA that is not the last of its tile
+//    to finish parks its unnormalised O (fp32), running max and row sum in a workspace, the last one (atomic ticket) merges
+//    them into its own accumulator and writes the output.  Finer work items fill the last wave; nothing is re-launched.
+// Numerics are those of attention.cu: online softmax in the exp2 domain, lazy rescale (the running max only moves on > 2^8
+// growth), P rounded to 16 bit for the P V GEMM, fp32 row sums of the unrounded P.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace b200 {
+
+struct Attn64Params {
+  CUtensorMap q_map;  // box {64, 128, 1, 1}
+  CUtensorMap k_map;  // box {64, 64, 1, 1}
+  CUtensorMap v_map;  // box {64, 64, 1, 1}
+  void* o;
+  long long o_row_stride, o_batch_stride;
+  int batch, heads, sq, sk;
+  int q_tiles;           // ceil(sq / 128)
+  int kv_halves;         // ceil(sk / 64)
+  int split;             // CTAs per tile (1, 2 or 4)
+  int halves_per_split;  // ceil(kv_halves / split)
+  float scale_log2;
+  float* ws_o;           // [tiles * split][128][64] fp32: unnormalised O of a CTA that was not the last of its tile
+  float* ws_ml;          // [tiles * split][128][2]: its running max (exp2 domain) and row sum
+  unsigned int* counters;  // [tiles] arrival tickets, self-resetting
+};
+
+struct Attn64Cfg {
+  static constexpr int Q_BYTES = 128 * 64 * 2;   // 16 KB
+  static constexpr int KV_BYTES = 64 * 64 * 2;   // 8 KB: one 64-key half of K or V
+  static constexpr int KS = 4, VS = 4;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int S_COL = 0, P_COL = 128, O_COL = 192;
+  static constexpr int SMEM_BYTES = Q_BYTES + (KS + VS) * KV_BYTES + 1024 + 256;
+  static constexpr int THREADS = 256;
+  static constexpr int REGS_LOW = 56, REGS_HIGH = 200;  // 128 * (56 + 200) = 32768 = half of the SM's register file
+};
+
+__device__ __forceinline__ float a64_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float a64_max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// 2^x for a pair, x <= ~0, on the FMA pipe: x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 polynomial
+// (relative error 1.1e-4: below the 16-bit rounding of P), the exponent added into the float's bits.
+__device__ __forceinline__ float2 a64_ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.05583828f, 0.05583828f), make_float2(0.24263948f, 0.24263948f));
+  p = __ffma2_rn(p, f, make_float2(0.69313675f, 0.69313675f));
+  p = __ffma2_rn(p, f, make_float2(0.99992454f, 0.99992454f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(const __grid_constant__ Attn64Params p) {
+  using Cfg = Attn64Cfg;
+  using H = Half16<FP16>;
+  constexpr int KS = Cfg::KS, VS = Cfg::VS;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_q = smem;                        // [128][64]
+  uint8_t* s_k = s_q + Cfg::Q_BYTES;          // [KS][64][64]
+  uint8_t* s_v = s_k + KS * Cfg::KV_BYTES;    // [VS][64][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + VS * Cfg::KV_BYTES);
+  uint64_t* q_full = bars;               // [1]
+  uint64_t* k_full = q_full + 1;         // [KS]
+  uint64_t* k_empty = k_full + KS;       // [KS]
+  uint64_t* v_full = k_empty + KS;       // [VS]
+  uint64_t* v_empty = v_full + VS;       // [VS]
+  uint64_t* s_full = v_empty + VS;       // [2]  S(h) landed in TMEM
+  uint64_t* p_full = s_full + 2;         // [2]  softmax wrote P(h) and is done with S(h): 128 arrivals
+  uint64_t* pv_done = p_full + 2;        // [2]  P(h) V(h) accumulated into O (P buffer reusable, O consistent)
+  uint64_t* o_full = pv_done + 2;        // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint32_t* ticket = tmem_ptr + 1;       // combine: this CTA's arrival order within its tile
+  static_assert((1 + 2 * KS + 2 * VS + 2 + 2 + 2 + 1) * 8 + 8 <= 256, "barrier area");
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x;                 // tile * split + part: the parts of a tile are launched back to back
+  const int part = item % p.split;
+  const int tile = item / p.split;
+  const int qt = tile % p.q_tiles;
+  const int bh = tile / p.q_tiles;
+  const int head = bh % p.heads;
+  const int b = bh / p.heads;
+  const int q_row0 = qt * 128;
+  const int h_begin = part * p.halves_per_split;
+  const int h_end = min(p.kv_halves, h_begin + p.halves_per_split);
+  const int n_half = h_end - h_begin;          // >= 1 by construction of split
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.q_map);
+    prefetch_tensormap(&p.k_map);
+    prefetch_tensormap(&p.v_map);
+    mbar_init(q_full, 1);
+    mbar_init(o_full, 1);
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < VS; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_LOW));
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (elect_one()) {
+        mbar_expect_tx(q_full, Cfg::Q_BYTES);
+        tma_load_4d(s_q, &p.q_map, q_full, 0, q_row0, head, b);
+      }
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0;
+      for (int h = h_begin; h < h_end; ++h) {
+        mbar_wait(&k_empty[ks], kph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&k_full[ks], Cfg::KV_BYTES);
+          tma_load_4d(s_k + ks * Cfg::KV_BYTES, &p.k_map, &k_full[ks], 0, h * 64, head, b);
+        }
+        if (++ks == KS) { ks = 0; kph ^= 1u; }
+        mbar_wait(&v_empty[vs], vph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&v_full[vs], Cfg::KV_BYTES);
+          tma_load_4d(s_v + vs * Cfg::KV_BYTES, &p.v_map, &v_full[vs], 0, h * 64, head, b);
+        }
+        if (++vs == VS) { vs = 0; vph ^= 1u; }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = make_idesc(128, 64, FP16, false, false);
+      constexpr uint32_t idesc_pv = make_idesc(128, 64, FP16, false, true);
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0;
+      const uint32_t qa = smem_u32(s_q);
+
+      auto issue_s = [&](int buf, int kstage) {  // S_buf = Q K_half^T: 128 x 64 x 64, four K steps of 16
+        const uint64_t qd = make_smem_desc_sw128(qa, 16, 1024);
+        const uint64_t kd = make_smem_desc_sw128(smem_u32(s_k + kstage * Cfg::KV_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem_base + Cfg::S_COL + buf * 64, qd + 2u * k, kd + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
+      };
+      auto issue_pv = [&](int buf, int vstage, bool accumulate) {  // O += P_buf V_half: K = 64 keys, four steps of 16
+        const uint32_t va = smem_u32(s_v + vstage * Cfg::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t vd = make_smem_desc_sw128(va + k * 2048, Cfg::KV_BYTES, 1024);  // MN-major: 16 keys = 2 x 8-row groups
+          umma_ts(tmem_base + Cfg::O_COL, tmem_base + Cfg::P_COL + buf * 32 + k * 8, vd, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+        }
+      };
+
+      mbar_wait(q_full, 0);
+      for (int h0 = 0; h0 < 2 && h0 < n_half; ++h0) {  // prologue: both score buffers filled
+        mbar_wait(&k_full[ks], kph);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_s(h0, ks);
+          umma_commit(&s_full[h0]);
+          umma_commit(&k_empty[ks]);
+        }
+        if (++ks == KS) { ks = 0; kph ^= 1u; }
+      }
+      for (int h = 0; h < n_half; ++h) {
+        const int buf = h & 1;
+        mbar_wait(&p_full[buf], (h >> 1) & 1u);
+        mbar_wait(&v_full[vs], vph);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_pv(buf, vs, h > 0);
+          umma_commit(&v_empty[vs]);
+          umma_commit(&pv_done[buf]);
+        }
+        if (++vs == VS) { vs = 0; vph ^= 1u; }
+        if (h + 2 < n_half) {  // the softmax has released S_buf: refill it two halves ahead
+          mbar_wait(&k_full[ks], kph);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_s(buf, ks);
+            umma_commit(&s_full[buf]);
+            umma_commit(&k_empty[ks]);
+          }
+          if (++ks == KS) { ks = 0; kph ^= 1u; }
+        }
+      }
+      if (elect_one()) umma_commit(o_full);
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_HIGH));
+    // ===================== softmax warpgroup (thread = query row) =====================
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t o_t = tmem_base + lane_off + Cfg::O_COL;
+    const float sc = p.scale_log2;
+    float m = 0.f;
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+
+    // scores of the last half of the sequence beyond sk: -inf (their exponentials are 0, V rows there are TMA zero fill)
+    auto mask_tail = [&](uint32_t (&s)[64], int hg) {
+      const int kv_left = p.sk - hg * 64;
+      if (kv_left < 64) {
+#pragma unroll
+        for (int k = 0; k < 64; ++k)
+          if (k >= kv_left) s[k] = 0xff800000u;
+      }
+    };
+    auto load_scores = [&](uint32_t (&s)[64], int h) {  // issue only; tmem_wait_ld() before use
+      const uint32_t s_t = tmem_base + lane_off + Cfg::S_COL + (h & 1) * 64;
+      tmem_ld32_at<0>(s_t, s);
+      tmem_ld32_at<32>(s_t + 32, s);
+    };
+    auto row_max = [&](const uint32_t (&s)[64]) {
+      float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 64; k += 8) {
+        a0 = a64_max3(a0, __uint_as_float(s[k + 0]), __uint_as_float(s[k + 1]));
+        a1 = a64_max3(a1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
+        a2 = a64_max3(a2, __uint_as_float(s[k + 4]), __uint_as_float(s[k + 5]));
+        a3 = a64_max3(a3, __uint_as_float(s[k + 6]), __uint_as_float(s[k + 7]));
+      }
+      return a64_max3(a0, a1, fmaxf(a2, a3));
+    };
+    // 32 scores s[OFF .. OFF+32) -> 16 packed P.  Of every 16 exponentials 10 go to MUFU and 6 (three packed pairs) to the
+    // FMA-pipe polynomial: MUFU 40 x 8 cycles, FMA pipe (scale, polynomial, row sums) ~300, ALU (max, clamps, exponent
+    // insertion, packing) ~270 cycles per warp and 64-key half - the three pipes finish together.
+    auto exps32 = [&](const uint32_t (&s)[64], auto off_tag, uint32_t (&dst)[16]) {
+      constexpr int OFF = decltype(off_tag)::value;
+      const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m, -m);
+#pragma unroll
+      for (int k = 0; k < 32; k += 16) {
+        float2 x[8], e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          x[j] = __ffma2_rn(make_float2(__uint_as_float(s[OFF + k + 2 * j]), __uint_as_float(s[OFF + k + 2 * j + 1])), sc2, nm2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j == 2 || j == 5 || j == 7)
+            e[j] = a64_ex2_poly2(x[j]);
+          else
+            e[j] = make_float2(a64_ex2(x[j].x), a64_ex2(x[j].y));
+        }
+        const float2 s01 = __fadd2_rn(e[0], e[1]), s23 = __fadd2_rn(e[2], e[3]), s45 = __fadd2_rn(e[4], e[5]), s67 = __fadd2_rn(e[6], e[7]);
+        const float2 sa_ = __fadd2_rn(s01, s23), sb_ = __fadd2_rn(s45, s67);
+        l0 += sa_.x; l1 += sa_.y; l2 += sb_.x; l3 += sb_.y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[k / 2 + j] = H::pack(e[j].x, e[j].y);
+      }
+    };
+    using Off0 = std::integral_constant<int, 0>;
+    using Off32 = std::integral_constant<int, 32>;
+
+    // one softmax step: exponentials of `cur` (local half h) and, interleaved with them, the row max of `nxt` (half h+1).
+    //   MODE 0  main loop: there is a next half and it is complete (branch-free: one basic block from the TMEM wait to the
+    //           P store, so the scheduler overlaps the two independent streams)
+    //   MODE 1  the next half is the last of the sequence and may be ragged (masked)
+    //   MODE 2  no next half
+    auto step = [&](uint32_t (&cur)[64], uint32_t (&nxt)[64], int h, auto mode_tag) {
+      constexpr int MODE = decltype(mode_tag)::value;
+      constexpr bool has_next = MODE != 2;
+      const int buf = h & 1;
+      const uint32_t p_t = tmem_base + lane_off + Cfg::P_COL + buf * 32;
+      if (has_next) {
+        mbar_wait_warp(&s_full[buf ^ 1], ((h + 1) >> 1) & 1u);
+        tc_fence_after();
+        load_scores(nxt, h + 1);
+      }
+      // P_buf still feeds P V of half h-2 until that MMA completes
+      if (h >= 2) mbar_wait_warp(&pv_done[buf], ((h - 2) >> 1) & 1u);
+      uint32_t pk[16];
+      exps32(cur, Off0{}, pk);
+      tmem_st16(p_t, pk);  // keys 0..31 of the half -> P columns 0..15
+      float mx = -INFINITY;
+      if (has_next) {
+        tmem_wait_ld();
+        if (MODE == 1) mask_tail(nxt, h_begin + h + 1);
+        mx = row_max(nxt);  // independent of the exponentials below
+      }
+      exps32(cur, Off32{}, pk);
+      tmem_st16(p_t + 16, pk);  // keys 32..63 -> P columns 16..31
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[buf]);
+      if (has_next) {
+        mx *= sc;  // sc > 0
+        const bool need = mx > m + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          // every P V issued so far (halves <= h, in order on the tensor pipe) must have landed before O is rescaled
+          mbar_wait_warp(&pv_done[buf], (h >> 1) & 1u);
+          tc_fence_after();
+          const float alpha = need ? a64_ex2(m - mx) : 1.0f;
+          if (need) {
+            m = mx;
+            l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+          }
+          uint32_t t0[32];
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld32(o_t + c * 32, t0);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) t0[k] = __float_as_uint(__uint_as_float(t0[k]) * alpha);
+            tmem_st32(o_t + c * 32, t0);
+          }
+          tmem_wait_st();
+        }
+      }
+    };
+    using ModeMain = std::integral_constant<int, 0>;
+    using ModeLastNext = std::integral_constant<int, 1>;
+    using ModeFinal = std::integral_constant<int, 2>;
+
+    uint32_t sa[64], sb[64];
+    mbar_wait_warp(&s_full[0], 0);
+    tc_fence_after();
+    load_scores(sa, 0);
+    tmem_wait_ld();
+    mask_tail(sa, h_begin);
+    {
+      const float mx = row_max(sa) * sc;
+      m = (mx == -INFINITY) ? 0.f : mx;
+    }
+    // halves 0 .. n_half-3 have a complete successor (main loop, two steps per trip so that the register sets swap roles
+    // without moves); half n_half-2 precedes the possibly ragged last half; half n_half-1 has no successor
+    int h = 0;
+#pragma unroll 1
+    for (; h + 3 < n_half; h += 2) {
+      step(sa, sb, h, ModeMain{});
+      step(sb, sa, h + 1, ModeMain{});
+    }
+    if (h + 2 < n_half) {  // one more main-loop step: afterwards the current half sits in sb -> move it to sa
+      step(sa, sb, h, ModeMain{});
+      ++h;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) sa[k] = sb[k];
+    }
+    if (h + 1 < n_half) {
+      step(sa, sb, h, ModeLastNext{});
+      ++h;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 64; ++k) sb[k] = sa[k];
+    }
+    step(sb, sa, h, ModeFinal{});
+    float l = (l0 + l1) + (l2 + l3);
+
+    // ---- epilogue: (combine the parts of the tile,) O / l -> global
+    mbar_wait_warp(o_full, 0);
+    tc_fence_after();
+    bool writer = true;       // this CTA writes the tile's output
+    unsigned int my_ticket = 0;
+    if (p.split > 1) {
+      // park this part's (O, m, l); the last part of the tile to arrive merges the others into its accumulator
+      float* wo = p.ws_o + (static_cast<size_t>(item) * 128 + row) * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(o_t + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(wo + c * 32 + g * 4) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      }
+      *reinterpret_cast<float2*>(p.ws_ml + (static_cast<size_t>(item) * 128 + row) * 2) = make_float2(m, l);
+      __threadfence();
+      named_bar_sync(1, 128);
+      if (threadIdx.x == 128) {
+        const unsigned int t = atomicAdd(p.counters + tile, 1u);
+        if (t == static_cast<unsigned int>(p.split - 1)) p.counters[tile] = 0;  // every part has arrived: ready for the next launch
+        *ticket = t;
+      }
+      named_bar_sync(1, 128);
+      my_ticket = *ticket;
+      writer = my_ticket == static_cast<unsigned int>(p.split - 1);
+      if (writer) __threadfence();
+    }
+    if (writer) {
+      const int qrow = q_row0 + row;
+      const bool valid = qrow < p.sq;
+      // merged running max / row sum over the parts (split == 1: this part's own)
+      float m_all = m;
+      float scale_self = 1.0f;
+      if (p.split > 1) {
+        for (int s = 0; s < p.split; ++s) {
+          if (s == part) continue;
+          m_all = fmaxf(m_all, __ldcg(p.ws_ml + (static_cast<size_t>(tile * p.split + s) * 128 + row) * 2));
+        }
+        scale_self = a64_ex2(m - m_all);
+        l *= scale_self;
+        for (int s = 0; s < p.split; ++s) {
+          if (s == part) continue;
+          const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.ws_ml + (static_cast<size_t>(tile * p.split + s) * 128 + row) * 2));
+          l += ml.y * a64_ex2(ml.x - m_all);
+        }
+      }
+      const float inv_l = 1.0f / l;
+      typename H::T* orow = static_cast<typename H::T*>(p.o) + static_cast<long long>(b) * p.o_batch_stride +
+                            static_cast<long long>(qrow) * p.o_row_stride + head * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(o_t + c * 32, v);
+        tmem_wait_ld();
+        if (p.split > 1) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) * scale_self);
+          for (int s = 0; s < p.split; ++s) {
+            if (s == part) continue;
+            const size_t base = static_cast<size_t>(tile * p.split + s) * 128 + row;
+            const float* src = p.ws_o + base * 64 + c * 32;
+            const float a = a64_ex2(__ldcg(p.ws_ml + base * 2) - m_all);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 t = __ldcg(reinterpret_cast<const float4*>(src + g * 4));
+              v[g * 4 + 0] = __float_as_uint(fmaf(t.x, a, __uint_as_float(v[g * 4 + 0])));
+              v[g * 4 + 1] = __float_as_uint(fmaf(t.y, a, __uint_as_float(v[g * 4 + 1])));
+              v[g * 4 + 2] = __float_as_uint(fmaf(t.z, a, __uint_as_float(v[g * 4 + 2])));
+              v[g * 4 + 3] = __float_as_uint(fmaf(t.w, a, __uint_as_float(v[g * 4 + 3])));
+            }
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = H::pack(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
+            o.y = H::pack(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
+            o.z = H::pack(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
+            o.w = H::pack(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+int init_attention64() {
+  cudaError_t e = cudaFuncSetAttribute(attention64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Cfg::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention (head_dim 64) smem attr: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+bool attention64_enabled() {
+  static const bool on = !(getenv("B200_ATTN_V2") && atoi(getenv("B200_ATTN_V2")) == 0);
+  return on;
+}
+
+// Work items = tiles x split on 2 x SMs CTA slots: pick the split whose last wave is fullest.  Cost in units of one
+// 64-key half of one CTA: fixed (prologue + epilogue) ~ 3, combine ~ 2 (tools/bench_attention.py sweeps B200_ATTN_KV_SPLIT).
+static int pick_split(long long tiles, int kv_halves, bool have_ws) {
+  static const int forced = getenv("B200_ATTN_KV_SPLIT") ? atoi(getenv("B200_ATTN_KV_SPLIT")) : 0;
+  if (!have_ws) return 1;
+  const long long slots = 2ll * num_sms();
+  double best = 1e30;
+  int best_s = 1;
+  for (int s : {1, 2, 4}) {
+    if (forced && s != forced) continue;
+    if (s > 1 && kv_halves < 4 * s) continue;  // keep >= 4 halves per part
+    const int per = (kv_halves + s - 1) / s;
+    if (static_cast<long long>(per) * (s - 1) >= kv_halves) continue;  // an empty part
+    const long long waves = (tiles * s + slots - 1) / slots;
+    const double cost = static_cast<double>(waves) * (per + 3.0) + (s > 1 ? 2.0 : 0.0);
+    if (cost < best * 0.97) {  // a split must win by 3 %
+      best = cost;
+      best_s = s;
+    }
+  }
+  return best_s;
+}
+
+static constexpr long long kWsPerItem = 128ll * 64 * 4 + 128 * 2 * 4;  // parked O + (m, l)
+
+long long attention64_workspace_bytes(long long tiles) {
+  // counters (one per tile, 4 B) + 4 parts per tile
+  return ((tiles * 4 + 255) / 256) * 256 + tiles * 4 * kWsPerItem;
+}
+
+// head_dim 64, one query tile per CTA; arguments already validated by b200_attention
+int launch_attention64(const b200_attention_args* a, cudaStream_t st) {
+  Attn64Params prm;
+  memset(&prm, 0, sizeof(prm));
+  auto mk = [&](CUtensorMap* m, const void* base, int rows, long long row_stride, long long batch_stride, uint32_t box_rows,
+                const char* what) {
+    const uint32_t box[4] = {64u, box_rows, 1u, 1u};
+    const uint64_t dims[4] = {64u, static_cast<uint64_t>(rows), static_cast<uint64_t>(a->heads), static_cast<uint64_t>(a->batch)};
+    const uint64_t str[3] = {static_cast<uint64_t>(row_stride) * 2, 64u * 2,
+                             static_cast<uint64_t>(batch_stride > 0 ? batch_stride : row_stride * rows) * 2};
+    return make_tensor_map_16b(m, base, 4, dims, str, box, what);
+  };
+  int r;
+  if ((r = mk(&prm.q_map, a->q, a->sq, a->q_row_stride, a->q_batch_stride, 128u, "attention Q"))) return r;
+  if ((r = mk(&prm.k_map, a->k, a->sk, a->k_row_stride, a->k_batch_stride, 64u, "attention K (halves)"))) return r;
+  if ((r = mk(&prm.v_map, a->v, a->sk, a->v_row_stride, a->v_batch_stride, 64u, "attention V (halves)"))) return r;
+  prm.o = a->o;
+  prm.o_row_stride = a->o_row_stride;
+  prm.o_batch_stride = a->o_batch_stride;
+  prm.batch = a->batch;
+  prm.heads = a->heads;
+  prm.sq = a->sq;
+  prm.sk = a->sk;
+  prm.q_tiles = (a->sq + 127) / 128;
+  prm.kv_halves = (a->sk + 63) / 64;
+  const float scale = a->scale > 0.f ? a->scale : 0.125f;
+  prm.scale_log2 = scale * 1.4426950408889634f;
+  const long long tiles = static_cast<long long>(a->batch) * a->heads * prm.q_tiles;
+  const bool have_ws = a->workspace != nullptr && a->workspace_bytes >= attention64_workspace_bytes(tiles) && aligned16(a->workspace);
+  int split = a->kv_split > 0 ? a->kv_split : pick_split(tiles, prm.kv_halves, have_ws);
+  B200_CHECK_ARG(split == 1 || split == 2 || split == 4, "attention: kv_split %d (1, 2 or 4)", split);
+  if (split > 1) {
+    B200_CHECK_ARG(have_ws, "attention: kv_split %d needs a workspace of b200_attention_workspace_bytes()", split);
+    const int per = (prm.kv_halves + split - 1) / split;
+    B200_CHECK_ARG(static_cast<long long>(per) * (split - 1) < prm.kv_halves, "attention: kv_split %d leaves a part without keys (sk=%d)", split, a->sk);
+  }
+  prm.split = split;
+  prm.halves_per_split = (prm.kv_halves + split - 1) / split;
+  if (split > 1) {
+    uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+    const long long cbytes = ((tiles * 4 + 255) / 256) * 256;
+    prm.counters = reinterpret_cast<unsigned int*>(ws);
+    prm.ws_o = reinterpret_cast<float*>(ws + cbytes);
+    prm.ws_ml = reinterpret_cast<float*>(ws + cbytes + tiles * split * 128ll * 64 * 4);
+  }
+  const long long grid_ll = tiles * split;
+  B200_CHECK_ARG(grid_ll < (1ll << 31), "attention: grid too large");
+  const bool fp16 = a->dtype == B200_DTYPE_FP16;
+  cudaError_t e = fp16 ? launch_pdl(attention64_kernel<true>, dim3(static_cast<unsigned>(grid_ll)), dim3(Attn64Cfg::THREADS),
+                                    Attn64Cfg::SMEM_BYTES, st, prm)
+                       : launch_pdl(attention64_kernel<false>, dim3(static_cast<unsigned>(grid_ll)), dim3(Attn64Cfg::THREADS),
+                                    Attn64Cfg::SMEM_BYTES, st, prm);
+  if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention (head_dim 64) launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace b200

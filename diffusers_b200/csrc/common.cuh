@@ -209,6 +209,22 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+// Same as tmem_ld32, into elements [OFF, OFF + 32) of a larger register array (no address-of: the array stays in registers).
+template <int OFF, int N>
+__device__ __forceinline__ void tmem_ld32_at(uint32_t taddr, uint32_t (&v)[N]) {
+  static_assert(OFF >= 0 && OFF + 32 <= N, "tmem_ld32_at: range");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[OFF + 0]), "=r"(v[OFF + 1]), "=r"(v[OFF + 2]), "=r"(v[OFF + 3]), "=r"(v[OFF + 4]), "=r"(v[OFF + 5]), "=r"(v[OFF + 6]),
+        "=r"(v[OFF + 7]), "=r"(v[OFF + 8]), "=r"(v[OFF + 9]), "=r"(v[OFF + 10]), "=r"(v[OFF + 11]), "=r"(v[OFF + 12]), "=r"(v[OFF + 13]),
+        "=r"(v[OFF + 14]), "=r"(v[OFF + 15]), "=r"(v[OFF + 16]), "=r"(v[OFF + 17]), "=r"(v[OFF + 18]), "=r"(v[OFF + 19]), "=r"(v[OFF + 20]),
+        "=r"(v[OFF + 21]), "=r"(v[OFF + 22]), "=r"(v[OFF + 23]), "=r"(v[OFF + 24]), "=r"(v[OFF + 25]), "=r"(v[OFF + 26]), "=r"(v[OFF + 27]),
+        "=r"(v[OFF + 28]), "=r"(v[OFF + 29]), "=r"(v[OFF + 30]), "=r"(v[OFF + 31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

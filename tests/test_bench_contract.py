@@ -17,13 +17,14 @@ REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
 
 def _args(**kw):
     d = dict(workload="sdxl", gpus=1, steps=3, warmup=3, impl="reference", batch=1, denoise_steps=50, guidance_scale=7.5,
-             no_cpu_baseline=False)
+             no_cpu_baseline=False, no_config3=False, no_reference_cuda=False)
     d.update(kw)
     return argparse.Namespace(**d)
 
 
 def test_reference_arm_line(monkeypatch):
-    stub = dict(value=3.2e-4, unit="images/s", cores=128, kind="port", sample="stub", t_unet_b2_s=60.0, setup_s=1.0)
+    stub = dict(value=3.2e-4, unit="images/s", cores=64, kind="reference", sample="stub", dtype="bf16", t_step_s=6.0, t_step_runs_s=[6.1, 5.9],
+                run_spread=0.03, setup_s=1.0)
     monkeypatch.setattr(bench, "cpu_reference", lambda args, full=True: stub)
     buf = io.StringIO()
     with redirect_stdout(buf):
@@ -38,7 +39,8 @@ def test_reference_arm_line(monkeypatch):
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["metric"].startswith("images/sec") and d["unit"] == "images/s"
     assert d["config"]["workload"] == bench.sdxl_workload(_args()) == "sdxl_unet_1024_50step_cfg7.5_b1_per_gpu+vae_decode"
-    assert d["cpu_baseline"] == {k: stub[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    assert {k: d["cpu_baseline"][k] for k in ("value", "unit", "cores", "kind", "sample")} == {k: stub[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    assert d["dtype"] == "bf16"  # the arm reports the dtype it actually ran
     assert d["e2e"] == dict(value=stub["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert d["gpu_launches"] == 0 and abs(d["ms_per_step"] - 1000.0 / stub["value"]) < 1e-6
 
@@ -65,5 +67,11 @@ def test_peaks_source(tmp_path, monkeypatch):
 
 
 def test_flop_constants_match_baseline():
-    assert abs(bench.IMAGE_FLOP / 1e12 - 686.6) < 0.1  # 2 x 50 x 6.7612 + 10.470 TFLOP per image
-    assert abs(bench.MID_BLOCK_SHARE - 0.1179) < 1e-3
+    # 2 x 50 x 6.7612 + 10.470 TFLOP per image; 74.385 TFLOP per Flux forward
+    assert abs((2 * 50 * bench.UNET_FLOP_PER_SAMPLE + bench.VAE_FLOP_PER_IMAGE) / 1e12 - 686.6) < 0.1
+    assert abs(28 * bench.FLUX_FLOP_PER_FORWARD / 1e12 - 2082.8) < 0.1
+
+
+def test_one_numa_node_physical_cores_is_a_subset_of_the_affinity_mask():
+    cores = bench.one_numa_node_physical_cores()
+    assert cores and set(cores) <= set(os.sched_getaffinity(0)) and len(set(cores)) == len(cores)

@@ -70,7 +70,11 @@ def test_reference_sdxl_pipeline_drives_the_shells(golden):
           f"image mean {float(ie.mean()):.4g}; vs this repo's loop: latents {d_lat:.3g} image {d_img:.3g}")
     assert tuple(img.shape) == tuple(fx["image"].shape) and img.dtype == torch.bfloat16
     assert d_lat == 0.0 and d_img <= 1e-2  # same kernels in the same order; the image differs only by where the [0,1] clamp rounds
-    assert float(e.mean()) < 3e-2 and float(ie.mean()) < 2e-2  # same bounds as tests/test_pipelines_gpu.py reaches for this fixture
+    # against the recorded fp32 run: the bound of tests/test_pipelines_gpu.py (the distance the oracle run in bf16 keeps)
+    from test_pipelines_gpu import _oracle_bf16_distance
+    ref_err, ref_img_err = _oracle_bf16_distance(fx)
+    assert float(e.mean()) <= 1.5 * float(ref_err.mean()) + 2e-3 and float(e.max()) <= 2.0 * float(ref_err.max()) + 2e-2
+    assert float(ie.mean()) <= 1.5 * float(ref_img_err.mean()) + 2e-3
 
 
 def test_reference_flux_pipeline_drives_the_shells(golden):
@@ -99,7 +103,7 @@ def test_reference_flux_pipeline_drives_the_shells(golden):
     d = float((lat.float() - lat_own.float()).abs().max())
     print(f"\nreference FluxPipeline around the shells: latents vs recorded reference fp32 max {float(e.max()):.4g} mean {float(e.mean()):.4g}; "
           f"vs this repo's loop {d:.3g}")
-    assert float(e.mean()) < 3e-2 and float(e.max()) < 0.3
+    assert float(e.mean()) < 3e-2 and float(e.max()) < 0.3  # the bound tests/test_pipelines_gpu.py::test_flux_pipeline uses
     assert d <= 2e-2
 
 

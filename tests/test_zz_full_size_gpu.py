@@ -91,13 +91,8 @@ def _attention_cases_under(env_extra, timeout=300):
     assert "FAIL" not in summary and "ERROR" not in summary, p.stdout[-3000:]
 
 
-def test_attention_unpipelined_kernel_still_matches():
-    """head_dim 64 defaults to the pipelined kernel (attention_pipe.cu); the original kernel stays reachable with
-    B200_ATTN_PIPE=0 and must keep passing the same cases."""
-    _attention_cases_under(dict(B200_ATTN_PIPE="0"))
-
-
-@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_EXPERIMENTAL") != "1",
-                    reason="attention_split.cu is experimental and off by default; set B200_TEST_EXPERIMENTAL=1 to try it")
-def test_attention_split_variant_experimental():
-    _attention_cases_under(dict(B200_ATTN_SPLIT="1"), timeout=120)
+def test_attention_fallback_kernels_still_match():
+    """head_dim 64 defaults to attention64.cu; the round-1 kernels stay reachable (B200_ATTN_V2=0 -> attention_pipe.cu,
+    additionally B200_ATTN_PIPE=0 -> attention.cu) and must keep passing the same cases."""
+    _attention_cases_under(dict(B200_ATTN_V2="0"))
+    _attention_cases_under(dict(B200_ATTN_V2="0", B200_ATTN_PIPE="0"))

@@ -15,15 +15,17 @@ for name, B, H, Sq, Sk, D in SHAPES:
     k = torch.randn(B, Sk, H * D, generator=g, device="cuda").bfloat16()
     v = torch.randn(B, Sk, H * D, generator=g, device="cuda").bfloat16()
     out = torch.empty_like(q)
-    for nq in (0, 1, 2):
+    for nq, split in ((0, 0), (1, 1), (1, 2), (1, 4), (2, 0)):
+        if split > 1 and (D != 64 or Sk < 512):
+            continue
         for _ in range(3):
-            ops.attention(q, k, v, heads=H, head_dim=D, out=out, nq=nq)
+            ops.attention(q, k, v, heads=H, head_dim=D, out=out, nq=nq, kv_split=split)
         torch.cuda.synchronize()
         gr = torch.cuda.CUDAGraph()
         n = 20
         with torch.cuda.graph(gr):
             for _ in range(n):
-                ops.attention(q, k, v, heads=H, head_dim=D, out=out, nq=nq)
+                ops.attention(q, k, v, heads=H, head_dim=D, out=out, nq=nq, kv_split=split)
         gr.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -33,4 +35,4 @@ for name, B, H, Sq, Sk, D in SHAPES:
         torch.cuda.synchronize()
         us = 1000 * e0.elapsed_time(e1) / n
         fl = 4.0 * B * H * Sq * Sk * D
-        print(f"{name:22s} nq={nq} (0 = heuristic) {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s")
+        print(f"{name:22s} nq={nq} kv_split={split} (0 = heuristic) {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s")

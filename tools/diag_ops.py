@@ -21,6 +21,13 @@ CASES = {
     "attn_d128_nq1": dict(kind="attn", B=1, H=4, Sq=640, Sk=640, D=128, nq=1),
     "attn_d64_fp16": dict(kind="attn", B=1, H=4, Sq=512, Sk=512, D=64, fp16=True),
     "attn_bigvals": dict(kind="attn", B=1, H=2, Sq=256, Sk=1024, D=64, qscale=6.0),
+    # head_dim 64: keys of one query tile split over 1 / 2 / 4 CTAs with the in-kernel combine (attention64.cu); ragged tails
+    "attn_d64_nosplit": dict(kind="attn", B=2, H=20, Sq=1024, Sk=1024, D=64, kv_split=1),
+    "attn_d64_split2": dict(kind="attn", B=2, H=20, Sq=1024, Sk=1024, D=64, kv_split=2),
+    "attn_d64_split4": dict(kind="attn", B=2, H=20, Sq=1024, Sk=1024, D=64, kv_split=4),
+    "attn_d64_split4_ragged": dict(kind="attn", B=1, H=3, Sq=300, Sk=1000, D=64, kv_split=4),
+    "attn_d64_split2_odd": dict(kind="attn", B=1, H=2, Sq=128, Sk=64 * 9 + 5, D=64, kv_split=2, qscale=3.0),
+    "attn_d64_halves_1to6": dict(kind="attn_sweep"),
     "gn_small": dict(kind="gn", B=2, HW=64, C=64, G=32, silu=True),
     "gn_320": dict(kind="gn", B=2, HW=16384, C=320, G=32, silu=True),
     "gn_1280": dict(kind="gn", B=2, HW=1024, C=1280, G=32, silu=False, eps=1e-6),
@@ -99,13 +106,27 @@ def run_case(name):
             if Sk != Sq:
                 kv = rnd(B, Sk, 2 * H * D)
                 k, v = kv[:, :, :H * D], kv[:, :, H * D:]
-        out = ops.attention(q, k, v, heads=H, head_dim=D, nq=cfg.get("nq", 0))
+        out = ops.attention(q, k, v, heads=H, head_dim=D, nq=cfg.get("nq", 0), kv_split=cfg.get("kv_split", 0))
+        if cfg.get("kv_split", 0) > 1:  # the arrival counters reset themselves: a second launch on the same workspace must agree
+            out2 = ops.attention(q, k, v, heads=H, head_dim=D, kv_split=cfg["kv_split"])
+            assert torch.equal(out, out2) or cfg["kv_split"] > 1 and (out.float() - out2.float()).abs().max() < 1e-2
         torch.cuda.synchronize()
         qf = q.float().reshape(B, Sq, H, D).transpose(1, 2)
         kf = k.float().reshape(B, Sk, H, D).transpose(1, 2)
         vf = v.float().reshape(B, Sk, H, D).transpose(1, 2)
         ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, Sq, H * D)
         return report(name, out, ref, 2e-2, 6e-3 if dt == torch.bfloat16 else 1.5e-3)
+    if kind == "attn_sweep":
+        # every count of 64-key halves from 1 to 6 with a ragged last half: each exit of the software-pipelined loop
+        ok = True
+        for Sk in (40, 64, 100, 128, 190, 256, 300, 384):
+            q, k, v = rnd(1, 130, 128), rnd(1, Sk, 128), rnd(1, Sk, 128)
+            out = ops.attention(q, k, v, heads=2, head_dim=64)
+            torch.cuda.synchronize()
+            sp = lambda t: t.float().reshape(1, -1, 2, 64).transpose(1, 2)  # noqa: E731
+            ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(1, 130, 128)
+            ok &= report(f"{name}_sk{Sk}", out, ref, 2e-2, 6e-3)
+        return ok
     if kind == "gn":
         B, HW, Cc, G = cfg["B"], cfg["HW"], cfg["C"], cfg["G"]
         C2 = cfg.get("C2", 0)

@@ -8,12 +8,14 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 for step in "$@"; do
   t0=$(date +%s)
   case "$step" in
-    tests)   timeout 1100 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" ;;
+    tests)   timeout 1100 python -m pytest tests -m gpu -q -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" ;;
     tests_noflux) timeout 900 python -m pytest tests -m gpu -x -q -s --deselect tests/test_full_size_parity_gpu.py::test_flux_full_size_parity > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" ;;
     newtests) timeout 900 python -m pytest tests/test_full_size_parity_gpu.py tests/test_dropin_reference_gpu.py -m gpu -q -s > gpurun_out/pytest_new.log 2>&1; echo "new tests rc=$?" ;;
     ncu)     timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off -f -o gpurun_out/r2_targets python tools/ncu_targets.py > gpurun_out/ncu_targets.log 2>&1; echo "ncu rc=$?" ;;
     libbar)  timeout 600 python tools/library_bar.py --json gpurun_out/library_bar.json > gpurun_out/library_bar.txt 2>&1; echo "libbar rc=$?" ;;
     attn)    timeout 300 python tools/bench_attention.py > gpurun_out/bench_attention.txt 2>&1; echo "attn rc=$?" ;;
+    attncheck) timeout 400 python tools/diag_ops.py --inproc $(python -c "import sys; sys.path.insert(0,'.'); from tools import diag_ops; print(' '.join(c for c in diag_ops.CASES if c.startswith('attn_')))") > gpurun_out/attn_check.txt 2>&1; echo "attncheck rc=$?"; tail -3 gpurun_out/attn_check.txt ;;
+    ncuattn) timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:attention -f -o gpurun_out/r2_attn python tools/ncu_targets.py > gpurun_out/ncu_attn.log 2>&1; echo "ncuattn rc=$?" ;;
     gemm)    timeout 600 python tools/bench_gemm.py > gpurun_out/bench_gemm.txt 2>&1; echo "gemm rc=$?" ;;
     bench)   timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" ;;
     benchref) timeout 900 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref rc=$?" ;;
