@@ -117,12 +117,24 @@ def _need_cuda(t, name):
     _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
 
 
+class FoldedLayerNorm:
+    """Operands of a LayerNorm folded into the Linear that consumes it (b200_conv_gemm_args.ln_*): the row statistics written
+    by the GEMM that produced the activations (`row_stats=True`), and the per-column fp32 vectors of packing.fold_layer_norm."""
+    __slots__ = ("stats", "colsum", "bias", "eps")
+
+    def __init__(self, stats, colsum, bias, eps):
+        self.stats, self.colsum, self.bias, self.eps = stats, colsum, bias, eps
+
+
 def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, act=ACT_NONE, geglu=False,
-              gate=None, rowvec=None, rows_per_group=0, residual=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None):
+              gate=None, rowvec=None, rows_per_group=0, residual=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None,
+              row_stats=False, ln=None):
     """y = epilogue(conv/linear(x [, x2]))  -  see b200_conv_gemm in include/b200_diffusion.h.
 
     x, x2: NHWC activations given as 2-D [batch*H*W, C] (or any shape whose last dim is C, contiguous rows).
-    w: packed [N, Kp] (packing.pack_conv_weight / pack_linear_weight / pack_geglu)."""
+    w: packed [N, Kp] (packing.pack_conv_weight / pack_linear_weight / pack_geglu).
+    row_stats=True: also returns the fp32 [M, N/32, 2] per-chunk (sum, sum of squares) of the rounded outputs -> (y, stats).
+    ln: a FoldedLayerNorm - w holds W*gamma and the epilogue applies the normalisation of the raw rows of x."""
     _need_cuda(x, "x")
     c0 = x.shape[-1]
     c1 = x2.shape[-1] if x2 is not None else 0
@@ -153,6 +165,13 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
     a.out_fp32 = 1 if out_fp32 else 0
     a.cluster_m = cluster_m
     a.debug_timestamps = _ptr(debug_timestamps)
+    stats = None
+    if row_stats:
+        stats = torch.empty((batch * Ho * Wo, n_out // 32, 2), dtype=torch.float32, device=x.device)
+        a.row_stats_out = stats.data_ptr()
+    if ln is not None:
+        a.ln_stats, a.ln_parts, a.ln_eps = ln.stats.data_ptr(), ln.stats.shape[1], ln.eps
+        a.ln_colsum, a.ln_bias = ln.colsum.data_ptr(), ln.bias.data_ptr()
     if _PLAN is not None:
         nxt = _PLAN._step(w)
         if nxt is not None:
@@ -167,16 +186,16 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
     else:
         _lib.check(_lib.lib().b200_conv_gemm(C.byref(a), _stream()), "b200_conv_gemm")
     _count()
-    return out
+    return (out, stats) if row_stats else out
 
 
 def linear(x, w, N, *, bias=None, act=ACT_NONE, geglu=False, gate=None, rowvec=None, rows_per_group=0,
-           residual=None, x2=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None):
+           residual=None, x2=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None, row_stats=False, ln=None):
     """nn.Linear on token rows: x [rows, K] (row stride arbitrary multiple of 8)."""
     rows = x.shape[0]
     return conv_gemm(x, w, N, batch=1, H=1, W=rows, ksize=1, stride=1, x2=x2, bias=bias, act=act, geglu=geglu,
                      gate=gate, rowvec=rowvec, rows_per_group=rows_per_group, residual=residual, out=out,
-                     tile_n=tile_n, out_fp32=out_fp32, cluster_m=cluster_m, debug_timestamps=debug_timestamps)
+                     tile_n=tile_n, out_fp32=out_fp32, cluster_m=cluster_m, debug_timestamps=debug_timestamps, row_stats=row_stats, ln=ln)
 
 
 def pick_tile_n(M, N, geglu=False):

@@ -55,6 +55,33 @@ def pack_geglu(w, b, tile_n):
     return pack_linear_weight(wp), bp
 
 
+def fold_layer_norm(w, gamma, beta, bias, dtype):
+    """nn.LayerNorm(gamma, beta) followed by nn.Linear(w, bias), as the operands of b200_conv_gemm's folded form:
+        LN(x) W^T + b = rstd * (x (W*gamma)^T) - rstd * mean * colsum + (b + W beta).
+    Returns (W*gamma rounded to `dtype` [N, K], ln_bias fp32 [N]); colsum is taken from the PACKED weight by `ln_colsum`
+    (it must sum exactly the 16-bit values the tensor cores multiply)."""
+    wf = w.to(torch.float32)
+    wg = wf if gamma is None else wf * gamma.to(torch.float32)[None, :]
+    lb = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device) if beta is None else wf @ beta.to(torch.float32)
+    if bias is not None:
+        lb = lb + bias.to(torch.float32)
+    return wg.to(dtype), lb.contiguous()
+
+
+def ln_colsum(w_packed):
+    """fp32 row sums of a packed 16-bit weight (the zero padding adds nothing)."""
+    return w_packed.to(torch.float32).sum(dim=1).contiguous()
+
+
+def unfold_layer_norm(w_folded, gamma):
+    """Inverse of the weight part of fold_layer_norm in 16-bit arithmetic: exact when every gamma is a power of two (the
+    default init, gamma = 1, included); otherwise the weight is re-rounded once (construct the model with fold_norms=False
+    to keep bit-exact copies of a checkpoint's weights)."""
+    if gamma is None:
+        return w_folded
+    return (w_folded.to(torch.float32) / gamma.to(torch.float32)[None, :]).to(w_folded.dtype)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # inverses (used by the shells' reference_state_dict(): packed buffers -> the reference's parameter tensors)
 # ----------------------------------------------------------------------------------------------------------------------

@@ -194,3 +194,49 @@ def test_unsupported_checkpoint_options_are_refused():
                 layers_per_block=1)
     with pytest.raises(NotImplementedError):
         AutoencoderKL(vcfg, {}, device="cpu")
+
+
+def test_fold_layer_norm_algebra_and_inverse():
+    """packing.fold_layer_norm / ln_colsum: LN(x) W^T + b == rstd * (x (W gamma)^T) - rstd * mean * colsum + (b + W beta), evaluated the way
+    the GEMM epilogue does (raw rows, per-row statistics from E[x^2] - E[x]^2); and the inverse used by reference_state_dict."""
+    torch.manual_seed(0)
+    M, K, N = 64, 96, 40
+    x = (torch.randn(M, K) * 2 + 1.5).bfloat16()
+    w, b = (torch.randn(N, K) * K ** -0.5).bfloat16(), torch.randn(N).bfloat16()
+    gamma, beta = (torch.randn(K) * 0.3 + 1).bfloat16(), (torch.randn(K) * 0.5).bfloat16()
+    wf, lb = packing.fold_layer_norm(w, gamma, beta, b, torch.bfloat16)
+    wp = packing.pack_linear_weight(wf)
+    cs = packing.ln_colsum(wp)
+    xf = x.float()
+    mean = xf.mean(1, keepdim=True)
+    var = (xf * xf).mean(1, keepdim=True) - mean * mean
+    rstd = torch.rsqrt(var + 1e-5)
+    acc = xf @ packing.unpack_linear_weight(wp, K).float().t()
+    got = rstd * acc - rstd * mean * cs[None] + lb[None]
+    ref = torch.nn.functional.layer_norm(xf, (K,), gamma.float(), beta.float(), 1e-5) @ w.float().t() + b.float()
+    assert (got - ref).abs().max() < 3e-2  # W*gamma is rounded to bf16 once
+    # gamma a power of two: the fold is exactly invertible
+    g2 = torch.full((K,), 0.5).bfloat16()
+    wf2, _ = packing.fold_layer_norm(w, g2, beta, b, torch.bfloat16)
+    assert torch.equal(packing.unfold_layer_norm(wf2, g2), w)
+
+
+def test_unet_fold_norms_flag_keeps_exact_weights_when_off():
+    ucfg = dict(specs.SDXL_UNET_CONFIG)
+    ucfg.update(sample_size=16, block_out_channels=(64, 128), down_block_types=("DownBlock2D", "CrossAttnDownBlock2D"),
+                up_block_types=("CrossAttnUpBlock2D", "UpBlock2D"), cross_attention_dim=64, transformer_layers_per_block=(1, 1),
+                attention_head_dim=(1, 2), addition_time_embed_dim=8, projection_class_embeddings_input_dim=6 * 8 + 16, layers_per_block=1)
+    from diffusers_b200.unet_2d_condition import UNet2DConditionModel
+    sd = specs.random_state_dict(specs.unet2d_condition_params(ucfg), seed=0)
+    g = torch.Generator().manual_seed(5)
+    for k in sd:  # non-trivial LayerNorm affine parameters (the default init is gamma = 1, beta = 0)
+        if ".transformer_blocks." in k and ".norm" in k:
+            sd[k] = (torch.randn(sd[k].shape, generator=g) * 0.3 + (1.0 if k.endswith("weight") else 0.0)).bfloat16()
+    exact = UNet2DConditionModel(ucfg, sd, device="cpu", fold_norms=False).reference_state_dict()
+    assert all(torch.equal(exact[k], sd[k]) for k in sd)
+    folded = UNet2DConditionModel(ucfg, sd, device="cpu").reference_state_dict()
+    for k in sd:
+        d = (folded[k].float() - sd[k].float()).abs().max()
+        # weights: re-rounded once at most; the GEGLU bias comes back as (b + W beta) - W' beta with the re-rounded W'
+        tol = 5e-3 if k.endswith("ff.net.0.proj.bias") else 2.0 ** -7 * sd[k].float().abs().max() + 1e-6
+        assert d <= tol, (k, float(d))

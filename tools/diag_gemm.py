@@ -28,6 +28,13 @@ CASES = {
     "lin_geglu64": dict(kind="linear", M=130, N=192, K=64, bias=True, geglu=True),
     "lin_fp16": dict(kind="linear", M=512, N=256, K=512, bias=True, fp16=True),
     "lin_ff": dict(kind="linear", M=2048, N=10240, K=1280, bias=True, geglu=True),
+    # LayerNorm folded into the consuming GEMM (b200_conv_gemm_args.ln_*): producer statistics + consumer epilogue, against
+    # fp32 LayerNorm -> Linear (-> GEGLU); gamma / beta random (the model fixtures only have the default gamma = 1, beta = 0)
+    "lnfold_sdxl": dict(kind="lnfold", M=2048, C=1280, N=3840),
+    "lnfold_bias": dict(kind="lnfold", M=1000, C=640, N=640, bias=True, mean=3.0),
+    "lnfold_geglu": dict(kind="lnfold", M=2048, C=1280, N=10240, bias=True, geglu=True),
+    "lnfold_small": dict(kind="lnfold", M=130, C=64, N=64, bias=True, geglu=True, mean=-2.0),
+    "lnfold_fp16": dict(kind="lnfold", M=512, C=320, N=320, bias=True, fp16=True),
     "conv_small": dict(kind="conv", B=2, H=16, W=16, C=64, N=64, bias=True),
     "conv_32": dict(kind="conv", B=2, H=32, W=32, C=128, N=192, bias=True, rowvec=True, residual=True),
     "conv_128": dict(kind="conv", B=2, H=128, W=128, C=320, N=320, bias=True),
@@ -58,6 +65,51 @@ def run_case(name):
     act = cfg.get("act", 0)
     geglu = cfg.get("geglu", False)
     tile_n = cfg.get("tile_n", 0)
+    if cfg["kind"] == "lnfold":
+        M, Cc, N = cfg["M"], cfg["C"], cfg["N"]
+        eps = 1e-5
+        # producer: h = linear(a, wp) + bias + residual with row statistics out
+        a = rnd(M, Cc)
+        w0 = rnd(Cc, Cc, scale=Cc ** -0.5)
+        b0 = rnd(Cc)
+        res = (torch.randn(M, Cc, generator=g, device=dev) * 1.5 + cfg.get("mean", 0.0)).to(dt)
+        h, st = ops.linear(a, packing.pack_linear_weight(w0), Cc, bias=b0, residual=res, row_stats=True)
+        torch.cuda.synchronize()
+        hf = h.float()
+        st_ref = torch.stack([hf.reshape(M, Cc // 32, 32).sum(-1), (hf * hf).reshape(M, Cc // 32, 32).sum(-1)], -1)
+        ok = bool(((st - st_ref).abs() <= 1e-4 * st_ref.abs() + 1e-3).all())
+        print("RESULT " + json.dumps(dict(case=name + "_producer_stats", max_abs=float((st - st_ref).abs().max()), ok=ok)))
+        # consumer: LN(h) W^T + b (-> GEGLU) with gamma folded into the weight
+        gamma, beta = rnd(Cc) * 0.3 + 1, rnd(Cc) * 0.5
+        w = rnd(N, Cc, scale=Cc ** -0.5)
+        b = rnd(N) if cfg.get("bias") else None
+        wf, lb = packing.fold_layer_norm(w, gamma, beta, b, dt)
+        if geglu:
+            tn = ops.pick_tile_n(M, N, True)
+            wp, lbp = packing.pack_geglu(wf, lb, tn)
+        else:
+            tn = 0
+            wp, lbp = packing.pack_linear_weight(wf), lb
+        out = ops.linear(h, wp, N, geglu=geglu, tile_n=tn, ln=ops.FoldedLayerNorm(st, packing.ln_colsum(wp), lbp.contiguous(), eps))
+        torch.cuda.synchronize()
+        n = F.layer_norm(hf, (Cc,), gamma.float(), beta.float(), eps)
+        ref = n @ w.float().t()
+        if b is not None:
+            ref = ref + b.float()
+        if geglu:
+            hv, gt = ref.chunk(2, dim=-1)
+            ref = hv * F.gelu(gt)
+        o = out.float()
+        err = (o - ref).abs()
+        tol = 1.5e-2 * ref.abs() + 2e-2 if dt == torch.bfloat16 else 3e-3 * ref.abs() + 4e-3
+        bad = err > tol
+        # the reference's own path rounds LN(h) to 16 bit before the GEMM: its distance from the same fp32 result, for the record
+        ref16 = (n.to(dt).float() @ w.float().t() + (b.float() if b is not None else 0)).to(dt).float() if not geglu else None
+        print("RESULT " + json.dumps(dict(case=name, shape=list(o.shape), max_abs=float(err.max()), ref_absmax=float(ref.abs().max()),
+                                           n_bad=int(bad.sum()), nan=int(torch.isnan(o).sum()),
+                                           mean_abs=float(err.mean()),
+                                           eager16_mean_abs=None if ref16 is None else float((ref16 - ref).abs().mean()))))
+        return ok and int(bad.sum()) == 0 and int(torch.isnan(o).sum()) == 0
     if cfg["kind"] == "linear":
         M, N, K = cfg["M"], cfg["N"], cfg["K"]
         K2 = cfg.get("K2", 0)
