@@ -113,10 +113,11 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
   uint64_t* s_full = v_empty + VS;       // [2]  S(h) landed in TMEM
   uint64_t* p_full = s_full + 2;         // [2]  softmax wrote P(h) and is done with S(h): 128 arrivals
   uint64_t* pv_done = p_full + 2;        // [2]  P(h) V(h) accumulated into O (P buffer reusable, O consistent)
-  uint64_t* o_full = pv_done + 2;        // [1]
+  uint64_t* s_free = pv_done + 2;        // [2]  every softmax thread holds S(h) in registers: the buffer can take S(h+2): 128 arrivals
+  uint64_t* o_full = s_free + 2;         // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
   uint32_t* ticket = tmem_ptr + 1;       // combine: this CTA's arrival order within its tile
-  static_assert((1 + 2 * KS + 2 * VS + 2 + 2 + 2 + 1) * 8 + 8 <= 256, "barrier area");
+  static_assert((1 + 2 * KS + 2 * VS + 2 + 2 + 2 + 2 + 1) * 8 + 8 <= 256, "barrier area");
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&s_free[i], 128);
     }
     fence_barrier_init();
   }
@@ -222,18 +224,13 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
         }
         if (++ks == KS) { ks = 0; kph ^= 1u; }
       }
+      // The softmax reads S(h) into registers one step before it turns it into P(h) (software pipelining), so the score
+      // buffer of half h is free a whole step before P(h) exists: S(h+2) is issued as soon as s_free(h) arrives, AHEAD of
+      // P(h) V(h), and is complete when the softmax asks for it.
       for (int h = 0; h < n_half; ++h) {
         const int buf = h & 1;
-        mbar_wait(&p_full[buf], (h >> 1) & 1u);
-        mbar_wait(&v_full[vs], vph);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_pv(buf, vs, h > 0);
-          umma_commit(&v_empty[vs]);
-          umma_commit(&pv_done[buf]);
-        }
-        if (++vs == VS) { vs = 0; vph ^= 1u; }
-        if (h + 2 < n_half) {  // the softmax has released S_buf: refill it two halves ahead
+        if (h + 2 < n_half) {
+          mbar_wait(&s_free[buf], (h >> 1) & 1u);
           mbar_wait(&k_full[ks], kph);
           tc_fence_after();
           if (elect_one()) {
@@ -243,6 +240,15 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
           }
           if (++ks == KS) { ks = 0; kph ^= 1u; }
         }
+        mbar_wait(&p_full[buf], (h >> 1) & 1u);
+        mbar_wait(&v_full[vs], vph);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_pv(buf, vs, h > 0);
+          umma_commit(&v_empty[vs]);
+          umma_commit(&pv_done[buf]);
+        }
+        if (++vs == VS) { vs = 0; vph ^= 1u; }
       }
       if (elect_one()) umma_commit(o_full);
     }
@@ -334,6 +340,8 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
       float mx = -INFINITY;
       if (has_next) {
         tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&s_free[buf ^ 1]);  // S(h+1) is in registers: its TMEM buffer may take S(h+3)
         if (MODE == 1) mask_tail(nxt, h_begin + h + 1);
         mx = row_max(nxt);  // independent of the exponentials below
       }
@@ -376,6 +384,8 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
     tc_fence_after();
     load_scores(sa, 0);
     tmem_wait_ld();
+    tc_fence_before();
+    mbar_arrive(&s_free[0]);
     mask_tail(sa, h_begin);
     {
       const float mx = row_max(sa) * sc;
@@ -438,21 +448,21 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
     if (writer) {
       const int qrow = q_row0 + row;
       const bool valid = qrow < p.sq;
-      // merged running max / row sum over the parts (split == 1: this part's own)
+      // merged running max / row sum over the parts (split == 1: this part's own).  The parts are accumulated in part order
+      // whichever of them happens to be the last to arrive, so the result does not depend on the schedule.
       float m_all = m;
-      float scale_self = 1.0f;
       if (p.split > 1) {
         for (int s = 0; s < p.split; ++s) {
           if (s == part) continue;
           m_all = fmaxf(m_all, __ldcg(p.ws_ml + (static_cast<size_t>(tile * p.split + s) * 128 + row) * 2));
         }
-        scale_self = a64_ex2(m - m_all);
-        l *= scale_self;
+        float l_acc = 0.f;
         for (int s = 0; s < p.split; ++s) {
-          if (s == part) continue;
-          const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.ws_ml + (static_cast<size_t>(tile * p.split + s) * 128 + row) * 2));
-          l += ml.y * a64_ex2(ml.x - m_all);
+          float2 ml = make_float2(m, l);
+          if (s != part) ml = __ldcg(reinterpret_cast<const float2*>(p.ws_ml + (static_cast<size_t>(tile * p.split + s) * 128 + row) * 2));
+          l_acc = fmaf(ml.y, a64_ex2(ml.x - m_all), l_acc);
         }
+        l = l_acc;
       }
       const float inv_l = 1.0f / l;
       typename H::T* orow = static_cast<typename H::T*>(p.o) + static_cast<long long>(b) * p.o_batch_stride +
@@ -463,22 +473,30 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
         tmem_ld32(o_t + c * 32, v);
         tmem_wait_ld();
         if (p.split > 1) {
+          float acc[32];
 #pragma unroll
-          for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) * scale_self);
+          for (int k = 0; k < 32; ++k) acc[k] = 0.f;
           for (int s = 0; s < p.split; ++s) {
-            if (s == part) continue;
-            const size_t base = static_cast<size_t>(tile * p.split + s) * 128 + row;
-            const float* src = p.ws_o + base * 64 + c * 32;
-            const float a = a64_ex2(__ldcg(p.ws_ml + base * 2) - m_all);
+            if (s == part) {
+              const float a = a64_ex2(m - m_all);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 t = __ldcg(reinterpret_cast<const float4*>(src + g * 4));
-              v[g * 4 + 0] = __float_as_uint(fmaf(t.x, a, __uint_as_float(v[g * 4 + 0])));
-              v[g * 4 + 1] = __float_as_uint(fmaf(t.y, a, __uint_as_float(v[g * 4 + 1])));
-              v[g * 4 + 2] = __float_as_uint(fmaf(t.z, a, __uint_as_float(v[g * 4 + 2])));
-              v[g * 4 + 3] = __float_as_uint(fmaf(t.w, a, __uint_as_float(v[g * 4 + 3])));
+              for (int k = 0; k < 32; ++k) acc[k] = fmaf(__uint_as_float(v[k]), a, acc[k]);
+            } else {
+              const size_t base = static_cast<size_t>(tile * p.split + s) * 128 + row;
+              const float* src = p.ws_o + base * 64 + c * 32;
+              const float a = a64_ex2(__ldcg(p.ws_ml + base * 2) - m_all);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(src + g * 4));
+                acc[g * 4 + 0] = fmaf(t.x, a, acc[g * 4 + 0]);
+                acc[g * 4 + 1] = fmaf(t.y, a, acc[g * 4 + 1]);
+                acc[g * 4 + 2] = fmaf(t.z, a, acc[g * 4 + 2]);
+                acc[g * 4 + 3] = fmaf(t.w, a, acc[g * 4 + 3]);
+              }
             }
           }
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(acc[k]);
         }
         if (valid) {
 #pragma unroll
@@ -540,10 +558,14 @@ static int pick_split(long long tiles, int kv_halves, bool have_ws) {
 }
 
 static constexpr long long kWsPerItem = 128ll * 64 * 4 + 128 * 2 * 4;  // parked O + (m, l)
+// The arrival counters live in a zone of FIXED size at the start of the workspace: launches of different shapes share the
+// workspace, and a counter must never sit where another shape parks data (a counter that is not zero when a launch starts
+// leaves its tile without a writer).
+static constexpr long long kWsMaxTiles = 65536, kWsCounterBytes = kWsMaxTiles * 4;
 
 long long attention64_workspace_bytes(long long tiles) {
-  // counters (one per tile, 4 B) + 4 parts per tile
-  return ((tiles * 4 + 255) / 256) * 256 + tiles * 4 * kWsPerItem;
+  if (tiles > kWsMaxTiles) return 0;  // never split
+  return kWsCounterBytes + tiles * 4 * kWsPerItem;  // up to 4 parts per tile
 }
 
 // head_dim 64, one query tile per CTA; arguments already validated by b200_attention
@@ -574,7 +596,8 @@ int launch_attention64(const b200_attention_args* a, cudaStream_t st) {
   const float scale = a->scale > 0.f ? a->scale : 0.125f;
   prm.scale_log2 = scale * 1.4426950408889634f;
   const long long tiles = static_cast<long long>(a->batch) * a->heads * prm.q_tiles;
-  const bool have_ws = a->workspace != nullptr && a->workspace_bytes >= attention64_workspace_bytes(tiles) && aligned16(a->workspace);
+  const bool have_ws = a->workspace != nullptr && tiles <= kWsMaxTiles && a->workspace_bytes >= attention64_workspace_bytes(tiles) &&
+                       aligned16(a->workspace);
   int split = a->kv_split > 0 ? a->kv_split : pick_split(tiles, prm.kv_halves, have_ws);
   B200_CHECK_ARG(split == 1 || split == 2 || split == 4, "attention: kv_split %d (1, 2 or 4)", split);
   if (split > 1) {
@@ -586,10 +609,9 @@ int launch_attention64(const b200_attention_args* a, cudaStream_t st) {
   prm.halves_per_split = (prm.kv_halves + split - 1) / split;
   if (split > 1) {
     uint8_t* ws = static_cast<uint8_t*>(a->workspace);
-    const long long cbytes = ((tiles * 4 + 255) / 256) * 256;
     prm.counters = reinterpret_cast<unsigned int*>(ws);
-    prm.ws_o = reinterpret_cast<float*>(ws + cbytes);
-    prm.ws_ml = reinterpret_cast<float*>(ws + cbytes + tiles * split * 128ll * 64 * 4);
+    prm.ws_o = reinterpret_cast<float*>(ws + kWsCounterBytes);
+    prm.ws_ml = reinterpret_cast<float*>(ws + kWsCounterBytes + tiles * split * 128ll * 64 * 4);
   }
   const long long grid_ll = tiles * split;
   B200_CHECK_ARG(grid_ll < (1ll << 31), "attention: grid too large");

@@ -68,6 +68,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Same contract, for register-starved code: the fast path is one try_wait, the bounded spin lives out of line so its
+// counters never occupy registers of the caller's hot loop.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0x3ffu) == 0) {
+      uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(smem_u32(bar), parity);
+}
 // Whole-warp wait with a single poller: lane 0 waits, the warp reconverges behind it.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);

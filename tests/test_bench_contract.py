@@ -17,7 +17,7 @@ REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
 
 def _args(**kw):
     d = dict(workload="sdxl", gpus=1, steps=3, warmup=3, impl="reference", batch=1, denoise_steps=50, guidance_scale=7.5,
-             no_cpu_baseline=False, no_config3=False, no_reference_cuda=False)
+             no_cpu_baseline=False, no_config3=False, no_reference_cuda=False, cpu_sample=False)
     d.update(kw)
     return argparse.Namespace(**d)
 

@@ -107,15 +107,21 @@ def run_case(name):
                 kv = rnd(B, Sk, 2 * H * D)
                 k, v = kv[:, :, :H * D], kv[:, :, H * D:]
         out = ops.attention(q, k, v, heads=H, head_dim=D, nq=cfg.get("nq", 0), kv_split=cfg.get("kv_split", 0))
-        if cfg.get("kv_split", 0) > 1:  # the arrival counters reset themselves: a second launch on the same workspace must agree
-            out2 = ops.attention(q, k, v, heads=H, head_dim=D, kv_split=cfg["kv_split"])
-            assert torch.equal(out, out2) or cfg["kv_split"] > 1 and (out.float() - out2.float()).abs().max() < 1e-2
+        same = True
+        if cfg.get("kv_split", 0) > 1:
+            # the arrival counters reset themselves and the parts are merged in a fixed order: launches on the same workspace,
+            # interleaved with launches of OTHER shapes that park data in it, must agree bit for bit
+            other = rnd(1, 2048, 3 * 128)
+            for _ in range(3):
+                ops.attention(other[:, :, :128], other[:, :, 128:256], other[:, :, 256:], heads=2, head_dim=64, kv_split=2)
+                out2 = ops.attention(q, k, v, heads=H, head_dim=D, kv_split=cfg["kv_split"])
+                same = same and bool(torch.equal(out, out2))
         torch.cuda.synchronize()
         qf = q.float().reshape(B, Sq, H, D).transpose(1, 2)
         kf = k.float().reshape(B, Sk, H, D).transpose(1, 2)
         vf = v.float().reshape(B, Sk, H, D).transpose(1, 2)
         ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, Sq, H * D)
-        return report(name, out, ref, 2e-2, 6e-3 if dt == torch.bfloat16 else 1.5e-3)
+        return report(name, out, ref, 2e-2, 6e-3 if dt == torch.bfloat16 else 1.5e-3, extra=dict(deterministic=same)) and same
     if kind == "attn_sweep":
         # every count of 64-key halves from 1 to 6 with a ragged last half: each exit of the software-pipelined loop
         ok = True
@@ -278,7 +284,18 @@ def run_case(name):
         ops.qk_norm_rope(work, heads=H, head_dim=D, k_off=C, seq=rows, txt_rows=txt, wq=wq, wk=wk, wq_txt=wqt if txt else None,
                          wk_txt=wkt if txt else None, cos=cos, sin=sin)
         torch.cuda.synchronize()
-        ok = report(name + "_qk", work[:, :2 * C], ref[:, :2 * C], 1.2e-2, 1.2e-2)   # two 16-bit roundings of O(1) values
+        # the rotation x*cos + rot(x)*sin cancels: the error scales with the normalised operands (|xn| up to ~16 here, rounded to
+        # 16 bit twice in the kernel - after the norm and after the weight, like the reference's RMSNorm), not with the result
+        mag = torch.zeros_like(ref[:, :2 * C])
+        for off in (0, C):
+            blk = ref[:, off:off + C].reshape(rows, H, D).abs().amax(-1, keepdim=True)
+            mag[:, off:off + C] = (blk * 1.5).expand(rows, H, D).reshape(rows, C)
+        o_, r_ = work[:, :2 * C].float(), ref[:, :2 * C]
+        err = (o_ - r_).abs()
+        bad = err > (2.0 ** -7 if dt == torch.bfloat16 else 2.0 ** -10) * mag + 1e-3
+        print("RESULT " + json.dumps(dict(case=name + "_qk", max_abs=float(err.max()), ref_absmax=float(r_.abs().max()), n_bad=int(bad.sum()),
+                                           nan=int(torch.isnan(o_).sum()))))
+        ok = int(bad.sum()) == 0 and int(torch.isnan(o_).sum()) == 0
         ok &= report(name + "_v_untouched", work[:, 2 * C:], qkv[:, 2 * C:].float(), 0, 0)
         return ok
     if kind == "softmax":
