@@ -43,7 +43,6 @@ class AttentionArgs(C.Structure):
         ("v_row_stride", C.c_int64), ("v_batch_stride", C.c_int64),
         ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
         ("scale", C.c_float), ("dtype", C.c_int32), ("nq_override", C.c_int32),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("kv_split", C.c_int32),
     ]
 
 
@@ -108,8 +107,6 @@ def lib():
         _lib.b200_conv_gemm_packed_k.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         _lib.b200_conv_gemm_pick_tile_n.restype = C.c_int32
         _lib.b200_conv_gemm_pick_tile_n.argtypes = [C.c_int64, C.c_int32, C.c_int32]
-        _lib.b200_attention_workspace_bytes.restype = C.c_int64
-        _lib.b200_attention_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         _lib.b200_group_norm_workspace_bytes.restype = C.c_int64
         _lib.b200_group_norm_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         I32, I64, F32, VP = C.c_int32, C.c_int64, C.c_float, C.c_void_p

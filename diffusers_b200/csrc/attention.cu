@@ -395,7 +395,6 @@ int launch_attention64_pipe(const b200_attention_args* a, cudaStream_t st);
 int init_attention64();
 bool attention64_enabled();
 int launch_attention64(const b200_attention_args* a, cudaStream_t st);
-long long attention64_workspace_bytes(long long tiles);
 
 template <int HD, int NQ, bool FP16>
 static int attn_set_attr() {
@@ -493,12 +492,6 @@ int b200_attention(const b200_attention_args* a, void* stream) {
     if (nq == 2) { B200_ATTN(128, 2); } else { B200_ATTN(128, 1); }
   }
 #undef B200_ATTN
-}
-
-int64_t b200_attention_workspace_bytes(int32_t batch, int32_t heads, int32_t sq, int32_t sk, int32_t head_dim) {
-  (void)sk;
-  if (head_dim != 64 || batch <= 0 || heads <= 0 || sq <= 0) return 0;
-  return b200::attention64_workspace_bytes(static_cast<long long>(batch) * heads * ((sq + 127) / 128));
 }
 
 }  // extern "C"

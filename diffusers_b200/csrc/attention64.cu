@@ -17,13 +17,14 @@
 //    independent instruction streams in one basic block, so the scheduler interleaves them and no pipe waits for a TMEM round
 //    trip.  128 score registers + 16 packed P need the register reallocation above.
 //  * cheaper arithmetic: 3-input max (FMNMX3), packed fp32x2 FMA / ADD for the scale-and-shift, the row sum and the
-//    exponential polynomial, 4 independent partial sums instead of one serial chain; 3 of every 8 exponentials are evaluated
-//    as a degree-3 polynomial on the FMA pipe (MUFU does 16 ex2 / clk / SM: with all 64 of a row's exponentials on it the
-//    unit alone would take longer than both GEMMs of the tile).
-//  * KV SPLIT with an in-kernel combine: 2 x 148 CTA slots make 320 tiles (1024 tokens, 20 heads, CFG batch 2) two waves of
-//    which the second is 8 % full.  Each tile's keys can be split over 2 or 4 CTAs; a CTA that is not the last of its tile
-//    to finish parks its unnormalised O (fp32), running max and row sum in a workspace, the last one (atomic ticket) merges
-//    them into its own accumulator and writes the output.  Finer work items fill the last wave; nothing is re-launched.
+//    exponential polynomial, 4 independent partial sums instead of one serial chain; kPolyPairs of every 8 score pairs
+//    are evaluated as a degree-3 polynomial on the FMA pipe instead of MUFU (16 ex2 / clk / SM).  The polynomial costs ~6
+//    issue slots per element against 1 for MUFU: it only pays once the kernel is MUFU-bound (see kPolyPairs).
+//  * S(h+2) is issued as soon as every softmax thread holds S(h) in registers (s_free), i.e. AHEAD of P(h) V(h): with the
+//    scores read one step early, waiting for P(h) first left the softmax without scores at the start of every step
+//    (measured: 248 us -> 153 us at 4096 tokens).
+//  (A split of one tile's keys over 2 / 4 CTAs with a merge through a global workspace was built and measured: correct, but
+//  parking 33 KB per CTA and the fence + ticket cost ~5 us per CTA, more than the fuller last wave returned - removed.)
 // Numerics are those of attention.cu: online softmax in the exp2 domain, lazy rescale (the running max only moves on > 2^8
 // growth), P rounded to 16 bit for the P V GEMM, fp32 row sums of the unrounded P.
 #include <math.h>
@@ -46,12 +47,7 @@ struct Attn64Params {
   int batch, heads, sq, sk;
   int q_tiles;           // ceil(sq / 128)
   int kv_halves;         // ceil(sk / 64)
-  int split;             // CTAs per tile (1, 2 or 4)
-  int halves_per_split;  // ceil(kv_halves / split)
   float scale_log2;
-  float* ws_o;           // [tiles * split][128][64] fp32: unnormalised O of a CTA that was not the last of its tile
-  float* ws_ml;          // [tiles * split][128][2]: its running max (exp2 domain) and row sum
-  unsigned int* counters;  // [tiles] arrival tickets, self-resetting
 };
 
 struct Attn64Cfg {
@@ -93,7 +89,8 @@ __device__ __forceinline__ float2 a64_ex2_poly2(float2 x) {
   return r;
 }
 
-template <bool FP16>
+// POLY: score pairs (of every 8) whose exponentials go to the FMA-pipe polynomial instead of MUFU (0..3)
+template <bool FP16, int POLY>
 __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(const __grid_constant__ Attn64Params p) {
   using Cfg = Attn64Cfg;
   using H = Half16<FP16>;
@@ -116,22 +113,19 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
   uint64_t* s_free = pv_done + 2;        // [2]  every softmax thread holds S(h) in registers: the buffer can take S(h+2): 128 arrivals
   uint64_t* o_full = s_free + 2;         // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
-  uint32_t* ticket = tmem_ptr + 1;       // combine: this CTA's arrival order within its tile
   static_assert((1 + 2 * KS + 2 * VS + 2 + 2 + 2 + 2 + 1) * 8 + 8 <= 256, "barrier area");
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x;                 // tile * split + part: the parts of a tile are launched back to back
-  const int part = item % p.split;
-  const int tile = item / p.split;
+  const int tile = blockIdx.x;
   const int qt = tile % p.q_tiles;
   const int bh = tile / p.q_tiles;
   const int head = bh % p.heads;
   const int b = bh / p.heads;
   const int q_row0 = qt * 128;
-  const int h_begin = part * p.halves_per_split;
-  const int h_end = min(p.kv_halves, h_begin + p.halves_per_split);
-  const int n_half = h_end - h_begin;          // >= 1 by construction of split
+  constexpr int h_begin = 0;
+  const int h_end = p.kv_halves;
+  const int n_half = h_end;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.q_map);
@@ -302,7 +296,7 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
           x[j] = __ffma2_rn(make_float2(__uint_as_float(s[OFF + k + 2 * j]), __uint_as_float(s[OFF + k + 2 * j + 1])), sc2, nm2);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (j == 2 || j == 5 || j == 7)
+          if ((POLY >= 1 && j == 5) || (POLY >= 2 && j == 2) || (POLY >= 3 && j == 7))
             e[j] = a64_ex2_poly2(x[j]);
           else
             e[j] = make_float2(a64_ex2(x[j].x), a64_ex2(x[j].y));
@@ -415,55 +409,12 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
     step(sb, sa, h, ModeFinal{});
     float l = (l0 + l1) + (l2 + l3);
 
-    // ---- epilogue: (combine the parts of the tile,) O / l -> global
+    // ---- epilogue: O / l -> global
     mbar_wait_warp(o_full, 0);
     tc_fence_after();
-    bool writer = true;       // this CTA writes the tile's output
-    unsigned int my_ticket = 0;
-    if (p.split > 1) {
-      // park this part's (O, m, l); the last part of the tile to arrive merges the others into its accumulator
-      float* wo = p.ws_o + (static_cast<size_t>(item) * 128 + row) * 64;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(o_t + c * 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<uint4*>(wo + c * 32 + g * 4) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-      }
-      *reinterpret_cast<float2*>(p.ws_ml + (static_cast<size_t>(item) * 128 + row) * 2) = make_float2(m, l);
-      __threadfence();
-      named_bar_sync(1, 128);
-      if (threadIdx.x == 128) {
-        const unsigned int t = atomicAdd(p.counters + tile, 1u);
-        if (t == static_cast<unsigned int>(p.split - 1)) p.counters[tile] = 0;  // every part has arrived: ready for the next launch
-        *ticket = t;
-      }
-      named_bar_sync(1, 128);
-      my_ticket = *ticket;
-      writer = my_ticket == static_cast<unsigned int>(p.split - 1);
-      if (writer) __threadfence();
-    }
-    if (writer) {
+    {
       const int qrow = q_row0 + row;
       const bool valid = qrow < p.sq;
-      // merged running max / row sum over the parts (split == 1: this part's own).  The parts are accumulated in part order
-      // whichever of them happens to be the last to arrive, so the result does not depend on the schedule.
-      float m_all = m;
-      if (p.split > 1) {
-        for (int s = 0; s < p.split; ++s) {
-          if (s == part) continue;
-          m_all = fmaxf(m_all, __ldcg(p.ws_ml + (static_cast<size_t>(tile * p.split + s) * 128 + row) * 2));
-        }
-        float l_acc = 0.f;
-        for (int s = 0; s < p.split; ++s) {
-          float2 ml = make_float2(m, l);
-          if (s != part) ml = __ldcg(reinterpret_cast<const float2*>(p.ws_ml + (static_cast<size_t>(tile * p.split + s) * 128 + row) * 2));
-          l_acc = fmaf(ml.y, a64_ex2(ml.x - m_all), l_acc);
-        }
-        l = l_acc;
-      }
       const float inv_l = 1.0f / l;
       typename H::T* orow = static_cast<typename H::T*>(p.o) + static_cast<long long>(b) * p.o_batch_stride +
                             static_cast<long long>(qrow) * p.o_row_stride + head * 64;
@@ -472,32 +423,6 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
         uint32_t v[32];
         tmem_ld32(o_t + c * 32, v);
         tmem_wait_ld();
-        if (p.split > 1) {
-          float acc[32];
-#pragma unroll
-          for (int k = 0; k < 32; ++k) acc[k] = 0.f;
-          for (int s = 0; s < p.split; ++s) {
-            if (s == part) {
-              const float a = a64_ex2(m - m_all);
-#pragma unroll
-              for (int k = 0; k < 32; ++k) acc[k] = fmaf(__uint_as_float(v[k]), a, acc[k]);
-            } else {
-              const size_t base = static_cast<size_t>(tile * p.split + s) * 128 + row;
-              const float* src = p.ws_o + base * 64 + c * 32;
-              const float a = a64_ex2(__ldcg(p.ws_ml + base * 2) - m_all);
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 t = __ldcg(reinterpret_cast<const float4*>(src + g * 4));
-                acc[g * 4 + 0] = fmaf(t.x, a, acc[g * 4 + 0]);
-                acc[g * 4 + 1] = fmaf(t.y, a, acc[g * 4 + 1]);
-                acc[g * 4 + 2] = fmaf(t.z, a, acc[g * 4 + 2]);
-                acc[g * 4 + 3] = fmaf(t.w, a, acc[g * 4 + 3]);
-              }
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(acc[k]);
-        }
         if (valid) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -521,10 +446,18 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
   }
 }
 
+template <bool FP16, int POLY>
+static cudaError_t a64_attr() {
+  return cudaFuncSetAttribute(attention64_kernel<FP16, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Cfg::SMEM_BYTES);
+}
+
 int init_attention64() {
-  cudaError_t e = cudaFuncSetAttribute(attention64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Cfg::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attention64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Cfg::SMEM_BYTES);
+  cudaError_t e = a64_attr<false, 0>();
+  if (e == cudaSuccess) e = a64_attr<true, 0>();
+  if (e == cudaSuccess) e = a64_attr<false, 1>();
+  if (e == cudaSuccess) e = a64_attr<true, 1>();
+  if (e == cudaSuccess) e = a64_attr<false, 3>();
+  if (e == cudaSuccess) e = a64_attr<true, 3>();
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention (head_dim 64) smem attr: %s", cudaGetErrorString(e));
   return 0;
 }
@@ -532,40 +465,6 @@ int init_attention64() {
 bool attention64_enabled() {
   static const bool on = !(getenv("B200_ATTN_V2") && atoi(getenv("B200_ATTN_V2")) == 0);
   return on;
-}
-
-// Work items = tiles x split on 2 x SMs CTA slots: pick the split whose last wave is fullest.  Cost in units of one
-// 64-key half of one CTA: fixed (prologue + epilogue) ~ 3, combine ~ 2 (tools/bench_attention.py sweeps B200_ATTN_KV_SPLIT).
-static int pick_split(long long tiles, int kv_halves, bool have_ws) {
-  static const int forced = getenv("B200_ATTN_KV_SPLIT") ? atoi(getenv("B200_ATTN_KV_SPLIT")) : 0;
-  if (!have_ws) return 1;
-  const long long slots = 2ll * num_sms();
-  double best = 1e30;
-  int best_s = 1;
-  for (int s : {1, 2, 4}) {
-    if (forced && s != forced) continue;
-    if (s > 1 && kv_halves < 4 * s) continue;  // keep >= 4 halves per part
-    const int per = (kv_halves + s - 1) / s;
-    if (static_cast<long long>(per) * (s - 1) >= kv_halves) continue;  // an empty part
-    const long long waves = (tiles * s + slots - 1) / slots;
-    const double cost = static_cast<double>(waves) * (per + 3.0) + (s > 1 ? 2.0 : 0.0);
-    if (cost < best * 0.97) {  // a split must win by 3 %
-      best = cost;
-      best_s = s;
-    }
-  }
-  return best_s;
-}
-
-static constexpr long long kWsPerItem = 128ll * 64 * 4 + 128 * 2 * 4;  // parked O + (m, l)
-// The arrival counters live in a zone of FIXED size at the start of the workspace: launches of different shapes share the
-// workspace, and a counter must never sit where another shape parks data (a counter that is not zero when a launch starts
-// leaves its tile without a writer).
-static constexpr long long kWsMaxTiles = 65536, kWsCounterBytes = kWsMaxTiles * 4;
-
-long long attention64_workspace_bytes(long long tiles) {
-  if (tiles > kWsMaxTiles) return 0;  // never split
-  return kWsCounterBytes + tiles * 4 * kWsPerItem;  // up to 4 parts per tile
 }
 
 // head_dim 64, one query tile per CTA; arguments already validated by b200_attention
@@ -595,31 +494,18 @@ int launch_attention64(const b200_attention_args* a, cudaStream_t st) {
   prm.kv_halves = (a->sk + 63) / 64;
   const float scale = a->scale > 0.f ? a->scale : 0.125f;
   prm.scale_log2 = scale * 1.4426950408889634f;
-  const long long tiles = static_cast<long long>(a->batch) * a->heads * prm.q_tiles;
-  const bool have_ws = a->workspace != nullptr && tiles <= kWsMaxTiles && a->workspace_bytes >= attention64_workspace_bytes(tiles) &&
-                       aligned16(a->workspace);
-  int split = a->kv_split > 0 ? a->kv_split : pick_split(tiles, prm.kv_halves, have_ws);
-  B200_CHECK_ARG(split == 1 || split == 2 || split == 4, "attention: kv_split %d (1, 2 or 4)", split);
-  if (split > 1) {
-    B200_CHECK_ARG(have_ws, "attention: kv_split %d needs a workspace of b200_attention_workspace_bytes()", split);
-    const int per = (prm.kv_halves + split - 1) / split;
-    B200_CHECK_ARG(static_cast<long long>(per) * (split - 1) < prm.kv_halves, "attention: kv_split %d leaves a part without keys (sk=%d)", split, a->sk);
-  }
-  prm.split = split;
-  prm.halves_per_split = (prm.kv_halves + split - 1) / split;
-  if (split > 1) {
-    uint8_t* ws = static_cast<uint8_t*>(a->workspace);
-    prm.counters = reinterpret_cast<unsigned int*>(ws);
-    prm.ws_o = reinterpret_cast<float*>(ws + kWsCounterBytes);
-    prm.ws_ml = reinterpret_cast<float*>(ws + kWsCounterBytes + tiles * split * 128ll * 64 * 4);
-  }
-  const long long grid_ll = tiles * split;
+  const long long grid_ll = static_cast<long long>(a->batch) * a->heads * prm.q_tiles;
   B200_CHECK_ARG(grid_ll < (1ll << 31), "attention: grid too large");
   const bool fp16 = a->dtype == B200_DTYPE_FP16;
-  cudaError_t e = fp16 ? launch_pdl(attention64_kernel<true>, dim3(static_cast<unsigned>(grid_ll)), dim3(Attn64Cfg::THREADS),
-                                    Attn64Cfg::SMEM_BYTES, st, prm)
-                       : launch_pdl(attention64_kernel<false>, dim3(static_cast<unsigned>(grid_ll)), dim3(Attn64Cfg::THREADS),
-                                    Attn64Cfg::SMEM_BYTES, st, prm);
+  static const int poly = getenv("B200_ATTN_POLY") ? atoi(getenv("B200_ATTN_POLY")) : 0;  // tuning knob: 0, 1 or 3
+  const dim3 grid(static_cast<unsigned>(grid_ll)), block(Attn64Cfg::THREADS);
+  cudaError_t e;
+#define B200_A64(P) (fp16 ? launch_pdl(attention64_kernel<true, P>, grid, block, Attn64Cfg::SMEM_BYTES, st, prm) \
+                          : launch_pdl(attention64_kernel<false, P>, grid, block, Attn64Cfg::SMEM_BYTES, st, prm))
+  if (poly >= 3) e = B200_A64(3);
+  else if (poly >= 1) e = B200_A64(1);
+  else e = B200_A64(0);
+#undef B200_A64
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention (head_dim 64) launch: %s", cudaGetErrorString(e));
   return 0;
 }

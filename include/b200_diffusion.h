@@ -259,17 +259,9 @@ typedef struct {
   float scale;
   int32_t dtype;
   int32_t nq_override; /* 0 = auto; 1 | 2 = query tiles (of 128 rows) per CTA */
-  /* head_dim 64 only: the keys of one query tile may be split over 2 or 4 CTAs whose partial results are merged in the
-   * kernel by the last CTA of the tile to finish (fills the last wave of 2 x SMs CTA slots).  Needs a caller-owned
-   * workspace of b200_attention_workspace_bytes() whose first use finds it ZEROED (arrival counters; they reset
-   * themselves) and that no other stream uses concurrently.  workspace == NULL: never split. */
-  void* workspace;
-  int64_t workspace_bytes;
-  int32_t kv_split;    /* 0 = auto; 1, 2, 4 = forced */
 } b200_attention_args;
 
 int b200_attention(const b200_attention_args* args, void* stream);
-int64_t b200_attention_workspace_bytes(int32_t batch, int32_t heads, int32_t sq, int32_t sk, int32_t head_dim);
 
 /* Unfused attention helpers for head_dim 512 (AutoencoderKL mid-block attention, one head:
  * models/attention_processor.py:2725-2789 via unets/unet_2d_blocks.py:684-698).  TMEM cannot hold a

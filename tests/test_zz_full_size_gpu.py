@@ -36,7 +36,7 @@ def test_sdxl_unet_full_size_properties():
     assert torch.isfinite(yf).all()
     amax = float(yf.abs().max())
     assert 1e-3 < amax < 1e3, amax
-    assert 900 <= launches <= 1000, launches  # ~950 hand-written kernels per forward, nothing silently skipped
+    assert 700 <= launches <= 780, launches  # 737 hand-written kernels per forward (the 210 LayerNorms are folded into GEMMs), nothing silently skipped
     # deterministic: the same launch sequence gives the same bits
     assert torch.equal(y, fwd(x, ehs, te))
     # the two samples of the CFG batch do not interact: swapping them swaps the outputs

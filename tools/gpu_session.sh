@@ -14,6 +14,8 @@ for step in "$@"; do
     ncu)     timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off -f -o gpurun_out/r2_targets python tools/ncu_targets.py > gpurun_out/ncu_targets.log 2>&1; echo "ncu rc=$?" ;;
     libbar)  timeout 600 python tools/library_bar.py --json gpurun_out/library_bar.json > gpurun_out/library_bar.txt 2>&1; echo "libbar rc=$?" ;;
     attn)    timeout 300 python tools/bench_attention.py > gpurun_out/bench_attention.txt 2>&1; echo "attn rc=$?" ;;
+    attnpoly) for p in 0 1 3; do echo "== B200_ATTN_POLY=$p"; B200_ATTN_POLY=$p timeout 200 python tools/bench_attention.py d64; done > gpurun_out/bench_attention_poly.txt 2>&1; echo "attnpoly rc=$?" ;;
+    benchsdxl) timeout 600 python bench.py --workload sdxl --no-cpu-baseline --no-reference-cuda > gpurun_out/bench_sdxl.json 2> gpurun_out/bench_sdxl.err; echo "bench sdxl rc=$?" ;;
     attncheck) timeout 400 python tools/diag_ops.py --inproc $(python -c "import sys; sys.path.insert(0,'.'); from tools import diag_ops; print(' '.join(c for c in diag_ops.CASES if c.startswith('attn_')))") > gpurun_out/attn_check.txt 2>&1; echo "attncheck rc=$?"; tail -3 gpurun_out/attn_check.txt ;;
     ncuattn) timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:attention -f -o gpurun_out/r2_attn python tools/ncu_targets.py > gpurun_out/ncu_attn.log 2>&1; echo "ncuattn rc=$?" ;;
     gemm)    timeout 600 python tools/bench_gemm.py > gpurun_out/bench_gemm.txt 2>&1; echo "gemm rc=$?" ;;
