@@ -30,7 +30,6 @@ class ConvGemmArgs(C.Structure):
         ("dtype", C.c_int32), ("tile_n", C.c_int32), ("out_fp32", C.c_int32), ("cluster_m", C.c_int32),
         ("debug_timestamps", C.c_void_p), ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
         ("row_stats_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_parts", C.c_int32), ("ln_eps", C.c_float),
-        ("ln_colsum", C.c_void_p), ("ln_bias", C.c_void_p),
     ]
 
 
@@ -107,6 +106,8 @@ def lib():
         _lib.b200_conv_gemm_packed_k.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         _lib.b200_conv_gemm_pick_tile_n.restype = C.c_int32
         _lib.b200_conv_gemm_pick_tile_n.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+        _lib.b200_conv_gemm_row_stats_parts.restype = C.c_int32
+        _lib.b200_conv_gemm_row_stats_parts.argtypes = [C.c_void_p]
         _lib.b200_group_norm_workspace_bytes.restype = C.c_int64
         _lib.b200_group_norm_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         I32, I64, F32, VP = C.c_int32, C.c_int64, C.c_float, C.c_void_p

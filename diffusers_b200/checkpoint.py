@@ -120,7 +120,9 @@ class FromPretrainedMixin:
         return sd
 
     @classmethod
-    def from_pretrained(cls, path, subfolder=None, variant=None, torch_dtype=torch.bfloat16, device="cuda", **unsupported):
+    def from_pretrained(cls, path, subfolder=None, variant=None, torch_dtype=torch.bfloat16, device="cuda", fold_norms=None, **unsupported):
+        """fold_norms (UNet2DConditionModel only): None = the class default (LayerNorms folded into the GEMMs, weights re-rounded
+        once), False = keep bit-exact copies of the checkpoint's weights."""
         for k, v in unsupported.items():
             if v not in (None, False):
                 raise NotImplementedError(f"from_pretrained option {k}={v!r} is outside the hot path (local directories only)")
@@ -135,7 +137,8 @@ class FromPretrainedMixin:
         missing = [k for k in spec if k not in sd]
         if missing:
             raise ValueError(f"{root}: checkpoint lacks {len(missing)} tensors the model needs, e.g. {missing[:3]}")
-        return cls(cfg, {k: sd[k] for k in spec}, dtype=torch_dtype, device=device)
+        extra = {} if fold_norms is None else dict(fold_norms=fold_norms)
+        return cls(cfg, {k: sd[k] for k in spec}, dtype=torch_dtype, device=device, **extra)
 
     @classmethod
     def _param_spec_for(cls, cfg):

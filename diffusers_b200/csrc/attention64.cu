@@ -456,8 +456,6 @@ int init_attention64() {
   if (e == cudaSuccess) e = a64_attr<true, 0>();
   if (e == cudaSuccess) e = a64_attr<false, 1>();
   if (e == cudaSuccess) e = a64_attr<true, 1>();
-  if (e == cudaSuccess) e = a64_attr<false, 3>();
-  if (e == cudaSuccess) e = a64_attr<true, 3>();
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention (head_dim 64) smem attr: %s", cudaGetErrorString(e));
   return 0;
 }
@@ -497,13 +495,13 @@ int launch_attention64(const b200_attention_args* a, cudaStream_t st) {
   const long long grid_ll = static_cast<long long>(a->batch) * a->heads * prm.q_tiles;
   B200_CHECK_ARG(grid_ll < (1ll << 31), "attention: grid too large");
   const bool fp16 = a->dtype == B200_DTYPE_FP16;
-  static const int poly = getenv("B200_ATTN_POLY") ? atoi(getenv("B200_ATTN_POLY")) : 0;  // tuning knob: 0, 1 or 3
+  // measured on B200 (tools/bench_attention.py, 4096 / 1024 tokens): POLY 0 -> 154.8 / 30.0 us, 1 -> 146.5 / 28.7 us, 3 -> 154.7 / 30.1 us
+  static const int poly = getenv("B200_ATTN_POLY") ? atoi(getenv("B200_ATTN_POLY")) : 1;  // tuning knob: 0 or 1
   const dim3 grid(static_cast<unsigned>(grid_ll)), block(Attn64Cfg::THREADS);
   cudaError_t e;
 #define B200_A64(P) (fp16 ? launch_pdl(attention64_kernel<true, P>, grid, block, Attn64Cfg::SMEM_BYTES, st, prm) \
                           : launch_pdl(attention64_kernel<false, P>, grid, block, Attn64Cfg::SMEM_BYTES, st, prm))
-  if (poly >= 3) e = B200_A64(3);
-  else if (poly >= 1) e = B200_A64(1);
+  if (poly >= 1) e = B200_A64(1);
   else e = B200_A64(0);
 #undef B200_A64
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention (head_dim 64) launch: %s", cudaGetErrorString(e));

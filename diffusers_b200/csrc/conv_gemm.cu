@@ -78,13 +78,11 @@ struct ConvGemmParams {
   int dbg_mode;  // tuning: 1 = producer stops loading after the first pipeline round, 2 = MMA thread issues no MMAs
   long long* dbg; // optional [grid][16] clock64 timestamps (tuning aid)
   // LayerNorm folded into the consuming GEMM (see b200_conv_gemm_args)
-  float2* stats_out;       // producer: [M][stats_parts] (sum, sumsq) of each 32-column chunk of the rounded outputs
-  int stats_parts;
+  float2* stats_out;       // producer: [M][stats_parts] (sum, sumsq) of the rounded outputs, one pair per (n tile, epilogue half)
+  int stats_parts;         // 2 * n_tiles
   const float2* ln_stats;  // consumer: [M][ln_parts]
   int ln_parts;
   float ln_eps, ln_inv_k;
-  const float* ln_colsum;  // [N] fp32
-  const float* ln_bias;    // [N] fp32
 };
 
 template <int BN, bool PAIR>
@@ -392,8 +390,6 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     const int act = p.act;
     const bool lean = !GEGLU && tma_store && act == ACT_NONE && gate == nullptr && rowvec == nullptr;
     const float2* ln_stats = p.ln_stats;
-    const float* ln_colsum = p.ln_colsum;
-    const float* ln_bias = p.ln_bias;
     float2* stats_out = p.stats_out;
     uint32_t k = 0;           // running chunk count over all tiles of this CTA (slab k % NSLAB, half k & 1)
     uint32_t prev_k = 0;      // issuer: chunk of this half's store still in flight
@@ -415,23 +411,28 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
       const int ycol0 = GEGLU ? (tc.n0 >> 1) : tc.n0;
 
-      // folded LayerNorm: this row's rstd and -mean * rstd from the producer's per-chunk partial sums (fixed summation order);
-      // runs under the main loop, before the accumulator is ready
-      float ln_r = 1.0f, ln_nmr = 0.0f;
+      // folded LayerNorm: this row's rstd from the producer's partial sums (fixed summation order).  All loads of a batch are
+      // issued before the first use (one L2 round trip per 16 parts); runs before the accumulator is needed.
+      float ln_r = 1.0f;
       if (ln_stats != nullptr && valid) {
-        const float2* sp = ln_stats + pix * p.ln_parts;
+        const float4* sp = reinterpret_cast<const float4*>(ln_stats + pix * p.ln_parts);  // ln_parts is even: 16-byte rows
+        const int n4 = p.ln_parts >> 1;
         float s0 = 0.f, s1 = 0.f;
-#pragma unroll 4
-        for (int i = 0; i < p.ln_parts; ++i) {
-          const float2 t = sp[i];
-          s0 += t.x;
-          s1 += t.y;
+        for (int i0 = 0; i0 < n4; i0 += 8) {
+          float4 t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = (i0 + i < n4) ? sp[i0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            s0 += t[i].x + t[i].z;
+            s1 += t[i].y + t[i].w;
+          }
         }
         const float mean = s0 * p.ln_inv_k;
         const float var = fmaxf(fmaf(-mean, mean, s1 * p.ln_inv_k), 0.0f);
         ln_r = rsqrtf(var + p.ln_eps);
-        ln_nmr = -mean * ln_r;
       }
+      float st_s = 0.f, st_q = 0.f;  // producer side of a folded LayerNorm: sums of this thread's ROUNDED outputs of the tile
 
       mbar_wait_warp(&tfull_bar[acc], (it >> 1) & 1u);
       tc_fence_after();
@@ -469,24 +470,16 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         const bool stamp = dbg && issuer && it == 0 && c < 2;
         if (stamp) dbg[8 + c * 4] = clock64();
         if (lean) {
-          float st_s = 0.f, st_q = 0.f;  // producer side of a folded LayerNorm: sums of this chunk's ROUNDED outputs
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             uint4* sp = reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4));
             float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
-            if (ln_stats != nullptr) {  // consumer side: rstd * acc - rstd * mean * colsum + (bias + W beta)
-              const float4 c0 = *reinterpret_cast<const float4*>(ln_colsum + yc0 + j8 * 8), c1 = *reinterpret_cast<const float4*>(ln_colsum + yc0 + j8 * 8 + 4);
-              const float4 b0 = *reinterpret_cast<const float4*>(ln_bias + yc0 + j8 * 8), b1 = *reinterpret_cast<const float4*>(ln_bias + yc0 + j8 * 8 + 4);
-              f[0] = fmaf(f[0], ln_r, fmaf(ln_nmr, c0.x, b0.x)); f[1] = fmaf(f[1], ln_r, fmaf(ln_nmr, c0.y, b0.y));
-              f[2] = fmaf(f[2], ln_r, fmaf(ln_nmr, c0.z, b0.z)); f[3] = fmaf(f[3], ln_r, fmaf(ln_nmr, c0.w, b0.w));
-              f[4] = fmaf(f[4], ln_r, fmaf(ln_nmr, c1.x, b1.x)); f[5] = fmaf(f[5], ln_r, fmaf(ln_nmr, c1.y, b1.y));
-              f[6] = fmaf(f[6], ln_r, fmaf(ln_nmr, c1.z, b1.z)); f[7] = fmaf(f[7], ln_r, fmaf(ln_nmr, c1.w, b1.w));
-            } else {
+            {  // acc * rstd + bias (rstd = 1 without a folded LayerNorm)
               float2 t0 = H::unpack(bc[j8].x), t1 = H::unpack(bc[j8].y), t2 = H::unpack(bc[j8].z), t3 = H::unpack(bc[j8].w);
-              f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
-              f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
+              f[0] = fmaf(__uint_as_float(v[j8 * 8 + 0]), ln_r, t0.x); f[1] = fmaf(__uint_as_float(v[j8 * 8 + 1]), ln_r, t0.y);
+              f[2] = fmaf(__uint_as_float(v[j8 * 8 + 2]), ln_r, t1.x); f[3] = fmaf(__uint_as_float(v[j8 * 8 + 3]), ln_r, t1.y);
+              f[4] = fmaf(__uint_as_float(v[j8 * 8 + 4]), ln_r, t2.x); f[5] = fmaf(__uint_as_float(v[j8 * 8 + 5]), ln_r, t2.y);
+              f[6] = fmaf(__uint_as_float(v[j8 * 8 + 6]), ln_r, t3.x); f[7] = fmaf(__uint_as_float(v[j8 * 8 + 7]), ln_r, t3.y);
             }
             if (tma_res) {  // the residual sits where this thread is about to write its output
               const uint4 r4 = *sp;
@@ -507,37 +500,26 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               st_q = fmaf(r2.x, r2.x, fmaf(r2.y, r2.y, fmaf(r3.x, r3.x, fmaf(r3.y, r3.y, st_q))));
             }
           }
-          if (stats_out != nullptr && valid) stats_out[pix * p.stats_parts + (yc0 >> 5)] = make_float2(st_s, st_q);
         } else if (chunk_vec) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             const int yc = yc0 + j8 * 8;
             uint4* sp = reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4));
             float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j8 * 8 + j]);
-            {
+            {  // acc * rstd + bias (rstd = 1 without a folded LayerNorm)
               float2 t0 = H::unpack(bc[j8].x), t1 = H::unpack(bc[j8].y), t2 = H::unpack(bc[j8].z), t3 = H::unpack(bc[j8].w);
-              f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
-              f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
+              f[0] = fmaf(__uint_as_float(v[j8 * 8 + 0]), ln_r, t0.x); f[1] = fmaf(__uint_as_float(v[j8 * 8 + 1]), ln_r, t0.y);
+              f[2] = fmaf(__uint_as_float(v[j8 * 8 + 2]), ln_r, t1.x); f[3] = fmaf(__uint_as_float(v[j8 * 8 + 3]), ln_r, t1.y);
+              f[4] = fmaf(__uint_as_float(v[j8 * 8 + 4]), ln_r, t2.x); f[5] = fmaf(__uint_as_float(v[j8 * 8 + 5]), ln_r, t2.y);
+              f[6] = fmaf(__uint_as_float(v[j8 * 8 + 6]), ln_r, t3.x); f[7] = fmaf(__uint_as_float(v[j8 * 8 + 7]), ln_r, t3.y);
             }
             if (GEGLU) {
               // packed rows: [n0, n0+BN/2) value, [n0+BN/2, n0+BN) gate
               uint4 bg = bias ? *reinterpret_cast<const uint4*>(bias + bcol + BN / 2 + j8 * 8) : make_uint4(0, 0, 0, 0);
               float2 t0 = H::unpack(bg.x), t1 = H::unpack(bg.y), t2 = H::unpack(bg.z), t3 = H::unpack(bg.w);
-              float gb[8] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y};
-              float gsc = 1.0f;
-              if (ln_stats != nullptr) {  // folded LayerNorm on both packed halves (value columns, gate columns); bias is NULL
-                const int vcol = bcol + j8 * 8, gcol = bcol + BN / 2 + j8 * 8;
+              const float gb[8] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  f[j] = fmaf(f[j], ln_r, fmaf(ln_nmr, ln_colsum[vcol + j], ln_bias[vcol + j]));
-                  gb[j] = fmaf(ln_nmr, ln_colsum[gcol + j], ln_bias[gcol + j]);
-                }
-                gsc = ln_r;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] *= gelu_erf_fast(fmaf(__uint_as_float(gv[j8 * 8 + j]), gsc, gb[j]));
+              for (int j = 0; j < 8; ++j) f[j] *= gelu_erf_fast(fmaf(__uint_as_float(gv[j8 * 8 + j]), ln_r, gb[j]));
             } else {
               if (act != ACT_NONE) {
 #pragma unroll
@@ -605,6 +587,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
         }
       }
+      if (stats_out != nullptr && valid) stats_out[pix * p.stats_parts + ((tc.n0 / BN) << 1) + half] = make_float2(st_s, st_q);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -798,6 +781,24 @@ int64_t b200_conv_gemm_packed_k(int32_t ksize, int32_t c0, int32_t c1) {
 
 int32_t b200_conv_gemm_pick_tile_n(int64_t M, int32_t N, int32_t geglu) { return b200::pick_tile_n(M, N, geglu); }
 
+/* Partial (sum, sum of squares) pairs per output row that a launch with these arguments writes to row_stats_out:
+ * 2 per N tile of the configuration the launch will pick. */
+int32_t b200_conv_gemm_row_stats_parts(const b200_conv_gemm_args* a) {
+  using namespace b200;
+  if (!a || a->N <= 0 || a->batch <= 0 || a->H <= 0 || a->W <= 0 || (a->ksize != 1 && a->ksize != 3)) return 0;
+  const int Ho = (a->stride == 2) ? a->H / 2 : a->H, Wo = (a->stride == 2) ? a->W / 2 : a->W;
+  long long best_tiles = -1;
+  for (int bw = 128; bw >= 1; bw >>= 1) {
+    const long long tiles = static_cast<long long>(cdiv(Wo, bw)) * cdiv(Ho, 128 / bw);
+    if (best_tiles < 0 || tiles < best_tiles) best_tiles = tiles;
+  }
+  const int nsrc = (a->x[1] != nullptr && a->c[1] > 0) ? 2 : 1;
+  const int k_chunks = a->ksize * a->ksize * (cdiv(a->c[0], 64) + (nsrc == 2 ? cdiv(a->c[1], 64) : 0));
+  int bn = 0, cm = 1;
+  pick_config(best_tiles * a->batch, a->N, k_chunks, a->geglu, a->geglu && !a->tile_n ? pick_tile_n(0, a->N, 1) : a->tile_n, a->cluster_m, &bn, &cm);
+  return bn ? 2 * cdiv(a->N, bn) : 0;
+}
+
 int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   using namespace b200;
   B200_CHECK_ARG(a != nullptr, "conv_gemm: null args");
@@ -965,24 +966,21 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   if (a->row_stats_out) {
     B200_CHECK_ARG(prm.tma_store && !a->geglu && a->act == B200_ACT_NONE && !a->gate && !a->rowvec && !a->out_fp32,
                    "conv_gemm: row_stats_out needs the plain TMA-store epilogue (aligned y, N %% 32 == 0, no act / gate / rowvec / geglu)");
-    B200_CHECK_ARG((reinterpret_cast<uintptr_t>(a->row_stats_out) & 7u) == 0, "conv_gemm: row_stats_out not 8-byte aligned");
+    B200_CHECK_ARG(aligned16(a->row_stats_out), "conv_gemm: row_stats_out not 16-byte aligned");
     prm.stats_out = reinterpret_cast<float2*>(a->row_stats_out);
-    prm.stats_parts = a->N / 32;
+    prm.stats_parts = 2 * prm.n_tiles;
   }
   if (a->ln_stats) {
     B200_CHECK_ARG(a->ksize == 1 && a->stride == 1 && nsrc == 1, "conv_gemm: folded LayerNorm needs a 1x1 / linear GEMM with one source");
-    B200_CHECK_ARG(a->ln_colsum && a->ln_bias && a->ln_parts > 0 && a->ln_eps > 0.f, "conv_gemm: folded LayerNorm needs ln_colsum, ln_bias, ln_parts, ln_eps");
-    B200_CHECK_ARG(!a->bias && a->act == B200_ACT_NONE && !a->gate && !a->rowvec && !a->residual && !a->out_fp32,
-                   "conv_gemm: folded LayerNorm excludes bias (use ln_bias) / act / gate / rowvec / residual / out_fp32");
+    B200_CHECK_ARG(a->ln_parts > 0 && a->ln_parts % 2 == 0 && a->ln_eps > 0.f, "conv_gemm: folded LayerNorm needs an even ln_parts > 0 and ln_eps > 0");
+    B200_CHECK_ARG(a->act == B200_ACT_NONE && !a->gate && !a->rowvec && !a->residual && !a->out_fp32,
+                   "conv_gemm: folded LayerNorm excludes act / gate / rowvec / residual / out_fp32");
     B200_CHECK_ARG(prm.tma_store && vec, "conv_gemm: folded LayerNorm needs the vector TMA-store epilogue (aligned y, y columns %% 32 == 0)");
-    B200_CHECK_ARG(aligned16(a->ln_colsum) && aligned16(a->ln_bias) && (reinterpret_cast<uintptr_t>(a->ln_stats) & 7u) == 0,
-                   "conv_gemm: ln_colsum / ln_bias / ln_stats alignment");
+    B200_CHECK_ARG(aligned16(a->ln_stats), "conv_gemm: ln_stats not 16-byte aligned");
     prm.ln_stats = reinterpret_cast<const float2*>(a->ln_stats);
     prm.ln_parts = a->ln_parts;
     prm.ln_eps = a->ln_eps;
     prm.ln_inv_k = 1.0f / static_cast<float>(a->c[0]);
-    prm.ln_colsum = a->ln_colsum;
-    prm.ln_bias = a->ln_bias;
   }
   static const bool no_pf = getenv("B200_NO_WEIGHT_PREFETCH") && atoi(getenv("B200_NO_WEIGHT_PREFETCH")) != 0;  // tuning knob
   if (a->prefetch && a->prefetch_bytes > 0 && !no_pf) {

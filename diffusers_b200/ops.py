@@ -118,12 +118,13 @@ def _need_cuda(t, name):
 
 
 class FoldedLayerNorm:
-    """Operands of a LayerNorm folded into the Linear that consumes it (b200_conv_gemm_args.ln_*): the row statistics written
-    by the GEMM that produced the activations (`row_stats=True`), and the per-column fp32 vectors of packing.fold_layer_norm."""
-    __slots__ = ("stats", "colsum", "bias", "eps")
+    """A LayerNorm folded into the Linear that consumes it (b200_conv_gemm_args.ln_*): the row statistics written by the GEMM
+    that produced the activations (`row_stats=True`) and eps.  The weight / bias of that Linear come from
+    packing.fold_layer_norm."""
+    __slots__ = ("stats", "eps")
 
-    def __init__(self, stats, colsum, bias, eps):
-        self.stats, self.colsum, self.bias, self.eps = stats, colsum, bias, eps
+    def __init__(self, stats, eps):
+        self.stats, self.eps = stats, eps
 
 
 def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, act=ACT_NONE, geglu=False,
@@ -133,8 +134,8 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
 
     x, x2: NHWC activations given as 2-D [batch*H*W, C] (or any shape whose last dim is C, contiguous rows).
     w: packed [N, Kp] (packing.pack_conv_weight / pack_linear_weight / pack_geglu).
-    row_stats=True: also returns the fp32 [M, N/32, 2] per-chunk (sum, sum of squares) of the rounded outputs -> (y, stats).
-    ln: a FoldedLayerNorm - w holds W*gamma and the epilogue applies the normalisation of the raw rows of x."""
+    row_stats=True: also returns fp32 [M, parts, 2] partial (sum, sum of squares) of the rounded outputs of each row -> (y, stats).
+    ln: a FoldedLayerNorm - w / bias come from packing.fold_layer_norm and the epilogue scales each row by its rstd."""
     _need_cuda(x, "x")
     c0 = x.shape[-1]
     c1 = x2.shape[-1] if x2 is not None else 0
@@ -167,11 +168,11 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
     a.debug_timestamps = _ptr(debug_timestamps)
     stats = None
     if row_stats:
-        stats = torch.empty((batch * Ho * Wo, n_out // 32, 2), dtype=torch.float32, device=x.device)
+        parts = int(_lib.lib().b200_conv_gemm_row_stats_parts(C.byref(a)))
+        stats = torch.empty((batch * Ho * Wo, parts, 2), dtype=torch.float32, device=x.device)
         a.row_stats_out = stats.data_ptr()
     if ln is not None:
         a.ln_stats, a.ln_parts, a.ln_eps = ln.stats.data_ptr(), ln.stats.shape[1], ln.eps
-        a.ln_colsum, a.ln_bias = ln.colsum.data_ptr(), ln.bias.data_ptr()
     if _PLAN is not None:
         nxt = _PLAN._step(w)
         if nxt is not None:

@@ -57,29 +57,27 @@ def pack_geglu(w, b, tile_n):
 
 def fold_layer_norm(w, gamma, beta, bias, dtype):
     """nn.LayerNorm(gamma, beta) followed by nn.Linear(w, bias), as the operands of b200_conv_gemm's folded form:
-        LN(x) W^T + b = rstd * (x (W*gamma)^T) - rstd * mean * colsum + (b + W beta).
-    Returns (W*gamma rounded to `dtype` [N, K], ln_bias fp32 [N]); colsum is taken from the PACKED weight by `ln_colsum`
-    (it must sum exactly the 16-bit values the tensor cores multiply)."""
+        LN(x) W^T + b = rstd * (x W'^T) + (b + W beta),   W' = W*gamma - rowmean(W*gamma)
+    (subtracting the row means makes x W'^T = (x - mean(x)) (W gamma)^T, so the mean never has to be applied).
+    Returns (W' rounded to `dtype` [N, K], bias b + W beta in `dtype` [N], the subtracted row means fp32 [N] - kept only so
+    that unfold_layer_norm can invert the fold)."""
     wf = w.to(torch.float32)
     wg = wf if gamma is None else wf * gamma.to(torch.float32)[None, :]
+    shift = wg.mean(dim=1)
     lb = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device) if beta is None else wf @ beta.to(torch.float32)
     if bias is not None:
         lb = lb + bias.to(torch.float32)
-    return wg.to(dtype), lb.contiguous()
+    return (wg - shift[:, None]).to(dtype), lb.to(dtype).contiguous(), shift.contiguous()
 
 
-def ln_colsum(w_packed):
-    """fp32 row sums of a packed 16-bit weight (the zero padding adds nothing)."""
-    return w_packed.to(torch.float32).sum(dim=1).contiguous()
-
-
-def unfold_layer_norm(w_folded, gamma):
-    """Inverse of the weight part of fold_layer_norm in 16-bit arithmetic: exact when every gamma is a power of two (the
-    default init, gamma = 1, included); otherwise the weight is re-rounded once (construct the model with fold_norms=False
-    to keep bit-exact copies of a checkpoint's weights)."""
-    if gamma is None:
-        return w_folded
-    return (w_folded.to(torch.float32) / gamma.to(torch.float32)[None, :]).to(w_folded.dtype)
+def unfold_layer_norm(w_folded, gamma, shift):
+    """Inverse of the weight part of fold_layer_norm, evaluated in fp32 and rounded once: the fold rounds W' to 16 bit, so the
+    weight comes back within one 16-bit ulp, not bit-exact (construct the model with fold_norms=False to keep exact copies of
+    a checkpoint's weights)."""
+    wg = w_folded.to(torch.float32) + shift.to(torch.float32)[:, None]
+    if gamma is not None:
+        wg = wg / gamma.to(torch.float32)[None, :]
+    return wg.to(w_folded.dtype)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -40,9 +40,10 @@ class UNet2DConditionModel(torch.nn.Module, FromPretrainedMixin):
 
     def __init__(self, config, state_dict, dtype=torch.bfloat16, device="cuda", fold_norms=True):
         """fold_norms: the three LayerNorms of every BasicTransformerBlock are folded into the Linear that follows them
-        (b200_conv_gemm_args.ln_*: gamma goes into the packed weight, the row statistics come from the epilogue of the GEMM
-        that produced the residual stream) - no LayerNorm kernel runs.  False keeps bit-exact copies of the checkpoint's
-        to_q/k/v, attn2.to_q and ff.net.0.proj weights and runs b200_layer_norm instead."""
+        (b200_conv_gemm_args.ln_*: gamma and the mean subtraction go into the packed weight, the row statistics come from the
+        epilogue of the GEMM that produced the residual stream) - no LayerNorm kernel runs.  The fold re-rounds those weights
+        once; fold_norms=False keeps bit-exact copies of the checkpoint's to_q/k/v, attn2.to_q and ff.net.0.proj weights
+        (exact `save_pretrained` round trips) and runs b200_layer_norm instead."""
         super().__init__()
         cfg = dict(specs.SDXL_UNET_CONFIG)
         cfg.update(config)
@@ -170,16 +171,13 @@ class UNet2DConditionModel(torch.nn.Module, FromPretrainedMixin):
                 tile = ops.pick_tile_n(1 << 20, ff1.shape[0], True)
                 fold = {}
                 if self._fold_norms:
-                    # LN(x) W^T + b = rstd (x (W gamma)^T) - rstd mean colsum + (b + W beta): packing.fold_layer_norm
-                    qkv, lb1 = packing.fold_layer_norm(qkv, g(b + ".norm1.weight"), g(b + ".norm1.bias"), None, dt)
-                    q2, lb2 = packing.fold_layer_norm(q2, g(b + ".norm2.weight"), g(b + ".norm2.bias"), None, dt)
-                    ff1, lb3 = packing.fold_layer_norm(ff1, g(b + ".norm3.weight"), g(b + ".norm3.bias"), ff1bias, dt)
-                    ff1bias = lb3  # fp32, permuted with the rows by pack_geglu below
+                    # LN(x) W^T + b = rstd (x W'^T) + (b + W beta), W' = W gamma - its row means: packing.fold_layer_norm
+                    qkv, lb1, sh1 = packing.fold_layer_norm(qkv, g(b + ".norm1.weight"), g(b + ".norm1.bias"), None, dt)
+                    q2, lb2, sh2 = packing.fold_layer_norm(q2, g(b + ".norm2.weight"), g(b + ".norm2.bias"), None, dt)
+                    ff1, ff1bias, sh3 = packing.fold_layer_norm(ff1, g(b + ".norm3.weight"), g(b + ".norm3.bias"), ff1bias, dt)
+                    fold = dict(qkv_b=R(lb1), q2_b=R(lb2), qkv_sh=R32(sh1), q2_sh=R32(sh2), ff1_sh=R32(sh3))
                 ff1w, ff1b = packing.pack_geglu(ff1, ff1bias, tile)
                 qkvw, q2w = packing.pack_linear_weight(qkv), packing.pack_linear_weight(q2)
-                if self._fold_norms:
-                    fold = dict(qkv_cs=R32(packing.ln_colsum(qkvw.to(dt))), qkv_lb=R32(lb1), q2_cs=R32(packing.ln_colsum(q2w.to(dt))), q2_lb=R32(lb2),
-                                ff1_cs=R32(packing.ln_colsum(ff1w.to(dt))), ff1_lb=R32(ff1b))
                 blk = dict(
                     l1w=R(g(b + ".norm1.weight")), l1b=R(g(b + ".norm1.bias")),
                     qkv=R(qkvw),
@@ -188,7 +186,7 @@ class UNet2DConditionModel(torch.nn.Module, FromPretrainedMixin):
                     q2=R(q2w),
                     o2w=R(packing.pack_linear_weight(g(b + ".attn2.to_out.0.weight"))), o2b=R(g(b + ".attn2.to_out.0.bias")),
                     l3w=R(g(b + ".norm3.weight")), l3b=R(g(b + ".norm3.bias")),
-                    ff1w=R(ff1w), ff1b=(None if self._fold_norms else R(ff1b)), ff1n=ff1.shape[0], ff1tile=tile,
+                    ff1w=R(ff1w), ff1b=R(ff1b), ff1n=ff1.shape[0], ff1tile=tile,
                     ff2w=R(packing.pack_linear_weight(g(b + ".ff.net.2.weight"))), ff2b=R(g(b + ".ff.net.2.bias")),
                     kv_off=self._kv_total, **fold)
                 kv_w.append(torch.cat([g(b + ".attn2.to_k.weight"), g(b + ".attn2.to_v.weight")], 0))
@@ -294,22 +292,21 @@ class UNet2DConditionModel(torch.nn.Module, FromPretrainedMixin):
                 fold = self._fold_norms
                 qkv = packing.unpack_linear_weight(W(blk["qkv"]), ch)
                 if fold:
-                    qkv = packing.unfold_layer_norm(qkv, W(blk["l1w"]))
+                    qkv = packing.unfold_layer_norm(qkv, W(blk["l1w"]), W(blk["qkv_sh"]))
                 out[b + ".attn1.to_q.weight"], out[b + ".attn1.to_k.weight"], out[b + ".attn1.to_v.weight"] = (
                     qkv[:ch].contiguous(), qkv[ch:2 * ch].contiguous(), qkv[2 * ch:].contiguous())
                 out[b + ".attn1.to_out.0.weight"], out[b + ".attn1.to_out.0.bias"] = packing.unpack_linear_weight(W(blk["ow"]), ch), W(blk["ob"])
                 q2 = packing.unpack_linear_weight(W(blk["q2"]), ch)
-                out[b + ".attn2.to_q.weight"] = packing.unfold_layer_norm(q2, W(blk["l2w"])) if fold else q2
+                out[b + ".attn2.to_q.weight"] = packing.unfold_layer_norm(q2, W(blk["l2w"]), W(blk["q2_sh"])) if fold else q2
                 o = blk["kv_off"]
                 out[b + ".attn2.to_k.weight"], out[b + ".attn2.to_v.weight"] = kv[o:o + ch].contiguous(), kv[o + ch:o + 2 * ch].contiguous()
                 out[b + ".attn2.to_out.0.weight"], out[b + ".attn2.to_out.0.bias"] = packing.unpack_linear_weight(W(blk["o2w"]), ch), W(blk["o2b"])
+                ffw, ffb = packing.unpack_geglu(W(blk["ff1w"]), W(blk["ff1b"]), ch, blk["ff1tile"])
                 if fold:
-                    # ff1_lb = bias + W beta (fp32, packed row order): bias = ff1_lb - W beta with the recovered W
-                    ffw, lb = packing.unpack_geglu(W(blk["ff1w"]), W(blk["ff1_lb"]), ch, blk["ff1tile"])
-                    ffw = packing.unfold_layer_norm(ffw, W(blk["l3w"]))
-                    ffb = (lb - ffw.to(torch.float32) @ W(blk["l3b"]).to(torch.float32)).to(ffw.dtype)
-                else:
-                    ffw, ffb = packing.unpack_geglu(W(blk["ff1w"]), W(blk["ff1b"]), ch, blk["ff1tile"])
+                    # the stored bias is b + W beta: b = bias - W beta with the recovered W (the row means `ff1_sh` are in the
+                    # unpacked row order: they were taken before pack_geglu interleaved the rows)
+                    ffw = packing.unfold_layer_norm(ffw, W(blk["l3w"]), W(blk["ff1_sh"]))
+                    ffb = (ffb.to(torch.float32) - ffw.to(torch.float32) @ W(blk["l3b"]).to(torch.float32)).to(ffw.dtype)
                 out[b + ".ff.net.0.proj.weight"], out[b + ".ff.net.0.proj.bias"] = ffw, ffb
                 out[b + ".ff.net.2.weight"] = packing.unpack_linear_weight(W(blk["ff2w"]), blk["ff1n"] // 2)
                 out[b + ".ff.net.2.bias"] = W(blk["ff2b"])
@@ -413,15 +410,14 @@ class UNet2DConditionModel(torch.nn.Module, FromPretrainedMixin):
         h, st = ops.linear(n, self.W(t["piw"]), C, bias=self.W(t["pib"]), row_stats=True)
         last = len(t["blocks"]) - 1
         for i, blk in enumerate(t["blocks"]):
-            qkv = ops.linear(h, self.W(blk["qkv"]), 3 * C, ln=FL(st, self.W(blk["qkv_cs"]), self.W(blk["qkv_lb"]), 1e-5)).view(B, hw, 3 * C)
+            qkv = ops.linear(h, self.W(blk["qkv"]), 3 * C, bias=self.W(blk["qkv_b"]), ln=FL(st, 1e-5)).view(B, hw, 3 * C)
             o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads=nh, head_dim=hd)
             h, st = ops.linear(o.view(B * hw, C), self.W(blk["ow"]), C, bias=self.W(blk["ob"]), residual=h, row_stats=True)
-            q = ops.linear(h, self.W(blk["q2"]), C, ln=FL(st, self.W(blk["q2_cs"]), self.W(blk["q2_lb"]), 1e-5)).view(B, hw, C)
+            q = ops.linear(h, self.W(blk["q2"]), C, bias=self.W(blk["q2_b"]), ln=FL(st, 1e-5)).view(B, hw, C)
             kvb = kv[:, :, blk["kv_off"]:blk["kv_off"] + 2 * C]
             o = ops.attention(q, kvb[:, :, :C], kvb[:, :, C:], heads=nh, head_dim=hd)
             h, st = ops.linear(o.view(B * hw, C), self.W(blk["o2w"]), C, bias=self.W(blk["o2b"]), residual=h, row_stats=True)
-            gg = ops.linear(h, self.W(blk["ff1w"]), blk["ff1n"], geglu=True, tile_n=blk["ff1tile"],
-                            ln=FL(st, self.W(blk["ff1_cs"]), self.W(blk["ff1_lb"]), 1e-5))
+            gg = ops.linear(h, self.W(blk["ff1w"]), blk["ff1n"], bias=self.W(blk["ff1b"]), geglu=True, tile_n=blk["ff1tile"], ln=FL(st, 1e-5))
             if i == last:
                 h = ops.linear(gg, self.W(blk["ff2w"]), C, bias=self.W(blk["ff2b"]), residual=h)
             else:

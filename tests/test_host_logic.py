@@ -197,28 +197,25 @@ def test_unsupported_checkpoint_options_are_refused():
 
 
 def test_fold_layer_norm_algebra_and_inverse():
-    """packing.fold_layer_norm / ln_colsum: LN(x) W^T + b == rstd * (x (W gamma)^T) - rstd * mean * colsum + (b + W beta), evaluated the way
-    the GEMM epilogue does (raw rows, per-row statistics from E[x^2] - E[x]^2); and the inverse used by reference_state_dict."""
+    """packing.fold_layer_norm: LN(x) W^T + b == rstd * (x W'^T) + (b + W beta) with W' = W gamma - rowmean(W gamma), evaluated the way
+    the GEMM epilogue does (raw rows, rstd from E[x^2] - E[x]^2); and the inverse used by reference_state_dict."""
     torch.manual_seed(0)
     M, K, N = 64, 96, 40
     x = (torch.randn(M, K) * 2 + 1.5).bfloat16()
     w, b = (torch.randn(N, K) * K ** -0.5).bfloat16(), torch.randn(N).bfloat16()
     gamma, beta = (torch.randn(K) * 0.3 + 1).bfloat16(), (torch.randn(K) * 0.5).bfloat16()
-    wf, lb = packing.fold_layer_norm(w, gamma, beta, b, torch.bfloat16)
+    wf, lb, shift = packing.fold_layer_norm(w, gamma, beta, b, torch.bfloat16)
     wp = packing.pack_linear_weight(wf)
-    cs = packing.ln_colsum(wp)
     xf = x.float()
     mean = xf.mean(1, keepdim=True)
     var = (xf * xf).mean(1, keepdim=True) - mean * mean
     rstd = torch.rsqrt(var + 1e-5)
     acc = xf @ packing.unpack_linear_weight(wp, K).float().t()
-    got = rstd * acc - rstd * mean * cs[None] + lb[None]
+    got = rstd * acc + lb.float()[None]
     ref = torch.nn.functional.layer_norm(xf, (K,), gamma.float(), beta.float(), 1e-5) @ w.float().t() + b.float()
-    assert (got - ref).abs().max() < 3e-2  # W*gamma is rounded to bf16 once
-    # gamma a power of two: the fold is exactly invertible
-    g2 = torch.full((K,), 0.5).bfloat16()
-    wf2, _ = packing.fold_layer_norm(w, g2, beta, b, torch.bfloat16)
-    assert torch.equal(packing.unfold_layer_norm(wf2, g2), w)
+    assert (got - ref).abs().max() < 4e-2  # W' and the bias are rounded to bf16 once
+    rec = packing.unfold_layer_norm(wf, gamma, shift)
+    assert (rec.float() - w.float()).abs().max() <= 2.0 ** -7 * w.float().abs().max()  # back within one bf16 ulp
 
 
 def test_unet_fold_norms_flag_keeps_exact_weights_when_off():
@@ -237,6 +234,6 @@ def test_unet_fold_norms_flag_keeps_exact_weights_when_off():
     folded = UNet2DConditionModel(ucfg, sd, device="cpu").reference_state_dict()
     for k in sd:
         d = (folded[k].float() - sd[k].float()).abs().max()
-        # weights: re-rounded once at most; the GEGLU bias comes back as (b + W beta) - W' beta with the re-rounded W'
-        tol = 5e-3 if k.endswith("ff.net.0.proj.bias") else 2.0 ** -7 * sd[k].float().abs().max() + 1e-6
+        # weights: re-rounded once (within an ulp); the GEGLU bias comes back as (b + W beta) - W' beta with the re-rounded W'
+        tol = 2e-2 if k.endswith("ff.net.0.proj.bias") else 2.0 ** -5 * sd[k].float().abs().max() + 1e-6  # gamma down to ~0.4 amplifies the ulp
         assert d <= tol, (k, float(d))
