@@ -119,6 +119,7 @@ def lib():
         _lib.b200_scale.argtypes = [VP, VP, I64, F32, I32, VP]
         _lib.b200_cfg_euler_step.argtypes = [VP, I32, VP, VP, I32, I32, I32, I32, F32, I32, F32, F32, I32, VP]
         _lib.b200_flow_match_step.argtypes = [VP, VP, VP, I64, F32, F32, I32, VP]
+        _lib.b200_linear_step.argtypes = [VP, VP, VP, VP, VP, I64, F32, F32, F32, F32, I32, VP]
         _lib.b200_ddpm_step.argtypes = [VP, VP, VP, VP, I64, F32, F32, F32, F32, F32, I32, F32, I32, VP]
         _lib.b200_softmax_rows.argtypes = [VP, I64, VP, I64, I32, I32, F32, I32, VP]
         _lib.b200_transpose_16.argtypes = [VP, I64, VP, I64, I32, I32, VP]

@@ -49,19 +49,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// 2^x on the FMA/ALU pipes (Cody-Waite split + cubic on [-0.5, 0.5], max rel. error 1.0e-4 << bf16/fp16 rounding of
-// P): the MUFU unit (16 ex2/clk/SM) is the bottleneck of a head_dim-64 attention tile, so half of the exponentials are
-// computed here, in parallel with the other half on MUFU.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(f, 0.05583828f, 0.24263948f);
-  p = fmaf(p, f, 0.69313675f);
-  p = fmaf(p, f, 0.99992454f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 template <int HD, int NQ, bool FP16>
 __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1) ? 2 : 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<HD, NQ>;
@@ -241,7 +228,8 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
     const uint32_t s_t = tmem_base + lane_off + i * 128;
     const uint32_t o_t = tmem_base + lane_off + NQ * 128 + i * HD;
     const float sc = p.scale_log2;
-    float m = 0.f, l = 0.f;
+    float m = 0.f;
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;  // four partial row sums: no serial FADD chain
 
     for (int j = 0; j < n_blocks; ++j) {
       mbar_wait_warp(&s_full[i], j & 1);
@@ -259,9 +247,24 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
       tmem_wait_ld();
       float mx = -INFINITY;
       if (!partial) {
+        // 3-input max (FMNMX3) into four independent accumulators: 48 ALU instructions for 96 scores, chains of 12
+        float x0 = -INFINITY, x1 = -INFINITY, x2 = -INFINITY, x3 = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < 32; ++k)
-          mx = fmaxf(mx, fmaxf(__uint_as_float(t0[k]), fmaxf(__uint_as_float(a1[k]), __uint_as_float(b1[k]))));
+        for (int k = 0; k < 32; k += 8) {
+          x0 = fmax3(x0, __uint_as_float(t0[k + 0]), __uint_as_float(t0[k + 1]));
+          x1 = fmax3(x1, __uint_as_float(t0[k + 2]), __uint_as_float(t0[k + 3]));
+          x2 = fmax3(x2, __uint_as_float(t0[k + 4]), __uint_as_float(t0[k + 5]));
+          x3 = fmax3(x3, __uint_as_float(t0[k + 6]), __uint_as_float(t0[k + 7]));
+          x0 = fmax3(x0, __uint_as_float(a1[k + 0]), __uint_as_float(a1[k + 1]));
+          x1 = fmax3(x1, __uint_as_float(a1[k + 2]), __uint_as_float(a1[k + 3]));
+          x2 = fmax3(x2, __uint_as_float(a1[k + 4]), __uint_as_float(a1[k + 5]));
+          x3 = fmax3(x3, __uint_as_float(a1[k + 6]), __uint_as_float(a1[k + 7]));
+          x0 = fmax3(x0, __uint_as_float(b1[k + 0]), __uint_as_float(b1[k + 1]));
+          x1 = fmax3(x1, __uint_as_float(b1[k + 2]), __uint_as_float(b1[k + 3]));
+          x2 = fmax3(x2, __uint_as_float(b1[k + 4]), __uint_as_float(b1[k + 5]));
+          x3 = fmax3(x3, __uint_as_float(b1[k + 6]), __uint_as_float(b1[k + 7]));
+        }
+        mx = fmax3(x0, x1, fmaxf(x2, x3));
       } else {
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
@@ -273,8 +276,15 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
       tmem_ld32(s_t + 32, t0);
       tmem_wait_ld();
       if (!partial) {
+        float x0 = mx, x1 = -INFINITY, x2 = -INFINITY, x3 = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(t0[k]));
+        for (int k = 0; k < 32; k += 8) {
+          x0 = fmax3(x0, __uint_as_float(t0[k + 0]), __uint_as_float(t0[k + 1]));
+          x1 = fmax3(x1, __uint_as_float(t0[k + 2]), __uint_as_float(t0[k + 3]));
+          x2 = fmax3(x2, __uint_as_float(t0[k + 4]), __uint_as_float(t0[k + 5]));
+          x3 = fmax3(x3, __uint_as_float(t0[k + 6]), __uint_as_float(t0[k + 7]));
+        }
+        mx = fmax3(x0, x1, fmaxf(x2, x3));
       } else {
 #pragma unroll
         for (int k = 0; k < 32; ++k)
@@ -289,7 +299,7 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
           const float alpha = need ? ex2_approx(m - mx) : 1.0f;
           if (need) {
             m = mx;
-            l *= alpha;
+            l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
           }
 #pragma unroll 1
           for (int c = 0; c < HD / 32; ++c) {
@@ -307,17 +317,35 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
       // (the ragged-tail masking is compiled out of the full-block path: as predicated compares/selects it cost two
       // instructions per score in EVERY block, a third of the loop)
       auto exps32 = [&](auto masked, const uint32_t (&src)[32], uint32_t* dst, int col0) {
+        if constexpr (decltype(masked)::value) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(src[2 * k]), sc, -m));
-          float p1 = (k & 1) ? ex2_poly(fmaf(__uint_as_float(src[2 * k + 1]), sc, -m))
-                             : ex2_approx(fmaf(__uint_as_float(src[2 * k + 1]), sc, -m));
-          if constexpr (decltype(masked)::value) {
+          for (int k = 0; k < 16; ++k) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(src[2 * k]), sc, -m));
+            float p1 = ex2_approx(fmaf(__uint_as_float(src[2 * k + 1]), sc, -m));
             if (col0 + 2 * k >= kv_left) p0 = 0.f;
             if (col0 + 2 * k + 1 >= kv_left) p1 = 0.f;
+            l0 += p0;
+            l1 += p1;
+            dst[k] = H::pack(p0, p1);
           }
-          l += p0 + p1;
-          dst[k] = H::pack(p0, p1);
+        } else {
+          // packed fp32x2 scale-and-shift; of every 8 score pairs 7 go to MUFU and 1 to the FMA-pipe polynomial (the share
+          // measured best for the head_dim-64 kernel, attention64.cu); pairwise packed row sums into 4 accumulators
+          const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m, -m);
+#pragma unroll
+          for (int k = 0; k < 16; k += 8) {
+            float2 x[8], e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              x[j] = __ffma2_rn(make_float2(__uint_as_float(src[2 * (k + j)]), __uint_as_float(src[2 * (k + j) + 1])), sc2, nm2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = (j == 5) ? ex2_poly_pair(x[j]) : make_float2(fast_ex2(x[j].x), fast_ex2(x[j].y));
+            const float2 s01 = __fadd2_rn(e[0], e[1]), s23 = __fadd2_rn(e[2], e[3]), s45 = __fadd2_rn(e[4], e[5]), s67 = __fadd2_rn(e[6], e[7]);
+            const float2 sa = __fadd2_rn(s01, s23), sb = __fadd2_rn(s45, s67);
+            l0 += sa.x; l1 += sa.y; l2 += sb.x; l3 += sb.y;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[k + j] = H::pack(e[j].x, e[j].y);
+          }
         }
       };
       using Masked = std::integral_constant<bool, true>;
@@ -357,7 +385,7 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
     tc_fence_after();
     const int qrow = q_row0 + i * 128 + row;
     const bool valid = qrow < p.sq;
-    const float inv_l = 1.0f / l;
+    const float inv_l = 1.0f / ((l0 + l1) + (l2 + l3));
     typename H::T* orow = static_cast<typename H::T*>(p.o) + static_cast<long long>(b) * p.o_batch_stride +
                           static_cast<long long>(qrow) * p.o_row_stride + head * HD;
 #pragma unroll 1

@@ -61,34 +61,6 @@ struct Attn64Cfg {
   static constexpr int REGS_LOW = 56, REGS_HIGH = 200;  // 128 * (56 + 200) = 32768 = half of the SM's register file
 };
 
-__device__ __forceinline__ float a64_ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float a64_max3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-// 2^x for a pair, x <= ~0, on the FMA pipe: x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 polynomial
-// (relative error 1.1e-4: below the 16-bit rounding of P), the exponent added into the float's bits.
-__device__ __forceinline__ float2 a64_ex2_poly2(float2 x) {
-  x.x = fmaxf(x.x, -126.0f);
-  x.y = fmaxf(x.y, -126.0f);
-  const float2 magic = make_float2(12582912.0f, 12582912.0f);
-  const float2 t = __fadd2_rn(x, magic);
-  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
-  float2 p = __ffma2_rn(f, make_float2(0.05583828f, 0.05583828f), make_float2(0.24263948f, 0.24263948f));
-  p = __ffma2_rn(p, f, make_float2(0.69313675f, 0.69313675f));
-  p = __ffma2_rn(p, f, make_float2(0.99992454f, 0.99992454f));
-  float2 r;
-  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
-  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
-  return r;
-}
-
 // POLY: score pairs (of every 8) whose exponentials go to the FMA-pipe polynomial instead of MUFU (0..3)
 template <bool FP16, int POLY>
 __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(const __grid_constant__ Attn64Params p) {
@@ -275,12 +247,12 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
       float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
 #pragma unroll
       for (int k = 0; k < 64; k += 8) {
-        a0 = a64_max3(a0, __uint_as_float(s[k + 0]), __uint_as_float(s[k + 1]));
-        a1 = a64_max3(a1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
-        a2 = a64_max3(a2, __uint_as_float(s[k + 4]), __uint_as_float(s[k + 5]));
-        a3 = a64_max3(a3, __uint_as_float(s[k + 6]), __uint_as_float(s[k + 7]));
+        a0 = fmax3(a0, __uint_as_float(s[k + 0]), __uint_as_float(s[k + 1]));
+        a1 = fmax3(a1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
+        a2 = fmax3(a2, __uint_as_float(s[k + 4]), __uint_as_float(s[k + 5]));
+        a3 = fmax3(a3, __uint_as_float(s[k + 6]), __uint_as_float(s[k + 7]));
       }
-      return a64_max3(a0, a1, fmaxf(a2, a3));
+      return fmax3(a0, a1, fmaxf(a2, a3));
     };
     // 32 scores s[OFF .. OFF+32) -> 16 packed P.  Of every 16 exponentials 10 go to MUFU and 6 (three packed pairs) to the
     // FMA-pipe polynomial: MUFU 40 x 8 cycles, FMA pipe (scale, polynomial, row sums) ~300, ALU (max, clamps, exponent
@@ -297,9 +269,9 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if ((POLY >= 1 && j == 5) || (POLY >= 2 && j == 2) || (POLY >= 3 && j == 7))
-            e[j] = a64_ex2_poly2(x[j]);
+            e[j] = ex2_poly_pair(x[j]);
           else
-            e[j] = make_float2(a64_ex2(x[j].x), a64_ex2(x[j].y));
+            e[j] = make_float2(fast_ex2(x[j].x), fast_ex2(x[j].y));
         }
         const float2 s01 = __fadd2_rn(e[0], e[1]), s23 = __fadd2_rn(e[2], e[3]), s45 = __fadd2_rn(e[4], e[5]), s67 = __fadd2_rn(e[6], e[7]);
         const float2 sa_ = __fadd2_rn(s01, s23), sb_ = __fadd2_rn(s45, s67);
@@ -351,7 +323,7 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
           // every P V issued so far (halves <= h, in order on the tensor pipe) must have landed before O is rescaled
           mbar_wait_warp(&pv_done[buf], (h >> 1) & 1u);
           tc_fence_after();
-          const float alpha = need ? a64_ex2(m - mx) : 1.0f;
+          const float alpha = need ? fast_ex2(m - mx) : 1.0f;
           if (need) {
             m = mx;
             l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;

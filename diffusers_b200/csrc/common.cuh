@@ -459,6 +459,34 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+// ---- softmax arithmetic shared by the attention kernels
+__device__ __forceinline__ float fast_ex2(float x) {  // MUFU.EX2 (16 / clk / SM)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {  // FMNMX3: one ALU instruction
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// 2^x for a pair, x <= ~0, on the FMA pipe (packed fp32x2): x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3
+// polynomial (relative error 1.1e-4: below the 16-bit rounding of P), the exponent added into the float's bits.
+__device__ __forceinline__ float2 ex2_poly_pair(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.05583828f, 0.05583828f), make_float2(0.24263948f, 0.24263948f));
+  p = __ffma2_rn(p, f, make_float2(0.69313675f, 0.69313675f));
+  p = __ffma2_rn(p, f, make_float2(0.99992454f, 0.99992454f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -92,13 +92,16 @@ struct ConvGemmCfg {
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;  // a CTA of a pair holds half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SLAB_BYTES = 128 * 32 * 2;  // one 32-column output slab (64 B rows)
-  static constexpr int NSLAB = 4;
-  static constexpr int RAW_STAGES = (232448 - NSLAB * SLAB_BYTES - 1024 - 256) / STAGE_BYTES;
+  // 6 output slabs = 3 per epilogue half: a half stores chunk i, works on chunk i+1 and the residual of chunk i+2 streams
+  // into the third (with 2 per half every chunk waited for the TMA store issued just before it to finish reading its slab:
+  // the full store latency on the critical path of every 32 columns)
+  static constexpr int NSLAB = 6;
+  static constexpr int RAW_STAGES = (232448 - NSLAB * SLAB_BYTES - 1024 - 512) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
   // accumulator buffers sit at power-of-two column offsets
   static constexpr int ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NSLAB * SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NSLAB * SLAB_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(SMEM_BYTES <= 232448 && STAGES >= 3, "shared memory budget");
 };
 
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* rfull_bar = tempty_bar + 2;          // residual slab landed (loader warp -> epilogue)
   uint64_t* sfree_bar = rfull_bar + Cfg::NSLAB;  // the TMA store that read the slab has drained it (epilogue -> loader)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfree_bar + Cfg::NSLAB);
-  static_assert((2 * STAGES + 4 + 2 * Cfg::NSLAB) * 8 + 4 <= 256, "barrier area");
+  static_assert((2 * STAGES + 4 + 2 * Cfg::NSLAB) * 8 + 4 <= 512, "barrier area");
 
   const long long t_entry = clock64();
   pdl_trigger();
@@ -392,8 +395,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     const float2* ln_stats = p.ln_stats;
     float2* stats_out = p.stats_out;
     uint32_t k = 0;           // running chunk count over all tiles of this CTA (slab k % NSLAB, half k & 1)
-    uint32_t prev_k = 0;      // issuer: chunk of this half's store still in flight
-    bool have_prev = false;
+    uint32_t prev_k = 0, prev2_k = 0;  // issuer: chunks of this half's (up to two) stores still in flight, newest first
+    bool have_prev = false, have_prev2 = false;
     int it = 0;
     for (int g = cluster; g < p.total_groups; g += n_clusters, ++it) {
       const int acc = it & 1;
@@ -456,13 +459,14 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           bc[j] = (chunk_vec && bias) ? *reinterpret_cast<const uint4*>(bias + bcol + j * 8) : make_uint4(0, 0, 0, 0);
         uint8_t* slab = slabs + (k % Cfg::NSLAB) * Cfg::SLAB_BYTES;
         if (tma_store) {
-          if (q == 0 && have_prev) {
-            // this half's previous store has long been read out: hand its slab back to the slab manager
+          if (q == 0 && have_prev2) {
+            // the store BEFORE the previous one has long been read out: hand its slab back to the slab manager (the
+            // previous store may still be reading its slab: nobody waits for it here)
             if (elect_one()) {
-              bulk_wait_group_read<0>();
-              mbar_arrive(&sfree_bar[prev_k % Cfg::NSLAB]);
+              bulk_wait_group_read<1>();
+              mbar_arrive(&sfree_bar[prev2_k % Cfg::NSLAB]);
             }
-            have_prev = false;
+            have_prev2 = false;
           }
           mbar_wait_warp(&rfull_bar[k % Cfg::NSLAB], (k / Cfg::NSLAB) & 1u);  // slab is ours (and holds the residual if any)
         }
@@ -582,6 +586,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               bulk_commit_group();
               if (stamp) dbg[11 + c * 4] = clock64();
             }
+            have_prev2 = have_prev;
+            prev2_k = prev_k;
             have_prev = true;
             prev_k = k;
           }
@@ -596,13 +602,11 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         else
           mbar_arrive(&tempty_bar[acc]);
       }
-      if (q == 0 && have_prev) {  // tile done: free this half's last slab so the next tile's residual can stream in
-        if (elect_one()) {
-          bulk_wait_group_read<0>();
-          mbar_arrive(&sfree_bar[prev_k % Cfg::NSLAB]);
-        }
-        have_prev = false;
-      }
+      // (stores still in flight carry over into the next tile: with three slabs per half one is always free for the next
+      // tile's first residual chunk, and nobody stalls on a store that has just been issued)
+    }
+    if (q == 0 && (have_prev || have_prev2)) {  // the stores must have read their slabs before the CTA gives up its shared memory
+      if (elect_one()) bulk_wait_group_read<0>();
     }
     if (dbg && issuer && half == 0) dbg[6] = clock64();
   }

@@ -259,6 +259,30 @@ __global__ void flow_match_step_kernel(const void* v_, const void* sample_, void
   prev[i] = H::from_float(__fadd_rn(H::to_float(sample[i]), m));
 }
 
+// Generic first / second order stepper update: prev = a * sample + b * m0 + c * m1 + s * noise, fp32 math on the 16-bit
+// operands, ONE rounding.  DDIM (eta = 0), Euler-ancestral and DPM-Solver++ (2M) steps are all of this form (their data
+// predictions x0 = (x - sigma_t eps) / alpha_t are linear in (x, eps) too); the reference evaluates them as chains of 16-bit
+// tensor ops, so this result is closer to the fp32 value of the same formula than the reference's own (tests compare both).
+template <bool FP16>
+__global__ void linear_step_kernel(const void* sample_, const void* m0_, const void* m1_, const void* noise_, void* prev_, long long n,
+                                   float a, float b, float c, float s) {
+  pdl_trigger();
+  pdl_wait();
+  using H = Half16<FP16>;
+  const typename H::T* sample = static_cast<const typename H::T*>(sample_);
+  const typename H::T* m0 = static_cast<const typename H::T*>(m0_);
+  const typename H::T* m1 = static_cast<const typename H::T*>(m1_);
+  const typename H::T* noise = static_cast<const typename H::T*>(noise_);
+  typename H::T* prev = static_cast<typename H::T*>(prev_);
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = a * H::to_float(sample[i]);
+  if (m0) v = fmaf(b, H::to_float(m0[i]), v);
+  if (m1) v = fmaf(c, H::to_float(m1[i]), v);
+  if (noise) v = fmaf(s, H::to_float(noise[i]), v);
+  prev[i] = H::from_float(v);
+}
+
 // y = r16(x / div)  (EulerDiscreteScheduler.scale_model_input, scheduling_euler_discrete.py:345)
 template <bool FP16>
 __global__ void scale_kernel(const void* x_, void* y_, long long n, float div) {
@@ -538,6 +562,19 @@ int b200_transpose_16(const void* src, int64_t ld_src, void* dst, int64_t ld_dst
   launch_pdl(transpose16_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const uint16_t*>(src), ld_src, static_cast<uint16_t*>(dst), ld_dst, rows, cols);
   return check_launch("transpose16_kernel");
+}
+
+int b200_linear_step(const void* sample, const void* m0, const void* m1, const void* noise, void* prev_sample, int64_t n, float a,
+                     float b, float c, float s, int32_t dtype, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(sample && prev_sample && n > 0, "linear_step: bad args");
+  B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "linear_step: dtype %d", dtype);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200_DTYPE_FP16)
+    launch_pdl(linear_step_kernel<true>, dim3(blocks_for(n, 256)), dim3(256), 0, st, sample, m0, m1, noise, prev_sample, n, a, b, c, s);
+  else
+    launch_pdl(linear_step_kernel<false>, dim3(blocks_for(n, 256)), dim3(256), 0, st, sample, m0, m1, noise, prev_sample, n, a, b, c, s);
+  return check_launch("linear_step_kernel");
 }
 
 int b200_ddpm_step(const void* model_output, const void* sample, const void* noise, void* prev_sample, int64_t n,

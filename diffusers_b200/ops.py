@@ -423,6 +423,23 @@ def flow_match_step(model_output, sample, sigma, sigma_next, out=None):
     return out
 
 
+def linear_step(sample, m0=None, m1=None, noise=None, *, a=1.0, b=0.0, c=0.0, s=0.0, out=None):
+    """prev = a*sample + b*m0 + c*m1 + s*noise in fp32 with one rounding (b200_linear_step): the update of the DDIM,
+    Euler-ancestral and DPM-Solver++ steppers."""
+    _need_cuda(sample, "sample")
+    sample = sample.contiguous()
+    dt = sample.dtype
+    prep = lambda t: None if t is None else t.to(dt).contiguous()  # noqa: E731
+    m0, m1, noise = prep(m0), prep(m1), prep(noise)
+    if out is None:
+        out = torch.empty_like(sample)
+    _lib.check(_lib.lib().b200_linear_step(C.c_void_p(sample.data_ptr()), C.c_void_p(_ptr(m0)), C.c_void_p(_ptr(m1)), C.c_void_p(_ptr(noise)),
+                                           C.c_void_p(out.data_ptr()), C.c_int64(sample.numel()), C.c_float(a), C.c_float(b), C.c_float(c),
+                                           C.c_float(s), _dtype_code(sample), _stream()), "b200_linear_step")
+    _count()
+    return out
+
+
 def softmax_rows(s, scale, dtype, out=None):
     """softmax(s * scale) over the last dim: s fp32 [rows, cols] -> 16-bit [rows, cols]."""
     _need_cuda(s, "s")

@@ -228,6 +228,14 @@ int b200_timestep_embedding(const float* t, int32_t n, void* out, int32_t ld_out
  *                         CFG combine, Euler update of the NCHW latents (in place), and the next
  *                         step's scaled, CFG-duplicated NHWC model input
  *   b200_flow_match_step  FlowMatchEulerDiscreteScheduler.step (scheduling_flow_match_euler_discrete.py:484-517) */
+/*   b200_linear_step      prev = a*sample + b*m0 + c*m1 + s*noise (m0 / m1 / noise may be NULL), fp32 math, one rounding: the
+ *                         update of DDIMScheduler.step with eta = 0 (schedulers/scheduling_ddim.py:384-520),
+ *                         EulerAncestralDiscreteScheduler.step (scheduling_euler_ancestral_discrete.py:330-440) and
+ *                         DPMSolverMultistepScheduler dpmsolver++ first / second order updates
+ *                         (scheduling_dpmsolver_multistep.py:620-800); the data prediction x0 = (x - sigma_t eps) / alpha_t is
+ *                         the same call */
+int b200_linear_step(const void* sample, const void* m0, const void* m1, const void* noise, void* prev_sample, int64_t n, float a,
+                     float b, float c, float s, int32_t dtype, void* stream);
 int b200_euler_step(const void* model_output, const void* sample, void* prev_sample, int64_t n, float sigma,
                     float sigma_next, int32_t dtype, void* stream);
 int b200_scale(const void* x, void* y, int64_t n, float divisor, int32_t dtype, void* stream);

@@ -5,6 +5,7 @@ set -u
 mkdir -p gpurun_out
 export PYTHONPATH="$PWD:${PYTHONPATH:-}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/nvsmi.txt 2>&1
+md5sum diffusers_b200/_C/libb200diff.so | tee -a gpurun_out/nvsmi.txt
 for step in "$@"; do
   t0=$(date +%s)
   case "$step" in
