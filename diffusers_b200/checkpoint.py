@@ -207,12 +207,14 @@ def load_pipeline_components(path, expected_class, wanted, torch_dtype=torch.bfl
         if slot not in comps:
             raise ValueError(f"{path}/model_index.json has no '{slot}' component")
         ref_cls = comps[slot][1]
-        if hasattr(shell, "_ref_class_names"):
+        if not isinstance(shell, (tuple, list)) and hasattr(shell, "_ref_class_names"):
             if ref_cls not in shell._ref_class_names:
                 raise NotImplementedError(f"{slot}: {ref_cls} is not on the accelerated path ({shell._ref_class_names})")
             out[slot] = shell.from_pretrained(path, subfolder=slot, variant=variant, torch_dtype=torch_dtype, device=device)
         else:
-            if ref_cls != shell.__name__:
-                raise NotImplementedError(f"{slot}: {ref_cls} is not on the accelerated path ({shell.__name__})")
-            out[slot] = scheduler_from_pretrained(shell, path, subfolder=slot)
+            choices = shell if isinstance(shell, (tuple, list)) else (shell,)  # scheduler slot: any of the implemented steppers
+            match = [c for c in choices if c.__name__ == ref_cls]
+            if not match:
+                raise NotImplementedError(f"{slot}: {ref_cls} is not on the accelerated path ({[c.__name__ for c in choices]})")
+            out[slot] = scheduler_from_pretrained(match[0], path, subfolder=slot)
     return out

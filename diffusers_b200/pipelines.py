@@ -56,10 +56,11 @@ class StableDiffusionXLPipeline:
         the text encoders / tokenizers are not on the path: call with prompt_embeds).  checkpoint.py, SURVEY.md 8f N1."""
         from . import checkpoint
         from .autoencoder_kl import AutoencoderKL
-        from .schedulers import EulerDiscreteScheduler
+        from .schedulers import DDIMScheduler, DPMSolverMultistepScheduler, EulerAncestralDiscreteScheduler, EulerDiscreteScheduler
         from .unet_2d_condition import UNet2DConditionModel
+        steppers = (EulerDiscreteScheduler, DDIMScheduler, EulerAncestralDiscreteScheduler, DPMSolverMultistepScheduler)
         c = checkpoint.load_pipeline_components(path, "StableDiffusionXLPipeline",
-                                                dict(unet=UNet2DConditionModel, vae=AutoencoderKL, scheduler=EulerDiscreteScheduler),
+                                                dict(unet=UNet2DConditionModel, vae=AutoencoderKL, scheduler=steppers),
                                                 torch_dtype=torch_dtype, device=device, variant=variant)
         return cls(c["vae"], c["unet"], c["scheduler"])
 
@@ -149,9 +150,14 @@ class StableDiffusionXLPipeline:
         added = dict(text_embeds=add_text, time_ids=add_time_ids)
         sched.set_begin_index(0)
 
-        if fused:
+        from .schedulers import EulerDiscreteScheduler
+        if fused and isinstance(sched, EulerDiscreteScheduler):
             lat = self._denoise_fused(lat, timesteps, prompt_embeds, added, guidance_scale, do_cfg)
         else:
+            # drop-in loop (any scheduler with the reference's scale_model_input / step surface: DDIM, Euler-ancestral,
+            # DPM-Solver++ here); `generator` reaches step() only if it takes one (pipeline_stable_diffusion_xl.py:599-607)
+            import inspect
+            extra = dict(generator=generator) if "generator" in inspect.signature(sched.step).parameters else {}
             for t in timesteps:
                 inp = torch.cat([lat] * 2) if do_cfg else lat
                 inp = sched.scale_model_input(inp, t)
@@ -159,7 +165,7 @@ class StableDiffusionXLPipeline:
                 if do_cfg:
                     u, c = noise_pred.chunk(2)
                     noise_pred = u + guidance_scale * (c - u)
-                lat = sched.step(noise_pred, t, lat, return_dict=False)[0]
+                lat = sched.step(noise_pred, t, lat, return_dict=False, **extra)[0]
 
         if output_type == "latent":
             image = lat

@@ -384,7 +384,9 @@ class DDPMScheduler:
         noise, sigma = None, 0.0
         if t > 0:
             from .pipelines import randn_tensor
-            # the draw happens in fp32 (config 0 is an fp32 model in the reference) and is rounded to the model dtype
+            # The reference draws in model_output.dtype (scheduling_ddpm.py:541-543).  BASELINE config 0 is an fp32 reference model
+            # that this 16-bit shell stands in for, so the draw stays in fp32 (the reference's stream for config 0, which the
+            # parity test relies on) and is rounded to the shell's dtype; a 16-bit REFERENCE model would draw a different stream.
             noise = randn_tensor(model_output.shape, generator=generator, device=model_output.device, dtype=torch.float32).to(model_output.dtype)
             sigma = float(self._get_variance(t) ** 0.5)
         prev = ops.ddpm_step(model_output, sample.to(model_output.dtype), noise, sqrt_beta_prod=float(b_t ** 0.5),
@@ -396,3 +398,319 @@ class DDPMScheduler:
 
     def __len__(self):
         return self.config.num_train_timesteps
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# more steppers on one fused update kernel (b200_linear_step: prev = a x + b m0 + c m1 + s noise in fp32
+# with ONE rounding; the reference evaluates the same formulas as chains of 16-bit tensor ops).  Host tables are the
+# reference's own numpy / torch expressions, bit for bit (tests/test_host_logic.py against tests/golden/schedulers2.pt).
+# ----------------------------------------------------------------------------------------------------------------------
+def _betas(beta_schedule, beta_start, beta_end, n):
+    if beta_schedule == "linear":
+        return torch.linspace(beta_start, beta_end, n, dtype=torch.float32)
+    if beta_schedule == "scaled_linear":
+        return torch.linspace(beta_start ** 0.5, beta_end ** 0.5, n, dtype=torch.float32) ** 2
+    raise NotImplementedError(beta_schedule)
+
+
+class _StepIndexMixin:
+    """Step bookkeeping without device->host syncs: the pipelines call set_begin_index(0); otherwise the first timestep is
+    looked up once in the host copy of the table (like the reference's index_for_timestep)."""
+
+    @property
+    def step_index(self):
+        return self._step_index
+
+    @property
+    def begin_index(self):
+        return self._begin_index
+
+    def set_begin_index(self, begin_index=0):
+        self._begin_index = begin_index
+
+    def _init_step_index(self, timestep):
+        if self._begin_index is None:
+            t = float(timestep)
+            idx = (self._timesteps_cpu.to(torch.float64) == t).nonzero()
+            if len(idx) == 0:
+                raise ValueError(f"timestep {t} is not in the schedule")
+            self._step_index = int(idx[1 if len(idx) > 1 else 0])
+        else:
+            self._step_index = self._begin_index
+
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None):
+        from .checkpoint import scheduler_from_pretrained
+        return scheduler_from_pretrained(cls, path, subfolder)
+
+    @classmethod
+    def from_config(cls, config):
+        from .checkpoint import scheduler_kwargs
+        return cls(**scheduler_kwargs(cls, config))
+
+    def __len__(self):
+        return self.config.num_train_timesteps
+
+
+def _reject(name, unsupported, not_implemented):
+    import warnings
+    for k, v in unsupported.items():
+        if k in not_implemented:
+            if v not in not_implemented[k]:
+                raise NotImplementedError(f"{name} option {k}={v!r} is outside the hot path")
+        else:
+            warnings.warn(f"{name}: config key {k!r} is not an argument of the reference scheduler and is ignored")
+
+
+class DDIMScheduler(_StepIndexMixin):
+    """schedulers/scheduling_ddim.py:137 - deterministic DDIM (eta = 0), epsilon prediction, no sample clipping (the latent
+    diffusion configuration: SD / SDXL checkpoints ship clip_sample=False).
+        x0 = (x - sqrt(1-a_t) eps) / sqrt(a_t);  prev = sqrt(a_prev) x0 + sqrt(1-a_prev) eps      (:470-500)"""
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", clip_sample=True,
+                 set_alpha_to_one=True, steps_offset=0, prediction_type="epsilon", timestep_spacing="leading", **unsupported):
+        _reject("DDIMScheduler", unsupported, dict(trained_betas=(None,), thresholding=(None, False), dynamic_thresholding_ratio=(0.995,),
+                                                   clip_sample_range=(1.0, 1), sample_max_value=(1.0, 1), rescale_betas_zero_snr=(None, False)))
+        if clip_sample:
+            raise NotImplementedError("DDIMScheduler clip_sample=True (pixel-space models) is outside the hot path; latent models use False")
+        if prediction_type != "epsilon":
+            raise NotImplementedError("only prediction_type='epsilon'")
+        self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end, beta_schedule=beta_schedule,
+                                   clip_sample=False, set_alpha_to_one=set_alpha_to_one, steps_offset=steps_offset, prediction_type=prediction_type,
+                                   timestep_spacing=timestep_spacing, thresholding=False)
+        self.betas = _betas(beta_schedule, beta_start, beta_end, num_train_timesteps)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.num_inference_steps = None
+        self._timesteps_cpu = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
+        self.timesteps = self._timesteps_cpu
+        self._step_index = self._begin_index = None
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        c = self.config
+        if num_inference_steps > c.num_train_timesteps:
+            raise ValueError("`num_inference_steps` cannot be larger than `num_train_timesteps`")
+        self.num_inference_steps = num_inference_steps
+        if c.timestep_spacing == "linspace":
+            ts = np.linspace(0, c.num_train_timesteps - 1, num_inference_steps).round()[::-1].copy().astype(np.int64)
+        elif c.timestep_spacing == "leading":
+            ts = (np.arange(0, num_inference_steps) * (c.num_train_timesteps // num_inference_steps)).round()[::-1].copy().astype(np.int64)
+            ts += c.steps_offset
+        elif c.timestep_spacing == "trailing":
+            ts = np.round(np.arange(c.num_train_timesteps, 0, -c.num_train_timesteps / num_inference_steps)).astype(np.int64)
+            ts -= 1
+        else:
+            raise ValueError(c.timestep_spacing)
+        self._timesteps_cpu = torch.from_numpy(ts)
+        self.timesteps = self._timesteps_cpu.to(device)
+        self._step_index = self._begin_index = None
+
+    def step(self, model_output, timestep, sample, eta=0.0, use_clipped_model_output=False, generator=None, variance_noise=None,
+             return_dict=True):
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
+        if eta != 0.0 or variance_noise is not None:
+            raise NotImplementedError("eta > 0 (stochastic DDIM) is outside the hot path")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        t = int(self._timesteps_cpu[self._step_index])  # host copy: no device sync
+        prev_t = t - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
+        sa, sb = float(a_t ** 0.5), float((1 - a_t) ** 0.5)
+        sap, sbp = float(a_prev ** 0.5), float((1 - a_prev) ** 0.5)
+        x0 = ops.linear_step(sample, m0=model_output, a=1.0 / sa, b=-sb / sa)
+        prev = ops.linear_step(sample, m0=model_output, a=sap / sa, b=sbp - sap * sb / sa)
+        self._step_index += 1
+        if not return_dict:
+            return (prev, x0)
+        return SchedulerOutput(prev, x0)
+
+
+class EulerAncestralDiscreteScheduler(_StepIndexMixin):
+    """schedulers/scheduling_euler_ancestral_discrete.py:133 - epsilon prediction: with sigma_up / sigma_down of :432-435
+        prev = x + eps (sigma_down - sigma) + noise sigma_up,   noise ~ randn_tensor(model_output.dtype, generator)   (:437-447)"""
+    order = 1
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", prediction_type="epsilon",
+                 timestep_spacing="linspace", steps_offset=0, **unsupported):
+        _reject("EulerAncestralDiscreteScheduler", unsupported, dict(trained_betas=(None,), rescale_betas_zero_snr=(None, False)))
+        if prediction_type != "epsilon":
+            raise NotImplementedError("only prediction_type='epsilon'")
+        self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end, beta_schedule=beta_schedule,
+                                   prediction_type=prediction_type, timestep_spacing=timestep_spacing, steps_offset=steps_offset)
+        self.betas = _betas(beta_schedule, beta_start, beta_end, num_train_timesteps)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        sigmas = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sigmas = np.concatenate([sigmas[::-1], [0.0]]).astype(np.float32)
+        self.sigmas = torch.from_numpy(sigmas)
+        self.num_inference_steps = None
+        self._timesteps_cpu = torch.from_numpy(np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=float)[::-1].copy())
+        self.timesteps = self._timesteps_cpu
+        self.is_scale_input_called = False
+        self._step_index = self._begin_index = None
+
+    @property
+    def init_noise_sigma(self):
+        max_sigma = self.sigmas.max()
+        if self.config.timestep_spacing in ("linspace", "trailing"):
+            return max_sigma
+        return (max_sigma ** 2 + 1) ** 0.5
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        c = self.config
+        self.num_inference_steps = num_inference_steps
+        if c.timestep_spacing == "linspace":
+            ts = np.linspace(0, c.num_train_timesteps - 1, num_inference_steps, dtype=np.float32)[::-1].copy()
+        elif c.timestep_spacing == "leading":
+            ts = (np.arange(0, num_inference_steps) * (c.num_train_timesteps // num_inference_steps)).round()[::-1].copy().astype(np.float32)
+            ts += c.steps_offset
+        elif c.timestep_spacing == "trailing":
+            ts = (np.arange(c.num_train_timesteps, 0, -c.num_train_timesteps / num_inference_steps)).round().copy().astype(np.float32)
+            ts -= 1
+        else:
+            raise ValueError(c.timestep_spacing)
+        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0.0]]).astype(np.float32))  # host table
+        self._timesteps_cpu = torch.from_numpy(ts)
+        self.timesteps = self._timesteps_cpu.to(device=device)
+        self._step_index = self._begin_index = None
+
+    def scale_model_input(self, sample, timestep):
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        sigma = self.sigmas[self._step_index]
+        self.is_scale_input_called = True
+        return ops.scale_div(sample, float((sigma ** 2 + 1) ** 0.5))
+
+    def step(self, model_output, timestep, sample, generator=None, return_dict=True):
+        if isinstance(timestep, (int, torch.IntTensor, torch.LongTensor)):
+            raise ValueError("Passing integer indices as timesteps to EulerAncestralDiscreteScheduler.step() is not supported.")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        sigma_from, sigma_to = self.sigmas[self._step_index], self.sigmas[self._step_index + 1]
+        sigma_up = (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5
+        sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
+        from .pipelines import randn_tensor
+        noise = randn_tensor(model_output.shape, dtype=model_output.dtype, device=model_output.device, generator=generator)
+        prev = ops.linear_step(sample.to(model_output.dtype), m0=model_output, noise=noise, a=1.0, b=float(sigma_down - sigma_from), s=float(sigma_up))
+        self._step_index += 1
+        if not return_dict:
+            return (prev, None)
+        return SchedulerOutput(prev)
+
+
+class DPMSolverMultistepScheduler(_StepIndexMixin):
+    """schedulers/scheduling_dpmsolver_multistep.py:132 - DPM-Solver++ (2M): algorithm_type 'dpmsolver++', solver_order 1 or 2,
+    midpoint, epsilon prediction, sigmas interpolated from the training schedule (no Karras / Lu / exponential / beta / flow
+    variants), final sigma 0.  Data prediction (:793-795) and the first / second order updates (:900-903, :980-992) are single
+    b200_linear_step launches; the coefficients are computed from the fp32 sigma table exactly as the reference does."""
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2,
+                 prediction_type="epsilon", algorithm_type="dpmsolver++", solver_type="midpoint", lower_order_final=True, euler_at_final=False,
+                 final_sigmas_type="zero", lambda_min_clipped=-float("inf"), timestep_spacing="linspace", steps_offset=0, **unsupported):
+        _reject("DPMSolverMultistepScheduler", unsupported,
+                dict(trained_betas=(None,), thresholding=(None, False), dynamic_thresholding_ratio=(0.995,), sample_max_value=(1.0, 1),
+                     use_karras_sigmas=(None, False), use_exponential_sigmas=(None, False), use_beta_sigmas=(None, False), use_lu_lambdas=(None, False),
+                     use_flow_sigmas=(None, False), flow_shift=(1.0, 1), variance_type=(None,), rescale_betas_zero_snr=(None, False),
+                     use_dynamic_shifting=(None, False), time_shift_type=("exponential",)))
+        if (prediction_type, algorithm_type, solver_type, final_sigmas_type) != ("epsilon", "dpmsolver++", "midpoint", "zero") or solver_order not in (1, 2):
+            raise NotImplementedError("DPMSolverMultistepScheduler: only epsilon / dpmsolver++ / midpoint / final sigma zero, order 1 or 2")
+        self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end, beta_schedule=beta_schedule,
+                                   solver_order=solver_order, prediction_type=prediction_type, algorithm_type=algorithm_type, solver_type=solver_type,
+                                   lower_order_final=lower_order_final, euler_at_final=euler_at_final, final_sigmas_type=final_sigmas_type,
+                                   lambda_min_clipped=lambda_min_clipped, timestep_spacing=timestep_spacing, steps_offset=steps_offset,
+                                   use_karras_sigmas=False, thresholding=False)
+        self.betas = _betas(beta_schedule, beta_start, beta_end, num_train_timesteps)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.alpha_t = torch.sqrt(self.alphas_cumprod)
+        self.sigma_t = torch.sqrt(1 - self.alphas_cumprod)
+        self.lambda_t = torch.log(self.alpha_t) - torch.log(self.sigma_t)
+        self.sigmas = ((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5
+        self.num_inference_steps = None
+        self._timesteps_cpu = torch.from_numpy(np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=np.float32)[::-1].copy())
+        self.timesteps = self._timesteps_cpu
+        self.model_outputs = [None] * solver_order
+        self.lower_order_nums = 0
+        self._step_index = self._begin_index = None
+
+    def scale_model_input(self, sample, *args, **kwargs):
+        return sample
+
+    def set_timesteps(self, num_inference_steps=None, device=None, timesteps=None):
+        if timesteps is not None:
+            raise NotImplementedError("custom timesteps")
+        c = self.config
+        clipped_idx = torch.searchsorted(torch.flip(self.lambda_t, [0]), c.lambda_min_clipped)
+        last_timestep = ((c.num_train_timesteps - clipped_idx).numpy()).item()
+        if c.timestep_spacing == "linspace":
+            ts = np.linspace(0, last_timestep - 1, num_inference_steps + 1).round()[::-1][:-1].copy().astype(np.int64)
+        elif c.timestep_spacing == "leading":
+            step_ratio = last_timestep // (num_inference_steps + 1)
+            ts = (np.arange(0, num_inference_steps + 1) * step_ratio).round()[::-1][:-1].copy().astype(np.int64)
+            ts += c.steps_offset
+        elif c.timestep_spacing == "trailing":
+            ts = np.arange(last_timestep, 0, -c.num_train_timesteps / num_inference_steps).round().copy().astype(np.int64)
+            ts -= 1
+        else:
+            raise ValueError(c.timestep_spacing)
+        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0]]).astype(np.float32))  # host table
+        self._timesteps_cpu = torch.from_numpy(ts)
+        self.timesteps = self._timesteps_cpu.to(device=device, dtype=torch.int64)
+        self.num_inference_steps = len(ts)
+        self.model_outputs = [None] * c.solver_order
+        self.lower_order_nums = 0
+        self._step_index = self._begin_index = None
+
+    @staticmethod
+    def _alpha_sigma(sigma):
+        alpha_t = 1 / ((sigma ** 2 + 1) ** 0.5)
+        return alpha_t, sigma * alpha_t
+
+    def step(self, model_output, timestep, sample, generator=None, variance_noise=None, return_dict=True):
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        i, n, c = self._step_index, len(self._timesteps_cpu), self.config
+        lower_order_final = (i == n - 1) and (c.euler_at_final or (c.lower_order_final and n < 15) or c.final_sigmas_type == "zero")
+        # data prediction x0 = (x - sigma_t eps) / alpha_t at the current sigma (:793-795)
+        a_cur, s_cur = self._alpha_sigma(self.sigmas[i])
+        x0 = ops.linear_step(sample.to(model_output.dtype), m0=model_output, a=float(1.0 / a_cur), b=float(-s_cur / a_cur))
+        for k in range(c.solver_order - 1):
+            self.model_outputs[k] = self.model_outputs[k + 1]
+        self.model_outputs[-1] = x0
+        alpha_t, sigma_t = self._alpha_sigma(self.sigmas[i + 1])
+        alpha_s0, sigma_s0 = self._alpha_sigma(self.sigmas[i])
+        lambda_t = torch.log(alpha_t) - torch.log(sigma_t)
+        lambda_s0 = torch.log(alpha_s0) - torch.log(sigma_s0)
+        h = lambda_t - lambda_s0
+        A = float(sigma_t / sigma_s0)
+        B = float(-(alpha_t * (torch.exp(-h) - 1.0)))
+        if c.solver_order == 1 or self.lower_order_nums < 1 or lower_order_final:
+            prev = ops.linear_step(sample.to(model_output.dtype), m0=x0, a=A, b=B)
+        else:
+            alpha_s1, sigma_s1 = self._alpha_sigma(self.sigmas[i - 1])
+            lambda_s1 = torch.log(alpha_s1) - torch.log(sigma_s1)
+            r0 = float((lambda_s0 - lambda_s1) / h)
+            # x_t = A x + B D0 + 0.5 B D1,  D0 = m0,  D1 = (m0 - m1) / r0
+            prev = ops.linear_step(sample.to(model_output.dtype), m0=x0, m1=self.model_outputs[-2], a=A, b=B * (1.0 + 0.5 / r0), c=-0.5 * B / r0)
+        if self.lower_order_nums < c.solver_order:
+            self.lower_order_nums += 1
+        self._step_index += 1
+        if not return_dict:
+            return (prev,)
+        return SchedulerOutput(prev)

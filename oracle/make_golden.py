@@ -135,6 +135,53 @@ def gen_schedulers(d):
     print("schedulers ok")
 
 
+STEPPERS = [  # (fixture key, reference class, constructor arguments)
+    ("ddim_sdxl", "DDIMScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False,
+                                        steps_offset=1, timestep_spacing="leading")),
+    ("ddim_trailing", "DDIMScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                                            timestep_spacing="trailing")),
+    ("euler_a_sdxl", "EulerAncestralDiscreteScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                                            timestep_spacing="leading", steps_offset=1)),
+    ("dpmpp_2m_sdxl", "DPMSolverMultistepScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                                         timestep_spacing="leading", steps_offset=1)),
+    ("dpmpp_2m_linspace", "DPMSolverMultistepScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")),
+    ("dpmpp_1", "DPMSolverMultistepScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", solver_order=1)),
+]
+
+
+def stepper_fake_model(x, t):
+    """A deterministic stand-in for the denoiser (same dtype in and out) so that scheduler trajectories can be compared alone."""
+    return (torch.sin(x.float() * 0.7 + float(t) * 0.01) * 0.8 + 0.1 * x.float()).to(x.dtype)
+
+
+def gen_steppers(d):
+    """tests/golden/schedulers2.pt: tables of the N4 steppers and whole trajectories of the REAL reference schedulers (fp32 and
+    bf16 tensors on CPU) driven by stepper_fake_model, with the ancestral sampler's noise drawn from seeded generators."""
+    out = {}
+    for key, cls, kw in STEPPERS:
+        tabs = {}
+        for n in (30, 7):
+            s = getattr(d, cls)(**kw)
+            s.set_timesteps(n)
+            tabs[n] = dict(timesteps=s.timesteps.clone(), sigmas=s.sigmas.clone() if hasattr(s, "sigmas") else None,
+                           init_noise_sigma=float(s.init_noise_sigma))
+        traj = {}
+        for dt in (torch.float32, torch.bfloat16):
+            s = getattr(d, cls)(**kw)
+            s.set_timesteps(8)
+            x = (torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(1)) * float(s.init_noise_sigma)).to(dt)
+            g = torch.Generator().manual_seed(0)
+            start = x.clone()
+            for t in s.timesteps:
+                eps = stepper_fake_model(s.scale_model_input(x, t), t)
+                extra = dict(generator=g) if cls.startswith("EulerAncestral") else {}
+                x = s.step(eps, t, x, return_dict=False, **extra)[0]
+            traj[str(dt).split(".")[-1]] = dict(start=start, final=x.clone())
+        out[key] = dict(cls=cls, config=kw, tables=tabs, trajectory=traj, steps=8)
+    torch.save(out, os.path.join(OUT, "schedulers2.pt"))
+    print("steppers ok")
+
+
 def _run(mod, sd32, sd16, fn):
     mod.load_state_dict(sd32)
     with torch.no_grad():
@@ -394,7 +441,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     dmod = ref_shim.import_reference()
-    which = sys.argv[1:] or ["blocks", "layers", "schedulers", "models", "pipelines", "checkpoints"]
+    which = sys.argv[1:] or ["blocks", "layers", "schedulers", "steppers", "models", "pipelines", "checkpoints"]
     for w in which:
         globals()["gen_" + w](dmod)
     for f in sorted(os.listdir(OUT)):

@@ -190,3 +190,157 @@ class DDPM:
             noise = torch.randn(model_output.shape, generator=generator, dtype=model_output.dtype)
             variance = (self._get_variance(t) ** 0.5) * noise
         return prev + variance
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# SURVEY.md 8f N4 steppers, restated op for op (tensor ops on the caller's dtype, fp32 0-dim table entries as scalars, the
+# upcasts where the reference has them) - pinned by tests/golden/schedulers2.pt (recorded from the real reference).
+# ----------------------------------------------------------------------------------------------------------------------
+def _betas(schedule, b0, b1, n):
+    if schedule == "linear":
+        return torch.linspace(b0, b1, n, dtype=torch.float32)
+    if schedule == "scaled_linear":
+        return torch.linspace(b0 ** 0.5, b1 ** 0.5, n, dtype=torch.float32) ** 2
+    raise NotImplementedError(schedule)
+
+
+class DDIM:
+    """schedulers/scheduling_ddim.py: __init__ :193-245, set_timesteps :328-381, step :384-520 (eta = 0, epsilon, no clipping)"""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", set_alpha_to_one=True,
+                 steps_offset=0, timestep_spacing="leading", clip_sample=False):
+        assert not clip_sample
+        self.N, self.offset, self.spacing = num_train_timesteps, steps_offset, timestep_spacing
+        self.alphas_cumprod = torch.cumprod(1.0 - _betas(beta_schedule, beta_start, beta_end, num_train_timesteps), dim=0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.init_noise_sigma = 1.0
+
+    def set_timesteps(self, n):
+        self.n = n
+        if self.spacing == "linspace":
+            ts = np.linspace(0, self.N - 1, n).round()[::-1].copy().astype(np.int64)
+        elif self.spacing == "leading":
+            ts = (np.arange(0, n) * (self.N // n)).round()[::-1].copy().astype(np.int64) + self.offset
+        else:
+            ts = np.round(np.arange(self.N, 0, -self.N / n)).astype(np.int64) - 1
+        self.timesteps = torch.from_numpy(ts)
+
+    def scale_model_input(self, x, t):
+        return x
+
+    def step(self, model_output, timestep, sample, generator=None):
+        t = int(timestep)
+        prev_t = t - self.N // self.n
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
+        b_t = 1 - a_t
+        x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+        direction = (1 - a_prev) ** 0.5 * model_output
+        return a_prev ** 0.5 * x0 + direction
+
+
+class EulerAncestral:
+    """schedulers/scheduling_euler_ancestral_discrete.py: __init__ :164-210, set_timesteps :285-328, scale_model_input :258-283,
+    step :376-455 (epsilon)"""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", timestep_spacing="linspace",
+                 steps_offset=0):
+        self.N, self.offset, self.spacing = num_train_timesteps, steps_offset, timestep_spacing
+        self.alphas_cumprod = torch.cumprod(1.0 - _betas(beta_schedule, beta_start, beta_end, num_train_timesteps), dim=0)
+        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        self.sigmas = torch.from_numpy(np.concatenate([sig[::-1], [0.0]]).astype(np.float32))
+        self.i = None
+
+    @property
+    def init_noise_sigma(self):
+        m = self.sigmas.max()
+        return m if self.spacing in ("linspace", "trailing") else (m ** 2 + 1) ** 0.5
+
+    def set_timesteps(self, n):
+        if self.spacing == "linspace":
+            ts = np.linspace(0, self.N - 1, n, dtype=np.float32)[::-1].copy()
+        elif self.spacing == "leading":
+            ts = (np.arange(0, n) * (self.N // n)).round()[::-1].copy().astype(np.float32) + self.offset
+        else:
+            ts = (np.arange(self.N, 0, -self.N / n)).round().copy().astype(np.float32) - 1
+        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0.0]]).astype(np.float32))
+        self.timesteps = torch.from_numpy(ts)
+        self.i = 0
+
+    def scale_model_input(self, x, t):
+        sigma = self.sigmas[self.i]
+        return x / ((sigma ** 2 + 1) ** 0.5)
+
+    def step(self, model_output, timestep, sample, generator=None):
+        sigma = self.sigmas[self.i]
+        sample = sample.to(torch.float32)
+        x0 = sample - sigma * model_output
+        s_from, s_to = self.sigmas[self.i], self.sigmas[self.i + 1]
+        s_up = (s_to ** 2 * (s_from ** 2 - s_to ** 2) / s_from ** 2) ** 0.5
+        s_down = (s_to ** 2 - s_up ** 2) ** 0.5
+        prev = sample + (sample - x0) / sigma * (s_down - sigma)
+        noise = torch.randn(model_output.shape, generator=generator, dtype=model_output.dtype)
+        prev = (prev + noise * s_up).to(model_output.dtype)
+        self.i += 1
+        return prev
+
+
+class DPMSolverPP2M:
+    """schedulers/scheduling_dpmsolver_multistep.py: __init__ :215-330, set_timesteps :366-497, _sigma_to_alpha_sigma_t :577-600,
+    convert_model_output :745-815 (dpmsolver++, epsilon), dpm_solver_first_order_update :855-915,
+    multistep_dpm_solver_second_order_update :925-1010 (midpoint), step :1196-1282"""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2,
+                 timestep_spacing="linspace", steps_offset=0, lower_order_final=True):
+        self.N, self.offset, self.spacing, self.order, self.lof = num_train_timesteps, steps_offset, timestep_spacing, solver_order, lower_order_final
+        self.alphas_cumprod = torch.cumprod(1.0 - _betas(beta_schedule, beta_start, beta_end, num_train_timesteps), dim=0)
+        self.init_noise_sigma = 1.0
+
+    def set_timesteps(self, n):
+        last = self.N  # lambda_min_clipped = -inf
+        if self.spacing == "linspace":
+            ts = np.linspace(0, last - 1, n + 1).round()[::-1][:-1].copy().astype(np.int64)
+        elif self.spacing == "leading":
+            ts = (np.arange(0, n + 1) * (last // (n + 1))).round()[::-1][:-1].copy().astype(np.int64) + self.offset
+        else:
+            ts = np.arange(last, 0, -self.N / n).round().copy().astype(np.int64) - 1
+        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0]]).astype(np.float32))
+        self.timesteps = torch.from_numpy(ts)
+        self.outs, self.lower, self.i = [None] * self.order, 0, 0
+
+    def scale_model_input(self, x, t):
+        return x
+
+    @staticmethod
+    def _as(sigma):
+        a = 1 / ((sigma ** 2 + 1) ** 0.5)
+        return a, sigma * a
+
+    def step(self, model_output, timestep, sample, generator=None):
+        n, i = len(self.timesteps), self.i
+        final = i == n - 1  # final_sigmas_type == "zero"
+        a_c, s_c = self._as(self.sigmas[i])
+        x0 = (sample - s_c * model_output) / a_c
+        self.outs = self.outs[1:] + [x0]
+        sample = sample.to(torch.float32)
+        a_t, s_t = self._as(self.sigmas[i + 1])
+        a_s0, s_s0 = self._as(self.sigmas[i])
+        lam_t, lam_s0 = torch.log(a_t) - torch.log(s_t), torch.log(a_s0) - torch.log(s_s0)
+        h = lam_t - lam_s0
+        if self.order == 1 or self.lower < 1 or final:
+            prev = (s_t / s_s0) * sample - (a_t * (torch.exp(-h) - 1.0)) * x0
+        else:
+            a_s1, s_s1 = self._as(self.sigmas[i - 1])
+            lam_s1 = torch.log(a_s1) - torch.log(s_s1)
+            r0 = (lam_s0 - lam_s1) / h
+            m0, m1 = self.outs[-1], self.outs[-2]
+            d1 = (1.0 / r0) * (m0 - m1)
+            prev = (s_t / s_s0) * sample - (a_t * (torch.exp(-h) - 1.0)) * m0 - 0.5 * (a_t * (torch.exp(-h) - 1.0)) * d1
+        if self.lower < self.order:
+            self.lower += 1
+        self.i += 1
+        return prev.to(model_output.dtype)

@@ -14,6 +14,7 @@ for step in "$@"; do
     newtests) timeout 900 python -m pytest tests/test_full_size_parity_gpu.py tests/test_dropin_reference_gpu.py -m gpu -q -s > gpurun_out/pytest_new.log 2>&1; echo "new tests rc=$?" ;;
     ncu)     timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off -f -o gpurun_out/r2_targets python tools/ncu_targets.py > gpurun_out/ncu_targets.log 2>&1; echo "ncu rc=$?" ;;
     libbar)  timeout 600 python tools/library_bar.py --json gpurun_out/library_bar.json > gpurun_out/library_bar.txt 2>&1; echo "libbar rc=$?" ;;
+    libquick) timeout 400 python tools/library_bar.py --only gemm,lnfold,attention --json gpurun_out/library_bar_quick.json > gpurun_out/library_bar_quick.txt 2>&1; echo "libquick rc=$?" ;;
     attn)    timeout 300 python tools/bench_attention.py > gpurun_out/bench_attention.txt 2>&1; echo "attn rc=$?" ;;
     attnpoly) for p in 0 1 3; do echo "== B200_ATTN_POLY=$p"; B200_ATTN_POLY=$p timeout 200 python tools/bench_attention.py d64; done > gpurun_out/bench_attention_poly.txt 2>&1; echo "attnpoly rc=$?" ;;
     benchsdxl) timeout 600 python bench.py --workload sdxl --no-cpu-baseline --no-reference-cuda > gpurun_out/bench_sdxl.json 2> gpurun_out/bench_sdxl.err; echo "bench sdxl rc=$?" ;;

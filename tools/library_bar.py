@@ -109,6 +109,39 @@ def gemm_rows():
         torch.cuda.empty_cache()
 
 
+def lnfold_rows():
+    """The folded-LayerNorm variants of the three dominant transformer GEMMs next to their plain forms and to the LayerNorm
+    kernel they replace (this repo only: the reference has no such fusion)."""
+    R = 8
+    M, Cc = 2048, 1280
+    xs = [rnd(M, Cc) for _ in range(R)]
+    rs = [rnd(M, Cc) for _ in range(R)]
+    b = rnd(Cc)
+    gam, bet = rnd(Cc), rnd(Cc)
+    wo = [packing.pack_linear_weight(rnd(Cc, Cc, sc=Cc ** -0.5)) for _ in range(R)]
+    plain = timed(lambda i: ops.linear(xs[i % R], wo[i % R], Cc, bias=b, residual=rs[i % R]))
+    with_stats = timed(lambda i: ops.linear(xs[i % R], wo[i % R], Cc, bias=b, residual=rs[i % R], row_stats=True))
+    ln = timed(lambda i: ops.layer_norm(xs[i % R], eps=1e-5, gamma=gam, beta=bet))
+    _, st = ops.linear(xs[0], wo[0], Cc, bias=b, residual=rs[0], row_stats=True)
+    for name, N, geglu in (("QKV 2048x3840x1280", 3840, False), ("attn2.to_q 2048x1280x1280", 1280, False), ("FF in + GEGLU 2048x10240x1280", 10240, True)):
+        ws = [rnd(N, Cc, sc=Cc ** -0.5) for _ in range(R)]
+        bn = rnd(N)
+        if geglu:
+            tn = ops.pick_tile_n(M, N, True)
+            pk = [packing.pack_geglu(w, bn, tn) for w in ws]
+            f_plain = lambda i: ops.linear(xs[i % R], pk[i % R][0], N, bias=pk[i % R][1], geglu=True, tile_n=tn)  # noqa: E731
+            f_fold = lambda i: ops.linear(xs[i % R], pk[i % R][0], N, bias=pk[i % R][1], geglu=True, tile_n=tn, ln=ops.FoldedLayerNorm(st, 1e-5))  # noqa: E731
+        else:
+            pw = [packing.pack_linear_weight(w) for w in ws]
+            f_plain = lambda i: ops.linear(xs[i % R], pw[i % R], N, bias=bn)  # noqa: E731
+            f_fold = lambda i: ops.linear(xs[i % R], pw[i % R], N, bias=bn, ln=ops.FoldedLayerNorm(st, 1e-5))  # noqa: E731
+        r = dict(op="folded LayerNorm: " + name, plain_gemm_us=round(timed(f_plain), 2), folded_gemm_us=round(timed(f_fold), 2),
+                 layer_norm_kernel_us=round(ln, 2), producer_plain_us=round(plain, 2), producer_with_row_stats_us=round(with_stats, 2))
+        r["saved_us_per_layer"] = round(r["plain_gemm_us"] + r["layer_norm_kernel_us"] + r["producer_plain_us"] - r["folded_gemm_us"] - r["producer_with_row_stats_us"], 2)
+        ROWS.append(r)
+        print(json.dumps(r), flush=True)
+
+
 def conv_rows():
     R = 4
     for name, B, C, N, H in (("conv3x3 320->320 @128^2 (SDXL)", 2, 320, 320, 128), ("conv3x3 640->640 @64^2 (SDXL)", 2, 640, 640, 64),
@@ -190,13 +223,13 @@ def norm_rows():
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
-    ap.add_argument("--only", default="gemm,conv,attention,norm")
+    ap.add_argument("--only", default="gemm,conv,attention,norm,lnfold")
     a = ap.parse_args()
     torch.backends.cudnn.benchmark = True  # let cuDNN pick its best convolution algorithm: the fair bar
     print(f"# {torch.cuda.get_device_name(0)}; torch {torch.__version__}; cudnn {torch.backends.cudnn.version()}", flush=True)
     with torch.no_grad():
         for part in a.only.split(","):
-            dict(gemm=gemm_rows, conv=conv_rows, attention=attention_rows, norm=norm_rows)[part]()
+            dict(gemm=gemm_rows, conv=conv_rows, attention=attention_rows, norm=norm_rows, lnfold=lnfold_rows)[part]()
     if a.json:
         with open(a.json, "w") as f:
             json.dump(dict(device=torch.cuda.get_device_name(0), torch=torch.__version__, rows=ROWS), f, indent=1)
