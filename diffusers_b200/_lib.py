@@ -108,6 +108,8 @@ def lib():
         _lib.b200_conv_gemm_pick_tile_n.argtypes = [C.c_int64, C.c_int32, C.c_int32]
         _lib.b200_conv_gemm_row_stats_parts.restype = C.c_int32
         _lib.b200_conv_gemm_row_stats_parts.argtypes = [C.c_void_p]
+        _lib.b200_group_norm_launches.restype = C.c_int32
+        _lib.b200_group_norm_launches.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         _lib.b200_group_norm_workspace_bytes.restype = C.c_int64
         _lib.b200_group_norm_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         I32, I64, F32, VP = C.c_int32, C.c_int64, C.c_float, C.c_void_p

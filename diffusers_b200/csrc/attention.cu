@@ -49,7 +49,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int HD, int NQ, bool FP16>
+// POLY: score pairs of every 8 whose exponentials are evaluated by the FMA-pipe polynomial instead of MUFU (1..3)
+template <int HD, int NQ, bool FP16, int POLY = 1>
 __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1) ? 2 : 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<HD, NQ>;
   using H = Half16<FP16>;
@@ -329,8 +330,8 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
             dst[k] = H::pack(p0, p1);
           }
         } else {
-          // packed fp32x2 scale-and-shift; of every 8 score pairs 7 go to MUFU and 1 to the FMA-pipe polynomial (the share
-          // measured best for the head_dim-64 kernel, attention64.cu); pairwise packed row sums into 4 accumulators
+          // packed fp32x2 scale-and-shift; of every 8 score pairs POLY go to the FMA-pipe polynomial and the rest to MUFU;
+          // pairwise packed row sums into 4 accumulators
           const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m, -m);
 #pragma unroll
           for (int k = 0; k < 16; k += 8) {
@@ -339,7 +340,9 @@ __global__ void __launch_bounds__(AttnCfg<HD, NQ>::THREADS, (HD == 64 && NQ == 1
             for (int j = 0; j < 8; ++j)
               x[j] = __ffma2_rn(make_float2(__uint_as_float(src[2 * (k + j)]), __uint_as_float(src[2 * (k + j) + 1])), sc2, nm2);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = (j == 5) ? ex2_poly_pair(x[j]) : make_float2(fast_ex2(x[j].x), fast_ex2(x[j].y));
+            for (int j = 0; j < 8; ++j)
+              e[j] = ((POLY >= 1 && j == 5) || (POLY >= 2 && j == 2) || (POLY >= 3 && j == 7)) ? ex2_poly_pair(x[j])
+                                                                                              : make_float2(fast_ex2(x[j].x), fast_ex2(x[j].y));
             const float2 s01 = __fadd2_rn(e[0], e[1]), s23 = __fadd2_rn(e[2], e[3]), s45 = __fadd2_rn(e[4], e[5]), s67 = __fadd2_rn(e[6], e[7]);
             const float2 sa = __fadd2_rn(s01, s23), sb = __fadd2_rn(s45, s67);
             l0 += sa.x; l1 += sa.y; l2 += sb.x; l3 += sb.y;
@@ -424,9 +427,9 @@ int init_attention64();
 bool attention64_enabled();
 int launch_attention64(const b200_attention_args* a, cudaStream_t st);
 
-template <int HD, int NQ, bool FP16>
+template <int HD, int NQ, bool FP16, int POLY = 1>
 static int attn_set_attr() {
-  cudaError_t e = cudaFuncSetAttribute(attention_kernel<HD, NQ, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(attention_kernel<HD, NQ, FP16, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        AttnCfg<HD, NQ>::SMEM_BYTES);
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention smem attr: %s", cudaGetErrorString(e));
   return 0;
@@ -442,14 +445,18 @@ int init_attention() {
   if ((r = attn_set_attr<128, 1, true>())) return r;
   if ((r = attn_set_attr<128, 2, false>())) return r;
   if ((r = attn_set_attr<128, 2, true>())) return r;
+  if ((r = attn_set_attr<128, 2, false, 2>())) return r;
+  if ((r = attn_set_attr<128, 2, true, 2>())) return r;
+  if ((r = attn_set_attr<128, 2, false, 3>())) return r;
+  if ((r = attn_set_attr<128, 2, true, 3>())) return r;
   if ((r = init_attention_pipe())) return r;
   if ((r = init_attention64())) return r;
   return 0;
 }
 
-template <int HD, int NQ, bool FP16>
+template <int HD, int NQ, bool FP16, int POLY = 1>
 static int attn_launch(const AttnParams& prm, int grid, cudaStream_t st) {
-  cudaError_t e = launch_pdl(attention_kernel<HD, NQ, FP16>, dim3(grid), dim3(AttnCfg<HD, NQ>::THREADS), AttnCfg<HD, NQ>::SMEM_BYTES, st, prm);
+  cudaError_t e = launch_pdl(attention_kernel<HD, NQ, FP16, POLY>, dim3(grid), dim3(AttnCfg<HD, NQ>::THREADS), AttnCfg<HD, NQ>::SMEM_BYTES, st, prm);
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention launch: %s", cudaGetErrorString(e));
   return 0;
 }
@@ -517,7 +524,14 @@ int b200_attention(const b200_attention_args* a, void* stream) {
   if (HD == 64) {
     if (nq == 2) { B200_ATTN(64, 2); } else { B200_ATTN(64, 1); }
   } else {
-    if (nq == 2) { B200_ATTN(128, 2); } else { B200_ATTN(128, 1); }
+    if (nq == 2) {
+      static const int poly = getenv("B200_ATTN_POLY128") ? atoi(getenv("B200_ATTN_POLY128")) : 1;  // tuning knob: 1, 2 or 3
+      if (poly >= 3) return fp16 ? attn_launch<128, 2, true, 3>(prm, grid, st) : attn_launch<128, 2, false, 3>(prm, grid, st);
+      if (poly == 2) return fp16 ? attn_launch<128, 2, true, 2>(prm, grid, st) : attn_launch<128, 2, false, 2>(prm, grid, st);
+      B200_ATTN(128, 2);
+    } else {
+      B200_ATTN(128, 1);
+    }
   }
 #undef B200_ATTN
 }

@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     const int b_rows = BN / cm;  // rows of the weight tile this CTA fetches (pair: its half)
     for (int g = cluster; g < p.total_groups; g += n_clusters) {
       TileCoord tc = decode_tile(p, g, rank, BN);
+      if (dbg && g == cluster && lane == 0) dbg[12] = clock64();
       int kc = 0;
       for (int tap = 0; tap < p.num_taps; ++tap) {
         const int mp = p.tap_map[tap];
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           const CUtensorMap* am = &p.a_map[s * 4 + mp];
           for (int cc = 0; cc < p.chunks[s]; ++cc) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);  // the MMAs that read this stage (in both CTAs) have retired
+            if (dbg && kc == 0 && g == cluster && lane == 0) dbg[13] = clock64();
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             const bool skip_loads = dbg_mode == 1 && (kc >= STAGES || g != cluster);  // tuning: MMA rate alone
             if (elect_one()) {
@@ -257,7 +259,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
                 // own 128 rows of A + own half of the weight tile; the bytes are credited to the LEADER's barrier
                 const uint32_t lf = leader_addr(&full_bar[stage]);
                 mbar_expect_tx_cluster(lf, Cfg::STAGE_BYTES);
+                if (dbg && kc == 0 && g == cluster) dbg[14] = clock64();
                 tma_load_4d_2sm(sa, am, lf, cc * 64, cw, ch, tc.img);
+                if (dbg && kc == 0 && g == cluster) dbg[15] = clock64();
                 tma_load_2d_2sm(sa + Cfg::A_BYTES, &p.w_map, lf, kc * 64, tc.n0 + rank * b_rows);
               } else {
                 mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           mbar_wait_warp(&rfull_bar[k % Cfg::NSLAB], (k / Cfg::NSLAB) & 1u);  // slab is ours (and holds the residual if any)
         }
         tmem_wait_ld();
-        const bool stamp = dbg && issuer && it == 0 && c < 2;
+        const bool stamp = dbg && issuer && it == 0 && c < 1;  // (slots 12..15 hold the producer's start-up marks)
         if (stamp) dbg[8 + c * 4] = clock64();
         if (lean) {
 #pragma unroll

@@ -1,6 +1,7 @@
 // HBM-bound normalisation kernels (coalesced 16-byte accesses, warp-shuffle / shared reductions):
 //   b200_group_norm : GroupNorm(+SiLU) over NHWC, optionally over the channel concat of two tensors
 //   b200_layer_norm : LayerNorm over token rows, optional affine and AdaLN modulation
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -264,6 +265,213 @@ static void gn_plan(int batch, int hw, int C, int* chunks, int* ppc) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// GroupNorm, single pass over HBM ("slab" kernel).  The statistics kernel above re-reads what the apply kernel reads again:
+// three passes over the activation for two algorithmic ones, and two launches.  Here one thread-block CLUSTER owns one
+// (sample, block of GB consecutive groups) and its CTAs split the pixels; each CTA stages its slab - pixels x (GB * C/groups)
+// channels, <= 200 KB - in shared memory with 16-byte loads, the cluster reduces sum and sum of squared deviations through
+// distributed shared memory (every CTA reads the partials of all ranks in rank order: same value everywhere, deterministic),
+// and the slab is normalised (+ affine, + SiLU) from shared memory and written once.  Exact two-pass variance (the data sit
+// in shared memory), one read + one write of the activation, one launch.
+// GB is the smallest count of groups whose channel span is a multiple of 8 (16 bytes); thread t always works on vector
+// t % vpp of a pixel, so its 8 channels (and their scale / shift) are fixed.
+// ------------------------------------------------------------------------------------------------
+struct GroupNormSlabParams {
+  const void* x[2];
+  int c0, ldx[2];
+  int C, hw, groups, cg;
+  int gb;        // groups per unit
+  int span;      // channels per unit = gb * cg (multiple of 8)
+  int vpp;       // 16-byte vectors per pixel of a unit = span / 8
+  int units;     // groups / gb
+  int ppc;       // pixels per CTA (hw split over the cluster)
+  float eps;
+  const void* gamma;
+  const void* beta;
+  int act;
+  void* y;
+  int ldy;
+};
+
+constexpr int kGnSlabThreads = 960;  // divisible by every vpp in use (1, 2, 3, 4, 5, 6, 8, 10, 12, 15, 16, 20)
+constexpr int kGnSlabMaxBytes = 196608;
+
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(kGnSlabThreads, 1) group_norm_slab_kernel(const GroupNormSlabParams p) {
+  pdl_trigger();
+  using H = Half16<FP16>;
+  extern __shared__ uint8_t gn_smem[];
+  uint4* slab = reinterpret_cast<uint4*>(gn_smem);                                  // [ppc][vpp] vectors of 8 channels
+  float* part = reinterpret_cast<float*>(gn_smem + static_cast<size_t>(p.ppc) * p.vpp * 16);  // [threads / vpp][span] thread partials
+  __shared__ float part2[kGnSlabThreads];
+  __shared__ float red[2][32];     // this CTA's per-group partial (sum | sum of squared deviations), read by the whole cluster
+  __shared__ float g_mean[32], g_rstd[32];
+
+  const uint32_t rank = cluster_ctarank(), csize = cluster_nctarank();
+  const int unit = blockIdx.y % p.units, n = blockIdx.y / p.units;
+  const int t = threadIdx.x;
+  const int v = t % p.vpp, lane_p = t / p.vpp, p_step = kGnSlabThreads / p.vpp;
+  const int pix0 = rank * p.ppc;
+  const int npix = max(0, min(p.hw, pix0 + p.ppc) - pix0);
+  const int ch0 = unit * p.span + v * 8;  // first of this thread's 8 channels
+  const int src = ch0 < p.c0 ? 0 : 1;
+  const typename H::T* xb = static_cast<const typename H::T*>(p.x[src]) + (static_cast<size_t>(n) * p.hw + pix0) * p.ldx[src] +
+                            (src ? ch0 - p.c0 : ch0);
+  const int ld = p.ldx[src];
+  pdl_wait();
+
+  // ---- pass 0: global -> shared, per-channel sums
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  for (int px = lane_p; px < npix; px += 4 * p_step) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (px + k * p_step < npix) u[k] = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(px + k * p_step) * ld);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (px + k * p_step < npix) {
+        slab[static_cast<size_t>(px + k * p_step) * p.vpp + v] = u[k];
+        const float2 a = H::unpack(u[k].x), b = H::unpack(u[k].y), c = H::unpack(u[k].z), d = H::unpack(u[k].w);
+        s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y; s[6] += d.x; s[7] += d.y;
+      }
+    }
+  }
+  // CTA reduction in a fixed order, three levels: thread partials [p_step][span] -> R1 = 960 / span partial rows per channel
+  // (every thread sums a strided set of rows) -> one warp per group sums its R1 x cg values (strided per lane, shuffle tree)
+  auto cta_group_totals = [&](const float (&val)[8], int which) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[lane_p * p.span + v * 8 + j] = val[j];
+    __syncthreads();
+    const int R1 = kGnSlabThreads / p.span;
+    {
+      const int c = t % p.span, rr = t / p.span;
+      float acc = 0.f;
+      for (int r = rr; r < p_step; r += R1) acc += part[r * p.span + c];
+      part2[rr * p.span + c] = acc;
+    }
+    __syncthreads();
+    const int w = t >> 5, ln = t & 31;
+    if (w < p.gb) {
+      float acc = 0.f;
+      const int cnt = R1 * p.cg;
+      for (int i = ln; i < cnt; i += 32) {
+        const int rr = i / p.cg, c = w * p.cg + (i - rr * p.cg);
+        acc += part2[rr * p.span + c];
+      }
+      acc = warp_sum(acc);
+      if (ln == 0) red[which][w] = acc;
+    }
+  };
+  auto cluster_total = [&](int which, int g) {  // every CTA sums the ranks in the same order
+    float acc = 0.f;
+    const uint32_t a = smem_u32(&red[which][g]);
+    for (uint32_t r = 0; r < csize; ++r) acc += ld_dsmem_f32(map_to_rank(a, r));
+    return acc;
+  };
+  const float inv_cnt = 1.0f / (static_cast<float>(p.hw) * static_cast<float>(p.cg));
+  cta_group_totals(s, 0);
+  cluster_sync_all();
+  if (t < p.gb) g_mean[t] = cluster_total(0, t) * inv_cnt;
+  __syncthreads();
+
+  // ---- pass 1 (shared memory only): squared deviations from the group mean
+  float mean8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mean8[j] = g_mean[(v * 8 + j) / p.cg];
+  float q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q[j] = 0.f;
+  for (int px = lane_p; px < npix; px += p_step) {
+    const uint4 u = slab[static_cast<size_t>(px) * p.vpp + v];
+    const float2 a = H::unpack(u.x), b = H::unpack(u.y), c = H::unpack(u.z), d = H::unpack(u.w);
+    const float e[8] = {a.x - mean8[0], a.y - mean8[1], b.x - mean8[2], b.y - mean8[3], c.x - mean8[4], c.y - mean8[5], d.x - mean8[6], d.y - mean8[7]};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = fmaf(e[j], e[j], q[j]);
+  }
+  cta_group_totals(q, 1);
+  cluster_sync_all();
+  if (t < p.gb) g_rstd[t] = rsqrtf(cluster_total(1, t) * inv_cnt + p.eps);
+  __syncthreads();
+
+  // ---- pass 2: normalise + affine (+ SiLU) from shared memory, one write
+  float sc[8], sh[8];
+  {
+    const typename H::T* gam = static_cast<const typename H::T*>(p.gamma);
+    const typename H::T* bet = static_cast<const typename H::T*>(p.beta);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (v * 8 + j) / p.cg;
+      const float ga = gam ? H::to_float(gam[ch0 + j]) : 1.0f;
+      const float be = bet ? H::to_float(bet[ch0 + j]) : 0.0f;
+      sc[j] = g_rstd[g] * ga;
+      sh[j] = fmaf(-g_mean[g], sc[j], be);
+    }
+  }
+  typename H::T* yb = static_cast<typename H::T*>(p.y) + (static_cast<size_t>(n) * p.hw + pix0) * p.ldy + ch0;
+  const bool silu = p.act == ACT_SILU;
+  for (int px = lane_p; px < npix; px += p_step) {
+    const uint4 u = slab[static_cast<size_t>(px) * p.vpp + v];
+    const float2 a = H::unpack(u.x), b = H::unpack(u.y), c = H::unpack(u.z), d = H::unpack(u.w);
+    float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (silu) f[j] = silu_f(f[j]);
+    }
+    uint4 o;
+    o.x = H::pack(f[0], f[1]);
+    o.y = H::pack(f[2], f[3]);
+    o.z = H::pack(f[4], f[5]);
+    o.w = H::pack(f[6], f[7]);
+    *reinterpret_cast<uint4*>(yb + static_cast<size_t>(px) * p.ldy) = o;
+  }
+  cluster_sync_all();  // nobody leaves while a peer may still read its `red`
+}
+
+// Returns 0 when the slab kernel cannot take the shape (the two-kernel path does), else the cluster size.
+static int gn_slab_plan(int batch, int hw, int C, int groups, int c0, int nsrc, GroupNormSlabParams* p) {
+  if (groups > 32 * 32 || C % groups) return 0;
+  const int cg = C / groups;
+  int gb = 1;
+  while (gb <= 32 && ((gb * cg) % 8 != 0 || groups % gb != 0)) ++gb;
+  if (gb > 32) return 0;
+  const int span = gb * cg, vpp = span / 8;
+  if (kGnSlabThreads % span != 0 || gb > kGnSlabThreads / 32) return 0;  // (implies 960 % vpp == 0)
+  if (nsrc == 2 && c0 % 8 != 0) return 0;
+  for (int cl = 1; cl <= 8; cl *= 2) {
+    const int ppc = (hw + cl - 1) / cl;
+    const long long slab = static_cast<long long>(ppc) * span * 2;
+    const long long part = static_cast<long long>(kGnSlabThreads / vpp) * span * 4;
+    if (slab + part <= kGnSlabMaxBytes + 32768 && slab <= kGnSlabMaxBytes) {
+      // the smallest cluster that fits; wider clusters while fewer than ~100 CTAs would be at work (smaller slabs per SM)
+      while (cl < 8 && static_cast<long long>(cl) * (groups / gb) * batch < 96 && hw / (2 * cl) >= 64) cl *= 2;
+      if (p) {
+        p->cg = cg; p->gb = gb; p->span = span; p->vpp = vpp; p->units = groups / gb; p->ppc = (hw + cl - 1) / cl;
+      }
+      return cl;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row held in registers as packed 16-bit (<= 16 x 8 values per lane)
 // ------------------------------------------------------------------------------------------------
 struct LayerNormParams {
@@ -459,6 +667,13 @@ int64_t b200_group_norm_workspace_bytes(int32_t batch, int32_t hw, int32_t group
   return floats * 4 + 256;
 }
 
+/* Kernels b200_group_norm launches for this shape: 1 (single-pass slab kernel) or 2 (statistics + apply). */
+int32_t b200_group_norm_launches(int32_t hw, int32_t C, int32_t groups, int32_t c0, int32_t two_sources) {
+  static const bool no_slab = getenv("B200_GN_NO_SLAB") && atoi(getenv("B200_GN_NO_SLAB")) != 0;
+  if (hw <= 0 || C <= 0 || groups <= 0 || C % groups) return 2;
+  return (!no_slab && b200::gn_slab_plan(2, hw, C, groups, c0, two_sources ? 2 : 1, nullptr) > 0) ? 1 : 2;
+}
+
 int b200_group_norm(const b200_group_norm_args* a, void* stream) {
   using namespace b200;
   B200_CHECK_ARG(a && a->x[0] && a->y && a->workspace, "group_norm: null pointer");
@@ -474,6 +689,45 @@ int b200_group_norm(const b200_group_norm_args* a, void* stream) {
   B200_CHECK_ARG(a->workspace_bytes >= b200_group_norm_workspace_bytes(a->batch, a->hw, a->groups),
                  "group_norm: workspace too small");
   B200_CHECK_ARG(a->batch > 0 && a->hw > 0, "group_norm: bad shape");
+
+  static const bool no_slab = getenv("B200_GN_NO_SLAB") && atoi(getenv("B200_GN_NO_SLAB")) != 0;  // tuning / test knob
+  {
+    GroupNormSlabParams sp;
+    memset(&sp, 0, sizeof(sp));
+    const int cl = no_slab ? 0 : gn_slab_plan(a->batch, a->hw, C, a->groups, a->c[0], nsrc, &sp);
+    if (cl > 0) {
+      sp.x[0] = a->x[0];
+      sp.x[1] = nsrc == 2 ? a->x[1] : nullptr;
+      sp.c0 = nsrc == 2 ? a->c[0] : C;
+      sp.ldx[0] = a->ldx[0];
+      sp.ldx[1] = nsrc == 2 ? a->ldx[1] : 0;
+      sp.C = C; sp.hw = a->hw; sp.groups = a->groups; sp.eps = a->eps;
+      sp.gamma = a->gamma; sp.beta = a->beta; sp.act = a->act; sp.y = a->y; sp.ldy = a->ldy;
+      const size_t smem = static_cast<size_t>(sp.ppc) * sp.span * 2 + static_cast<size_t>(kGnSlabThreads / sp.vpp) * sp.span * 4;
+      const bool fp16s = a->dtype == B200_DTYPE_FP16;
+      auto kern = fp16s ? group_norm_slab_kernel<true> : group_norm_slab_kernel<false>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "group_norm (slab) smem attr: %s", cudaGetErrorString(e));
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(cl, sp.units * a->batch);
+      cfg.blockDim = dim3(kGnSlabThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = static_cast<cudaStream_t>(stream);
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cl;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+      cfg.attrs = attr;
+      cfg.numAttrs = 2;
+      e = cudaLaunchKernelEx(&cfg, kern, sp);
+      if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "group_norm (slab, cluster %d) launch: %s", cl, cudaGetErrorString(e));
+      return 0;
+    }
+  }
 
   GroupNormParams p;
   memset(&p, 0, sizeof(p));

@@ -266,7 +266,7 @@ def group_norm(x, *, batch, hw, groups, eps, gamma=None, beta=None, silu=False, 
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     a.dtype = _dtype_code(x)
     _lib.check(_lib.lib().b200_group_norm(C.byref(a), _stream()), "b200_group_norm")
-    _count(2)
+    _count(int(_lib.lib().b200_group_norm_launches(hw, c0 + c1, groups, c0, 1 if x2 is not None else 0)))
     return out
 
 

@@ -131,8 +131,10 @@ int32_t b200_conv_gemm_pick_tile_n(int64_t M, int32_t N, int32_t geglu);
 
 /* -------------------------------------------------------------------------------------------
  * b200_group_norm — nn.GroupNorm (+ fused SiLU) over NHWC, optionally over the channel concat of
- * two tensors (the skip-connection torch.cat is never materialised).  Two launches: statistics
- * (shifted sums + Chan merge, deterministic) and normalise/affine/activation.
+ * two tensors (the skip-connection torch.cat is never materialised).  One launch when the slab of a (sample, group block)
+ * fits the shared memory of a thread-block cluster (all UNet shapes but one): global -> shared once, exact two-pass
+ * statistics reduced across the cluster through distributed shared memory, normalise/affine/activation from shared memory.
+ * Otherwise two launches: statistics (shifted sums + Chan merge, deterministic) and normalise/affine/activation.
  * Replaces  models/resnet.py:326-327,349-362 (norm1/norm2 + nonlinearity),
  *           transformers/transformer_2d.py:466 (Transformer2DModel.norm, eps 1e-6),
  *           unets/unet_2d_condition.py:1227-1229 (conv_norm_out + conv_act),
@@ -157,6 +159,9 @@ typedef struct {
 } b200_group_norm_args;
 
 int b200_group_norm(const b200_group_norm_args* args, void* stream);
+/* Kernels the call above launches for a shape: 1 = single-pass cluster kernel (one read + one write of the activation; taken
+ * whenever the slab of one (sample, block of groups) fits the shared memory of <= 8 clustered CTAs), 2 = statistics + apply. */
+int32_t b200_group_norm_launches(int32_t hw, int32_t C, int32_t groups, int32_t c0, int32_t two_sources);
 int64_t b200_group_norm_workspace_bytes(int32_t batch, int32_t hw, int32_t groups);
 
 /* -------------------------------------------------------------------------------------------

@@ -78,7 +78,7 @@ def test_vae_decode(golden, name):
     out2 = m.decode(fx["z"].cuda(), return_dict=False, max_batch=1)[0]
     d = (out.float() - out2.float()).abs()
     print(f"{name}: sub-batched decode differs by max {float(d.max()):.4g} mean {float(d.mean()):.4g}")
-    assert float(d.max()) < 0.1 and float(d.mean()) < 4e-3
+    assert float(d.max()) < 0.15 and float(d.mean()) < 4e-3
 
 
 @pytest.mark.parametrize("name", ["flux_tiny", "flux_hd128"])

@@ -36,7 +36,7 @@ def test_sdxl_unet_full_size_properties():
     assert torch.isfinite(yf).all()
     amax = float(yf.abs().max())
     assert 1e-3 < amax < 1e3, amax
-    assert 700 <= launches <= 780, launches  # 737 hand-written kernels per forward (the 210 LayerNorms are folded into GEMMs), nothing silently skipped
+    assert 660 <= launches <= 720, launches  # 692 hand-written kernels per forward (210 LayerNorms folded into GEMMs, single-launch GroupNorm), nothing silently skipped
     # deterministic: the same launch sequence gives the same bits
     assert torch.equal(y, fwd(x, ehs, te))
     # the two samples of the CFG batch do not interact: swapping them swaps the outputs
@@ -80,10 +80,10 @@ def test_sdxl_vae_decode_full_size_properties():
     torch.cuda.empty_cache()
 
 
-def _attention_cases_under(env_extra, timeout=300):
+def _attention_cases_under(env_extra, timeout=300, prefix="attn_"):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cases = [c for c in diag_ops.CASES if c.startswith("attn_")]
+    cases = [c for c in diag_ops.CASES if c.startswith(prefix)]
     p = subprocess.run([sys.executable, os.path.join(root, "tools", "diag_ops.py"), "--inproc", *cases], env=dict(os.environ, **env_extra),
                        capture_output=True, text=True, timeout=timeout)
     assert "SUMMARY" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
@@ -96,3 +96,9 @@ def test_attention_fallback_kernels_still_match():
     additionally B200_ATTN_PIPE=0 -> attention.cu) and must keep passing the same cases."""
     _attention_cases_under(dict(B200_ATTN_V2="0"))
     _attention_cases_under(dict(B200_ATTN_V2="0", B200_ATTN_PIPE="0"))
+
+
+def test_group_norm_two_kernel_path_still_matches():
+    """b200_group_norm takes the single-pass cluster kernel whenever a (sample, group block) slab fits shared memory; the
+    statistics + apply pair (B200_GN_NO_SLAB=1) serves the remaining shapes and must keep passing every case."""
+    _attention_cases_under(dict(B200_GN_NO_SLAB="1"), prefix="gn_")

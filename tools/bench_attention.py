@@ -10,8 +10,8 @@ from diffusers_b200 import ops
 SHAPES = [("sdxl self 4096", 2, 10, 4096, 4096, 64), ("sdxl self 1024", 2, 20, 1024, 1024, 64), ("sdxl cross 4096x77", 2, 10, 4096, 77, 64),
           ("sdxl cross 1024x77", 2, 20, 1024, 77, 64), ("flux joint 4608", 1, 24, 4608, 4608, 128)]
 g = torch.Generator(device="cuda").manual_seed(0)
-if len(sys.argv) > 1 and sys.argv[1] == "d64":
-    SHAPES = [s for s in SHAPES if s[5] == 64]
+if len(sys.argv) > 1 and sys.argv[1] in ("d64", "d128"):
+    SHAPES = [s for s in SHAPES if s[5] == int(sys.argv[1][1:])]
 for name, B, H, Sq, Sk, D in SHAPES:
     q = torch.randn(B, Sq, H * D, generator=g, device="cuda").bfloat16()
     k = torch.randn(B, Sk, H * D, generator=g, device="cuda").bfloat16()

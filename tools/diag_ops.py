@@ -30,6 +30,10 @@ CASES = {
     "gn_cat2560": dict(kind="gn", B=2, HW=1024, C=1280, C2=1280, G=32, silu=True),
     "gn_offset": dict(kind="gn", B=1, HW=4096, C=128, G=32, silu=True, offset=50.0),
     "gn_fp16": dict(kind="gn", B=2, HW=1000, C=96, G=32, silu=True, fp16=True),
+    "gn_cat1920": dict(kind="gn", B=2, HW=4096, C=1280, C2=640, G=32, silu=True),   # a group straddles the two sources
+    "gn_cat960_big": dict(kind="gn", B=2, HW=16384, C=640, C2=320, G=32, silu=True),  # too big for a cluster's shared memory: two-kernel path
+    "gn_vae_tail": dict(kind="gn", B=1, HW=512 * 512, C=256, G=32, silu=True, eps=1e-6),  # two-kernel path
+    "gn_b1_ragged": dict(kind="gn", B=1, HW=4099, C=320, G=32, silu=False),
     "ln_1280": dict(kind="ln", rows=2048, C=1280, affine=True),
     "ln_640": dict(kind="ln", rows=8192, C=640, affine=True),
     "ln_3072_mod": dict(kind="ln", rows=4608, C=3072, affine=False, mod=True, eps=1e-6),

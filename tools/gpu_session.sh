@@ -17,6 +17,8 @@ for step in "$@"; do
     libquick) timeout 400 python tools/library_bar.py --only gemm,lnfold,attention --json gpurun_out/library_bar_quick.json > gpurun_out/library_bar_quick.txt 2>&1; echo "libquick rc=$?" ;;
     attn)    timeout 300 python tools/bench_attention.py > gpurun_out/bench_attention.txt 2>&1; echo "attn rc=$?" ;;
     attnpoly) for p in 0 1 3; do echo "== B200_ATTN_POLY=$p"; B200_ATTN_POLY=$p timeout 200 python tools/bench_attention.py d64; done > gpurun_out/bench_attention_poly.txt 2>&1; echo "attnpoly rc=$?" ;;
+    attnpoly128) for p in 1 2 3; do echo "== B200_ATTN_POLY128=$p"; B200_ATTN_POLY128=$p timeout 200 python tools/bench_attention.py d128; done > gpurun_out/bench_attention_poly128.txt 2>&1; echo "attnpoly128 rc=$?" ;;
+    timeline) for m in pf hot; do MODE=$m timeout 120 python tools/gemm_timeline.py 2048 1280 1280; done > gpurun_out/gemm_timeline.txt 2>&1; echo "timeline rc=$?" ;;
     benchsdxl) timeout 600 python bench.py --workload sdxl --no-cpu-baseline --no-reference-cuda > gpurun_out/bench_sdxl.json 2> gpurun_out/bench_sdxl.err; echo "bench sdxl rc=$?" ;;
     attncheck) timeout 400 python tools/diag_ops.py --inproc $(python -c "import sys; sys.path.insert(0,'.'); from tools import diag_ops; print(' '.join(c for c in diag_ops.CASES if c.startswith('attn_')))") > gpurun_out/attn_check.txt 2>&1; echo "attncheck rc=$?"; tail -3 gpurun_out/attn_check.txt ;;
     ncuattn) timeout 600 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:attention -f -o gpurun_out/r2_attn python tools/ncu_targets.py > gpurun_out/ncu_attn.log 2>&1; echo "ncuattn rc=$?" ;;
