@@ -115,7 +115,10 @@ class AutoencoderKL(torch.nn.Module, FromPretrainedMixin):
                 blk["res"].append(resnet(f"{p}.resnets.{j}"))
                 j += 1
             if f"{p}.upsamplers.0.conv.weight" in sd:
+                # 3x3 weight kept for reference_state_dict; the forward runs the four 2x2 parity weights (ops.upsample2x_conv)
                 blk["up"] = conv(f"{p}.upsamplers.0.conv")
+                uw = g(f"{p}.upsamplers.0.conv.weight")
+                blk["up"]["w4"] = [R(t) for t in packing.pack_upsample_conv(uw)] if uw.shape[0] % 32 == 0 else None
             self.up.append(blk)
             i += 1
         self.norm_out = dict(w=R(g(d + ".conv_norm_out.weight")), b=R(g(d + ".conv_norm_out.bias")))
@@ -236,9 +239,14 @@ class AutoencoderKL(torch.nn.Module, FromPretrainedMixin):
             for r in blk["res"]:
                 x = self._resnet(r, x, B, H, W)
             if blk["up"] is not None:
-                xu = ops.upsample_nearest2x(x, batch=B, H=H, W=W)
-                H, W = 2 * H, 2 * W
-                x = self._conv(blk["up"], xu, B, H, W)
+                u = blk["up"]
+                if u["w4"] is not None:
+                    x = ops.upsample2x_conv(x, [self.W(t) for t in u["w4"]], u["n"], batch=B, H=H, W=W, bias=self.W(u["b"]))
+                    H, W = 2 * H, 2 * W
+                else:
+                    xu = ops.upsample_nearest2x(x, batch=B, H=H, W=W)
+                    H, W = 2 * H, 2 * W
+                    x = self._conv(u, xu, B, H, W)
         n = self._gn(x, self.norm_out["w"], self.norm_out["b"], B, H * W, True)
         y = self._conv(self.conv_out, n, B, H, W)
         return y, H, W

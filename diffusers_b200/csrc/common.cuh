@@ -315,6 +315,9 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0,
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {  // bytes % 16 == 0, p 16-byte aligned
   if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

@@ -235,7 +235,6 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     const int b_rows = BN / cm;  // rows of the weight tile this CTA fetches (pair: its half)
     for (int g = cluster; g < p.total_groups; g += n_clusters) {
       TileCoord tc = decode_tile(p, g, rank, BN);
-      if (dbg && g == cluster && lane == 0) dbg[12] = clock64();
       int kc = 0;
       for (int tap = 0; tap < p.num_taps; ++tap) {
         const int mp = p.tap_map[tap];
@@ -245,7 +244,6 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           const CUtensorMap* am = &p.a_map[s * 4 + mp];
           for (int cc = 0; cc < p.chunks[s]; ++cc) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);  // the MMAs that read this stage (in both CTAs) have retired
-            if (dbg && kc == 0 && g == cluster && lane == 0) dbg[13] = clock64();
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             const bool skip_loads = dbg_mode == 1 && (kc >= STAGES || g != cluster);  // tuning: MMA rate alone
             if (elect_one()) {
@@ -259,9 +257,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
                 // own 128 rows of A + own half of the weight tile; the bytes are credited to the LEADER's barrier
                 const uint32_t lf = leader_addr(&full_bar[stage]);
                 mbar_expect_tx_cluster(lf, Cfg::STAGE_BYTES);
-                if (dbg && kc == 0 && g == cluster) dbg[14] = clock64();
                 tma_load_4d_2sm(sa, am, lf, cc * 64, cw, ch, tc.img);
-                if (dbg && kc == 0 && g == cluster) dbg[15] = clock64();
                 tma_load_2d_2sm(sa + Cfg::A_BYTES, &p.w_map, lf, kc * 64, tc.n0 + rank * b_rows);
               } else {
                 mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -440,12 +436,15 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         ln_r = rsqrtf(var + p.ln_eps);
       }
       float st_s = 0.f, st_q = 0.f;  // producer side of a folded LayerNorm: sums of this thread's ROUNDED outputs of the tile
+      if (bias != nullptr && real_tile && lane * 64 < BN && tc.n0 + lane * 64 < p.N) prefetch_l1(bias + tc.n0 + lane * 64);  // the tile's bias: L1 hits in the chunk loop
 
       mbar_wait_warp(&tfull_bar[acc], (it >> 1) & 1u);
       tc_fence_after();
       if (dbg && issuer && half == 0) dbg[5] = clock64();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
 
+      uint32_t v[32];
+      bool preloaded = false;
 #pragma unroll 1
       for (int c = 0; c < OUT_COLS / 32; ++c, ++k) {
         const int yc0 = ycol0 + c * 32;
@@ -453,8 +452,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         if ((k & 1u) != static_cast<uint32_t>(half)) continue;
         const bool chunk_vec = p.vec_ok && (yc0 + 32 <= n_limit);
         const int bcol = GEGLU ? (tc.n0 + c * 32) : yc0;
-        uint32_t v[32];
-        tmem_ld32(t_row + c * 32, v);
+        if (!preloaded) tmem_ld32(t_row + c * 32, v);  // (else issued during the previous chunk's store phase)
         uint32_t gv[32];
         if (GEGLU) tmem_ld32(t_row + BN / 2 + c * 32, gv);
         uint4 bc[4];  // bias of this chunk (same for every row: L1 hits after the first warp)
@@ -475,7 +473,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           mbar_wait_warp(&rfull_bar[k % Cfg::NSLAB], (k / Cfg::NSLAB) & 1u);  // slab is ours (and holds the residual if any)
         }
         tmem_wait_ld();
-        const bool stamp = dbg && issuer && it == 0 && c < 1;  // (slots 12..15 hold the producer's start-up marks)
+        const bool stamp = dbg && issuer && it == 0 && c < 2;
         if (stamp) dbg[8 + c * 4] = clock64();
         if (lean) {
 #pragma unroll
@@ -581,6 +579,12 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           epilogue_scalar<GEGLU, FP16>(tv, tg, p, bias, gate_row, rv_row, res_row, y_row, pix, yc0, tc.n0 + c * 32, BN, n_limit);
         }
         if (stamp) dbg[9 + c * 4] = clock64();
+        // this warp's next chunk (c + 2: the halves alternate) starts its TMEM read now, under the fence / barrier / store below
+        preloaded = false;
+        if (!GEGLU && c + 2 < OUT_COLS / 32 && ycol0 + (c + 2) * 32 < n_limit) {
+          tmem_ld32(t_row + (c + 2) * 32, v);
+          preloaded = true;
+        }
         if (tma_store) {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
           named_bar_sync(bar_id, 128);
@@ -793,7 +797,7 @@ int32_t b200_conv_gemm_pick_tile_n(int64_t M, int32_t N, int32_t geglu) { return
  * 2 per N tile of the configuration the launch will pick. */
 int32_t b200_conv_gemm_row_stats_parts(const b200_conv_gemm_args* a) {
   using namespace b200;
-  if (!a || a->N <= 0 || a->batch <= 0 || a->H <= 0 || a->W <= 0 || (a->ksize != 1 && a->ksize != 3)) return 0;
+  if (!a || a->N <= 0 || a->batch <= 0 || a->H <= 0 || a->W <= 0 || (a->ksize != 1 && a->ksize != 2 && a->ksize != 3)) return 0;
   const int Ho = (a->stride == 2) ? a->H / 2 : a->H, Wo = (a->stride == 2) ? a->W / 2 : a->W;
   long long best_tiles = -1;
   for (int bw = 128; bw >= 1; bw >>= 1) {
@@ -811,7 +815,14 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   using namespace b200;
   B200_CHECK_ARG(a != nullptr, "conv_gemm: null args");
   B200_CHECK_ARG(a->x[0] && a->w && a->y, "conv_gemm: null x/w/y");
-  B200_CHECK_ARG(a->ksize == 1 || a->ksize == 3, "conv_gemm: ksize %d (need 1 or 3)", a->ksize);
+  B200_CHECK_ARG(a->ksize == 1 || a->ksize == 3 || (a->ksize == 2 && a->up2x_parity >= 1 && a->up2x_parity <= 4),
+                 "conv_gemm: ksize %d (need 1 or 3; 2 only as a parity class of the folded nearest-2x upsample)", a->ksize);
+  const bool up2x = a->ksize == 2;
+  if (up2x)
+    B200_CHECK_ARG(a->stride == 1 && !a->geglu && !a->gate && !a->rowvec && !a->residual && !a->out_fp32 && !a->row_stats_out && !a->ln_stats,
+                   "conv_gemm: the folded-upsample form takes bias / act only");
+  else
+    B200_CHECK_ARG(a->up2x_parity == 0, "conv_gemm: up2x_parity needs ksize 2");
   B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_gemm: stride %d (need 1 or 2)", a->stride);
   B200_CHECK_ARG(a->batch > 0 && a->H > 0 && a->W > 0 && a->N > 0, "conv_gemm: bad shape");
   B200_CHECK_ARG(a->dtype == B200_DTYPE_BF16 || a->dtype == B200_DTYPE_FP16, "conv_gemm: dtype %d", a->dtype);
@@ -881,6 +892,12 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
         prm.tap_map[tap] = 0;
         prm.tap_dh[tap] = 0;
         prm.tap_dw[tap] = 0;
+      } else if (up2x) {
+        // output pixel (2i + ph, 2j + pw) of conv3x3(nearest2x(x)) reads x rows {i + ph - 1, i + ph} and columns {j + pw - 1, j + pw}
+        const int ph = (a->up2x_parity - 1) >> 1, pw = (a->up2x_parity - 1) & 1;
+        prm.tap_map[tap] = 0;
+        prm.tap_dh[tap] = static_cast<int8_t>(ph - 1 + r);
+        prm.tap_dw[tap] = static_cast<int8_t>(pw - 1 + s);
       } else if (a->stride == 1) {
         prm.tap_map[tap] = 0;
         prm.tap_dh[tap] = static_cast<int8_t>(r - 1);
@@ -950,14 +967,24 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   prm.dbg_mode = dbg_mode;
   const int n_out = a->geglu ? a->N / 2 : a->N;
   static const bool no_tma_store = getenv("B200_NO_TMA_STORE") && atoi(getenv("B200_NO_TMA_STORE")) != 0;  // tuning knob
-  prm.tma_store = (vec && !a->out_fp32 && n_out % 32 == 0 && !no_tma_store) ? 1 : 0;
+  prm.tma_store = (vec && !a->out_fp32 && n_out % 32 == 0 && (!no_tma_store || up2x)) ? 1 : 0;
+  if (up2x) B200_CHECK_ARG(prm.tma_store, "conv_gemm: the folded-upsample form needs the TMA-store epilogue (aligned y, N %% 32 == 0)");
   if (prm.tma_store) {
     const uint64_t ldy = static_cast<uint64_t>(a->ldy);
     const uint64_t dims[4] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
                               static_cast<uint64_t>(a->batch)};
-    const uint64_t str[3] = {ldy * 2, ldy * 2 * Wo, ldy * 2 * Wo * Ho};
     const uint32_t ybox[4] = {32u, static_cast<uint32_t>(prm.bw), static_cast<uint32_t>(prm.bh), 1u};
-    int r = make_tensor_map_16b(&prm.y_map, a->y, 4, dims, str, ybox, "conv_gemm Y", 64);
+    int r;
+    if (up2x) {
+      // y is the [batch, 2H, 2W, ldy] image; this launch owns the pixels (2i + ph, 2j + pw): a view with doubled pixel strides
+      const int ph = (a->up2x_parity - 1) >> 1, pw = (a->up2x_parity - 1) & 1;
+      const uint64_t str[3] = {ldy * 2 * 2, ldy * 2 * (2 * Wo) * 2, ldy * 2 * (2 * Wo) * (2 * Ho)};
+      const uint8_t* base = static_cast<const uint8_t*>(a->y) + (static_cast<uint64_t>(ph) * (2 * Wo) + pw) * ldy * 2;
+      r = make_tensor_map_16b(&prm.y_map, base, 4, dims, str, ybox, "conv_gemm Y (upsampled parity view)", 64);
+    } else {
+      const uint64_t str[3] = {ldy * 2, ldy * 2 * Wo, ldy * 2 * Wo * Ho};
+      r = make_tensor_map_16b(&prm.y_map, a->y, 4, dims, str, ybox, "conv_gemm Y", 64);
+    }
     if (r) return r;
   }
 

@@ -455,13 +455,16 @@ static int gn_slab_plan(int batch, int hw, int C, int groups, int c0, int nsrc, 
   const int span = gb * cg, vpp = span / 8;
   if (kGnSlabThreads % span != 0 || gb > kGnSlabThreads / 32) return 0;  // (implies 960 % vpp == 0)
   if (nsrc == 2 && c0 % 8 != 0) return 0;
-  for (int cl = 1; cl <= 8; cl *= 2) {
+  // Clusters of up to 4 CTAs: measured on B200 (tools/library_bar.py --only norm, us per launch, slab vs two kernels):
+  // 4096 x 640: 18.5 vs 28.8, 4096 x 1280: 27.4 vs 39.1, 1024 x 1280: 14.2 vs 22.0, 1024 x 2560: 18.6 vs 25.6 - but
+  // 16384 x 320, which needs clusters of 8, 48.6 vs 39.7: those shapes keep the two-kernel path.
+  for (int cl = 1; cl <= 4; cl *= 2) {
     const int ppc = (hw + cl - 1) / cl;
     const long long slab = static_cast<long long>(ppc) * span * 2;
     const long long part = static_cast<long long>(kGnSlabThreads / vpp) * span * 4;
     if (slab + part <= kGnSlabMaxBytes + 32768 && slab <= kGnSlabMaxBytes) {
       // the smallest cluster that fits; wider clusters while fewer than ~100 CTAs would be at work (smaller slabs per SM)
-      while (cl < 8 && static_cast<long long>(cl) * (groups / gb) * batch < 96 && hw / (2 * cl) >= 64) cl *= 2;
+      while (cl < 4 && static_cast<long long>(cl) * (groups / gb) * batch < 96 && hw / (2 * cl) >= 64) cl *= 2;
       if (p) {
         p->cg = cg; p->gb = gb; p->span = span; p->vpp = vpp; p->units = groups / gb; p->ppc = (hw + cl - 1) / cl;
       }

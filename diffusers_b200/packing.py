@@ -55,6 +55,31 @@ def pack_geglu(w, b, tile_n):
     return pack_linear_weight(wp), bp
 
 
+def pack_upsample_conv(w):
+    """nn.Conv2d 3x3 weight [O, I, 3, 3] applied AFTER a nearest-2x upsample -> four packed [O, 4 * rup64(I)] weights, one per output
+    parity class (ph, pw) in the order 2 * ph + pw (b200_conv_gemm ksize = 2, up2x_parity = 1 + index).  Output row 2i + ph reads
+    input rows {i + ph - 1, i + ph}: for ph = 0 filter row 0 lands on i - 1 and rows 1, 2 on i; for ph = 1 rows 0, 1 land on i and
+    row 2 on i + 1 (columns alike).  Taps that share an input pixel are summed in fp32 and rounded once."""
+    O, I, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    wf = w.to(torch.float32)
+    sets = (((0,), (1, 2)), ((0, 1), (2,)))  # [parity][tap] -> filter rows / columns merged into that tap
+    out = []
+    for ph in range(2):
+        for pw in range(2):
+            m = wf.new_zeros(O, I, 2, 2)
+            for a in range(2):
+                for b in range(2):
+                    for r in sets[ph][a]:
+                        for s_ in sets[pw][b]:
+                            m[:, :, a, b] += wf[:, :, r, s_]
+            cp = rup(I, 64)
+            packed = wf.new_zeros(O, 4, cp)
+            packed[:, :, :I] = m.permute(0, 2, 3, 1).reshape(O, 4, I)
+            out.append(packed.reshape(O, -1).to(w.dtype).contiguous())
+    return out
+
+
 def fold_layer_norm(w, gamma, beta, bias, dtype):
     """nn.LayerNorm(gamma, beta) followed by nn.Linear(w, bias), as the operands of b200_conv_gemm's folded form:
         LN(x) W^T + b = rstd * (x W'^T) + (b + W beta),   W' = W*gamma - rowmean(W*gamma)

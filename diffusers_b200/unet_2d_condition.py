@@ -229,8 +229,11 @@ class UNet2DConditionModel(torch.nn.Module, FromPretrainedMixin):
                 if bt == "CrossAttnUpBlock2D":
                     blk["attn"].append(transformer(f"{p}.attentions.{j}", cur, _t(rtl[i], nl)[j], rheads[i]))
             if i != n - 1:
-                blk["up"] = dict(w=R(packing.pack_conv_weight(g(f"{p}.upsamplers.0.conv.weight"))),
-                                 b=R(g(f"{p}.upsamplers.0.conv.bias")), n=cur)
+                # the 3x3 weight is kept for reference_state_dict (the parity fold sums taps: not invertible); the forward runs
+                # the four 2x2 parity weights (ops.upsample2x_conv) when the channel count allows the TMA-store epilogue
+                uw = g(f"{p}.upsamplers.0.conv.weight")
+                blk["up"] = dict(w=R(packing.pack_conv_weight(uw)), b=R(g(f"{p}.upsamplers.0.conv.bias")), n=cur,
+                                 w4=[R(t) for t in packing.pack_upsample_conv(uw)] if cur % 32 == 0 else None)
             self.up.append(blk)
         self.norm_out = dict(w=R(g("conv_norm_out.weight")), b=R(g("conv_norm_out.bias")))
         self.conv_out = dict(w=R(packing.pack_conv_weight(g("conv_out.weight"))), b=R(g("conv_out.bias")),
@@ -505,9 +508,13 @@ class UNet2DConditionModel(torch.nn.Module, FromPretrainedMixin):
                     x = self._transformer(blk["attn"][j], x, kv, B, H, W, S_txt)
             if blk["up"] is not None:
                 u = blk["up"]
-                xu = ops.upsample_nearest2x(x, batch=B, H=H, W=W)
-                H, W = 2 * H, 2 * W
-                x = ops.conv_gemm(xu, self.W(u["w"]), u["n"], batch=B, H=H, W=W, ksize=3, bias=self.W(u["b"]))
+                if u["w4"] is not None:
+                    x = ops.upsample2x_conv(x, [self.W(t) for t in u["w4"]], u["n"], batch=B, H=H, W=W, bias=self.W(u["b"]))
+                    H, W = 2 * H, 2 * W
+                else:
+                    xu = ops.upsample_nearest2x(x, batch=B, H=H, W=W)
+                    H, W = 2 * H, 2 * W
+                    x = ops.conv_gemm(xu, self.W(u["w"]), u["n"], batch=B, H=H, W=W, ksize=3, bias=self.W(u["b"]))
         n = ops.group_norm(x, batch=B, hw=H * W, groups=self.config["norm_num_groups"], eps=self.config.get("norm_eps", 1e-5),
                            gamma=self.W(self.norm_out["w"]), beta=self.W(self.norm_out["b"]), silu=True)
         return ops.conv_gemm(n, self.W(self.conv_out["w"]), self.conv_out["n"], batch=B, H=H, W=W, ksize=3,

@@ -119,6 +119,14 @@ typedef struct {
   const float* ln_stats;
   int32_t ln_parts;
   float ln_eps;
+  /* ---- nearest-2x upsample folded into the 3x3 convolution that follows it (models/upsampling.py:175-190: F.interpolate then
+   * self.conv).  Output pixel (2i + ph, 2j + pw) of conv3x3(nearest2x(x)) only ever sees the 2 x 2 input pixels
+   * x[i + ph - 1 .. i + ph, j + pw - 1 .. j + pw]; the 3 x 3 taps that land on the same input pixel are summed into one weight
+   * at load time (packing.pack_upsample_conv).  One launch per parity class with ksize = 2 and up2x_parity = 1 + 2 ph + pw:
+   * H, W are the INPUT size, w is that class's packed [N, 4 * rup64(c0)] weight, y is the full [batch, 2H, 2W, ldy] output
+   * of which the launch writes its pixels.  The upsampled tensor never exists and the convolution does 4/9 of the FLOPs.
+   * bias / act only; needs the TMA-store epilogue. */
+  int32_t up2x_parity;
 } b200_conv_gemm_args;
 
 int b200_conv_gemm(const b200_conv_gemm_args* args, void* stream);

@@ -73,12 +73,15 @@ def test_vae_decode(golden, name):
     out = m.decode(fx["z"].cuda(), return_dict=False)[0]
     _check(out, fx, name)
     assert m.config.scaling_factor == 0.13025 and tuple(m.config.block_out_channels) == tuple(fx["cfg"]["block_out_channels"])
-    # sub-batched decode (HBM footprint control) gives the same result up to the GroupNorm reduction order, which
-    # depends on how the batch is chunked across CTAs
+    # sub-batched decode (HBM footprint control): GroupNorm picks its kernel (one-pass slab or two kernels) and its
+    # reduction order from the batch it sees, so the two decodes are two independent bf16 roundings of the same
+    # network - each must meet the parity bar on its own, and they differ by about sqrt(2) x that rounding noise
     out2 = m.decode(fx["z"].cuda(), return_dict=False, max_batch=1)[0]
+    _check(out2, fx, name + " (sub-batched)")
     d = (out.float() - out2.float()).abs()
+    e = (out.float().cpu() - fx["ref32"]).abs()
     print(f"{name}: sub-batched decode differs by max {float(d.max()):.4g} mean {float(d.mean()):.4g}")
-    assert float(d.max()) < 0.15 and float(d.mean()) < 4e-3
+    assert float(d.mean()) <= 2.0 * float(e.mean()) and float(d.max()) <= 3.0 * float(e.max())
 
 
 @pytest.mark.parametrize("name", ["flux_tiny", "flux_hd128"])

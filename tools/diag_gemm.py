@@ -45,6 +45,12 @@ CASES = {
     "conv_s2_big": dict(kind="conv", B=2, H=128, W=128, C=320, N=320, bias=True, stride=2),
     "conv_c8": dict(kind="conv", B=2, H=32, W=32, C=8, N=64, bias=True),
     "conv_1x1": dict(kind="conv", B=2, H=32, W=32, C=192, N=64, bias=True, ksize=1),
+    # conv3x3(nearest2x(x)) as four 2x2 parity convolutions over the low-resolution input (ops.upsample2x_conv), against
+    # F.interpolate -> F.conv2d in fp32
+    "up2x_small": dict(kind="conv", B=2, H=16, W=16, C=64, N=64, bias=True, up2x=True),
+    "up2x_odd": dict(kind="conv", B=3, H=12, W=20, C=96, N=160, bias=True, up2x=True),      # partial pixel tiles, C not a multiple of 64
+    "up2x_sdxl": dict(kind="conv", B=2, H=32, W=32, C=1280, N=1280, bias=True, up2x=True),
+    "up2x_vae": dict(kind="conv", B=1, H=128, W=128, C=256, N=256, bias=True, up2x=True, fp16=True),
 }
 
 
@@ -171,7 +177,10 @@ def run_case(name):
         w = rnd(N, Cc + C2, ks, ks, scale=((Cc + C2) * ks * ks) ** -0.5)
         b = rnd(N) if cfg.get("bias") else None
         xx = torch.cat([x, x2], -1) if x2 is not None else x
-        ref = F.conv2d(xx.float().permute(0, 3, 1, 2), w.float(), b.float() if b is not None else None,
+        xin = xx.float().permute(0, 3, 1, 2)
+        if cfg.get("up2x"):
+            xin = F.interpolate(xin, scale_factor=2.0, mode="nearest")
+        ref = F.conv2d(xin, w.float(), b.float() if b is not None else None,
                        stride=stride, padding=ks // 2).permute(0, 2, 3, 1).contiguous()
         Ho, Wo = ref.shape[1], ref.shape[2]
         rowvec = rnd(B, N) if cfg.get("rowvec") else None
@@ -181,10 +190,13 @@ def run_case(name):
         ref = ref.reshape(B * Ho * Wo, N)
         if res is not None:
             ref = ref + res.float()
-        wp = packing.pack_conv_weight(w, (Cc, C2) if C2 else None)
-        out = ops.conv_gemm(x.reshape(-1, Cc), wp, N, batch=B, H=H, W=W, ksize=ks, stride=stride,
-                            x2=x2.reshape(-1, C2) if x2 is not None else None, bias=b, rowvec=rowvec,
-                            rows_per_group=Ho * Wo, residual=res, tile_n=tile_n)
+        if cfg.get("up2x"):
+            out = ops.upsample2x_conv(x.reshape(-1, Cc), packing.pack_upsample_conv(w), N, batch=B, H=H, W=W, bias=b)
+        else:
+            wp = packing.pack_conv_weight(w, (Cc, C2) if C2 else None)
+            out = ops.conv_gemm(x.reshape(-1, Cc), wp, N, batch=B, H=H, W=W, ksize=ks, stride=stride,
+                                x2=x2.reshape(-1, C2) if x2 is not None else None, bias=b, rowvec=rowvec,
+                                rows_per_group=Ho * Wo, residual=res, tile_n=tile_n)
     torch.cuda.synchronize()
     o = out.float()
     err = (o - ref).abs()

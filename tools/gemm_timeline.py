@@ -28,7 +28,7 @@ xs = torch.randn(256, 256, device="cuda").bfloat16()
 ws = packing.pack_linear_weight(torch.randn(256, 256, device="cuda").bfloat16())
 names = ["entry", "prologue done", "first TMA issued", "first data landed", "last MMA committed", "accumulator ready (epi)",
          "epilogue stores issued", "exit", "c0 tmem loaded", "c0 math+sts done", "c0 fence done", "c0 store issued",
-         "producer: tile decoded", "producer: first stage free", "producer: expect_tx done", "producer: first TMA (A) issued"]
+         "c1 tmem loaded", "c1 math+sts done", "c1 fence done", "c1 store issued"]
 for rep in range(2):
     if mode != "hot":
         flush.zero_()

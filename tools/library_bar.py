@@ -193,8 +193,9 @@ def attention_rows():
 
 def norm_rows():
     R = 8
-    for name, B, HW, C in (("GroupNorm(32)+SiLU 320ch @128^2", 2, 16384, 320), ("GroupNorm(32)+SiLU 1280ch @32^2", 2, 1024, 1280),
-                           ("GroupNorm(32)+SiLU 128ch @1024^2 (VAE)", 1, 1 << 20, 128)):
+    for name, B, HW, C in (("GroupNorm(32)+SiLU 320ch @128^2", 2, 16384, 320), ("GroupNorm(32)+SiLU 640ch @64^2", 2, 4096, 640),
+                           ("GroupNorm(32)+SiLU 1280ch @64^2", 2, 4096, 1280), ("GroupNorm(32)+SiLU 1280ch @32^2", 2, 1024, 1280),
+                           ("GroupNorm(32)+SiLU 2560ch @32^2", 2, 1024, 2560), ("GroupNorm(32)+SiLU 128ch @1024^2 (VAE)", 1, 1 << 20, 128)):
         xs = [rnd(B * HW, C) for _ in range(R)]
         gam, bet = rnd(C), rnd(C)
         ours = timed(lambda i: ops.group_norm(xs[i % R], batch=B, hw=HW, groups=32, eps=1e-5, gamma=gam, beta=bet, silu=True))
