@@ -43,6 +43,7 @@ class AttentionArgs(C.Structure):
         ("v_row_stride", C.c_int64), ("v_batch_stride", C.c_int64),
         ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
         ("scale", C.c_float), ("dtype", C.c_int32), ("nq_override", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -111,6 +112,8 @@ def lib():
         _lib.b200_conv_gemm_row_stats_parts.argtypes = [C.c_void_p]
         _lib.b200_group_norm_launches.restype = C.c_int32
         _lib.b200_group_norm_launches.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        _lib.b200_attention_workspace_bytes.restype = C.c_int64
+        _lib.b200_attention_workspace_bytes.argtypes = [C.c_int32] * 5
         _lib.b200_group_norm_workspace_bytes.restype = C.c_int64
         _lib.b200_group_norm_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         I32, I64, F32, VP = C.c_int32, C.c_int64, C.c_float, C.c_void_p

@@ -426,6 +426,7 @@ int launch_attention64_pipe(const b200_attention_args* a, cudaStream_t st);
 int init_attention64();
 bool attention64_enabled();
 int launch_attention64(const b200_attention_args* a, cudaStream_t st);
+long long attention64_workspace_bytes(long long tiles, int kv_halves);
 
 template <int HD, int NQ, bool FP16, int POLY = 1>
 static int attn_set_attr() {
@@ -464,6 +465,12 @@ static int attn_launch(const AttnParams& prm, int grid, cudaStream_t st) {
 }  // namespace b200
 
 extern "C" {
+
+int64_t b200_attention_workspace_bytes(int32_t batch, int32_t heads, int32_t sq, int32_t sk, int32_t head_dim) {
+  using namespace b200;
+  if (head_dim != 64 || batch <= 0 || heads <= 0 || sq <= 0 || sk <= 0 || !attention64_enabled()) return 0;
+  return attention64_workspace_bytes(static_cast<long long>(batch) * heads * ((sq + 127) / 128), (sk + 63) / 64);
+}
 
 int b200_attention(const b200_attention_args* a, void* stream) {
   using namespace b200;

@@ -23,8 +23,13 @@
 //  * S(h+2) is issued as soon as every softmax thread holds S(h) in registers (s_free), i.e. AHEAD of P(h) V(h): with the
 //    scores read one step early, waiting for P(h) first left the softmax without scores at the start of every step
 //    (measured: 248 us -> 153 us at 4096 tokens).
-//  (A split of one tile's keys over 2 / 4 CTAs with a merge through a global workspace was built and measured: correct, but
-//  parking 33 KB per CTA and the fence + ticket cost ~5 us per CTA, more than the fuller last wave returned - removed.)
+//  * TAIL SPLIT: with one query tile per CTA and 2 CTAs per SM the SDXL shapes quantise badly - 640 tiles on 296 slots are
+//    2.16 waves (4096 tokens), 320 tiles 1.08 waves (1024 tokens) - and the last, nearly empty wave costs as much as a full
+//    one.  The tiles of that last wave are therefore split along the keys over `split` CTAs each (so that they fill the
+//    machine once more, for 1/split of a tile's time); every part parks its unnormalised O, m and l in a workspace and the
+//    part that arrives last (ticket counter per tile) merges all parts IN INDEX ORDER - the result does not depend on which
+//    part that is.  Splitting EVERY tile was measured earlier and does not pay (the merge costs ~3-5 us per CTA, more than a
+//    fuller last wave returns); splitting the tail pays that once.
 // Numerics are those of attention.cu: online softmax in the exp2 domain, lazy rescale (the running max only moves on > 2^8
 // growth), P rounded to 16 bit for the P V GEMM, fp32 row sums of the unrounded P.
 #include <math.h>
@@ -48,6 +53,10 @@ struct Attn64Params {
   int q_tiles;           // ceil(sq / 128)
   int kv_halves;         // ceil(sk / 64)
   float scale_log2;
+  // tail split: CTAs [0, n_whole) take whole tiles; CTA n_whole + u takes part u % split of tile n_whole + u / split
+  int n_whole, split;
+  float* ws_part;        // [tail tiles][split][64 * 128 O (column-major: [col][row]) + 128 m + 128 l] fp32
+  int* ws_ticket;        // [tail tiles], zero between launches (the merging CTA resets it)
 };
 
 struct Attn64Cfg {
@@ -62,7 +71,8 @@ struct Attn64Cfg {
 };
 
 // POLY: score pairs (of every 8) whose exponentials go to the FMA-pipe polynomial instead of MUFU (0..3)
-template <bool FP16, int POLY>
+// SPLIT: the launch has tail parts (see TAIL SPLIT above); the plain instance keeps the key range compile-time [0, kv_halves)
+template <bool FP16, int POLY, bool SPLIT>
 __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(const __grid_constant__ Attn64Params p) {
   using Cfg = Attn64Cfg;
   using H = Half16<FP16>;
@@ -85,19 +95,26 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
   uint64_t* s_free = pv_done + 2;        // [2]  every softmax thread holds S(h) in registers: the buffer can take S(h+2): 128 arrivals
   uint64_t* o_full = s_free + 2;         // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
+  int* ticket_s = reinterpret_cast<int*>(tmem_ptr + 1);  // tail split: this part's arrival number, broadcast to the softmax warps
   static_assert((1 + 2 * KS + 2 * VS + 2 + 2 + 2 + 2 + 1) * 8 + 8 <= 256, "barrier area");
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
+  int tile = blockIdx.x, part = 0;
+  const bool is_part = SPLIT && tile >= p.n_whole;
+  if (is_part) {
+    const int u = tile - p.n_whole;
+    tile = p.n_whole + u / p.split;
+    part = u - (u / p.split) * p.split;
+  }
   const int qt = tile % p.q_tiles;
   const int bh = tile / p.q_tiles;
   const int head = bh % p.heads;
   const int b = bh / p.heads;
   const int q_row0 = qt * 128;
-  constexpr int h_begin = 0;
-  const int h_end = p.kv_halves;
-  const int n_half = h_end;
+  const int h_begin = (SPLIT && is_part) ? (part * p.kv_halves) / p.split : 0;
+  const int h_end = (SPLIT && is_part) ? ((part + 1) * p.kv_halves) / p.split : p.kv_halves;
+  const int n_half = h_end - h_begin;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.q_map);
@@ -381,15 +398,68 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
     step(sb, sa, h, ModeFinal{});
     float l = (l0 + l1) + (l2 + l3);
 
-    // ---- epilogue: O / l -> global
     mbar_wait_warp(o_full, 0);
     tc_fence_after();
-    {
-      const int qrow = q_row0 + row;
+    const int qrow = q_row0 + row;
+    typename H::T* const orow = static_cast<typename H::T*>(p.o) + static_cast<long long>(b) * p.o_batch_stride +
+                                static_cast<long long>(qrow) * p.o_row_stride + head * 64;
+    if (SPLIT && is_part) {
+      // ---- one part of a split tile: park (O, m, l), take a ticket; the last part to arrive merges all of them
+      constexpr int PART_FLOATS = 64 * 128 + 256;
+      float* const tile_ws = p.ws_part + static_cast<size_t>(tile - p.n_whole) * p.split * PART_FLOATS;
+      float* const mine = tile_ws + static_cast<size_t>(part) * PART_FLOATS;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(o_t + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) mine[(c * 32 + k) * 128 + row] = __uint_as_float(v[k]);  // [col][row]: coalesced over the warp
+      }
+      mine[64 * 128 + row] = m;
+      mine[64 * 128 + 128 + row] = l;
+      __threadfence();
+      named_bar_sync(1, 128);  // the 128 softmax threads: every row of this part is fenced before the ticket is taken
+      if (threadIdx.x == 128) *ticket_s = atomicAdd(&p.ws_ticket[tile - p.n_whole], 1);
+      named_bar_sync(1, 128);
+      if (*ticket_s == p.split - 1) {
+        __threadfence();
+        // merge in part order (NOT arrival order): out = sum_i 2^(m_i - M) O_i / sum_i 2^(m_i - M) l_i, M = max_i m_i
+        float M = -INFINITY;
+        for (int i = 0; i < p.split; ++i) M = fmaxf(M, __ldcg(tile_ws + static_cast<size_t>(i) * PART_FLOATS + 64 * 128 + row));
+        float acc[64];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) acc[k] = 0.f;
+        float L = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < p.split; ++i) {
+          const float* src = tile_ws + static_cast<size_t>(i) * PART_FLOATS;
+          float t[64];
+#pragma unroll
+          for (int k = 0; k < 64; ++k) t[k] = __ldcg(src + k * 128 + row);  // all 64 loads in flight: one L2 round trip per part
+          const float wgt = fast_ex2(__ldcg(src + 64 * 128 + row) - M);
+          L = fmaf(wgt, __ldcg(src + 64 * 128 + 128 + row), L);
+#pragma unroll
+          for (int k = 0; k < 64; ++k) acc[k] = fmaf(wgt, t[k], acc[k]);
+        }
+        if (qrow < p.sq) {
+          const float inv_l = 1.0f / L;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            uint4 o;
+            o.x = H::pack(acc[g * 8 + 0] * inv_l, acc[g * 8 + 1] * inv_l);
+            o.y = H::pack(acc[g * 8 + 2] * inv_l, acc[g * 8 + 3] * inv_l);
+            o.z = H::pack(acc[g * 8 + 4] * inv_l, acc[g * 8 + 5] * inv_l);
+            o.w = H::pack(acc[g * 8 + 6] * inv_l, acc[g * 8 + 7] * inv_l);
+            *reinterpret_cast<uint4*>(orow + g * 8) = o;
+          }
+        }
+        if (threadIdx.x == 128) p.ws_ticket[tile - p.n_whole] = 0;  // ready for the next launch (stream order)
+      }
+    } else {
+      // ---- epilogue: O / l -> global
       const bool valid = qrow < p.sq;
       const float inv_l = 1.0f / l;
-      typename H::T* orow = static_cast<typename H::T*>(p.o) + static_cast<long long>(b) * p.o_batch_stride +
-                            static_cast<long long>(qrow) * p.o_row_stride + head * 64;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
@@ -418,16 +488,18 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
   }
 }
 
-template <bool FP16, int POLY>
+template <bool FP16, int POLY, bool SPLIT>
 static cudaError_t a64_attr() {
-  return cudaFuncSetAttribute(attention64_kernel<FP16, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Cfg::SMEM_BYTES);
+  return cudaFuncSetAttribute(attention64_kernel<FP16, POLY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Cfg::SMEM_BYTES);
 }
 
 int init_attention64() {
-  cudaError_t e = a64_attr<false, 0>();
-  if (e == cudaSuccess) e = a64_attr<true, 0>();
-  if (e == cudaSuccess) e = a64_attr<false, 1>();
-  if (e == cudaSuccess) e = a64_attr<true, 1>();
+  cudaError_t e = a64_attr<false, 0, false>();
+  if (e == cudaSuccess) e = a64_attr<true, 0, false>();
+  if (e == cudaSuccess) e = a64_attr<false, 1, false>();
+  if (e == cudaSuccess) e = a64_attr<true, 1, false>();
+  if (e == cudaSuccess) e = a64_attr<false, 1, true>();
+  if (e == cudaSuccess) e = a64_attr<true, 1, true>();
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention (head_dim 64) smem attr: %s", cudaGetErrorString(e));
   return 0;
 }
@@ -435,6 +507,49 @@ int init_attention64() {
 bool attention64_enabled() {
   static const bool on = !(getenv("B200_ATTN_V2") && atoi(getenv("B200_ATTN_V2")) == 0);
   return on;
+}
+
+// ---- tail split (see the header comment).  slots = CTAs resident at once (2 per SM).
+struct Attn64Split {
+  int tail;   // tiles of the last, partial wave
+  int split;  // parts per tail tile (1 = no split)
+};
+constexpr int kAttn64TicketBytes = 4096;  // up to 1024 tail tiles (there are < 2 * SMs of them)
+constexpr long long kAttn64PartBytes = (64 * 128 + 256) * 4;
+
+static int attention64_slots() {
+  static const int slots = [] {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return 2 * sms;
+  }();
+  return slots;
+}
+
+static Attn64Split attention64_split(long long tiles, int kv_halves) {
+  static const bool off = getenv("B200_ATTN_TAIL_SPLIT") && atoi(getenv("B200_ATTN_TAIL_SPLIT")) == 0;  // tuning / test knob
+  Attn64Split r{0, 1};
+  const int slots = attention64_slots();
+  const int tail = static_cast<int>(tiles % slots);
+  // measured on B200 (tools/bench_attention.py): 4096 keys (64 halves, 48 tail tiles 6-way) 155.8 -> 141.1 us; 1024 keys (16 halves,
+  // 24 tail tiles 8-way) 30.5 -> 31.5 us: a CTA that is alone on its SM runs ~1.7x faster than one of a pair, so the last wave is
+  // far cheaper than a full one and only long tiles repay a part's ~4 us of start-up, parking and merging
+  static const int min_halves = getenv("B200_ATTN_SPLIT_MIN_HALVES") ? atoi(getenv("B200_ATTN_SPLIT_MIN_HALVES")) : 32;
+  if (off || tail == 0 || kv_halves < min_halves || tail * 4 > kAttn64TicketBytes) return r;
+  int s = slots / tail;
+  if (s > kv_halves / 2) s = kv_halves / 2;  // at least two 64-key halves per part
+  if (s > 8) s = 8;
+  // a part costs its share of the tile plus ~4 us of start-up, parking and merging (a 64-key step is ~0.75 us): split only when
+  // the tail wave gets clearly shorter
+  if (s < 2 || 0.75 * kv_halves * (1.0 - 1.0 / s) < 8.0) return r;
+  r.tail = tail;
+  r.split = s;
+  return r;
+}
+
+long long attention64_workspace_bytes(long long tiles, int kv_halves) {
+  const Attn64Split sp = attention64_split(tiles, kv_halves);
+  return sp.split > 1 ? kAttn64TicketBytes + static_cast<long long>(sp.tail) * sp.split * kAttn64PartBytes : 0;
 }
 
 // head_dim 64, one query tile per CTA; arguments already validated by b200_attention
@@ -464,17 +579,30 @@ int launch_attention64(const b200_attention_args* a, cudaStream_t st) {
   prm.kv_halves = (a->sk + 63) / 64;
   const float scale = a->scale > 0.f ? a->scale : 0.125f;
   prm.scale_log2 = scale * 1.4426950408889634f;
-  const long long grid_ll = static_cast<long long>(a->batch) * a->heads * prm.q_tiles;
-  B200_CHECK_ARG(grid_ll < (1ll << 31), "attention: grid too large");
+  const long long tiles = static_cast<long long>(a->batch) * a->heads * prm.q_tiles;
+  B200_CHECK_ARG(tiles < (1ll << 30), "attention: grid too large");
+  const Attn64Split sp = attention64_split(tiles, prm.kv_halves);
+  long long grid_ll = tiles;
+  prm.n_whole = static_cast<int>(tiles);
+  prm.split = 1;
+  if (sp.split > 1 && a->workspace != nullptr && a->workspace_bytes >= attention64_workspace_bytes(tiles, prm.kv_halves)) {
+    B200_CHECK_ARG((reinterpret_cast<uintptr_t>(a->workspace) & 15u) == 0, "attention: workspace not 16-byte aligned");
+    prm.n_whole = static_cast<int>(tiles - sp.tail);
+    prm.split = sp.split;
+    prm.ws_ticket = static_cast<int*>(a->workspace);
+    prm.ws_part = reinterpret_cast<float*>(static_cast<uint8_t*>(a->workspace) + kAttn64TicketBytes);
+    grid_ll = prm.n_whole + static_cast<long long>(sp.tail) * sp.split;
+  }
   const bool fp16 = a->dtype == B200_DTYPE_FP16;
   // measured on B200 (tools/bench_attention.py, 4096 / 1024 tokens): POLY 0 -> 154.8 / 30.0 us, 1 -> 146.5 / 28.7 us, 3 -> 154.7 / 30.1 us
   static const int poly = getenv("B200_ATTN_POLY") ? atoi(getenv("B200_ATTN_POLY")) : 1;  // tuning knob: 0 or 1
   const dim3 grid(static_cast<unsigned>(grid_ll)), block(Attn64Cfg::THREADS);
   cudaError_t e;
-#define B200_A64(P) (fp16 ? launch_pdl(attention64_kernel<true, P>, grid, block, Attn64Cfg::SMEM_BYTES, st, prm) \
-                          : launch_pdl(attention64_kernel<false, P>, grid, block, Attn64Cfg::SMEM_BYTES, st, prm))
-  if (poly >= 1) e = B200_A64(1);
-  else e = B200_A64(0);
+#define B200_A64(P, S) (fp16 ? launch_pdl(attention64_kernel<true, P, S>, grid, block, Attn64Cfg::SMEM_BYTES, st, prm) \
+                             : launch_pdl(attention64_kernel<false, P, S>, grid, block, Attn64Cfg::SMEM_BYTES, st, prm))
+  if (prm.split > 1) e = B200_A64(1, true);
+  else if (poly >= 1) e = B200_A64(1, false);
+  else e = B200_A64(0, false);
 #undef B200_A64
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention (head_dim 64) launch: %s", cudaGetErrorString(e));
   return 0;

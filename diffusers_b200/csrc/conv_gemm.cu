@@ -58,6 +58,9 @@ struct ConvGemmParams {
   int cm;                // 1, or 2 = CTA pair (cta_group::2 MMA over two consecutive m tiles)
   int m_groups;          // ceil(m_tiles / cm)
   int total_groups;      // n_tiles * m_groups
+  // n / d as (n * M) >> 40 with M = 2^40 / d + 1 (exact while n * d < 2^40: tile counts are far below that): the three divisions of
+  // decode_tile sit on the start-up path of every role of every launch
+  unsigned long long div_m_groups, div_per_img, div_tiles_w;
   int N;  // rows of w
   int num_taps, nsrc;
   int chunks[2];
@@ -73,10 +76,13 @@ struct ConvGemmParams {
   int out_fp32;  // y is float (attention scores of the unfused head_dim-512 path)
   int tma_store; // epilogue stages 32-column slabs in smem and writes them with TMA (needs vec_ok, 16-bit y)
   int tma_res;   // residual tiles are staged by the loader warp (needs tma_store, 16-bit residual, no GEGLU)
+  int seeded;    // bias (+ residual) are written into the TMEM accumulator BEFORE the tile's MMAs (which then all accumulate):
+                 // the epilogue warps do it while they would otherwise wait for the main loop, and the drain is LDTM -> scale ->
+                 // pack -> store only (plain bias / residual / folded-LayerNorm epilogues with the TMA store)
   const uint8_t* pf_ptr;  // next launch's weights: pulled into L2 while this launch runs (nullptr = none)
   long long pf_bytes;
   int dbg_mode;  // tuning: 1 = producer stops loading after the first pipeline round, 2 = MMA thread issues no MMAs
-  long long* dbg; // optional [grid][16] clock64 timestamps (tuning aid)
+  long long* dbg; // optional [grid][32] clock64 timestamps (tuning aid)
   // LayerNorm folded into the consuming GEMM (see b200_conv_gemm_args)
   float2* stats_out;       // producer: [M][stats_parts] (sum, sumsq) of the rounded outputs, one pair per (n tile, epilogue half)
   int stats_parts;         // 2 * n_tiles
@@ -113,12 +119,12 @@ struct TileCoord {
 // past the end: its loads are all out of bounds -> zeros, and it stores nothing)
 __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int g, int rank, int BN) {
   TileCoord c;
-  int n_blk = g / p.m_groups;
+  int n_blk = static_cast<int>((static_cast<unsigned long long>(g) * p.div_m_groups) >> 40);
   int m = (g - n_blk * p.m_groups) * p.cm + rank;
   int per_img = p.tiles_w * p.tiles_h;
-  c.img = m / per_img;
+  c.img = static_cast<int>((static_cast<unsigned long long>(m) * p.div_per_img) >> 40);
   int r = m - c.img * per_img;
-  int th = r / p.tiles_w;
+  int th = static_cast<int>((static_cast<unsigned long long>(r) * p.div_tiles_w) >> 40);
   int tw = r - th * p.tiles_w;
   c.h0 = th * p.bh;
   c.w0 = tw * p.bw;
@@ -187,23 +193,23 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   const int cluster = cm > 1 ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
   const int n_clusters = cm > 1 ? static_cast<int>(num_clusters_x()) : static_cast<int>(gridDim.x);
 
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.nsrc; ++s) prefetch_tensormap(&p.a_map[s * 4]);
-    prefetch_tensormap(&p.w_map);
-    if (p.tma_store) prefetch_tensormap(&p.y_map);
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], PAIR ? 2 : 1);  // pair: one expect_tx arrive from each CTA's producer (leader's copy is used)
-      mbar_init(&empty_bar[i], 1);
+  if (warp == 0) {
+    // one barrier per lane (the 2 * STAGES + 4 + 2 * NSLAB <= 32 barriers are contiguous): a single lane initialising all of
+    // them costs one serialised shared-memory operation per barrier at the head of every launch
+    constexpr int NBAR = 2 * STAGES + 4 + 2 * Cfg::NSLAB;
+    static_assert(NBAR <= 32, "one barrier per lane");
+    if (lane < NBAR) {
+      uint32_t count = 1;
+      if (lane < STAGES) count = PAIR ? 2 : 1;  // full: pair = one expect_tx arrive from each CTA's producer (the leader's copy is used)
+      if (lane >= 2 * STAGES + 2 && lane < 2 * STAGES + 4) count = PAIR ? 16 : 8;  // tempty: 8 epilogue warps; pair: those of both CTAs
+      mbar_init(&full_bar[lane], count);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], PAIR ? 16 : 8);  // 8 epilogue warps; pair: the leader waits for those of both CTAs
+    if (lane == 0) {
+      for (int s = 0; s < p.nsrc; ++s) prefetch_tensormap(&p.a_map[s * 4]);
+      prefetch_tensormap(&p.w_map);
+      if (p.tma_store) prefetch_tensormap(&p.y_map);
+      if (p.tma_res) prefetch_tensormap(&p.r_map);
     }
-    for (int i = 0; i < Cfg::NSLAB; ++i) {
-      mbar_init(&rfull_bar[i], 1);
-      mbar_init(&sfree_bar[i], 1);
-    }
-    if (p.tma_res) prefetch_tensormap(&p.r_map);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -221,13 +227,14 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();  // everything above overlapped the previous kernel's tail; no global access before this point
-  long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
-  if (dbg && threadIdx.x == 0) {
-    dbg[0] = t_entry;
-    dbg[1] = clock64();
-  }
+  // (the marks of thread 0 are kept in registers and stored at the very end: a store here makes the compiler peel lane 0 of
+  // the producer warp onto its own path, and the timeline then measures that divergence)
+  long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 32 : nullptr;
+  const long long t_prologue = clock64();
+  long long t_decoded = 0, t_stage_free = 0;
 
   const int dbg_mode = p.dbg_mode;
+  const bool seeded = !GEGLU && p.seeded != 0;
   if (warp == 0) {
     // ===================== TMA producer (whole warp, one elected lane issues) =====================
     int stage = 0;
@@ -235,6 +242,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     const int b_rows = BN / cm;  // rows of the weight tile this CTA fetches (pair: its half)
     for (int g = cluster; g < p.total_groups; g += n_clusters) {
       TileCoord tc = decode_tile(p, g, rank, BN);
+      if (g == cluster) t_decoded = clock64();
       int kc = 0;
       for (int tap = 0; tap < p.num_taps; ++tap) {
         const int mp = p.tap_map[tap];
@@ -244,6 +252,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           const CUtensorMap* am = &p.a_map[s * 4 + mp];
           for (int cc = 0; cc < p.chunks[s]; ++cc) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);  // the MMAs that read this stage (in both CTAs) have retired
+            if (kc == 0 && g == cluster) t_stage_free = clock64();
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             const bool skip_loads = dbg_mode == 1 && (kc >= STAGES || g != cluster);  // tuning: MMA rate alone
             if (elect_one()) {
@@ -285,7 +294,8 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       for (int g = cluster; g < p.total_groups; g += n_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        // seeded: the epilogue warps complete phase it/2 of tempty when the buffer is drained AND holds the tile's bias/residual
+        mbar_wait(&tempty_bar[acc], seeded ? acc_phase : (acc_phase ^ 1u));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -301,9 +311,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               for (int k = 0; k < 4; ++k) {
                 // +32 B per UMMA_K=16 step inside the 128 B swizzle atom -> +2 in the (addr>>4) field
                 if (PAIR)
-                  umma_ss2(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                  umma_ss2(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (seeded || (kc | k) != 0) ? 1u : 0u);
                 else
-                  umma_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
+                  umma_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (seeded || (kc | k) != 0) ? 1u : 0u);
               }
             }
             if (PAIR)
@@ -397,6 +407,76 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     uint32_t k = 0;           // running chunk count over all tiles of this CTA (slab k % NSLAB, half k & 1)
     uint32_t prev_k = 0, prev2_k = 0;  // issuer: chunks of this half's (up to two) stores still in flight, newest first
     bool have_prev = false, have_prev2 = false;
+
+    // folded LayerNorm: a row's rstd from the producer's partial sums (fixed summation order).  All loads of a batch are issued
+    // before the first use (one L2 round trip per 16 parts).
+    auto row_rstd = [&](long long pix) {
+      const float4* sp = reinterpret_cast<const float4*>(ln_stats + pix * p.ln_parts);  // ln_parts is even: 16-byte rows
+      const int n4 = p.ln_parts >> 1;
+      float s0 = 0.f, s1 = 0.f;
+      for (int i0 = 0; i0 < n4; i0 += 8) {
+        float4 t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = (i0 + i < n4) ? sp[i0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s0 += t[i].x + t[i].z;
+          s1 += t[i].y + t[i].w;
+        }
+      }
+      const float mean = s0 * p.ln_inv_k;
+      const float var = fmaxf(fmaf(-mean, mean, s1 * p.ln_inv_k), 0.0f);
+      return rsqrtf(var + p.ln_eps);
+    };
+    auto tile_chunks = [&](const TileCoord& t) {  // 32-column chunks of the tile inside the output
+      const int left = n_limit - (GEGLU ? (t.n0 >> 1) : t.n0);
+      return left >= (GEGLU ? BN / 2 : BN) ? (GEGLU ? BN / 64 : BN / 32) : (left <= 0 ? 0 : (left + 31) >> 5);
+    };
+    // seeded launches: accumulator buffer `acc2` <- bias / rstd + residual for tile g2 (chunks of this warp only: the ones it
+    // drains, and - two tiles earlier in the same buffer - has just drained), then the arrival the MMA warp waits for.
+    // k2 = running chunk count at the start of that tile.
+    auto seed_tile = [&](int g2, int acc2, uint32_t k2) {
+      const TileCoord t2 = decode_tile(p, g2, rank, BN);
+      const int oh2 = t2.h0 + rh, ow2 = t2.w0 + rw;
+      const bool valid2 = t2.img < p.batch && oh2 < p.Ho && ow2 < p.Wo;
+      const long long pix2 = (static_cast<long long>(t2.img) * p.Ho + oh2) * p.Wo + ow2;
+      const float inv = (ln_stats != nullptr && valid2) ? 1.0f / row_rstd(pix2) : 1.0f;  // y = rstd * acc: the bias goes in as bias / rstd
+      const typename H::T* rrow = (residual != nullptr && valid2) ? residual + pix2 * p.ldr + t2.n0 : nullptr;
+      const uint32_t t_row2 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc2 * Cfg::ACC_STRIDE;
+      const int nch = tile_chunks(t2);
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        if (((k2 + c) & 1u) != static_cast<uint32_t>(half)) continue;
+        uint32_t sv[32];
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          const uint4 b4 = bias ? *reinterpret_cast<const uint4*>(bias + t2.n0 + c * 32 + j8 * 8) : make_uint4(0, 0, 0, 0);
+          const uint4 r4 = rrow ? *reinterpret_cast<const uint4*>(rrow + c * 32 + j8 * 8) : make_uint4(0, 0, 0, 0);
+          const float2 b0 = H::unpack(b4.x), b1 = H::unpack(b4.y), b2 = H::unpack(b4.z), b3 = H::unpack(b4.w);
+          const float2 r0 = H::unpack(r4.x), r1 = H::unpack(r4.y), r2 = H::unpack(r4.z), r3 = H::unpack(r4.w);
+          sv[j8 * 8 + 0] = __float_as_uint(fmaf(b0.x, inv, r0.x)); sv[j8 * 8 + 1] = __float_as_uint(fmaf(b0.y, inv, r0.y));
+          sv[j8 * 8 + 2] = __float_as_uint(fmaf(b1.x, inv, r1.x)); sv[j8 * 8 + 3] = __float_as_uint(fmaf(b1.y, inv, r1.y));
+          sv[j8 * 8 + 4] = __float_as_uint(fmaf(b2.x, inv, r2.x)); sv[j8 * 8 + 5] = __float_as_uint(fmaf(b2.y, inv, r2.y));
+          sv[j8 * 8 + 6] = __float_as_uint(fmaf(b3.x, inv, r3.x)); sv[j8 * 8 + 7] = __float_as_uint(fmaf(b3.y, inv, r3.y));
+        }
+        tmem_st32(t_row2 + c * 32, sv);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR)
+          mbar_arrive_cluster(leader_addr(&tempty_bar[acc2]));
+        else
+          mbar_arrive(&tempty_bar[acc2]);
+      }
+      return nch;
+    };
+    if (seeded && cluster < p.total_groups) {  // both accumulator buffers are free at the start: seed the first two tiles
+      const int n0c = seed_tile(cluster, 0, 0);
+      if (cluster + n_clusters < p.total_groups) seed_tile(cluster + n_clusters, 1, static_cast<uint32_t>(n0c));
+    }
+
     int it = 0;
     for (int g = cluster; g < p.total_groups; g += n_clusters, ++it) {
       const int acc = it & 1;
@@ -414,29 +494,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
       const int ycol0 = GEGLU ? (tc.n0 >> 1) : tc.n0;
 
-      // folded LayerNorm: this row's rstd from the producer's partial sums (fixed summation order).  All loads of a batch are
-      // issued before the first use (one L2 round trip per 16 parts); runs before the accumulator is needed.
-      float ln_r = 1.0f;
-      if (ln_stats != nullptr && valid) {
-        const float4* sp = reinterpret_cast<const float4*>(ln_stats + pix * p.ln_parts);  // ln_parts is even: 16-byte rows
-        const int n4 = p.ln_parts >> 1;
-        float s0 = 0.f, s1 = 0.f;
-        for (int i0 = 0; i0 < n4; i0 += 8) {
-          float4 t[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) t[i] = (i0 + i < n4) ? sp[i0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            s0 += t[i].x + t[i].z;
-            s1 += t[i].y + t[i].w;
-          }
-        }
-        const float mean = s0 * p.ln_inv_k;
-        const float var = fmaxf(fmaf(-mean, mean, s1 * p.ln_inv_k), 0.0f);
-        ln_r = rsqrtf(var + p.ln_eps);
-      }
+      const float ln_r = (ln_stats != nullptr && valid) ? row_rstd(pix) : 1.0f;  // (runs before the accumulator is needed)
       float st_s = 0.f, st_q = 0.f;  // producer side of a folded LayerNorm: sums of this thread's ROUNDED outputs of the tile
-      if (bias != nullptr && real_tile && lane * 64 < BN && tc.n0 + lane * 64 < p.N) prefetch_l1(bias + tc.n0 + lane * 64);  // the tile's bias: L1 hits in the chunk loop
+      if (!lean && bias != nullptr && real_tile && lane * 64 < BN && tc.n0 + lane * 64 < p.N) prefetch_l1(bias + tc.n0 + lane * 64);  // the tile's bias: L1 hits in the chunk loop
 
       mbar_wait_warp(&tfull_bar[acc], (it >> 1) & 1u);
       tc_fence_after();
@@ -444,7 +504,6 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
 
       uint32_t v[32];
-      bool preloaded = false;
 #pragma unroll 1
       for (int c = 0; c < OUT_COLS / 32; ++c, ++k) {
         const int yc0 = ycol0 + c * 32;
@@ -452,13 +511,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         if ((k & 1u) != static_cast<uint32_t>(half)) continue;
         const bool chunk_vec = p.vec_ok && (yc0 + 32 <= n_limit);
         const int bcol = GEGLU ? (tc.n0 + c * 32) : yc0;
-        if (!preloaded) tmem_ld32(t_row + c * 32, v);  // (else issued during the previous chunk's store phase)
+        tmem_ld32(t_row + c * 32, v);  // (TMEM reads are cheap: 22 cycles per x32 load and warp, ~55 cycles latency - tools/micro/tmem_bw.cu)
         uint32_t gv[32];
         if (GEGLU) tmem_ld32(t_row + BN / 2 + c * 32, gv);
         uint4 bc[4];  // bias of this chunk (same for every row: L1 hits after the first warp)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          bc[j] = (chunk_vec && bias) ? *reinterpret_cast<const uint4*>(bias + bcol + j * 8) : make_uint4(0, 0, 0, 0);
+          bc[j] = (!lean && chunk_vec && bias) ? *reinterpret_cast<const uint4*>(bias + bcol + j * 8) : make_uint4(0, 0, 0, 0);
         uint8_t* slab = slabs + (k % Cfg::NSLAB) * Cfg::SLAB_BYTES;
         if (tma_store) {
           if (q == 0 && have_prev2) {
@@ -472,33 +531,22 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
           mbar_wait_warp(&rfull_bar[k % Cfg::NSLAB], (k / Cfg::NSLAB) & 1u);  // slab is ours (and holds the residual if any)
         }
+        // marks of the first two rounds of half 0 in the CTA's first tile: 8 + 6 r + {0 slab ready, 1 arithmetic + smem stores done
+        // (includes the wait for the TMEM data), 2 fence + barrier passed, 3 TMA store issued, 4 register rotation done}
+        const bool stamp = dbg && issuer && half == 0 && it == 0 && c < 4;
+        const int sb = 8 + (c >> 1) * 6;
+        if (stamp) dbg[sb] = clock64();
         tmem_wait_ld();
-        const bool stamp = dbg && issuer && it == 0 && c < 2;
-        if (stamp) dbg[8 + c * 4] = clock64();
         if (lean) {
+          // bias and residual are already in the accumulator (seeded launch; a lean launch without them has neither)
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
-            uint4* sp = reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4));
-            float f[8];
-            {  // acc * rstd + bias (rstd = 1 without a folded LayerNorm)
-              float2 t0 = H::unpack(bc[j8].x), t1 = H::unpack(bc[j8].y), t2 = H::unpack(bc[j8].z), t3 = H::unpack(bc[j8].w);
-              f[0] = fmaf(__uint_as_float(v[j8 * 8 + 0]), ln_r, t0.x); f[1] = fmaf(__uint_as_float(v[j8 * 8 + 1]), ln_r, t0.y);
-              f[2] = fmaf(__uint_as_float(v[j8 * 8 + 2]), ln_r, t1.x); f[3] = fmaf(__uint_as_float(v[j8 * 8 + 3]), ln_r, t1.y);
-              f[4] = fmaf(__uint_as_float(v[j8 * 8 + 4]), ln_r, t2.x); f[5] = fmaf(__uint_as_float(v[j8 * 8 + 5]), ln_r, t2.y);
-              f[6] = fmaf(__uint_as_float(v[j8 * 8 + 6]), ln_r, t3.x); f[7] = fmaf(__uint_as_float(v[j8 * 8 + 7]), ln_r, t3.y);
-            }
-            if (tma_res) {  // the residual sits where this thread is about to write its output
-              const uint4 r4 = *sp;
-              float2 t0 = H::unpack(r4.x), t1 = H::unpack(r4.y), t2 = H::unpack(r4.z), t3 = H::unpack(r4.w);
-              f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
-              f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
-            }
             uint4 o;
-            o.x = H::pack(f[0], f[1]);
-            o.y = H::pack(f[2], f[3]);
-            o.z = H::pack(f[4], f[5]);
-            o.w = H::pack(f[6], f[7]);
-            *sp = o;
+            o.x = H::pack(__uint_as_float(v[j8 * 8 + 0]) * ln_r, __uint_as_float(v[j8 * 8 + 1]) * ln_r);
+            o.y = H::pack(__uint_as_float(v[j8 * 8 + 2]) * ln_r, __uint_as_float(v[j8 * 8 + 3]) * ln_r);
+            o.z = H::pack(__uint_as_float(v[j8 * 8 + 4]) * ln_r, __uint_as_float(v[j8 * 8 + 5]) * ln_r);
+            o.w = H::pack(__uint_as_float(v[j8 * 8 + 6]) * ln_r, __uint_as_float(v[j8 * 8 + 7]) * ln_r);
+            *reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4)) = o;
             if (stats_out != nullptr) {
               const float2 r0 = H::unpack(o.x), r1 = H::unpack(o.y), r2 = H::unpack(o.z), r3 = H::unpack(o.w);
               st_s += ((r0.x + r0.y) + (r1.x + r1.y)) + ((r2.x + r2.y) + (r3.x + r3.y));
@@ -578,21 +626,16 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
           epilogue_scalar<GEGLU, FP16>(tv, tg, p, bias, gate_row, rv_row, res_row, y_row, pix, yc0, tc.n0 + c * 32, BN, n_limit);
         }
-        if (stamp) dbg[9 + c * 4] = clock64();
-        // this warp's next chunk (c + 2: the halves alternate) starts its TMEM read now, under the fence / barrier / store below
-        preloaded = false;
-        if (!GEGLU && c + 2 < OUT_COLS / 32 && ycol0 + (c + 2) * 32 < n_limit) {
-          tmem_ld32(t_row + (c + 2) * 32, v);
-          preloaded = true;
-        }
+        if (stamp) dbg[sb + 1] = clock64();
         if (tma_store) {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
           named_bar_sync(bar_id, 128);
+          if (stamp) dbg[sb + 2] = clock64();
           if (q == 0) {
             if (elect_one()) {
               if (real_tile) tma_store_4d(&p.y_map, slab, yc0, tc.w0, tc.h0, tc.img);
               bulk_commit_group();
-              if (stamp) dbg[11 + c * 4] = clock64();
+              if (stamp) dbg[sb + 3] = clock64();
             }
             have_prev2 = have_prev;
             prev2_k = prev_k;
@@ -602,13 +645,18 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         }
       }
       if (stats_out != nullptr && valid) stats_out[pix * p.stats_parts + ((tc.n0 / BN) << 1) + half] = make_float2(st_s, st_q);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (PAIR)
-          mbar_arrive_cluster(leader_addr(&tempty_bar[acc]));
-        else
-          mbar_arrive(&tempty_bar[acc]);
+      if (seeded && g + 2 * n_clusters < p.total_groups) {
+        // this warp's chunks of the buffer are drained: seed them for the tile after next (which ends with the arrival)
+        seed_tile(g + 2 * n_clusters, acc, k + static_cast<uint32_t>(tile_chunks(decode_tile(p, g + n_clusters, rank, BN))));
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR)
+            mbar_arrive_cluster(leader_addr(&tempty_bar[acc]));
+          else
+            mbar_arrive(&tempty_bar[acc]);
+        }
       }
       // (stores still in flight carry over into the next tile: with three slabs per half one is always free for the next
       // tile's first residual chunk, and nobody stalls on a store that has just been issued)
@@ -629,7 +677,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     else
       tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
-  if (dbg && threadIdx.x == 0) dbg[7] = clock64();
+  if (dbg && threadIdx.x == 0) {
+    dbg[0] = t_entry;
+    dbg[1] = t_prologue;
+    dbg[24] = t_decoded;
+    dbg[25] = t_stage_free;
+    dbg[7] = clock64();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -883,6 +937,11 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   prm.n_tiles = cdiv(a->N, bn);
   prm.m_groups = cdiv(prm.m_tiles, cm);
   prm.total_groups = prm.n_tiles * prm.m_groups;
+  B200_CHECK_ARG(static_cast<long long>(prm.total_groups) * prm.m_groups < (1ll << 38) && static_cast<long long>(prm.m_groups) * cm < (1ll << 19),
+                 "conv_gemm: too many tiles (%d groups)", prm.total_groups);
+  prm.div_m_groups = (1ull << 40) / static_cast<unsigned long long>(prm.m_groups) + 1;
+  prm.div_per_img = (1ull << 40) / static_cast<unsigned long long>(prm.tiles_w * prm.tiles_h) + 1;
+  prm.div_tiles_w = (1ull << 40) / static_cast<unsigned long long>(prm.tiles_w) + 1;
 
   // ---- filter taps: which (parity) tensor map and which box shift each tap uses
   int tap = 0;
@@ -988,7 +1047,8 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
     if (r) return r;
   }
 
-  prm.tma_res = (prm.tma_store && a->residual && !a->geglu) ? 1 : 0;
+  prm.seeded = (prm.tma_store && !a->geglu && a->act == B200_ACT_NONE && !a->gate && !a->rowvec && (a->bias || a->residual)) ? 1 : 0;
+  prm.tma_res = (prm.tma_store && a->residual && !a->geglu && !prm.seeded) ? 1 : 0;
   if (prm.tma_res) {
     const uint64_t ldr = static_cast<uint64_t>(a->ldr);
     const uint64_t dims[4] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),

@@ -232,6 +232,23 @@ def pick_tile_n(M, N, geglu=False):
     return int(_lib.lib().b200_conv_gemm_pick_tile_n(M, N, 1 if geglu else 0))
 
 
+_ATTN_WS = {}
+
+
+def _attention_workspace(device, B, heads, Sq, Sk, head_dim):
+    """Scratch of the tail split (b200_attention_args.workspace): one buffer per (device, stream), zeroed once - the kernel
+    leaves its ticket words zero again."""
+    need = int(_lib.lib().b200_attention_workspace_bytes(B, heads, Sq, Sk, head_dim))
+    if need == 0:
+        return None
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _ATTN_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 16 << 20), dtype=torch.uint8, device=device)
+        _ATTN_WS[key] = ws
+    return ws
+
+
 def attention(q, k, v, *, heads, head_dim, scale=None, out=None, nq=0):
     """softmax(q k^T * scale) v.  q [B, Sq, heads*head_dim-wide rows], k/v [B, Sk, ...]: 3-D views whose last
     dim starts at this tensor's first head (row stride / batch stride taken from the view, so slices of a fused
@@ -251,6 +268,9 @@ def attention(q, k, v, *, heads, head_dim, scale=None, out=None, nq=0):
     a.scale = float(scale) if scale is not None else 0.0
     a.dtype = _dtype_code(q)
     a.nq_override = nq
+    ws = _attention_workspace(q.device, B, heads, Sq, Sk, head_dim)
+    if ws is not None:
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     if _PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -100,7 +100,7 @@ typedef struct {
   int32_t tile_n;        /* 0 = auto, else force BN in {32, 64, 96, 128, 160, 192, 256}         */
   int32_t out_fp32;      /* 1: y is float32 [.., ldy] (attention scores of the head_dim-512 path) */
   int32_t cluster_m;     /* 0 = auto, 1 = one CTA per tile, 2 = CTA pairs (cta_group::2) (tuning / tests)   */
-  void* debug_timestamps; /* NULL, or int64 [grid][16] device buffer receiving per-CTA clock64 marks (tuning) */
+  void* debug_timestamps; /* NULL, or int64 [grid][32] device buffer receiving per-CTA clock64 marks (tuning) */
   const void* prefetch;  /* NULL, or device memory (16-byte aligned) to pull into L2 while this launch runs:      */
   int64_t prefetch_bytes; /* the packed weights of the NEXT launch, which would otherwise start DRAM-latency-bound */
   /* ---- nn.LayerNorm folded into the Linear that consumes it (models/attention.py:986,1030,1056 -> attn1.to_q/k/v,
@@ -281,9 +281,17 @@ typedef struct {
   float scale;
   int32_t dtype;
   int32_t nq_override; /* 0 = auto; 1 | 2 = query tiles (of 128 rows) per CTA */
+  /* Optional scratch of >= b200_attention_workspace_bytes(...) bytes, 16-byte aligned, ZERO before its first use and private to
+   * one stream.  With it, head_dim-64 launches whose query tiles do not fill the last wave of CTAs split the tiles of that wave
+   * along the keys and merge the parts in a fixed order (bitwise reproducible; the kernel leaves the ticket words zero again).
+   * NULL / too small: every tile is computed by one CTA.  Same results either way up to fp32 summation order of the merge. */
+  void* workspace;
+  int64_t workspace_bytes;
 } b200_attention_args;
 
 int b200_attention(const b200_attention_args* args, void* stream);
+/* Scratch the shape can use (0 = none; depends on the device's SM count: call after b200_init on the current device). */
+int64_t b200_attention_workspace_bytes(int32_t batch, int32_t heads, int32_t sq, int32_t sk, int32_t head_dim);
 
 /* Unfused attention helpers for head_dim 512 (AutoencoderKL mid-block attention, one head:
  * models/attention_processor.py:2725-2789 via unets/unet_2d_blocks.py:684-698).  TMEM cannot hold a

@@ -119,7 +119,8 @@ def test_weight_prefetch_plan_records_and_replays():
 
 
 HELPERS = {"b200_version", "b200_last_error", "b200_init", "b200_num_sms", "b200_conv_gemm_packed_k", "b200_conv_gemm_pick_tile_n",
-           "b200_group_norm_workspace_bytes", "b200_conv_gemm_row_stats_parts", "b200_group_norm_launches"}
+           "b200_group_norm_workspace_bytes", "b200_conv_gemm_row_stats_parts", "b200_group_norm_launches",
+           "b200_attention_workspace_bytes"}
 
 
 def test_every_compute_entry_point_rejects_null_operands():

@@ -98,6 +98,12 @@ def test_attention_fallback_kernels_still_match():
     _attention_cases_under(dict(B200_ATTN_V2="0", B200_ATTN_PIPE="0"))
 
 
+def test_attention_without_tail_split_still_matches():
+    """The tail split (attention64.cu) is on whenever the caller passes a workspace; B200_ATTN_TAIL_SPLIT=0 computes every
+    tile in one CTA and must pass the same cases."""
+    _attention_cases_under(dict(B200_ATTN_TAIL_SPLIT="0"))
+
+
 def test_group_norm_two_kernel_path_still_matches():
     """b200_group_norm takes the single-pass cluster kernel whenever a (sample, group block) slab fits shared memory; the
     statistics + apply pair (B200_GN_NO_SLAB=1) serves the remaining shapes and must keep passing every case."""

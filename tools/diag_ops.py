@@ -15,6 +15,12 @@ CASES = {
     "attn_d64_sdxl": dict(kind="attn", B=2, H=20, Sq=1024, Sk=1024, D=64),
     "attn_d64_4096": dict(kind="attn", B=2, H=10, Sq=4096, Sk=4096, D=64),
     "attn_d64_cross": dict(kind="attn", B=2, H=20, Sq=1024, Sk=77, D=64, cross=True),
+    # tail split (tiles of >= 32 key halves whose count leaves a partial last wave; attn_d64_4096 above splits 6-way): ragged last
+    # half and ragged last query tile, odd part sizes, fp16, large scores
+    "attn_d64_split_ragged": dict(kind="attn", B=1, H=40, Sq=1000, Sk=2100, D=64),
+    "attn_d64_split_sk3000": dict(kind="attn", B=2, H=20, Sq=1024, Sk=3000, D=64),
+    "attn_d64_split_fp16": dict(kind="attn", B=2, H=20, Sq=1024, Sk=2048, D=64, fp16=True),
+    "attn_d64_split_bigvals": dict(kind="attn", B=1, H=40, Sq=1024, Sk=2048, D=64, qscale=6.0),
     "attn_d64_ragged": dict(kind="attn", B=2, H=3, Sq=200, Sk=333, D=64),
     "attn_d128_1blk": dict(kind="attn", B=1, H=1, Sq=128, Sk=128, D=128),
     "attn_d128_flux": dict(kind="attn", B=1, H=24, Sq=4608, Sk=4608, D=128),

@@ -13,7 +13,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 x = torch.randn(M, K, generator=g, device="cuda").bfloat16()
 w = packing.pack_linear_weight((torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).bfloat16())
 out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-dbg = torch.zeros(148, 16, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(148, 32, dtype=torch.int64, device="cuda")
 print(f"M {M} N {N} K {K} chunks {K // 64} debug_mode {os.environ.get('B200_GEMM_DEBUG_MODE', '0')}")
 for cm in (1, 2):
     for bn in (64, 96, 128, 160, 192, 256):

@@ -15,7 +15,7 @@ w = packing.pack_linear_weight((torch.randn(N, K, generator=g, device="cuda") * 
 b = torch.randn(N, generator=g, device="cuda").bfloat16()
 r = torch.randn(M, N, generator=g, device="cuda").bfloat16()
 out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-dbg = torch.zeros(148, 16, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(148, 32, dtype=torch.int64, device="cuda")
 use_res = os.environ.get('NORES') is None
 if not use_res:
     r = None
@@ -27,8 +27,11 @@ mode = os.environ.get("MODE", "cold")  # cold | hotact (activations in L2, weigh
 xs = torch.randn(256, 256, device="cuda").bfloat16()
 ws = packing.pack_linear_weight(torch.randn(256, 256, device="cuda").bfloat16())
 names = ["entry", "prologue done", "first TMA issued", "first data landed", "last MMA committed", "accumulator ready (epi)",
-         "epilogue stores issued", "exit", "c0 tmem loaded", "c0 math+sts done", "c0 fence done", "c0 store issued",
-         "c1 tmem loaded", "c1 math+sts done", "c1 fence done", "c1 store issued"]
+         "epilogue stores issued", "exit"]
+for rnd_ in range(2):
+    names += [f"half0 round{rnd_}: slab ready", f"half0 round{rnd_}: math+sts done", f"half0 round{rnd_}: fence+barrier passed",
+              f"half0 round{rnd_}: store issued", f"half0 round{rnd_}: rotation done", ""]
+names += [""] * 4 + ["producer: first tile decoded", "producer: first stage free"]
 for rep in range(2):
     if mode != "hot":
         flush.zero_()
@@ -50,8 +53,8 @@ for rep in range(2):
     span = int(d[:, 7].max() - d[:, 0].min())
     print(f"mode {mode}: {d.shape[0]} CTAs; first entry -> last exit {span} cycles (clock64 is per SM: indicative only); "
           f"medians of (t_i - t_entry) in cycles:")
-    for i in range(1, 16):
+    for i in range(1, len(names)):
         v = (d[:, i] - d[:, 0]).float()
         v = v[d[:, i] > 0]
-        if len(v):
+        if len(v) and names[i]:
             print(f"   {names[i]:28s} median {int(v.median()):7d}  min {int(v.min()):7d}  max {int(v.max()):7d}")

@@ -109,6 +109,26 @@ def gemm_rows():
         torch.cuda.empty_cache()
 
 
+def ksweep_rows():
+    """Fixed cost per launch vs cost per K chunk: the one-wave 2048 x 1280 GEMM at growing K (intercept = launch + prologue +
+    first-load latency + epilogue, slope = main loop), with and without the epilogue operands, beside cuBLASLt."""
+    R = 8
+    M, N = 2048, 1280
+    for K in (64, 320, 640, 1280, 2560, 5120):
+        xs = [rnd(M, K) for _ in range(R)]
+        ws = [rnd(N, K, sc=K ** -0.5) for _ in range(R)]
+        pw = [packing.pack_linear_weight(w) for w in ws]
+        b = rnd(N)
+        rs = [rnd(M, N) for _ in range(R)]
+        plain = timed(lambda i: ops.linear(xs[i % R], pw[i % R], N))
+        bias = timed(lambda i: ops.linear(xs[i % R], pw[i % R], N, bias=b))
+        full = timed(lambda i: ops.linear(xs[i % R], pw[i % R], N, bias=b, residual=rs[i % R]))
+        libs = dict(cublaslt_no_bias=safe(lambda i: F.linear(xs[i % R], ws[i % R])), cublaslt_bias=safe(lambda i: F.linear(xs[i % R], ws[i % R], b)))
+        row("ksweep linear+bias+residual", f"{M}x{N}x{K}", 2.0 * M * N * K, full, libs, note=f"ours without operands {plain:.2f} us, bias only {bias:.2f} us")
+        del xs, ws, pw, rs
+        torch.cuda.empty_cache()
+
+
 def lnfold_rows():
     """The folded-LayerNorm variants of the three dominant transformer GEMMs next to their plain forms and to the LayerNorm
     kernel they replace (this repo only: the reference has no such fusion)."""
@@ -230,7 +250,7 @@ if __name__ == "__main__":
     print(f"# {torch.cuda.get_device_name(0)}; torch {torch.__version__}; cudnn {torch.backends.cudnn.version()}", flush=True)
     with torch.no_grad():
         for part in a.only.split(","):
-            dict(gemm=gemm_rows, conv=conv_rows, attention=attention_rows, norm=norm_rows, lnfold=lnfold_rows)[part]()
+            dict(gemm=gemm_rows, conv=conv_rows, attention=attention_rows, norm=norm_rows, lnfold=lnfold_rows, ksweep=ksweep_rows)[part]()
     if a.json:
         with open(a.json, "w") as f:
             json.dump(dict(device=torch.cuda.get_device_name(0), torch=torch.__version__, rows=ROWS), f, indent=1)
