@@ -76,9 +76,6 @@ struct ConvGemmParams {
   int out_fp32;  // y is float (attention scores of the unfused head_dim-512 path)
   int tma_store; // epilogue stages 32-column slabs in smem and writes them with TMA (needs vec_ok, 16-bit y)
   int tma_res;   // residual tiles are staged by the loader warp (needs tma_store, 16-bit residual, no GEGLU)
-  int seeded;    // bias (+ residual) are written into the TMEM accumulator BEFORE the tile's MMAs (which then all accumulate):
-                 // the epilogue warps do it while they would otherwise wait for the main loop, and the drain is LDTM -> scale ->
-                 // pack -> store only (plain bias / residual / folded-LayerNorm epilogues with the TMA store)
   const uint8_t* pf_ptr;  // next launch's weights: pulled into L2 while this launch runs (nullptr = none)
   long long pf_bytes;
   int dbg_mode;  // tuning: 1 = producer stops loading after the first pipeline round, 2 = MMA thread issues no MMAs
@@ -234,7 +231,6 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
   long long t_decoded = 0, t_stage_free = 0;
 
   const int dbg_mode = p.dbg_mode;
-  const bool seeded = !GEGLU && p.seeded != 0;
   if (warp == 0) {
     // ===================== TMA producer (whole warp, one elected lane issues) =====================
     int stage = 0;
@@ -294,8 +290,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       for (int g = cluster; g < p.total_groups; g += n_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
-        // seeded: the epilogue warps complete phase it/2 of tempty when the buffer is drained AND holds the tile's bias/residual
-        mbar_wait(&tempty_bar[acc], seeded ? acc_phase : (acc_phase ^ 1u));
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -311,9 +306,9 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               for (int k = 0; k < 4; ++k) {
                 // +32 B per UMMA_K=16 step inside the 128 B swizzle atom -> +2 in the (addr>>4) field
                 if (PAIR)
-                  umma_ss2(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (seeded || (kc | k) != 0) ? 1u : 0u);
+                  umma_ss2(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
                 else
-                  umma_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (seeded || (kc | k) != 0) ? 1u : 0u);
+                  umma_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kc | k) != 0 ? 1u : 0u);
               }
             }
             if (PAIR)
@@ -407,76 +402,6 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
     uint32_t k = 0;           // running chunk count over all tiles of this CTA (slab k % NSLAB, half k & 1)
     uint32_t prev_k = 0, prev2_k = 0;  // issuer: chunks of this half's (up to two) stores still in flight, newest first
     bool have_prev = false, have_prev2 = false;
-
-    // folded LayerNorm: a row's rstd from the producer's partial sums (fixed summation order).  All loads of a batch are issued
-    // before the first use (one L2 round trip per 16 parts).
-    auto row_rstd = [&](long long pix) {
-      const float4* sp = reinterpret_cast<const float4*>(ln_stats + pix * p.ln_parts);  // ln_parts is even: 16-byte rows
-      const int n4 = p.ln_parts >> 1;
-      float s0 = 0.f, s1 = 0.f;
-      for (int i0 = 0; i0 < n4; i0 += 8) {
-        float4 t[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = (i0 + i < n4) ? sp[i0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s0 += t[i].x + t[i].z;
-          s1 += t[i].y + t[i].w;
-        }
-      }
-      const float mean = s0 * p.ln_inv_k;
-      const float var = fmaxf(fmaf(-mean, mean, s1 * p.ln_inv_k), 0.0f);
-      return rsqrtf(var + p.ln_eps);
-    };
-    auto tile_chunks = [&](const TileCoord& t) {  // 32-column chunks of the tile inside the output
-      const int left = n_limit - (GEGLU ? (t.n0 >> 1) : t.n0);
-      return left >= (GEGLU ? BN / 2 : BN) ? (GEGLU ? BN / 64 : BN / 32) : (left <= 0 ? 0 : (left + 31) >> 5);
-    };
-    // seeded launches: accumulator buffer `acc2` <- bias / rstd + residual for tile g2 (chunks of this warp only: the ones it
-    // drains, and - two tiles earlier in the same buffer - has just drained), then the arrival the MMA warp waits for.
-    // k2 = running chunk count at the start of that tile.
-    auto seed_tile = [&](int g2, int acc2, uint32_t k2) {
-      const TileCoord t2 = decode_tile(p, g2, rank, BN);
-      const int oh2 = t2.h0 + rh, ow2 = t2.w0 + rw;
-      const bool valid2 = t2.img < p.batch && oh2 < p.Ho && ow2 < p.Wo;
-      const long long pix2 = (static_cast<long long>(t2.img) * p.Ho + oh2) * p.Wo + ow2;
-      const float inv = (ln_stats != nullptr && valid2) ? 1.0f / row_rstd(pix2) : 1.0f;  // y = rstd * acc: the bias goes in as bias / rstd
-      const typename H::T* rrow = (residual != nullptr && valid2) ? residual + pix2 * p.ldr + t2.n0 : nullptr;
-      const uint32_t t_row2 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc2 * Cfg::ACC_STRIDE;
-      const int nch = tile_chunks(t2);
-#pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
-        if (((k2 + c) & 1u) != static_cast<uint32_t>(half)) continue;
-        uint32_t sv[32];
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          const uint4 b4 = bias ? *reinterpret_cast<const uint4*>(bias + t2.n0 + c * 32 + j8 * 8) : make_uint4(0, 0, 0, 0);
-          const uint4 r4 = rrow ? *reinterpret_cast<const uint4*>(rrow + c * 32 + j8 * 8) : make_uint4(0, 0, 0, 0);
-          const float2 b0 = H::unpack(b4.x), b1 = H::unpack(b4.y), b2 = H::unpack(b4.z), b3 = H::unpack(b4.w);
-          const float2 r0 = H::unpack(r4.x), r1 = H::unpack(r4.y), r2 = H::unpack(r4.z), r3 = H::unpack(r4.w);
-          sv[j8 * 8 + 0] = __float_as_uint(fmaf(b0.x, inv, r0.x)); sv[j8 * 8 + 1] = __float_as_uint(fmaf(b0.y, inv, r0.y));
-          sv[j8 * 8 + 2] = __float_as_uint(fmaf(b1.x, inv, r1.x)); sv[j8 * 8 + 3] = __float_as_uint(fmaf(b1.y, inv, r1.y));
-          sv[j8 * 8 + 4] = __float_as_uint(fmaf(b2.x, inv, r2.x)); sv[j8 * 8 + 5] = __float_as_uint(fmaf(b2.y, inv, r2.y));
-          sv[j8 * 8 + 6] = __float_as_uint(fmaf(b3.x, inv, r3.x)); sv[j8 * 8 + 7] = __float_as_uint(fmaf(b3.y, inv, r3.y));
-        }
-        tmem_st32(t_row2 + c * 32, sv);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (PAIR)
-          mbar_arrive_cluster(leader_addr(&tempty_bar[acc2]));
-        else
-          mbar_arrive(&tempty_bar[acc2]);
-      }
-      return nch;
-    };
-    if (seeded && cluster < p.total_groups) {  // both accumulator buffers are free at the start: seed the first two tiles
-      const int n0c = seed_tile(cluster, 0, 0);
-      if (cluster + n_clusters < p.total_groups) seed_tile(cluster + n_clusters, 1, static_cast<uint32_t>(n0c));
-    }
-
     int it = 0;
     for (int g = cluster; g < p.total_groups; g += n_clusters, ++it) {
       const int acc = it & 1;
@@ -494,9 +419,29 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
       const int ycol0 = GEGLU ? (tc.n0 >> 1) : tc.n0;
 
-      const float ln_r = (ln_stats != nullptr && valid) ? row_rstd(pix) : 1.0f;  // (runs before the accumulator is needed)
+      // folded LayerNorm: this row's rstd from the producer's partial sums (fixed summation order).  All loads of a batch are
+      // issued before the first use (one L2 round trip per 16 parts); runs before the accumulator is needed.
+      float ln_r = 1.0f;
+      if (ln_stats != nullptr && valid) {
+        const float4* sp = reinterpret_cast<const float4*>(ln_stats + pix * p.ln_parts);  // ln_parts is even: 16-byte rows
+        const int n4 = p.ln_parts >> 1;
+        float s0 = 0.f, s1 = 0.f;
+        for (int i0 = 0; i0 < n4; i0 += 8) {
+          float4 t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = (i0 + i < n4) ? sp[i0 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            s0 += t[i].x + t[i].z;
+            s1 += t[i].y + t[i].w;
+          }
+        }
+        const float mean = s0 * p.ln_inv_k;
+        const float var = fmaxf(fmaf(-mean, mean, s1 * p.ln_inv_k), 0.0f);
+        ln_r = rsqrtf(var + p.ln_eps);
+      }
       float st_s = 0.f, st_q = 0.f;  // producer side of a folded LayerNorm: sums of this thread's ROUNDED outputs of the tile
-      if (!lean && bias != nullptr && real_tile && lane * 64 < BN && tc.n0 + lane * 64 < p.N) prefetch_l1(bias + tc.n0 + lane * 64);  // the tile's bias: L1 hits in the chunk loop
+      if (bias != nullptr && real_tile && lane * 64 < BN && tc.n0 + lane * 64 < p.N) prefetch_l1(bias + tc.n0 + lane * 64);  // the tile's bias: L1 hits in the chunk loop
 
       mbar_wait_warp(&tfull_bar[acc], (it >> 1) & 1u);
       tc_fence_after();
@@ -504,6 +449,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
 
       uint32_t v[32];
+      bool preloaded = false;
 #pragma unroll 1
       for (int c = 0; c < OUT_COLS / 32; ++c, ++k) {
         const int yc0 = ycol0 + c * 32;
@@ -511,13 +457,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         if ((k & 1u) != static_cast<uint32_t>(half)) continue;
         const bool chunk_vec = p.vec_ok && (yc0 + 32 <= n_limit);
         const int bcol = GEGLU ? (tc.n0 + c * 32) : yc0;
-        tmem_ld32(t_row + c * 32, v);  // (TMEM reads are cheap: 22 cycles per x32 load and warp, ~55 cycles latency - tools/micro/tmem_bw.cu)
+        if (!preloaded) tmem_ld32(t_row + c * 32, v);  // (else issued during the previous chunk's store phase)
         uint32_t gv[32];
         if (GEGLU) tmem_ld32(t_row + BN / 2 + c * 32, gv);
         uint4 bc[4];  // bias of this chunk (same for every row: L1 hits after the first warp)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          bc[j] = (!lean && chunk_vec && bias) ? *reinterpret_cast<const uint4*>(bias + bcol + j * 8) : make_uint4(0, 0, 0, 0);
+          bc[j] = (chunk_vec && bias) ? *reinterpret_cast<const uint4*>(bias + bcol + j * 8) : make_uint4(0, 0, 0, 0);
         uint8_t* slab = slabs + (k % Cfg::NSLAB) * Cfg::SLAB_BYTES;
         if (tma_store) {
           if (q == 0 && have_prev2) {
@@ -531,22 +477,33 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
           mbar_wait_warp(&rfull_bar[k % Cfg::NSLAB], (k / Cfg::NSLAB) & 1u);  // slab is ours (and holds the residual if any)
         }
-        // marks of the first two rounds of half 0 in the CTA's first tile: 8 + 6 r + {0 slab ready, 1 arithmetic + smem stores done
-        // (includes the wait for the TMEM data), 2 fence + barrier passed, 3 TMA store issued, 4 register rotation done}
-        const bool stamp = dbg && issuer && half == 0 && it == 0 && c < 4;
-        const int sb = 8 + (c >> 1) * 6;
-        if (stamp) dbg[sb] = clock64();
         tmem_wait_ld();
+        const bool stamp = dbg && issuer && it == 0 && c < 2;
+        if (stamp) dbg[8 + c * 4] = clock64();
         if (lean) {
-          // bias and residual are already in the accumulator (seeded launch; a lean launch without them has neither)
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
+            uint4* sp = reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4));
+            float f[8];
+            {  // acc * rstd + bias (rstd = 1 without a folded LayerNorm)
+              float2 t0 = H::unpack(bc[j8].x), t1 = H::unpack(bc[j8].y), t2 = H::unpack(bc[j8].z), t3 = H::unpack(bc[j8].w);
+              f[0] = fmaf(__uint_as_float(v[j8 * 8 + 0]), ln_r, t0.x); f[1] = fmaf(__uint_as_float(v[j8 * 8 + 1]), ln_r, t0.y);
+              f[2] = fmaf(__uint_as_float(v[j8 * 8 + 2]), ln_r, t1.x); f[3] = fmaf(__uint_as_float(v[j8 * 8 + 3]), ln_r, t1.y);
+              f[4] = fmaf(__uint_as_float(v[j8 * 8 + 4]), ln_r, t2.x); f[5] = fmaf(__uint_as_float(v[j8 * 8 + 5]), ln_r, t2.y);
+              f[6] = fmaf(__uint_as_float(v[j8 * 8 + 6]), ln_r, t3.x); f[7] = fmaf(__uint_as_float(v[j8 * 8 + 7]), ln_r, t3.y);
+            }
+            if (tma_res) {  // the residual sits where this thread is about to write its output
+              const uint4 r4 = *sp;
+              float2 t0 = H::unpack(r4.x), t1 = H::unpack(r4.y), t2 = H::unpack(r4.z), t3 = H::unpack(r4.w);
+              f[0] += t0.x; f[1] += t0.y; f[2] += t1.x; f[3] += t1.y;
+              f[4] += t2.x; f[5] += t2.y; f[6] += t3.x; f[7] += t3.y;
+            }
             uint4 o;
-            o.x = H::pack(__uint_as_float(v[j8 * 8 + 0]) * ln_r, __uint_as_float(v[j8 * 8 + 1]) * ln_r);
-            o.y = H::pack(__uint_as_float(v[j8 * 8 + 2]) * ln_r, __uint_as_float(v[j8 * 8 + 3]) * ln_r);
-            o.z = H::pack(__uint_as_float(v[j8 * 8 + 4]) * ln_r, __uint_as_float(v[j8 * 8 + 5]) * ln_r);
-            o.w = H::pack(__uint_as_float(v[j8 * 8 + 6]) * ln_r, __uint_as_float(v[j8 * 8 + 7]) * ln_r);
-            *reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4)) = o;
+            o.x = H::pack(f[0], f[1]);
+            o.y = H::pack(f[2], f[3]);
+            o.z = H::pack(f[4], f[5]);
+            o.w = H::pack(f[6], f[7]);
+            *sp = o;
             if (stats_out != nullptr) {
               const float2 r0 = H::unpack(o.x), r1 = H::unpack(o.y), r2 = H::unpack(o.z), r3 = H::unpack(o.w);
               st_s += ((r0.x + r0.y) + (r1.x + r1.y)) + ((r2.x + r2.y) + (r3.x + r3.y));
@@ -626,16 +583,21 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           }
           epilogue_scalar<GEGLU, FP16>(tv, tg, p, bias, gate_row, rv_row, res_row, y_row, pix, yc0, tc.n0 + c * 32, BN, n_limit);
         }
-        if (stamp) dbg[sb + 1] = clock64();
+        if (stamp) dbg[9 + c * 4] = clock64();
+        // this warp's next chunk (c + 2: the halves alternate) starts its TMEM read now, under the fence / barrier / store below
+        preloaded = false;
+        if (!GEGLU && c + 2 < OUT_COLS / 32 && ycol0 + (c + 2) * 32 < n_limit) {
+          tmem_ld32(t_row + (c + 2) * 32, v);
+          preloaded = true;
+        }
         if (tma_store) {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
           named_bar_sync(bar_id, 128);
-          if (stamp) dbg[sb + 2] = clock64();
           if (q == 0) {
             if (elect_one()) {
               if (real_tile) tma_store_4d(&p.y_map, slab, yc0, tc.w0, tc.h0, tc.img);
               bulk_commit_group();
-              if (stamp) dbg[sb + 3] = clock64();
+              if (stamp) dbg[11 + c * 4] = clock64();
             }
             have_prev2 = have_prev;
             prev2_k = prev_k;
@@ -645,18 +607,13 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         }
       }
       if (stats_out != nullptr && valid) stats_out[pix * p.stats_parts + ((tc.n0 / BN) << 1) + half] = make_float2(st_s, st_q);
-      if (seeded && g + 2 * n_clusters < p.total_groups) {
-        // this warp's chunks of the buffer are drained: seed them for the tile after next (which ends with the arrival)
-        seed_tile(g + 2 * n_clusters, acc, k + static_cast<uint32_t>(tile_chunks(decode_tile(p, g + n_clusters, rank, BN))));
-      } else {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (PAIR)
-            mbar_arrive_cluster(leader_addr(&tempty_bar[acc]));
-          else
-            mbar_arrive(&tempty_bar[acc]);
-        }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR)
+          mbar_arrive_cluster(leader_addr(&tempty_bar[acc]));
+        else
+          mbar_arrive(&tempty_bar[acc]);
       }
       // (stores still in flight carry over into the next tile: with three slabs per half one is always free for the next
       // tile's first residual chunk, and nobody stalls on a store that has just been issued)
@@ -1047,8 +1004,7 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
     if (r) return r;
   }
 
-  prm.seeded = (prm.tma_store && !a->geglu && a->act == B200_ACT_NONE && !a->gate && !a->rowvec && (a->bias || a->residual)) ? 1 : 0;
-  prm.tma_res = (prm.tma_store && a->residual && !a->geglu && !prm.seeded) ? 1 : 0;
+  prm.tma_res = (prm.tma_store && a->residual && !a->geglu) ? 1 : 0;
   if (prm.tma_res) {
     const uint64_t ldr = static_cast<uint64_t>(a->ldr);
     const uint64_t dims[4] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),

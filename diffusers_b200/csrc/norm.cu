@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(512) group_norm_apply_kernel(const GroupNormPa
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float o = fmaf(v[j], sc[j], bi[j]);
-          v[j] = do_silu ? silu_f(o) : o;
+          v[j] = do_silu ? silu_fast(o) : o;
         }
         uint4 o;
         o.x = H::pack(v[0], v[1]);
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(kGnSlabThreads, 1) group_norm_slab_kernel(cons
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       f[j] = fmaf(f[j], sc[j], sh[j]);
-      if (silu) f[j] = silu_f(f[j]);
+      if (silu) f[j] = silu_fast(f[j]);
     }
     uint4 o;
     o.x = H::pack(f[0], f[1]);

@@ -27,11 +27,8 @@ mode = os.environ.get("MODE", "cold")  # cold | hotact (activations in L2, weigh
 xs = torch.randn(256, 256, device="cuda").bfloat16()
 ws = packing.pack_linear_weight(torch.randn(256, 256, device="cuda").bfloat16())
 names = ["entry", "prologue done", "first TMA issued", "first data landed", "last MMA committed", "accumulator ready (epi)",
-         "epilogue stores issued", "exit"]
-for rnd_ in range(2):
-    names += [f"half0 round{rnd_}: slab ready", f"half0 round{rnd_}: math+sts done", f"half0 round{rnd_}: fence+barrier passed",
-              f"half0 round{rnd_}: store issued", f"half0 round{rnd_}: rotation done", ""]
-names += [""] * 4 + ["producer: first tile decoded", "producer: first stage free"]
+         "epilogue stores issued", "exit", "c0 tmem loaded", "c0 math+sts done", "", "c0 store issued",
+         "c1 tmem loaded", "c1 math+sts done", "", "c1 store issued"] + [""] * 8 + ["producer: first tile decoded", "producer: first stage free"]
 for rep in range(2):
     if mode != "hot":
         flush.zero_()
