@@ -29,15 +29,22 @@ namespace b200 {
 //   SiLU      x * sigmoid(x)
 //   GELU-tanh 0.5 x (1 + tanh(u)) == x * sigmoid(2u),  u = sqrt(2/pi) (x + 0.044715 x^3)
 //   GELU-erf  0.5 x (1 + erf(x / sqrt 2)) with Abramowitz-Stegun 7.1.26 (|erf error| < 1.5e-7, far below 16-bit rounding)
-__device__ __forceinline__ float sigmoid_fast(float t) { return __fdividef(1.0f, 1.0f + __expf(-t)); }
+// (ex2 / rcp in their .ftz forms: __expf / __fdividef without -ftz carry range fix-ups around the MUFU instruction)
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float exp_fast(float x) { return fast_ex2(x * 1.4426950408889634f); }
+__device__ __forceinline__ float sigmoid_fast(float t) { return rcp_fast(1.0f + exp_fast(-t)); }
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_fast(fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+  const float erf_abs = 1.0f - poly * t * exp_fast(-z * z);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 __device__ __forceinline__ float act_fast(float x, int act) {

@@ -78,8 +78,17 @@ __global__ void group_norm_stats_kernel(const GroupNormParams p) {
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = sh[j] = 0.f;
   float cnt = 0.f;
   if (pl < p.P) {
+    {  // group of channel cv * 8 + j without eight integer divisions: one division, then count up
+      int g = (cv * 8) / p.cg, r = cv * 8 - g * p.cg;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sh[j] = rep_value((cv * 8 + j) / p.cg);
+      for (int j = 0; j < 8; ++j) {
+        sh[j] = rep_value(g);
+        if (++r == p.cg) {
+          r = 0;
+          ++g;
+        }
+      }
+    }
     const int step = p.P;
     for (int pix = pix0 + pl; pix < pix1; pix += 4 * step) {
       uint4 u[4];
@@ -208,16 +217,31 @@ __global__ void __launch_bounds__(512) group_norm_apply_kernel(const GroupNormPa
   const typename H::T* gamma = static_cast<const typename H::T*>(p.gamma);
   const typename H::T* beta = static_cast<const typename H::T*>(p.beta);
   float sc[8], bi[8];
+  {
+    // this thread's 8 channels: gamma / beta as one 16-byte load each, the group index by counting up from one division (eight
+    // runtime divisions cost more than the thread's share of the pixel loop at the small shapes)
+    uint4 g4 = make_uint4(0, 0, 0, 0), b4 = make_uint4(0, 0, 0, 0);
+    if (gamma) g4 = *reinterpret_cast<const uint4*>(gamma + cv * 8);
+    if (beta) b4 = *reinterpret_cast<const uint4*>(beta + cv * 8);
+    const float2 ga01 = H::unpack(g4.x), ga23 = H::unpack(g4.y), ga45 = H::unpack(g4.z), ga67 = H::unpack(g4.w);
+    const float2 be01 = H::unpack(b4.x), be23 = H::unpack(b4.y), be45 = H::unpack(b4.z), be67 = H::unpack(b4.w);
+    const float gav[8] = {ga01.x, ga01.y, ga23.x, ga23.y, ga45.x, ga45.y, ga67.x, ga67.y};
+    const float bev[8] = {be01.x, be01.y, be23.x, be23.y, be45.x, be45.y, be67.x, be67.y};
+    int g = (cv * 8) / p.cg, r = cv * 8 - g * p.cg;
+    const float2* st = reinterpret_cast<const float2*>(p.stats) + static_cast<size_t>(n) * p.groups;
+    float2 mr = st[g];  // (mean, rstd)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cv * 8 + j;
-    const int g = c / p.cg;
-    const float mean = p.stats[(static_cast<size_t>(n) * p.groups + g) * 2 + 0];
-    const float rstd = p.stats[(static_cast<size_t>(n) * p.groups + g) * 2 + 1];
-    const float ga = gamma ? H::to_float(gamma[c]) : 1.f;
-    const float be = beta ? H::to_float(beta[c]) : 0.f;
-    sc[j] = rstd * ga;
-    bi[j] = be - mean * rstd * ga;
+    for (int j = 0; j < 8; ++j) {
+      const float ga = gamma ? gav[j] : 1.f;
+      const float be = beta ? bev[j] : 0.f;
+      sc[j] = mr.y * ga;
+      bi[j] = be - mr.x * mr.y * ga;
+      if (++r == p.cg) {
+        r = 0;
+        ++g;
+        if (j < 7) mr = st[g < p.groups ? g : p.groups - 1];
+      }
+    }
   }
   const int src = cv < p.V0 ? 0 : 1;
   const int ld = p.ldx[src];
@@ -458,13 +482,14 @@ static int gn_slab_plan(int batch, int hw, int C, int groups, int c0, int nsrc, 
   // Clusters of up to 4 CTAs: measured on B200 (tools/library_bar.py --only norm, us per launch, slab vs two kernels):
   // 4096 x 640: 18.5 vs 28.8, 4096 x 1280: 27.4 vs 39.1, 1024 x 1280: 14.2 vs 22.0, 1024 x 2560: 18.6 vs 25.6 - but
   // 16384 x 320, which needs clusters of 8, 48.6 vs 39.7: those shapes keep the two-kernel path.
-  for (int cl = 1; cl <= 4; cl *= 2) {
+  static const int max_cl = getenv("B200_GN_SLAB_MAX_CLUSTER") ? atoi(getenv("B200_GN_SLAB_MAX_CLUSTER")) : 4;  // tuning knob (1..8)
+  for (int cl = 1; cl <= max_cl; cl *= 2) {
     const int ppc = (hw + cl - 1) / cl;
     const long long slab = static_cast<long long>(ppc) * span * 2;
     const long long part = static_cast<long long>(kGnSlabThreads / vpp) * span * 4;
     if (slab + part <= kGnSlabMaxBytes + 32768 && slab <= kGnSlabMaxBytes) {
       // the smallest cluster that fits; wider clusters while fewer than ~100 CTAs would be at work (smaller slabs per SM)
-      while (cl < 4 && static_cast<long long>(cl) * (groups / gb) * batch < 96 && hw / (2 * cl) >= 64) cl *= 2;
+      while (cl < max_cl && static_cast<long long>(cl) * (groups / gb) * batch < 96 && hw / (2 * cl) >= 64) cl *= 2;
       if (p) {
         p->cg = cg; p->gb = gb; p->span = span; p->vpp = vpp; p->units = groups / gb; p->ppc = (hw + cl - 1) / cl;
       }
@@ -689,6 +714,7 @@ int b200_group_norm(const b200_group_norm_args* a, void* stream) {
   }
   B200_CHECK_ARG(a->ldy % 8 == 0 && a->ldy >= C && aligned16(a->y), "group_norm: y stride/alignment");
   B200_CHECK_ARG(a->act == B200_ACT_NONE || a->act == B200_ACT_SILU, "group_norm: act must be NONE or SILU");
+  B200_CHECK_ARG((!a->gamma || aligned16(a->gamma)) && (!a->beta || aligned16(a->beta)), "group_norm: gamma / beta must be 16-byte aligned");
   B200_CHECK_ARG(a->workspace_bytes >= b200_group_norm_workspace_bytes(a->batch, a->hw, a->groups),
                  "group_norm: workspace too small");
   B200_CHECK_ARG(a->batch > 0 && a->hw > 0, "group_norm: bad shape");

@@ -156,7 +156,7 @@ typedef struct {
   int32_t ldx[2];
   int32_t batch, hw, groups;
   float eps;
-  const void* gamma;  /* [C] or NULL                                                            */
+  const void* gamma;  /* [C] or NULL, 16-byte aligned                                           */
   const void* beta;   /* [C] or NULL                                                            */
   int32_t act;        /* B200_ACT_NONE | B200_ACT_SILU                                          */
   void* y;            /* [batch, hw, ldy]                                                       */
