@@ -34,6 +34,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in this image's environment) goes there too
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 import torch  # noqa: E402
 
 UNET_FLOP_PER_SAMPLE = 6.7612e12      # BASELINE.md section 3 (FlopCounterMode on the reference, meta device)
@@ -288,7 +291,7 @@ def run_reference(args, rank, world):
                             note="bounded sample of the workload (a few denoising steps + one decode), extrapolated to 50 steps: see cpu_baseline.sample"),
                 cpu_baseline={k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "dtype", "t_step_runs_s", "run_spread")},
                 e2e=dict(value=cb["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm: rooflines
@@ -709,10 +712,29 @@ def run_b200(args, rank, world, local_rank):
             cb = cpu_reference_subprocess(args)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "dtype", "t_step_runs_s", "run_spread") if k in cb}
     if rank == 0 and line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's real stdout (everything else written to fd 1 - NCCL's version banner, library
+    chatter of child processes - was diverted to stderr by main())."""
+    sys.stdout.flush()
+    text = json.dumps(line) + "\n"
+    if _JSON_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, text.encode())
 
 
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="all", choices=["all", "sdxl", "flux", "vae"])
     ap.add_argument("--gpus", type=int, default=1)
@@ -732,7 +754,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         if args.cpu_sample:
-            print(json.dumps(cpu_reference(args, full=False)), flush=True)
+            emit(cpu_reference(args, full=False))
         else:
             run_reference(args, rank, world)
         return

@@ -43,7 +43,8 @@ def main():
     dist.broadcast(ref0, src=0)
     assert torch.equal(ref0, imgs)
     if rank == 0:
-        lat = parallel.seeded_latent_shard((n, 4, 4, 4), 123, 0, 1, torch.bfloat16, dev)
+        lat_hw = 32 // pipe.vae_scale_factor  # the shape parallel.sdxl_data_parallel draws for the whole batch
+        lat = parallel.seeded_latent_shard((n, pipe.unet.config.in_channels, lat_hw, lat_hw), 123, 0, 1, torch.bfloat16, dev)
         single = pipe(pe, npe, po, npo, height=32, width=32, num_inference_steps=3, guidance_scale=7.5, latents=lat, output_type="pt").images
         per_sample = torch.cat([pipe(pe[i:i + 1], npe[i:i + 1], po[i:i + 1], npo[i:i + 1], height=32, width=32, num_inference_steps=3,
                                      guidance_scale=7.5, latents=lat[i:i + 1], output_type="pt").images for i in range(n)])
