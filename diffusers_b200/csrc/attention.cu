@@ -425,6 +425,7 @@ int launch_attention64_pipe(const b200_attention_args* a, cudaStream_t st);
 // attention64.cu: the head_dim-64 default (software-pipelined softmax, register reallocation, KV split with in-kernel combine)
 int init_attention64();
 bool attention64_enabled();
+bool attention128_v2_enabled();
 int launch_attention64(const b200_attention_args* a, cudaStream_t st);
 long long attention64_workspace_bytes(long long tiles, int kv_halves);
 
@@ -484,6 +485,8 @@ int b200_attention(const b200_attention_args* a, void* stream) {
                  "attention: strides must be multiples of 8 elements");
   const int HD = a->head_dim;
   if (HD == 64 && a->nq_override != 2 && attention64_enabled())
+    return launch_attention64(a, static_cast<cudaStream_t>(stream));
+  if (HD == 128 && a->nq_override == 0 && attention128_v2_enabled())
     return launch_attention64(a, static_cast<cudaStream_t>(stream));
   if (HD == 64 && a->nq_override != 2 && attention_pipe_enabled())
     return launch_attention64_pipe(a, static_cast<cudaStream_t>(stream));

@@ -59,12 +59,22 @@ struct Attn64Params {
   int* ws_ticket;        // [tail tiles], zero between launches (the merging CTA resets it)
 };
 
+// HD = 64 (SDXL) or 128 (Flux).  Operands live in shared memory as HD / 64 "slabs" of 64 columns (128-byte swizzled rows).
+// head_dim 128 keeps ONE score buffer (S(h+1) is issued as soon as the softmax holds S(h) in registers, one step ahead instead
+// of two) so that S + P0 + P1 + O still fit 256 TMEM columns and two CTAs share an SM.
+template <int HD>
 struct Attn64Cfg {
-  static constexpr int Q_BYTES = 128 * 64 * 2;   // 16 KB
-  static constexpr int KV_BYTES = 64 * 64 * 2;   // 8 KB: one 64-key half of K or V
-  static constexpr int KS = 4, VS = 4;
+  static_assert(HD == 64 || HD == 128, "head_dim");
+  static constexpr int SLABS = HD / 64;
+  static constexpr int Q_SLAB = 128 * 64 * 2;    // 16 KB
+  static constexpr int KV_SLAB = 64 * 64 * 2;    // 8 KB
+  static constexpr int Q_BYTES = SLABS * Q_SLAB;
+  static constexpr int KV_BYTES = SLABS * KV_SLAB;  // one 64-key half of K or V
+  static constexpr int KS = HD == 64 ? 4 : 2, VS = KS;
+  static constexpr int LA = HD == 64 ? 2 : 1;    // score buffers = halves S is issued ahead of the softmax
   static constexpr int TMEM_COLS = 256;
-  static constexpr int S_COL = 0, P_COL = 128, O_COL = 192;
+  static constexpr int S_COL = 0, P_COL = LA * 64, O_COL = P_COL + 64;
+  static_assert(O_COL + HD <= TMEM_COLS, "TMEM budget");
   static constexpr int SMEM_BYTES = Q_BYTES + (KS + VS) * KV_BYTES + 1024 + 256;
   static constexpr int THREADS = 256;
   static constexpr int REGS_LOW = 56, REGS_HIGH = 200;  // 128 * (56 + 200) = 32768 = half of the SM's register file
@@ -72,9 +82,11 @@ struct Attn64Cfg {
 
 // POLY: score pairs (of every 8) whose exponentials go to the FMA-pipe polynomial instead of MUFU (0..3)
 // SPLIT: the launch has tail parts (see TAIL SPLIT above); the plain instance keeps the key range compile-time [0, kv_halves)
-template <bool FP16, int POLY, bool SPLIT>
-__global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(const __grid_constant__ Attn64Params p) {
-  using Cfg = Attn64Cfg;
+template <int HD, bool FP16, int POLY, bool SPLIT>
+__global__ void __launch_bounds__(Attn64Cfg<HD>::THREADS, 2) attention64_kernel(const __grid_constant__ Attn64Params p) {
+  using Cfg = Attn64Cfg<HD>;
+  static_assert(!SPLIT || HD == 64, "the tail split merges 64 output columns per thread");
+  constexpr int SLABS = Cfg::SLABS, LA = Cfg::LA;
   using H = Half16<FP16>;
   constexpr int KS = Cfg::KS, VS = Cfg::VS;
 
@@ -154,7 +166,8 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
       // ===================== TMA producer =====================
       if (elect_one()) {
         mbar_expect_tx(q_full, Cfg::Q_BYTES);
-        tma_load_4d(s_q, &p.q_map, q_full, 0, q_row0, head, b);
+#pragma unroll
+        for (int s = 0; s < SLABS; ++s) tma_load_4d(s_q + s * Cfg::Q_SLAB, &p.q_map, q_full, s * 64, q_row0, head, b);
       }
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0;
@@ -162,13 +175,17 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
         mbar_wait(&k_empty[ks], kph ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(&k_full[ks], Cfg::KV_BYTES);
-          tma_load_4d(s_k + ks * Cfg::KV_BYTES, &p.k_map, &k_full[ks], 0, h * 64, head, b);
+#pragma unroll
+          for (int s = 0; s < SLABS; ++s)
+            tma_load_4d(s_k + ks * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.k_map, &k_full[ks], s * 64, h * 64, head, b);
         }
         if (++ks == KS) { ks = 0; kph ^= 1u; }
         mbar_wait(&v_empty[vs], vph ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(&v_full[vs], Cfg::KV_BYTES);
-          tma_load_4d(s_v + vs * Cfg::KV_BYTES, &p.v_map, &v_full[vs], 0, h * 64, head, b);
+#pragma unroll
+          for (int s = 0; s < SLABS; ++s)
+            tma_load_4d(s_v + vs * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.v_map, &v_full[vs], s * 64, h * 64, head, b);
         }
         if (++vs == VS) { vs = 0; vph ^= 1u; }
       }
@@ -180,24 +197,30 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
       uint32_t kph = 0, vph = 0;
       const uint32_t qa = smem_u32(s_q);
 
-      auto issue_s = [&](int buf, int kstage) {  // S_buf = Q K_half^T: 128 x 64 x 64, four K steps of 16
-        const uint64_t qd = make_smem_desc_sw128(qa, 16, 1024);
-        const uint64_t kd = make_smem_desc_sw128(smem_u32(s_k + kstage * Cfg::KV_BYTES), 16, 1024);
+      auto issue_s = [&](int buf, int kstage) {  // S_buf = Q K_half^T: 128 x 64 x HD, four K steps of 16 per 64-column slab
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem_base + Cfg::S_COL + buf * 64, qd + 2u * k, kd + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
+        for (int s = 0; s < SLABS; ++s) {
+          const uint64_t qd = make_smem_desc_sw128(qa + s * Cfg::Q_SLAB, 16, 1024);
+          const uint64_t kd = make_smem_desc_sw128(smem_u32(s_k + kstage * Cfg::KV_BYTES + s * Cfg::KV_SLAB), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tmem_base + Cfg::S_COL + buf * 64, qd + 2u * k, kd + 2u * k, idesc_qk, (s | k) != 0 ? 1u : 0u);
+        }
       };
       auto issue_pv = [&](int buf, int vstage, bool accumulate) {  // O += P_buf V_half: K = 64 keys, four steps of 16
         const uint32_t va = smem_u32(s_v + vstage * Cfg::KV_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t vd = make_smem_desc_sw128(va + k * 2048, Cfg::KV_BYTES, 1024);  // MN-major: 16 keys = 2 x 8-row groups
-          umma_ts(tmem_base + Cfg::O_COL, tmem_base + Cfg::P_COL + buf * 32 + k * 8, vd, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+#pragma unroll
+          for (int s = 0; s < SLABS; ++s) {  // O[:, slab s] += P V[:, slab s] (N = 64 per instruction)
+            const uint64_t vd = make_smem_desc_sw128(va + s * Cfg::KV_SLAB + k * 2048, Cfg::KV_SLAB, 1024);  // MN-major: 16 keys = 2 x 8-row groups
+            umma_ts(tmem_base + Cfg::O_COL + s * 64, tmem_base + Cfg::P_COL + buf * 32 + k * 8, vd, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+          }
         }
       };
 
       mbar_wait(q_full, 0);
-      for (int h0 = 0; h0 < 2 && h0 < n_half; ++h0) {  // prologue: both score buffers filled
+      for (int h0 = 0; h0 < LA && h0 < n_half; ++h0) {  // prologue: every score buffer filled
         mbar_wait(&k_full[ks], kph);
         tc_fence_after();
         if (elect_one()) {
@@ -212,13 +235,14 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
       // P(h) V(h), and is complete when the softmax asks for it.
       for (int h = 0; h < n_half; ++h) {
         const int buf = h & 1;
-        if (h + 2 < n_half) {
-          mbar_wait(&s_free[buf], (h >> 1) & 1u);
+        if (h + LA < n_half) {
+          const int sbuf = h % LA;
+          mbar_wait(&s_free[sbuf], (h / LA) & 1u);
           mbar_wait(&k_full[ks], kph);
           tc_fence_after();
           if (elect_one()) {
-            issue_s(buf, ks);
-            umma_commit(&s_full[buf]);
+            issue_s(sbuf, ks);
+            umma_commit(&s_full[sbuf]);
             umma_commit(&k_empty[ks]);
           }
           if (++ks == KS) { ks = 0; kph ^= 1u; }
@@ -256,7 +280,7 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
       }
     };
     auto load_scores = [&](uint32_t (&s)[64], int h) {  // issue only; tmem_wait_ld() before use
-      const uint32_t s_t = tmem_base + lane_off + Cfg::S_COL + (h & 1) * 64;
+      const uint32_t s_t = tmem_base + lane_off + Cfg::S_COL + (h % LA) * 64;
       tmem_ld32_at<0>(s_t, s);
       tmem_ld32_at<32>(s_t + 32, s);
     };
@@ -311,7 +335,7 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
       const int buf = h & 1;
       const uint32_t p_t = tmem_base + lane_off + Cfg::P_COL + buf * 32;
       if (has_next) {
-        mbar_wait_warp(&s_full[buf ^ 1], ((h + 1) >> 1) & 1u);
+        mbar_wait_warp(&s_full[(h + 1) % LA], ((h + 1) / LA) & 1u);
         tc_fence_after();
         load_scores(nxt, h + 1);
       }
@@ -324,7 +348,7 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
       if (has_next) {
         tmem_wait_ld();
         tc_fence_before();
-        mbar_arrive(&s_free[buf ^ 1]);  // S(h+1) is in registers: its TMEM buffer may take S(h+3)
+        mbar_arrive(&s_free[(h + 1) % LA]);  // S(h+1) is in registers: its TMEM buffer may take S(h+1+LA)
         if (MODE == 1) mask_tail(nxt, h_begin + h + 1);
         mx = row_max(nxt);  // independent of the exponentials below
       }
@@ -347,7 +371,7 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
           }
           uint32_t t0[32];
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < HD / 32; ++c) {
             tmem_ld32(o_t + c * 32, t0);
             tmem_wait_ld();
 #pragma unroll
@@ -402,8 +426,10 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
     tc_fence_after();
     const int qrow = q_row0 + row;
     typename H::T* const orow = static_cast<typename H::T*>(p.o) + static_cast<long long>(b) * p.o_batch_stride +
-                                static_cast<long long>(qrow) * p.o_row_stride + head * 64;
-    if (SPLIT && is_part) {
+                                static_cast<long long>(qrow) * p.o_row_stride + head * HD;
+    bool parked = false;
+    if constexpr (SPLIT) if (is_part) {
+      parked = true;
       // ---- one part of a split tile: park (O, m, l), take a ticket; the last part to arrive merges all of them
       constexpr int PART_FLOATS = 64 * 128 + 256;
       float* const tile_ws = p.ws_part + static_cast<size_t>(tile - p.n_whole) * p.split * PART_FLOATS;
@@ -456,12 +482,13 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
         }
         if (threadIdx.x == 128) p.ws_ticket[tile - p.n_whole] = 0;  // ready for the next launch (stream order)
       }
-    } else {
+    }
+    if (!parked) {
       // ---- epilogue: O / l -> global
       const bool valid = qrow < p.sq;
       const float inv_l = 1.0f / l;
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < HD / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(o_t + c * 32, v);
         tmem_wait_ld();
@@ -488,24 +515,30 @@ __global__ void __launch_bounds__(Attn64Cfg::THREADS, 2) attention64_kernel(cons
   }
 }
 
-template <bool FP16, int POLY, bool SPLIT>
+template <int HD, bool FP16, int POLY, bool SPLIT>
 static cudaError_t a64_attr() {
-  return cudaFuncSetAttribute(attention64_kernel<FP16, POLY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Cfg::SMEM_BYTES);
+  return cudaFuncSetAttribute(attention64_kernel<HD, FP16, POLY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Cfg<HD>::SMEM_BYTES);
 }
 
 int init_attention64() {
-  cudaError_t e = a64_attr<false, 0, false>();
-  if (e == cudaSuccess) e = a64_attr<true, 0, false>();
-  if (e == cudaSuccess) e = a64_attr<false, 1, false>();
-  if (e == cudaSuccess) e = a64_attr<true, 1, false>();
-  if (e == cudaSuccess) e = a64_attr<false, 1, true>();
-  if (e == cudaSuccess) e = a64_attr<true, 1, true>();
+  cudaError_t e = a64_attr<64, false, 0, false>();
+  if (e == cudaSuccess) e = a64_attr<64, true, 0, false>();
+  if (e == cudaSuccess) e = a64_attr<64, false, 1, false>();
+  if (e == cudaSuccess) e = a64_attr<64, true, 1, false>();
+  if (e == cudaSuccess) e = a64_attr<64, false, 1, true>();
+  if (e == cudaSuccess) e = a64_attr<64, true, 1, true>();
+  if (e == cudaSuccess) e = a64_attr<128, false, 1, false>();
+  if (e == cudaSuccess) e = a64_attr<128, true, 1, false>();
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention (head_dim 64) smem attr: %s", cudaGetErrorString(e));
   return 0;
 }
 
 bool attention64_enabled() {
   static const bool on = !(getenv("B200_ATTN_V2") && atoi(getenv("B200_ATTN_V2")) == 0);
+  return on;
+}
+bool attention128_v2_enabled() {  // head_dim 128 through this kernel (B200_ATTN128_V2=0: attention.cu, two query tiles per CTA)
+  static const bool on = attention64_enabled() && !(getenv("B200_ATTN128_V2") && atoi(getenv("B200_ATTN128_V2")) == 0);
   return on;
 }
 
@@ -552,15 +585,16 @@ long long attention64_workspace_bytes(long long tiles, int kv_halves) {
   return sp.split > 1 ? kAttn64TicketBytes + static_cast<long long>(sp.tail) * sp.split * kAttn64PartBytes : 0;
 }
 
-// head_dim 64, one query tile per CTA; arguments already validated by b200_attention
+// head_dim 64 or 128, one query tile per CTA; arguments already validated by b200_attention
 int launch_attention64(const b200_attention_args* a, cudaStream_t st) {
+  const int HD = a->head_dim;
   Attn64Params prm;
   memset(&prm, 0, sizeof(prm));
   auto mk = [&](CUtensorMap* m, const void* base, int rows, long long row_stride, long long batch_stride, uint32_t box_rows,
                 const char* what) {
     const uint32_t box[4] = {64u, box_rows, 1u, 1u};
-    const uint64_t dims[4] = {64u, static_cast<uint64_t>(rows), static_cast<uint64_t>(a->heads), static_cast<uint64_t>(a->batch)};
-    const uint64_t str[3] = {static_cast<uint64_t>(row_stride) * 2, 64u * 2,
+    const uint64_t dims[4] = {static_cast<uint64_t>(HD), static_cast<uint64_t>(rows), static_cast<uint64_t>(a->heads), static_cast<uint64_t>(a->batch)};
+    const uint64_t str[3] = {static_cast<uint64_t>(row_stride) * 2, static_cast<uint64_t>(HD) * 2,
                              static_cast<uint64_t>(batch_stride > 0 ? batch_stride : row_stride * rows) * 2};
     return make_tensor_map_16b(m, base, 4, dims, str, box, what);
   };
@@ -577,11 +611,11 @@ int launch_attention64(const b200_attention_args* a, cudaStream_t st) {
   prm.sk = a->sk;
   prm.q_tiles = (a->sq + 127) / 128;
   prm.kv_halves = (a->sk + 63) / 64;
-  const float scale = a->scale > 0.f ? a->scale : 0.125f;
+  const float scale = a->scale > 0.f ? a->scale : (HD == 64 ? 0.125f : 0.08838834764831845f);
   prm.scale_log2 = scale * 1.4426950408889634f;
   const long long tiles = static_cast<long long>(a->batch) * a->heads * prm.q_tiles;
   B200_CHECK_ARG(tiles < (1ll << 30), "attention: grid too large");
-  const Attn64Split sp = attention64_split(tiles, prm.kv_halves);
+  const Attn64Split sp = HD == 64 ? attention64_split(tiles, prm.kv_halves) : Attn64Split{0, 1};
   long long grid_ll = tiles;
   prm.n_whole = static_cast<int>(tiles);
   prm.split = 1;
@@ -596,15 +630,16 @@ int launch_attention64(const b200_attention_args* a, cudaStream_t st) {
   const bool fp16 = a->dtype == B200_DTYPE_FP16;
   // measured on B200 (tools/bench_attention.py, 4096 / 1024 tokens): POLY 0 -> 154.8 / 30.0 us, 1 -> 146.5 / 28.7 us, 3 -> 154.7 / 30.1 us
   static const int poly = getenv("B200_ATTN_POLY") ? atoi(getenv("B200_ATTN_POLY")) : 1;  // tuning knob: 0 or 1
-  const dim3 grid(static_cast<unsigned>(grid_ll)), block(Attn64Cfg::THREADS);
+  const dim3 grid(static_cast<unsigned>(grid_ll)), block(Attn64Cfg<64>::THREADS);
   cudaError_t e;
-#define B200_A64(P, S) (fp16 ? launch_pdl(attention64_kernel<true, P, S>, grid, block, Attn64Cfg::SMEM_BYTES, st, prm) \
-                             : launch_pdl(attention64_kernel<false, P, S>, grid, block, Attn64Cfg::SMEM_BYTES, st, prm))
-  if (prm.split > 1) e = B200_A64(1, true);
-  else if (poly >= 1) e = B200_A64(1, false);
-  else e = B200_A64(0, false);
+#define B200_A64(D, P, S) (fp16 ? launch_pdl(attention64_kernel<D, true, P, S>, grid, block, Attn64Cfg<D>::SMEM_BYTES, st, prm) \
+                                : launch_pdl(attention64_kernel<D, false, P, S>, grid, block, Attn64Cfg<D>::SMEM_BYTES, st, prm))
+  if (HD == 128) e = B200_A64(128, 1, false);
+  else if (prm.split > 1) e = B200_A64(64, 1, true);
+  else if (poly >= 1) e = B200_A64(64, 1, false);
+  else e = B200_A64(64, 0, false);
 #undef B200_A64
-  if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention (head_dim 64) launch: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "attention (head_dim %d) launch: %s", HD, cudaGetErrorString(e));
   return 0;
 }
 

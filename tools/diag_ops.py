@@ -25,6 +25,11 @@ CASES = {
     "attn_d128_1blk": dict(kind="attn", B=1, H=1, Sq=128, Sk=128, D=128),
     "attn_d128_flux": dict(kind="attn", B=1, H=24, Sq=4608, Sk=4608, D=128),
     "attn_d128_nq1": dict(kind="attn", B=1, H=4, Sq=640, Sk=640, D=128, nq=1),
+    "attn_d128_nq2": dict(kind="attn", B=1, H=4, Sq=640, Sk=640, D=128, nq=2),     # attention.cu (the head_dim-128 default is attention64.cu)
+    "attn_d128_ragged": dict(kind="attn", B=2, H=3, Sq=200, Sk=333, D=128),
+    "attn_d128_1half": dict(kind="attn", B=1, H=2, Sq=130, Sk=40, D=128),
+    "attn_d128_fp16": dict(kind="attn", B=1, H=4, Sq=512, Sk=512, D=128, fp16=True),
+    "attn_d128_bigvals": dict(kind="attn", B=1, H=2, Sq=256, Sk=1024, D=128, qscale=4.0),
     "attn_d64_fp16": dict(kind="attn", B=1, H=4, Sq=512, Sk=512, D=64, fp16=True),
     "attn_bigvals": dict(kind="attn", B=1, H=2, Sq=256, Sk=1024, D=64, qscale=6.0),
     # every count of 64-key halves with a ragged tail: each exit of the software-pipelined softmax loop (attention64.cu)
