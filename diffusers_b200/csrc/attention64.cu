@@ -2,9 +2,9 @@
 // (B200_ATTN_V2=0 falls back to the kernel in attention.cu).
 //
 // Structure (2 CTAs per SM, 256 threads each):
-//   warp 0  TMA producer (Q once, K / V rings in 64-key halves)
+//   warp 0  TMA producer (Q once, K ring in 64-key halves); warp 3: TMA producer of the V ring
 //   warp 1  tcgen05.mma issuer:  S(h) = Q K_h^T  (SS, 128 x 64 x 64)   and   O += P(h) V_h  (TS: P from TMEM, V MN-major)
-//   warp 2  TMEM allocator (idle afterwards), warp 3 idle         -> warps 0-3 give their registers away (setmaxnreg.dec)
+//   warp 2  TMEM allocator (idle afterwards)                      -> warps 0-3 give their registers away (setmaxnreg.dec)
 //   warps 4-7  softmax warpgroup, thread = query row               -> 200 registers per thread (setmaxnreg.inc)
 //
 //   TMEM (256 columns): S0 [0,64)  S1 [64,128)  P0 [128,160)  P1 [160,192)  O [192,256)
@@ -70,12 +70,17 @@ struct Attn64Cfg {
   static constexpr int KV_SLAB = 64 * 64 * 2;    // 8 KB
   static constexpr int Q_BYTES = SLABS * Q_SLAB;
   static constexpr int KV_BYTES = SLABS * KV_SLAB;  // one 64-key half of K or V
-  static constexpr int KS = HD == 64 ? 4 : 2, VS = KS;
+  // head_dim 128: three K stages and two V stages are what two CTAs per SM leave room for (115,712 bytes each): K(h+2) is
+  // needed half a step after its stage frees, V(h) a step and a half after
+  static constexpr int KS = HD == 64 ? 4 : 3, VS = HD == 64 ? 4 : 2;
   static constexpr int LA = HD == 64 ? 2 : 1;    // score buffers = halves S is issued ahead of the softmax
   static constexpr int TMEM_COLS = 256;
   static constexpr int S_COL = 0, P_COL = LA * 64, O_COL = P_COL + 64;
   static_assert(O_COL + HD <= TMEM_COLS, "TMEM budget");
-  static constexpr int SMEM_BYTES = Q_BYTES + (KS + VS) * KV_BYTES + 1024 + 256;
+  // (head_dim 128 has no room for alignment slack: the dynamic shared memory is declared 1024-byte aligned and checked)
+  static constexpr int ALIGN_SLACK = HD == 64 ? 1024 : 0;
+  static constexpr int SMEM_BYTES = Q_BYTES + (KS + VS) * KV_BYTES + ALIGN_SLACK + 256;
+  static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two CTAs per SM");
   static constexpr int THREADS = 256;
   static constexpr int REGS_LOW = 56, REGS_HIGH = 200;  // 128 * (56 + 200) = 32768 = half of the SM's register file
 };
@@ -90,8 +95,9 @@ __global__ void __launch_bounds__(Attn64Cfg<HD>::THREADS, 2) attention64_kernel(
   using H = Half16<FP16>;
   constexpr int KS = Cfg::KS, VS = Cfg::VS;
 
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  if (Cfg::ALIGN_SLACK == 0 && smem != smem_raw) __trap();  // the swizzled tiles need 1024-byte alignment
   uint8_t* s_q = smem;                        // [128][64]
   uint8_t* s_k = s_q + Cfg::Q_BYTES;          // [KS][64][64]
   uint8_t* s_v = s_k + KS * Cfg::KV_BYTES;    // [VS][64][64]
@@ -169,8 +175,11 @@ __global__ void __launch_bounds__(Attn64Cfg<HD>::THREADS, 2) attention64_kernel(
 #pragma unroll
         for (int s = 0; s < SLABS; ++s) tma_load_4d(s_q + s * Cfg::Q_SLAB, &p.q_map, q_full, s * 64, q_row0, head, b);
       }
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0;
+      // K ring here, V ring in warp 3: one in-order loop over both made every K load wait for the V stage before it, i.e. for
+      // a P V two halves back - with two stages per ring (head_dim 128) K(h+3) was then requested half a step before S(h+3)
+      // needed it and the softmax waited for scores at the start of every step
+      int ks = 0;
+      uint32_t kph = 0;
       for (int h = h_begin; h < h_end; ++h) {
         mbar_wait(&k_empty[ks], kph ^ 1u);
         if (elect_one()) {
@@ -180,6 +189,12 @@ __global__ void __launch_bounds__(Attn64Cfg<HD>::THREADS, 2) attention64_kernel(
             tma_load_4d(s_k + ks * Cfg::KV_BYTES + s * Cfg::KV_SLAB, &p.k_map, &k_full[ks], s * 64, h * 64, head, b);
         }
         if (++ks == KS) { ks = 0; kph ^= 1u; }
+      }
+    } else if (warp == 3) {
+      // ===================== TMA producer of V =====================
+      int vs = 0;
+      uint32_t vph = 0;
+      for (int h = h_begin; h < h_end; ++h) {
         mbar_wait(&v_empty[vs], vph ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(&v_full[vs], Cfg::KV_BYTES);
@@ -220,33 +235,25 @@ __global__ void __launch_bounds__(Attn64Cfg<HD>::THREADS, 2) attention64_kernel(
       };
 
       mbar_wait(q_full, 0);
-      for (int h0 = 0; h0 < LA && h0 < n_half; ++h0) {  // prologue: every score buffer filled
+      // S is always issued TWO halves ahead of the P V it precedes; with one score buffer (head_dim 128) S(h+2) additionally waits
+      // until the softmax has read S(h+1) into registers (s_free), which happens in the middle of softmax step h - well before
+      // P(h) exists.  (Issuing S(h+1) only after P(h-1) V had been issued left the softmax waiting for the score MMA at the start
+      // of every step: 362 us instead of 272 for the Flux shape.)
+      auto issue_scores = [&](int hh) {  // S(hh) into buffer hh % LA
+        if (hh >= LA) mbar_wait(&s_free[(hh - LA) % LA], ((hh - LA) / LA) & 1u);
         mbar_wait(&k_full[ks], kph);
         tc_fence_after();
         if (elect_one()) {
-          issue_s(h0, ks);
-          umma_commit(&s_full[h0]);
+          issue_s(hh % LA, ks);
+          umma_commit(&s_full[hh % LA]);
           umma_commit(&k_empty[ks]);
         }
         if (++ks == KS) { ks = 0; kph ^= 1u; }
-      }
-      // The softmax reads S(h) into registers one step before it turns it into P(h) (software pipelining), so the score
-      // buffer of half h is free a whole step before P(h) exists: S(h+2) is issued as soon as s_free(h) arrives, AHEAD of
-      // P(h) V(h), and is complete when the softmax asks for it.
+      };
+      for (int h0 = 0; h0 < 2 && h0 < n_half; ++h0) issue_scores(h0);
       for (int h = 0; h < n_half; ++h) {
         const int buf = h & 1;
-        if (h + LA < n_half) {
-          const int sbuf = h % LA;
-          mbar_wait(&s_free[sbuf], (h / LA) & 1u);
-          mbar_wait(&k_full[ks], kph);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_s(sbuf, ks);
-            umma_commit(&s_full[sbuf]);
-            umma_commit(&k_empty[ks]);
-          }
-          if (++ks == KS) { ks = 0; kph ^= 1u; }
-        }
+        if (h + 2 < n_half) issue_scores(h + 2);
         mbar_wait(&p_full[buf], (h >> 1) & 1u);
         mbar_wait(&v_full[vs], vph);
         tc_fence_after();
@@ -334,7 +341,10 @@ __global__ void __launch_bounds__(Attn64Cfg<HD>::THREADS, 2) attention64_kernel(
       constexpr bool has_next = MODE != 2;
       const int buf = h & 1;
       const uint32_t p_t = tmem_base + lane_off + Cfg::P_COL + buf * 32;
-      if (has_next) {
+      // With two score buffers S(h+1) was issued a whole step ago and is read first thing; with one buffer (head_dim 128) it was
+      // issued in the middle of the previous step behind up to ~1000 cycles of queued MMAs of both CTAs of the SM, so its read
+      // comes after the first block of exponentials (which only needs `cur`): the step never starts by waiting for the tensor pipe.
+      if (has_next && LA > 1) {
         mbar_wait_warp(&s_full[(h + 1) % LA], ((h + 1) / LA) & 1u);
         tc_fence_after();
         load_scores(nxt, h + 1);
@@ -346,6 +356,11 @@ __global__ void __launch_bounds__(Attn64Cfg<HD>::THREADS, 2) attention64_kernel(
       tmem_st16(p_t, pk);  // keys 0..31 of the half -> P columns 0..15
       float mx = -INFINITY;
       if (has_next) {
+        if (LA == 1) {
+          mbar_wait_warp(&s_full[0], (h + 1) & 1u);
+          tc_fence_after();
+          load_scores(nxt, h + 1);
+        }
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(&s_free[(h + 1) % LA]);  // S(h+1) is in registers: its TMEM buffer may take S(h+1+LA)

@@ -28,7 +28,7 @@ for step in "$@"; do
     flux)    timeout 900 python bench.py --workload flux --steps 5 > gpurun_out/bench_flux.json 2> gpurun_out/bench_flux.err; echo "flux rc=$?" ;;
     vae)     timeout 600 python bench.py --workload vae > gpurun_out/bench_vae.json 2> gpurun_out/bench_vae.err; echo "vae rc=$?" ;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python tools/profile_forward.py ncu > gpurun_out/launches.log 2>&1; echo "launches rc=$?" ;;
-    ncuhot_*) t=${step#ncuhot_}; timeout 600 ncu --section SourceCounters --section WarpStateStats --section SchedulerStats --section SpeedOfLight --section LaunchStats --import-source on --clock-control none --profile-from-start off --warp-sampling-interval 0 -c 3 -f -o gpurun_out/r2_hot_$t python tools/ncu_hot.py $t > gpurun_out/ncu_hot_$t.log 2>&1; echo "ncuhot $t rc=$?" ;;
+    ncuhot_*) t=${step#ncuhot_}; timeout 600 ncu --section SourceCounters --section WarpStateStats --section SchedulerStats --section SpeedOfLight --section LaunchStats --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --import-source on --clock-control none --profile-from-start off --warp-sampling-interval 0 -c 3 -f -o gpurun_out/r2_hot_$t python tools/ncu_hot.py $t > gpurun_out/ncu_hot_$t.log 2>&1; echo "ncuhot $t rc=$?" ;;
     smoke)   timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
     *)       timeout 900 bash -c "$step" ; echo "custom rc=$?" ;;
   esac

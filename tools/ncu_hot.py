@@ -25,6 +25,10 @@ elif what in ("gn", "gn64"):
     xs = [rnd(2 * hw, C) for _ in range(4)]
     gam, bet = rnd(C), rnd(C)
     fn = lambda i: ops.group_norm(xs[i % 4], batch=2, hw=hw, groups=32, eps=1e-5, gamma=gam, beta=bet, silu=True)  # noqa: E731
+elif what == "attn128":
+    qkvs = [rnd(1, 4608, 3 * 24 * 128) for _ in range(2)]
+    C = 24 * 128
+    fn = lambda i: ops.attention(qkvs[i % 2][..., :C], qkvs[i % 2][..., C:2 * C], qkvs[i % 2][..., 2 * C:], heads=24, head_dim=128)  # noqa: E731
 else:
     S, H = (4096, 10) if what == "attn" else (1024, 20)
     qkvs = [rnd(2, S, 3 * H * 64) for _ in range(2)]
