@@ -44,6 +44,7 @@ class AttentionArgs(C.Structure):
         ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
         ("scale", C.c_float), ("dtype", C.c_int32), ("nq_override", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("o_seg_rows", C.c_int32), ("o_seg", C.c_void_p * 8),
     ]
 
 
@@ -74,6 +75,7 @@ class QkNormRopeArgs(C.Structure):
         ("txt_rows", C.c_int32), ("seq", C.c_int32),
         ("wq", C.c_void_p), ("wk", C.c_void_p), ("wq_txt", C.c_void_p), ("wk_txt", C.c_void_p),
         ("cos_table", C.c_void_p), ("sin_table", C.c_void_p), ("eps", C.c_float), ("dtype", C.c_int32),
+        ("txt_period", C.c_int32),
     ]
 
 
@@ -129,6 +131,11 @@ def lib():
         _lib.b200_ddpm_step.argtypes = [VP, VP, VP, VP, I64, F32, F32, F32, F32, F32, I32, F32, I32, VP]
         _lib.b200_softmax_rows.argtypes = [VP, I64, VP, I64, I32, I32, F32, I32, VP]
         _lib.b200_transpose_16.argtypes = [VP, I64, VP, I64, I32, I32, VP]
+        _lib.b200_peer_alloc.argtypes = [I64, C.POINTER(VP), C.c_char_p]
+        _lib.b200_peer_open.argtypes = [C.c_char_p, C.POINTER(VP)]
+        _lib.b200_peer_close.argtypes = [VP]
+        _lib.b200_peer_free.argtypes = [VP]
+        _lib.b200_peer_barrier.argtypes = [C.POINTER(VP), VP, I32, I32, VP]
         for fn in ("b200_conv_gemm", "b200_attention", "b200_group_norm", "b200_layer_norm", "b200_small_linear",
                    "b200_qk_norm_rope"):
             getattr(_lib, fn).argtypes = [VP, VP]

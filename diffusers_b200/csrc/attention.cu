@@ -475,7 +475,7 @@ int64_t b200_attention_workspace_bytes(int32_t batch, int32_t heads, int32_t sq,
 
 int b200_attention(const b200_attention_args* a, void* stream) {
   using namespace b200;
-  B200_CHECK_ARG(a && a->q && a->k && a->v && a->o, "attention: null pointer");
+  B200_CHECK_ARG(a && a->q && a->k && a->v && (a->o || a->o_seg_rows > 0), "attention: null pointer");
   B200_CHECK_ARG(a->head_dim == 64 || a->head_dim == 128, "attention: head_dim %d (64 or 128 supported)", a->head_dim);
   B200_CHECK_ARG(a->batch > 0 && a->heads > 0 && a->sq > 0 && a->sk > 0, "attention: bad shape");
   B200_CHECK_ARG(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->o), "attention: alignment");
@@ -488,6 +488,7 @@ int b200_attention(const b200_attention_args* a, void* stream) {
     return launch_attention64(a, static_cast<cudaStream_t>(stream));
   if (HD == 128 && a->nq_override == 0 && attention128_v2_enabled())
     return launch_attention64(a, static_cast<cudaStream_t>(stream));
+  B200_CHECK_ARG(a->o_seg_rows <= 0, "attention: o_seg (context parallelism) needs the default kernel (attention64.cu)");
   if (HD == 64 && a->nq_override != 2 && attention_pipe_enabled())
     return launch_attention64_pipe(a, static_cast<cudaStream_t>(stream));
 

@@ -57,6 +57,10 @@ struct Attn64Params {
   int n_whole, split;
   float* ws_part;        // [tail tiles][split][64 * 128 O (column-major: [col][row]) + 128 m + 128 l] fp32
   int* ws_ticket;        // [tail tiles], zero between launches (the merging CTA resets it)
+  // context parallelism: output row r lives in o_seg[r / o_seg_rows] (the buffer of the rank that owns it, a peer mapping
+  // over NVLink for the other ranks) at row r % o_seg_rows; o_seg_rows == 0 -> plain `o`
+  void* o_seg[8];
+  int o_seg_rows;
 };
 
 // HD = 64 (SDXL) or 128 (Flux).  Operands live in shared memory as HD / 64 "slabs" of 64 columns (128-byte swizzled rows).
@@ -440,8 +444,12 @@ __global__ void __launch_bounds__(Attn64Cfg<HD>::THREADS, 2) attention64_kernel(
     mbar_wait_warp(o_full, 0);
     tc_fence_after();
     const int qrow = q_row0 + row;
-    typename H::T* const orow = static_cast<typename H::T*>(p.o) + static_cast<long long>(b) * p.o_batch_stride +
-                                static_cast<long long>(qrow) * p.o_row_stride + head * HD;
+    typename H::T* orow = static_cast<typename H::T*>(p.o) + static_cast<long long>(b) * p.o_batch_stride +
+                          static_cast<long long>(qrow) * p.o_row_stride + head * HD;
+    if (p.o_seg_rows > 0) {  // the all-to-all back to the row owners, folded into this store
+      const int seg = min(qrow / p.o_seg_rows, 7);
+      orow = static_cast<typename H::T*>(p.o_seg[seg]) + static_cast<long long>(qrow - seg * p.o_seg_rows) * p.o_row_stride + head * HD;
+    }
     bool parked = false;
     if constexpr (SPLIT) if (is_part) {
       parked = true;
@@ -620,6 +628,17 @@ int launch_attention64(const b200_attention_args* a, cudaStream_t st) {
   prm.o = a->o;
   prm.o_row_stride = a->o_row_stride;
   prm.o_batch_stride = a->o_batch_stride;
+  if (a->o_seg_rows > 0) {
+    B200_CHECK_ARG(a->batch == 1, "attention: o_seg needs batch 1");
+    const int nseg = (a->sq + a->o_seg_rows - 1) / a->o_seg_rows;
+    B200_CHECK_ARG(nseg <= 8, "attention: %d output segments (at most 8)", nseg);
+    for (int i = 0; i < nseg; ++i) {
+      B200_CHECK_ARG(a->o_seg[i] != nullptr && (reinterpret_cast<uintptr_t>(a->o_seg[i]) & 15u) == 0, "attention: o_seg[%d] null or not 16-byte aligned", i);
+      prm.o_seg[i] = a->o_seg[i];
+    }
+    for (int i = nseg; i < 8; ++i) prm.o_seg[i] = a->o_seg[nseg - 1];
+    prm.o_seg_rows = a->o_seg_rows;
+  }
   prm.batch = a->batch;
   prm.heads = a->heads;
   prm.sq = a->sq;

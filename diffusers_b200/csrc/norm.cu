@@ -607,6 +607,7 @@ struct QkNormRopeParams {
   int rows, heads, k_off;
   int txt_rows;  // rows [0, txt_rows) of every sequence use the *_txt weights (joint attention: text first)
   int seq;       // rows per sequence (rope position = row % seq)
+  int txt_period;  // the text rows are [0, txt_rows) of every txt_period positions (== seq unless context-parallel)
   const void* wq;
   const void* wk;
   const void* wq_txt;
@@ -629,7 +630,7 @@ __global__ void __launch_bounds__(256) qk_norm_rope_kernel(const QkNormRopeParam
   if (head >= p.heads) return;
   const long long row = blockIdx.x;
   const int pos = static_cast<int>(static_cast<unsigned>(blockIdx.x) % static_cast<unsigned>(p.seq));
-  const bool is_txt = pos < p.txt_rows;
+  const bool is_txt = static_cast<int>(static_cast<unsigned>(pos) % static_cast<unsigned>(p.txt_period)) < p.txt_rows;
   typename H::T* base = static_cast<typename H::T*>(p.qkv) + row * p.ld + head * HD + lane * EPL;
   float cs[EPL], sn[EPL];
   if (p.cos_t) {
@@ -891,6 +892,7 @@ int b200_qk_norm_rope(const b200_qk_norm_rope_args* a, void* stream) {
   QkNormRopeParams p;
   p.qkv = a->qkv; p.ld = a->ld; p.rows = a->rows; p.heads = a->heads; p.k_off = a->k_off;
   p.txt_rows = a->txt_rows; p.seq = a->seq;
+  p.txt_period = a->txt_period > 0 ? a->txt_period : a->seq;
   p.wq = a->wq; p.wk = a->wk;
   p.wq_txt = a->wq_txt ? a->wq_txt : a->wq;
   p.wk_txt = a->wk_txt ? a->wk_txt : a->wk;

@@ -249,16 +249,27 @@ def _attention_workspace(device, B, heads, Sq, Sk, head_dim):
     return ws
 
 
-def attention(q, k, v, *, heads, head_dim, scale=None, out=None, nq=0):
+def attention(q, k, v, *, heads, head_dim, scale=None, out=None, nq=0, o_seg=None, o_seg_rows=0):
     """softmax(q k^T * scale) v.  q [B, Sq, heads*head_dim-wide rows], k/v [B, Sk, ...]: 3-D views whose last
     dim starts at this tensor's first head (row stride / batch stride taken from the view, so slices of a fused
-    QKV buffer work).  Returns [B, Sq, heads*head_dim]."""
+    QKV buffer work).  Returns [B, Sq, heads*head_dim].
+    o_seg (context parallelism): list of 2-D [o_seg_rows, heads*head_dim]-wide views (same row stride), one per
+    o_seg_rows query rows; row r is stored into o_seg[r // o_seg_rows][r % o_seg_rows] and nothing is returned."""
     _need_cuda(q, "q")
     B, Sq = q.shape[0], q.shape[1]
     Sk = k.shape[1]
-    if out is None:
-        out = torch.empty((B, Sq, heads * head_dim), dtype=q.dtype, device=q.device)
     a = _lib.AttentionArgs()
+    if o_seg is not None:
+        if B != 1 or o_seg_rows <= 0 or len(o_seg) * o_seg_rows < Sq or len(o_seg) > 8:
+            raise B200Error("attention: o_seg needs batch 1 and ceil(Sq / o_seg_rows) <= 8 segments")
+        if any(t.stride(0) != o_seg[0].stride(0) or t.stride(1) != 1 for t in o_seg):
+            raise B200Error("attention: o_seg views must share one row stride")
+        out = o_seg[0].unsqueeze(0)
+        a.o_seg_rows = o_seg_rows
+        for i, t in enumerate(o_seg):
+            a.o_seg[i] = t.data_ptr()
+    elif out is None:
+        out = torch.empty((B, Sq, heads * head_dim), dtype=q.dtype, device=q.device)
     a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
     a.batch, a.heads, a.sq, a.sk, a.head_dim = B, heads, Sq, Sk, head_dim
     a.q_row_stride, a.q_batch_stride = q.stride(1), q.stride(0)
@@ -280,7 +291,7 @@ def attention(q, k, v, *, heads, head_dim, scale=None, out=None, nq=0):
     else:
         _lib.check(_lib.lib().b200_attention(C.byref(a), _stream()), "b200_attention")
     _count()
-    return out
+    return None if o_seg is not None else out
 
 
 _GN_WS = {}
@@ -539,14 +550,14 @@ def attention_unfused(q, k, v, *, scale):
     return linear(p, vt, D)
 
 
-def qk_norm_rope(qkv, *, heads, head_dim, k_off, seq, txt_rows=0, wq=None, wk=None, wq_txt=None, wk_txt=None,
+def qk_norm_rope(qkv, *, heads, head_dim, k_off, seq, txt_rows=0, txt_period=0, wq=None, wk=None, wq_txt=None, wk_txt=None,
                  cos=None, sin=None, eps=1e-6):
     """In place on qkv [rows, ld]: RMSNorm(q), RMSNorm(k) per head (+ weight), then rotary embedding."""
     _need_cuda(qkv, "qkv")
     a = _lib.QkNormRopeArgs()
     a.qkv, a.ld = qkv.data_ptr(), qkv.stride(0)
     a.rows, a.heads, a.head_dim, a.k_off = qkv.shape[0], heads, head_dim, k_off
-    a.txt_rows, a.seq = txt_rows, seq
+    a.txt_rows, a.seq, a.txt_period = txt_rows, seq, txt_period
     a.wq, a.wk, a.wq_txt, a.wk_txt = _ptr(wq), _ptr(wk), _ptr(wq_txt), _ptr(wk_txt)
     a.cos_table, a.sin_table = _ptr(cos), _ptr(sin)
     a.eps = eps

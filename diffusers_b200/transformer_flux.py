@@ -60,6 +60,7 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         self._ctx = None
         self._rope_key = None
         self._rope = None
+        self._cp = None  # context parallelism (enable_parallelism): dict(world, rank, group, plans, peers)
 
     def _reg(self, t, device):
         name = f"w{self._n}"
@@ -137,6 +138,9 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
 
     def reference_state_dict(self):
         """The reference's `state_dict()` rebuilt from the packed buffers (exact inverse of `_build`)."""
+        if self._cp is not None:
+            raise RuntimeError("reference_state_dict: the fused QKV weights were permuted for context parallelism (enable_parallelism); "
+                               "export the checkpoint from a model without it")
         cfg = self.config
         spec = specs.flux_params(dict(cfg))
         W = lambda n: self._buffers[n].detach().cpu()  # noqa: E731
@@ -278,6 +282,140 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         e = ops.small_linear(pooled.to(dt), self.W(self.p_emb[0]["w"]), bias=self.W(self.p_emb[0]["b"]), act_out=ACT_SILU)
         return ops.small_linear(e, self.W(self.p_emb[1]["w"]), bias=self.W(self.p_emb[1]["b"]), addend=emb)
 
+    # ------------------------------------------------------------------ context parallelism (Ulysses)
+    def enable_parallelism(self, *, config, cp_plan=None, group=None):
+        """ModelMixin.enable_parallelism (models/modeling_utils.py:1607) for `ContextParallelConfig(ulysses_degree=N)`: the
+        token sequence of ONE sample is sharded over the N ranks of the (default) process group, every rank calls forward
+        with the full inputs and receives the full output, like the reference's `_cp_plan` (transformer_flux.py:573: inputs
+        split on the sequence dim, `proj_out` gathered).  See context_parallel.py for how the two all-to-alls of
+        TemplatedUlyssesAttention (attention_dispatch.py:2504) are folded into the QKV GEMM and the attention kernel."""
+        import torch.distributed as dist
+
+        from .context_parallel import ContextParallelConfig, UlyssesPlan
+        if cp_plan is not None:
+            raise NotImplementedError("custom cp_plan: the built-in plan of FluxTransformer2DModel is the only one")
+        if not isinstance(config, ContextParallelConfig):
+            cpc = getattr(config, "context_parallel_config", None)  # the reference's ParallelConfig wrapper
+            if cpc is None:
+                raise NotImplementedError("only context parallelism (ContextParallelConfig) is built")
+            config = ContextParallelConfig(ring_degree=cpc.ring_degree, ulysses_degree=cpc.ulysses_degree) if not isinstance(cpc, ContextParallelConfig) else cpc
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("torch.distributed must be initialized before calling `enable_parallelism`.")
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if config.ulysses_degree != world:
+            raise ValueError(f"ulysses_degree ({config.ulysses_degree}) must equal the size of the process group ({world})")
+        if self._cp is not None:
+            raise RuntimeError("enable_parallelism was already called on this model")
+        if world == 1:
+            return
+        cfg = self.config
+        probe = UlyssesPlan(world, rank, world * 8, world * 8, cfg["num_attention_heads"], cfg["attention_head_dim"])  # validates heads % world
+        perm = probe.qkv_row_permutation().to(self.device)
+        for blk in self.double + self.single:
+            for key in ("qkv", "aqkv"):
+                if key in blk:
+                    for part in ("w", "b"):
+                        name = blk[key][part]
+                        self._buffers[name] = self._buffers[name].index_select(0, perm).contiguous()
+        self.__dict__.pop("_weight_prefetch_plan", None)  # the launch order (and the weight addresses) changed
+        self._cp = dict(world=world, rank=rank, group=group, plans={}, peers={}, rope_key=None, rope=None)
+
+    def _cp_state(self, T, S, out_ch):
+        """(plan, peer buffers) for a joint sequence of T text + S image tokens; the peer-mapped buffers are allocated (a
+        collective step: every rank reaches it with the same shapes) on first use."""
+        from .context_parallel import PeerGroup, UlyssesPlan
+        cp = self._cp
+        key = (T, S, out_ch)
+        if key not in cp["plans"]:
+            cfg = self.config
+            plan = UlyssesPlan(cp["world"], cp["rank"], T, S, cfg["num_attention_heads"], cfg["attention_head_dim"])
+            es = torch.empty((), dtype=self._dtype).element_size()
+            rup = lambda n: (n + 255) // 256 * 256  # noqa: E731
+            nbytes = rup(plan.L * 3 * plan.Dl * es) + rup(plan.Ll * plan.D * es) + rup(S * out_ch * es)
+            pg = PeerGroup(nbytes, cp["group"])
+            bufs = dict(pg=pg, J=pg.carve(self._dtype, (plan.L, 3 * plan.Dl)), A=pg.carve(self._dtype, (plan.Ll, plan.D)),
+                        O=pg.carve(self._dtype, (S, out_ch)))
+            cp["plans"][key] = (plan, bufs)
+        return cp["plans"][key]
+
+    def _cp_rope(self, plan, rope):
+        cp = self._cp
+        if cp["rope_key"] is not rope[0]:
+            g = plan.joint_to_rank_major().to(rope[0].device)
+            cp["rope"] = (rope[0].index_select(0, g).contiguous(), rope[1].index_select(0, g).contiguous())
+            cp["rope_key"] = rope[0]
+        return cp["rope"]
+
+    def _forward_one_cp(self, x_in, ctx, mod, rope):
+        """_forward_one with the joint sequence sharded over the ranks: this rank carries text rows [t0, t1) and image
+        rows [s0, s1) through every per-token op; only the attention sees the whole sequence, for its own heads."""
+        cfg = self.config
+        D, hd = self.D, cfg["attention_head_dim"]
+        S, T = x_in.shape[0], ctx.shape[0]
+        plan, bufs = self._cp_state(T, S, self.proj_out["n"])
+        pg, J, A, O = bufs["pg"], bufs["J"], bufs["A"], bufs["O"]
+        r, P, Tl, Sl, Ll, L, Dl, hl = plan.rank, plan.world, plan.Tl, plan.Sl, plan.Ll, plan.L, plan.Dl, plan.hl
+        (t0, t1), (s0, s1) = plan.text_rows(), plan.image_rows()
+        b0 = plan.block()[0]
+        cos, sin = self._cp_rope(plan, rope)
+        dev = x_in.device
+        hbuf = torch.empty((Ll, D), dtype=self._dtype, device=dev)  # this rank's slice of the residual stream [text | image]
+        c, x = hbuf[:Tl], hbuf[Tl:]
+        self._lin(self.x_embedder, x_in[s0:s1], out=x)
+        c.copy_(ctx[t0:t1])
+        Jl, Al = J[r], A[r]
+        J3 = Jl.view(1, L, 3 * Dl)
+        o_seg = [A[s_][:, r * Dl:(r + 1) * Dl] for s_ in range(P)]  # rank s_ owns output rows [s_*Ll, (s_+1)*Ll): my heads' columns of its A
+        order = plan.send_order()
+
+        def m(off, i):
+            return mod[:, off + i * D: off + (i + 1) * D]
+
+        def send_qkv(l, rows_in, row_off):
+            # the first all-to-all of Ulysses, folded into the GEMM: destination d receives its heads' [q | k | v] columns of my rows
+            n = rows_in.shape[0]
+            for d in order:
+                ops.linear(rows_in, self.W(l["w"])[d * 3 * Dl:(d + 1) * 3 * Dl], 3 * Dl, bias=self.W(l["b"])[d * 3 * Dl:(d + 1) * 3 * Dl],
+                           out=J[d][b0 + row_off: b0 + row_off + n])
+
+        def attend(blk, txt_rows):
+            pg.barrier()  # every rank's q/k/v tiles have landed in my J
+            ops.qk_norm_rope(Jl, heads=hl, head_dim=hd, k_off=Dl, seq=L, txt_rows=txt_rows, txt_period=Ll, wq=self.W(blk["nq"]),
+                             wk=self.W(blk["nk"]), wq_txt=self.W(blk["naq"]) if "naq" in blk else None,
+                             wk_txt=self.W(blk["nak"]) if "nak" in blk else None, cos=cos, sin=sin, eps=1e-6)
+            # the second all-to-all, folded into the attention epilogue: row i goes to the rank that owns it
+            ops.attention(J3[:, :, :Dl], J3[:, :, Dl:2 * Dl], J3[:, :, 2 * Dl:], heads=hl, head_dim=hd, o_seg=o_seg, o_seg_rows=Ll)
+            pg.barrier()  # every rank's output rows have landed in my A
+            return Al
+
+        for blk in self.double:
+            o, co = blk["mod"], blk["cmod"]
+            nx = ops.layer_norm(x, eps=1e-6, scale=m(o, 1), shift=m(o, 0), rows_per_group=Sl)
+            nc = ops.layer_norm(c, eps=1e-6, scale=m(co, 1), shift=m(co, 0), rows_per_group=Tl)
+            send_qkv(blk["aqkv"], nc, 0)
+            send_qkv(blk["qkv"], nx, Tl)
+            a = attend(blk, Tl)
+            self._lin(blk["out"], a[Tl:], gate=m(o, 2), rows_per_group=Sl, residual=x, out=x)
+            self._lin(blk["aout"], a[:Tl], gate=m(co, 2), rows_per_group=Tl, residual=c, out=c)
+            nx = ops.layer_norm(x, eps=1e-6, scale=m(o, 4), shift=m(o, 3), rows_per_group=Sl)
+            h = self._lin(blk["ff1"], nx, act=ACT_GELU_TANH)
+            self._lin(blk["ff2"], h, gate=m(o, 5), rows_per_group=Sl, residual=x, out=x)
+            nc = ops.layer_norm(c, eps=1e-6, scale=m(co, 4), shift=m(co, 3), rows_per_group=Tl)
+            h = self._lin(blk["cff1"], nc, act=ACT_GELU_TANH)
+            self._lin(blk["cff2"], h, gate=m(co, 5), rows_per_group=Tl, residual=c, out=c)
+        for blk in self.single:
+            o = blk["mod"]
+            nh_ = ops.layer_norm(hbuf, eps=1e-6, scale=m(o, 1), shift=m(o, 0), rows_per_group=Ll)
+            send_qkv(blk["qkv"], nh_, 0)
+            mlp = self._lin(blk["mlp"], nh_, act=ACT_GELU_TANH)
+            a = attend(blk, 0)
+            self._lin(blk["out"], a, x2=mlp, gate=m(o, 2), rows_per_group=Ll, residual=hbuf, out=hbuf)
+        nx = ops.layer_norm(x, eps=1e-6, scale=m(self.mod_out, 0), shift=m(self.mod_out, 1), rows_per_group=Sl)
+        for d in order:  # `proj_out` gathered on every rank (_cp_plan: ContextParallelOutput(gather_dim=1))
+            self._lin(self.proj_out, nx, out=O[d][s0:s1])
+        pg.barrier()
+        return O[r].clone()
+
     # ------------------------------------------------------------------ one batch element
     def _lin(self, l, x, **kw):
         return ops.linear(x, self.W(l["w"]), l["n"], bias=self.W(l["b"]), **kw)
@@ -355,8 +493,9 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         ctx = self._context(encoder_hidden_states)
         rope = self._rope_tables(txt_ids, img_ids, owners=id_owners)
         out = torch.empty((B, S, self.proj_out["n"]), dtype=self._dtype, device=hs.device)
+        one = self._forward_one if self._cp is None else self._forward_one_cp
         for b in range(B):
-            out[b] = self._forward_one(hs[b], ctx[b], mod[b:b + 1], rope)
+            out[b] = one(hs[b], ctx[b], mod[b:b + 1], rope)
         if not return_dict:
             return (out,)
         return Transformer2DModelOutput(out)

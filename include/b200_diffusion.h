@@ -287,6 +287,12 @@ typedef struct {
    * NULL / too small: every tile is computed by one CTA.  Same results either way up to fp32 summation order of the merge. */
   void* workspace;
   int64_t workspace_bytes;
+  /* Context parallelism (see the peer-memory section): with o_seg_rows > 0 (batch must be 1) output row r of head h goes to
+   * o_seg[r / o_seg_rows] + (r % o_seg_rows) * o_row_stride + h * head_dim instead of `o` - the segments are the output
+   * buffers of the ranks that own those rows (peer mappings; the local one for this rank's own rows).  head_dim 64 / 128
+   * through the default kernel only. */
+  int32_t o_seg_rows;
+  void* o_seg[8];
 } b200_attention_args;
 
 int b200_attention(const b200_attention_args* args, void* stream);
@@ -325,6 +331,7 @@ typedef struct {
   const float* sin_table;
   float eps;
   int32_t dtype;
+  int32_t txt_period; /* 0 = seq; else the text rows are [0, txt_rows) of every txt_period rows (rank-major joint order of context parallelism) */
 } b200_qk_norm_rope_args;
 
 int b200_qk_norm_rope(const b200_qk_norm_rope_args* args, void* stream);
@@ -335,6 +342,30 @@ int b200_qk_norm_rope(const b200_qk_norm_rope_args* args, void* stream);
 int b200_ddpm_step(const void* model_output, const void* sample, const void* noise, void* prev_sample, int64_t n,
                    float sqrt_beta_prod_t, float sqrt_alpha_prod_t, float pred_original_coeff, float current_sample_coeff,
                    float sigma, int32_t clip_sample, float clip_range, int32_t dtype, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Peer memory over NVLink / NVSwitch — context parallelism (Ulysses) for one image on several GPUs of a node.
+ * Replaces the all-to-all collectives of  models/attention_dispatch.py:2504-2580 (TemplatedUlyssesAttention:
+ * _all_to_all_single on q/k/v before and on the output after the attention, funcol over NCCL) driven by
+ * hooks/context_parallel.py:129,220 and transformers/transformer_flux.py:573-581 (_cp_plan).
+ * No collective library sits on the data path: b200_conv_gemm stores the QKV tiles of the heads a peer owns straight
+ * into that peer's buffer (`y` = a mapping returned by b200_peer_open), b200_attention stores every output row into
+ * the peer that owns the row (o_seg below), and b200_peer_barrier separates the phases.
+ *   b200_peer_alloc   : cudaMalloc + zero + export; `handle64` receives the 64-byte cudaIpcMemHandle_t (HOST pointer)
+ *   b200_peer_open    : maps another process's buffer (same node) into this process; peer access is enabled lazily
+ *   b200_peer_close / b200_peer_free : undo the two above
+ *   b200_peer_barrier : one small kernel on `stream`.  flags is a HOST array of nranks device pointers: flags[r] =
+ *                       this process's mapping of rank r's flag words (>= B200_MAX_PEERS uint32, zero at start);
+ *                       epoch = one local uint32 in device memory (zero at start; advanced by the kernel, so the
+ *                       call is CUDA-graph capturable).  Every rank must issue the same sequence of barriers.
+ *                       A rank that waits longer than 20 s traps (a CUDA error on that rank, never a hung GPU).
+ * ------------------------------------------------------------------------------------------- */
+#define B200_MAX_PEERS 8
+int b200_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
+int b200_peer_open(const unsigned char* handle64, void** ptr);
+int b200_peer_close(void* ptr);
+int b200_peer_free(void* ptr);
+int b200_peer_barrier(void* const* flags, void* epoch, int32_t rank, int32_t nranks, void* stream);
 
 #ifdef __cplusplus
 }
