@@ -30,7 +30,7 @@ class ConvGemmArgs(C.Structure):
         ("dtype", C.c_int32), ("tile_n", C.c_int32), ("out_fp32", C.c_int32), ("cluster_m", C.c_int32),
         ("debug_timestamps", C.c_void_p), ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
         ("row_stats_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_parts", C.c_int32), ("ln_eps", C.c_float),
-        ("up2x_parity", C.c_int32),
+        ("up2x_parity", C.c_int32), ("pad_after_only", C.c_int32),
     ]
 
 

@@ -138,7 +138,15 @@ class FromPretrainedMixin:
         if missing:
             raise ValueError(f"{root}: checkpoint lacks {len(missing)} tensors the model needs, e.g. {missing[:3]}")
         extra = {} if fold_norms is None else dict(fold_norms=fold_norms)
-        return cls(cfg, {k: sd[k] for k in spec}, dtype=torch_dtype, device=device, **extra)
+        keep = {k: sd[k] for k in spec}
+        opt = cls._optional_param_spec(cfg)
+        if opt and all(k in sd for k in opt):  # e.g. the encoder half of an AutoencoderKL checkpoint
+            keep.update({k: sd[k] for k in opt})
+        return cls(cfg, keep, dtype=torch_dtype, device=device, **extra)
+
+    @classmethod
+    def _optional_param_spec(cls, cfg):
+        return {}
 
     @classmethod
     def _param_spec_for(cls, cfg):

@@ -842,6 +842,7 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   else
     B200_CHECK_ARG(a->up2x_parity == 0, "conv_gemm: up2x_parity needs ksize 2");
   B200_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv_gemm: stride %d (need 1 or 2)", a->stride);
+  B200_CHECK_ARG(!a->pad_after_only || (a->stride == 2 && a->ksize == 3), "conv_gemm: pad_after_only is the stride-2 3x3 case");
   B200_CHECK_ARG(a->batch > 0 && a->H > 0 && a->W > 0 && a->N > 0, "conv_gemm: bad shape");
   B200_CHECK_ARG(a->dtype == B200_DTYPE_BF16 || a->dtype == B200_DTYPE_FP16, "conv_gemm: dtype %d", a->dtype);
   const int nsrc = (a->x[1] != nullptr && a->c[1] > 0) ? 2 : 1;
@@ -925,6 +926,12 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
         prm.tap_map[tap] = 0;
         prm.tap_dh[tap] = static_cast<int8_t>(r - 1);
         prm.tap_dw[tap] = static_cast<int8_t>(s - 1);
+      } else if (a->pad_after_only) {
+        // input row 2*ho + r:  r=0 -> even rows of ho, r=1 -> odd rows of ho, r=2 -> even rows of ho+1 (out of bounds at the bottom: zeros)
+        const int ph = (r == 1) ? 1 : 0, pw = (s == 1) ? 1 : 0;
+        prm.tap_map[tap] = static_cast<int8_t>(ph * 2 + pw);
+        prm.tap_dh[tap] = static_cast<int8_t>(r == 2 ? 1 : 0);
+        prm.tap_dw[tap] = static_cast<int8_t>(s == 2 ? 1 : 0);
       } else {
         // input row 2*ho + r - 1:  r=0 -> odd rows of ho-1, r=1 -> even rows of ho, r=2 -> odd rows of ho
         const int ph = (r == 1) ? 0 : 1, pw = (s == 1) ? 0 : 1;

@@ -129,7 +129,7 @@ class FoldedLayerNorm:
 
 def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, act=ACT_NONE, geglu=False,
               gate=None, rowvec=None, rows_per_group=0, residual=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None,
-              row_stats=False, ln=None):
+              row_stats=False, ln=None, pad_after_only=False):
     """y = epilogue(conv/linear(x [, x2]))  -  see b200_conv_gemm in include/b200_diffusion.h.
 
     x, x2: NHWC activations given as 2-D [batch*H*W, C] (or any shape whose last dim is C, contiguous rows).
@@ -166,6 +166,7 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
     a.out_fp32 = 1 if out_fp32 else 0
     a.cluster_m = cluster_m
     a.debug_timestamps = _ptr(debug_timestamps)
+    a.pad_after_only = 1 if pad_after_only else 0
     stats = None
     if row_stats:
         parts = int(_lib.lib().b200_conv_gemm_row_stats_parts(C.byref(a)))

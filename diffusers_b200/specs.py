@@ -239,6 +239,42 @@ def vae_decoder_params(cfg):
     return s
 
 
+def vae_encoder_params(cfg):
+    """AutoencoderKL: encoder.* + quant_conv (autoencoders/vae.py:59-180, autoencoder_kl.py:126) - image -> latent moments."""
+    s = _Spec()
+    boc = tuple(cfg["block_out_channels"])
+    lc = cfg["latent_channels"]
+    lpb = cfg.get("layers_per_block", 1)
+    for t in tuple(cfg.get("down_block_types", ("DownEncoderBlock2D",) * len(boc))):
+        if t != "DownEncoderBlock2D":
+            raise NotImplementedError(t)
+    e = "encoder"
+    s.conv(e + ".conv_in", cfg["in_channels"], boc[0], 3)
+    out_ch = boc[0]
+    for i in range(len(boc)):
+        in_ch, out_ch = out_ch, boc[i]
+        for j in range(lpb):
+            _resnet(s, f"{e}.down_blocks.{i}.resnets.{j}", in_ch if j == 0 else out_ch, out_ch, 0)
+        if i != len(boc) - 1:
+            s.conv(f"{e}.down_blocks.{i}.downsamplers.0.conv", out_ch, out_ch, 3)
+    _resnet(s, e + ".mid_block.resnets.0", boc[-1], boc[-1], 0)
+    if cfg.get("mid_block_add_attention", True):
+        _attn_block(s, e + ".mid_block.attentions.0", boc[-1])
+    _resnet(s, e + ".mid_block.resnets.1", boc[-1], boc[-1], 0)
+    s.norm(e + ".conv_norm_out", boc[-1])
+    s.conv(e + ".conv_out", boc[-1], 2 * lc, 3)
+    if cfg.get("use_quant_conv", True):
+        s.conv("quant_conv", 2 * lc, 2 * lc, 1)
+    return s
+
+
+def vae_params(cfg):
+    """The whole AutoencoderKL state_dict: encoder + quant_conv + post_quant_conv + decoder."""
+    s = vae_encoder_params(cfg)
+    s.update(vae_decoder_params(cfg))
+    return s
+
+
 def flux_params(cfg):
     s = _Spec()
     H, hd = cfg["num_attention_heads"], cfg["attention_head_dim"]

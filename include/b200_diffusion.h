@@ -127,6 +127,10 @@ typedef struct {
    * of which the launch writes its pixels.  The upsampled tensor never exists and the convolution does 4/9 of the FLOPs.
    * bias / act only; needs the TMA-store epilogue. */
   int32_t up2x_parity;
+  /* ---- stride-2 3x3 convolution with the padding on the bottom / right only: Downsample2D(padding=0) of the VAE encoder
+   * (models/downsampling.py:141-143: F.pad(x, (0, 1, 0, 1)) then Conv2d(stride=2, padding=0)); output (ho, wo) reads input rows
+   * 2 ho .. 2 ho + 2.  0 = the symmetric padding of 1 every other 3x3 convolution of the path uses. */
+  int32_t pad_after_only;
 } b200_conv_gemm_args;
 
 int b200_conv_gemm(const b200_conv_gemm_args* args, void* stream);

@@ -437,11 +437,37 @@ def gen_checkpoints(d):
     print("ckpt_sdxl_micro", n // 1024, "KiB;", "bf16-vs-fp32 max", float((img16.float() - img32).abs().max()))
 
 
+def gen_vae_encode(d):
+    """tests/golden/vae_encode.pt: AutoencoderKL.encode of the real reference (moments in fp32 and bf16 CPU eager, and one seeded
+    posterior sample) for the two tiny VAE configs (mid attention head_dim 128 -> fused kernel, 512 -> unfused path)."""
+    out = {}
+    g = torch.Generator().manual_seed(7)
+    for name, upd, seed in (("vae_enc_tiny", TINY_VAE, 12), ("vae_enc_d512", TINY_VAE_D512, 13)):
+        cfg = dict(specs.SDXL_VAE_CONFIG)
+        cfg.update(upd)
+        sd16, sd32 = _sd(specs.vae_params(cfg), seed=seed)
+        x = (torch.randn(2, 3, 64, 64, generator=g) * 0.6).clamp(-1, 1).bfloat16()
+        m = d.AutoencoderKL(**cfg).eval()
+        assert set(m.state_dict().keys()) == set(sd32.keys()), set(m.state_dict().keys()) ^ set(sd32.keys())
+        r32, r16 = _run(m, sd32, sd16, lambda mod, dt: mod.encode(x.to(dt)).latent_dist.parameters)
+        post = d.models.autoencoders.vae.DiagonalGaussianDistribution(r16)
+        smp = post.sample(generator=torch.Generator().manual_seed(0))
+        rt32 = None
+        if name == "vae_enc_tiny":
+            m32 = d.AutoencoderKL(**cfg).eval()
+            m32.load_state_dict(sd32)
+            with torch.no_grad():
+                rt32 = m32(x.float(), sample_posterior=False).sample   # encode -> mode -> decode
+        out[name] = dict(cfg=cfg, seed=seed, x=x, ref32=r32, ref16=r16, sample16=smp, sample_seed=0, roundtrip32=rt32)
+        print(name, tuple(r32.shape), float((r32 - r16.float()).abs().max()))
+    torch.save(out, os.path.join(OUT, "vae_encode.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     dmod = ref_shim.import_reference()
-    which = sys.argv[1:] or ["blocks", "layers", "schedulers", "steppers", "models", "pipelines", "checkpoints"]
+    which = sys.argv[1:] or ["blocks", "layers", "schedulers", "steppers", "models", "pipelines", "checkpoints", "vae_encode"]
     for w in which:
         globals()["gen_" + w](dmod)
     for f in sorted(os.listdir(OUT)):

@@ -84,6 +84,29 @@ def test_vae_decode(golden, name):
     assert float(d.mean()) <= 2.0 * float(e.mean()) and float(d.max()) <= 3.0 * float(e.max())
 
 
+@pytest.mark.parametrize("name", ["vae_enc_tiny", "vae_enc_d512"])
+def test_vae_encode(golden, name):
+    """N3: AutoencoderKL.encode (moments) against the reference's recorded fp32 / bf16 runs; the stride-2 convolutions use the
+    bottom/right-only padding of Downsample2D(padding=0) as tap offsets."""
+    from diffusers_b200.autoencoder_kl import AutoencoderKL
+    fx = golden("vae_encode")[name]
+    sd16, _ = state_dicts(specs.vae_params(fx["cfg"]), fx["seed"])
+    m = AutoencoderKL(fx["cfg"], sd16, dtype=torch.bfloat16, device="cuda")
+    post = m.encode(fx["x"].cuda()).latent_dist
+    _check(post.parameters, fx, name)
+    assert post.mean.shape[1] == 4 and post.sample(generator=torch.Generator().manual_seed(0)).shape == post.mean.shape
+    single = m.encode(fx["x"][:1].cuda(), return_dict=False)[0].parameters
+    assert float((single.float() - post.parameters[:1].float()).abs().max()) <= 3e-2
+    if fx["roundtrip32"] is not None:
+        rt = m(fx["x"].cuda()).sample
+        e = (rt.float().cpu() - fx["roundtrip32"]).abs()
+        print(f"{name}: encode->mode->decode vs reference fp32 max {float(e.max()):.4g} mean {float(e.mean()):.4g}")
+        assert float(e.mean()) <= 2e-2
+    decoder_only = AutoencoderKL(fx["cfg"], {k: v for k, v in sd16.items() if not k.startswith(("encoder.", "quant_conv."))}, device="cuda")
+    with pytest.raises(NotImplementedError):
+        decoder_only.encode(fx["x"].cuda())
+
+
 @pytest.mark.parametrize("name", ["flux_tiny", "flux_hd128"])
 def test_flux_transformer(golden, name):
     from diffusers_b200.transformer_flux import FluxTransformer2DModel

@@ -213,6 +213,30 @@ def test_vae_decode_matches_reference(golden, name):
     assert torch.allclose(out, fx["ref32"], atol=5e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("name", ["vae_enc_tiny", "vae_enc_d512"])
+def test_vae_encode_matches_reference(golden, name):
+    """N3: the oracle's AutoencoderKL.encode (moments) against the real reference's fp32 run (tests/golden/vae_encode.pt)."""
+    fx = golden("vae_encode")[name]
+    _, sd32 = state_dicts(specs.vae_params(fx["cfg"]), fx["seed"])
+    out = ovae.vae_encode(sd32, fx["cfg"], fx["x"].float())
+    assert tuple(out.shape) == tuple(fx["ref32"].shape)
+    assert float((out - fx["ref32"]).abs().max()) <= 5e-5
+    if fx["roundtrip32"] is not None:  # AutoencoderKL.forward: encode -> mode -> decode
+        mean = out[:, : out.shape[1] // 2]
+        assert float((ovae.vae_decode(sd32, fx["cfg"], mean) - fx["roundtrip32"]).abs().max()) <= 1e-4
+
+
+def test_diagonal_gaussian_is_the_reference_distribution(golden):
+    """The product's DiagonalGaussianDistribution on the reference's bf16 moments: same clamp / exp / seeded sample, bit for bit."""
+    import torch
+    from diffusers_b200.autoencoder_kl import DiagonalGaussianDistribution
+    fx = golden("vae_encode")["vae_enc_tiny"]
+    post = DiagonalGaussianDistribution(fx["ref16"])
+    assert torch.equal(post.sample(generator=torch.Generator().manual_seed(fx["sample_seed"])), fx["sample16"])
+    assert torch.equal(post.mode(), fx["ref16"][:, :4]) and post.std.dtype == torch.bfloat16
+    assert float(DiagonalGaussianDistribution(fx["ref32"]).kl().min()) > 0
+
+
 @pytest.mark.parametrize("name", ["flux_tiny", "flux_hd128"])
 def test_flux_matches_reference(golden, name):
     fx = golden("models")[name]
