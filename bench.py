@@ -453,6 +453,7 @@ class Ctx:
         self.dev = torch.device("cuda", local_rank)
         self.dt = torch.bfloat16
         self.pk = peaks()
+        self.gpu_dead = False
 
     def barrier(self):
         if self.world > 1:
@@ -639,9 +640,37 @@ def flux_section(cx, standalone=False):
             sec["attention"] = kernel_roofline(prof, total, "attention", pk)
         except Exception as e:  # noqa: BLE001
             sec["roofline"] = f"failed: {type(e).__name__}: {str(e)[:160]}"
+    # N > 1: ONE latent sharded over all N GPUs (Ulysses context parallelism over peer memory): strong scaling of
+    # the single-image latency.  Runs last: it permutes the QKV weight rows of `tr` in place.
+    if world > 1 and not args.no_context_parallel:
+        sec["context_parallel"] = flux_context_parallel(cx, pipe, tr, res, call, nsteps, ms / n)
     del pipe, tr
     torch.cuda.empty_cache()
     return sec
+
+
+def flux_context_parallel(cx, pipe, tr, res, call, nsteps, replica_ms):
+    from diffusers_b200.context_parallel import ContextParallelConfig
+    args, dev, world = cx.args, cx.dev, cx.world
+    try:
+        tr.enable_parallelism(config=ContextParallelConfig(ulysses_degree=world))
+
+        def one(seed):  # every rank runs the same sampling loop on the same seeded latents and gets the full latent back
+            return pipe(generator=torch.Generator(device=dev).manual_seed(seed), **res, **call).images
+
+        one(0)
+        n = max(2, min(args.steps, 3))
+        with ClockSampler(cx.local_rank) as cs:
+            ms, launches = cx.timed(n, lambda i: one(300 + i))
+        _, bufs = next(iter(tr._cp["plans"].values()))
+        return dict(ulysses_degree=world, scaling="strong", value=round(n / (ms * 1e-3), 4), unit="latents/s", ms_per_latent=round(ms / n, 1),
+                    ms_per_forward=round(ms / n / nsteps, 2), one_gpu_ms_per_latent=round(replica_ms, 1), speedup_vs_one_gpu=round(replica_ms / (ms / n), 3),
+                    gpu_launches=launches, clocks=cs.summary(), barriers_per_forward=bufs["pg"].barriers // max(1, (n + 1) * nsteps),
+                    collective="none: the QKV GEMM stores into the head owner's buffer, the attention epilogue into the row owner's, over NVLink peer "
+                               "mappings; b200_peer_barrier between the phases")
+    except Exception as e:  # noqa: BLE001  (a device-side failure poisons the context: report it, the caller must not touch the GPU again)
+        cx.gpu_dead = True
+        return f"failed: {type(e).__name__}: {str(e)[:200]}"
 
 
 def vae_section(cx):
@@ -713,6 +742,10 @@ def run_b200(args, rank, world, local_rank):
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "dtype", "t_step_runs_s", "run_spread") if k in cb}
     if rank == 0 and line is not None:
         emit(line)
+    if cx.gpu_dead:  # a trapped kernel left the CUDA context unusable: the line is out, skip the collective teardown
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 _JSON_FD = None
@@ -746,6 +779,7 @@ def main():
     ap.add_argument("--guidance-scale", type=float, default=7.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config3", action="store_true")
+    ap.add_argument("--no-context-parallel", action="store_true", help="N > 1: skip the Flux context-parallel (one latent over N GPUs) measurement")
     ap.add_argument("--no-reference-cuda", action="store_true")
     ap.add_argument("--cpu-sample", action="store_true", help="with --impl reference: print only the bounded cpu_baseline sample (used by the B200 arm)")
     args = ap.parse_args()

@@ -31,6 +31,8 @@ class ConvGemmArgs(C.Structure):
         ("debug_timestamps", C.c_void_p), ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
         ("row_stats_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_parts", C.c_int32), ("ln_eps", C.c_float),
         ("up2x_parity", C.c_int32), ("pad_after_only", C.c_int32),
+        ("qk_cols", C.c_int32), ("qk_head_dim", C.c_int32), ("qk_norm_w", C.c_void_p), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+        ("rope_ld", C.c_int32), ("rope_row0", C.c_int32), ("qk_eps", C.c_float),
     ]
 
 

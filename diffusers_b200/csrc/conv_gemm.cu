@@ -93,6 +93,13 @@ struct ConvGemmParams {
   const float2* ln_stats;  // consumer: [M][ln_parts]
   int ln_parts;
   float ln_eps, ln_inv_k;
+  // per-head RMSNorm + rotary embedding of the q / k columns of a fused QKV projection (QKR instantiations; see b200_conv_gemm_args)
+  int qk_cols, qk_hd;      // columns [0, qk_cols) are q then k heads of qk_hd (64 | 128) columns each
+  const void* qk_w;        // 16-bit [2][qk_hd]: RMSNorm weights of q, then of k
+  const float* rope_cos;   // fp32 [qk_hd / 2][rope_ld], position-minor (lanes = consecutive rows read consecutive words)
+  const float* rope_sin;
+  int rope_ld, rope_row0;  // position of output row r = rope_row0 + r
+  float qk_eps;
 };
 
 template <int BN, bool PAIR>
@@ -170,7 +177,7 @@ __device__ __noinline__ void epilogue_scalar(const uint32_t* v, const uint32_t* 
   }
 }
 
-template <int BN, bool GEGLU, bool FP16, bool PAIR>
+template <int BN, bool GEGLU, bool FP16, bool PAIR, bool QKR = false>
 __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using Cfg = ConvGemmCfg<BN, PAIR>;
   using H = Half16<FP16>;
@@ -447,6 +454,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         const float var = fmaxf(fmaf(-mean, mean, s1 * p.ln_inv_k), 0.0f);
         ln_r = rsqrtf(var + p.ln_eps);
       }
+      float qk_rstd = 1.0f;          // QKR: 1 / rms of this row over the head being written
       float st_s = 0.f, st_q = 0.f;  // producer side of a folded LayerNorm: sums of this thread's ROUNDED outputs of the tile
       if (bias != nullptr && real_tile && lane * 64 < BN && tc.n0 + lane * 64 < p.N) prefetch_l1(bias + tc.n0 + lane * 64);  // the tile's bias: L1 hits in the chunk loop
 
@@ -487,7 +495,75 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         tmem_wait_ld();
         const bool stamp = dbg && issuer && it == 0 && c < 2;
         if (stamp) dbg[8 + c * 4] = clock64();
-        if (lean) {
+        if (QKR && yc0 < p.qk_cols) {
+          // ---- q / k head columns of a fused QKV projection: per-head RMSNorm (weight) + rotary embedding before the store, so
+          // that the attention kernel reads finished q / k (transformer_flux.py:102-119 without the extra pass over the buffer).
+          // Rounding points are those of the reference's eager ops (and of qk_norm_rope_kernel): the projection is rounded to 16
+          // bit, the normalised value twice (x * rstd, then * weight), the rotation is computed in fp32 and rounded once.
+          const int cph = p.qk_hd >> 5;       // 32-column chunks per head (2 | 4)
+          const int cin = c & (cph - 1);      // this chunk's index inside its head (heads never straddle tiles: BN % 128 == 0)
+          if (cin == half) {
+            // first of this warp's chunks of the head: sum of squares over the WHOLE head (the other warp of the quarter owns the
+            // alternate chunks and does the same; TMEM reads are cheap, an exchange would couple the two halves)
+            float ss = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < cph; ++cc) {
+              uint32_t u[32];
+              tmem_ld32(t_row + (c - cin + cc) * 32, u);
+              const typename H::T* bp = bias + (yc0 - cin * 32 + cc * 32);
+              uint4 bb[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) bb[j] = bias ? *reinterpret_cast<const uint4*>(bp + j * 8) : make_uint4(0, 0, 0, 0);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 t0 = H::unpack(bb[j].x), t1 = H::unpack(bb[j].y), t2 = H::unpack(bb[j].z), t3 = H::unpack(bb[j].w);
+                const float bq[8] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float q = H::to_float(H::from_float(fmaf(__uint_as_float(u[j * 8 + e]), ln_r, bq[e])));
+                  ss = fmaf(q, q, ss);
+                }
+              }
+            }
+            qk_rstd = rsqrtf(ss * (p.qk_hd == 128 ? (1.0f / 128.0f) : (1.0f / 64.0f)) + p.qk_eps);
+          }
+          const int hcol = cin * 32;  // first column of the chunk inside its head
+          const typename H::T* nw = static_cast<const typename H::T*>(p.qk_w) + ((yc0 - hcol) >= (p.qk_cols >> 1) ? p.qk_hd : 0) + hcol;
+          const long long pos = valid ? (p.rope_row0 + pix) : 0;
+          const float* cs_p = p.rope_cos + static_cast<long long>(hcol >> 1) * p.rope_ld + pos;
+          const float* sn_p = p.rope_sin + static_cast<long long>(hcol >> 1) * p.rope_ld + pos;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            uint4* sp = reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4));
+            const uint4 w4 = *reinterpret_cast<const uint4*>(nw + j8 * 8);
+            const float2 b0 = H::unpack(bc[j8].x), b1 = H::unpack(bc[j8].y), b2 = H::unpack(bc[j8].z), b3 = H::unpack(bc[j8].w);
+            const float2 w0 = H::unpack(w4.x), w1 = H::unpack(w4.y), w2 = H::unpack(w4.z), w3 = H::unpack(w4.w);
+            const float bq[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
+            const float wq[8] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y};
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = H::to_float(H::from_float(fmaf(__uint_as_float(v[j8 * 8 + e]), ln_r, bq[e])));
+              x = H::to_float(H::from_float(x * qk_rstd));
+              f[e] = H::to_float(H::from_float(x * wq[e]));
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              const float cs = cs_p[static_cast<long long>(j8 * 4 + (e >> 1)) * p.rope_ld];
+              const float sn = sn_p[static_cast<long long>(j8 * 4 + (e >> 1)) * p.rope_ld];
+              const float re = f[e], im = f[e + 1];
+              f[e] = re * cs + (-im) * sn;
+              f[e + 1] = im * cs + re * sn;
+            }
+            uint4 o;
+            o.x = H::pack(f[0], f[1]);
+            o.y = H::pack(f[2], f[3]);
+            o.z = H::pack(f[4], f[5]);
+            o.w = H::pack(f[6], f[7]);
+            *sp = o;
+          }
+        } else if (lean) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             uint4* sp = reinterpret_cast<uint4*>(slab + row * 64 + ((j8 ^ sw) << 4));
@@ -653,15 +729,15 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, bool GEGLU, bool FP16>
+template <int BN, bool GEGLU, bool FP16, bool QKR = false>
 static int set_smem_attr() {
-  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, GEGLU, FP16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, GEGLU, FP16, false, QKR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        ConvGemmCfg<BN, false>::SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_gemm_kernel<BN, GEGLU, FP16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(conv_gemm_kernel<BN, GEGLU, FP16, true, QKR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              ConvGemmCfg<BN, true>::SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_gemm_kernel<BN, GEGLU, FP16, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+    e = cudaFuncSetAttribute(conv_gemm_kernel<BN, GEGLU, FP16, true, QKR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "conv_gemm smem attr BN=%d: %s", BN, cudaGetErrorString(e));
   return 0;
 }
@@ -678,10 +754,15 @@ int init_conv_gemm() {
   if ((r = set_smem_attr<BN, true, true>())) return r;
   B200_SETG(64) B200_SETG(128) B200_SETG(256)
 #undef B200_SETG
+#define B200_SETQ(BN)                                        \
+  if ((r = set_smem_attr<BN, false, false, true>())) return r; \
+  if ((r = set_smem_attr<BN, false, true, true>())) return r;
+  B200_SETQ(128) B200_SETQ(256)
+#undef B200_SETQ
   return 0;
 }
 
-template <int BN, bool GEGLU, bool FP16, bool PAIR>
+template <int BN, bool GEGLU, bool FP16, bool PAIR, bool QKR = false>
 static int launch_one(const ConvGemmParams& prm, int grid, cudaStream_t st) {
   constexpr int cm = PAIR ? 2 : 1;
   cudaLaunchConfig_t cfg;
@@ -707,7 +788,7 @@ static int launch_one(const ConvGemmParams& prm, int grid, cudaStream_t st) {
       int n = 0;
       cudaLaunchConfig_t q = cfg;
       q.gridDim = dim3(num_sms() / cm * cm);
-      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<BN, GEGLU, FP16, PAIR>, &q) != cudaSuccess || n <= 0) {
+      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_kernel<BN, GEGLU, FP16, PAIR, QKR>, &q) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         n = num_sms() / cm;
       }
@@ -715,13 +796,18 @@ static int launch_one(const ConvGemmParams& prm, int grid, cudaStream_t st) {
     }
     if (grid > max_active * cm) cfg.gridDim = dim3(max_active * cm);
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, GEGLU, FP16, PAIR>, prm);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, GEGLU, FP16, PAIR, QKR>, prm);
   if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "conv_gemm launch (BN=%d cm=%d grid=%d): %s", BN, cm, grid, cudaGetErrorString(e));
   return 0;
 }
 
 template <bool GEGLU, bool FP16, bool PAIR>
 static int launch_bn(int bn, const ConvGemmParams& prm, int grid, cudaStream_t st) {
+  if (!GEGLU && prm.qk_cols > 0) {  // fused RMSNorm + rotary embedding of the q / k columns
+    if (bn == 256) return launch_one<256, false, FP16, PAIR, true>(prm, grid, st);
+    if (bn == 128) return launch_one<128, false, FP16, PAIR, true>(prm, grid, st);
+    return set_error(B200_ERR_UNSUPPORTED, "conv_gemm: qk_rope needs tile_n 128 or 256 (got %d)", bn);
+  }
   switch (bn) {
     case 256: return launch_one<256, GEGLU, FP16, PAIR>(prm, grid, st);
     case 128: return launch_one<128, GEGLU, FP16, PAIR>(prm, grid, st);
@@ -756,7 +842,7 @@ static double launch_cost(int bn, int cm, int k_chunks, bool geglu, long long wa
   return 3000.0 + (cm == 2 ? 900.0 : 0.0) + waves * main_loop + (waves - 1) * hidden + epi;
 }
 
-static void pick_config(long long m_tiles, int N, int k_chunks, int geglu, int force_bn, int force_cm_arg, int* bn_out, int* cm_out) {
+static void pick_config(long long m_tiles, int N, int k_chunks, int geglu, int force_bn, int force_cm_arg, int* bn_out, int* cm_out, bool qkr = false) {
   const int sms = num_sms();
   static const int env_cm = getenv("B200_FORCE_CM") ? atoi(getenv("B200_FORCE_CM")) : 0;  // test knob
   const int force_cm = force_cm_arg ? force_cm_arg : env_cm;
@@ -767,6 +853,7 @@ static void pick_config(long long m_tiles, int N, int k_chunks, int geglu, int f
     if (force_bn && bn != force_bn) continue;
     if (geglu && !(bn == 256 || bn == 128 || bn == 64)) continue;
     if (geglu && N % bn != 0) continue;
+    if (qkr && !(bn == 256 || bn == 128)) continue;  // heads of 64 / 128 columns must not straddle tiles
     const long long n_tiles = (N + bn - 1) / bn;
     static const bool no_pair = getenv("B200_NO_PAIR") && atoi(getenv("B200_NO_PAIR")) != 0;  // tuning knob
     for (int cm : {1, 2}) {
@@ -895,7 +982,20 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   prm.k_chunks = prm.num_taps * (prm.chunks[0] + prm.chunks[1]);
 
   int bn = 0, cm = 1;
-  pick_config(prm.m_tiles, a->N, prm.k_chunks, a->geglu, a->geglu && !a->tile_n ? pick_tile_n(0, a->N, 1) : a->tile_n, a->cluster_m, &bn, &cm);
+  const bool qkr = a->qk_cols > 0;
+  if (qkr) {
+    B200_CHECK_ARG(a->qk_head_dim == 64 || a->qk_head_dim == 128, "conv_gemm: qk_head_dim %d (64 or 128)", a->qk_head_dim);
+    B200_CHECK_ARG(a->qk_cols % (2 * a->qk_head_dim) == 0 && a->qk_cols <= a->N && a->N % 64 == 0,
+                   "conv_gemm: qk_cols %d must be q heads + k heads of %d columns inside N = %d (N %% 64 == 0)", a->qk_cols, a->qk_head_dim, a->N);
+    B200_CHECK_ARG(a->ksize == 1 && a->stride == 1 && a->H == 1 && !a->geglu && !a->gate && !a->rowvec && !a->residual && !a->out_fp32 && !a->row_stats_out &&
+                       a->act == B200_ACT_NONE,
+                   "conv_gemm: qk_rope is the epilogue of a plain linear projection (bias and a folded LayerNorm only)");
+    B200_CHECK_ARG(a->qk_norm_w && a->rope_cos && a->rope_sin && aligned16(a->qk_norm_w), "conv_gemm: qk_rope needs qk_norm_w (16-byte aligned), rope_cos and rope_sin");
+    B200_CHECK_ARG(a->rope_ld > 0 && a->rope_row0 >= 0 && a->rope_row0 + a->W <= a->rope_ld, "conv_gemm: rope table of %d positions does not cover rows [%d, %d)",
+                   a->rope_ld, a->rope_row0, a->rope_row0 + a->W);
+    B200_CHECK_ARG(a->tile_n == 0 || a->tile_n == 128 || a->tile_n == 256, "conv_gemm: qk_rope needs tile_n 128 or 256");
+  }
+  pick_config(prm.m_tiles, a->N, prm.k_chunks, a->geglu, a->geglu && !a->tile_n ? pick_tile_n(0, a->N, 1) : a->tile_n, a->cluster_m, &bn, &cm, qkr);
   B200_CHECK_ARG(bn != 0, "conv_gemm: no valid tile configuration (N=%d geglu=%d tile_n=%d)", a->N, a->geglu, a->tile_n);
   if (a->geglu) B200_CHECK_ARG(a->N % bn == 0, "conv_gemm: geglu N=%d not a multiple of tile_n=%d", a->N, bn);
   prm.cm = cm;
@@ -1046,6 +1146,17 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
     prm.ln_parts = a->ln_parts;
     prm.ln_eps = a->ln_eps;
     prm.ln_inv_k = 1.0f / static_cast<float>(a->c[0]);
+  }
+  if (qkr) {
+    B200_CHECK_ARG(prm.tma_store && vec, "conv_gemm: qk_rope needs the vector TMA-store epilogue (aligned y / bias)");
+    prm.qk_cols = a->qk_cols;
+    prm.qk_hd = a->qk_head_dim;
+    prm.qk_w = a->qk_norm_w;
+    prm.rope_cos = a->rope_cos;
+    prm.rope_sin = a->rope_sin;
+    prm.rope_ld = a->rope_ld;
+    prm.rope_row0 = a->rope_row0;
+    prm.qk_eps = a->qk_eps;
   }
   static const bool no_pf = getenv("B200_NO_WEIGHT_PREFETCH") && atoi(getenv("B200_NO_WEIGHT_PREFETCH")) != 0;  // tuning knob
   if (a->prefetch && a->prefetch_bytes > 0 && !no_pf) {

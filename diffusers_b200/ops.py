@@ -117,6 +117,21 @@ def _need_cuda(t, name):
     _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
 
 
+class QkRope:
+    """Per-head RMSNorm + rotary embedding of the q / k columns of a fused QKV projection, folded into the GEMM epilogue
+    (b200_conv_gemm_args.qk_*): `w` 16-bit [2, head_dim] (norm_q.weight, norm_k.weight), `cos` / `sin` fp32
+    [head_dim / 2, positions] (rope_tables_transposed), `row0` the position of the launch's first row, `cols` = q + k columns."""
+    __slots__ = ("w", "cos", "sin", "row0", "cols", "head_dim", "eps")
+
+    def __init__(self, w, cos, sin, row0, cols, head_dim, eps=1e-6):
+        self.w, self.cos, self.sin, self.row0, self.cols, self.head_dim, self.eps = w, cos, sin, row0, cols, head_dim, eps
+
+
+def rope_tables_transposed(cos, sin):
+    """FluxPosEmbed's repeat-interleaved fp32 [positions, head_dim] tables -> the [head_dim / 2, positions] form the fused epilogue reads."""
+    return cos[:, 0::2].t().contiguous(), sin[:, 0::2].t().contiguous()
+
+
 class FoldedLayerNorm:
     """A LayerNorm folded into the Linear that consumes it (b200_conv_gemm_args.ln_*): the row statistics written by the GEMM
     that produced the activations (`row_stats=True`) and eps.  The weight / bias of that Linear come from
@@ -129,7 +144,7 @@ class FoldedLayerNorm:
 
 def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, act=ACT_NONE, geglu=False,
               gate=None, rowvec=None, rows_per_group=0, residual=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None,
-              row_stats=False, ln=None, pad_after_only=False):
+              row_stats=False, ln=None, pad_after_only=False, qk_rope=None):
     """y = epilogue(conv/linear(x [, x2]))  -  see b200_conv_gemm in include/b200_diffusion.h.
 
     x, x2: NHWC activations given as 2-D [batch*H*W, C] (or any shape whose last dim is C, contiguous rows).
@@ -174,6 +189,14 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
         a.row_stats_out = stats.data_ptr()
     if ln is not None:
         a.ln_stats, a.ln_parts, a.ln_eps = ln.stats.data_ptr(), ln.stats.shape[1], ln.eps
+    if qk_rope is not None:
+        q = qk_rope
+        if q.cos.dtype != torch.float32 or q.cos.shape[0] * 2 != q.head_dim or not q.cos.is_contiguous() or q.cos.shape != q.sin.shape or not q.sin.is_contiguous():
+            raise B200Error("qk_rope: cos / sin must be contiguous fp32 [head_dim / 2, positions] tables")
+        if q.w.dtype != x.dtype or q.w.numel() != 2 * q.head_dim:
+            raise B200Error("qk_rope: w must be [2, head_dim] in the activation dtype")
+        a.qk_cols, a.qk_head_dim, a.qk_norm_w = q.cols, q.head_dim, q.w.data_ptr()
+        a.rope_cos, a.rope_sin, a.rope_ld, a.rope_row0, a.qk_eps = q.cos.data_ptr(), q.sin.data_ptr(), q.cos.shape[1], q.row0, q.eps
     if _PLAN is not None:
         nxt = _PLAN._step(w)
         if nxt is not None:
@@ -192,12 +215,13 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
 
 
 def linear(x, w, N, *, bias=None, act=ACT_NONE, geglu=False, gate=None, rowvec=None, rows_per_group=0,
-           residual=None, x2=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None, row_stats=False, ln=None):
+           residual=None, x2=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None, row_stats=False, ln=None, qk_rope=None):
     """nn.Linear on token rows: x [rows, K] (row stride arbitrary multiple of 8)."""
     rows = x.shape[0]
     return conv_gemm(x, w, N, batch=1, H=1, W=rows, ksize=1, stride=1, x2=x2, bias=bias, act=act, geglu=geglu,
                      gate=gate, rowvec=rowvec, rows_per_group=rows_per_group, residual=residual, out=out,
-                     tile_n=tile_n, out_fp32=out_fp32, cluster_m=cluster_m, debug_timestamps=debug_timestamps, row_stats=row_stats, ln=ln)
+                     tile_n=tile_n, out_fp32=out_fp32, cluster_m=cluster_m, debug_timestamps=debug_timestamps, row_stats=row_stats, ln=ln,
+                     qk_rope=qk_rope)
 
 
 def upsample2x_conv(x, w4, N, *, batch, H, W, bias=None, act=ACT_NONE, out=None):

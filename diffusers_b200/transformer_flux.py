@@ -13,6 +13,7 @@ B200-first structure (not a port):
   * context_embedder(text) and the RoPE tables are step-invariant and cached.
 """
 import contextlib
+import os
 
 import torch
 
@@ -61,6 +62,11 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         self._rope_key = None
         self._rope = None
         self._cp = None  # context parallelism (enable_parallelism): dict(world, rank, group, plans, peers)
+        # per-head RMSNorm + rotary embedding of q / k in the EPILOGUE of the fused QKV GEMM (the north star's "QKV + RoPE" fusion;
+        # B200_FLUX_FUSED_QKROPE=0: the separate in-place b200_qk_norm_rope pass of round 1, kept for A/B runs and as its test oracle)
+        self.fused_qk_rope = os.environ.get("B200_FLUX_FUSED_QKROPE", "1") != "0"
+        self._ropeT_key = None
+        self._ropeT = None
 
     def _reg(self, t, device):
         name = f"w{self._n}"
@@ -120,6 +126,8 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
                 aqkv=lin_cat([a + ".add_q_proj", a + ".add_k_proj", a + ".add_v_proj"]),
                 nq=R(g(a + ".norm_q.weight")), nk=R(g(a + ".norm_k.weight")),
                 naq=R(g(a + ".norm_added_q.weight")), nak=R(g(a + ".norm_added_k.weight")),
+                nqk=R(torch.stack([g(a + ".norm_q.weight"), g(a + ".norm_k.weight")])),
+                naqk=R(torch.stack([g(a + ".norm_added_q.weight"), g(a + ".norm_added_k.weight")])),
                 out=lin(a + ".to_out.0"), aout=lin(a + ".to_add_out"),
                 ff1=lin(p + ".ff.net.0.proj"), ff2=lin(p + ".ff.net.2"),
                 cff1=lin(p + ".ff_context.net.0.proj"), cff2=lin(p + ".ff_context.net.2")))
@@ -131,6 +139,7 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
                 mod=mod(p + ".norm.linear"),
                 qkv=lin_cat([a + ".to_q", a + ".to_k", a + ".to_v"]),
                 nq=R(g(a + ".norm_q.weight")), nk=R(g(a + ".norm_k.weight")),
+                nqk=R(torch.stack([g(a + ".norm_q.weight"), g(a + ".norm_k.weight")])),
                 mlp=lin(p + ".proj_mlp"), out=lin(p + ".proj_out", split=(D, 4 * D))))
         self.mod_out = mod("norm_out.linear")
         self.proj_out = lin("proj_out")
@@ -222,7 +231,7 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         yield
 
     def _reset_stateful_cache(self):
-        self._ctx_key = self._ctx = self._rope_key = self._rope = None
+        self._ctx_key = self._ctx = self._rope_key = self._rope = self._ropeT_key = self._ropeT = None
 
     @classmethod
     def random_init(cls, config=None, seed=0, dtype=torch.bfloat16, device="cuda"):
@@ -252,6 +261,12 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
             self._rope = (torch.cat(cos_out, dim=-1).contiguous(), torch.cat(sin_out, dim=-1).contiguous())
             self._rope_key = (ko[0], ko[1], (ko[0]._version, ko[1]._version))
         return self._rope
+
+    def _rope_transposed(self, rope):
+        if self._ropeT_key is not rope[0]:
+            self._ropeT = ops.rope_tables_transposed(rope[0], rope[1])
+            self._ropeT_key = rope[0]
+        return self._ropeT
 
     def _context(self, ehs):
         k = self._ctx_key
@@ -339,10 +354,14 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         return cp["plans"][key]
 
     def _cp_rope(self, plan, rope):
+        """(cos, sin) of the whole sequence in rank-major order [positions, head_dim] (destination-side b200_qk_norm_rope), and of
+        THIS rank's rows transposed [head_dim / 2, Ll] (source-side fused epilogue)."""
         cp = self._cp
         if cp["rope_key"] is not rope[0]:
             g = plan.joint_to_rank_major().to(rope[0].device)
-            cp["rope"] = (rope[0].index_select(0, g).contiguous(), rope[1].index_select(0, g).contiguous())
+            full = (rope[0].index_select(0, g).contiguous(), rope[1].index_select(0, g).contiguous())
+            b0, b1 = plan.block()
+            cp["rope"] = full + ops.rope_tables_transposed(full[0][b0:b1], full[1][b0:b1])
             cp["rope_key"] = rope[0]
         return cp["rope"]
 
@@ -357,7 +376,8 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         r, P, Tl, Sl, Ll, L, Dl, hl = plan.rank, plan.world, plan.Tl, plan.Sl, plan.Ll, plan.L, plan.Dl, plan.hl
         (t0, t1), (s0, s1) = plan.text_rows(), plan.image_rows()
         b0 = plan.block()[0]
-        cos, sin = self._cp_rope(plan, rope)
+        cos, sin, cosT, sinT = self._cp_rope(plan, rope)
+        fused = self.fused_qk_rope
         dev = x_in.device
         hbuf = torch.empty((Ll, D), dtype=self._dtype, device=dev)  # this rank's slice of the residual stream [text | image]
         c, x = hbuf[:Tl], hbuf[Tl:]
@@ -371,18 +391,21 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         def m(off, i):
             return mod[:, off + i * D: off + (i + 1) * D]
 
-        def send_qkv(l, rows_in, row_off):
-            # the first all-to-all of Ulysses, folded into the GEMM: destination d receives its heads' [q | k | v] columns of my rows
+        def send_qkv(l, rows_in, row_off, nw):
+            # the first all-to-all of Ulysses, folded into the GEMM: destination d receives its heads' [q | k | v] columns of my rows,
+            # q / k already normalised and rotated (positions of MY rows: the local transposed tables)
             n = rows_in.shape[0]
+            qk = ops.QkRope(self.W(nw), cosT, sinT, row_off, 2 * Dl, hd, 1e-6) if fused else None
             for d in order:
                 ops.linear(rows_in, self.W(l["w"])[d * 3 * Dl:(d + 1) * 3 * Dl], 3 * Dl, bias=self.W(l["b"])[d * 3 * Dl:(d + 1) * 3 * Dl],
-                           out=J[d][b0 + row_off: b0 + row_off + n])
+                           out=J[d][b0 + row_off: b0 + row_off + n], qk_rope=qk)
 
         def attend(blk, txt_rows):
             pg.barrier()  # every rank's q/k/v tiles have landed in my J
-            ops.qk_norm_rope(Jl, heads=hl, head_dim=hd, k_off=Dl, seq=L, txt_rows=txt_rows, txt_period=Ll, wq=self.W(blk["nq"]),
-                             wk=self.W(blk["nk"]), wq_txt=self.W(blk["naq"]) if "naq" in blk else None,
-                             wk_txt=self.W(blk["nak"]) if "nak" in blk else None, cos=cos, sin=sin, eps=1e-6)
+            if not fused:
+                ops.qk_norm_rope(Jl, heads=hl, head_dim=hd, k_off=Dl, seq=L, txt_rows=txt_rows, txt_period=Ll, wq=self.W(blk["nq"]),
+                                 wk=self.W(blk["nk"]), wq_txt=self.W(blk["naq"]) if "naq" in blk else None,
+                                 wk_txt=self.W(blk["nak"]) if "nak" in blk else None, cos=cos, sin=sin, eps=1e-6)
             # the second all-to-all, folded into the attention epilogue: row i goes to the rank that owns it
             ops.attention(J3[:, :, :Dl], J3[:, :, Dl:2 * Dl], J3[:, :, 2 * Dl:], heads=hl, head_dim=hd, o_seg=o_seg, o_seg_rows=Ll)
             pg.barrier()  # every rank's output rows have landed in my A
@@ -392,8 +415,8 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
             o, co = blk["mod"], blk["cmod"]
             nx = ops.layer_norm(x, eps=1e-6, scale=m(o, 1), shift=m(o, 0), rows_per_group=Sl)
             nc = ops.layer_norm(c, eps=1e-6, scale=m(co, 1), shift=m(co, 0), rows_per_group=Tl)
-            send_qkv(blk["aqkv"], nc, 0)
-            send_qkv(blk["qkv"], nx, Tl)
+            send_qkv(blk["aqkv"], nc, 0, blk["naqk"])
+            send_qkv(blk["qkv"], nx, Tl, blk["nqk"])
             a = attend(blk, Tl)
             self._lin(blk["out"], a[Tl:], gate=m(o, 2), rows_per_group=Sl, residual=x, out=x)
             self._lin(blk["aout"], a[:Tl], gate=m(co, 2), rows_per_group=Tl, residual=c, out=c)
@@ -406,7 +429,7 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         for blk in self.single:
             o = blk["mod"]
             nh_ = ops.layer_norm(hbuf, eps=1e-6, scale=m(o, 1), shift=m(o, 0), rows_per_group=Ll)
-            send_qkv(blk["qkv"], nh_, 0)
+            send_qkv(blk["qkv"], nh_, 0, blk["nqk"])
             mlp = self._lin(blk["mlp"], nh_, act=ACT_GELU_TANH)
             a = attend(blk, 0)
             self._lin(blk["out"], a, x2=mlp, gate=m(o, 2), rows_per_group=Ll, residual=hbuf, out=hbuf)
@@ -434,22 +457,30 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         c.copy_(ctx)
         J = torch.empty((L, 3 * D), dtype=self._dtype, device=dev)  # joint fused QKV
         J3 = J.view(1, L, 3 * D)
+        fused = self.fused_qk_rope
+        if fused:
+            cosT, sinT = self._rope_transposed(rope)
 
         def m(off, i):
             return mod[:, off + i * D: off + (i + 1) * D]
 
+        def qkr(blk, key, row0):
+            # q / k leave the projection normalised and rotated: no second pass over the joint buffer
+            return ops.QkRope(self.W(blk[key]), cosT, sinT, row0, 2 * D, hd, 1e-6) if fused else None
+
         def attend(blk, txt_rows):
-            ops.qk_norm_rope(J, heads=nh, head_dim=hd, k_off=D, seq=L, txt_rows=txt_rows, wq=self.W(blk["nq"]),
-                             wk=self.W(blk["nk"]), wq_txt=self.W(blk["naq"]) if "naq" in blk else None,
-                             wk_txt=self.W(blk["nak"]) if "nak" in blk else None, cos=cos, sin=sin, eps=1e-6)
+            if not fused:
+                ops.qk_norm_rope(J, heads=nh, head_dim=hd, k_off=D, seq=L, txt_rows=txt_rows, wq=self.W(blk["nq"]),
+                                 wk=self.W(blk["nk"]), wq_txt=self.W(blk["naq"]) if "naq" in blk else None,
+                                 wk_txt=self.W(blk["nak"]) if "nak" in blk else None, cos=cos, sin=sin, eps=1e-6)
             return ops.attention(J3[:, :, :D], J3[:, :, D:2 * D], J3[:, :, 2 * D:], heads=nh, head_dim=hd).view(L, D)
 
         for blk in self.double:
             o, co = blk["mod"], blk["cmod"]
             nx = ops.layer_norm(x, eps=1e-6, scale=m(o, 1), shift=m(o, 0), rows_per_group=S)
             nc = ops.layer_norm(c, eps=1e-6, scale=m(co, 1), shift=m(co, 0), rows_per_group=T)
-            self._lin(blk["aqkv"], nc, out=J[:T])
-            self._lin(blk["qkv"], nx, out=J[T:])
+            self._lin(blk["aqkv"], nc, out=J[:T], qk_rope=qkr(blk, "naqk", 0))
+            self._lin(blk["qkv"], nx, out=J[T:], qk_rope=qkr(blk, "nqk", T))
             a = attend(blk, T)
             self._lin(blk["out"], a[T:], gate=m(o, 2), rows_per_group=S, residual=x, out=x)
             self._lin(blk["aout"], a[:T], gate=m(co, 2), rows_per_group=T, residual=c, out=c)
@@ -462,7 +493,7 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
         for blk in self.single:
             o = blk["mod"]
             nh_ = ops.layer_norm(hbuf, eps=1e-6, scale=m(o, 1), shift=m(o, 0), rows_per_group=L)
-            self._lin(blk["qkv"], nh_, out=J)
+            self._lin(blk["qkv"], nh_, out=J, qk_rope=qkr(blk, "nqk", 0))
             mlp = self._lin(blk["mlp"], nh_, act=ACT_GELU_TANH)
             a = attend(blk, 0)
             self._lin(blk["out"], a, x2=mlp, gate=m(o, 2), rows_per_group=L, residual=hbuf, out=hbuf)

@@ -131,6 +131,22 @@ typedef struct {
    * (models/downsampling.py:141-143: F.pad(x, (0, 1, 0, 1)) then Conv2d(stride=2, padding=0)); output (ho, wo) reads input rows
    * 2 ho .. 2 ho + 2.  0 = the symmetric padding of 1 every other 3x3 convolution of the path uses. */
   int32_t pad_after_only;
+  /* ---- per-head RMSNorm + rotary embedding of q and k folded into the fused QKV projection (FluxAttnProcessor:
+   * transformers/transformer_flux.py:84-136 = to_q/to_k/to_v -> norm_q / norm_k (torch.nn.RMSNorm(head_dim, eps 1e-6)) ->
+   * apply_rotary_emb (models/embeddings.py:1187-1231) -> attention).  With qk_cols > 0 the output columns [0, qk_cols) are
+   * q heads then k heads of qk_head_dim (64 | 128) columns; each (row, head) is RMS-normalised over its columns, multiplied by
+   * qk_norm_w ([2][qk_head_dim] 16-bit: the q weights, then the k weights) and rotated by the angle of position
+   * rope_row0 + row: rope_cos / rope_sin are fp32 [qk_head_dim / 2][rope_ld] tables (entry [i][pos] = cos / sin of pair i at
+   * position pos - position-minor so that the 32 rows of a warp read consecutive words).  Columns >= qk_cols (v) are plain.
+   * Rounding points are those of the reference's eager ops.  Linear (H == 1) launches with bias / folded LayerNorm only. */
+  int32_t qk_cols;
+  int32_t qk_head_dim;
+  const void* qk_norm_w;
+  const float* rope_cos;
+  const float* rope_sin;
+  int32_t rope_ld;
+  int32_t rope_row0;
+  float qk_eps;
 } b200_conv_gemm_args;
 
 int b200_conv_gemm(const b200_conv_gemm_args* args, void* stream);

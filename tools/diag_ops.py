@@ -60,6 +60,11 @@ CASES = {
     "qk_norm_rope_flux": dict(kind="qkrope", rows=4608, txt=512, H=24, D=128),
     "qk_norm_rope_small": dict(kind="qkrope", rows=88, txt=24, H=2, D=64),
     "qk_norm_rope_notxt": dict(kind="qkrope", rows=200, txt=0, H=3, D=128),
+    # the same math as the EPILOGUE of the fused QKV projection (b200_conv_gemm_args.qk_*) against projection -> qk_norm_rope
+    "qkv_rope_fused_flux": dict(kind="qkrope_fused", rows=4096, row0=512, pos=4608, H=24, D=128, K=3072),
+    "qkv_rope_fused_hd64": dict(kind="qkrope_fused", rows=200, row0=24, pos=224, H=6, D=64, K=128),
+    "qkv_rope_fused_ragged": dict(kind="qkrope_fused", rows=1152, row0=0, pos=1152, H=3, D=128, K=256),
+    "qkv_rope_fused_fp16": dict(kind="qkrope_fused", rows=264, row0=8, pos=300, H=2, D=128, K=192, fp16=True),
     "softmax_rows": dict(kind="softmax"),
     "transpose_16": dict(kind="transpose"),
     "ddpm_step": dict(kind="ddpm"),
@@ -300,6 +305,39 @@ def run_case(name):
                                            nan=int(torch.isnan(o_).sum()))))
         ok = int(bad.sum()) == 0 and int(torch.isnan(o_).sum()) == 0
         ok &= report(name + "_v_untouched", work[:, 2 * C:], qkv[:, 2 * C:].float(), 0, 0)
+        return ok
+    if kind == "qkrope_fused":
+        # q/k RMSNorm + rotary embedding in the epilogue of the fused QKV GEMM == the same GEMM followed by b200_qk_norm_rope
+        # (which the cases above hold to the fp32 formula); the v columns must be the plain projection, bit for bit
+        from diffusers_b200 import packing
+        rows, row0, npos, H, D, K = cfg["rows"], cfg["row0"], cfg["pos"], cfg["H"], cfg["D"], cfg["K"]
+        C = H * D
+        x = rnd(rows, K)
+        w = rnd(3 * C, K, scale=K ** -0.5 * 1.5)
+        b = rnd(3 * C, scale=0.3)
+        wq, wk = rnd(D) + 1, rnd(D) + 1
+        ang = torch.rand(npos, D // 2, generator=g, device="cuda") * 6.28
+        cos = torch.cos(ang).repeat_interleave(2, dim=1).contiguous()
+        sin = torch.sin(ang).repeat_interleave(2, dim=1).contiguous()
+        wp = packing.pack_linear_weight(w.float()).to(dt).cuda()
+        plain = ops.linear(x, wp, 3 * C, bias=b)
+        two = plain.clone()
+        ops.qk_norm_rope(two, heads=H, head_dim=D, k_off=C, seq=rows, txt_rows=0, wq=wq, wk=wk, cos=cos[row0:row0 + rows].contiguous(),
+                         sin=sin[row0:row0 + rows].contiguous())
+        cT, sT = ops.rope_tables_transposed(cos, sin)
+        ok = True
+        for tile in (0, 128, 256):
+            fused = ops.linear(x, wp, 3 * C, bias=b, tile_n=tile, qk_rope=ops.QkRope(torch.stack([wq, wk]).contiguous(), cT, sT, row0, 2 * C, D))
+            torch.cuda.synchronize()
+            d = (fused[:, :2 * C].float() - two[:, :2 * C].float()).abs()
+            mag = two[:, :2 * C].float().reshape(rows, 2 * H, D).abs().amax(-1, keepdim=True).expand(rows, 2 * H, D).reshape(rows, 2 * C)
+            ulp = 2.0 ** -7 if dt == torch.bfloat16 else 2.0 ** -10
+            bad = d > 1.5 * ulp * mag + 1e-3  # the fp32 sum of squares runs in a different order: the odd last-bit flip of a rounded value
+            same = float((d == 0).float().mean())
+            v_equal = torch.equal(fused[:, 2 * C:], plain[:, 2 * C:])
+            print("RESULT " + json.dumps(dict(case=f"{name}_tile{tile}", max_abs=float(d.max()), identical_frac=round(same, 4), n_bad=int(bad.sum()),
+                                               v_bit_equal=v_equal, nan=int(torch.isnan(fused.float()).sum()))))
+            ok &= int(bad.sum()) == 0 and same > 0.97 and v_equal and int(torch.isnan(fused.float()).sum()) == 0
         return ok
     if kind == "softmax":
         ok = True
