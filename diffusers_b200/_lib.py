@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libb200diff.so")
 
 DTYPE_BF16, DTYPE_FP16 = 0, 1
-ACT_NONE, ACT_SILU, ACT_GELU_ERF, ACT_GELU_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_GELU_ERF, ACT_GELU_TANH, ACT_QUICK_GELU = 0, 1, 2, 3, 4
 
 
 class B200Error(RuntimeError):
@@ -66,7 +66,19 @@ class LayerNormArgs(C.Structure):
         ("x", C.c_void_p), ("ldx", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32), ("eps", C.c_float),
         ("gamma", C.c_void_p), ("beta", C.c_void_p),
         ("scale", C.c_void_p), ("shift", C.c_void_p), ("ld_mod", C.c_int32), ("rows_per_group", C.c_int32),
-        ("y", C.c_void_p), ("ldy", C.c_int32), ("dtype", C.c_int32),
+        ("y", C.c_void_p), ("ldy", C.c_int32), ("dtype", C.c_int32), ("rms", C.c_int32),
+    ]
+
+
+class TextAttentionArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("sq", C.c_int32), ("sk", C.c_int32),
+        ("q_row_stride", C.c_int64), ("q_batch_stride", C.c_int64),
+        ("k_row_stride", C.c_int64), ("k_batch_stride", C.c_int64),
+        ("v_row_stride", C.c_int64), ("v_batch_stride", C.c_int64),
+        ("o_row_stride", C.c_int64), ("o_batch_stride", C.c_int64),
+        ("scale", C.c_float), ("causal", C.c_int32), ("bias", C.c_void_p), ("dtype", C.c_int32),
     ]
 
 
@@ -138,6 +150,7 @@ def lib():
         _lib.b200_peer_close.argtypes = [VP]
         _lib.b200_peer_free.argtypes = [VP]
         _lib.b200_peer_barrier.argtypes = [C.POINTER(VP), VP, I32, I32, VP]
+        _lib.b200_text_attention.argtypes = [VP, VP]
         for fn in ("b200_conv_gemm", "b200_attention", "b200_group_norm", "b200_layer_norm", "b200_small_linear",
                    "b200_qk_norm_rope"):
             getattr(_lib, fn).argtypes = [VP, VP]

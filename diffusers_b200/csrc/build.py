@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(os.path.dirname(HERE), "_C")
 LIB = os.path.join(OUT_DIR, "libb200diff.so")
-SOURCES = ["lib.cu", "conv_gemm.cu", "attention.cu", "attention_pipe.cu", "attention64.cu", "norm.cu", "elementwise.cu", "peer.cu"]
+SOURCES = ["lib.cu", "conv_gemm.cu", "attention.cu", "attention_pipe.cu", "attention64.cu", "norm.cu", "elementwise.cu", "peer.cu", "text_attention.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -444,7 +444,7 @@ struct Half16<true> {
 // ----------------------------------------------------------------------------
 // activations (match torch: F.silu, F.gelu(approximate="none"|"tanh"))
 // ----------------------------------------------------------------------------
-enum : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU_ERF = 2, ACT_GELU_TANH = 3 };
+enum : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU_ERF = 2, ACT_GELU_TANH = 3, ACT_QUICK_GELU = 4 };
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 // SiLU for the memory-bound normalisation kernels: the IEEE division above expands to ~20 instructions with a slow path and made
@@ -467,6 +467,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     case ACT_SILU: return silu_f(x);
     case ACT_GELU_ERF: return gelu_erf_f(x);
     case ACT_GELU_TANH: return gelu_tanh_f(x);
+    case ACT_QUICK_GELU: return x / (1.0f + __expf(-1.702f * x));
     default: return x;
   }
 }

@@ -49,8 +49,9 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 }
 __device__ __forceinline__ float act_fast(float x, int act) {
   if (act == ACT_GELU_ERF) return gelu_erf_fast(x);
-  const float a = (act == ACT_SILU) ? 1.0f : 1.5957691216057308f;     // 2*sqrt(2/pi)
-  const float b = (act == ACT_SILU) ? 0.0f : 0.07135481627f;          // 2*sqrt(2/pi)*0.044715
+  // QuickGELU (CLIP text encoders, transformers activations.py QuickGELUActivation): x * sigmoid(1.702 x)
+  const float a = (act == ACT_SILU) ? 1.0f : (act == ACT_QUICK_GELU ? 1.702f : 1.5957691216057308f);  // 2*sqrt(2/pi)
+  const float b = (act == ACT_GELU_TANH) ? 0.07135481627f : 0.0f;                                      // 2*sqrt(2/pi)*0.044715
   return x * sigmoid_fast(x * fmaf(b, x * x, a));
 }
 
@@ -162,7 +163,7 @@ __device__ __noinline__ void epilogue_scalar(const uint32_t* v, const uint32_t* 
         x += H::to_float(bias[wcol0 + j]);
         gg += H::to_float(bias[wcol0 + bn / 2 + j]);
       }
-      x *= gelu_erf_fast(gg);
+      x *= (p.act == ACT_GELU_TANH) ? act_fast(gg, ACT_GELU_TANH) : gelu_erf_fast(gg);
     } else {
       if (bias) x += H::to_float(bias[n]);
       if (p.act != ACT_NONE) x = act_fast(x, p.act);
@@ -613,7 +614,10 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
               float2 t0 = H::unpack(bg.x), t1 = H::unpack(bg.y), t2 = H::unpack(bg.z), t3 = H::unpack(bg.w);
               const float gb[8] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] *= gelu_erf_fast(fmaf(__uint_as_float(gv[j8 * 8 + j]), ln_r, gb[j]));
+              for (int j = 0; j < 8; ++j) {
+                const float gx = fmaf(__uint_as_float(gv[j8 * 8 + j]), ln_r, gb[j]);
+                f[j] *= (act == ACT_GELU_TANH) ? act_fast(gx, ACT_GELU_TANH) : gelu_erf_fast(gx);  // tanh gate: T5 gated-gelu ("gelu_new")
+              }
             } else {
               if (act != ACT_NONE) {
 #pragma unroll

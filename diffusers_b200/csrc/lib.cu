@@ -79,6 +79,7 @@ int make_tensor_map_16b(CUtensorMap* out, const void* base, int rank, const uint
 
 int init_conv_gemm();  // conv_gemm.cu
 int init_attention();  // attention.cu
+int init_text_attention();  // text_attention.cu
 
 }  // namespace b200
 
@@ -103,6 +104,8 @@ int b200_init(int device) {
   int r = b200::init_conv_gemm();
   if (r) return r;
   r = b200::init_attention();
+  if (r) return r;
+  r = b200::init_text_attention();
   if (r) return r;
   return 0;
 }

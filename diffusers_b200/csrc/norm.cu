@@ -513,6 +513,7 @@ struct LayerNormParams {
   int ld_mod, rows_per_group;
   void* y;
   int ldy;
+  int rms;  // 1: no mean subtraction (T5LayerNorm / RMSNorm): y = x * rsqrt(mean(x^2) + eps) * gamma
 };
 
 template <bool FP16, int NV>
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const LayerNormParams p
       sum += (a.x + a.y) + (b.x + b.y) + (c.x + c.y) + (d.x + d.y);
     }
   }
-  const float mean = warp_sum(sum) / static_cast<float>(p.cols);
+  const float mean = p.rms ? 0.f : warp_sum(sum) / static_cast<float>(p.cols);
   float sq = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -856,6 +857,7 @@ int b200_layer_norm(const b200_layer_norm_args* a, void* stream) {
   p.shift = a->shift;
   p.ld_mod = a->ld_mod;
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  p.rms = a->rms ? 1 : 0;
   p.y = a->y;
   p.ldy = a->ldy;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

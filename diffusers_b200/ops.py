@@ -5,7 +5,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_SILU, DTYPE_BF16, DTYPE_FP16,  # noqa: F401
+from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, DTYPE_BF16, DTYPE_FP16,  # noqa: F401
                    B200Error)
 
 _LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -319,6 +319,32 @@ def attention(q, k, v, *, heads, head_dim, scale=None, out=None, nq=0, o_seg=Non
     return None if o_seg is not None else out
 
 
+def text_attention(q, k, v, *, heads, scale, causal=False, bias=None, out=None):
+    """Attention of the text encoders (head_dim 64, <= 512 keys): q/k/v [B, S, heads*64] views, optional causal mask and
+    fp32 bias [heads, Sq, Sk] added to the scaled scores.  Returns [B, Sq, heads*64]."""
+    _need_cuda(q, "q")
+    B, Sq = q.shape[0], q.shape[1]
+    Sk = k.shape[1]
+    if out is None:
+        out = torch.empty((B, Sq, heads * 64), dtype=q.dtype, device=q.device)
+    a = _lib.TextAttentionArgs()
+    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.batch, a.heads, a.sq, a.sk = B, heads, Sq, Sk
+    a.q_row_stride, a.q_batch_stride = q.stride(1), q.stride(0)
+    a.k_row_stride, a.k_batch_stride = k.stride(1), k.stride(0)
+    a.v_row_stride, a.v_batch_stride = v.stride(1), v.stride(0)
+    a.o_row_stride, a.o_batch_stride = out.stride(1), out.stride(0)
+    a.scale, a.causal = float(scale), 1 if causal else 0
+    if bias is not None:
+        if bias.dtype != torch.float32 or tuple(bias.shape) != (heads, Sq, Sk) or not bias.is_contiguous():
+            raise B200Error("text_attention: bias must be a contiguous fp32 [heads, Sq, Sk] tensor")
+        a.bias = bias.data_ptr()
+    a.dtype = _dtype_code(q)
+    _lib.check(_lib.lib().b200_text_attention(C.byref(a), _stream()), "b200_text_attention")
+    _count()
+    return out
+
+
 _GN_WS = {}
 
 
@@ -355,8 +381,8 @@ def group_norm(x, *, batch, hw, groups, eps, gamma=None, beta=None, silu=False, 
     return out
 
 
-def layer_norm(x, *, eps, gamma=None, beta=None, scale=None, shift=None, rows_per_group=0, out=None):
-    """LayerNorm over rows of x [rows, C]; optional AdaLN modulation y*(1+scale[g])+shift[g]."""
+def layer_norm(x, *, eps, gamma=None, beta=None, scale=None, shift=None, rows_per_group=0, out=None, rms=False):
+    """LayerNorm over rows of x [rows, C]; optional AdaLN modulation y*(1+scale[g])+shift[g].  rms=True: RMSNorm (no mean)."""
     _need_cuda(x, "x")
     rows, cols = x.shape
     if out is None:
@@ -370,6 +396,7 @@ def layer_norm(x, *, eps, gamma=None, beta=None, scale=None, shift=None, rows_pe
     a.rows_per_group = rows_per_group
     a.y, a.ldy = out.data_ptr(), out.stride(0)
     a.dtype = _dtype_code(x)
+    a.rms = 1 if rms else 0
     _lib.check(_lib.lib().b200_layer_norm(C.byref(a), _stream()), "b200_layer_norm")
     _count()
     return out

@@ -39,6 +39,7 @@ extern "C" {
 #define B200_ACT_SILU 1
 #define B200_ACT_GELU_ERF 2
 #define B200_ACT_GELU_TANH 3
+#define B200_ACT_QUICK_GELU 4 /* x * sigmoid(1.702 x): CLIP text encoders */
 
 /* Library / device -------------------------------------------------------------------------- */
 int b200_version(void);
@@ -211,6 +212,8 @@ typedef struct {
   void* y;
   int32_t ldy;
   int32_t dtype;
+  int32_t rms;        /* 1 = RMSNorm: no mean subtraction, y = x * rsqrt(mean(x^2) + eps) * gamma  (T5LayerNorm,
+                       * transformers models/t5/modeling_t5.py T5LayerNorm.forward); 0 = LayerNorm                */
 } b200_layer_norm_args;
 
 int b200_layer_norm(const b200_layer_norm_args* args, void* stream);
@@ -362,6 +365,35 @@ int b200_qk_norm_rope(const b200_qk_norm_rope_args* args, void* stream);
 int b200_ddpm_step(const void* model_output, const void* sample, const void* noise, void* prev_sample, int64_t n,
                    float sqrt_beta_prod_t, float sqrt_alpha_prod_t, float pred_original_coeff, float current_sample_coeff,
                    float sigma, int32_t clip_sample, float clip_range, int32_t dtype, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * b200_text_attention — attention of the text encoders either side of the denoiser: head_dim 64, at most 512
+ * keys, optional causal mask and additive bias, fp32 arithmetic.  q/k/v/o are [batch, seq, heads, 64] views given by row and
+ * batch strides in elements, like b200_attention.
+ * Replaces  the attention of transformers' CLIPTextModel / CLIPTextModelWithProjection (models/clip/modeling_clip.py
+ *           CLIPAttention: scale head_dim^-0.5, causal mask) and T5EncoderModel (models/t5/modeling_t5.py T5Attention: no
+ *           scaling, position_bias = relative_attention_bias[bucket(j - i)] added to the scores) as called from
+ *           pipelines/stable_diffusion_xl/pipeline_stable_diffusion_xl.py:283 (encode_prompt) and
+ *           pipelines/flux/pipeline_flux.py:217-387 (_get_t5_prompt_embeds / _get_clip_prompt_embeds).
+ * out[i] = softmax_j(scale * q_i . k_j + bias[h, i, j], j <= i when causal) v_j
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  int32_t batch, heads, sq, sk; /* head_dim is 64; sk <= 512 */
+  int64_t q_row_stride, q_batch_stride;
+  int64_t k_row_stride, k_batch_stride;
+  int64_t v_row_stride, v_batch_stride;
+  int64_t o_row_stride, o_batch_stride;
+  float scale;
+  int32_t causal;
+  const float* bias; /* fp32 [heads, sq, sk] or NULL */
+  int32_t dtype;
+} b200_text_attention_args;
+
+int b200_text_attention(const b200_text_attention_args* args, void* stream);
 
 /* -------------------------------------------------------------------------------------------
  * Peer memory over NVLink / NVSwitch — context parallelism (Ulysses) for one image on several GPUs of a node.

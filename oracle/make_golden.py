@@ -463,11 +463,68 @@ def gen_vae_encode(d):
     torch.save(out, os.path.join(OUT, "vae_encode.pt"))
 
 
+TEXT_CASES = [
+    # name, kind, config overrides, seed, (batch, tokens)
+    ("clip_l_tiny", "clip", dict(vocab_size=1000, hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2, hidden_act="quick_gelu",
+                                 projection_dim=128), 21, (2, 77)),
+    ("clip_g_tiny", "clip_proj", dict(vocab_size=1000, hidden_size=192, intermediate_size=512, num_hidden_layers=2, num_attention_heads=3, hidden_act="gelu",
+                                      projection_dim=64), 22, (3, 77)),
+    ("t5_tiny", "t5", dict(vocab_size=1000, d_model=128, d_kv=64, d_ff=256, num_layers=2, num_heads=2), 23, (2, 96)),
+    ("t5_tiny_512", "t5", dict(vocab_size=1000, d_model=192, d_kv=64, d_ff=384, num_layers=1, num_heads=3), 24, (1, 512)),
+]
+
+
+def gen_text(d):
+    """tests/golden/text.pt: the text encoders of the REAL transformers package (the third-party dependency the reference's
+    pipelines call) in fp32 and bf16 CPU eager, on seeded token ids; weights are regenerated from (spec, seed) on both sides."""
+    import transformers
+    from diffusers_b200 import text_encoders as T
+    out = {"transformers_version": transformers.__version__}
+    for name, kind, upd, seed, (B, S) in TEXT_CASES:
+        if kind == "t5":
+            cfg = dict(T.T5_XXL_CONFIG, **upd)
+            spec = T.t5_encoder_params(cfg)
+            hf = transformers.T5EncoderModel(transformers.T5Config(**cfg)).eval()
+        else:
+            cfg = dict(T.CLIP_L_CONFIG, **upd)
+            spec = T.clip_text_params(cfg, kind == "clip_proj")
+            cls = transformers.CLIPTextModelWithProjection if kind == "clip_proj" else transformers.CLIPTextModel
+            hf = cls(transformers.CLIPTextConfig(**cfg)).eval()
+        sd16 = T.random_state_dict(spec, seed)
+        sd32 = {k: v.float() for k, v in sd16.items()}
+        g = torch.Generator().manual_seed(seed)
+        ids = torch.randint(3, cfg["vocab_size"] - 1, (B, S), generator=g)
+        if kind != "t5":  # an EOS (the largest id: legacy argmax pooling) somewhere in each row, padding after it
+            for b in range(B):
+                e = 5 + 9 * b
+                ids[b, e] = cfg["vocab_size"] - 1
+                ids[b, e + 1:] = 1
+        rec = {}
+        for tag, sdx, dt in (("ref32", sd32, torch.float32), ("ref16", sd16, torch.bfloat16)):
+            m = hf.to(dt)
+            full = dict(sdx)
+            if kind == "t5":
+                full["encoder.embed_tokens.weight"] = full["shared.weight"]
+            missing, unexpected = m.load_state_dict(full, strict=False)
+            assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+            with torch.no_grad():
+                o = m(ids, output_hidden_states=True)
+            r = dict(last_hidden_state=o.last_hidden_state.clone(), penultimate=o.hidden_states[-2].clone(), n_hidden=len(o.hidden_states))
+            if kind == "clip":
+                r["pooler_output"] = o.pooler_output.clone()
+            if kind == "clip_proj":
+                r["text_embeds"] = o.text_embeds.clone()
+            rec[tag] = r
+        out[name] = dict(kind=kind, cfg=cfg, seed=seed, ids=ids, **rec)
+        print(name, tuple(rec["ref32"]["last_hidden_state"].shape), float((rec["ref32"]["last_hidden_state"] - rec["ref16"]["last_hidden_state"].float()).abs().max()))
+    torch.save(out, os.path.join(OUT, "text.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     dmod = ref_shim.import_reference()
-    which = sys.argv[1:] or ["blocks", "layers", "schedulers", "steppers", "models", "pipelines", "checkpoints", "vae_encode"]
+    which = sys.argv[1:] or ["blocks", "layers", "schedulers", "steppers", "models", "pipelines", "checkpoints", "vae_encode", "text"]
     for w in which:
         globals()["gen_" + w](dmod)
     for f in sorted(os.listdir(OUT)):

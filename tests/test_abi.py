@@ -134,7 +134,8 @@ def test_every_compute_entry_point_rejects_null_operands():
         assert fn.argtypes is not None, f"{name}: no ctypes signature declared in _lib.py"
         args = []
         for t in fn.argtypes:
-            args.append(None if t is C.c_void_p else (t(0.0) if t is C.c_float else t(0)))
+            is_ptr = t in (C.c_void_p, C.c_char_p) or isinstance(t, type(C.POINTER(C.c_void_p)))
+            args.append(None if is_ptr else (t(0.0) if t is C.c_float else t(0)))
         rc = fn(*args)
         assert rc < 0, f"{name} accepted null operands (rc={rc})"
         assert len(lib.b200_last_error()) > 0, name

@@ -237,6 +237,39 @@ def test_diagonal_gaussian_is_the_reference_distribution(golden):
     assert float(DiagonalGaussianDistribution(fx["ref32"]).kl().min()) > 0
 
 
+@pytest.mark.parametrize("name", ["clip_l_tiny", "clip_g_tiny", "t5_tiny", "t5_tiny_512"])
+def test_text_encoder_oracle_matches_transformers(golden, name):
+    """N3: oracle/text.py against the real transformers classes the reference's pipelines call (fp32, tests/golden/text.pt)."""
+    import torch
+    from diffusers_b200 import text_encoders as T
+    from oracle import text as otext
+    fx = golden("text")[name]
+    spec = T.t5_encoder_params(fx["cfg"]) if fx["kind"] == "t5" else T.clip_text_params(fx["cfg"], fx["kind"] == "clip_proj")
+    sd32 = {k: v.float() for k, v in T.random_state_dict(spec, fx["seed"]).items()}
+    ref = fx["ref32"]
+    if fx["kind"] == "t5":
+        out = otext.t5_encoder_forward(sd32, fx["cfg"], fx["ids"])
+    else:
+        out = otext.clip_text_forward(sd32, fx["cfg"], fx["ids"], with_projection=fx["kind"] == "clip_proj")
+    scale = float(ref["last_hidden_state"].abs().max())
+    assert float((out["last_hidden_state"] - ref["last_hidden_state"]).abs().max()) <= 2e-5 * max(1.0, scale)
+    assert len(out["hidden_states"]) == ref["n_hidden"]
+    assert float((out["hidden_states"][-2] - ref["penultimate"]).abs().max()) <= 2e-5 * max(1.0, float(ref["penultimate"].abs().max()))
+    if "pooler_output" in ref:
+        assert float((out["pooler_output"] - ref["pooler_output"]).abs().max()) <= 2e-5 * max(1.0, scale)
+    if "text_embeds" in ref:
+        assert float((out["text_embeds"] - ref["text_embeds"]).abs().max()) <= 2e-5 * max(1.0, scale)
+
+
+def test_t5_bucket_table_is_the_oracles():
+    import torch
+    from diffusers_b200.text_encoders import t5_relative_position_bucket
+    from oracle.text import t5_bucket
+    pos = torch.arange(512)
+    rel = pos[None, :] - pos[:, None]
+    assert torch.equal(t5_relative_position_bucket(rel, 32, 128), t5_bucket(rel, 32, 128))
+
+
 @pytest.mark.parametrize("name", ["flux_tiny", "flux_hd128"])
 def test_flux_matches_reference(golden, name):
     fx = golden("models")[name]
