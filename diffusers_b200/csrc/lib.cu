@@ -91,7 +91,18 @@ const char* b200_last_error(void) { return b200::g_err; }
 
 int b200_num_sms(void) { return b200::num_sms(); }
 
+static int init_device(int device);
+
 int b200_init(int device) {
+  // the process's current device is the caller's business: validate / configure `device`, then put back what was current
+  int prev = -1;
+  const bool have_prev = cudaGetDevice(&prev) == cudaSuccess;
+  const int rc = init_device(device);
+  if (have_prev && prev != device) cudaSetDevice(prev);
+  return rc;
+}
+
+static int init_device(int device) {
   B200_CHECK_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   B200_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));

@@ -114,7 +114,12 @@ def _ptr(t):
 def _need_cuda(t, name):
     if not t.is_cuda:
         raise B200Error(f"{name} must be a CUDA tensor (no CPU fallback)")
-    _lib.init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        # every launch goes to torch.cuda.current_stream(): a stream of the CURRENT device
+        raise B200Error(f"{name} lives on cuda:{idx} but the current device is cuda:{torch.cuda.current_device()}: "
+                        f"wrap the call in `with torch.cuda.device({idx}):`")
+    _lib.init(idx)
 
 
 class QkRope:

@@ -64,11 +64,42 @@ class StableDiffusionXLPipeline:
                                                 torch_dtype=torch_dtype, device=device, variant=variant)
         return cls(c["vae"], c["unet"], c["scheduler"])
 
-    def __init__(self, vae, unet, scheduler):
+    def __init__(self, vae, unet, scheduler, text_encoder=None, text_encoder_2=None, force_zeros_for_empty_prompt=True):
         self.vae, self.unet, self.scheduler = vae, unet, scheduler
+        self.text_encoder, self.text_encoder_2 = text_encoder, text_encoder_2  # text_encoders.CLIPTextModel / ...WithProjection (optional)
+        self.force_zeros_for_empty_prompt = force_zeros_for_empty_prompt
         self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
         self.default_sample_size = unet.config.sample_size
         self._graph = None
+
+    @torch.no_grad()
+    def encode_prompt(self, text_input_ids, text_input_ids_2, negative_input_ids=None, negative_input_ids_2=None, do_classifier_free_guidance=True):
+        """StableDiffusionXLPipeline.encode_prompt (pipeline_stable_diffusion_xl.py:283-470) from TOKEN IDS (the tokenizers are host-side
+        string processing and stay with transformers): per encoder `hidden_states[-2]`, concatenated on the feature axis; the pooled
+        embedding is `[0]` of the last (projection) encoder; without negative ids the negative embeddings are zeros
+        (force_zeros_for_empty_prompt).  -> (prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds)"""
+        if self.text_encoder is None or self.text_encoder_2 is None:
+            raise ValueError("encode_prompt needs text_encoder and text_encoder_2 (diffusers_b200.text_encoders)")
+
+        def run(ids_pair):
+            embeds, pooled = [], None
+            for ids, enc in zip(ids_pair, (self.text_encoder, self.text_encoder_2)):
+                out = enc(ids.to(self.device), output_hidden_states=True)
+                if out[0].ndim == 2:
+                    pooled = out[0]
+                embeds.append(out.hidden_states[-2])
+            return torch.cat(embeds, dim=-1), pooled
+
+        pe, pooled = run((text_input_ids, text_input_ids_2))
+        npe = npooled = None
+        if do_classifier_free_guidance:
+            if negative_input_ids is None and self.force_zeros_for_empty_prompt:
+                npe, npooled = torch.zeros_like(pe), torch.zeros_like(pooled)
+            else:
+                if negative_input_ids is None or negative_input_ids_2 is None:
+                    raise ValueError("negative token ids for both encoders are needed when force_zeros_for_empty_prompt is False")
+                npe, npooled = run((negative_input_ids, negative_input_ids_2))
+        return pe, npe, pooled, npooled
 
     @property
     def device(self):
@@ -170,6 +201,11 @@ class StableDiffusionXLPipeline:
         if output_type == "latent":
             image = lat
         else:
+            if self.vae.dtype == torch.float16 and self.vae.config.force_upcast:
+                # the reference up-casts such a VAE to fp32 for the decode (pipeline_stable_diffusion_xl.py:1262-1270 `needs_upcasting`:
+                # the SDXL VAE overflows in fp16); there is no fp32 kernel path here, so refuse instead of returning NaN / black images
+                raise NotImplementedError("an fp16 AutoencoderKL with force_upcast=True must be decoded in fp32 by the reference; "
+                                          "build the AutoencoderKL in bfloat16 (same range as fp32) instead")
             lat = lat / self.vae.config.scaling_factor
             image = self.vae.decode(lat, return_dict=False)[0]
             image = postprocess_pt(image)
@@ -225,10 +261,24 @@ class FluxPipeline:
         vae = type("VaeGeometry", (), dict(config=FrozenConfig(vae_cfg)))()
         return cls(c["scheduler"], vae, c["transformer"])
 
-    def __init__(self, scheduler, vae, transformer):
+    def __init__(self, scheduler, vae, transformer, text_encoder=None, text_encoder_2=None):
         self.scheduler, self.vae, self.transformer = scheduler, vae, transformer
+        self.text_encoder, self.text_encoder_2 = text_encoder, text_encoder_2  # text_encoders.CLIPTextModel, T5EncoderModel (optional)
         self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
         self.default_sample_size = 128
+
+    @torch.no_grad()
+    def encode_prompt(self, clip_input_ids, t5_input_ids):
+        """FluxPipeline.encode_prompt (pipeline_flux.py:217-387) from TOKEN IDS: pooled = CLIP `pooler_output`
+        (_get_clip_prompt_embeds), prompt_embeds = T5 `[0]` (_get_t5_prompt_embeds), text_ids = zeros.
+        -> (prompt_embeds, pooled_prompt_embeds, text_ids)"""
+        if self.text_encoder is None or self.text_encoder_2 is None:
+            raise ValueError("encode_prompt needs text_encoder (CLIP) and text_encoder_2 (T5) (diffusers_b200.text_encoders)")
+        dev = self.transformer.device
+        pooled = self.text_encoder(clip_input_ids.to(dev), output_hidden_states=False).pooler_output
+        pe = self.text_encoder_2(t5_input_ids.to(dev), output_hidden_states=False)[0]
+        dt = self.transformer.dtype
+        return pe.to(dt), pooled.to(dt), torch.zeros(pe.shape[1], 3, device=dev, dtype=dt)
 
     @staticmethod
     def _prepare_latent_image_ids(height, width, device, dtype):

@@ -68,3 +68,32 @@ def test_text_attention_kernel(B, H, Sq, Sk, causal, bias, dt):
     err = (out.float() - ref).abs()
     tol = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
     assert float((err - tol * ref.abs()).max()) <= 2e-3, float(err.max())  # fp32 arithmetic, one rounding of the result
+
+
+def test_pipelines_encode_prompt_from_token_ids(golden):
+    """encode_prompt of both pipelines composes the encoders exactly as the reference does (pipeline_stable_diffusion_xl.py:283-470,
+    pipeline_flux.py:217-387): penultimate hidden states concatenated + projection pooled (SDXL); T5 states + CLIP pooler (Flux)."""
+    from diffusers_b200.pipelines import FluxPipeline, StableDiffusionXLPipeline
+    fx = golden("text")
+    mk = lambda name, cls, spec_fn: cls(fx[name]["cfg"], T.random_state_dict(spec_fn(fx[name]["cfg"]), fx[name]["seed"]), device="cuda")  # noqa: E731
+    te1 = mk("clip_l_tiny", T.CLIPTextModel, lambda c: T.clip_text_params(c, False))
+    te2 = mk("clip_g_tiny", T.CLIPTextModelWithProjection, lambda c: T.clip_text_params(c, True))
+    t5 = mk("t5_tiny", T.T5EncoderModel, T.t5_encoder_params)
+    unet = type("U", (), dict(config=type("C", (), dict(sample_size=16))(), device=torch.device("cuda"), dtype=torch.bfloat16))()
+    pipe = StableDiffusionXLPipeline(None, unet, None, text_encoder=te1, text_encoder_2=te2)
+    ids1, ids2 = fx["clip_l_tiny"]["ids"][:2], fx["clip_g_tiny"]["ids"][:2]
+    pe, npe, pooled, npooled = pipe.encode_prompt(ids1, ids2)
+    assert tuple(pe.shape) == (2, 77, 128 + 192) and tuple(pooled.shape) == (2, 64)
+    assert float(npe.abs().max()) == 0 and float(npooled.abs().max()) == 0
+    _close("sdxl prompt_embeds[..., :128]", pe[..., :128], fx["clip_l_tiny"]["ref32"]["penultimate"], fx["clip_l_tiny"]["ref16"]["penultimate"])
+    _close("sdxl prompt_embeds[..., 128:]", pe[..., 128:], fx["clip_g_tiny"]["ref32"]["penultimate"][:2], fx["clip_g_tiny"]["ref16"]["penultimate"][:2])
+    _close("sdxl pooled", pooled, fx["clip_g_tiny"]["ref32"]["text_embeds"][:2], fx["clip_g_tiny"]["ref16"]["text_embeds"][:2])
+    pe2, npe2, _, _ = pipe.encode_prompt(ids1, ids2, negative_input_ids=ids1.flip(0), negative_input_ids_2=ids2.flip(0))
+    assert torch.equal(pe2, pe) and torch.equal(npe2, pe.flip(0))
+    tr = type("Tr", (), dict(device=torch.device("cuda"), dtype=torch.bfloat16))()
+    vae = type("V", (), dict(config=type("C", (), dict(block_out_channels=(1, 1, 1, 1)))()))()
+    fpipe = FluxPipeline(None, vae, tr, text_encoder=te1, text_encoder_2=t5)
+    fpe, fpool, tids = fpipe.encode_prompt(ids1, fx["t5_tiny"]["ids"])
+    _close("flux prompt_embeds", fpe, fx["t5_tiny"]["ref32"]["last_hidden_state"], fx["t5_tiny"]["ref16"]["last_hidden_state"])
+    _close("flux pooled", fpool, fx["clip_l_tiny"]["ref32"]["pooler_output"], fx["clip_l_tiny"]["ref16"]["pooler_output"])
+    assert tuple(tids.shape) == (96, 3) and float(tids.abs().max()) == 0
