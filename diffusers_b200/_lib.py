@@ -33,6 +33,7 @@ class ConvGemmArgs(C.Structure):
         ("up2x_parity", C.c_int32), ("pad_after_only", C.c_int32),
         ("qk_cols", C.c_int32), ("qk_head_dim", C.c_int32), ("qk_norm_w", C.c_void_p), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
         ("rope_ld", C.c_int32), ("rope_row0", C.c_int32), ("qk_eps", C.c_float),
+        ("y_peers", C.c_void_p * 8), ("y_block_cols", C.c_int32),
     ]
 
 

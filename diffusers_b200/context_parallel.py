@@ -7,8 +7,8 @@ head-sharded q/k/v over the full sequence, and the attention output back.
 
 Here neither all-to-all exists as a separate step (no NCCL on the data path):
   * the QKV GEMM of rank r stores the columns of the heads rank d owns straight into d's joint QKV buffer over NVLink
-    (b200_conv_gemm with `y` = a peer mapping; one launch per destination, weight rows permuted once so that a
-    destination's [q | k | v] rows are contiguous);
+    (b200_conv_gemm_args.y_peers: ONE launch whose output column blocks go to different peer mappings; the weight rows are
+    permuted once so that a destination's [q | k | v] rows are one block, q / k normalised and rotated in the epilogue);
   * the attention kernel stores output row i straight into the buffer of the rank that owns row i
     (b200_attention_args.o_seg);
   * b200_peer_barrier (one tiny kernel, flags in peer memory) separates the phases.
@@ -100,11 +100,12 @@ class UlyssesPlan:
         return torch.cat(idx)
 
     # --- fused-QKV weight rows ([q | k | v], each D rows, head-major): destination-major order
-    def qkv_row_permutation(self):
-        """perm: row j of the permuted weight = row perm[j] of the fused [q | k | v] weight; destination d's rows are
-        [d*3*Dl, (d+1)*3*Dl) = [q heads of d | k heads of d | v heads of d]."""
+    def qkv_row_permutation(self, order=None):
+        """perm: row j of the permuted weight = row perm[j] of the fused [q | k | v] weight; block i (3*Dl rows) holds destination
+        order[i]'s rows [q heads | k heads | v heads] (order = range(world) unless given; the model uses send_order(), so that at
+        any moment the ranks' GEMMs store to different peers)."""
         idx = []
-        for d in range(self.world):
+        for d in (range(self.world) if order is None else order):
             for part in range(3):
                 idx.append(part * self.D + torch.arange(d * self.Dl, (d + 1) * self.Dl))
         return torch.cat(idx)

@@ -101,6 +101,10 @@ struct ConvGemmParams {
   const float* rope_sin;
   int rope_ld, rope_row0;  // position of output row r = rope_row0 + r
   float qk_eps;
+  // context parallelism: output column block j (y_block_cols columns) is stored through y_map (j == 0) / y_map_peer[j - 1]: the
+  // buffers of the ranks that own those heads (peer mappings over NVLink); the q / k / v pattern of QKR repeats per block
+  CUtensorMap y_map_peer[7];
+  int y_block_cols;  // 0 = one output tensor
 };
 
 template <int BN, bool PAIR>
@@ -496,12 +500,14 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
         tmem_wait_ld();
         const bool stamp = dbg && issuer && it == 0 && c < 2;
         if (stamp) dbg[8 + c * 4] = clock64();
-        if (QKR && yc0 < p.qk_cols) {
+        const int ycb = (QKR && p.y_block_cols > 0) ? yc0 % p.y_block_cols : yc0;  // column inside its destination block ([q | k | v] per block)
+        if (QKR && ycb < p.qk_cols) {
           // ---- q / k head columns of a fused QKV projection: per-head RMSNorm (weight) + rotary embedding before the store, so
           // that the attention kernel reads finished q / k (transformer_flux.py:102-119 without the extra pass over the buffer).
           // Rounding points are those of the reference's eager ops (and of qk_norm_rope_kernel): the projection is rounded to 16
           // bit, the normalised value twice (x * rstd, then * weight), the rotation is computed in fp32 and rounded once.
           const int cph = p.qk_hd >> 5;       // 32-column chunks per head (2 | 4)
+          (void)0;
           const int cin = c & (cph - 1);      // this chunk's index inside its head (heads never straddle tiles: BN % 128 == 0)
           if (cin == half) {
             // first of this warp's chunks of the head: sum of squares over the WHOLE head (the other warp of the quarter owns the
@@ -530,7 +536,7 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
             qk_rstd = rsqrtf(ss * (p.qk_hd == 128 ? (1.0f / 128.0f) : (1.0f / 64.0f)) + p.qk_eps);
           }
           const int hcol = cin * 32;  // first column of the chunk inside its head
-          const typename H::T* nw = static_cast<const typename H::T*>(p.qk_w) + ((yc0 - hcol) >= (p.qk_cols >> 1) ? p.qk_hd : 0) + hcol;
+          const typename H::T* nw = static_cast<const typename H::T*>(p.qk_w) + ((ycb - hcol) >= (p.qk_cols >> 1) ? p.qk_hd : 0) + hcol;
           const long long pos = valid ? (p.rope_row0 + pix) : 0;
           const float* cs_p = p.rope_cos + static_cast<long long>(hcol >> 1) * p.rope_ld + pos;
           const float* sn_p = p.rope_sin + static_cast<long long>(hcol >> 1) * p.rope_ld + pos;
@@ -682,7 +688,14 @@ __global__ void __launch_bounds__(384, 1) conv_gemm_kernel(const __grid_constant
           named_bar_sync(bar_id, 128);
           if (q == 0) {
             if (elect_one()) {
-              if (real_tile) tma_store_4d(&p.y_map, slab, yc0, tc.w0, tc.h0, tc.img);
+              if (real_tile) {
+                if (p.y_block_cols > 0) {
+                  const int dest = yc0 / p.y_block_cols;  // the all-to-all of Ulysses: this chunk belongs to the heads of rank `dest`
+                  tma_store_4d(dest == 0 ? &p.y_map : &p.y_map_peer[dest - 1], slab, yc0 - dest * p.y_block_cols, tc.w0, tc.h0, tc.img);
+                } else {
+                  tma_store_4d(&p.y_map, slab, yc0, tc.w0, tc.h0, tc.img);
+                }
+              }
               bulk_commit_group();
               if (stamp) dbg[11 + c * 4] = clock64();
             }
@@ -923,7 +936,15 @@ int32_t b200_conv_gemm_row_stats_parts(const b200_conv_gemm_args* a) {
 int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
   using namespace b200;
   B200_CHECK_ARG(a != nullptr, "conv_gemm: null args");
-  B200_CHECK_ARG(a->x[0] && a->w && a->y, "conv_gemm: null x/w/y");
+  B200_CHECK_ARG(a->x[0] && a->w && (a->y || a->y_block_cols > 0), "conv_gemm: null x/w/y");
+  if (a->y_block_cols > 0) {
+    B200_CHECK_ARG(a->y_block_cols % 32 == 0 && a->N % a->y_block_cols == 0 && a->N / a->y_block_cols <= 8 && !a->geglu && !a->out_fp32 && a->ksize == 1 &&
+                       !a->residual && !a->row_stats_out,
+                   "conv_gemm: y_peers splits the N = %d output columns of a plain linear into at most 8 blocks of y_block_cols = %d (a multiple of 32)", a->N,
+                   a->y_block_cols);
+    for (int j = 0; j < a->N / a->y_block_cols; ++j)
+      B200_CHECK_ARG(a->y_peers[j] != nullptr && aligned16(a->y_peers[j]), "conv_gemm: y_peers[%d] null or not 16-byte aligned", j);
+  }
   B200_CHECK_ARG(a->ksize == 1 || a->ksize == 3 || (a->ksize == 2 && a->up2x_parity >= 1 && a->up2x_parity <= 4),
                  "conv_gemm: ksize %d (need 1 or 3; 2 only as a parity class of the folded nearest-2x upsample)", a->ksize);
   const bool up2x = a->ksize == 2;
@@ -998,6 +1019,9 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
     B200_CHECK_ARG(a->rope_ld > 0 && a->rope_row0 >= 0 && a->rope_row0 + a->W <= a->rope_ld, "conv_gemm: rope table of %d positions does not cover rows [%d, %d)",
                    a->rope_ld, a->rope_row0, a->rope_row0 + a->W);
     B200_CHECK_ARG(a->tile_n == 0 || a->tile_n == 128 || a->tile_n == 256, "conv_gemm: qk_rope needs tile_n 128 or 256");
+    if (a->y_block_cols > 0)
+      B200_CHECK_ARG(a->qk_cols <= a->y_block_cols && a->y_block_cols % 128 == 0, "conv_gemm: qk_cols %d must fit a block of y_block_cols = %d (a multiple of 128)",
+                     a->qk_cols, a->y_block_cols);
   }
   pick_config(prm.m_tiles, a->N, prm.k_chunks, a->geglu, a->geglu && !a->tile_n ? pick_tile_n(0, a->N, 1) : a->tile_n, a->cluster_m, &bn, &cm, qkr);
   B200_CHECK_ARG(bn != 0, "conv_gemm: no valid tile configuration (N=%d geglu=%d tile_n=%d)", a->N, a->geglu, a->tile_n);
@@ -1115,12 +1139,22 @@ int b200_conv_gemm(const b200_conv_gemm_args* a, void* stream) {
       const uint64_t str[3] = {ldy * 2 * 2, ldy * 2 * (2 * Wo) * 2, ldy * 2 * (2 * Wo) * (2 * Ho)};
       const uint8_t* base = static_cast<const uint8_t*>(a->y) + (static_cast<uint64_t>(ph) * (2 * Wo) + pw) * ldy * 2;
       r = make_tensor_map_16b(&prm.y_map, base, 4, dims, str, ybox, "conv_gemm Y (upsampled parity view)", 64);
+    } else if (a->y_block_cols > 0) {
+      const uint64_t bdims[4] = {static_cast<uint64_t>(a->y_block_cols), dims[1], dims[2], dims[3]};
+      const uint64_t str[3] = {ldy * 2, ldy * 2 * Wo, ldy * 2 * Wo * Ho};
+      const int nblk = n_out / a->y_block_cols;
+      r = 0;
+      for (int j = 0; j < nblk && !r; ++j)
+        r = make_tensor_map_16b(j == 0 ? &prm.y_map : &prm.y_map_peer[j - 1], a->y_peers[j], 4, bdims, str, ybox, "conv_gemm Y (peer block)", 64);
+      prm.y_block_cols = a->y_block_cols;
     } else {
       const uint64_t str[3] = {ldy * 2, ldy * 2 * Wo, ldy * 2 * Wo * Ho};
       r = make_tensor_map_16b(&prm.y_map, a->y, 4, dims, str, ybox, "conv_gemm Y", 64);
     }
     if (r) return r;
   }
+  if (a->y_block_cols > 0)
+    B200_CHECK_ARG(prm.tma_store, "conv_gemm: y_peers needs the TMA-store epilogue (16-byte aligned buffers, N %% 32 == 0, B200_NO_TMA_STORE unset)");
 
   prm.tma_res = (prm.tma_store && a->residual && !a->geglu) ? 1 : 0;
   if (prm.tma_res) {

@@ -149,7 +149,7 @@ class FoldedLayerNorm:
 
 def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, act=ACT_NONE, geglu=False,
               gate=None, rowvec=None, rows_per_group=0, residual=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None,
-              row_stats=False, ln=None, pad_after_only=False, qk_rope=None):
+              row_stats=False, ln=None, pad_after_only=False, qk_rope=None, out_blocks=None):
     """y = epilogue(conv/linear(x [, x2]))  -  see b200_conv_gemm in include/b200_diffusion.h.
 
     x, x2: NHWC activations given as 2-D [batch*H*W, C] (or any shape whose last dim is C, contiguous rows).
@@ -161,7 +161,14 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
     c1 = x2.shape[-1] if x2 is not None else 0
     Ho, Wo = (H, W) if stride == 1 else (H // 2, W // 2)
     n_out = N // 2 if geglu else N
-    if out is None:
+    if out_blocks is not None:
+        # context parallelism: column block j of the output goes to out_blocks[j] ([rows, N / len] views of the owners' buffers)
+        nb = len(out_blocks)
+        if out is not None or nb < 1 or nb > 8 or N % nb or any(tuple(t.shape) != (batch * Ho * Wo, N // nb) or t.stride(0) != out_blocks[0].stride(0) or
+                                                                t.stride(1) != 1 for t in out_blocks):
+            raise B200Error("conv_gemm: out_blocks must be 1..8 [rows, N / blocks] views with one row stride (and no `out`)")
+        out = out_blocks[0]
+    elif out is None:
         out = torch.empty((batch * Ho * Wo, n_out), dtype=torch.float32 if out_fp32 else x.dtype, device=x.device)
     a = _lib.ConvGemmArgs()
     a.x[0] = x.data_ptr()
@@ -187,6 +194,10 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
     a.cluster_m = cluster_m
     a.debug_timestamps = _ptr(debug_timestamps)
     a.pad_after_only = 1 if pad_after_only else 0
+    if out_blocks is not None:
+        a.y_block_cols = N // len(out_blocks)
+        for j, t in enumerate(out_blocks):
+            a.y_peers[j] = t.data_ptr()
     stats = None
     if row_stats:
         parts = int(_lib.lib().b200_conv_gemm_row_stats_parts(C.byref(a)))
@@ -216,17 +227,20 @@ def conv_gemm(x, w, N, *, batch, H, W, ksize=1, stride=1, x2=None, bias=None, ac
     else:
         _lib.check(_lib.lib().b200_conv_gemm(C.byref(a), _stream()), "b200_conv_gemm")
     _count()
+    if out_blocks is not None:
+        return None
     return (out, stats) if row_stats else out
 
 
 def linear(x, w, N, *, bias=None, act=ACT_NONE, geglu=False, gate=None, rowvec=None, rows_per_group=0,
-           residual=None, x2=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None, row_stats=False, ln=None, qk_rope=None):
+           residual=None, x2=None, out=None, tile_n=0, out_fp32=False, cluster_m=0, debug_timestamps=None, row_stats=False, ln=None, qk_rope=None,
+           out_blocks=None):
     """nn.Linear on token rows: x [rows, K] (row stride arbitrary multiple of 8)."""
     rows = x.shape[0]
     return conv_gemm(x, w, N, batch=1, H=1, W=rows, ksize=1, stride=1, x2=x2, bias=bias, act=act, geglu=geglu,
                      gate=gate, rowvec=rowvec, rows_per_group=rows_per_group, residual=residual, out=out,
                      tile_n=tile_n, out_fp32=out_fp32, cluster_m=cluster_m, debug_timestamps=debug_timestamps, row_stats=row_stats, ln=ln,
-                     qk_rope=qk_rope)
+                     qk_rope=qk_rope, out_blocks=out_blocks)
 
 
 def upsample2x_conv(x, w4, N, *, batch, H, W, bias=None, act=ACT_NONE, out=None):

@@ -325,7 +325,7 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
             return
         cfg = self.config
         probe = UlyssesPlan(world, rank, world * 8, world * 8, cfg["num_attention_heads"], cfg["attention_head_dim"])  # validates heads % world
-        perm = probe.qkv_row_permutation().to(self.device)
+        perm = probe.qkv_row_permutation(probe.send_order()).to(self.device)  # block i = the rows of destination send_order()[i]
         for blk in self.double + self.single:
             for key in ("qkv", "aqkv"):
                 if key in blk:
@@ -396,9 +396,8 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
             # q / k already normalised and rotated (positions of MY rows: the local transposed tables)
             n = rows_in.shape[0]
             qk = ops.QkRope(self.W(nw), cosT, sinT, row_off, 2 * Dl, hd, 1e-6) if fused else None
-            for d in order:
-                ops.linear(rows_in, self.W(l["w"])[d * 3 * Dl:(d + 1) * 3 * Dl], 3 * Dl, bias=self.W(l["b"])[d * 3 * Dl:(d + 1) * 3 * Dl],
-                           out=J[d][b0 + row_off: b0 + row_off + n], qk_rope=qk)
+            ops.linear(rows_in, self.W(l["w"]), 3 * D, bias=self.W(l["b"]), qk_rope=qk,
+                       out_blocks=[J[d][b0 + row_off: b0 + row_off + n] for d in order])  # ONE launch, column block i -> rank order[i]
 
         def attend(blk, txt_rows):
             pg.barrier()  # every rank's q/k/v tiles have landed in my J

@@ -148,6 +148,13 @@ typedef struct {
   int32_t rope_ld;
   int32_t rope_row0;
   float qk_eps;
+  /* ---- context parallelism (see the peer-memory section): with y_block_cols > 0 the N output columns of a plain linear are
+   * N / y_block_cols (<= 8) blocks; block j is stored to y_peers[j] ([rows, ldy] buffers, columns [0, y_block_cols)) instead of
+   * `y` - the joint QKV buffers of the ranks that own those heads, peer mappings over NVLink for the other ranks.  This is the
+   * first all-to-all of Ulysses attention (models/attention_dispatch.py:2528-2540) done by the GEMM's own TMA stores.  With
+   * qk_cols > 0 the [q | k | v] column pattern repeats in every block (qk_cols <= y_block_cols). */
+  void* y_peers[8];
+  int32_t y_block_cols;
 } b200_conv_gemm_args;
 
 int b200_conv_gemm(const b200_conv_gemm_args* args, void* stream);

@@ -107,3 +107,37 @@ def test_conv_gemm_cluster_multicast_sizes(cm):
     summary = p.stdout.split("SUMMARY", 1)[1]
     assert "FAIL" not in summary and "ERROR" not in summary, p.stdout[-3000:]
 
+
+
+@pytest.mark.parametrize("rows,K,blocks,bcols,hd", [(576, 256, 8, 384, 128), (2304, 128, 2, 1536, 128), (200, 64, 3, 384, 64)])
+def test_conv_gemm_column_blocks_to_separate_buffers(rows, K, blocks, bcols, hd):
+    """b200_conv_gemm_args.y_peers (context parallelism: column block j of the output goes to rank j's buffer), here with local
+    buffers: every block must equal the matching columns of the plain launch bit for bit, with and without the q/k RMSNorm + RoPE
+    epilogue whose [q | k | v] pattern repeats per block."""
+    from diffusers_b200 import ops, packing
+    g = torch.Generator(device="cuda").manual_seed(7)
+    N = blocks * bcols
+    x = torch.randn(rows, K, generator=g, device="cuda").bfloat16()
+    w = packing.pack_linear_weight(torch.randn(N, K, generator=g, device="cuda").float() * K ** -0.5).bfloat16().cuda()
+    b = (torch.randn(N, generator=g, device="cuda") * 0.2).bfloat16()
+    plain = ops.linear(x, w, N, bias=b)
+    bufs = [torch.full((rows + 3, bcols + 64), 7.0, dtype=torch.bfloat16, device="cuda") for _ in range(blocks)]
+    views = [t[3:, 64:] for t in bufs] if bcols % 8 == 0 else None  # offset views: separate bases, same row stride
+    ops.linear(x, w, N, bias=b, out_blocks=views)
+    torch.cuda.synchronize()
+    for j, v in enumerate(views):
+        assert torch.equal(v, plain[:, j * bcols:(j + 1) * bcols]), j
+        assert float((bufs[j][:3] - 7).abs().max()) == 0 and float((bufs[j][:, :64] - 7).abs().max()) == 0  # nothing outside the view
+    # q/k pattern per block: compare with the one-block-at-a-time launches
+    qk = 2 * (bcols // 3)
+    if qk % (2 * hd) == 0:
+        ang = torch.rand(rows, hd // 2, generator=g, device="cuda") * 6.28
+        cos, sin = torch.cos(ang).repeat_interleave(2, 1).contiguous(), torch.sin(ang).repeat_interleave(2, 1).contiguous()
+        cT, sT = ops.rope_tables_transposed(cos, sin)
+        nw = (torch.randn(2, hd, generator=g, device="cuda") * 0.1 + 1).bfloat16()
+        rope = ops.QkRope(nw, cT, sT, 0, qk, hd)
+        ops.linear(x, w, N, bias=b, out_blocks=views, qk_rope=rope)
+        for j, v in enumerate(views):
+            one = ops.linear(x, w[j * bcols:(j + 1) * bcols], bcols, bias=b[j * bcols:(j + 1) * bcols], qk_rope=rope)
+            torch.cuda.synchronize()
+            assert torch.equal(v, one), j
