@@ -454,6 +454,7 @@ class Ctx:
         self.dt = torch.bfloat16
         self.pk = peaks()
         self.gpu_dead = False
+        self.flux_state = None
 
     def barrier(self):
         if self.world > 1:
@@ -643,7 +644,8 @@ def flux_section(cx, standalone=False):
     # N > 1: ONE latent sharded over all N GPUs (Ulysses context parallelism over peer memory): strong scaling of
     # the single-image latency.  Runs last: it permutes the QKV weight rows of `tr` in place.
     if world > 1 and not args.no_context_parallel:
-        sec["context_parallel"] = flux_context_parallel(cx, pipe, tr, res, call, nsteps, ms / n)
+        cx.flux_state = (pipe, tr, res, call, nsteps, ms / n)  # run_b200 runs it LAST, under a watchdog (see there)
+        return sec
     del pipe, tr
     torch.cuda.empty_cache()
     return sec
@@ -740,6 +742,27 @@ def run_b200(args, rank, world, local_rank):
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_subprocess(args)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "dtype", "t_step_runs_s", "run_spread") if k in cb}
+    if cx.flux_state is not None:
+        # ONE latent over all N GPUs (context parallelism over peer memory).  It is the only section in which a rank can wait for a
+        # peer inside a kernel, so it runs last and under a watchdog: whatever happens to it, rank 0 prints the line it already has.
+        import threading
+        sec = line if wl == "flux" else line["flux"]
+        sec["context_parallel"] = "failed: no result within 240 s (watchdog)"
+
+        def give_up():
+            if rank == 0:
+                emit(line)
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+        dog = threading.Timer(240.0, give_up)
+        dog.daemon = True
+        dog.start()
+        res = flux_context_parallel(cx, *cx.flux_state)
+        dog.cancel()
+        sec["context_parallel"] = res
+        cx.flux_state = None
     if rank == 0 and line is not None:
         emit(line)
     if cx.gpu_dead:  # a trapped kernel left the CUDA context unusable: the line is out, skip the collective teardown

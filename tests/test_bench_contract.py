@@ -75,3 +75,40 @@ def test_flop_constants_match_baseline():
 def test_one_numa_node_physical_cores_is_a_subset_of_the_affinity_mask():
     cores = bench.one_numa_node_physical_cores()
     assert cores and set(cores) <= set(os.sched_getaffinity(0)) and len(set(cores)) == len(cores)
+
+
+def test_context_parallel_section_runs_last_and_lands_in_the_flux_section(monkeypatch):
+    """N > 1: the Flux context-parallel measurement is deferred to the end of run_b200 (under its watchdog) and its result - or
+    its failure string - ends up in line["flux"]["context_parallel"] of the one JSON line; ranks other than 0 print nothing."""
+    class FakeCtx:
+        def __init__(self, args, rank, world, local_rank):
+            self.args, self.rank, self.world, self.gpu_dead, self.flux_state = args, rank, world, False, None
+
+    order = []
+
+    def fake_flux(cx, standalone=False):
+        order.append("flux")
+        cx.flux_state = ("pipe", "tr", "res", "call", 28, 1900.0)
+        return dict(metric="latents/sec", value=1.0)
+
+    def fake_cp(cx, pipe, tr, res, call, nsteps, replica_ms):
+        order.append("cp")
+        assert (pipe, tr, res, call, nsteps, replica_ms) == ("pipe", "tr", "res", "call", 28, 1900.0)
+        return dict(ulysses_degree=cx.world, value=0.8)
+
+    monkeypatch.setattr(bench, "Ctx", FakeCtx)
+    monkeypatch.setattr(bench, "sdxl_section", lambda cx: order.append("sdxl") or dict(metric="images/sec", value=2.0))
+    monkeypatch.setattr(bench, "flux_section", fake_flux)
+    monkeypatch.setattr(bench, "flux_context_parallel", fake_cp)
+    out = []
+    monkeypatch.setattr(bench, "emit", lambda line: out.append(json.loads(json.dumps(line))))
+    a = _args(workload="all", gpus=2, impl="b200", no_context_parallel=False)
+    bench.run_b200(a, 0, 2, 0)
+    assert order == ["sdxl", "flux", "cp"] and len(out) == 1
+    assert out[0]["flux"]["context_parallel"] == dict(ulysses_degree=2, value=0.8) and out[0]["value"] == 2.0
+    order.clear()
+    bench.run_b200(a, 1, 2, 1)
+    assert order == ["sdxl", "flux", "cp"] and len(out) == 1  # rank 1 measures too, prints nothing
+    order.clear()
+    bench.run_b200(_args(workload="flux", gpus=2, impl="b200", no_context_parallel=False), 0, 2, 0)
+    assert order == ["flux", "cp"] and out[1]["context_parallel"]["value"] == 0.8
