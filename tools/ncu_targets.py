@@ -38,6 +38,15 @@ bmod = rnd(18432 * 8)
 xv = rnd(1024 * 1024, 128)
 wv = packing.pack_conv_weight(rnd(128, 128, 3, 3, sc=(128 * 9) ** -0.5))
 gv, bv = rnd(128), rnd(128)
+# round 2, second session: fused QKV projection with the q/k RMSNorm + RoPE epilogue (Flux single block), T5-XXL / CLIP text attention
+xq = rnd(4608, 3072)
+wq3 = packing.pack_linear_weight(rnd(9216, 3072, sc=3072 ** -0.5))
+bq3 = rnd(9216)
+nw2 = (rnd(2, 128, sc=0.1) + 1).contiguous()
+cosT, sinT = ops.rope_tables_transposed(cos, sin)
+t5q = rnd(1, 512, 3 * 4096)
+t5b = (torch.randn(64, 512, 512, generator=g, device=dev)).contiguous()
+clq = rnd(2, 77, 3 * 1280)
 flush = torch.empty(64 << 20, dtype=torch.int32, device=dev)
 
 
@@ -56,6 +65,10 @@ def run():
     ops.small_linear(temb, wmod, bias=bmod, act_in=ops.ACT_SILU)                       # Flux AdaLN modulation GEMV batch
     ops.conv_gemm(xv, wv, 128, batch=1, H=1024, W=1024, ksize=3, bias=gv)              # VAE 128-ch conv at 1024^2
     ops.group_norm(xv, batch=1, hw=1024 * 1024, groups=32, eps=1e-6, gamma=gv, beta=bv, silu=True)
+    ops.linear(xq, wq3, 9216, bias=bq3, qk_rope=ops.QkRope(nw2, cosT, sinT, 0, 6144, 128))         # Flux fused QKV + q/k RMSNorm + RoPE epilogue
+    ops.linear(xq, wq3, 9216, bias=bq3)                                                              # the same projection, plain epilogue
+    ops.text_attention(t5q[..., :4096], t5q[..., 4096:8192], t5q[..., 8192:], heads=64, scale=1.0, bias=t5b)     # T5-XXL self-attention, 512 tokens
+    ops.text_attention(clq[..., :1280], clq[..., 1280:2560], clq[..., 2560:], heads=20, scale=0.125, causal=True)  # OpenCLIP bigG, 77 tokens
 
 
 for _ in range(2):
