@@ -76,10 +76,12 @@ def t5_encoder_params(cfg):
 def random_state_dict(spec, seed=0, dtype=torch.bfloat16, device="cpu"):
     """Random text-encoder weights (tests / benchmarks: there are no checkpoints offline): N(0, 1/fan_in) matrices, N(0, 0.02)
     biases, norm weights around 1, unit-scale embeddings.  Deterministic in (spec, seed) on a CPU generator."""
-    g = torch.Generator().manual_seed(seed)
+    device = torch.device(device)
+    on_gpu = device.type == "cuda"  # a CUDA device draws from its own Philox stream (other values, same distributions): seconds for T5-XXL
+    g = torch.Generator(device=device if on_gpu else "cpu").manual_seed(seed)
     sd = {}
     for name, shape in spec.items():
-        r = torch.randn(shape, generator=g)
+        r = torch.randn(shape, generator=g, device=g.device)
         if "norm" in name and name.endswith("weight") and len(shape) == 1:
             t = 1.0 + 0.1 * r
         elif "embedding" in name or name in ("shared.weight",) or "relative_attention_bias" in name:

@@ -55,7 +55,7 @@ def clip_text_forward(sd, cfg, ids, with_projection=False):
         idx = ids.to(torch.int).argmax(-1)
     else:
         idx = (ids.to(torch.int) == cfg["eos_token_id"]).int().argmax(-1)
-    pooled = last[torch.arange(B), idx]
+    pooled = last[torch.arange(B, device=ids.device), idx]
     te = F.linear(pooled, sd["text_projection.weight"]) if with_projection else None
     return dict(last_hidden_state=last, pooler_output=pooled, hidden_states=tuple(hidden), text_embeds=te)
 
@@ -79,7 +79,7 @@ def t5_encoder_forward(sd, cfg, ids):
     B, S = ids.shape
     nh, hd, eps = cfg["num_heads"], cfg["d_kv"], cfg["layer_norm_epsilon"]
     x = sd["shared.weight"][ids]
-    pos = torch.arange(S)
+    pos = torch.arange(S, device=ids.device)
     bucket = t5_bucket(pos[None, :] - pos[:, None], cfg["relative_attention_num_buckets"], cfg["relative_attention_max_distance"])
     bias = sd["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"][bucket].permute(2, 0, 1)[None]
     hidden = [x]

@@ -222,6 +222,111 @@ def test_flux_full_size_parity():
     _free()
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# N3: AutoencoderKL.encode at 1024^2 and the text encoders at their real sizes (CLIP-L, OpenCLIP bigG, T5-XXL v1.1)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_sdxl_vae_encode_full_size_parity():
+    from diffusers_b200.autoencoder_kl import AutoencoderKL
+    from oracle import vae as ovae
+    _no_tf32()
+    dt = torch.bfloat16
+    cfg = dict(specs.SDXL_VAE_CONFIG)
+    sd16 = specs.random_state_dict(specs.vae_params(cfg), seed=0, dtype=dt, device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = (torch.randn(1, 3, 1024, 1024, generator=g, device=DEV) * 0.5).clamp(-1, 1).to(dt)
+    ours = AutoencoderKL(cfg, sd16, dtype=dt, device=DEV)
+    y = ours.encode(x).latent_dist.parameters.float()
+    del ours
+    _free()
+    with torch.no_grad():
+        sd32 = {k: v.float() for k, v in sd16.items()}
+        truth = ovae.vae_encode(sd32, cfg, x.float())
+        if ref_env.available():
+            m = _ref_module("AutoencoderKL", cfg, sd32, torch.float32)
+            r32 = m.encode(x.float()).latent_dist.parameters
+            d = float((r32 - truth).abs().max())
+            print(f"\n[full-size parity] sdxl_vae_encode: oracle fp32 vs unmodified reference fp32: max |diff| {d:.3g} (absmax {float(truth.abs().max()):.3g})")
+            assert d <= 1e-3 * float(truth.abs().max()) + 1e-4
+            m = m.to(dt)
+            r16 = m.encode(x).latent_dist.parameters
+            del m
+        else:
+            r16 = ovae.vae_encode(sd16, cfg, x)
+        del sd32
+    st = _stats("sdxl_vae_encode_1024_bf16", y, truth, r16)
+    _criterion(st, eps_mean=1e-4 * st["absmax_truth"], eps_max=2e-3 * st["absmax_truth"])
+    _free()
+
+
+@pytest.mark.parametrize("name", ["clip_l", "openclip_bigg", "t5_xxl"])
+def test_text_encoder_full_size_parity(name):
+    """The real shapes against transformers itself run live on the box: fp32 (== the oracle: pins oracle/text.py at full size) and its
+    own bf16 CUDA-eager run as the yardstick."""
+    import transformers
+    from diffusers_b200 import text_encoders as T
+    from oracle import text as otext
+    _no_tf32()
+    dt = torch.bfloat16
+    g = torch.Generator(device=DEV).manual_seed(1)
+    if name == "t5_xxl":
+        cfg, spec, cls, hf_cls, hf_cfg = dict(T.T5_XXL_CONFIG), T.t5_encoder_params(T.T5_XXL_CONFIG), T.T5EncoderModel, transformers.T5EncoderModel, transformers.T5Config
+        ids = torch.randint(3, cfg["vocab_size"], (1, 512), generator=g, device=DEV)
+    else:
+        base = T.CLIP_L_CONFIG if name == "clip_l" else T.CLIP_BIGG_CONFIG
+        proj = name != "clip_l"
+        cfg, spec = dict(base), T.clip_text_params(base, proj)
+        cls, hf_cls, hf_cfg = (T.CLIPTextModelWithProjection, transformers.CLIPTextModelWithProjection, transformers.CLIPTextConfig) if proj else \
+            (T.CLIPTextModel, transformers.CLIPTextModel, transformers.CLIPTextConfig)
+        ids = torch.randint(3, cfg["vocab_size"] - 1, (2, 77), generator=g, device=DEV)
+        ids[0, 20], ids[1, 41] = cfg["vocab_size"] - 1, cfg["vocab_size"] - 1  # EOS = the largest id (legacy argmax pooling)
+    sd16 = T.random_state_dict(spec, seed=5, dtype=dt, device=DEV)
+    ours = cls(cfg, sd16, dtype=dt, device=DEV)
+    o = ours(ids, output_hidden_states=True)
+    y_last, y_pen = o.last_hidden_state.float(), o.hidden_states[-2].float()
+    y_pool = o[0].float() if name == "openclip_bigg" else (o.pooler_output.float() if name == "clip_l" else None)
+    del ours, o
+    _free()
+
+    def hf(dtype):
+        with torch.device("meta"):
+            m = hf_cls(hf_cfg(**cfg))
+        full = {k: v.to(dtype) for k, v in sd16.items()}
+        if name == "t5_xxl":
+            full["encoder.embed_tokens.weight"] = full["shared.weight"]
+        missing, unexpected = m.load_state_dict(full, strict=False, assign=True)
+        assert not unexpected and all("position_ids" in k for k in missing), (missing[:3], unexpected[:3])
+        for n_, b_ in list(m.named_buffers()):  # position_ids (CLIP) stay on meta after assign: rebuild them
+            if b_.is_meta:
+                mod = m.get_submodule(n_.rsplit(".", 1)[0])
+                mod.register_buffer(n_.rsplit(".", 1)[1], torch.arange(cfg["max_position_embeddings"], device=DEV).expand((1, -1)), persistent=False)
+        return m.eval()
+
+    with torch.no_grad():
+        m = hf(dt)
+        r = m(ids, output_hidden_states=True)
+        r16 = dict(last=r.last_hidden_state, pen=r.hidden_states[-2], pool=(r[0] if name == "openclip_bigg" else (r.pooler_output if name == "clip_l" else None)))
+        del m, r
+        _free()
+        sd32 = {k: v.float() for k, v in sd16.items()}
+        tr = otext.t5_encoder_forward(sd32, cfg, ids) if name == "t5_xxl" else otext.clip_text_forward(sd32, cfg, ids, with_projection=name == "openclip_bigg")
+        m = hf(torch.float32)
+        r = m(ids, output_hidden_states=True)
+        d = float((r.last_hidden_state - tr["last_hidden_state"]).abs().max())
+        scale = float(tr["last_hidden_state"].abs().max())
+        print(f"\n[full-size parity] {name}: oracle fp32 vs transformers {transformers.__version__} fp32: max |diff| {d:.3g} (absmax {scale:.3g})")
+        assert d <= 1e-3 * scale + 1e-4
+        del m, r, sd32
+    st = _stats(f"{name}_last_hidden_state_bf16", y_last, tr["last_hidden_state"], r16["last"])
+    _criterion(st, eps_mean=1e-4 * st["absmax_truth"], eps_max=2e-3 * st["absmax_truth"])
+    st = _stats(f"{name}_penultimate_bf16", y_pen, tr["hidden_states"][-2], r16["pen"])
+    _criterion(st, eps_mean=1e-4 * st["absmax_truth"], eps_max=2e-3 * st["absmax_truth"])
+    if y_pool is not None:
+        truth_pool = tr["text_embeds"] if name == "openclip_bigg" else tr["pooler_output"]
+        st = _stats(f"{name}_pooled_bf16", y_pool, truth_pool, r16["pool"])
+        _criterion(st, eps_mean=1e-4 * st["absmax_truth"], eps_max=2e-3 * st["absmax_truth"])
+    _free()
+
+
 def test_zz_dump_full_size_parity_record():
     """Writes what the cases above measured to gpurun_out/ (scratch that travels back from the GPU box)."""
     import json
