@@ -90,6 +90,9 @@ def random_state_dict(spec, seed=0, dtype=torch.bfloat16, device="cpu"):
             t = 0.02 * r
         else:
             t = r * (1.0 / math.sqrt(shape[1]))
+            if name.endswith("SelfAttention.q.weight"):
+                t = t * 0.125  # T5 does not scale q.k: its own init draws q with std (d_model * d_kv)^-0.5 (modeling_t5.py _init_weights);
+                               # unit-variance queries would saturate every softmax and make the network chaotic in any 16-bit dtype
         sd[name] = t.to(dtype=dtype, device=device)
     return sd
 
