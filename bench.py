@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark (BASELINE.json): images/sec @ SDXL 1024^2 50-step & latents/sec @ Flux 1024^2 28-step, 1/2/4/8 B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload all|sdxl|flux|vae]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload all|sdxl|flux|vae|encoders]
 
 ONE JSON line (rank 0).  Top level = BASELINE config 1: SDXL UNet 1024^2 bf16, batch 1 per GPU (CFG -> 2 samples per
 forward), 50 Euler steps + VAE decode to a (1,3,1024,1024) tensor; a "step" is one whole image.
@@ -718,6 +718,65 @@ def vae_section(cx):
     return sec
 
 
+def encoders_section(cx):
+    """SURVEY.md N3, either side of the loop: prompts/s of the text encoders at their real sizes (SDXL: CLIP-L + OpenCLIP-bigG on 77
+    tokens; Flux: CLIP-L + T5-XXL on 77 / 512 tokens; token ids in from pinned host memory, embeddings back to the host) and
+    images/s of AutoencoderKL.encode at 1024^2.  Random-init weights of those architectures (no checkpoints offline)."""
+    from diffusers_b200 import text_encoders as T
+    from diffusers_b200.autoencoder_kl import AutoencoderKL
+    args, dev, dt = cx.args, cx.dev, cx.dt
+    if cx.world != 1:
+        return "single-GPU section (run without torchrun)"
+    out = {}
+    mk = lambda cls, cfg, spec, seed: cls(cfg, T.random_state_dict(spec, seed=seed, dtype=dt, device=dev), dtype=dt, device=dev)  # noqa: E731
+    te1 = mk(T.CLIPTextModel, T.CLIP_L_CONFIG, T.clip_text_params(T.CLIP_L_CONFIG, False), 1)
+    te2 = mk(T.CLIPTextModelWithProjection, T.CLIP_BIGG_CONFIG, T.clip_text_params(T.CLIP_BIGG_CONFIG, True), 2)
+    g = torch.Generator().manual_seed(3)
+    ids77 = torch.randint(3, 49000, (2, 77), generator=g).pin_memory()  # prompt + negative prompt
+    n = max(3, args.steps)
+
+    def sdxl_encode(i):
+        ids = ids77.to(dev, non_blocking=True)
+        a, b = te1(ids, output_hidden_states=True), te2(ids, output_hidden_states=True)
+        return to_host(torch.cat([a.hidden_states[-2], b.hidden_states[-2]], -1)), to_host(b[0])
+
+    sdxl_encode(0)
+    ms, launches = cx.timed(n, sdxl_encode)
+    out["sdxl_text_encode"] = dict(value=round(n / (ms * 1e-3), 2), unit="prompt pairs/s", ms=round(ms / n, 3), gpu_launches=launches // n,
+                                   models="CLIPTextModel (CLIP-L, 123 M) + CLIPTextModelWithProjection (OpenCLIP bigG, 695 M), 2 x 77 tokens",
+                                   h2d_bytes_per_step=ids77.numel() * 8, d2h_bytes_per_step=2 * 77 * 2048 * 2 + 2 * 1280 * 2)
+    del te2
+    t5 = mk(T.T5EncoderModel, T.T5_XXL_CONFIG, T.t5_encoder_params(T.T5_XXL_CONFIG), 3)
+    ids512 = torch.randint(3, 32000, (1, 512), generator=g).pin_memory()
+
+    def flux_encode(i):
+        pooled = te1(ids77[:1].to(dev, non_blocking=True), output_hidden_states=False).pooler_output
+        pe = t5(ids512.to(dev, non_blocking=True), output_hidden_states=False)[0]
+        return to_host(pe), to_host(pooled)
+
+    flux_encode(0)
+    ms, launches = cx.timed(n, flux_encode)
+    out["flux_text_encode"] = dict(value=round(n / (ms * 1e-3), 2), unit="prompts/s", ms=round(ms / n, 3), gpu_launches=launches // n,
+                                   models="CLIPTextModel (CLIP-L) on 77 tokens + T5EncoderModel (T5-XXL v1.1, 4.76 B) on 512 tokens",
+                                   h2d_bytes_per_step=(77 + 512) * 8, d2h_bytes_per_step=512 * 4096 * 2 + 768 * 2)
+    del te1, t5
+    torch.cuda.empty_cache()
+    vae = AutoencoderKL.random_init(seed=0, dtype=dt, device=dev, encoder=True)
+    xh = (torch.randn(1, 3, 1024, 1024, generator=g) * 0.5).clamp(-1, 1).to(dt).pin_memory()
+
+    def enc(i):
+        return to_host(vae.encode(xh.to(dev, non_blocking=True)).latent_dist.parameters)
+
+    enc(0)
+    ms, launches = cx.timed(n, enc)
+    out["vae_encode"] = dict(value=round(n / (ms * 1e-3), 2), unit="images/s", ms=round(ms / n, 3), gpu_launches=launches // n,
+                             workload="AutoencoderKL.encode 1024^2 -> moments (SDXL VAE encoder, 34 M params)", h2d_bytes_per_step=3 * 1024 * 1024 * 2,
+                             d2h_bytes_per_step=8 * 128 * 128 * 2)
+    del vae
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args, rank, world, local_rank):
     cx = Ctx(args, rank, world, local_rank)
     wl = args.workload
@@ -725,6 +784,8 @@ def run_b200(args, rank, world, local_rank):
         line = flux_section(cx, standalone=True)
     elif wl == "vae":
         line = vae_section(cx) if rank == 0 else None
+    elif wl == "encoders":
+        line = encoders_section(cx) if rank == 0 else None
     else:
         line = sdxl_section(cx)
         if wl == "all":
@@ -739,6 +800,10 @@ def run_b200(args, rank, world, local_rank):
                     line["vae"] = vae_section(cx)
                 except Exception as e:  # noqa: BLE001
                     line["vae"] = f"failed: {type(e).__name__}: {str(e)[:200]}"
+                try:
+                    line["encoders"] = encoders_section(cx)
+                except Exception as e:  # noqa: BLE001
+                    line["encoders"] = f"failed: {type(e).__name__}: {str(e)[:200]}"
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_subprocess(args)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "dtype", "t_step_runs_s", "run_spread") if k in cb}
@@ -792,7 +857,7 @@ def main():
     _JSON_FD = os.dup(1)
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="all", choices=["all", "sdxl", "flux", "vae"])
+    ap.add_argument("--workload", default="all", choices=["all", "sdxl", "flux", "vae", "encoders"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)

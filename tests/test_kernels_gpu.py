@@ -141,3 +141,23 @@ def test_conv_gemm_column_blocks_to_separate_buffers(rows, K, blocks, bcols, hd)
             one = ops.linear(x, w[j * bcols:(j + 1) * bcols], bcols, bias=b[j * bcols:(j + 1) * bcols], qk_rope=rope)
             torch.cuda.synchronize()
             assert torch.equal(v, one), j
+
+
+@pytest.mark.parametrize("Sq,H,D,seg", [(4608, 3, 128, 576), (1152, 2, 64, 288), (2304, 2, 128, 1152)])
+def test_attention_scatters_output_rows_to_segment_buffers(Sq, H, D, seg):
+    """b200_attention_args.o_seg (context parallelism: output row r goes to the buffer of the rank that owns it), here with local
+    buffers and segment sizes that are NOT multiples of the 128-row query tile (8 ranks: 576 rows): every segment equals the
+    matching rows of the plain launch bit for bit, at this rank's head columns of the owners' wider [rows, all heads] buffers."""
+    from diffusers_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = torch.randn(1, Sq, 3 * H * D, generator=g, device="cuda").bfloat16()
+    q, k, v = qkv[:, :, :H * D], qkv[:, :, H * D:2 * H * D], qkv[:, :, 2 * H * D:]
+    plain = ops.attention(q, k, v, heads=H, head_dim=D)
+    nseg = Sq // seg
+    wide = [torch.full((seg, 4 * H * D), 3.0, dtype=torch.bfloat16, device="cuda") for _ in range(nseg)]
+    views = [w[:, H * D:2 * H * D] for w in wide]
+    assert ops.attention(q, k, v, heads=H, head_dim=D, o_seg=views, o_seg_rows=seg) is None
+    torch.cuda.synchronize()
+    for s_, w in enumerate(wide):
+        assert torch.equal(w[:, H * D:2 * H * D], plain[0, s_ * seg:(s_ + 1) * seg]), s_
+        assert float((w[:, :H * D] - 3).abs().max()) == 0 and float((w[:, 2 * H * D:] - 3).abs().max()) == 0
