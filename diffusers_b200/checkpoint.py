@@ -62,9 +62,11 @@ def _safetensors_load(file, wanted=None):
     return out
 
 
-def load_state_dict(path, variant=None, wanted=None):
+def load_state_dict(path, variant=None, wanted=None, safetensors_name=SAFETENSORS_WEIGHTS_NAME, pickle_name=WEIGHTS_NAME):
     """All tensors (or only the names in `wanted`) of one component directory: single safetensors file, sharded
-    safetensors with an index, or the legacy pickle (`weights_only`)."""
+    safetensors with an index, or the legacy pickle (`weights_only`).  transformers components (text encoders) use
+    safetensors_name='model.safetensors', pickle_name='pytorch_model.bin'."""
+    SAFETENSORS_WEIGHTS_NAME, WEIGHTS_NAME = safetensors_name, pickle_name  # noqa: N806  (shadow the module defaults below)
     st = os.path.join(path, add_variant(SAFETENSORS_WEIGHTS_NAME, variant))
     idx = os.path.join(path, add_variant(SAFETENSORS_WEIGHTS_NAME + ".index.json", variant))
     if not os.path.isfile(idx):

@@ -51,9 +51,10 @@ class PipelineOutput:
 
 class StableDiffusionXLPipeline:
     @classmethod
-    def from_pretrained(cls, path, torch_dtype=torch.bfloat16, device="cuda", variant=None):
-        """A reference `StableDiffusionXLPipeline.save_pretrained` directory -> this pipeline (unet/, vae/, scheduler/;
-        the text encoders / tokenizers are not on the path: call with prompt_embeds).  checkpoint.py, SURVEY.md 8f N1."""
+    def from_pretrained(cls, path, torch_dtype=torch.bfloat16, device="cuda", variant=None, text_encoders=False):
+        """A reference `StableDiffusionXLPipeline.save_pretrained` directory -> this pipeline (unet/, vae/, scheduler/; with
+        text_encoders=True also text_encoder/ and text_encoder_2/ for `encode_prompt` from token ids - the tokenizers stay with
+        transformers; otherwise call with prompt_embeds).  checkpoint.py, SURVEY.md 8f N1."""
         from . import checkpoint
         from .autoencoder_kl import AutoencoderKL
         from .schedulers import DDIMScheduler, DPMSolverMultistepScheduler, EulerAncestralDiscreteScheduler, EulerDiscreteScheduler
@@ -62,7 +63,13 @@ class StableDiffusionXLPipeline:
         c = checkpoint.load_pipeline_components(path, "StableDiffusionXLPipeline",
                                                 dict(unet=UNet2DConditionModel, vae=AutoencoderKL, scheduler=steppers),
                                                 torch_dtype=torch_dtype, device=device, variant=variant)
-        return cls(c["vae"], c["unet"], c["scheduler"])
+        te = {}
+        if text_encoders:
+            from .text_encoders import CLIPTextModel, CLIPTextModelWithProjection
+            te = dict(text_encoder=CLIPTextModel.from_pretrained(path, subfolder="text_encoder", variant=variant, torch_dtype=torch_dtype, device=device),
+                      text_encoder_2=CLIPTextModelWithProjection.from_pretrained(path, subfolder="text_encoder_2", variant=variant, torch_dtype=torch_dtype,
+                                                                                 device=device))
+        return cls(c["vae"], c["unet"], c["scheduler"], **te)
 
     def __init__(self, vae, unet, scheduler, text_encoder=None, text_encoder_2=None, force_zeros_for_empty_prompt=True):
         self.vae, self.unet, self.scheduler = vae, unet, scheduler
@@ -247,9 +254,10 @@ def calculate_shift(image_seq_len, base_seq_len=256, max_seq_len=4096, base_shif
 
 class FluxPipeline:
     @classmethod
-    def from_pretrained(cls, path, torch_dtype=torch.bfloat16, device="cuda", variant=None):
+    def from_pretrained(cls, path, torch_dtype=torch.bfloat16, device="cuda", variant=None, text_encoders=False):
         """A reference `FluxPipeline.save_pretrained` directory -> this pipeline (transformer/, vae/ config for the latent
-        geometry, scheduler/); output_type='latent' only, prompt embeddings in."""
+        geometry, scheduler/; with text_encoders=True also text_encoder/ (CLIP-L) and text_encoder_2/ (T5) for `encode_prompt` from
+        token ids); output_type='latent' only."""
         from . import checkpoint
         from .config import FrozenConfig
         from .schedulers import FlowMatchEulerDiscreteScheduler
@@ -259,7 +267,12 @@ class FluxPipeline:
                                                 torch_dtype=torch_dtype, device=device, variant=variant)
         vae_cfg = checkpoint.public_config(checkpoint.load_config(os.path.join(path, "vae")))
         vae = type("VaeGeometry", (), dict(config=FrozenConfig(vae_cfg)))()
-        return cls(c["scheduler"], vae, c["transformer"])
+        te = {}
+        if text_encoders:
+            from .text_encoders import CLIPTextModel, T5EncoderModel
+            te = dict(text_encoder=CLIPTextModel.from_pretrained(path, subfolder="text_encoder", variant=variant, torch_dtype=torch_dtype, device=device),
+                      text_encoder_2=T5EncoderModel.from_pretrained(path, subfolder="text_encoder_2", variant=variant, torch_dtype=torch_dtype, device=device))
+        return cls(c["scheduler"], vae, c["transformer"], **te)
 
     def __init__(self, scheduler, vae, transformer, text_encoder=None, text_encoder_2=None):
         self.scheduler, self.vae, self.transformer = scheduler, vae, transformer

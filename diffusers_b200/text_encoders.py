@@ -135,6 +135,25 @@ class _Base(torch.nn.Module):
     def device(self):
         return self._buffers["w0"].device
 
+    _hf_architectures = ()
+
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, variant=None, torch_dtype=torch.bfloat16, device="cuda"):
+        """A transformers `save_pretrained` directory (config.json with `architectures`, model[.variant].safetensors or its sharded
+        index, or pytorch_model.bin) - e.g. `text_encoder/`, `text_encoder_2/` of an SDXL or Flux checkpoint - -> this shell.
+        Local directories only."""
+        import os
+
+        from . import checkpoint
+        root = os.path.join(path, subfolder) if subfolder else path
+        raw = checkpoint.load_config(root)
+        arch = raw.get("architectures") or []
+        if arch and not set(arch) & set(cls._hf_architectures):
+            raise ValueError(f"{root} holds a {arch}, not one of {cls._hf_architectures}")
+        cfg = {k: raw[k] for k in cls._default_config if k in raw}
+        sd = checkpoint.load_state_dict(root, variant=variant, safetensors_name="model.safetensors", pickle_name="pytorch_model.bin")
+        return cls(cfg, sd, dtype=torch_dtype, device=device)
+
     @staticmethod
     def _check(spec, sd):
         for k, shp in spec.items():
@@ -148,6 +167,8 @@ class CLIPTextModel(_Base):
     """transformers CLIPTextModel (models/clip/modeling_clip.py: CLIPTextTransformer) - and, with `with_projection=True`,
     CLIPTextModelWithProjection."""
     with_projection = False
+    _hf_architectures = ("CLIPTextModel",)
+    _default_config = CLIP_L_CONFIG
 
     def __init__(self, config, state_dict, dtype=torch.bfloat16, device="cuda"):
         super().__init__()
@@ -225,6 +246,7 @@ class CLIPTextModel(_Base):
 
 class CLIPTextModelWithProjection(CLIPTextModel):
     with_projection = True
+    _hf_architectures = ("CLIPTextModelWithProjection",)
 
 
 def t5_relative_position_bucket(relative_position, num_buckets=32, max_distance=128):
@@ -243,6 +265,8 @@ def t5_relative_position_bucket(relative_position, num_buckets=32, max_distance=
 class T5EncoderModel(_Base):
     """transformers T5EncoderModel (models/t5/modeling_t5.py: T5Stack of T5Block(T5LayerSelfAttention, T5LayerFF)), gated-GELU
     feed-forward (T5 v1.1 / XXL).  Flux calls it without an attention mask."""
+    _hf_architectures = ("T5EncoderModel", "T5ForConditionalGeneration", "T5Model")
+    _default_config = T5_XXL_CONFIG
 
     def __init__(self, config, state_dict, dtype=torch.bfloat16, device="cuda"):
         super().__init__()

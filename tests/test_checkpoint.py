@@ -268,3 +268,40 @@ def test_unmodified_reference_loads_what_the_shells_save(tmp_path):
         assert not info["missing_keys"] and not info["unexpected_keys"] and not info["mismatched_keys"], info
         rsd = ref.state_dict()
         assert all(torch.equal(rsd[k], sd[k]) for k in sd)
+
+
+@pytest.mark.parametrize("kind", ["clip", "clip_proj", "t5"])
+def test_text_encoder_shells_load_transformers_checkpoints(tmp_path, kind):
+    """N1 x N3: `text_encoder/` directories written by the real transformers `save_pretrained` (config.json with `architectures`,
+    model.safetensors) load into the shells: same config, same tensors (checked on the unpacked embedding / norm buffers and,
+    through the packing inverse, on a projection weight).  Construction is host-side; no GPU involved."""
+    import transformers
+    from diffusers_b200 import packing
+    from diffusers_b200 import text_encoders as T
+    torch.manual_seed(0)
+    if kind == "t5":
+        hf = transformers.T5EncoderModel(transformers.T5Config(vocab_size=300, d_model=128, d_kv=64, d_ff=256, num_layers=2, num_heads=2,
+                                                               feed_forward_proj="gated-gelu"))
+        cls = T.T5EncoderModel
+    else:
+        cfg = transformers.CLIPTextConfig(vocab_size=300, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                                          hidden_act="quick_gelu" if kind == "clip" else "gelu", projection_dim=64)
+        hf = (transformers.CLIPTextModel if kind == "clip" else transformers.CLIPTextModelWithProjection)(cfg)
+        cls = T.CLIPTextModel if kind == "clip" else T.CLIPTextModelWithProjection
+    d = tmp_path / "text_encoder"
+    hf.save_pretrained(d, safe_serialization=True)
+    m = cls.from_pretrained(str(tmp_path), subfolder="text_encoder", torch_dtype=torch.bfloat16, device="cpu")
+    sd = hf.state_dict()
+    if kind == "t5":
+        assert m.config.d_model == 128 and m.config.num_layers == 2 and m.config.feed_forward_proj == "gated-gelu"
+        assert torch.equal(m.W(m.tok), sd["shared.weight"].bfloat16())
+        assert torch.equal(m.W(m.blocks[1]["n2"]), sd["encoder.block.1.layer.1.layer_norm.weight"].bfloat16())
+        assert torch.equal(packing.unpack_linear_weight(m.W(m.blocks[0]["o"]), 128), sd["encoder.block.0.layer.0.SelfAttention.o.weight"].bfloat16())
+    else:
+        assert m.config.hidden_size == 128 and m.config.hidden_act == ("quick_gelu" if kind == "clip" else "gelu") and m.config.eos_token_id == hf.config.eos_token_id
+        assert torch.equal(m.W(m.tok), sd["text_model.embeddings.token_embedding.weight"].bfloat16())
+        assert torch.equal(packing.unpack_linear_weight(m.W(m.layers[1]["f2w"]), 256), sd["text_model.encoder.layers.1.mlp.fc2.weight"].bfloat16())
+        if kind == "clip_proj":
+            assert torch.equal(m.W(m.proj), sd["text_projection.weight"].bfloat16())
+    with pytest.raises(ValueError):
+        (T.T5EncoderModel if kind != "t5" else T.CLIPTextModel).from_pretrained(str(tmp_path), subfolder="text_encoder", device="cpu")
