@@ -305,3 +305,33 @@ def test_text_encoder_shells_load_transformers_checkpoints(tmp_path, kind):
             assert torch.equal(m.W(m.proj), sd["text_projection.weight"].bfloat16())
     with pytest.raises(ValueError):
         (T.T5EncoderModel if kind != "t5" else T.CLIPTextModel).from_pretrained(str(tmp_path), subfolder="text_encoder", device="cpu")
+
+
+def test_whole_vae_checkpoint_round_trip(tmp_path):
+    """With the encoder half loaded (N3) the AutoencoderKL shell holds the reference's complete state_dict: reference_state_dict()
+    is the exact inverse of the packing for encoder.* / quant_conv.* too, save_pretrained writes a directory that from_pretrained
+    reads back WITH the encoder - and that the unmodified reference loads without missing / unexpected keys."""
+    cfg = dict(specs.SDXL_VAE_CONFIG)
+    cfg.update(MICRO_VAE)
+    spec = specs.vae_params(cfg)
+    sd = specs.random_state_dict(spec, seed=13, dtype=torch.bfloat16)
+    m = AutoencoderKL(cfg, sd, dtype=torch.bfloat16, device="cpu")
+    assert m.enc is not None
+    back = m.reference_state_dict()
+    assert sorted(back) == sorted(spec)
+    for k, v in sd.items():
+        assert tuple(back[k].shape) == tuple(spec[k]) and torch.equal(back[k], v), k
+    m.save_pretrained(str(tmp_path / "vae"))
+    again = AutoencoderKL.from_pretrained(str(tmp_path / "vae"), device="cpu")
+    assert again.enc is not None
+    _same_buffers(m, again)
+    # a checkpoint that lacks part of the encoder is an error, not a silent decoder-only model
+    with pytest.raises(ValueError):
+        AutoencoderKL(cfg, {k: v for k, v in sd.items() if k != "encoder.conv_out.bias"}, device="cpu")
+    if os.path.isdir("/root/reference/src"):
+        from oracle import ref_shim
+        d = ref_shim.import_reference()
+        ref, info = d.AutoencoderKL.from_pretrained(str(tmp_path / "vae"), torch_dtype=torch.bfloat16, output_loading_info=True)
+        assert not info["missing_keys"] and not info["unexpected_keys"] and not info["mismatched_keys"], info
+        rsd = ref.state_dict()
+        assert all(torch.equal(rsd[k], sd[k]) for k in sd)
