@@ -64,3 +64,54 @@ def test_t5_bucket_properties():
     assert b[rel == 0].item() == 0 and b[rel == 3].item() == 16 + 3 and b[rel == -3].item() == 3       # exact buckets near zero, sign in the upper half
     assert b[rel == 500].item() == 31 and b[rel == -500].item() == 15                                    # saturate beyond max_distance
     assert bool((b[rel > 0][1:] >= b[rel > 0][:-1]).all())                                                # monotone in the distance
+
+
+def test_pipelines_encode_prompt_composition_on_the_host(golden):
+    """encode_prompt of both pipelines with stand-in encoders that answer from the ORACLE (same output objects as the CUDA shells):
+    checks the composition the reference prescribes (pipeline_stable_diffusion_xl.py:283-470, pipeline_flux.py:217-387) against the
+    recorded transformers outputs - penultimate hidden states concatenated, pooled = [0] of the projection encoder, zeros for an
+    empty negative prompt, T5 states + CLIP pooler for Flux."""
+    from diffusers_b200.pipelines import FluxPipeline, StableDiffusionXLPipeline
+    from oracle import text as otext
+    fx = golden("text")
+
+    class Stand:
+        def __init__(self, name):
+            f = fx[name]
+            self.kind, self.cfg = f["kind"], f["cfg"]
+            spec = T.t5_encoder_params(self.cfg) if self.kind == "t5" else T.clip_text_params(self.cfg, self.kind == "clip_proj")
+            self.sd = {k: v.float() for k, v in T.random_state_dict(spec, f["seed"]).items()}
+
+        def __call__(self, ids, output_hidden_states=False):
+            if self.kind == "t5":
+                o = otext.t5_encoder_forward(self.sd, self.cfg, ids)
+                return T._Output(last_hidden_state=o["last_hidden_state"], hidden_states=o["hidden_states"] if output_hidden_states else None)
+            o = otext.clip_text_forward(self.sd, self.cfg, ids, with_projection=self.kind == "clip_proj")
+            hs = o["hidden_states"] if output_hidden_states else None
+            if self.kind == "clip_proj":
+                return T._Output(text_embeds=o["text_embeds"], last_hidden_state=o["last_hidden_state"], hidden_states=hs)
+            return T._Output(last_hidden_state=o["last_hidden_state"], pooler_output=o["pooler_output"], hidden_states=hs)
+
+    te1, te2, t5 = Stand("clip_l_tiny"), Stand("clip_g_tiny"), Stand("t5_tiny")
+    unet = type("U", (), dict(config=type("C", (), dict(sample_size=16))(), device=torch.device("cpu"), dtype=torch.float32))()
+    pipe = StableDiffusionXLPipeline(None, unet, None, text_encoder=te1, text_encoder_2=te2)
+    ids1, ids2 = fx["clip_l_tiny"]["ids"][:2], fx["clip_g_tiny"]["ids"][:2]
+    pe, npe, pooled, npooled = pipe.encode_prompt(ids1, ids2)
+    assert tuple(pe.shape) == (2, 77, 128 + 192) and tuple(pooled.shape) == (2, 64)
+    assert float(npe.abs().max()) == 0 and float(npooled.abs().max()) == 0 and npe.shape == pe.shape
+    close = lambda a, b: float((a - b).abs().max()) <= 2e-5 * max(1.0, float(b.abs().max()))  # noqa: E731
+    assert close(pe[..., :128], fx["clip_l_tiny"]["ref32"]["penultimate"]) and close(pe[..., 128:], fx["clip_g_tiny"]["ref32"]["penultimate"][:2])
+    assert close(pooled, fx["clip_g_tiny"]["ref32"]["text_embeds"][:2])
+    pe2, npe2, _, npool2 = pipe.encode_prompt(ids1, ids2, negative_input_ids=ids1.flip(0), negative_input_ids_2=ids2.flip(0))
+    assert torch.equal(pe2, pe) and close(npe2, pe.flip(0)) and close(npool2, pooled.flip(0))
+    assert pipe.encode_prompt(ids1, ids2, do_classifier_free_guidance=False)[1] is None
+    pipe.force_zeros_for_empty_prompt = False
+    with pytest.raises(ValueError):
+        pipe.encode_prompt(ids1, ids2)
+    with pytest.raises(ValueError):
+        StableDiffusionXLPipeline(None, unet, None).encode_prompt(ids1, ids2)
+    tr = type("Tr", (), dict(device=torch.device("cpu"), dtype=torch.float32))()
+    vae = type("V", (), dict(config=type("C", (), dict(block_out_channels=(1, 1, 1, 1)))()))()
+    fpe, fpool, tids = FluxPipeline(None, vae, tr, text_encoder=te1, text_encoder_2=t5).encode_prompt(ids1, fx["t5_tiny"]["ids"])
+    assert close(fpe, fx["t5_tiny"]["ref32"]["last_hidden_state"]) and close(fpool, fx["clip_l_tiny"]["ref32"]["pooler_output"])
+    assert tuple(tids.shape) == (96, 3) and float(tids.abs().max()) == 0
