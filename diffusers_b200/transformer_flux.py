@@ -350,6 +350,11 @@ class FluxTransformer2DModel(torch.nn.Module, FromPretrainedMixin):
             pg = PeerGroup(nbytes, cp["group"])
             bufs = dict(pg=pg, J=pg.carve(self._dtype, (plan.L, 3 * plan.Dl)), A=pg.carve(self._dtype, (plan.Ll, plan.D)),
                         O=pg.carve(self._dtype, (S, out_ch)))
+            if len(cp["plans"]) >= 4:
+                # a serving process that keeps changing resolution must not accumulate peer mappings (cudaMalloc + IPC handles): drop the
+                # oldest shape.  Every rank sees the same sequence of shapes, so every rank closes the same buffers (close() is collective)
+                old_key = next(iter(cp["plans"]))
+                cp["plans"].pop(old_key)[1]["pg"].close()
             cp["plans"][key] = (plan, bufs)
         return cp["plans"][key]
 
