@@ -99,6 +99,93 @@ def _worker(rank, world, port, q_out):
         dist.destroy_process_group()
 
 
+def _enable_worker(rank, world, port, q_out):
+    """FluxTransformer2DModel.enable_parallelism on the host (gloo, CPU buffers): the QKV weights / biases of every block end up in
+    destination blocks in send order, the API refuses what is not built, and the permuted model no longer exports a checkpoint."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from diffusers_b200 import packing, specs
+        from diffusers_b200.transformer_flux import FluxTransformer2DModel
+        cfg = dict(patch_size=1, in_channels=16, num_layers=1, num_single_layers=1, attention_head_dim=64, num_attention_heads=4,
+                   joint_attention_dim=32, pooled_projection_dim=16, guidance_embeds=True, axes_dims_rope=(8, 28, 28))
+        sd = specs.random_state_dict(specs.flux_params(dict(specs.FLUX_DEV_CONFIG, **cfg)), seed=3)
+        m = FluxTransformer2DModel(cfg, sd, device="cpu")
+        for bad in (dict(ulysses_degree=4), dict(ulysses_degree=1)):
+            try:
+                m.enable_parallelism(config=ContextParallelConfig(**bad))
+                raise AssertionError("a degree that differs from the group size must be refused")
+            except ValueError:
+                pass
+        try:
+            m.enable_parallelism(config=ContextParallelConfig(ulysses_degree=2), cp_plan={"": {}})
+            raise AssertionError("custom cp_plan must be refused")
+        except NotImplementedError:
+            pass
+        m.enable_parallelism(config=ContextParallelConfig(ulysses_degree=world))
+        plan = UlyssesPlan(world, rank, 16, 16, 4, 64)
+        D, Dl = plan.D, plan.Dl
+        a = "transformer_blocks.0.attn"
+        full_w = torch.cat([sd[a + ".to_q.weight"], sd[a + ".to_k.weight"], sd[a + ".to_v.weight"]], 0)
+        full_b = torch.cat([sd[a + ".to_q.bias"], sd[a + ".to_k.bias"], sd[a + ".to_v.bias"]], 0)
+        w = packing.unpack_linear_weight(m.W(m.double[0]["qkv"]["w"]).cpu(), D)
+        b = m.W(m.double[0]["qkv"]["b"]).cpu()
+        for i, d in enumerate(plan.send_order()):
+            for part in range(3):  # block i = [q | k | v] rows of the heads rank d owns
+                rows = slice(part * D + d * Dl, part * D + (d + 1) * Dl)
+                blk = slice(i * 3 * Dl + part * Dl, i * 3 * Dl + (part + 1) * Dl)
+                assert torch.equal(w[blk], full_w[rows]) and torch.equal(b[blk], full_b[rows]), (i, d, part)
+        # the text-stream projection and the single blocks are permuted the same way; everything else is untouched
+        aw = packing.unpack_linear_weight(m.W(m.double[0]["aqkv"]["w"]).cpu(), D)
+        assert torch.equal(aw[:Dl], sd[a + ".add_q_proj.weight"][plan.send_order()[0] * Dl:(plan.send_order()[0] + 1) * Dl])
+        assert torch.equal(packing.unpack_linear_weight(m.W(m.double[0]["out"]["w"]).cpu(), D), sd[a + ".to_out.0.weight"])
+        for must_fail, exc in ((lambda: m.reference_state_dict(), RuntimeError),
+                               (lambda: m.enable_parallelism(config=ContextParallelConfig(ulysses_degree=world)), RuntimeError)):
+            try:
+                must_fail()
+                raise AssertionError("expected a refusal")
+            except exc:
+                pass
+        q_out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q_out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_two(worker):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    return sorted(res)
+
+
+def test_enable_parallelism_host_side_two_rank_gloo():
+    assert _run_two(_enable_worker) == [(0, "ok"), (1, "ok")]
+
+
+def test_enable_parallelism_needs_an_initialized_process_group():
+    from diffusers_b200 import specs
+    from diffusers_b200.transformer_flux import FluxTransformer2DModel
+    cfg = dict(patch_size=1, in_channels=16, num_layers=1, num_single_layers=1, attention_head_dim=64, num_attention_heads=2,
+               joint_attention_dim=32, pooled_projection_dim=16, guidance_embeds=True, axes_dims_rope=(8, 28, 28))
+    m = FluxTransformer2DModel(cfg, specs.random_state_dict(specs.flux_params(dict(specs.FLUX_DEV_CONFIG, **cfg)), seed=3), device="cpu")
+    with pytest.raises(RuntimeError):
+        m.enable_parallelism(config=ContextParallelConfig(ulysses_degree=2))
+    with pytest.raises(NotImplementedError):
+        m.enable_parallelism(config=object())
+
+
 def test_two_rank_gloo_ulysses_data_movement_equals_joint_attention():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
