@@ -154,7 +154,9 @@ class StableDiffusionXLPipeline:
     def __call__(self, prompt_embeds, negative_prompt_embeds=None, pooled_prompt_embeds=None,
                  negative_pooled_prompt_embeds=None, height=None, width=None, num_inference_steps=50,
                  guidance_scale=5.0, generator=None, latents=None, output_type="pt", original_size=None,
-                 crops_coords_top_left=(0, 0), target_size=None, return_dict=True, fused=True):
+                 crops_coords_top_left=(0, 0), target_size=None, return_dict=True, fused=True, guidance_rescale=0.0):
+        """guidance_rescale > 0 (`rescale_noise_cfg`, pipeline_stable_diffusion_xl.py:1236-1238) runs the drop-in loop: the fused CFG + Euler
+        kernel has no per-sample reduction."""
         unet, sched = self.unet, self.scheduler
         device = unet.device
         height = height or self.default_sample_size * self.vae_scale_factor
@@ -189,7 +191,8 @@ class StableDiffusionXLPipeline:
         sched.set_begin_index(0)
 
         from .schedulers import EulerDiscreteScheduler
-        if fused and isinstance(sched, EulerDiscreteScheduler):
+        rescale = do_cfg and guidance_rescale > 0.0
+        if fused and isinstance(sched, EulerDiscreteScheduler) and not rescale:
             lat = self._denoise_fused(lat, timesteps, prompt_embeds, added, guidance_scale, do_cfg)
         else:
             # drop-in loop (any scheduler with the reference's scale_model_input / step surface: DDIM, Euler-ancestral,
@@ -203,6 +206,8 @@ class StableDiffusionXLPipeline:
                 if do_cfg:
                     u, c = noise_pred.chunk(2)
                     noise_pred = u + guidance_scale * (c - u)
+                    if rescale:
+                        noise_pred = rescale_noise_cfg(noise_pred, c, guidance_rescale=guidance_rescale)
                 lat = sched.step(noise_pred, t, lat, return_dict=False, **extra)[0]
 
         if output_type == "latent":
@@ -243,6 +248,15 @@ class StableDiffusionXLPipeline:
                                sigma=float(sig[i]), sigma_next=float(sig[i + 1]))
         sched._step_index = n
         return lat
+
+
+def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
+    """pipeline_stable_diffusion_xl.py:84-107 (Lin et al. 2305.08891, section 3.4): bring the per-sample standard deviation of the guided
+    prediction back to the text-conditional one's, then blend by `guidance_rescale`.  Same op sequence as the reference (per-sample
+    std over every non-batch axis, 16-bit tensor arithmetic), so the drop-in loop reproduces its rounding."""
+    dims = list(range(1, noise_pred_text.ndim))
+    factor = noise_pred_text.std(dim=dims, keepdim=True) / noise_cfg.std(dim=dims, keepdim=True)
+    return guidance_rescale * (noise_cfg * factor) + (1 - guidance_rescale) * noise_cfg
 
 
 def calculate_shift(image_seq_len, base_seq_len=256, max_seq_len=4096, base_shift=0.5, max_shift=1.15):
@@ -326,7 +340,11 @@ class FluxPipeline:
 
     @torch.no_grad()
     def __call__(self, prompt_embeds, pooled_prompt_embeds, height=None, width=None, num_inference_steps=28,
-                 guidance_scale=3.5, generator=None, latents=None, output_type="latent", return_dict=True):
+                 guidance_scale=3.5, generator=None, latents=None, output_type="latent", return_dict=True,
+                 negative_prompt_embeds=None, negative_pooled_prompt_embeds=None, true_cfg_scale=1.0):
+        """true_cfg_scale > 1 with negative embeddings = the reference's "true" classifier-free guidance for Flux
+        (pipeline_flux.py:778-780, 911-927): a second transformer call per step under cache_context("uncond") and
+        noise = neg + true_cfg_scale * (cond - neg)."""
         tr, sched = self.transformer, self.scheduler
         device = tr.device
         height = height or self.default_sample_size * self.vae_scale_factor
@@ -336,6 +354,15 @@ class FluxPipeline:
         prompt_embeds = prompt_embeds.to(device)
         pooled_prompt_embeds = pooled_prompt_embeds.to(device)
         text_ids = torch.zeros(prompt_embeds.shape[1], 3).to(device=device, dtype=dtype)
+        do_true_cfg = true_cfg_scale > 1 and negative_prompt_embeds is not None
+        if do_true_cfg:
+            if negative_pooled_prompt_embeds is None:
+                raise ValueError("true CFG needs negative_pooled_prompt_embeds next to negative_prompt_embeds")
+            negative_prompt_embeds = negative_prompt_embeds.to(device)
+            negative_pooled_prompt_embeds = negative_pooled_prompt_embeds.to(device)
+            # all-zero ids of the negative prompt's length: the SAME tensor when the lengths agree, so the transformer's RoPE-table cache holds
+            neg_text_ids = text_ids if negative_prompt_embeds.shape[1] == prompt_embeds.shape[1] else \
+                torch.zeros(negative_prompt_embeds.shape[1], 3).to(device=device, dtype=dtype)
         lat, img_ids = self.prepare_latents(batch, tr.config.in_channels // 4, height, width, dtype, device, generator, latents)
         sigmas = np.linspace(1.0, 1 / num_inference_steps, num_inference_steps)
         c = sched.config
@@ -353,6 +380,12 @@ class FluxPipeline:
                 noise_pred = tr(hidden_states=lat, timestep=timestep / 1000, guidance=guidance,
                                 pooled_projections=pooled_prompt_embeds, encoder_hidden_states=prompt_embeds,
                                 txt_ids=text_ids, img_ids=img_ids, joint_attention_kwargs=None, return_dict=False)[0]
+            if do_true_cfg:
+                with tr.cache_context("uncond"):
+                    neg_noise_pred = tr(hidden_states=lat, timestep=timestep / 1000, guidance=guidance,
+                                        pooled_projections=negative_pooled_prompt_embeds, encoder_hidden_states=negative_prompt_embeds,
+                                        txt_ids=neg_text_ids, img_ids=img_ids, joint_attention_kwargs=None, return_dict=False)[0]
+                noise_pred = neg_noise_pred + true_cfg_scale * (noise_pred - neg_noise_pred)
             lat = sched.step(noise_pred, t, lat, return_dict=False)[0]
         if output_type == "latent":
             image = lat

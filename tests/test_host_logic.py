@@ -237,3 +237,125 @@ def test_unet_fold_norms_flag_keeps_exact_weights_when_off():
         # weights: re-rounded once (within an ulp); the GEGLU bias comes back as (b + W beta) - W' beta with the re-rounded W'
         tol = 2e-2 if k.endswith("ff.net.0.proj.bias") else 2.0 ** -5 * sd[k].float().abs().max() + 1e-6  # gamma down to ~0.4 amplifies the ulp
         assert d <= tol, (k, float(d))
+
+
+def test_rescale_noise_cfg_is_the_references(monkeypatch):
+    """N4: guidance_rescale.  The formula against the unmodified reference's function on the same 16-bit tensors (bit for bit), and
+    the SDXL drop-in loop applying it after the CFG combine (fake denoiser / stepper: the loop is glue, the kernels are tested elsewhere)."""
+    from baseline import ref_env
+    from diffusers_b200.pipelines import StableDiffusionXLPipeline, rescale_noise_cfg
+    g = torch.Generator().manual_seed(0)
+    cfg_pred, text_pred = torch.randn(3, 4, 8, 8, generator=g).bfloat16() * 2, torch.randn(3, 4, 8, 8, generator=g).bfloat16()
+    if ref_env.available():
+        ref_env.import_reference()
+        from diffusers.pipelines.stable_diffusion_xl.pipeline_stable_diffusion_xl import rescale_noise_cfg as ref_fn
+        for gr in (0.0, 0.3, 0.7, 1.0):
+            assert torch.equal(rescale_noise_cfg(cfg_pred, text_pred, gr), ref_fn(cfg_pred, text_pred, guidance_rescale=gr)), gr
+    out = rescale_noise_cfg(cfg_pred.float(), text_pred.float(), 1.0)
+    assert torch.allclose(out.std(dim=[1, 2, 3]), text_pred.float().std(dim=[1, 2, 3]), rtol=1e-5)  # full rescale: the text prediction's std per sample
+
+    class Unet:
+        config = type("C", (), dict(sample_size=2, in_channels=4, time_cond_proj_dim=None, addition_time_embed_dim=2))()
+        add_embedding = type("A", (), dict(linear_1=type("L", (), dict(in_features=2 * 6 + 5))()))()
+        device, dtype = torch.device("cpu"), torch.float32
+
+        def __call__(self, x, t, encoder_hidden_states=None, added_cond_kwargs=None, return_dict=False):
+            return (x * encoder_hidden_states.mean((1, 2))[:, None, None, None] + 0.25,)
+
+    class Sched:
+        init_noise_sigma = 1.0
+        timesteps = torch.tensor([2.0, 1.0])
+        seen = []
+
+        def set_timesteps(self, n, device=None):
+            pass
+
+        def set_begin_index(self, i):
+            pass
+
+        def scale_model_input(self, x, t):
+            return x
+
+        def step(self, eps, t, x, return_dict=False):
+            self.seen.append(eps.clone())
+            return (x - 0.1 * eps,)
+
+    vae = type("V", (), dict(config=type("C", (), dict(block_out_channels=(1, 1, 1, 1), scaling_factor=1.0))()))()
+    pe, npe = torch.full((1, 3, 5), 2.0), torch.full((1, 3, 5), 0.5)
+    pool = torch.ones(1, 5)
+    lat0 = torch.randn(1, 4, 2, 2, generator=g)
+    for gr in (0.0, 0.6):
+        sch = Sched()
+        sch.seen = []
+        pipe = StableDiffusionXLPipeline(vae, Unet(), sch)
+        out = pipe(pe, npe, pool, pool, height=16, width=16, num_inference_steps=2, guidance_scale=5.0, latents=lat0.clone(), output_type="latent",
+                   fused=False, guidance_rescale=gr).images
+        x = lat0.clone()
+        for _ in range(2):
+            u, c = x * 0.5 + 0.25, x * 2.0 + 0.25
+            n = u + 5.0 * (c - u)
+            if gr:
+                n = rescale_noise_cfg(n, c, gr)
+            x = x - 0.1 * n
+        assert torch.allclose(out, x, rtol=1e-6, atol=1e-6), gr
+
+
+def test_flux_true_cfg_composition():
+    """N4: true CFG for Flux (pipeline_flux.py:911-927): a second transformer call per step under cache_context("uncond") with the negative
+    embeddings, noise = neg + true_cfg_scale * (cond - neg); off unless true_cfg_scale > 1 AND negative embeddings are given."""
+    calls = []
+
+    class Tr:
+        config = FrozenConfig(dict(in_channels=16, guidance_embeds=True))
+        device, dtype = torch.device("cpu"), torch.float32
+        ctx = None
+
+        def cache_context(self, name):
+            import contextlib
+
+            @contextlib.contextmanager
+            def cm():
+                Tr.ctx = name
+                yield
+                Tr.ctx = None
+            return cm()
+
+        def __call__(self, hidden_states, timestep, guidance, pooled_projections, encoder_hidden_states, txt_ids, img_ids, joint_attention_kwargs=None,
+                     return_dict=False):
+            calls.append((Tr.ctx, float(encoder_hidden_states.mean()), txt_ids))
+            return (hidden_states * encoder_hidden_states.mean() + pooled_projections.mean(),)
+
+    class Sched:
+        config = dict()
+        timesteps = torch.tensor([900.0, 500.0])
+
+        def set_timesteps(self, n, device=None, sigmas=None, mu=None):
+            pass
+
+        def set_begin_index(self, i):
+            pass
+
+        def step(self, eps, t, x, return_dict=False):
+            return (x - 0.5 * eps,)
+
+    vae = type("V", (), dict(config=type("C", (), dict(block_out_channels=(1, 1, 1, 1)))()))()
+    pipe = FluxPipeline(Sched(), vae, Tr())
+    pe, npe = torch.full((1, 6, 8), 2.0), torch.full((1, 6, 8), -1.0)
+    pool, npool = torch.full((1, 4), 0.5), torch.full((1, 4), 0.25)
+    lat0 = torch.randn(1, 4, 16, generator=torch.Generator().manual_seed(1))
+    kw = dict(height=32, width=32, num_inference_steps=2, latents=lat0.clone(), output_type="latent")
+    plain = pipe(pe, pool, **kw).images
+    assert [c[0] for c in calls] == ["cond", "cond"]
+    calls.clear()
+    assert torch.equal(pipe(pe, pool, negative_prompt_embeds=npe, negative_pooled_prompt_embeds=npool, true_cfg_scale=1.0, **kw).images, plain)  # scale 1: off
+    assert torch.equal(pipe(pe, pool, true_cfg_scale=4.0, **kw).images, plain)                                                                   # no negatives: off
+    calls.clear()
+    out = pipe(pe, pool, negative_prompt_embeds=npe, negative_pooled_prompt_embeds=npool, true_cfg_scale=4.0, **kw).images
+    assert [c[0] for c in calls] == ["cond", "uncond", "cond", "uncond"] and calls[0][2] is calls[1][2]  # same ids tensor: the RoPE cache holds
+    x = lat0.clone()
+    for _ in range(2):
+        cond, neg = x * 2.0 + 0.5, x * -1.0 + 0.25
+        x = x - 0.5 * (neg + 4.0 * (cond - neg))
+    assert torch.allclose(out, x, rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        pipe(pe, pool, negative_prompt_embeds=npe, true_cfg_scale=4.0, **kw)
