@@ -45,9 +45,10 @@ class EulerDiscreteScheduler:
         # (legacy entries of published configs: SDXL-base's scheduler_config.json carries `sample_max_value`, `skip_prk_steps`,
         # `set_alpha_to_one`, `clip_sample`) are ignored with a warning, as the reference's own config loader does
         # (configuration_utils.py extract_init_dict).
-        not_implemented = dict(trained_betas=(None,), use_karras_sigmas=(None, False), use_exponential_sigmas=(None, False),
+        not_implemented = dict(trained_betas=(None,), use_exponential_sigmas=(None, False),
                                use_beta_sigmas=(None, False), sigma_min=(None,), sigma_max=(None,), timestep_type=("discrete",),
                                rescale_betas_zero_snr=(None, False))
+        use_karras_sigmas = bool(unsupported.pop("use_karras_sigmas", False))  # "Euler Karras": a different sigma table, same step
         for k, v in unsupported.items():
             if k in not_implemented:
                 if v not in not_implemented[k]:
@@ -62,7 +63,7 @@ class EulerDiscreteScheduler:
         self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
                                    beta_schedule=beta_schedule, prediction_type=prediction_type,
                                    interpolation_type=interpolation_type, timestep_spacing=timestep_spacing,
-                                   steps_offset=steps_offset, final_sigmas_type=final_sigmas_type, use_karras_sigmas=False,
+                                   steps_offset=steps_offset, final_sigmas_type=final_sigmas_type, use_karras_sigmas=use_karras_sigmas,
                                    timestep_type="discrete")
         if beta_schedule == "linear":
             self.betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
@@ -117,8 +118,12 @@ class EulerDiscreteScheduler:
             ts -= 1
         else:
             raise ValueError(c.timestep_spacing)
-        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
-        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        full = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = np.interp(ts, np.arange(0, len(full)), full)
+        if c.use_karras_sigmas:
+            # scheduling_euler_discrete.py:448-450: Karras spacing between the extremes of the INTERPOLATED table; the timesteps become the
+            # (fractional) positions of those sigmas on the training schedule
+            sig, ts = _karras_sigmas_and_timesteps(full, num_inference_steps, sigma_min=sig[-1].item(), sigma_max=sig[0].item())
         sig = np.concatenate([sig, [0]]).astype(np.float32)
         self.sigmas = torch.from_numpy(sig).to(dtype=torch.float32)  # stays on the host, like the reference (:481)
         self._timesteps_cpu = torch.from_numpy(ts.astype(np.float32))
@@ -608,20 +613,43 @@ class EulerAncestralDiscreteScheduler(_StepIndexMixin):
         return SchedulerOutput(prev)
 
 
+def _karras_sigmas_and_timesteps(train_sigmas, n, rho=7.0, sigma_min=None, sigma_max=None):
+    """The reference's `_convert_to_karras` + `_sigma_to_t` (scheduling_dpmsolver_multistep.py:544-638; same numpy operations by necessity:
+    the tables are compared bit for bit).  train_sigmas ascending (index = training timestep) -> (n descending sigmas, their float timesteps).
+    sigma_min / sigma_max default to the extremes of the training schedule (DPM-Solver); Euler passes those of its interpolated table."""
+    log_sigmas = np.log(train_sigmas)
+    sigma_min = train_sigmas[0].item() if sigma_min is None else sigma_min
+    sigma_max = train_sigmas[-1].item() if sigma_max is None else sigma_max
+    ramp = np.linspace(0, 1, n)
+    min_inv_rho, max_inv_rho = sigma_min ** (1 / rho), sigma_max ** (1 / rho)
+    sig = (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** rho
+    ts = []
+    for sigma in sig:
+        log_sigma = np.log(np.maximum(sigma, 1e-10))
+        dists = log_sigma - log_sigmas[:, np.newaxis]
+        low_idx = np.cumsum((dists >= 0), axis=0).argmax(axis=0).clip(max=log_sigmas.shape[0] - 2)
+        high_idx = low_idx + 1
+        low, high = log_sigmas[low_idx], log_sigmas[high_idx]
+        w = np.clip((low - log_sigma) / (low - high), 0, 1)
+        ts.append(((1 - w) * low_idx + w * high_idx).reshape(sigma.shape))
+    return sig, np.array(ts)
+
+
 class DPMSolverMultistepScheduler(_StepIndexMixin):
     """schedulers/scheduling_dpmsolver_multistep.py:132 - DPM-Solver++ (2M): algorithm_type 'dpmsolver++', solver_order 1 or 2,
-    midpoint, epsilon prediction, sigmas interpolated from the training schedule (no Karras / Lu / exponential / beta / flow
-    variants), final sigma 0.  Data prediction (:793-795) and the first / second order updates (:900-903, :980-992) are single
+    midpoint, epsilon prediction, sigmas interpolated from the training schedule or Karras-spaced (`use_karras_sigmas`: "DPM++ 2M
+    Karras"; no Lu / exponential / beta / flow variants), final sigma 0.  Data prediction (:793-795) and the first / second order updates (:900-903, :980-992) are single
     b200_linear_step launches; the coefficients are computed from the fp32 sigma table exactly as the reference does."""
     order = 1
     init_noise_sigma = 1.0
 
     def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2,
                  prediction_type="epsilon", algorithm_type="dpmsolver++", solver_type="midpoint", lower_order_final=True, euler_at_final=False,
-                 final_sigmas_type="zero", lambda_min_clipped=-float("inf"), timestep_spacing="linspace", steps_offset=0, **unsupported):
+                 final_sigmas_type="zero", lambda_min_clipped=-float("inf"), timestep_spacing="linspace", steps_offset=0, use_karras_sigmas=False,
+                 **unsupported):
         _reject("DPMSolverMultistepScheduler", unsupported,
                 dict(trained_betas=(None,), thresholding=(None, False), dynamic_thresholding_ratio=(0.995,), sample_max_value=(1.0, 1),
-                     use_karras_sigmas=(None, False), use_exponential_sigmas=(None, False), use_beta_sigmas=(None, False), use_lu_lambdas=(None, False),
+                     use_exponential_sigmas=(None, False), use_beta_sigmas=(None, False), use_lu_lambdas=(None, False),
                      use_flow_sigmas=(None, False), flow_shift=(1.0, 1), variance_type=(None,), rescale_betas_zero_snr=(None, False),
                      use_dynamic_shifting=(None, False), time_shift_type=("exponential",)))
         if (prediction_type, algorithm_type, solver_type, final_sigmas_type) != ("epsilon", "dpmsolver++", "midpoint", "zero") or solver_order not in (1, 2):
@@ -630,7 +658,7 @@ class DPMSolverMultistepScheduler(_StepIndexMixin):
                                    solver_order=solver_order, prediction_type=prediction_type, algorithm_type=algorithm_type, solver_type=solver_type,
                                    lower_order_final=lower_order_final, euler_at_final=euler_at_final, final_sigmas_type=final_sigmas_type,
                                    lambda_min_clipped=lambda_min_clipped, timestep_spacing=timestep_spacing, steps_offset=steps_offset,
-                                   use_karras_sigmas=False, thresholding=False)
+                                   use_karras_sigmas=bool(use_karras_sigmas), thresholding=False)
         self.betas = _betas(beta_schedule, beta_start, beta_end, num_train_timesteps)
         self.alphas = 1.0 - self.betas
         self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
@@ -666,7 +694,13 @@ class DPMSolverMultistepScheduler(_StepIndexMixin):
         else:
             raise ValueError(c.timestep_spacing)
         sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
-        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        if c.use_karras_sigmas:
+            # "DPM++ 2M Karras" (scheduling_dpmsolver_multistep.py:444-449): Karras et al.'s rho = 7 spacing between the schedule's extreme
+            # sigmas; a timestep is the rounded position of its sigma on the training schedule.  The step below reads only the sigma table.
+            sig, ts = _karras_sigmas_and_timesteps(sig, num_inference_steps)
+            ts = ts.round().astype(np.int64)
+        else:
+            sig = np.interp(ts, np.arange(0, len(sig)), sig)
         self.sigmas = torch.from_numpy(np.concatenate([sig, [0]]).astype(np.float32))  # host table
         self._timesteps_cpu = torch.from_numpy(ts)
         self.timesteps = self._timesteps_cpu.to(device=device, dtype=torch.int64)

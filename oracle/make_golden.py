@@ -146,6 +146,8 @@ STEPPERS = [  # (fixture key, reference class, constructor arguments)
                                                          timestep_spacing="leading", steps_offset=1)),
     ("dpmpp_2m_linspace", "DPMSolverMultistepScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")),
     ("dpmpp_1", "DPMSolverMultistepScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", solver_order=1)),
+    ("dpmpp_2m_karras", "DPMSolverMultistepScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="leading",
+                                                           steps_offset=1, use_karras_sigmas=True)),
 ]
 
 
@@ -178,6 +180,20 @@ def gen_steppers(d):
                 x = s.step(eps, t, x, return_dict=False, **extra)[0]
             traj[str(dt).split(".")[-1]] = dict(start=start, final=x.clone())
         out[key] = dict(cls=cls, config=kw, tables=tabs, trajectory=traj, steps=8)
+    # "Euler Karras" (EulerDiscreteScheduler(use_karras_sigmas=True)): tables and an fp32 trajectory of the real reference
+    ek = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="leading", steps_offset=1, use_karras_sigmas=True)
+    tabs = {}
+    for n in (30, 7):
+        s = d.EulerDiscreteScheduler(**ek)
+        s.set_timesteps(n)
+        tabs[n] = dict(timesteps=s.timesteps.clone(), sigmas=s.sigmas.clone(), init_noise_sigma=float(s.init_noise_sigma))
+    s = d.EulerDiscreteScheduler(**ek)
+    s.set_timesteps(8)
+    x = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(1)) * float(s.init_noise_sigma)
+    start = x.clone()
+    for t in s.timesteps:
+        x = s.step(stepper_fake_model(s.scale_model_input(x, t), t), t, x, return_dict=False)[0]
+    out["euler_karras_sdxl"] = dict(cls="EulerDiscreteScheduler", config=ek, tables=tabs, steps=8, trajectory=dict(float32=dict(start=start, final=x.clone())))
     torch.save(out, os.path.join(OUT, "schedulers2.pt"))
     print("steppers ok")
 

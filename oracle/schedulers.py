@@ -287,14 +287,37 @@ class EulerAncestral:
         return prev
 
 
+def karras_sigmas_and_timesteps(train_sigmas, n, rho=7.0):
+    """_convert_to_karras (scheduling_dpmsolver_multistep.py:603-638, scheduling_euler_discrete.py:520-556) on the flipped training sigmas,
+    then _sigma_to_t (:544-578) for each: log-linear interpolation of the sigma's position on the training schedule."""
+    log_sigmas = np.log(train_sigmas)
+    desc = np.flip(train_sigmas).copy()
+    smin, smax = desc[-1].item(), desc[0].item()
+    ramp = np.linspace(0, 1, n)
+    lo, hi = smin ** (1 / rho), smax ** (1 / rho)
+    sig = (hi + ramp * (lo - hi)) ** rho
+
+    def sigma_to_t(sigma):
+        log_sigma = np.log(np.maximum(sigma, 1e-10))
+        dists = log_sigma - log_sigmas[:, np.newaxis]
+        low_idx = np.cumsum((dists >= 0), axis=0).argmax(axis=0).clip(max=log_sigmas.shape[0] - 2)
+        high_idx = low_idx + 1
+        low, high = log_sigmas[low_idx], log_sigmas[high_idx]
+        w = np.clip((low - log_sigma) / (low - high), 0, 1)
+        return ((1 - w) * low_idx + w * high_idx).reshape(sigma.shape)
+
+    return sig, np.array([sigma_to_t(x) for x in sig])
+
+
 class DPMSolverPP2M:
     """schedulers/scheduling_dpmsolver_multistep.py: __init__ :215-330, set_timesteps :366-497, _sigma_to_alpha_sigma_t :577-600,
     convert_model_output :745-815 (dpmsolver++, epsilon), dpm_solver_first_order_update :855-915,
     multistep_dpm_solver_second_order_update :925-1010 (midpoint), step :1196-1282"""
 
     def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2,
-                 timestep_spacing="linspace", steps_offset=0, lower_order_final=True):
+                 timestep_spacing="linspace", steps_offset=0, lower_order_final=True, use_karras_sigmas=False):
         self.N, self.offset, self.spacing, self.order, self.lof = num_train_timesteps, steps_offset, timestep_spacing, solver_order, lower_order_final
+        self.karras = use_karras_sigmas
         self.alphas_cumprod = torch.cumprod(1.0 - _betas(beta_schedule, beta_start, beta_end, num_train_timesteps), dim=0)
         self.init_noise_sigma = 1.0
 
@@ -307,9 +330,15 @@ class DPMSolverPP2M:
         else:
             ts = np.arange(last, 0, -self.N / n).round().copy().astype(np.int64) - 1
         sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
-        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        if self.karras:
+            # :444-449 "DPM++ 2M Karras": the n sigmas of Karras et al. (2206.00364, rho = 7) between the schedule's extremes, timesteps = the
+            # (rounded) positions of those sigmas on the training schedule
+            sig, ts = karras_sigmas_and_timesteps(sig, n)
+            ts = ts.round()
+        else:
+            sig = np.interp(ts, np.arange(0, len(sig)), sig)
         self.sigmas = torch.from_numpy(np.concatenate([sig, [0]]).astype(np.float32))
-        self.timesteps = torch.from_numpy(ts)
+        self.timesteps = torch.from_numpy(ts).to(torch.int64)
         self.outs, self.lower, self.i = [None] * self.order, 0, 0
 
     def scale_model_input(self, x, t):

@@ -135,8 +135,12 @@ def test_scheduler_configs(tmp_path):
     os.makedirs(tmp_path / "karras")
     with open(tmp_path / "karras" / "scheduler_config.json", "w") as f:
         json.dump({**raw, "use_karras_sigmas": True}, f)
+    assert EulerDiscreteScheduler.from_pretrained(str(tmp_path / "karras")).config.use_karras_sigmas is True  # "Euler Karras" is on the path
+    os.makedirs(tmp_path / "beta")
+    with open(tmp_path / "beta" / "scheduler_config.json", "w") as f:
+        json.dump({**raw, "use_beta_sigmas": True}, f)
     with pytest.raises(NotImplementedError):  # an option outside the path must not be dropped silently
-        EulerDiscreteScheduler.from_pretrained(str(tmp_path / "karras"))
+        EulerDiscreteScheduler.from_pretrained(str(tmp_path / "beta"))
     with pytest.raises(NotImplementedError):  # nor a different scheduler class be mistaken for this one
         DDPMScheduler.from_pretrained(FIXTURE, subfolder="scheduler")
     assert EulerDiscreteScheduler.from_config(s.config).config == s.config
@@ -164,7 +168,7 @@ def test_published_sdxl_scheduler_config_with_legacy_keys(tmp_path):
     ref.set_timesteps(50)
     assert torch.equal(s.sigmas, ref.sigmas) and torch.equal(s.timesteps, ref.timesteps)
     # reference-signature options this path does not implement still fail loudly
-    for bad in (dict(use_karras_sigmas=True), dict(rescale_betas_zero_snr=True), dict(timestep_type="continuous"), dict(sigma_min=0.1)):
+    for bad in (dict(rescale_betas_zero_snr=True), dict(timestep_type="continuous"), dict(sigma_min=0.1)):
         with pytest.raises(NotImplementedError):
             EulerDiscreteScheduler.from_config({**published, **bad})
 

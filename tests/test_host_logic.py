@@ -33,7 +33,7 @@ def test_flow_match_tables_bit_identical_to_reference(golden):
 
 def test_scheduler_rejects_unsupported_options():
     with pytest.raises(NotImplementedError):
-        S.EulerDiscreteScheduler(use_karras_sigmas=True)
+        S.EulerDiscreteScheduler(use_exponential_sigmas=True)
     with pytest.raises(NotImplementedError):
         S.EulerDiscreteScheduler(prediction_type="v_prediction")
 

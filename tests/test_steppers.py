@@ -78,11 +78,31 @@ def test_product_host_logic_follows_the_reference_trajectory(key, monkeypatch):
     assert (got - ref).abs().max() <= 1e-4 * ref.abs().max()
 
 
+def test_euler_karras_tables_and_host_logic(monkeypatch):
+    """EulerDiscreteScheduler(use_karras_sigmas=True): sigma / (fractional) timestep tables bit-identical to the reference's, and the
+    product's stepping logic on them (b200_euler_step / b200_scale evaluated in float64 by stand-ins) follows the reference trajectory."""
+    fx = FX["euler_karras_sdxl"]
+    for n, tab in fx["tables"].items():
+        s = S.EulerDiscreteScheduler(**fx["config"])
+        s.set_timesteps(n)
+        assert torch.equal(s.sigmas, tab["sigmas"]) and torch.equal(s.timesteps, tab["timesteps"]) and s.timesteps.dtype == torch.float32
+        assert float(s.init_noise_sigma) == tab["init_noise_sigma"] and s.config.use_karras_sigmas is True
+    monkeypatch.setattr(ops, "euler_step", lambda eps, x, sigma, sigma_next, out=None: (x.double() + eps.double() * (sigma_next - sigma)).to(eps.dtype))
+    monkeypatch.setattr(ops, "scale_div", lambda x, div, out=None: (x.double() / div).to(x.dtype))
+    s = S.EulerDiscreteScheduler(**fx["config"])
+    s.set_timesteps(fx["steps"])
+    s.set_begin_index(0)
+    got = _run(s, fx["trajectory"]["float32"]["start"].clone(), dict(return_dict=False))
+    ref = fx["trajectory"]["float32"]["final"]
+    assert (got - ref).abs().max() <= 1e-4 * ref.abs().max()
+    assert S.EulerDiscreteScheduler(beta_schedule="scaled_linear").config.use_karras_sigmas is False
+
+
 def test_steppers_reject_options_outside_the_path():
     with pytest.raises(NotImplementedError):
         S.DDIMScheduler(clip_sample=True)
     with pytest.raises(NotImplementedError):
-        S.DPMSolverMultistepScheduler(use_karras_sigmas=True)
+        S.DPMSolverMultistepScheduler(use_lu_lambdas=True)
     with pytest.raises(NotImplementedError):
         S.DPMSolverMultistepScheduler(algorithm_type="sde-dpmsolver++")
     with pytest.raises(NotImplementedError):
