@@ -57,9 +57,10 @@ class StableDiffusionXLPipeline:
         transformers; otherwise call with prompt_embeds).  checkpoint.py, SURVEY.md 8f N1."""
         from . import checkpoint
         from .autoencoder_kl import AutoencoderKL
-        from .schedulers import DDIMScheduler, DPMSolverMultistepScheduler, EulerAncestralDiscreteScheduler, EulerDiscreteScheduler
+        from .schedulers import (DDIMScheduler, DPMSolverMultistepScheduler, EulerAncestralDiscreteScheduler, EulerDiscreteScheduler,
+                                 UniPCMultistepScheduler)
         from .unet_2d_condition import UNet2DConditionModel
-        steppers = (EulerDiscreteScheduler, DDIMScheduler, EulerAncestralDiscreteScheduler, DPMSolverMultistepScheduler)
+        steppers = (EulerDiscreteScheduler, DDIMScheduler, EulerAncestralDiscreteScheduler, DPMSolverMultistepScheduler, UniPCMultistepScheduler)
         c = checkpoint.load_pipeline_components(path, "StableDiffusionXLPipeline",
                                                 dict(unet=UNet2DConditionModel, vae=AutoencoderKL, scheduler=steppers),
                                                 torch_dtype=torch_dtype, device=device, variant=variant)

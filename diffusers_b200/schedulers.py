@@ -748,3 +748,151 @@ class DPMSolverMultistepScheduler(_StepIndexMixin):
         if not return_dict:
             return (prev,)
         return SchedulerOutput(prev)
+
+
+class UniPCMultistepScheduler(_StepIndexMixin):
+    """schedulers/scheduling_unipc_multistep.py:123 - UniPC (Zhao et al. 2302.04867) as the reference configures it by default: solver_order
+    1 or 2, 'bh2', data prediction (predict_x0), epsilon prediction, corrector after every step, lower_order_final, sigmas interpolated from
+    the training schedule (or Karras-spaced), final sigma 0.
+
+    Every update of the reference is a linear combination of at most four tensors with scalar coefficients that depend only on the sigma
+    table, so each is ONE b200_linear_step launch (fp32 arithmetic, one rounding) with the coefficients computed on the host in fp32 exactly
+    as the reference computes its 0-dim tensors:
+        x0        = x / alpha - (sigma / alpha) eps                                                        convert_model_output :796-799
+        corrector = (s_t/s_s0) x_last - a_t h_phi_1 m0 - a_t B_h (rho_0 (m1 - m0)/r + rho_c (x0 - m0))     multistep_uni_c_bh_update :1080-1087
+        predictor = (s_t/s_s0) x      - a_t h_phi_1 m0 - a_t B_h (1/2) (m1 - m0)/r                         multistep_uni_p_bh_update :940-947
+    (rho = 1/2 at order 1; at order 2 the corrector's weights solve the reference's 2x2 system R rho = b).  The reference rounds those
+    weights and every intermediate to the sample's 16-bit dtype; here they stay fp32 until the single final rounding."""
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2, prediction_type="epsilon",
+                 predict_x0=True, solver_type="bh2", lower_order_final=True, disable_corrector=(), timestep_spacing="linspace", steps_offset=0,
+                 final_sigmas_type="zero", use_karras_sigmas=False, **unsupported):
+        _reject("UniPCMultistepScheduler", unsupported,
+                dict(trained_betas=(None,), thresholding=(None, False), dynamic_thresholding_ratio=(0.995,), sample_max_value=(1.0, 1), solver_p=(None,),
+                     use_exponential_sigmas=(None, False), use_beta_sigmas=(None, False), use_flow_sigmas=(None, False), flow_shift=(1.0, 1),
+                     rescale_betas_zero_snr=(None, False), use_dynamic_shifting=(None, False), time_shift_type=("exponential",), sigma_min=(None,),
+                     sigma_max=(None,), shift_terminal=(None,)))
+        if solver_type in ("midpoint", "heun", "logrho"):
+            solver_type = "bh2"  # the reference maps the DPM-Solver names onto bh2 (:274-276)
+        if (prediction_type, predict_x0, solver_type, final_sigmas_type) != ("epsilon", True, "bh2", "zero") or solver_order not in (1, 2) or list(disable_corrector):
+            raise NotImplementedError("UniPCMultistepScheduler: only epsilon / predict_x0 / bh2 / final sigma zero / corrector on, order 1 or 2")
+        self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end, beta_schedule=beta_schedule,
+                                   solver_order=solver_order, prediction_type=prediction_type, predict_x0=predict_x0, solver_type=solver_type,
+                                   lower_order_final=lower_order_final, disable_corrector=[], timestep_spacing=timestep_spacing, steps_offset=steps_offset,
+                                   final_sigmas_type=final_sigmas_type, use_karras_sigmas=bool(use_karras_sigmas), thresholding=False)
+        self.betas = _betas(beta_schedule, beta_start, beta_end, num_train_timesteps)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.sigmas = ((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5
+        self.num_inference_steps = None
+        self._timesteps_cpu = torch.from_numpy(np.linspace(0, num_train_timesteps - 1, num_train_timesteps, dtype=np.float32)[::-1].copy())
+        self.timesteps = self._timesteps_cpu
+        self.model_outputs = [None] * solver_order
+        self.lower_order_nums = 0
+        self.last_sample = None
+        self.this_order = None
+        self._step_index = self._begin_index = None
+
+    def scale_model_input(self, sample, *args, **kwargs):
+        return sample
+
+    def set_timesteps(self, num_inference_steps=None, device=None, sigmas=None, mu=None):
+        if sigmas is not None or mu is not None:
+            raise NotImplementedError("custom sigmas / dynamic shifting (flow-matching variants)")
+        c = self.config
+        N = c.num_train_timesteps
+        if c.timestep_spacing == "linspace":
+            ts = np.linspace(0, N - 1, num_inference_steps + 1).round()[::-1][:-1].copy().astype(np.int64)
+        elif c.timestep_spacing == "leading":
+            ts = (np.arange(0, num_inference_steps + 1) * (N // (num_inference_steps + 1))).round()[::-1][:-1].copy().astype(np.int64)
+            ts += c.steps_offset
+        elif c.timestep_spacing == "trailing":
+            ts = np.arange(N, 0, -N / num_inference_steps).round().copy().astype(np.int64)
+            ts -= 1
+        else:
+            raise ValueError(c.timestep_spacing)
+        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        if c.use_karras_sigmas:
+            sig, ts = _karras_sigmas_and_timesteps(sig, num_inference_steps)  # :375-383
+            ts = ts.round().astype(np.int64)
+        else:
+            sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0]]).astype(np.float32))  # host table
+        self._timesteps_cpu = torch.from_numpy(ts)
+        self.timesteps = self._timesteps_cpu.to(device=device, dtype=torch.int64)
+        self.num_inference_steps = len(ts)
+        self.model_outputs = [None] * c.solver_order
+        self.lower_order_nums = 0
+        self.last_sample = None
+        self.this_order = None
+        self._step_index = self._begin_index = None
+
+    @staticmethod
+    def _alpha_sigma(sigma):
+        alpha_t = 1 / ((sigma ** 2 + 1) ** 0.5)
+        return alpha_t, sigma * alpha_t
+
+    def _lambda(self, idx):
+        a, s = self._alpha_sigma(self.sigmas[idx])
+        return torch.log(a) - torch.log(s)
+
+    def _bh2(self, idx_t, idx_s0, idx_s1):
+        """The scalars of one update from sigma index idx_s0 to idx_t (idx_s1: the older point of an order-2 update, or None):
+        s_t/s_s0, a_t, h_phi_1 = B_h = expm1(-h), r = (lambda_s1 - lambda_s0) / h, and the reference's b vector (:905-916)."""
+        alpha_t, sigma_t = self._alpha_sigma(self.sigmas[idx_t])
+        alpha_s0, sigma_s0 = self._alpha_sigma(self.sigmas[idx_s0])
+        lambda_s0 = torch.log(alpha_s0) - torch.log(sigma_s0)
+        h = (torch.log(alpha_t) - torch.log(sigma_t)) - lambda_s0
+        hh = -h
+        h_phi_1 = torch.expm1(hh)
+        B_h = torch.expm1(hh)
+        r = (self._lambda(idx_s1) - lambda_s0) / h if idx_s1 is not None else None
+        h_phi_k = h_phi_1 / hh - 1
+        b1 = h_phi_k / B_h
+        b2 = (h_phi_k / hh - 0.5) * 2 / B_h
+        return sigma_t / sigma_s0, alpha_t, h_phi_1, B_h, r, b1, b2
+
+    def step(self, model_output, timestep, sample, return_dict=True):
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        i, n, c = self._step_index, len(self._timesteps_cpu), self.config
+        dt = model_output.dtype
+        a_cur, s_cur = self._alpha_sigma(self.sigmas[i])
+        x0 = ops.linear_step(sample.to(dt), m0=model_output, a=float(1.0 / a_cur), b=float(-s_cur / a_cur))
+        if i > 0 and self.last_sample is not None:
+            # ---- corrector: re-does the step that led here (from sigma[i-1] to sigma[i]) now that x0 at its end point is known
+            m0 = self.model_outputs[-1]
+            if self.this_order == 1:
+                A, a_t, hp1, Bh, _, _, _ = self._bh2(i, i - 1, None)
+                sample = ops.linear_step(self.last_sample, m0=m0, m1=x0, a=float(A), b=float(-a_t * hp1 + a_t * Bh * 0.5), c=float(-a_t * Bh * 0.5))
+            else:
+                A, a_t, hp1, Bh, r, b1, b2 = self._bh2(i, i - 1, i - 2)
+                # R rho = b with R = [[1, 1], [r, 1]] (:1062-1076): rho_0 weighs D1 = (m1 - m0) / r, rho_c weighs x0 - m0
+                rho_0 = (b1 - b2) / (1.0 - r)
+                rho_c = b1 - rho_0
+                m1 = self.model_outputs[-2]
+                sample = ops.linear_step(self.last_sample, m0=m0, m1=m1, noise=x0, a=float(A), b=float(-a_t * hp1 + a_t * Bh * (rho_0 / r + rho_c)),
+                                         c=float(-a_t * Bh * rho_0 / r), s=float(-a_t * Bh * rho_c))
+        for k in range(c.solver_order - 1):
+            self.model_outputs[k] = self.model_outputs[k + 1]
+        self.model_outputs[-1] = x0
+        this_order = min(c.solver_order, n - i) if c.lower_order_final else c.solver_order
+        self.this_order = min(this_order, self.lower_order_nums + 1)  # warm-up of the multistep history
+        self.last_sample = sample
+        # ---- predictor: from sigma[i] to sigma[i+1]
+        if self.this_order == 1:
+            A, a_t, hp1, Bh, _, _, _ = self._bh2(i + 1, i, None)
+            prev = ops.linear_step(sample.to(dt), m0=x0, a=float(A), b=float(-a_t * hp1))
+        else:
+            A, a_t, hp1, Bh, r, _, _ = self._bh2(i + 1, i, i - 1)
+            prev = ops.linear_step(sample.to(dt), m0=x0, m1=self.model_outputs[-2], a=float(A), b=float(-a_t * hp1 + a_t * Bh * 0.5 / r), c=float(-a_t * Bh * 0.5 / r))
+        if self.lower_order_nums < c.solver_order:
+            self.lower_order_nums += 1
+        self._step_index += 1
+        if not return_dict:
+            return (prev,)
+        return SchedulerOutput(prev)

@@ -146,6 +146,8 @@ STEPPERS = [  # (fixture key, reference class, constructor arguments)
                                                          timestep_spacing="leading", steps_offset=1)),
     ("dpmpp_2m_linspace", "DPMSolverMultistepScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")),
     ("dpmpp_1", "DPMSolverMultistepScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", solver_order=1)),
+    ("unipc_sdxl", "UniPCMultistepScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="leading", steps_offset=1)),
+    ("unipc_linspace", "UniPCMultistepScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")),
     ("dpmpp_2m_karras", "DPMSolverMultistepScheduler", dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="leading",
                                                            steps_offset=1, use_karras_sigmas=True)),
 ]

@@ -373,3 +373,111 @@ class DPMSolverPP2M:
             self.lower += 1
         self.i += 1
         return prev.to(model_output.dtype)
+
+
+class UniPC:
+    """schedulers/scheduling_unipc_multistep.py - UniPCMultistepScheduler with its defaults: solver_order 2, epsilon prediction,
+    predict_x0, solver_type 'bh2', lower_order_final, corrector on, final sigma 0.  set_timesteps :318-482 (default branch),
+    convert_model_output :760-832, multistep_uni_p_bh_update :833-960 (predictor), multistep_uni_c_bh_update :962-1098 (corrector),
+    step :1153-1232.  Same torch operations in the same order (0-dim fp32 coefficient tensors against tensors of the sample's dtype),
+    so the recorded reference trajectories are reproduced bit for bit."""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2,
+                 timestep_spacing="linspace", steps_offset=0):
+        self.N, self.offset, self.spacing, self.order = num_train_timesteps, steps_offset, timestep_spacing, solver_order
+        self.alphas_cumprod = torch.cumprod(1.0 - _betas(beta_schedule, beta_start, beta_end, num_train_timesteps), dim=0)
+        self.init_noise_sigma = 1.0
+
+    def set_timesteps(self, n):
+        if self.spacing == "linspace":
+            ts = np.linspace(0, self.N - 1, n + 1).round()[::-1][:-1].copy().astype(np.int64)
+        elif self.spacing == "leading":
+            ts = (np.arange(0, n + 1) * (self.N // (n + 1))).round()[::-1][:-1].copy().astype(np.int64) + self.offset
+        else:
+            ts = np.arange(self.N, 0, -self.N / n).round().copy().astype(np.int64) - 1
+        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0]]).astype(np.float32))
+        self.timesteps = torch.from_numpy(ts)
+        self.outs, self.lower, self.i, self.last_sample, self.this_order = [None] * self.order, 0, 0, None, None
+
+    def scale_model_input(self, x, t):
+        return x
+
+    @staticmethod
+    def _as(sigma):
+        a = 1 / ((sigma ** 2 + 1) ** 0.5)
+        return a, sigma * a
+
+    def _lam(self, idx):
+        a, s = self._as(self.sigmas[idx])
+        return torch.log(a) - torch.log(s)
+
+    def _bh(self, h, rks, order):
+        hh = -h
+        h_phi_1 = torch.expm1(hh)
+        h_phi_k = h_phi_1 / hh - 1
+        fact = 1
+        B_h = torch.expm1(hh)  # bh2
+        R, b = [], []
+        for i in range(1, order + 1):
+            R.append(torch.pow(rks, i - 1))
+            b.append(h_phi_k * fact / B_h)
+            fact *= i + 1
+            h_phi_k = h_phi_k / hh - 1 / fact
+        return h_phi_1, B_h, torch.stack(R), torch.stack(b)
+
+    def _predict(self, x, order):
+        i, m0 = self.i, self.outs[-1]
+        a_t, s_t = self._as(self.sigmas[i + 1])
+        a_s0, s_s0 = self._as(self.sigmas[i])
+        lam_s0 = torch.log(a_s0) - torch.log(s_s0)
+        h = (torch.log(a_t) - torch.log(s_t)) - lam_s0
+        rks, D1s = [], []
+        for k in range(1, order):
+            rk = (self._lam(i - k) - lam_s0) / h
+            rks.append(rk)
+            D1s.append((self.outs[-(k + 1)] - m0) / rk)
+        rks.append(torch.ones(()))
+        h_phi_1, B_h, R, b = self._bh(h, torch.stack(rks), order)
+        x_t_ = s_t / s_s0 * x - a_t * h_phi_1 * m0
+        if D1s:
+            rhos_p = torch.ones(1, dtype=x.dtype) * 0.5  # order 2: the simplified weights
+            pred_res = torch.einsum("k,bkc...->bc...", rhos_p, torch.stack(D1s, dim=1))
+        else:
+            pred_res = 0
+        return (x_t_ - a_t * B_h * pred_res).to(x.dtype)
+
+    def _correct(self, model_t, last_sample, order):
+        i, m0, x = self.i, self.outs[-1], last_sample
+        a_t, s_t = self._as(self.sigmas[i])
+        a_s0, s_s0 = self._as(self.sigmas[i - 1])
+        lam_s0 = torch.log(a_s0) - torch.log(s_s0)
+        h = (torch.log(a_t) - torch.log(s_t)) - lam_s0
+        rks, D1s = [], []
+        for k in range(1, order):
+            rk = (self._lam(i - (k + 1)) - lam_s0) / h
+            rks.append(rk)
+            D1s.append((self.outs[-(k + 1)] - m0) / rk)
+        rks.append(torch.ones(()))
+        h_phi_1, B_h, R, b = self._bh(h, torch.stack(rks), order)
+        rhos_c = torch.ones(1, dtype=x.dtype) * 0.5 if order == 1 else torch.linalg.solve(R, b).to(x.dtype)
+        x_t_ = s_t / s_s0 * x - a_t * h_phi_1 * m0
+        corr_res = torch.einsum("k,bkc...->bc...", rhos_c[:-1], torch.stack(D1s, dim=1)) if D1s else 0
+        D1_t = model_t - m0
+        return (x_t_ - a_t * B_h * (corr_res + rhos_c[-1] * D1_t)).to(x.dtype)
+
+    def step(self, model_output, timestep, sample, generator=None):
+        n, i = len(self.timesteps), self.i
+        a_c, s_c = self._as(self.sigmas[i])
+        x0 = (sample - s_c * model_output) / a_c
+        if i > 0 and self.last_sample is not None:
+            sample = self._correct(x0, self.last_sample, self.this_order)
+        self.outs = self.outs[1:] + [x0]
+        self.this_order = min(min(self.order, n - i), self.lower + 1)  # lower_order_final, multistep warm-up
+        self.last_sample = sample
+        prev = self._predict(sample, self.this_order)
+        if self.lower < self.order:
+            self.lower += 1
+        self.i += 1
+        return prev

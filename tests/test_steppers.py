@@ -18,7 +18,8 @@ from oracle import schedulers as osched  # noqa: E402
 from oracle.make_golden import STEPPERS, stepper_fake_model  # noqa: E402
 
 FX = torch.load(os.path.join(GOLDEN, "schedulers2.pt"), weights_only=False)
-ORACLE = dict(DDIMScheduler=osched.DDIM, EulerAncestralDiscreteScheduler=osched.EulerAncestral, DPMSolverMultistepScheduler=osched.DPMSolverPP2M)
+ORACLE = dict(DDIMScheduler=osched.DDIM, EulerAncestralDiscreteScheduler=osched.EulerAncestral, DPMSolverMultistepScheduler=osched.DPMSolverPP2M,
+              UniPCMultistepScheduler=osched.UniPC)
 KEYS = [k for k, _, _ in STEPPERS]
 
 
@@ -107,6 +108,10 @@ def test_steppers_reject_options_outside_the_path():
         S.DPMSolverMultistepScheduler(algorithm_type="sde-dpmsolver++")
     with pytest.raises(NotImplementedError):
         S.EulerAncestralDiscreteScheduler(prediction_type="v_prediction")
+    for bad in (dict(solver_type="bh1"), dict(predict_x0=False), dict(disable_corrector=[0]), dict(use_flow_sigmas=True), dict(solver_order=3)):
+        with pytest.raises(NotImplementedError):
+            S.UniPCMultistepScheduler(**bad)
+    assert S.UniPCMultistepScheduler(solver_type="midpoint").config.solver_type == "bh2"  # the reference maps the DPM-Solver names onto bh2
     s = S.DDIMScheduler(clip_sample=False)
     s.set_timesteps(10)
     with pytest.raises(NotImplementedError):
