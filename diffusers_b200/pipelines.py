@@ -193,7 +193,7 @@ class StableDiffusionXLPipeline:
 
         from .schedulers import EulerDiscreteScheduler
         rescale = do_cfg and guidance_rescale > 0.0
-        if fused and isinstance(sched, EulerDiscreteScheduler) and not rescale:
+        if fused and isinstance(sched, EulerDiscreteScheduler) and sched.config.prediction_type == "epsilon" and not rescale:
             lat = self._denoise_fused(lat, timesteps, prompt_embeds, added, guidance_scale, do_cfg)
         else:
             # drop-in loop (any scheduler with the reference's scale_model_input / step surface: DDIM, Euler-ancestral,

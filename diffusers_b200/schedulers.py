@@ -56,8 +56,8 @@ class EulerDiscreteScheduler:
             else:
                 import warnings
                 warnings.warn(f"EulerDiscreteScheduler: config key {k!r} is not an argument of the reference scheduler and is ignored")
-        if prediction_type != "epsilon":
-            raise NotImplementedError("only prediction_type='epsilon'")
+        if prediction_type not in ("epsilon", "v_prediction"):
+            raise NotImplementedError("prediction_type 'epsilon' or 'v_prediction'")
         if interpolation_type != "linear" or final_sigmas_type != "zero":
             raise NotImplementedError("only linear interpolation with a final sigma of zero")
         self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
@@ -158,7 +158,12 @@ class EulerDiscreteScheduler:
             self._init_step_index(timestep)
         sigma = float(self.sigmas[self._step_index])
         sigma_next = float(self.sigmas[self._step_index + 1])
-        prev = ops.euler_step(model_output, sample, sigma, sigma_next)
+        if self.config.prediction_type == "v_prediction":
+            # x0 = -sigma / sqrt(sigma^2 + 1) v + x / (sigma^2 + 1) (:773-775); prev = x + (x - x0) / sigma * dt: linear in (x, v)
+            dt = sigma_next - sigma
+            prev = ops.linear_step(sample.to(model_output.dtype), m0=model_output, a=1.0 + dt * sigma / (sigma * sigma + 1.0), b=dt / (sigma * sigma + 1.0) ** 0.5)
+        else:
+            prev = ops.euler_step(model_output, sample, sigma, sigma_next)
         self._step_index += 1
         if not return_dict:
             return (prev, None)
@@ -480,8 +485,8 @@ class DDIMScheduler(_StepIndexMixin):
                                                    clip_sample_range=(1.0, 1), sample_max_value=(1.0, 1), rescale_betas_zero_snr=(None, False)))
         if clip_sample:
             raise NotImplementedError("DDIMScheduler clip_sample=True (pixel-space models) is outside the hot path; latent models use False")
-        if prediction_type != "epsilon":
-            raise NotImplementedError("only prediction_type='epsilon'")
+        if prediction_type not in ("epsilon", "v_prediction"):
+            raise NotImplementedError("prediction_type 'epsilon' or 'v_prediction'")
         self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end, beta_schedule=beta_schedule,
                                    clip_sample=False, set_alpha_to_one=set_alpha_to_one, steps_offset=steps_offset, prediction_type=prediction_type,
                                    timestep_spacing=timestep_spacing, thresholding=False)
@@ -530,8 +535,13 @@ class DDIMScheduler(_StepIndexMixin):
         a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
         sa, sb = float(a_t ** 0.5), float((1 - a_t) ** 0.5)
         sap, sbp = float(a_prev ** 0.5), float((1 - a_prev) ** 0.5)
-        x0 = ops.linear_step(sample, m0=model_output, a=1.0 / sa, b=-sb / sa)
-        prev = ops.linear_step(sample, m0=model_output, a=sap / sa, b=sbp - sap * sb / sa)
+        if self.config.prediction_type == "v_prediction":
+            # x0 = sqrt(a_t) x - sqrt(1-a_t) v,  eps = sqrt(a_t) v + sqrt(1-a_t) x  (:468-470)
+            x0 = ops.linear_step(sample, m0=model_output, a=sa, b=-sb)
+            prev = ops.linear_step(sample, m0=model_output, a=sap * sa + sbp * sb, b=sbp * sa - sap * sb)
+        else:
+            x0 = ops.linear_step(sample, m0=model_output, a=1.0 / sa, b=-sb / sa)
+            prev = ops.linear_step(sample, m0=model_output, a=sap / sa, b=sbp - sap * sb / sa)
         self._step_index += 1
         if not return_dict:
             return (prev, x0)
@@ -652,8 +662,9 @@ class DPMSolverMultistepScheduler(_StepIndexMixin):
                      use_exponential_sigmas=(None, False), use_beta_sigmas=(None, False), use_lu_lambdas=(None, False),
                      use_flow_sigmas=(None, False), flow_shift=(1.0, 1), variance_type=(None,), rescale_betas_zero_snr=(None, False),
                      use_dynamic_shifting=(None, False), time_shift_type=("exponential",)))
-        if (prediction_type, algorithm_type, solver_type, final_sigmas_type) != ("epsilon", "dpmsolver++", "midpoint", "zero") or solver_order not in (1, 2):
-            raise NotImplementedError("DPMSolverMultistepScheduler: only epsilon / dpmsolver++ / midpoint / final sigma zero, order 1 or 2")
+        if (algorithm_type, solver_type, final_sigmas_type) != ("dpmsolver++", "midpoint", "zero") or solver_order not in (1, 2) or \
+                prediction_type not in ("epsilon", "v_prediction"):
+            raise NotImplementedError("DPMSolverMultistepScheduler: only epsilon / v_prediction, dpmsolver++ / midpoint / final sigma zero, order 1 or 2")
         self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end, beta_schedule=beta_schedule,
                                    solver_order=solver_order, prediction_type=prediction_type, algorithm_type=algorithm_type, solver_type=solver_type,
                                    lower_order_final=lower_order_final, euler_at_final=euler_at_final, final_sigmas_type=final_sigmas_type,
@@ -723,7 +734,10 @@ class DPMSolverMultistepScheduler(_StepIndexMixin):
         lower_order_final = (i == n - 1) and (c.euler_at_final or (c.lower_order_final and n < 15) or c.final_sigmas_type == "zero")
         # data prediction x0 = (x - sigma_t eps) / alpha_t at the current sigma (:793-795)
         a_cur, s_cur = self._alpha_sigma(self.sigmas[i])
-        x0 = ops.linear_step(sample.to(model_output.dtype), m0=model_output, a=float(1.0 / a_cur), b=float(-s_cur / a_cur))
+        if c.prediction_type == "v_prediction":  # x0 = alpha_t x - sigma_t v (:797-799)
+            x0 = ops.linear_step(sample.to(model_output.dtype), m0=model_output, a=float(a_cur), b=float(-s_cur))
+        else:
+            x0 = ops.linear_step(sample.to(model_output.dtype), m0=model_output, a=float(1.0 / a_cur), b=float(-s_cur / a_cur))
         for k in range(c.solver_order - 1):
             self.model_outputs[k] = self.model_outputs[k + 1]
         self.model_outputs[-1] = x0
@@ -776,8 +790,9 @@ class UniPCMultistepScheduler(_StepIndexMixin):
                      sigma_max=(None,), shift_terminal=(None,)))
         if solver_type in ("midpoint", "heun", "logrho"):
             solver_type = "bh2"  # the reference maps the DPM-Solver names onto bh2 (:274-276)
-        if (prediction_type, predict_x0, solver_type, final_sigmas_type) != ("epsilon", True, "bh2", "zero") or solver_order not in (1, 2) or list(disable_corrector):
-            raise NotImplementedError("UniPCMultistepScheduler: only epsilon / predict_x0 / bh2 / final sigma zero / corrector on, order 1 or 2")
+        if (predict_x0, solver_type, final_sigmas_type) != (True, "bh2", "zero") or solver_order not in (1, 2) or list(disable_corrector) or \
+                prediction_type not in ("epsilon", "v_prediction"):
+            raise NotImplementedError("UniPCMultistepScheduler: only epsilon / v_prediction, predict_x0 / bh2 / final sigma zero / corrector on, order 1 or 2")
         self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end, beta_schedule=beta_schedule,
                                    solver_order=solver_order, prediction_type=prediction_type, predict_x0=predict_x0, solver_type=solver_type,
                                    lower_order_final=lower_order_final, disable_corrector=[], timestep_spacing=timestep_spacing, steps_offset=steps_offset,
@@ -862,7 +877,10 @@ class UniPCMultistepScheduler(_StepIndexMixin):
         i, n, c = self._step_index, len(self._timesteps_cpu), self.config
         dt = model_output.dtype
         a_cur, s_cur = self._alpha_sigma(self.sigmas[i])
-        x0 = ops.linear_step(sample.to(dt), m0=model_output, a=float(1.0 / a_cur), b=float(-s_cur / a_cur))
+        if c.prediction_type == "v_prediction":  # x0 = alpha_t x - sigma_t v (:800-801)
+            x0 = ops.linear_step(sample.to(dt), m0=model_output, a=float(a_cur), b=float(-s_cur))
+        else:
+            x0 = ops.linear_step(sample.to(dt), m0=model_output, a=float(1.0 / a_cur), b=float(-s_cur / a_cur))
         if i > 0 and self.last_sample is not None:
             # ---- corrector: re-does the step that led here (from sigma[i-1] to sigma[i]) now that x0 at its end point is known
             m0 = self.model_outputs[-1]

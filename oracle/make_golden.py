@@ -153,6 +153,16 @@ STEPPERS = [  # (fixture key, reference class, constructor arguments)
 ]
 
 
+_SDXL_BETAS = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+VPRED_STEPPERS = [  # v_prediction variants (SD 2.x-v, v-pred SDXL fine-tunes): CPU-side fixtures only (same kernels, other coefficients)
+    ("vpred_euler", "EulerDiscreteScheduler", dict(_SDXL_BETAS, timestep_spacing="trailing", prediction_type="v_prediction")),
+    ("vpred_ddim", "DDIMScheduler", dict(_SDXL_BETAS, clip_sample=False, set_alpha_to_one=False, steps_offset=1, timestep_spacing="leading",
+                                         prediction_type="v_prediction")),
+    ("vpred_dpmpp_2m", "DPMSolverMultistepScheduler", dict(_SDXL_BETAS, timestep_spacing="leading", steps_offset=1, prediction_type="v_prediction")),
+    ("vpred_unipc", "UniPCMultistepScheduler", dict(_SDXL_BETAS, prediction_type="v_prediction")),
+]
+
+
 def stepper_fake_model(x, t):
     """A deterministic stand-in for the denoiser (same dtype in and out) so that scheduler trajectories can be compared alone."""
     return (torch.sin(x.float() * 0.7 + float(t) * 0.01) * 0.8 + 0.1 * x.float()).to(x.dtype)
@@ -162,7 +172,7 @@ def gen_steppers(d):
     """tests/golden/schedulers2.pt: tables of the N4 steppers and whole trajectories of the REAL reference schedulers (fp32 and
     bf16 tensors on CPU) driven by stepper_fake_model, with the ancestral sampler's noise drawn from seeded generators."""
     out = {}
-    for key, cls, kw in STEPPERS:
+    for key, cls, kw in STEPPERS + VPRED_STEPPERS:
         tabs = {}
         for n in (30, 7):
             s = getattr(d, cls)(**kw)

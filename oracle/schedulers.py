@@ -208,9 +208,9 @@ class DDIM:
     """schedulers/scheduling_ddim.py: __init__ :193-245, set_timesteps :328-381, step :384-520 (eta = 0, epsilon, no clipping)"""
 
     def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", set_alpha_to_one=True,
-                 steps_offset=0, timestep_spacing="leading", clip_sample=False):
+                 steps_offset=0, timestep_spacing="leading", clip_sample=False, prediction_type="epsilon"):
         assert not clip_sample
-        self.N, self.offset, self.spacing = num_train_timesteps, steps_offset, timestep_spacing
+        self.N, self.offset, self.spacing, self.prediction_type = num_train_timesteps, steps_offset, timestep_spacing, prediction_type
         self.alphas_cumprod = torch.cumprod(1.0 - _betas(beta_schedule, beta_start, beta_end, num_train_timesteps), dim=0)
         self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
         self.init_noise_sigma = 1.0
@@ -234,8 +234,13 @@ class DDIM:
         a_t = self.alphas_cumprod[t]
         a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
         b_t = 1 - a_t
-        x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
-        direction = (1 - a_prev) ** 0.5 * model_output
+        if self.prediction_type == "v_prediction":  # :468-470
+            x0 = (a_t ** 0.5) * sample - (b_t ** 0.5) * model_output
+            eps = (a_t ** 0.5) * model_output + (b_t ** 0.5) * sample
+        else:
+            x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+            eps = model_output
+        direction = (1 - a_prev) ** 0.5 * eps
         return a_prev ** 0.5 * x0 + direction
 
 
@@ -315,9 +320,9 @@ class DPMSolverPP2M:
     multistep_dpm_solver_second_order_update :925-1010 (midpoint), step :1196-1282"""
 
     def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2,
-                 timestep_spacing="linspace", steps_offset=0, lower_order_final=True, use_karras_sigmas=False):
+                 timestep_spacing="linspace", steps_offset=0, lower_order_final=True, use_karras_sigmas=False, prediction_type="epsilon"):
         self.N, self.offset, self.spacing, self.order, self.lof = num_train_timesteps, steps_offset, timestep_spacing, solver_order, lower_order_final
-        self.karras = use_karras_sigmas
+        self.karras, self.prediction_type = use_karras_sigmas, prediction_type
         self.alphas_cumprod = torch.cumprod(1.0 - _betas(beta_schedule, beta_start, beta_end, num_train_timesteps), dim=0)
         self.init_noise_sigma = 1.0
 
@@ -353,7 +358,7 @@ class DPMSolverPP2M:
         n, i = len(self.timesteps), self.i
         final = i == n - 1  # final_sigmas_type == "zero"
         a_c, s_c = self._as(self.sigmas[i])
-        x0 = (sample - s_c * model_output) / a_c
+        x0 = a_c * sample - s_c * model_output if self.prediction_type == "v_prediction" else (sample - s_c * model_output) / a_c  # :793-799
         self.outs = self.outs[1:] + [x0]
         sample = sample.to(torch.float32)
         a_t, s_t = self._as(self.sigmas[i + 1])
@@ -383,8 +388,9 @@ class UniPC:
     so the recorded reference trajectories are reproduced bit for bit."""
 
     def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2,
-                 timestep_spacing="linspace", steps_offset=0):
+                 timestep_spacing="linspace", steps_offset=0, prediction_type="epsilon"):
         self.N, self.offset, self.spacing, self.order = num_train_timesteps, steps_offset, timestep_spacing, solver_order
+        self.prediction_type = prediction_type
         self.alphas_cumprod = torch.cumprod(1.0 - _betas(beta_schedule, beta_start, beta_end, num_train_timesteps), dim=0)
         self.init_noise_sigma = 1.0
 
@@ -470,7 +476,7 @@ class UniPC:
     def step(self, model_output, timestep, sample, generator=None):
         n, i = len(self.timesteps), self.i
         a_c, s_c = self._as(self.sigmas[i])
-        x0 = (sample - s_c * model_output) / a_c
+        x0 = a_c * sample - s_c * model_output if self.prediction_type == "v_prediction" else (sample - s_c * model_output) / a_c  # :796-801
         if i > 0 and self.last_sample is not None:
             sample = self._correct(x0, self.last_sample, self.this_order)
         self.outs = self.outs[1:] + [x0]

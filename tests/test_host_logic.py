@@ -35,7 +35,7 @@ def test_scheduler_rejects_unsupported_options():
     with pytest.raises(NotImplementedError):
         S.EulerDiscreteScheduler(use_exponential_sigmas=True)
     with pytest.raises(NotImplementedError):
-        S.EulerDiscreteScheduler(prediction_type="v_prediction")
+        S.EulerDiscreteScheduler(prediction_type="sample")
 
 
 def test_pack_conv_weight_layout():

@@ -15,7 +15,7 @@ from conftest import GOLDEN  # noqa: E402
 from diffusers_b200 import ops  # noqa: E402
 from diffusers_b200 import schedulers as S  # noqa: E402
 from oracle import schedulers as osched  # noqa: E402
-from oracle.make_golden import STEPPERS, stepper_fake_model  # noqa: E402
+from oracle.make_golden import STEPPERS, VPRED_STEPPERS, stepper_fake_model  # noqa: E402
 
 FX = torch.load(os.path.join(GOLDEN, "schedulers2.pt"), weights_only=False)
 ORACLE = dict(DDIMScheduler=osched.DDIM, EulerAncestralDiscreteScheduler=osched.EulerAncestral, DPMSolverMultistepScheduler=osched.DPMSolverPP2M,
@@ -99,6 +99,56 @@ def test_euler_karras_tables_and_host_logic(monkeypatch):
     assert S.EulerDiscreteScheduler(beta_schedule="scaled_linear").config.use_karras_sigmas is False
 
 
+class _OracleEuler:
+    """oracle.schedulers.EulerDiscrete behind the (timestep-taking) call surface the runner uses."""
+
+    def __init__(self, **kw):
+        self.o = osched.EulerDiscrete(**kw)
+
+    def set_timesteps(self, n):
+        self.o.set_timesteps(n)
+        self.timesteps = self.o.timesteps
+
+    def scale_model_input(self, x, t):
+        return self.o.scale_model_input(x)
+
+    def step(self, eps, t, x):
+        return self.o.step(eps, x)
+
+
+@pytest.mark.parametrize("key", [k for k, _, _ in VPRED_STEPPERS])
+def test_v_prediction_steppers(key, monkeypatch):
+    """prediction_type='v_prediction' (SD 2.x-v, v-pred SDXL fine-tunes) on Euler, DDIM, DPM-Solver++ and UniPC: the oracle reproduces the real
+    reference's fp32 and bf16 trajectories bit for bit; the product's tables are the reference's and its host logic (the step kernels
+    evaluated exactly by stand-ins) follows the reference's fp32 trajectory.  Same kernels as the epsilon steppers, other coefficients."""
+    fx = FX[key]
+    oracle_cls = dict(ORACLE, EulerDiscreteScheduler=_OracleEuler)[fx["cls"]]
+    for dtn in ("float32", "bfloat16"):
+        o = oracle_cls(**fx["config"])
+        o.set_timesteps(fx["steps"])
+        got = _run(o, fx["trajectory"][dtn]["start"].clone(), {})
+        assert torch.equal(got, fx["trajectory"][dtn]["final"]), (key, dtn)
+    for n, tab in fx["tables"].items():
+        s = getattr(S, fx["cls"])(**fx["config"])
+        s.set_timesteps(n)
+        assert torch.equal(s.timesteps, tab["timesteps"]) and (tab["sigmas"] is None or torch.equal(s.sigmas, tab["sigmas"]))
+
+    def lin(sample, m0=None, m1=None, noise=None, *, a=1.0, b=0.0, c=0.0, s=0.0, out=None):
+        v = a * sample.double()
+        for coef, t in ((b, m0), (c, m1), (s, noise)):
+            if t is not None:
+                v = v + coef * t.double()
+        return v.to(sample.dtype)
+    monkeypatch.setattr(ops, "linear_step", lin)
+    monkeypatch.setattr(ops, "scale_div", lambda x, div, out=None: (x.double() / div).to(x.dtype))
+    s = getattr(S, fx["cls"])(**fx["config"])
+    s.set_timesteps(fx["steps"])
+    s.set_begin_index(0)
+    got = _run(s, fx["trajectory"]["float32"]["start"].clone(), dict(return_dict=False))
+    ref = fx["trajectory"]["float32"]["final"]
+    assert (got - ref).abs().max() <= 1e-4 * ref.abs().max()
+
+
 def test_steppers_reject_options_outside_the_path():
     with pytest.raises(NotImplementedError):
         S.DDIMScheduler(clip_sample=True)
@@ -108,6 +158,8 @@ def test_steppers_reject_options_outside_the_path():
         S.DPMSolverMultistepScheduler(algorithm_type="sde-dpmsolver++")
     with pytest.raises(NotImplementedError):
         S.EulerAncestralDiscreteScheduler(prediction_type="v_prediction")
+    with pytest.raises(NotImplementedError):
+        S.DPMSolverMultistepScheduler(prediction_type="sample")
     for bad in (dict(solver_type="bh1"), dict(predict_x0=False), dict(disable_corrector=[0]), dict(use_flow_sigmas=True), dict(solver_order=3)):
         with pytest.raises(NotImplementedError):
             S.UniPCMultistepScheduler(**bad)
