@@ -208,8 +208,8 @@ class DDIM:
     """schedulers/scheduling_ddim.py: __init__ :193-245, set_timesteps :328-381, step :384-520 (eta = 0, epsilon, no clipping)"""
 
     def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", set_alpha_to_one=True,
-                 steps_offset=0, timestep_spacing="leading", clip_sample=False, prediction_type="epsilon"):
-        assert not clip_sample
+                 steps_offset=0, timestep_spacing="leading", clip_sample=False, prediction_type="epsilon", clip_sample_range=1.0):
+        self.clip = clip_sample_range if clip_sample else None  # :476-479 (pixel-space models; the reference's own test configuration)
         self.N, self.offset, self.spacing, self.prediction_type = num_train_timesteps, steps_offset, timestep_spacing, prediction_type
         self.alphas_cumprod = torch.cumprod(1.0 - _betas(beta_schedule, beta_start, beta_end, num_train_timesteps), dim=0)
         self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
@@ -240,6 +240,8 @@ class DDIM:
         else:
             x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
             eps = model_output
+        if self.clip is not None:
+            x0 = x0.clamp(-self.clip, self.clip)
         direction = (1 - a_prev) ** 0.5 * eps
         return a_prev ** 0.5 * x0 + direction
 
@@ -320,9 +322,10 @@ class DPMSolverPP2M:
     multistep_dpm_solver_second_order_update :925-1010 (midpoint), step :1196-1282"""
 
     def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2,
-                 timestep_spacing="linspace", steps_offset=0, lower_order_final=True, use_karras_sigmas=False, prediction_type="epsilon"):
+                 timestep_spacing="linspace", steps_offset=0, lower_order_final=True, use_karras_sigmas=False, prediction_type="epsilon",
+                 final_sigmas_type="zero", euler_at_final=False):
         self.N, self.offset, self.spacing, self.order, self.lof = num_train_timesteps, steps_offset, timestep_spacing, solver_order, lower_order_final
-        self.karras, self.prediction_type = use_karras_sigmas, prediction_type
+        self.karras, self.prediction_type, self.final, self.eaf = use_karras_sigmas, prediction_type, final_sigmas_type, euler_at_final
         self.alphas_cumprod = torch.cumprod(1.0 - _betas(beta_schedule, beta_start, beta_end, num_train_timesteps), dim=0)
         self.init_noise_sigma = 1.0
 
@@ -342,7 +345,8 @@ class DPMSolverPP2M:
             ts = ts.round()
         else:
             sig = np.interp(ts, np.arange(0, len(sig)), sig)
-        self.sigmas = torch.from_numpy(np.concatenate([sig, [0]]).astype(np.float32))
+        last = 0 if self.final == "zero" else ((1 - self.alphas_cumprod[0]) / self.alphas_cumprod[0]) ** 0.5  # :473-481
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [last]]).astype(np.float32))
         self.timesteps = torch.from_numpy(ts).to(torch.int64)
         self.outs, self.lower, self.i = [None] * self.order, 0, 0
 
@@ -356,7 +360,7 @@ class DPMSolverPP2M:
 
     def step(self, model_output, timestep, sample, generator=None):
         n, i = len(self.timesteps), self.i
-        final = i == n - 1  # final_sigmas_type == "zero"
+        final = (i == n - 1) and (self.eaf or (self.lof and n < 15) or self.final == "zero")  # :1235-1240
         a_c, s_c = self._as(self.sigmas[i])
         x0 = a_c * sample - s_c * model_output if self.prediction_type == "v_prediction" else (sample - s_c * model_output) / a_c  # :793-799
         self.outs = self.outs[1:] + [x0]
@@ -388,9 +392,9 @@ class UniPC:
     so the recorded reference trajectories are reproduced bit for bit."""
 
     def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2,
-                 timestep_spacing="linspace", steps_offset=0, prediction_type="epsilon"):
+                 timestep_spacing="linspace", steps_offset=0, prediction_type="epsilon", final_sigmas_type="zero", use_karras_sigmas=False):
         self.N, self.offset, self.spacing, self.order = num_train_timesteps, steps_offset, timestep_spacing, solver_order
-        self.prediction_type = prediction_type
+        self.prediction_type, self.final, self.karras = prediction_type, final_sigmas_type, use_karras_sigmas
         self.alphas_cumprod = torch.cumprod(1.0 - _betas(beta_schedule, beta_start, beta_end, num_train_timesteps), dim=0)
         self.init_noise_sigma = 1.0
 
@@ -402,8 +406,14 @@ class UniPC:
         else:
             ts = np.arange(self.N, 0, -self.N / n).round().copy().astype(np.int64) - 1
         sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
-        sig = np.interp(ts, np.arange(0, len(sig)), sig)
-        self.sigmas = torch.from_numpy(np.concatenate([sig, [0]]).astype(np.float32))
+        if self.karras:  # :374-391: the last sigma of the Karras table itself is "sigma_min"
+            sig, ts = karras_sigmas_and_timesteps(sig, n)
+            ts = ts.round().astype(np.int64)
+            last = 0 if self.final == "zero" else sig[-1]
+        else:
+            sig = np.interp(ts, np.arange(0, len(sig)), sig)
+            last = 0 if self.final == "zero" else ((1 - self.alphas_cumprod[0]) / self.alphas_cumprod[0]) ** 0.5  # :455-462
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [last]]).astype(np.float32))
         self.timesteps = torch.from_numpy(ts)
         self.outs, self.lower, self.i, self.last_sample, self.this_order = [None] * self.order, 0, 0, None, None
 

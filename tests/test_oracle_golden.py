@@ -152,6 +152,54 @@ def test_euler_full_loop_known_answer(golden):
     assert abs(float(sample.abs().mean()) - kmean) < 1e-3
 
 
+def _full_loop(s, scale_input=False, generator=None, init_sigma=False):
+    """tests/schedulers/test_scheduler_*.py `full_loop`: 10 steps of the deterministic dummy model on dummy_sample_deter."""
+    s.set_timesteps(10)
+    sample = _dummy_sample_deter() * (s.init_noise_sigma if init_sigma else 1.0)
+    for t in s.timesteps:
+        if scale_input:
+            sample = s.scale_model_input(sample, t)
+        sample = s.step(_dummy_model(sample, t), t, sample, **(dict(generator=generator) if generator is not None else {}))
+    return sample
+
+
+@pytest.mark.parametrize("kw,mean", [(dict(), 0.2464), (dict(use_karras_sigmas=True), 0.2925), (dict(prediction_type="v_prediction"), 0.1014),
+                                     (dict(prediction_type="v_prediction", use_karras_sigmas=True), 0.1966)])
+def test_unipc_known_answers(kw, mean):
+    """The reference's own hard-coded results: tests/schedulers/test_scheduler_unipc.py:143-233 (config :19-31: linear betas, order 2, bh2,
+    final_sigmas_type='sigma_min')."""
+    s = osched.UniPC(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2, final_sigmas_type="sigma_min", **kw)
+    assert abs(float(_full_loop(s).abs().mean()) - mean) < 1e-3
+
+
+@pytest.mark.parametrize("kw,mean", [(dict(), 0.3301), (dict(prediction_type="v_prediction"), 0.2251),
+                                     (dict(prediction_type="v_prediction", use_karras_sigmas=True), 0.2096)])
+def test_dpm_solver_multistep_known_answers(kw, mean):
+    """tests/schedulers/test_scheduler_dpm_multi.py:246-295 (config :20-37: dpmsolver++, midpoint, order 2, lower_order_final=False,
+    final_sigmas_type='sigma_min')."""
+    s = osched.DPMSolverPP2M(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", solver_order=2, lower_order_final=False,
+                             final_sigmas_type="sigma_min", **kw)
+    assert abs(float(_full_loop(s).abs().mean()) - mean) < 1e-3
+
+
+@pytest.mark.parametrize("kw,ksum,mean", [(dict(), 172.0067, 0.223967), (dict(prediction_type="v_prediction"), 52.5302, 0.0684),
+                                          (dict(set_alpha_to_one=True, beta_start=0.01), 149.8295, 0.1951),
+                                          (dict(set_alpha_to_one=False, beta_start=0.01), 149.0784, 0.1941)])
+def test_ddim_known_answers(kw, ksum, mean):
+    """tests/schedulers/test_scheduler_ddim.py:112-148 (config :12-22: linear betas, clip_sample=True; eta = 0)."""
+    cfg = dict(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", clip_sample=True)
+    cfg.update(kw)
+    out = _full_loop(osched.DDIM(**cfg))
+    assert abs(float(out.abs().sum()) - ksum) < 1e-2 and abs(float(out.abs().mean()) - mean) < 1e-3
+
+
+def test_euler_ancestral_known_answer():
+    """tests/schedulers/test_scheduler_euler_ancestral.py:44-70 (1100 training steps, linear betas; noise from torch.manual_seed(0)): 152.3192 / 0.1983"""
+    s = osched.EulerAncestral(num_train_timesteps=1100, beta_start=0.0001, beta_end=0.02, beta_schedule="linear")
+    out = _full_loop(s, scale_input=True, generator=torch.manual_seed(0), init_sigma=True)
+    assert abs(float(out.abs().sum()) - 152.3192) < 1e-2 and abs(float(out.abs().mean()) - 0.1983) < 1e-3
+
+
 def test_ddpm_known_answers(golden):
     """tests/schedulers/test_scheduler_ddpm.py:62-70 (variances), :72-104 (full loop 258.9606 / 0.3372)"""
     kat = golden("schedulers")["kat"]
