@@ -136,22 +136,42 @@ class PeerBuffer:
         lib = _lib.lib()
         ptr = C.c_void_p()
         handle = C.create_string_buffer(64)
-        _lib.check(lib.b200_peer_alloc(self.nbytes, C.byref(ptr), handle), "b200_peer_alloc")
+        # A failure on ONE rank (out of memory, no peer access) must not leave the others waiting in the next collective: every step
+        # is followed by an exchange of its outcome, and all ranks raise together.
+        err = None
+        try:
+            _lib.check(lib.b200_peer_alloc(self.nbytes, C.byref(ptr), handle), "b200_peer_alloc")
+        except B200Error as e:
+            err = str(e)
         self._own_ptr = ptr.value
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        dist.all_gather_object(handles, (bytes(handle.raw), err), group=group)
+        self._raise_together([e for _, e in handles], "allocate")
+        handles = [h for h, _ in handles]
         self._ptrs, self._opened = [], []
         for r in range(self.world):
             if r == self.rank:
                 self._ptrs.append(self._own_ptr)
                 continue
             p = C.c_void_p()
-            _lib.check(lib.b200_peer_open(handles[r], C.byref(p)), f"b200_peer_open (rank {r})")
+            try:
+                _lib.check(lib.b200_peer_open(handles[r], C.byref(p)), f"b200_peer_open (rank {r})")
+            except B200Error as e:
+                err = str(e)
+                break
             self._ptrs.append(p.value)
             self._opened.append(p.value)
+        outcomes = [None] * self.world
+        dist.all_gather_object(outcomes, err, group=group)
+        self._raise_together(outcomes, "map")
         self._holders = [_RawDeviceMemory(p, self.nbytes) for p in self._ptrs]
         self._tensors = [torch.as_tensor(h, device=torch.device("cuda", dev)) for h in self._holders]
         dist.barrier(group=group)  # every mapping exists before anyone writes through one
+
+    def _raise_together(self, errors, what):
+        bad = [(r, e) for r, e in enumerate(errors) if e]
+        if bad:
+            raise B200Error(f"context parallelism: could not {what} the peer buffers on rank(s) {[r for r, _ in bad]}: {bad[0][1]}")
 
     @property
     def local(self):

@@ -170,6 +170,33 @@ def _run_two(worker):
     return sorted(res)
 
 
+def _peer_failure_worker(rank, world, port, q_out):
+    """No GPU here, so b200_peer_alloc fails on every rank: the failure must surface as the SAME error on all ranks (after the outcome
+    exchange), not as one rank raising while the other waits in a collective."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torch.cuda
+        from diffusers_b200 import _lib
+        from diffusers_b200 import context_parallel as cp
+        torch.cuda.current_device = lambda: 0      # host-only stand-ins: the allocation itself is what must fail
+        _lib.init = lambda d: None
+        try:
+            cp.PeerBuffer(1 << 20)
+            q_out.put((rank, "no error"))
+        except cp.B200Error as e:
+            q_out.put((rank, "ok" if "could not allocate the peer buffers on rank(s) [0, 1]" in str(e) else repr(e)))
+    except Exception as e:  # noqa: BLE001
+        q_out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_buffer_failures_are_raised_on_every_rank():
+    assert _run_two(_peer_failure_worker) == [(0, "ok"), (1, "ok")]
+
+
 def test_enable_parallelism_host_side_two_rank_gloo():
     assert _run_two(_enable_worker) == [(0, "ok"), (1, "ok")]
 
